@@ -1,0 +1,187 @@
+/*
+ * mpmb.h — C-ABI of the B200-native MLS-MPM substep engine (libmpmb.so).
+ *
+ * This is the drop-in boundary for ONE hot path of yuanming-hu/taichi_mpm: the calls made by
+ * MPM<3>::substep() (reference src/mpm.cpp:452-575) between particle ordering and particle
+ * deletion.  Every entry point names the reference interface it replaces (path:line under the
+ * reference tree).  Plain C types only: opaque handle, pointers and sizes; no exceptions cross the
+ * boundary; every call returns 0 on success or a negative MpmbStatus, and the text of the last
+ * failure is available from mpmb_last_error().
+ *
+ * Ownership: the library owns all device memory; the caller owns every host buffer it passes and
+ * no host pointer is retained after a call returns.  Entry points are not re-entrant per handle;
+ * distinct handles are independent.  One handle drives one GPU (one process per GPU; multi-GPU
+ * z-slab runs exchange the buffers exposed by the mpmb_halo_* / mpmb_migrate_* calls with
+ * whatever transport the host owns — torch.distributed/NCCL in this repository).
+ *
+ * Numeric contract: fp32 state (reference `real = float`, README.md:316-317), 3x3 matrices stored
+ * column-major as 9 floats (m[c*3+r]; reference `M[i]` is column i, README.md:314), `b` is the
+ * reference's `apic_b` (src/particles.h:24-45): C = -4/dx * b in the 88-line notation.
+ */
+#ifndef MPMB_H_
+#define MPMB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPMB_VERSION 1
+#define MPMB_MAX_GROUPS 16  /* material groups per handle */
+#define MPMB_MAT_PARAMS 8
+
+typedef struct MpmbEngine *MpmbHandle;
+
+typedef enum MpmbStatus {
+  MPMB_OK = 0,
+  MPMB_ERR_INVALID = -1,   /* bad argument */
+  MPMB_ERR_CUDA = -2,      /* a CUDA call failed (sticky per handle) */
+  MPMB_ERR_CAPACITY = -3,  /* particle / tile / exchange-buffer capacity exceeded */
+  MPMB_ERR_STATE = -4      /* call not valid in the current state */
+} MpmbStatus;
+
+/* Material kinds = the registered particle type names of the reference
+ * (TC_REGISTER_MPM_PARTICLE, src/particles.cpp:845-856).  Parameter vectors (unused entries 0):
+ *   LINEAR  "linear" (src/particles.cpp:297-363): [0]=mu [1]=lambda
+ *   JELLY   "jelly"  (src/particles.cpp:365-438): [0]=mu [1]=lambda
+ *   SNOW    "snow"   (src/particles.cpp:165-295): [0]=mu_0 [1]=lambda_0 [2]=hardening [3]=theta_c
+ *                                                  [4]=theta_s [5]=min_Jp [6]=max_Jp ; scalar = Jp
+ *   WATER   "water"  (src/particles.cpp:440-499): [0]=k [1]=gamma ; scalar = j
+ *   SAND    "sand"   (src/particles.cpp:563-676): [0]=mu_0 [1]=lambda_0 [2]=alpha [3]=cohesion
+ *                                                  [4]=beta ; scalar = logJp                      */
+typedef enum MpmbMaterial {
+  MPMB_MAT_LINEAR = 0,
+  MPMB_MAT_JELLY = 1,
+  MPMB_MAT_SNOW = 2,
+  MPMB_MAT_WATER = 3,
+  MPMB_MAT_SAND = 4
+} MpmbMaterial;
+
+/* Mirrors the keys MPM<dim>::initialize reads from its Config (src/mpm.cpp:27-75). */
+typedef struct MpmbConfig {
+  int32_t res[3];            /* cells per axis (`res`); nodes = res+1 (src/mpm.cpp:66)            */
+  float dx;                  /* `delta_x`                                                         */
+  float dt;                  /* `base_delta_t` (already multiplied by dt_multiplier)              */
+  float gravity[3];          /* `gravity` (src/mpm.cpp:38)                                        */
+  int32_t particle_gravity;  /* src/mpm.cpp:47 (default 1): kick particles in P2G, not the grid   */
+  int32_t clean_boundary;    /* src/mpm.cpp:563 (default 1): delete particles in the 7-cell band  */
+  int32_t device;            /* CUDA device ordinal                                               */
+  int64_t capacity;          /* max resident particles; 0 = sized at the first upload             */
+  /* z-slab decomposition.  world==1: whole domain.  A rank owns the particles whose
+   * base node lies in tile layers [tile_z0, tile_z1) (tiles are 4x4x4 nodes).                    */
+  int32_t rank, world;
+  int32_t tile_z0, tile_z1;
+  int64_t migrate_capacity;  /* max particles leaving through one face per substep (world>1)      */
+  int32_t reserved[8];       /* must be 0                                                         */
+} MpmbConfig;
+
+/* Byte offsets of the fields of one reference particle slot (ParticleContainer<3>, 320 B,
+ * src/mpm_fwd.h:59-67; fields src/particles.h:24-45).  Obtained with offsetof() on the reference
+ * side; never hard-coded here.  Offset < 0 = field absent.                       */
+typedef struct MpmbAosLayout {
+  int32_t stride;      /* bytes per slot (320)                                       */
+  int32_t off_pos;     /* float[3]   `pos`                                           */
+  int32_t off_v_and_m; /* float[4]   `v_and_m` = (vx,vy,vz,mass)                     */
+  int32_t off_dg_e;    /* 3 x float[4] padded columns of `dg_e` (column pitch below) */
+  int32_t off_apic_b;  /* 3 x float[4] padded columns of `apic_b`                    */
+  int32_t col_pitch;   /* bytes between matrix columns (16)                          */
+  int32_t off_vol;     /* float      `vol`                                           */
+  int32_t off_scalar;  /* float      Jp / j / logJp of the subclass, or -1           */
+  int32_t reserved[4];
+} MpmbAosLayout;
+
+/* ------------------------------------------------------------------------------ lifetime */
+/* Replaces MPM<3>::initialize (src/mpm.cpp:27-75): sizes the tile grid, allocates device state. */
+int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out);
+int mpmb_destroy(MpmbHandle h);
+/* Text of the last error on this handle ("" if none).  h may be NULL for create-time errors.    */
+const char *mpmb_last_error(MpmbHandle h);
+int mpmb_version(void);
+/* All work is enqueued on `cuda_stream` (a cudaStream_t cast to void*; NULL = default stream).   */
+int mpmb_set_stream(MpmbHandle h, void *cuda_stream);
+int mpmb_synchronize(MpmbHandle h);
+
+/* ------------------------------------------------------------------------------ scene     */
+/* Replaces Particle::initialize(config) of the registered type (e.g. SandParticle::initialize,
+ * src/particles.cpp:587-597) for every particle of `group`.                                      */
+int mpmb_set_material(MpmbHandle h, int32_t group, int32_t kind, const float *params, int32_t n_params);
+/* Replaces Simulation::set_levelset + DynamicLevelSet::sample/get_spatial_gradient as used by
+ * apply_grid_boundary_conditions (src/mpm.cpp:296-372) for a static level set.  `sdf4` is a host
+ * array [res0+1][res1+1][res2+1][4] = (n_x,n_y,n_z,phi), phi in grid units at the node, n the
+ * unit spatial gradient.  NULL removes the boundary.  `friction` = levelset0->friction
+ * (-1 sticky, <=-2 slip, >=0 separate with Coulomb friction; src/mpm_fwd.h:25-57).               */
+int mpmb_set_sdf(MpmbHandle h, const float *sdf4, float friction);
+/* Same boundary built on the device from half-spaces phi_i(X) = n_i . X + d_i (grid units, n unit):
+ * phi = min_i phi_i, n = n of the minimiser (levelset.add_plane in scripts/mls-cpic/sand_sweep.py:13-19). */
+int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float friction);
+
+/* ------------------------------------------------------------------------------ particles */
+/* Replaces MPM<3>::add_particles' writes into the particle pool (src/mpm.cpp:93-148) for n
+ * particles given field-wise: x[n][3], v[n][3], F[n][9], b[n][9] (apic_b), mass[n], vol[n],
+ * scalar[n] (Jp/j/logJp), group[n].  F, b, scalar, group may be NULL (identity, 0, material
+ * default, group 0).  Replaces the resident set.  Particle k gets id k.                           */
+int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *v, const float *F, const float *b,
+                          const float *mass, const float *vol, const float *scalar, const int32_t *group);
+/* Same, reading the reference's own AoS pool: slot indices[k] of `pool` (ParticleAllocator::pool,
+ * src/particle_allocator.h:39; MPM::particles index vector, src/mpm.h:116).  group[k] may be NULL. */
+int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slots, const uint32_t *indices,
+                    const MpmbAosLayout *layout, const int32_t *group);
+/* Number of live particles (device value; synchronises).  Reference: particles.size().           */
+int mpmb_num_particles(MpmbHandle h, int64_t *n);
+/* Copies the live particles out, any pointer may be NULL.  Row k of every array belongs to the
+ * particle whose id (upload index) is id[k]; rows are in the engine's storage order.  `cap` rows
+ * are available in each array; *n_out receives the number written.                                */
+int mpmb_download_particles(MpmbHandle h, int64_t cap, int64_t *n_out, uint32_t *id, float *x, float *v, float *F,
+                            float *b, float *mass, float *vol, float *scalar, int32_t *group);
+/* Writes the live particles back into the reference's AoS pool (slot = indices[id]); returns the
+ * number of survivors and compacts `indices` to the survivors, which is what
+ * clear_boundary_particles (src/mpm.cpp:583-633) leaves in MPM::particles.                         */
+int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *indices, int64_t n_indices,
+                      const MpmbAosLayout *layout, int64_t *n_alive);
+
+/* ------------------------------------------------------------------------------ hot path  */
+/* The whole of MPM<3>::substep() on the fast path, `nsub` times (src/mpm.cpp:452-575):
+ * sort_particles_and_populate_grid (464-465) -> rasterize_optimized (510-512) ->
+ * normalize_grid_and_apply_external_force (526-533) -> apply_grid_boundary_conditions (539-540) ->
+ * resample_optimized (548-549) -> clear_boundary_particles (563-565).  Asynchronous.              */
+int mpmb_substep(MpmbHandle h, int32_t nsub);
+/* The same stages one at a time (for parity tests and for a host that interleaves its own work,
+ * e.g. rigid bodies).  Must be called in this order; mpmb_substep == these three.                  */
+int mpmb_sort_particles_and_populate_grid(MpmbHandle h); /* src/mpm.cpp:770-918                   */
+int mpmb_rasterize(MpmbHandle h);                        /* src/transfer.cpp:361-581 (P2G)        */
+int mpmb_resample(MpmbHandle h);                         /* src/mpm.cpp:277-372 + src/transfer.cpp:702-970 + src/mpm.cpp:583-633 */
+
+/* Parity/debug: dense node grid [res0+1][res1+1][res2+1][4] on the host.
+ * which=0: (p_x,p_y,p_z,m) after P2G; which=1: (v_x,v_y,v_z,m) after normalise + boundary.
+ * Valid between mpmb_rasterize and the next mpmb_sort_particles_and_populate_grid.                 */
+int mpmb_download_grid(MpmbHandle h, int32_t which, float *dense4);
+
+/* ------------------------------------------------------------------------------ profiling */
+#define MPMB_N_STAGES 4 /* 0 sort+tiles, 1 P2G, 2 G2P(+grid update), 3 exchange pack/unpack */
+/* When enabled, CUDA events bracket every stage on the engine's stream.                          */
+int mpmb_set_profiling(MpmbHandle h, int32_t enabled);
+/* Accumulated milliseconds and launch counts per stage since the last reset (synchronises).      */
+int mpmb_get_profile(MpmbHandle h, double ms[MPMB_N_STAGES], int64_t launches[MPMB_N_STAGES], int32_t reset);
+/* Device counters: active tiles of the last substep, live particles, kernels launched so far.    */
+int mpmb_get_counters(MpmbHandle h, int64_t *active_tiles, int64_t *alive, int64_t *kernel_launches);
+
+/* ------------------------------------------------------------------------------ multi-GPU */
+/* z-slab runs (world>1).  The host moves the bytes; the engine packs and unpacks on the device.
+ * Halo: after mpmb_rasterize, face 0 (-z) / 1 (+z) tile-layer partial sums of (p,m) are packed
+ * into a device buffer of mpmb_halo_bytes() bytes; the neighbour unpacks them as ghost tiles
+ * before mpmb_resample.  Migration: after mpmb_resample, particles that left the slab through a
+ * face are packed (mpmb_migrate_bytes() bytes per face) and appended by the neighbour before its
+ * next sort.  All pointers are DEVICE pointers owned by the caller.                               */
+int64_t mpmb_halo_bytes(MpmbHandle h);
+int mpmb_halo_pack(MpmbHandle h, int32_t face, void *dev_buf);
+int mpmb_halo_unpack(MpmbHandle h, int32_t face, const void *dev_buf);
+int64_t mpmb_migrate_bytes(MpmbHandle h);
+int mpmb_migrate_pack(MpmbHandle h, int32_t face, void *dev_buf);
+int mpmb_migrate_unpack(MpmbHandle h, int32_t face, const void *dev_buf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPMB_H_ */

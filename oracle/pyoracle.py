@@ -1,0 +1,207 @@
+"""ctypes front-end of the CPU oracle (oracle/mpm_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND = range(5)
+N_MAT_PARAMS = 8
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "mpm_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.oracle_fast_create.restype = C.c_void_p
+        _LIB.oracle_fast_substeps.restype = C.c_int64
+        _LIB.oracle_fast_num_threads.restype = C.c_int
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _suf(dtype):
+    return "f32" if np.dtype(dtype) == np.float32 else "f64"
+
+
+def _scalar(dtype):
+    return C.c_float if np.dtype(dtype) == np.float32 else C.c_double
+
+
+def quadratic_kernel(x, dtype=np.float32):
+    w = np.zeros(3, dtype)
+    dw = np.zeros(3, dtype)
+    getattr(lib(), "oracle_quadratic_kernel_" + _suf(dtype))(_scalar(dtype)(x), _p(w), _p(dw))
+    return w, dw
+
+
+def cubic_kernel(x, dtype=np.float32):
+    w = np.zeros(4, dtype)
+    dw = np.zeros(4, dtype)
+    getattr(lib(), "oracle_cubic_kernel_" + _suf(dtype))(_scalar(dtype)(x), _p(w), _p(dw))
+    return w, dw
+
+
+def mls_fast_kernel(rel, dtype=np.float32):
+    rel = np.ascontiguousarray(rel, dtype)
+    w = np.zeros(27, dtype)
+    getattr(lib(), "oracle_mls_fast_kernel_" + _suf(dtype))(_p(rel), _p(w))
+    return w.reshape(3, 3, 3)
+
+
+def svd3(A, dtype=np.float64):
+    """A: 3x3 numpy (row/col as math). Returns U, s, V with A = U diag(s) V^T."""
+    a = np.ascontiguousarray(np.asarray(A, dtype).T)  # column-major storage
+    U = np.zeros((3, 3), dtype)
+    s = np.zeros(3, dtype)
+    V = np.zeros((3, 3), dtype)
+    getattr(lib(), "oracle_svd3_" + _suf(dtype))(_p(a), _p(U), _p(s), _p(V))
+    return U.T.copy(), s, V.T.copy()
+
+
+def polar3(A, dtype=np.float64):
+    a = np.ascontiguousarray(np.asarray(A, dtype).T)
+    R = np.zeros((3, 3), dtype)
+    S = np.zeros((3, 3), dtype)
+    getattr(lib(), "oracle_polar3_" + _suf(dtype))(_p(a), _p(R), _p(S))
+    return R.T.copy(), S.T.copy()
+
+
+def calculate_force(kind, params, F, ps, vol, dtype=np.float64):
+    """F: 3x3 math layout. Returns -vol*P*F^T (3x3 math layout)."""
+    prm = np.zeros(N_MAT_PARAMS, dtype)
+    prm[: len(params)] = params
+    f = np.ascontiguousarray(np.asarray(F, dtype).T)
+    out = np.zeros((3, 3), dtype)
+    sc = _scalar(dtype)
+    getattr(lib(), "oracle_calculate_force_" + _suf(dtype))(C.c_int(kind), _p(prm), _p(f), sc(ps), sc(vol), _p(out))
+    return out.T.copy()
+
+
+def plasticity(kind, params, cdg, F, ps, dtype=np.float64):
+    prm = np.zeros(N_MAT_PARAMS, dtype)
+    prm[: len(params)] = params
+    c = np.ascontiguousarray(np.asarray(cdg, dtype).T)
+    f = np.ascontiguousarray(np.asarray(F, dtype).T)
+    p = np.array([ps], dtype)
+    getattr(lib(), "oracle_plasticity_" + _suf(dtype))(C.c_int(kind), _p(prm), _p(c), _p(f), _p(p))
+    return f.T.copy(), p[0]
+
+
+def friction_project(vel, base, n, friction, dtype=np.float64):
+    vel = np.ascontiguousarray(vel, dtype)
+    base = np.ascontiguousarray(base, dtype)
+    n = np.ascontiguousarray(n, dtype)
+    out = np.zeros(3, dtype)
+    getattr(lib(), "oracle_friction_project_" + _suf(dtype))(_p(vel), _p(base), _p(n), _scalar(dtype)(friction), _p(out))
+    return out
+
+
+def substep(scene, state, dtype=np.float64, want_grids=True):
+    """One reference substep on a dense grid.
+
+    scene: dict(res, dx, dt, gravity, particle_gravity, mat_kind[int32 G], mat_params[G,8],
+                sdf (nx,ny,nz,4) or None, friction)
+    state: dict(x[N,3], v[N,3], F[N,9] col-major, b[N,9] col-major, mass[N], vol[N], ps[N],
+                group[N] int32, alive[N] uint8)  -- converted to `dtype`, returned as new dict.
+    Returns (new_state, grid_rast, grid_vel); grids are (nx,ny,nz,4).
+    """
+    res = np.asarray(scene["res"], np.int32)
+    st = {k: np.ascontiguousarray(np.asarray(state[k], dtype)) for k in ("x", "v", "F", "b", "mass", "vol", "ps")}
+    st = {k: a.copy() for k, a in st.items()}
+    st["group"] = np.ascontiguousarray(state["group"], np.int32)
+    st["alive"] = np.ascontiguousarray(state.get("alive", np.ones(len(st["mass"]), np.uint8)), np.uint8).copy()
+    n = len(st["mass"])
+    mk = np.ascontiguousarray(scene["mat_kind"], np.int32)
+    mp = np.ascontiguousarray(scene["mat_params"], dtype)
+    sdf = scene.get("sdf")
+    sdf = None if sdf is None else np.ascontiguousarray(sdf, dtype)
+    g = np.ascontiguousarray(scene["gravity"], dtype)
+    nn = tuple(int(r) + 1 for r in res)
+    grid_rast = np.zeros(nn + (4,), dtype) if want_grids else None
+    grid_vel = np.zeros(nn + (4,), dtype) if want_grids else None
+    sc = _scalar(dtype)
+    getattr(lib(), "oracle_substep_" + _suf(dtype))(
+        _p(res), sc(scene["dx"]), sc(scene["dt"]), _p(g), C.c_int(int(scene.get("particle_gravity", 1))), C.c_int(len(mk)),
+        _p(mk), _p(mp), _p(sdf), sc(scene.get("friction", 0.0)), C.c_int64(n),
+        _p(st["x"]), _p(st["v"]), _p(st["F"]), _p(st["b"]), _p(st["mass"]), _p(st["vol"]), _p(st["ps"]), _p(st["group"]),
+        _p(st["alive"]), _p(grid_rast), _p(grid_vel))
+    return st, grid_rast, grid_vel
+
+
+class FastOracle:
+    """fp32 OpenMP restatement of the reference's optimized CPU path (the timed CPU baseline)."""
+
+    def __init__(self, scene, state, threads=None):
+        self.scene = scene
+        self.res = np.asarray(scene["res"], np.int32)
+        self.h = C.c_void_p(lib().oracle_fast_create(_p(self.res)))
+        if threads:
+            lib().oracle_fast_set_threads(C.c_int(threads))
+        self.threads = lib().oracle_fast_num_threads()
+        f32 = np.float32
+        self.st = {k: np.ascontiguousarray(np.asarray(state[k], f32)).copy() for k in ("x", "v", "F", "b", "mass", "vol", "ps")}
+        self.st["group"] = np.ascontiguousarray(state["group"], np.int32)
+        self.st["alive"] = np.ascontiguousarray(state.get("alive", np.ones(len(self.st["mass"]), np.uint8)), np.uint8).copy()
+        self.mk = np.ascontiguousarray(scene["mat_kind"], np.int32)
+        self.mp = np.ascontiguousarray(scene["mat_params"], f32)
+        sdf = scene.get("sdf")
+        self.sdf = None if sdf is None else np.ascontiguousarray(sdf, f32)
+        self.g = np.ascontiguousarray(scene["gravity"], f32)
+
+    def substeps(self, nsub):
+        """Returns (particle_updates, timings[sort,p2g,grid,g2p] seconds)."""
+        t = np.zeros(4, np.float64)
+        st = self.st
+        sc = self.scene
+        upd = lib().oracle_fast_substeps(
+            self.h, C.c_int(nsub), _p(self.res), C.c_float(sc["dx"]), C.c_float(sc["dt"]), _p(self.g),
+            C.c_int(int(sc.get("particle_gravity", 1))), _p(self.mk), _p(self.mp), _p(self.sdf), C.c_float(sc.get("friction", 0.0)),
+            C.c_int64(len(st["mass"])), _p(st["x"]), _p(st["v"]), _p(st["F"]), _p(st["b"]), _p(st["mass"]), _p(st["vol"]),
+            _p(st["ps"]), _p(st["group"]), _p(st["alive"]), _p(t))
+        return int(upd), t
+
+    def download_grid(self):
+        nn = tuple(int(r) + 1 for r in self.res)
+        g = np.zeros(nn + (4,), np.float32)
+        lib().oracle_fast_download_grid(self.h, _p(g))
+        return g
+
+    def __del__(self):
+        try:
+            lib().oracle_fast_destroy(self.h)
+        except Exception:
+            pass
+
+
+def mpm88_advance(n, dt, x, v, F, C_, Jp, E=1e4, nu=0.2, hardening=10.0, gravity_y=-200.0, plastic=False, dtype=np.float64):
+    """One step of the 88-line 2D algorithm (mls-mpm88.cpp:16-69). Arrays are modified copies."""
+    x = np.ascontiguousarray(x, dtype).copy()
+    v = np.ascontiguousarray(v, dtype).copy()
+    F = np.ascontiguousarray(F, dtype).copy()
+    C_ = np.ascontiguousarray(C_, dtype).copy()
+    Jp = np.ascontiguousarray(Jp, dtype).copy()
+    grid = np.zeros((n + 1, n + 1, 3), dtype)
+    sc = _scalar(dtype)
+    getattr(lib(), "oracle_mpm88_advance_" + _suf(dtype))(
+        C.c_int(n), sc(dt), sc(E), sc(nu), sc(hardening), sc(gravity_y), C.c_int(int(plastic)), C.c_int64(len(Jp)),
+        _p(x), _p(v), _p(F), _p(C_), _p(Jp), _p(grid))
+    return x, v, F, C_, Jp, grid

@@ -1,0 +1,255 @@
+"""ctypes binding of the C-ABI in include/mpmb.h (libmpmb.so).
+
+This is the only way Python reaches the engine: plain pointers and sizes, no torch types.
+The library must exist (build.py builds it in-tree); there is NO CPU fallback — if the CUDA
+library cannot be loaded, import of this module's `lib()` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MPMB_MAX_GROUPS = 16
+MPMB_MAT_PARAMS = 8
+MPMB_N_STAGES = 4
+MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND = range(5)
+MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, "water": MAT_WATER, "sand": MAT_SAND}
+
+# every symbol include/mpmb.h declares
+EXPORTS = [
+    "mpmb_create", "mpmb_destroy", "mpmb_last_error", "mpmb_version", "mpmb_set_stream", "mpmb_synchronize",
+    "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes",
+    "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_num_particles", "mpmb_download_particles", "mpmb_download_aos",
+    "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_download_grid",
+    "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters",
+    "mpmb_halo_bytes", "mpmb_halo_pack", "mpmb_halo_unpack", "mpmb_migrate_bytes", "mpmb_migrate_pack", "mpmb_migrate_unpack",
+]
+
+
+class MpmbConfig(C.Structure):
+    _fields_ = [
+        ("res", C.c_int32 * 3),
+        ("dx", C.c_float),
+        ("dt", C.c_float),
+        ("gravity", C.c_float * 3),
+        ("particle_gravity", C.c_int32),
+        ("clean_boundary", C.c_int32),
+        ("device", C.c_int32),
+        ("capacity", C.c_int64),
+        ("rank", C.c_int32),
+        ("world", C.c_int32),
+        ("tile_z0", C.c_int32),
+        ("tile_z1", C.c_int32),
+        ("migrate_capacity", C.c_int64),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+class MpmbAosLayout(C.Structure):
+    _fields_ = [
+        ("stride", C.c_int32), ("off_pos", C.c_int32), ("off_v_and_m", C.c_int32), ("off_dg_e", C.c_int32),
+        ("off_apic_b", C.c_int32), ("col_pitch", C.c_int32), ("off_vol", C.c_int32), ("off_scalar", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+_LIB = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def lib():
+    """Loads libmpmb.so (building it in-tree if the source is newer).  Raises if unavailable."""
+    global _LIB
+    if _LIB is None:
+        path = _build.build()
+        if not os.path.exists(path):
+            raise RuntimeError("libmpmb.so is missing: the CUDA engine has not been built (python -m taichi_mpm_b200.build)")
+        L = C.CDLL(path)
+        L.mpmb_last_error.restype = C.c_char_p
+        L.mpmb_last_error.argtypes = [C.c_void_p]
+        L.mpmb_halo_bytes.restype = C.c_int64
+        L.mpmb_migrate_bytes.restype = C.c_int64
+        L.mpmb_create.argtypes = [C.POINTER(MpmbConfig), C.POINTER(C.c_void_p)]
+        for name in EXPORTS:
+            getattr(L, name)  # AttributeError if a declared symbol is not exported
+        _LIB = L
+    return _LIB
+
+
+class MpmbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mpmb error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Engine:
+    """Thin object wrapper over one MpmbHandle."""
+
+    def __init__(self, res, dx, dt, gravity=(0.0, -10.0, 0.0), particle_gravity=True, clean_boundary=True, device=0,
+                 capacity=0, rank=0, world=1, tile_z0=0, tile_z1=0, migrate_capacity=0):
+        self.L = lib()
+        cfg = MpmbConfig()
+        if np.isscalar(res):
+            res = (res, res, res)
+        cfg.res[:] = [int(r) for r in res]
+        cfg.dx, cfg.dt = float(dx), float(dt)
+        cfg.gravity[:] = [float(g) for g in gravity]
+        cfg.particle_gravity = int(bool(particle_gravity))
+        cfg.clean_boundary = int(bool(clean_boundary))
+        cfg.device = int(device)
+        cfg.capacity = int(capacity)
+        cfg.rank, cfg.world, cfg.tile_z0, cfg.tile_z1 = int(rank), int(world), int(tile_z0), int(tile_z1)
+        cfg.migrate_capacity = int(migrate_capacity)
+        self.res = tuple(int(r) for r in res)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.L.mpmb_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise MpmbError(rc, self.L.mpmb_last_error(None).decode())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MpmbError(rc, self.L.mpmb_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.L.mpmb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- scene
+    def set_stream(self, cuda_stream):
+        self._check(self.L.mpmb_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def synchronize(self):
+        self._check(self.L.mpmb_synchronize(self.h))
+
+    def set_material(self, group, kind, params):
+        p = np.zeros(MPMB_MAT_PARAMS, np.float32)
+        p[: len(params)] = params
+        self._check(self.L.mpmb_set_material(self.h, C.c_int32(group), C.c_int32(kind), _ptr(p), C.c_int32(len(params))))
+
+    def set_sdf(self, sdf4, friction):
+        if sdf4 is not None:
+            sdf4 = _f32(sdf4)
+            assert sdf4.shape == tuple(r + 1 for r in self.res) + (4,)
+        self._check(self.L.mpmb_set_sdf(self.h, _ptr(sdf4), C.c_float(friction)))
+
+    def set_planes(self, planes4, friction):
+        planes4 = _f32(planes4).reshape(-1, 4)
+        self._check(self.L.mpmb_set_planes(self.h, C.c_int32(len(planes4)), _ptr(planes4), C.c_float(friction)))
+
+    # --- particles
+    def upload(self, x, v, mass, vol, F=None, b=None, scalar=None, group=None):
+        x = _f32(x).reshape(-1, 3)
+        n = len(x)
+        v, F, b = _f32(v, (n, 3)), _f32(F, (n, 9)), _f32(b, (n, 9))
+        mass, vol, scalar = _f32(mass, (n,)), _f32(vol, (n,)), _f32(scalar, (n,))
+        group = None if group is None else np.ascontiguousarray(group, np.int32).reshape(n)
+        self._check(self.L.mpmb_upload_particles(self.h, C.c_int64(n), _ptr(x), _ptr(v), _ptr(F), _ptr(b), _ptr(mass), _ptr(vol),
+                                                 _ptr(scalar), _ptr(group)))
+
+    def upload_ptrs(self, n, x, v, F, b, mass, vol, scalar, group):
+        """Raw-pointer variant (ints), e.g. pinned host buffers owned by the caller."""
+        vp = lambda p: C.c_void_p(p) if p else None
+        self._check(self.L.mpmb_upload_particles(self.h, C.c_int64(n), vp(x), vp(v), vp(F), vp(b), vp(mass), vp(vol), vp(scalar), vp(group)))
+
+    def download_ptrs(self, cap, id_, x, v, F, b, mass, vol, scalar, group):
+        vp = lambda p: C.c_void_p(p) if p else None
+        n = C.c_int64(0)
+        self._check(self.L.mpmb_download_particles(self.h, C.c_int64(cap), C.byref(n), vp(id_), vp(x), vp(v), vp(F), vp(b), vp(mass),
+                                                   vp(vol), vp(scalar), vp(group)))
+        return n.value
+
+    def upload_aos(self, pool, indices, layout, group=None):
+        pool = np.ascontiguousarray(pool, np.uint8)
+        indices = np.ascontiguousarray(indices, np.uint32)
+        slots = pool.size // layout.stride
+        group = None if group is None else np.ascontiguousarray(group, np.int32)
+        self._check(self.L.mpmb_upload_aos(self.h, C.c_int64(len(indices)), _ptr(pool), C.c_int64(slots), _ptr(indices), C.byref(layout),
+                                           _ptr(group)))
+
+    def download_aos(self, pool, indices, layout):
+        assert pool.dtype == np.uint8 and pool.flags.c_contiguous and indices.dtype == np.uint32
+        n = C.c_int64(0)
+        self._check(self.L.mpmb_download_aos(self.h, _ptr(pool), C.c_int64(pool.size // layout.stride), _ptr(indices), C.c_int64(len(indices)),
+                                             C.byref(layout), C.byref(n)))
+        return n.value
+
+    def num_particles(self):
+        n = C.c_int64(0)
+        self._check(self.L.mpmb_num_particles(self.h, C.byref(n)))
+        return n.value
+
+    def download(self, cap=None, sort_by_id=True):
+        """Returns dict(id,x,v,F,b,mass,vol,ps,group) of the live particles."""
+        if cap is None:
+            cap = max(self.num_particles(), 1)
+        out = dict(id=np.zeros(cap, np.uint32), x=np.zeros((cap, 3), np.float32), v=np.zeros((cap, 3), np.float32),
+                   F=np.zeros((cap, 9), np.float32), b=np.zeros((cap, 9), np.float32), mass=np.zeros(cap, np.float32),
+                   vol=np.zeros(cap, np.float32), ps=np.zeros(cap, np.float32), group=np.zeros(cap, np.int32))
+        n = C.c_int64(0)
+        self._check(self.L.mpmb_download_particles(self.h, C.c_int64(cap), C.byref(n), _ptr(out["id"]), _ptr(out["x"]), _ptr(out["v"]),
+                                                   _ptr(out["F"]), _ptr(out["b"]), _ptr(out["mass"]), _ptr(out["vol"]), _ptr(out["ps"]),
+                                                   _ptr(out["group"])))
+        out = {k: a[: n.value] for k, a in out.items()}
+        if sort_by_id:
+            o = np.argsort(out["id"], kind="stable")
+            out = {k: a[o] for k, a in out.items()}
+        return out
+
+    # --- hot path
+    def substep(self, nsub=1):
+        self._check(self.L.mpmb_substep(self.h, C.c_int32(nsub)))
+
+    def sort_particles_and_populate_grid(self):
+        self._check(self.L.mpmb_sort_particles_and_populate_grid(self.h))
+
+    def rasterize(self):
+        self._check(self.L.mpmb_rasterize(self.h))
+
+    def resample(self):
+        self._check(self.L.mpmb_resample(self.h))
+
+    def download_grid(self, which):
+        g = np.zeros(tuple(r + 1 for r in self.res) + (4,), np.float32)
+        self._check(self.L.mpmb_download_grid(self.h, C.c_int32(which), _ptr(g)))
+        return g
+
+    # --- profiling
+    def set_profiling(self, enabled):
+        self._check(self.L.mpmb_set_profiling(self.h, C.c_int32(int(enabled))))
+
+    def get_profile(self, reset=True):
+        ms = (C.c_double * MPMB_N_STAGES)()
+        ln = (C.c_int64 * MPMB_N_STAGES)()
+        self._check(self.L.mpmb_get_profile(self.h, ms, ln, C.c_int32(int(reset))))
+        return list(ms), list(ln)
+
+    def get_counters(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self.L.mpmb_get_counters(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(active_tiles=a.value, alive=b.value, kernel_launches=c.value)

@@ -1,0 +1,325 @@
+// Device math for the MLS-MPM substep kernels (sm_100a).
+//
+// All isotropic constitutive updates of the reference (src/particles.cpp) are evaluated from ONE
+// decomposition: the eigen-system of the small-strain-exact tensor E = F F^T - I, built from
+// G = F - I as E = G + G^T + G G^T so that the small quantity is formed without cancellation.
+// With F = U S V^T:  E = U (S^2 - I) U^T, hence
+//   * every Kirchhoff stress  P F^T = U diag(tau_i(sigma)) U^T          (calculate_force)
+//   * every return map        U S' V^T = U diag(sigma'_i/sigma_i) U^T F (plasticity)
+// needs U and e_i = sigma_i^2 - 1 only — no V, no second factorisation, and ln(sigma) =
+// 0.5*log1p(e) keeps full relative precision at the 1e-4 strains sand lives at.
+// The reference calls svd()/polar_decomp() of the (un-vendored) taichi core at
+// src/particles.cpp:212,227,394,630,642; results here are compared against the fp64 oracle
+// through convention-invariant quantities only.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace mpmb {
+
+enum { MAT_LINEAR = 0, MAT_JELLY = 1, MAT_SNOW = 2, MAT_WATER = 3, MAT_SAND = 4 };
+
+struct Mat3 {  // column-major: m[c*3+r]
+  float m[9];
+  __device__ __forceinline__ float &operator()(int r, int c) { return m[c * 3 + r]; }
+  __device__ __forceinline__ float operator()(int r, int c) const { return m[c * 3 + r]; }
+};
+
+struct Sym3 {  // symmetric 3x3
+  float xx, yy, zz, xy, xz, yz;
+};
+
+// One cyclic Jacobi rotation annihilating a_pq; (app,aqq,apq) the 2x2 pivot, (arp,arq) the
+// remaining off-diagonals, v*p/v*q the eigenvector columns p and q.
+__device__ __forceinline__ void jacobi_rotate(float &app, float &aqq, float &apq, float &arp, float &arq, float &v0p,
+                                              float &v1p, float &v2p, float &v0q, float &v1q, float &v2q) {
+  // tan of the rotation angle, smaller root: t = sgn(th)/(|th|+sqrt(th^2+1)), th=(aqq-app)/(2apq)
+  float d = aqq - app;
+  float two_apq = 2.0f * apq;
+  // t = 2apq / (d + sgn(d) sqrt(d^2 + 4apq^2)) avoids the division by apq (safe for apq == 0).
+  float h = sqrtf(fmaf(d, d, two_apq * two_apq));
+  float den = d + copysignf(h, d);
+  float t = (den != 0.0f) ? __fdividef(two_apq, den) : 0.0f;
+  float c = rsqrtf(fmaf(t, t, 1.0f));
+  float s = t * c;
+  app = fmaf(-t, apq, app);
+  aqq = fmaf(t, apq, aqq);
+  apq = 0.0f;
+  float n_rp = fmaf(c, arp, -s * arq);
+  float n_rq = fmaf(s, arp, c * arq);
+  arp = n_rp;
+  arq = n_rq;
+  float t0 = fmaf(c, v0p, -s * v0q), t1 = fmaf(c, v1p, -s * v1q), t2 = fmaf(c, v2p, -s * v2q);
+  v0q = fmaf(s, v0p, c * v0q);
+  v1q = fmaf(s, v1p, c * v1q);
+  v2q = fmaf(s, v2p, c * v2q);
+  v0p = t0;
+  v1p = t1;
+  v2p = t2;
+}
+
+// Eigen-decomposition A = U diag(e) U^T by cyclic Jacobi, fixed sweep count (quadratic
+// convergence; SWEEPS=4 reaches fp32 round-off for any symmetric 3x3, see tests).
+template <int SWEEPS>
+__device__ __forceinline__ void eig_sym3(Sym3 A, Mat3 &U, float e[3]) {
+  float u00 = 1.f, u10 = 0.f, u20 = 0.f, u01 = 0.f, u11 = 1.f, u21 = 0.f, u02 = 0.f, u12 = 0.f, u22 = 1.f;
+#pragma unroll
+  for (int s = 0; s < SWEEPS; s++) {
+    // (p,q,r) = (0,1,2): pivot xy, others xz (r=2 with p=0), yz (r=2 with q=1)
+    jacobi_rotate(A.xx, A.yy, A.xy, A.xz, A.yz, u00, u10, u20, u01, u11, u21);
+    // (0,2,1): pivot xz, others xy (r=1 with p=0), yz (r=1 with q=2)
+    jacobi_rotate(A.xx, A.zz, A.xz, A.xy, A.yz, u00, u10, u20, u02, u12, u22);
+    // (1,2,0): pivot yz, others xy (r=0 with p=1), xz (r=0 with q=2)
+    jacobi_rotate(A.yy, A.zz, A.yz, A.xy, A.xz, u01, u11, u21, u02, u12, u22);
+  }
+  U.m[0] = u00; U.m[1] = u10; U.m[2] = u20;
+  U.m[3] = u01; U.m[4] = u11; U.m[5] = u21;
+  U.m[6] = u02; U.m[7] = u12; U.m[8] = u22;
+  e[0] = A.xx; e[1] = A.yy; e[2] = A.zz;
+}
+
+// E = F F^T - I from G = F - I (no cancellation for F ~ I).
+__device__ __forceinline__ Sym3 left_strain(const Mat3 &F) {
+  float g00 = F.m[0] - 1.f, g10 = F.m[1], g20 = F.m[2];
+  float g01 = F.m[3], g11 = F.m[4] - 1.f, g21 = F.m[5];
+  float g02 = F.m[6], g12 = F.m[7], g22 = F.m[8] - 1.f;
+  Sym3 E;
+  // (G G^T)_rs = sum_c G_rc G_sc
+  E.xx = fmaf(g00, g00, fmaf(g01, g01, g02 * g02)) + 2.f * g00;
+  E.yy = fmaf(g10, g10, fmaf(g11, g11, g12 * g12)) + 2.f * g11;
+  E.zz = fmaf(g20, g20, fmaf(g21, g21, g22 * g22)) + 2.f * g22;
+  E.xy = fmaf(g00, g10, fmaf(g01, g11, g02 * g12)) + (g01 + g10);
+  E.xz = fmaf(g00, g20, fmaf(g01, g21, g02 * g22)) + (g02 + g20);
+  E.yz = fmaf(g10, g20, fmaf(g11, g21, g12 * g22)) + (g12 + g21);
+  return E;
+}
+
+// M = U diag(d) U^T
+__device__ __forceinline__ Sym3 sym_from_eig(const Mat3 &U, const float d[3]) {
+  Sym3 M;
+  M.xx = fmaf(d[0] * U.m[0], U.m[0], fmaf(d[1] * U.m[3], U.m[3], d[2] * U.m[6] * U.m[6]));
+  M.yy = fmaf(d[0] * U.m[1], U.m[1], fmaf(d[1] * U.m[4], U.m[4], d[2] * U.m[7] * U.m[7]));
+  M.zz = fmaf(d[0] * U.m[2], U.m[2], fmaf(d[1] * U.m[5], U.m[5], d[2] * U.m[8] * U.m[8]));
+  M.xy = fmaf(d[0] * U.m[0], U.m[1], fmaf(d[1] * U.m[3], U.m[4], d[2] * U.m[6] * U.m[7]));
+  M.xz = fmaf(d[0] * U.m[0], U.m[2], fmaf(d[1] * U.m[3], U.m[5], d[2] * U.m[6] * U.m[8]));
+  M.yz = fmaf(d[0] * U.m[1], U.m[2], fmaf(d[1] * U.m[4], U.m[5], d[2] * U.m[7] * U.m[8]));
+  return M;
+}
+
+// out = S * F (S symmetric)
+__device__ __forceinline__ Mat3 sym_mul(const Sym3 &S, const Mat3 &F) {
+  Mat3 o;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    float f0 = F.m[c * 3], f1 = F.m[c * 3 + 1], f2 = F.m[c * 3 + 2];
+    o.m[c * 3 + 0] = fmaf(S.xx, f0, fmaf(S.xy, f1, S.xz * f2));
+    o.m[c * 3 + 1] = fmaf(S.xy, f0, fmaf(S.yy, f1, S.yz * f2));
+    o.m[c * 3 + 2] = fmaf(S.xz, f0, fmaf(S.yz, f1, S.zz * f2));
+  }
+  return o;
+}
+
+__device__ __forceinline__ Mat3 mat_mul(const Mat3 &A, const Mat3 &B) {
+  Mat3 o;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) o.m[c * 3 + r] = fmaf(A(r, 0), B(0, c), fmaf(A(r, 1), B(1, c), A(r, 2) * B(2, c)));
+  return o;
+}
+
+struct Material {
+  int kind;
+  float p[8];
+};
+
+#ifndef MPMB_EIG_SWEEPS
+#define MPMB_EIG_SWEEPS 4
+#endif
+
+// -vol * P(F) F^T  ==  the value of Particle::calculate_force() (src/particles.cpp:216-218,
+// 335-337,409-411,463-467,628-637), returned as a symmetric tensor where it is one (all kinds
+// except LINEAR, whose P F^T is not symmetric for finite strain).
+// Returns through `out` (column-major full matrix).
+__device__ __forceinline__ void calculate_force(const Material &mat, const Mat3 &F, float ps, float vol, Mat3 &out) {
+  if (mat.kind == MAT_WATER) {
+    // p = k (j^-gamma - 1); sigma = -p I; force = -vol j sigma = vol j p I   (463-467)
+    float j = ps;
+    float p = mat.p[0] * (powf(j, -mat.p[1]) - 1.0f);
+    float d = vol * j * p;
+#pragma unroll
+    for (int i = 0; i < 9; i++) out.m[i] = 0.f;
+    out.m[0] = d; out.m[4] = d; out.m[8] = d;
+    return;
+  }
+  if (mat.kind == MAT_LINEAR) {
+    // P = mu (F + F^T - 2I) + lambda (tr F - 3) I ; force = -vol P F^T   (329-337)
+    float mu = mat.p[0], la = mat.p[1];
+    Mat3 P;
+    float tr = (F.m[0] - 1.f) + (F.m[4] - 1.f) + (F.m[8] - 1.f);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        float g = (F(r, c) - (r == c ? 1.f : 0.f)) + (F(c, r) - (r == c ? 1.f : 0.f));
+        P(r, c) = mu * g + (r == c ? la * tr : 0.f);
+      }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        // (P F^T)_rc = sum_k P_rk F_ck
+        float s = fmaf(P(r, 0), F(c, 0), fmaf(P(r, 1), F(c, 1), P(r, 2) * F(c, 2)));
+        out(r, c) = -vol * s;
+      }
+    return;
+  }
+  Mat3 U;
+  float e[3];
+  eig_sym3<MPMB_EIG_SWEEPS>(left_strain(F), U, e);
+  float tau[3];
+  if (mat.kind == MAT_SAND) {
+    // tau_i = 2 mu ln s_i + lambda sum ln s   (628-637: U (2mu S^-1 lnS + lambda tr(lnS) S^-1) V^T F^T)
+    float mu = mat.p[0], la = mat.p[1];
+    float l0 = 0.5f * log1pf(e[0]), l1 = 0.5f * log1pf(e[1]), l2 = 0.5f * log1pf(e[2]);
+    float tr = la * (l0 + l1 + l2);
+    tau[0] = fmaf(2.f * mu, l0, tr);
+    tau[1] = fmaf(2.f * mu, l1, tr);
+    tau[2] = fmaf(2.f * mu, l2, tr);
+  } else {
+    // fixed corotated (jelly 391-398, snow 207-214): P F^T = 2mu (F-R)F^T + lambda (J-1) J I
+    //   (F-R)F^T = U diag(s(s-1)) U^T ;  s-1 = e/(s+1) ;  J^2-1 = sum e + sum e e + e e e
+    float mu = mat.p[0], la = mat.p[1];
+    if (mat.kind == MAT_SNOW) {
+      float h = __expf(mat.p[2] * (1.0f - ps));  // 244-252
+      mu *= h;
+      la *= h;
+    }
+    float s0 = sqrtf(1.f + e[0]), s1 = sqrtf(1.f + e[1]), s2 = sqrtf(1.f + e[2]);
+    float J = s0 * s1 * s2;
+    float J2m1 = (e[0] + e[1] + e[2]) + fmaf(e[0], e[1], fmaf(e[0], e[2], e[1] * e[2])) + e[0] * e[1] * e[2];
+    float Jm1 = J2m1 / (J + 1.f);
+    float vol_term = la * Jm1 * J;
+    tau[0] = fmaf(2.f * mu * s0, e[0] / (s0 + 1.f), vol_term);
+    tau[1] = fmaf(2.f * mu * s1, e[1] / (s1 + 1.f), vol_term);
+    tau[2] = fmaf(2.f * mu * s2, e[2] / (s2 + 1.f), vol_term);
+  }
+  tau[0] *= -vol; tau[1] *= -vol; tau[2] *= -vol;
+  Sym3 T = sym_from_eig(U, tau);
+  out.m[0] = T.xx; out.m[1] = T.xy; out.m[2] = T.xz;
+  out.m[3] = T.xy; out.m[4] = T.yy; out.m[5] = T.yz;
+  out.m[6] = T.xz; out.m[7] = T.yz; out.m[8] = T.zz;
+}
+
+// Particle::plasticity(cdg) (src/particles.cpp:222-242,340-344,413-416,469-478,639-647):
+// F <- cdg F, then the return map of the material; ps is Jp / j / logJp.
+__device__ __forceinline__ void plasticity(const Material &mat, const Mat3 &cdg, Mat3 &F, float &ps) {
+  if (mat.kind == MAT_WATER) {
+    ps *= (cdg.m[0] + cdg.m[4] + cdg.m[8]) - 2.0f;  // j *= tr(cdg) - (dim-1)
+    if (ps < 0.1f) ps = 0.1f;
+    return;
+  }
+  Mat3 Ft = mat_mul(cdg, F);
+  if (mat.kind == MAT_LINEAR || mat.kind == MAT_JELLY) {
+    F = Ft;
+    return;
+  }
+  Mat3 U;
+  float e[3];
+  eig_sym3<MPMB_EIG_SWEEPS>(left_strain(Ft), U, e);
+  float ratio[3];
+  bool changed;
+  if (mat.kind == MAT_SNOW) {
+    // sigma clamped to [1-theta_c, 1+theta_s]; Jp <- clamp(Jp * prod(s)/prod(s'))   (222-242)
+    float lo = 1.f - mat.p[3], hi = 1.f + mat.p[4];
+    float prod = 1.f;
+    changed = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      float s = sqrtf(fmaxf(1.f + e[i], 0.f));
+      float sc = fminf(fmaxf(s, lo), hi);
+      ratio[i] = sc / s;
+      prod *= s / sc;
+      changed |= (sc != s);
+    }
+    float Jp = ps * prod;
+    if (!(Jp <= mat.p[6])) Jp = mat.p[6];
+    if (!(Jp >= mat.p[5])) Jp = mat.p[5];
+    ps = Jp;
+  } else {
+    // SandParticle::project (599-626) in log-strain space
+    float mu = mat.p[0], la = mat.p[1], alpha = mat.p[2], coh = mat.p[3], beta = mat.p[4];
+    float ls[3], eps[3];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      // ln max(|s|,1e-4) with s = sqrt(1+e) >= 0
+      float ec = fmaxf(e[i], 1e-8f - 1.f);
+      ls[i] = 0.5f * log1pf(ec);
+      eps[i] = ls[i] - coh;
+      sum += eps[i];
+    }
+    float tr = sum + ps;
+    float hat[3] = {eps[0] - tr * (1.f / 3.f), eps[1] - tr * (1.f / 3.f), eps[2] - tr * (1.f / 3.f)};
+    float hn = sqrtf(fmaf(hat[0], hat[0], fmaf(hat[1], hat[1], hat[2] * hat[2])));
+    if (tr >= 0.f) {
+      // sigma' = e^c I ; logJp += beta * sum(eps)
+#pragma unroll
+      for (int i = 0; i < 3; i++) ratio[i] = __expf(coh - ls[i]);
+      ps = fmaf(beta, sum, ps);
+      changed = true;
+    } else {
+      ps = 0.f;
+      float dg = hn + (3.f * la + 2.f * mu) / (2.f * mu) * tr * alpha;
+      if (dg <= 0.f) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) ratio[i] = 1.f;
+        changed = false;
+        // NB the reference still rebuilds F = U exp(eps+c) V^T here, which equals cdg F up to
+        // rounding unless a singular value was clamped at 1e-4 (never for physical states).
+        if (e[0] < 1e-8f - 1.f || e[1] < 1e-8f - 1.f || e[2] < 1e-8f - 1.f) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) ratio[i] = __expf(ls[i]) * rsqrtf(fmaxf(1.f + e[i], 1e-30f));
+          changed = true;
+        }
+      } else {
+        float k = dg / hn;
+#pragma unroll
+        for (int i = 0; i < 3; i++) ratio[i] = expf(-k * hat[i]);
+        changed = true;
+      }
+    }
+  }
+  if (changed) {
+    Sym3 M = sym_from_eig(U, ratio);
+    F = sym_mul(M, Ft);
+  } else {
+    F = Ft;
+  }
+}
+
+// friction_project (src/mpm_fwd.h:25-57) with base velocity 0 (static level set).
+__device__ __forceinline__ float3 friction_project0(float3 v, float3 n, float friction) {
+  if (friction == -1.0f) return make_float3(0.f, 0.f, 0.f);
+  bool slip = friction <= -2.0f;
+  if (slip) friction = -friction - 2.0f;
+  float nn = n.x * v.x + n.y * v.y + n.z * v.z;
+  float3 t = make_float3(v.x - nn * n.x, v.y - nn * n.y, v.z - nn * n.z);
+  float tn = sqrtf(t.x * t.x + t.y * t.y + t.z * t.z);
+  float scale = fmaxf(tn + fminf(nn, 0.f) * friction, 0.f) / fmaxf(1e-30f, tn);
+  float keep = fmaxf(0.f, slip ? 0.f : nn);
+  return make_float3(scale * t.x + keep * n.x, scale * t.y + keep * n.y, scale * t.z + keep * n.z);
+}
+
+// Quadratic B-spline weights of MLSMPMFastKernel32 (src/transfer.cpp:168-186) for
+// rel = x/dx - base in [0.5,1.5): w0 = .5(1.5-r)^2, w1 = .75-(r-1)^2, w2 = .5(r-.5)^2,
+// evaluated in the reference's polynomial form.
+__device__ __forceinline__ void bspline_weights(float rel, float w[3]) {
+  float pf = rel - 0.5f;
+  float t0 = pf + 0.5f, t1 = pf - 0.5f, t2 = pf - 1.5f;
+  w[0] = fmaf(0.5f, t0 * t0, fmaf(-1.5f, t0, 1.125f));
+  w[1] = fmaf(-1.0f, t1 * t1, 0.75f);
+  w[2] = fmaf(0.5f, t2 * t2, fmaf(1.5f, t2, 1.125f));
+}
+
+}  // namespace mpmb

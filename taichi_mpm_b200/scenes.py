@@ -1,0 +1,160 @@
+"""Synthetic inputs for the BASELINE.json configs (numpy, host side).
+
+Generator = the reference's deterministic `benchmark` lattice (src/mpm.cpp:149-186): 8 particles
+per cell at cell-centre +- 0.25 dx, with the physically consistent volume vol = dx^3/8
+(texture-seeding convention vol = dx^dim / maximum, src/mpm.cpp:134-135) and mass = vol*density.
+Material parameter vectors follow include/mpmb.h; defaults are the reference's
+(src/particles.cpp:192-205,383-389,448-449,570-597).
+"""
+import math
+
+import numpy as np
+
+MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND = range(5)
+N_MAT_PARAMS = 8
+
+
+def lame(E, nu):
+    mu = E / (2 * (1 + nu))
+    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+    return mu, lam
+
+
+def material_params(kind, **kw):
+    """Parameter vector of a reference particle type, with the reference's defaults."""
+    p = np.zeros(N_MAT_PARAMS, np.float32)
+    if kind in (MAT_LINEAR, MAT_JELLY):  # src/particles.cpp:317-323,383-389
+        mu, lam = lame(kw.get("E", 1e5), kw.get("nu", 0.3))
+        p[0], p[1] = mu, lam
+    elif kind == MAT_SNOW:  # src/particles.cpp:192-205
+        E, nu = kw.get("youngs_modulus", 1.4e5), kw.get("poisson_ratio", 0.2)
+        mu, lam = lame(E, nu)
+        p[0], p[1] = kw.get("mu_0", mu), kw.get("lambda_0", lam)
+        p[2] = kw.get("hardening", 10.0)
+        p[3], p[4] = kw.get("theta_c", 2.5e-2), kw.get("theta_s", 7.5e-3)
+        p[5], p[6] = kw.get("min_Jp", 0.6), kw.get("max_Jp", 20.0)
+    elif kind == MAT_WATER:  # src/particles.cpp:448-461
+        p[0], p[1] = kw.get("k", 1e4), kw.get("gamma", 7.0)
+    elif kind == MAT_SAND:  # src/particles.cpp:570-597
+        p[0], p[1] = kw.get("mu_0", 136038.0), kw.get("lambda_0", 204057.0)
+        phi = kw.get("friction_angle", 30.0)
+        s = math.sin(np.float32(phi) / np.float32(180.0) * np.float32(3.141592653))
+        p[2] = math.sqrt(2.0 / 3.0) * 2.0 * s / (3.0 - s)
+        p[3], p[4] = kw.get("cohesion", 0.0), kw.get("beta", 1.0)
+    else:
+        raise ValueError("unknown material kind %r" % (kind,))
+    return p
+
+
+def default_scalar(kind):
+    return 1.0 if kind in (MAT_SNOW, MAT_WATER) else 0.0  # Jp=1, j=1, logJp=0
+
+
+def lattice_block(res, lo_cell, hi_cell, density=400.0, jitter=0.0, seed=20260922, dtype=np.float32):
+    """8 particles per cell over cells [lo_cell, hi_cell) (3-vectors), dx = 1/res."""
+    dx = 1.0 / res
+    lo = np.asarray(lo_cell, np.int64)
+    hi = np.asarray(hi_cell, np.int64)
+    ii, jj, kk = np.meshgrid(np.arange(lo[0], hi[0]), np.arange(lo[1], hi[1]), np.arange(lo[2], hi[2]), indexing="ij")
+    centre = (np.stack([ii, jj, kk], -1).reshape(-1, 1, 3) + 0.5)  # cell centre, grid units
+    sign = np.array([[(-1 if (i % 2 == 0) else 1), (-1 if (i // 2 % 2 == 0) else 1), (-1 if (i // 4 % 2 == 0) else 1)] for i in range(8)],
+                    np.float64)
+    X = (centre + 0.25 * sign[None]).reshape(-1, 3)
+    if jitter > 0:
+        rng = np.random.default_rng(seed)
+        X = X + rng.uniform(-jitter, jitter, X.shape)
+    x = (X * dx).astype(dtype)
+    n = len(x)
+    vol = np.full(n, dx ** 3 / 8.0, dtype)
+    mass = (vol * density).astype(dtype)
+    return x, mass, vol
+
+
+def make_state(x, mass, vol, kind, group=0, v0=(0.0, 0.0, 0.0)):
+    n = len(x)
+    F = np.zeros((n, 9), np.float32)
+    F[:, 0] = F[:, 4] = F[:, 8] = 1.0
+    return dict(x=x.astype(np.float32), v=np.tile(np.asarray(v0, np.float32), (n, 1)), F=F, b=np.zeros((n, 9), np.float32),
+                mass=mass.astype(np.float32), vol=vol.astype(np.float32), ps=np.full(n, default_scalar(kind), np.float32),
+                group=np.full(n, group, np.int32), alive=np.ones(n, np.uint8))
+
+
+def floor_sdf(res, floor_cells, dtype=np.float32):
+    """Dense node level set of one floor plane y >= floor_cells (grid units): (n, phi)."""
+    n = res + 1
+    sdf = np.zeros((n, n, n, 4), dtype)
+    sdf[..., 1] = 1.0
+    sdf[..., 3] = (np.arange(n, dtype=np.float64) - floor_cells)[None, :, None]
+    return sdf
+
+
+def planes_sdf(res, planes, dtype=np.float32):
+    """Dense node level set of an intersection of half-spaces phi_i = n_i.X + d_i (grid units)."""
+    if np.isscalar(res):
+        res = (res, res, res)
+    nn = [r + 1 for r in res]
+    I, J, K = np.meshgrid(np.arange(nn[0], dtype=np.float32), np.arange(nn[1], dtype=np.float32), np.arange(nn[2], dtype=np.float32),
+                          indexing="ij")
+    best = np.full(nn, 1e30, np.float32)
+    out = np.zeros(tuple(nn) + (4,), np.float32)
+    out[..., 0] = 1.0
+    out[..., 3] = 1e30
+    for pl in np.asarray(planes, np.float32).reshape(-1, 4):
+        phi = pl[0] * I + pl[1] * J + pl[2] * K + pl[3]
+        m = phi < best
+        best = np.where(m, phi, best)
+        out[m, 0], out[m, 1], out[m, 2] = pl[0], pl[1], pl[2]
+        out[..., 3] = np.where(m, phi, out[..., 3])
+    return out.astype(dtype)
+
+
+def config(name, scale=1.0):
+    """The BASELINE.json configs as dict(scene=..., state=..., meta=...).
+
+    `scale` < 1 shrinks grid and block together (parity-test sizes); 1.0 is the quoted size.
+    scene: res, dx, dt, gravity, particle_gravity, mat_kind, mat_params, planes, friction
+    """
+    if name == "jelly128":      # config 2: 3D fixed-corotated block, 128^3 grid, 1M particles
+        res, cells, kind, dt = 128, 50, MAT_JELLY, 1e-4
+        kw, floor, friction = dict(E=1e5, nu=0.3), 0.1, -1.0
+    elif name == "sand256":     # config 3 (north star): 256^3 grid, 8M Drucker-Prager sand
+        res, cells, kind, dt = 256, 100, MAT_SAND, 2e-5
+        kw, floor, friction = dict(), None, 0.4
+    elif name == "snow256":     # config 4: 256^3 grid, 16M snow, block 100x100x200
+        res, cells, kind, dt = 256, 100, MAT_SNOW, 1e-4
+        kw, floor, friction = dict(), None, 0.4
+    elif name == "water512":    # config 5: 512^3 grid, 64M water
+        res, cells, kind, dt = 512, 200, MAT_WATER, 5e-5
+        kw, floor, friction = dict(), None, 0.4
+    elif name == "linear125":   # the reference's own benchmark (scripts/benchmark/benchmark_3d.py)
+        res, cells, kind, dt = 125, 100, MAT_LINEAR, 1e-2
+        kw, floor, friction = dict(E=1e2, nu=0.3), None, None
+    else:
+        raise ValueError(name)
+    res = int(round(res * scale))
+    cells = int(round(cells * scale))
+    dx = 1.0 / res
+    if name == "jelly128":
+        lo = np.array([(res - cells) // 2] * 3)
+        hi = lo + cells
+        floor_cells = floor * res
+        gravity = (0.0, -10.0, 0.0)
+    elif name == "linear125":
+        lo = np.array([int(round(res * 0.1))] * 3)
+        hi = lo + int(round(res * 0.8))
+        floor_cells = None
+        gravity = (0.0, 0.0, 0.0)
+    else:
+        floor_cells = 10.0
+        lo = np.array([(res - cells) // 2, 10, (res - cells) // 2])
+        hi = lo + cells
+        if name == "snow256":
+            lo[2] = (res - 2 * cells) // 2
+            hi[2] = lo[2] + 2 * cells
+        gravity = (0.0, -10.0, 0.0)
+    x, mass, vol = lattice_block(res, lo, hi, jitter=0.05, seed=20260922)
+    state = make_state(x, mass, vol, kind)
+    planes = None if floor_cells is None else np.array([[0.0, 1.0, 0.0, -floor_cells]], np.float32)
+    scene = dict(res=(res, res, res), dx=dx, dt=dt, gravity=gravity, particle_gravity=1, mat_kind=np.array([kind], np.int32),
+                 mat_params=material_params(kind, **kw)[None], planes=planes, friction=friction if planes is not None else 0.0)
+    return dict(scene=scene, state=state, meta=dict(name=name, res=res, n=len(x), kind=kind))

@@ -1,0 +1,221 @@
+"""GPU parity: the CUDA path, called through the C-ABI, against the fp64 oracle on identical
+seeded inputs (tolerances of SURVEY.md §8d, stated in tests/common.py)."""
+import numpy as np
+import pytest
+
+from taichi_mpm_b200 import scenes
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [("linear", scenes.MAT_LINEAR), ("jelly", scenes.MAT_JELLY), ("snow", scenes.MAT_SNOW), ("water", scenes.MAT_WATER),
+         ("sand", scenes.MAT_SAND)]
+
+
+def _assert_parity(err):
+    assert err["alive_match"]
+    assert err["grid_rast"] <= T.TOL_GRID_REL, err
+    assert err["grid_vel"] <= 5 * T.TOL_GRID_REL, err   # v = p/m amplifies the relative error of tiny masses
+    assert err["grid_mass_outside"] == 0.0, err
+    assert err["x"] <= T.TOL_X_ABS, err
+    assert err["v"] <= T.TOL_V_REL, err
+    assert err["b"] <= T.TOL_V_REL, err
+    assert err["F"] <= T.TOL_F_ABS, err
+    assert err["ps"] <= T.TOL_PS_ABS, err
+    assert err["mass"] == 0.0
+
+
+@pytest.mark.parametrize("name,kind", KINDS)
+def test_single_substep_vs_fp64_oracle(name, kind):
+    scene, st = T.perturbed_scene(kind, res=32, cells=8, seed=3)
+    e = T.make_engine(scene, st)
+    err, got, ref = T.compare_substep(e, scene, st)
+    print(name, {k: (float(v) if not isinstance(v, bool) else v) for k, v in err.items()})
+    _assert_parity(err)
+    e.close()
+
+
+@pytest.mark.parametrize("name,kind", KINDS)
+def test_single_substep_vs_fp32_oracle(name, kind):
+    # same bounds against the fp32 restatement (reference operation order)
+    from oracle import pyoracle as O
+    scene, st = T.perturbed_scene(kind, res=32, cells=6, seed=4)
+    e = T.make_engine(scene, st)
+    ref, _, _ = O.substep(scene, st, np.float32)
+    e.substep(1)
+    got = e.download()
+    ids = got["id"].astype(np.int64)
+    vmax = np.abs(ref["v"]).max()
+    assert np.abs(got["v"] - ref["v"][ids]).max() <= 2 * T.TOL_V_REL * vmax
+    assert np.abs(got["F"] - ref["F"][ids]).max() <= 2 * T.TOL_F_ABS
+    assert np.abs(got["x"] - ref["x"][ids]).max() <= T.TOL_X_ABS
+    e.close()
+
+
+def test_sand_plastic_branches_are_exercised():
+    # the three Drucker-Prager cases (expansion / inside cone / projected) all occur and agree
+    from oracle import pyoracle as O
+    scene, st = T.perturbed_scene(scenes.MAT_SAND, res=32, cells=8, seed=5, strain=0.01)
+    ref, _, _ = O.substep(scene, st, np.float64)
+    Ftrial_changed = np.abs(ref["F"] - st["F"]).max(1)
+    assert (ref["ps"] > 0).any() and (ref["ps"] == 0).any()
+    e = T.make_engine(scene, st)
+    err, got, ref = T.compare_substep(e, scene, st, check_grid=False)
+    assert err["F"] <= T.TOL_F_ABS and err["ps"] <= T.TOL_PS_ABS, err
+    e.close()
+
+
+def test_dense_sdf_equals_planes():
+    scene, st = T.perturbed_scene(scenes.MAT_JELLY, res=32, cells=6, seed=6, friction=-1.0)
+    e1 = T.make_engine(scene, st)
+    scene2 = dict(scene)
+    scene2["sdf_dense_upload"] = scene["sdf"]
+    e2 = T.make_engine(scene2, st)
+    e1.substep(2)
+    e2.substep(2)
+    a, b = e1.download(), e2.download()
+    for k in ("x", "v", "F", "b"):
+        assert np.array_equal(a[k], b[k]), k
+    e1.close(); e2.close()
+
+
+@pytest.mark.parametrize("friction", [-1.0, -2.3, 0.0, 0.4])
+def test_boundary_modes(friction):
+    scene, st = T.perturbed_scene(scenes.MAT_JELLY, res=32, cells=6, seed=7, friction=friction, vel=1.0)
+    e = T.make_engine(scene, st)
+    err, _, _ = T.compare_substep(e, scene, st)
+    _assert_parity(err)
+    e.close()
+
+
+def test_grid_gravity_mode():
+    scene, st = T.perturbed_scene(scenes.MAT_JELLY, res=32, cells=6, seed=8)
+    scene["particle_gravity"] = 0
+    e = T.make_engine(scene, st)
+    err, _, _ = T.compare_substep(e, scene, st)
+    _assert_parity(err)
+    e.close()
+
+
+def test_two_materials_in_one_scene():
+    sc1, st1 = T.perturbed_scene(scenes.MAT_SAND, res=32, cells=6, seed=9)
+    x2, m2, v2 = scenes.lattice_block(32, (8, 18, 8), (12, 22, 12), jitter=0.1, seed=10)
+    st2 = scenes.make_state(x2, m2, v2, scenes.MAT_WATER, group=1)
+    st = {k: np.concatenate([st1[k], st2[k]]) for k in st1}
+    scene = dict(sc1)
+    scene["mat_kind"] = np.array([scenes.MAT_SAND, scenes.MAT_WATER], np.int32)
+    scene["mat_params"] = np.stack([scenes.material_params(scenes.MAT_SAND), scenes.material_params(scenes.MAT_WATER)])
+    e = T.make_engine(scene, st)
+    err, _, _ = T.compare_substep(e, scene, st)
+    _assert_parity(err)
+    e.close()
+
+
+def test_particle_deletion_matches_reference_band():
+    scene, st = T.perturbed_scene(scenes.MAT_JELLY, res=32, cells=4, seed=11, with_floor=False)
+    res = 32
+    st["x"][0] = [6.9 / res, 0.5, 0.5]
+    st["x"][1] = [0.5, (res - 6.9) / res, 0.5]
+    st["x"][2] = [7.6 / res, 0.5, 0.5]
+    st["v"][:3] = 0
+    e = T.make_engine(scene, st)
+    err, got, ref = T.compare_substep(e, scene, st, check_grid=False)
+    assert err["alive_match"]
+    assert 0 not in got["id"] and 1 not in got["id"] and 2 in got["id"]
+    assert e.num_particles() == len(st["x"]) - 2
+    # deleted particles stay deleted and the rest keep evolving
+    e.substep(3)
+    assert e.num_particles() == len(st["x"]) - 2
+    e.close()
+
+
+def test_empty_and_tiny_inputs():
+    scene, st = T.perturbed_scene(scenes.MAT_JELLY, res=32, cells=4, seed=12)
+    one = {k: v[:1] for k, v in st.items()}
+    e = T.make_engine(scene, one)
+    err, _, _ = T.compare_substep(e, scene, one)
+    assert err["alive_match"] and err["v"] <= T.TOL_V_REL
+    e.close()
+    from taichi_mpm_b200 import capi
+    e = capi.Engine(scene["res"], scene["dx"], scene["dt"])
+    e.upload(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0), np.zeros(0))
+    e.substep(2)
+    assert e.num_particles() == 0
+    e.close()
+
+
+def test_stage_order_is_enforced():
+    from taichi_mpm_b200 import capi
+    scene, st = T.perturbed_scene(scenes.MAT_JELLY, res=32, cells=4, seed=13)
+    e = T.make_engine(scene, st)
+    with pytest.raises(capi.MpmbError):
+        e.rasterize()
+    e.sort_particles_and_populate_grid()
+    with pytest.raises(capi.MpmbError):
+        e.resample()
+    e.close()
+
+
+def test_multi_step_invariants_sand():
+    # >=100 substeps: trajectories are chaotic, compare invariants
+    from oracle import pyoracle as O
+    scene, st = T.perturbed_scene(scenes.MAT_SAND, res=32, cells=8, seed=14, strain=0.0, vel=0.2, with_floor=True)
+    e = T.make_engine(scene, st)
+    fast = O.FastOracle(scene, st, threads=4)
+    nsub = 100
+    e.substep(nsub)
+    fast.substeps(nsub)
+    got = e.download()
+    alive = fast.st["alive"].astype(bool)
+    assert len(got["id"]) == alive.sum()
+    m = got["mass"].astype(np.float64)
+    assert m.sum() == pytest.approx(fast.st["mass"][alive].astype(np.float64).sum(), rel=1e-12)
+    com_g = (m[:, None] * got["x"]).sum(0) / m.sum()
+    mo = fast.st["mass"][alive].astype(np.float64)
+    com_o = (mo[:, None] * fast.st["x"][alive]).sum(0) / mo.sum()
+    assert np.abs(com_g - com_o).max() < 2e-5
+    mom_g = (m[:, None] * got["v"]).sum(0)
+    mom_o = (mo[:, None] * fast.st["v"][alive]).sum(0)
+    assert np.abs(mom_g - mom_o).max() <= 2e-3 * max(np.abs(mom_o).max(), m.sum() * 0.01)
+    assert np.isfinite(got["F"]).all()
+    e.close()
+
+
+def test_aos_round_trip():
+    # the reference's 320 B particle slots in, the same slots out (drop-in adapter path)
+    from taichi_mpm_b200 import capi
+    scene, st = T.perturbed_scene(scenes.MAT_SAND, res=32, cells=4, seed=15)
+    n = len(st["x"])
+    L = capi.MpmbAosLayout()
+    L.stride, L.off_v_and_m, L.off_pos, L.off_dg_e, L.off_apic_b, L.col_pitch = 320, 16, 32, 48, 96, 16
+    L.off_vol, L.off_scalar = 164, 200
+    slots = n + 7
+    pool = np.zeros((slots, 320), np.uint8)
+    rng = np.random.default_rng(1)
+    indices = rng.permutation(slots)[:n].astype(np.uint32)
+    f = pool.view(np.float32).reshape(slots, 80)
+    for k, s in enumerate(indices):
+        f[s, 4:7] = st["v"][k]; f[s, 7] = st["mass"][k]
+        f[s, 8:11] = st["x"][k]
+        for c in range(3):
+            f[s, 12 + 4 * c: 15 + 4 * c] = st["F"][k, 3 * c: 3 * c + 3]
+            f[s, 24 + 4 * c: 27 + 4 * c] = st["b"][k, 3 * c: 3 * c + 3]
+        f[s, 41] = st["vol"][k]
+        f[s, 50] = st["ps"][k]
+    e = capi.Engine(scene["res"], scene["dx"], scene["dt"], scene["gravity"])
+    e.set_material(0, scenes.MAT_SAND, scene["mat_params"][0])
+    e.set_planes(scene["planes"], scene["friction"])
+    e.upload_aos(pool, indices, L)
+    e2 = T.make_engine(scene, st)
+    e.substep(1); e2.substep(1)
+    ref = e2.download()
+    idx = indices.copy()
+    n_alive = e.download_aos(pool, idx, L)
+    assert n_alive == len(ref["id"])
+    f = pool.view(np.float32).reshape(slots, 80)
+    for k in range(n_alive):
+        s = idx[k]
+        assert s == indices[ref["id"][k]]
+        assert np.array_equal(f[s, 8:11], ref["x"][k]) and np.array_equal(f[s, 4:7], ref["v"][k])
+        assert f[s, 50] == ref["ps"][k]
+    e.close(); e2.close()
