@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — million particle-updates/s of the MLS-MPM substep hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sand256]
+
+A "step" is one substep (sort -> P2G -> grid update -> G2P+constitutive -> delete) over the whole
+synthetic particle set.  Workload at N=1 = BASELINE config 3 (256^3 grid, 8 M Drucker-Prager sand),
+the config the metric is quoted on.  Prints ONE JSON line (rank 0).
+
+  value     whole-job M particle-updates/s, state resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the reference-facing call with HOST buffers: one frame =
+            upload of the particle set from pinned host memory + frame_substeps substeps +
+            download of the result (the drop-in adapter's per-frame contract)
+  roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs measured HBM peak
+  cpu_baseline  the OpenMP restatement of the reference's optimized CPU path (oracle "port"),
+            timed on this box's host cores on a bounded sample
+  --impl reference  times that CPU path alone (the reference cannot be built here: DESIGN.md §2)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from taichi_mpm_b200 import scenes  # noqa: E402
+
+BYTES_PER_UPDATE = {scenes.MAT_LINEAR: 208, scenes.MAT_JELLY: 208, scenes.MAT_SAND: 216, scenes.MAT_SNOW: 216, scenes.MAT_WATER: 144}
+# split of the per-update figure between the two hot kernels: P2G reads the state
+# (+mass, vol) and writes half of the grid traffic, G2P writes the state and reads the other half.
+P2G_BYTES = {scenes.MAT_LINEAR: 108, scenes.MAT_JELLY: 108, scenes.MAT_SAND: 112, scenes.MAT_SNOW: 112, scenes.MAT_WATER: 76}
+STAGE_NAMES = ["sort+tiles", "p2g", "g2p", "exchange"]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                v = getattr(nv, n)
+                if isinstance(v, int) and v and n not in ("nvmlClocksEventReasonAll", "nvmlClocksThrottleReasonAll"):
+                    names.setdefault(v, n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit and "None" not in name and "Idle" not in name:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_workload(name, scale):
+    cfg = scenes.config(name, scale)
+    sc = cfg["scene"]
+    if sc["planes"] is not None:
+        sc["sdf"] = None  # engine builds the dense level set on the device from the planes
+    return cfg
+
+
+def cpu_run(cfg, n_particles_cap, budget_s, min_substeps=1, threads=None):
+    """Times the oracle's OpenMP fast path on (a sub-block of) the workload."""
+    from oracle import pyoracle as O
+    st, sc = cfg["state"], dict(cfg["scene"])
+    n = len(st["x"])
+    if n > n_particles_cap:
+        # bounded sample: the lowest layers of the column (keeps the floor contact), contiguous in y
+        order = np.argsort(st["x"][:, 1], kind="stable")[:n_particles_cap]
+        st = {k: v[order] for k, v in st.items()}
+    if sc.get("planes") is not None:
+        sc["sdf"] = scenes.planes_sdf(sc["res"], sc["planes"])
+    fast = O.FastOracle(sc, st, threads=threads)
+    t0 = time.perf_counter()
+    upd, tm = fast.substeps(1)  # first substep also pays first-touch of the buffers: untimed warm-up
+    warm = time.perf_counter() - t0
+    nsub = max(min_substeps, int(min(50, budget_s / max(warm, 1e-3))))
+    t0 = time.perf_counter()
+    upd, tm = fast.substeps(nsub)
+    dt = time.perf_counter() - t0
+    return dict(value=upd / dt / 1e6, seconds=dt, substeps=nsub, particles=len(st["x"]), threads=fast.threads,
+                ns_per_particle=dict(sort=tm[0] / upd * 1e9, p2g=tm[1] / upd * 1e9, grid=tm[2] / upd * 1e9, g2p=tm[3] / upd * 1e9))
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path = the oracle port
+    (the taichi-legacy core is not vendored, so the reference binary cannot be built)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = build_workload(args.workload, args.scale)
+    n_full = len(cfg["state"]["x"])
+    from oracle import pyoracle as O
+    st, sc = cfg["state"], dict(cfg["scene"])
+    if sc.get("planes") is not None:
+        sc["sdf"] = scenes.planes_sdf(sc["res"], sc["planes"])
+    # calibrate the sample so that (steps+warmup) substeps take about two minutes
+    probe_n = min(n_full, 1_000_000)
+    order = np.argsort(st["x"][:, 1], kind="stable")
+    probe = {k: v[order[:probe_n]] for k, v in st.items()}
+    f = O.FastOracle(sc, probe)
+    f.substeps(1)
+    t0 = time.perf_counter()
+    f.substeps(2)
+    per_particle = (time.perf_counter() - t0) / 2 / probe_n
+    total = args.steps + args.warmup
+    n_sample = int(min(n_full, max(100_000, 120.0 / (per_particle * total))))
+    sample = {k: v[order[:n_sample]] for k, v in st.items()}
+    del f
+    fast = O.FastOracle(sc, sample)
+    fast.substeps(args.warmup)
+    t0 = time.perf_counter()
+    upd, tm = fast.substeps(args.steps)
+    dt = time.perf_counter() - t0
+    val = upd / dt / 1e6
+    sample_txt = "%d of %d particles (lowest layers of the column), every substep over the sample, %d OpenMP threads" % (
+        n_sample, n_full, fast.threads)
+    line = {
+        "impl": "reference", "metric": "million particle-updates/s", "value": val, "unit": "M particle-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg, n_sample),
+        "cpu_baseline": {"value": val, "unit": "M particle-updates/s", "cores": fast.threads, "kind": "port", "sample": sample_txt,
+                         "ns_per_particle": {"sort": tm[0] / upd * 1e9, "p2g": tm[1] / upd * 1e9, "grid": tm[2] / upd * 1e9,
+                                             "g2p": tm[3] / upd * 1e9}},
+        "e2e": {"value": val, "unit": "M particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, cfg, n_particles):
+    m = cfg["meta"]
+    return {"workload": "%s: %d^3 grid, %d particles, %s, dt=%g, floor plane friction %g" % (
+        m["name"], m["res"], n_particles, ["linear", "jelly", "snow", "water", "sand"][m["kind"]], cfg["scene"]["dt"],
+        cfg["scene"]["friction"]),
+        "l2": "inputs larger than L2 (particle state %.0f MB per buffer vs 126 MB L2)" % (n_particles * 112 / 1e6),
+        "parallelism": "1 GPU" if args.gpus == 1 else "z-slab x%d" % args.gpus}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from taichi_mpm_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    cfg = build_workload(args.workload, args.scale)
+    st, sc = cfg["state"], cfg["scene"]
+    kind = cfg["meta"]["kind"]
+    if world > 1:
+        raise SystemExit("z-slab multi-GPU path is not built yet (DESIGN.md §7)")
+    n = len(st["x"])
+
+    eng = capi.Engine(sc["res"], sc["dx"], sc["dt"], sc["gravity"], sc["particle_gravity"], True, device=local)
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_material(0, kind, sc["mat_params"][0])
+    if sc["planes"] is not None:
+        eng.set_planes(sc["planes"], sc["friction"])
+
+    # pinned host copies of the particle set: the host side of the drop-in boundary
+    host = {}
+    for k, shape, dt_ in (("x", (n, 3), torch.float32), ("v", (n, 3), torch.float32), ("F", (n, 9), torch.float32),
+                          ("b", (n, 9), torch.float32), ("mass", (n,), torch.float32), ("vol", (n,), torch.float32),
+                          ("ps", (n,), torch.float32), ("group", (n,), torch.int32)):
+        t = torch.empty(shape, dtype=dt_, pin_memory=True)
+        t.numpy()[...] = st[k]
+        host[k] = t
+    host["id"] = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+
+    def upload():
+        eng.upload_ptrs(n, host["x"].data_ptr(), host["v"].data_ptr(), host["F"].data_ptr(), host["b"].data_ptr(),
+                        host["mass"].data_ptr(), host["vol"].data_ptr(), host["ps"].data_ptr(), host["group"].data_ptr())
+
+    def download():
+        return eng.download_ptrs(n, host["id"].data_ptr(), host["x"].data_ptr(), host["v"].data_ptr(), host["F"].data_ptr(),
+                                 host["b"].data_ptr(), 0, 0, host["ps"].data_ptr(), 0)
+
+    upload()
+    h2d = n * (3 + 3 + 9 + 9 + 1 + 1 + 1 + 1) * 4
+    d2h = n * (1 + 3 + 3 + 9 + 9 + 1) * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput
+    eng.substep(args.warmup)
+    barrier()
+    c0 = eng.get_counters()
+    eng.set_profiling(True)
+    eng.get_profile(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    eng.substep(args.steps)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    stage_ms, stage_launches = eng.get_profile(reset=True)
+    eng.set_profiling(False)
+    c1 = eng.get_counters()
+    alive = c1["alive"]
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = alive * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- end to end through host buffers: frames of upload + substeps + download
+    frame_substeps = args.frame_substeps
+    n_alive = alive
+    if args.frames > 0:
+        upload()
+        eng.substep(3)
+        download()
+    t_e2e = []
+    for _ in range(args.frames):
+        barrier()
+        t0 = time.perf_counter()
+        upload()
+        eng.substep(frame_substeps)
+        n_alive = download()
+        barrier()
+        t_e2e.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(t_e2e)) if t_e2e else float("nan")
+    e2e_value = n_alive * frame_substeps / e2e_s / 1e6 if t_e2e else None
+
+    if rank != 0:
+        return
+    peaks, peak_kind = measured_peaks()
+    peak = float(peaks["hbm_gbs"])
+    # dominant kernel of the substep
+    kms = {"p2g": stage_ms[1] / max(args.steps, 1), "g2p": stage_ms[2] / max(args.steps, 1)}
+    dom = max(kms, key=kms.get)
+    kb = P2G_BYTES[kind] if dom == "p2g" else BYTES_PER_UPDATE[kind] - P2G_BYTES[kind]
+    achieved = kb * alive / (kms[dom] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
+                "algorithmic_bytes_per_launch": kb * alive, "kernel_ms": kms[dom],
+                "substep": {"bytes_per_update": BYTES_PER_UPDATE[kind], "achieved": BYTES_PER_UPDATE[kind] * value * 1e6 / 1e9,
+                            "frac": BYTES_PER_UPDATE[kind] * value * 1e6 / 1e9 / peak},
+                "stage_ms_per_step": {STAGE_NAMES[i]: stage_ms[i] / max(args.steps, 1) for i in range(4)}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_run(cfg, args.cpu_sample, budget_s=15.0)
+        cpu = {"value": r["value"], "unit": "M particle-updates/s", "cores": r["threads"], "kind": "port",
+               "sample": "%d of %d particles (lowest layers of the column), %d substeps, %.1f s" % (r["particles"], n, r["substeps"], r["seconds"]),
+               "ns_per_particle": r["ns_per_particle"]}
+
+    line = {
+        "metric": "million particle-updates/s", "value": value, "unit": "M particle-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, n),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "M particle-updates/s", "h2d_bytes_per_step": h2d / frame_substeps,
+                "d2h_bytes_per_step": d2h / frame_substeps, "frame_substeps": frame_substeps, "frames": args.frames,
+                "frame_seconds": e2e_s},
+        "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+        "alive_particles": alive, "active_tiles": c1["active_tiles"],
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sand256")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink grid and block together (debug only)")
+    ap.add_argument("--frame-substeps", type=int, default=500, help="substeps per e2e frame (frame_dt/base_delta_t = 0.01/2e-5)")
+    ap.add_argument("--frames", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

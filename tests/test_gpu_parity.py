@@ -74,8 +74,9 @@ def test_dense_sdf_equals_planes():
     e1.substep(2)
     e2.substep(2)
     a, b = e1.download(), e2.download()
+    # not bitwise: the shared-memory float atomics of P2G commit in a run-dependent order
     for k in ("x", "v", "F", "b"):
-        assert np.array_equal(a[k], b[k]), k
+        assert np.abs(a[k] - b[k]).max() <= 1e-5 * max(np.abs(a[k]).max(), 1e-30), k
     e1.close(); e2.close()
 
 
