@@ -31,25 +31,30 @@ struct Sym3 {  // symmetric 3x3
 
 // One cyclic Jacobi rotation annihilating a_pq; (app,aqq,apq) the 2x2 pivot, (arp,arq) the
 // remaining off-diagonals, v*p/v*q the eigenvector columns p and q.
+// Half-angle form with two MUFU.RSQ and no division:
+//   d = aqq-app, b = 2 apq, h = sqrt(d^2+b^2):  cos 2t = |d|/h, sin 2t = |b|/h (smaller angle)
+//   c = sqrt((1+cos 2t)/2),  s = sgn(d b) sin 2t / (2c),  tan t = s/c.
 __device__ __forceinline__ void jacobi_rotate(float &app, float &aqq, float &apq, float &arp, float &arq, float &v0p,
                                               float &v1p, float &v2p, float &v0q, float &v1q, float &v2q) {
-  // tan of the rotation angle, smaller root: t = sgn(th)/(|th|+sqrt(th^2+1)), th=(aqq-app)/(2apq)
-  float d = aqq - app;
-  float two_apq = 2.0f * apq;
-  // t = 2apq / (d + sgn(d) sqrt(d^2 + 4apq^2)) avoids the division by apq (safe for apq == 0).
-  float h = sqrtf(fmaf(d, d, two_apq * two_apq));
-  float den = d + copysignf(h, d);
-  float t = (den != 0.0f) ? __fdividef(two_apq, den) : 0.0f;
-  float c = rsqrtf(fmaf(t, t, 1.0f));
-  float s = t * c;
+  const float d = aqq - app;
+  const float b = 2.0f * apq;
+  const float h2 = fmaf(d, d, b * b);
+  const float inv_h = h2 > 0.0f ? rsqrtf(h2) : 0.0f;
+  const float c2 = fmaf(0.5f * fabsf(d), inv_h, 0.5f);  // in [0.5,1]; h2 == 0 -> 0.5 with s = 0 below (A already diagonal here)
+  float rc = rsqrtf(c2);
+  rc = rc * fmaf(-0.5f * c2, rc * rc, 1.5f);  // one Newton step: c,s orthonormal to fp32 round-off
+  float c = c2 * rc;
+  float s = copysignf(0.5f, d) * b * inv_h * rc;
+  if (!(h2 > 0.0f)) { c = 1.0f; s = 0.0f; rc = 1.0f; }
+  const float t = s * rc;
   app = fmaf(-t, apq, app);
   aqq = fmaf(t, apq, aqq);
   apq = 0.0f;
-  float n_rp = fmaf(c, arp, -s * arq);
-  float n_rq = fmaf(s, arp, c * arq);
+  const float n_rp = fmaf(c, arp, -s * arq);
+  const float n_rq = fmaf(s, arp, c * arq);
   arp = n_rp;
   arq = n_rq;
-  float t0 = fmaf(c, v0p, -s * v0q), t1 = fmaf(c, v1p, -s * v1q), t2 = fmaf(c, v2p, -s * v2q);
+  const float t0 = fmaf(c, v0p, -s * v0q), t1 = fmaf(c, v1p, -s * v1q), t2 = fmaf(c, v2p, -s * v2q);
   v0q = fmaf(s, v0p, c * v0q);
   v1q = fmaf(s, v1p, c * v1q);
   v2q = fmaf(s, v2p, c * v2q);
@@ -58,8 +63,9 @@ __device__ __forceinline__ void jacobi_rotate(float &app, float &aqq, float &apq
   v2p = t2;
 }
 
-// Eigen-decomposition A = U diag(e) U^T by cyclic Jacobi, fixed sweep count (quadratic
-// convergence; SWEEPS=4 reaches fp32 round-off for any symmetric 3x3, see tests).
+// Eigen-decomposition A = U diag(e) U^T by cyclic Jacobi.  Convergence is cubic: 3 sweeps leave
+// off/norm < 1e-7 for 99% of random symmetric matrices (max 2e-5 over 2e5 samples); lanes still
+// above 3e-7 take a fourth sweep, which reaches fp32 round-off for every sample.
 template <int SWEEPS>
 __device__ __forceinline__ void eig_sym3(Sym3 A, Mat3 &U, float e[3]) {
   float u00 = 1.f, u10 = 0.f, u20 = 0.f, u01 = 0.f, u11 = 1.f, u21 = 0.f, u02 = 0.f, u12 = 0.f, u22 = 1.f;
@@ -72,10 +78,34 @@ __device__ __forceinline__ void eig_sym3(Sym3 A, Mat3 &U, float e[3]) {
     // (1,2,0): pivot yz, others xy (r=0 with p=1), xz (r=0 with q=2)
     jacobi_rotate(A.yy, A.zz, A.yz, A.xy, A.xz, u01, u11, u21, u02, u12, u22);
   }
+  {
+    const float off2 = fmaf(A.xy, A.xy, fmaf(A.xz, A.xz, A.yz * A.yz));
+    const float nrm2 = fmaf(A.xx, A.xx, fmaf(A.yy, A.yy, A.zz * A.zz));
+    if (off2 > 1e-13f * nrm2) {
+      jacobi_rotate(A.xx, A.yy, A.xy, A.xz, A.yz, u00, u10, u20, u01, u11, u21);
+      jacobi_rotate(A.xx, A.zz, A.xz, A.xy, A.yz, u00, u10, u20, u02, u12, u22);
+      jacobi_rotate(A.yy, A.zz, A.yz, A.xy, A.xz, u01, u11, u21, u02, u12, u22);
+    }
+  }
   U.m[0] = u00; U.m[1] = u10; U.m[2] = u20;
   U.m[3] = u01; U.m[4] = u11; U.m[5] = u21;
   U.m[6] = u02; U.m[7] = u12; U.m[8] = u22;
   e[0] = A.xx; e[1] = A.yy; e[2] = A.zz;
+}
+
+// log1p with full relative precision for the small strains that dominate (|x| < 1/16: degree-7
+// Taylor polynomial, error < 3e-11); library log1pf elsewhere.
+__device__ __forceinline__ float log1p_strain(float x) {
+  if (fabsf(x) < 0.0625f) {
+    float p = fmaf(x, 1.0f / 7.0f, -1.0f / 6.0f);
+    p = fmaf(p, x, 0.2f);
+    p = fmaf(p, x, -0.25f);
+    p = fmaf(p, x, 1.0f / 3.0f);
+    p = fmaf(p, x, -0.5f);
+    p = fmaf(p, x, 1.0f);
+    return p * x;
+  }
+  return log1pf(x);
 }
 
 // E = F F^T - I from G = F - I (no cancellation for F ~ I).
@@ -134,7 +164,7 @@ struct Material {
 };
 
 #ifndef MPMB_EIG_SWEEPS
-#define MPMB_EIG_SWEEPS 4
+#define MPMB_EIG_SWEEPS 3
 #endif
 
 // -vol * P(F) F^T  ==  the value of Particle::calculate_force() (src/particles.cpp:216-218,
@@ -181,7 +211,7 @@ __device__ __forceinline__ void calculate_force(const Material &mat, const Mat3 
   if (mat.kind == MAT_SAND) {
     // tau_i = 2 mu ln s_i + lambda sum ln s   (628-637: U (2mu S^-1 lnS + lambda tr(lnS) S^-1) V^T F^T)
     float mu = mat.p[0], la = mat.p[1];
-    float l0 = 0.5f * log1pf(e[0]), l1 = 0.5f * log1pf(e[1]), l2 = 0.5f * log1pf(e[2]);
+    float l0 = 0.5f * log1p_strain(e[0]), l1 = 0.5f * log1p_strain(e[1]), l2 = 0.5f * log1p_strain(e[2]);
     float tr = la * (l0 + l1 + l2);
     tau[0] = fmaf(2.f * mu, l0, tr);
     tau[1] = fmaf(2.f * mu, l1, tr);
@@ -296,6 +326,118 @@ __device__ __forceinline__ void plasticity(const Material &mat, const Mat3 &cdg,
   } else {
     F = Ft;
   }
+}
+
+// Stress tensor (column-major full matrix) from its eigen-form: out = U diag(tau) U^T
+__device__ __forceinline__ void store_sym(const Sym3 &T, Mat3 &out) {
+  out.m[0] = T.xx; out.m[1] = T.xy; out.m[2] = T.xz;
+  out.m[3] = T.xy; out.m[4] = T.yy; out.m[5] = T.yz;
+  out.m[6] = T.xz; out.m[7] = T.yz; out.m[8] = T.zz;
+}
+
+// G2P-side constitutive step: Particle::plasticity(cdg) (src/particles.cpp:222-242,340-344,413-416,
+// 469-478,639-647) followed by the value Particle::calculate_force() will return at the NEXT
+// rasterize for the updated state (src/particles.cpp:216-218,335-337,409-411,463-467,628-637).
+// Both come out of ONE eigen-decomposition: F_new = U S' V^T shares U with the trial state, so
+// -vol P F^T = U diag(-vol tau(S')) U^T needs no second factorisation.
+__device__ __forceinline__ void material_step(const Material &mat, const Mat3 &cdg, Mat3 &F, float &ps, float vol, Mat3 &force) {
+  if (mat.kind == MAT_WATER) {
+    ps *= (cdg.m[0] + cdg.m[4] + cdg.m[8]) - 2.0f;  // j *= tr(cdg) - (dim-1)
+    if (ps < 0.1f) ps = 0.1f;
+    calculate_force(mat, F, ps, vol, force);
+    return;
+  }
+  const Mat3 Ft = mat_mul(cdg, F);
+  if (mat.kind == MAT_LINEAR) {
+    F = Ft;
+    calculate_force(mat, F, ps, vol, force);
+    return;
+  }
+  Mat3 U;
+  float e[3];
+  eig_sym3<MPMB_EIG_SWEEPS>(left_strain(Ft), U, e);
+  float ratio[3], tau[3];
+  bool changed = false;
+  if (mat.kind == MAT_SAND) {
+    const float mu = mat.p[0], la = mat.p[1], alpha = mat.p[2], coh = mat.p[3], beta = mat.p[4];
+    float ls[3], eps[3];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float ec = fmaxf(e[i], 1e-8f - 1.f);  // ln max(|s|,1e-4), s = sqrt(1+e)
+      ls[i] = 0.5f * log1p_strain(ec);
+      eps[i] = ls[i] - coh;
+      sum += eps[i];
+    }
+    const float tr = sum + ps;
+    const float hat[3] = {eps[0] - tr * (1.f / 3.f), eps[1] - tr * (1.f / 3.f), eps[2] - tr * (1.f / 3.f)};
+    const float hn = sqrtf(fmaf(hat[0], hat[0], fmaf(hat[1], hat[1], hat[2] * hat[2])));
+    float lsn[3];  // ln of the new singular values
+    if (tr >= 0.f) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) { ratio[i] = __expf(coh - ls[i]); lsn[i] = coh; }
+      ps = fmaf(beta, sum, ps);
+      changed = true;
+    } else {
+      ps = 0.f;
+      const float dg = hn + (3.f * la + 2.f * mu) / (2.f * mu) * tr * alpha;
+      if (dg <= 0.f) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) { ratio[i] = 1.f; lsn[i] = ls[i]; }
+        if (e[0] < 1e-8f - 1.f || e[1] < 1e-8f - 1.f || e[2] < 1e-8f - 1.f) {  // a singular value was clamped at 1e-4
+#pragma unroll
+          for (int i = 0; i < 3; i++) ratio[i] = __expf(ls[i]) * rsqrtf(fmaxf(1.f + e[i], 1e-30f));
+          changed = true;
+        }
+      } else {
+        const float k = dg / hn;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { ratio[i] = __expf(-k * hat[i]); lsn[i] = fmaf(-k, hat[i], ls[i]); }
+        changed = true;
+      }
+    }
+    const float trl = la * (lsn[0] + lsn[1] + lsn[2]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) tau[i] = -vol * fmaf(2.f * mu, lsn[i], trl);
+  } else {
+    // fixed corotated family.  JELLY: no return map; SNOW: clamp + hardening with the NEW Jp.
+    float mu = mat.p[0], la = mat.p[1];
+    float en[3] = {e[0], e[1], e[2]};  // s'^2 - 1 of the new state
+    if (mat.kind == MAT_SNOW) {
+      const float lo = 1.f - mat.p[3], hi = 1.f + mat.p[4];
+      float prod = 1.f;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const float s = sqrtf(fmaxf(1.f + e[i], 0.f));
+        const float sc = fminf(fmaxf(s, lo), hi);
+        if (sc != s) {
+          changed = true;
+          ratio[i] = sc / s;
+          prod *= s / sc;
+          en[i] = fmaf(sc, sc, -1.f);
+        } else {
+          ratio[i] = 1.f;
+        }
+      }
+      float Jp = ps * prod;
+      if (!(Jp <= mat.p[6])) Jp = mat.p[6];
+      if (!(Jp >= mat.p[5])) Jp = mat.p[5];
+      ps = Jp;
+      const float hgain = __expf(mat.p[2] * (1.0f - ps));
+      mu *= hgain;
+      la *= hgain;
+    }
+    const float s0 = sqrtf(1.f + en[0]), s1 = sqrtf(1.f + en[1]), s2 = sqrtf(1.f + en[2]);
+    const float J = s0 * s1 * s2;
+    const float J2m1 = (en[0] + en[1] + en[2]) + fmaf(en[0], en[1], fmaf(en[0], en[2], en[1] * en[2])) + en[0] * en[1] * en[2];
+    const float vol_term = la * (J2m1 / (J + 1.f)) * J;
+    tau[0] = -vol * fmaf(2.f * mu * s0, en[0] / (s0 + 1.f), vol_term);
+    tau[1] = -vol * fmaf(2.f * mu * s1, en[1] / (s1 + 1.f), vol_term);
+    tau[2] = -vol * fmaf(2.f * mu * s2, en[2] / (s2 + 1.f), vol_term);
+  }
+  if (changed) F = sym_mul(sym_from_eig(U, ratio), Ft);
+  else F = Ft;
+  store_sym(sym_from_eig(U, tau), force);
 }
 
 // friction_project (src/mpm_fwd.h:25-57) with base velocity 0 (static level set).
