@@ -78,6 +78,15 @@ struct View {  // raw pointers handed to kernels
 };
 
 // ------------------------------------------------------------------------------ helpers
+// Asynchronous 16-byte global->shared copies (LDGSTS): the gathered particle rows of a tile are
+// put in flight in one batch, no register staging, and waited for once.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 __device__ __forceinline__ void base_rel(float x, float inv_dx, int &base, float &rel) {
   // pos_ = p.pos * inv_delta_x (src/transfer.cpp:490); base = int(x - 0.5f) (src/kernel.h:119-121).
   // Explicit round-to-nearest ops so that no FMA contraction changes the cell assignment.
@@ -315,17 +324,36 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
 #pragma unroll
       for (int e = 0; e < P2G_K * 2; e++) s_hist[e][tid] = 0;
       __syncthreads();
-      // ---- 1+2a: stage rows, per-(pass,warp) cell histograms
+      // ---- 1: stage rows: all gathers of the chunk in flight at once (perm, then 4 x 16 B per row)
+      {
+        uint32_t pidx[P2G_K];
+#pragma unroll
+        for (int k = 0; k < P2G_K; k++) {
+          const int r = k * P2G_T + tid;
+          pidx[k] = r < nrows ? V.perm[cb + r] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < P2G_K; k++) {
+          const int r = k * P2G_T + tid;
+          if (r < nrows) {
+            const int ri = r + (r >> 3);
+            cp_async16(&s_rows[0][ri], &V.q[0][pidx[k]]);
+            cp_async16(&s_rows[1][ri], &V.q[1][pidx[k]]);
+            cp_async16(&s_rows[2][ri], &V.q[2][pidx[k]]);
+            cp_async16(&s_rows[3][ri], &V.q[3][pidx[k]]);
+          }
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+      }
+      // ---- 2a: per-(pass,warp) cell histograms (each thread reads back its own rows)
       uint32_t cr[P2G_K];
 #pragma unroll
       for (int k = 0; k < P2G_K; k++) {
         const int r = k * P2G_T + tid;
         int cell = 64 + warp;  // invalid rows: a private bucket
         if (r < nrows) {
-          const uint32_t p = V.perm[cb + r];
-          const float4 a0 = V.q[0][p], a1 = V.q[1][p], a2 = V.q[2][p], a3 = V.q[3][p];
-          const int ri = r + (r >> 3);
-          s_rows[0][ri] = a0; s_rows[1][ri] = a1; s_rows[2][ri] = a2; s_rows[3][ri] = a3;
+          const float4 a0 = s_rows[0][r + (r >> 3)];
           int bx, by, bz;
           float rr;
           base_rel(a0.x, P.inv_dx, bx, rr);
@@ -456,25 +484,23 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
 // ------------------------------------------------------------------------------ grid node
 // Momentum/mass of global node g = fixed-order sum of the arenas that cover it:
 // owner tile T=(g>>2) holds it at local l=g&3; tile T-o (o in {0,1}^3) holds it at l+4o (needs l<=1).
+// Branch-free: absent contributions read the all-zero arena `zero_slot`, so the 8 loads are
+// independent and issue back to back.
 template <class SlotOf>
-__device__ __forceinline__ float4 gather_node(const float4 *arena, int lx, int ly, int lz, SlotOf slot_of) {
+__device__ __forceinline__ float4 gather_node(const float4 *arena, int zero_slot, int lx, int ly, int lz, SlotOf slot_of) {
+  float4 a[8];
+#pragma unroll
+  for (int o = 0; o < 8; o++) {
+    const int ox = o >> 2, oy = (o >> 1) & 1, oz = o & 1;
+    int slot = slot_of(ox, oy, oz);
+    const bool covered = !(ox && lx > 1) && !(oy && ly > 1) && !(oz && lz > 1);
+    if (!covered || slot < 0) slot = zero_slot;
+    const int idx = covered ? ((lx + 4 * ox) * 6 + (ly + 4 * oy)) * 6 + (lz + 4 * oz) : 0;
+    a[o] = arena[(size_t)slot * ARENA + idx];
+  }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int ox = 0; ox < 2; ox++) {
-    if (ox && lx > 1) continue;
-#pragma unroll
-    for (int oy = 0; oy < 2; oy++) {
-      if (oy && ly > 1) continue;
-#pragma unroll
-      for (int oz = 0; oz < 2; oz++) {
-        if (oz && lz > 1) continue;
-        int slot = slot_of(ox, oy, oz);
-        if (slot < 0) continue;
-        float4 a = arena[(size_t)slot * ARENA + ((lx + 4 * ox) * 6 + (ly + 4 * oy)) * 6 + (lz + 4 * oz)];
-        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-      }
-    }
-  }
+  for (int o = 0; o < 8; o++) { acc.x += a[o].x; acc.y += a[o].y; acc.z += a[o].z; acc.w += a[o].w; }
   return acc;
 }
 
@@ -504,16 +530,41 @@ __device__ __forceinline__ float4 node_update(const Params &P, const float4 *sdf
 // MPM<3>::resample_optimized / block_op_normal (src/transfer.cpp:837-954) + Particle::plasticity +
 // clear_boundary_particles (src/mpm.cpp:583-633); produces the affine matrix of the NEXT rasterize
 // (calculate_force of the updated state) and the next substep's sort key.
+constexpr int G2P_CH = 512;  // particles staged per chunk
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P) {
   __shared__ float4 s_vel[ARENA];
   __shared__ int s_nb[27];
+  __shared__ float4 s_in[4][G2P_CH];
+  constexpr int KPT = G2P_CH / BLOCK;
   const int tid = threadIdx.x;
   const int n_tiles = V.cnt->n_tiles;
   const float scale = -4.0f * P.inv_dx * P.dt;  // src/transfer.cpp:938
+  // gathers the G2P set (x|mass, F, scalar|vol|tag: 64 B/particle) of one chunk into shared memory
+  auto stage = [&](int cb, int nrows) {
+    uint32_t pidx[KPT];
+#pragma unroll
+    for (int k = 0; k < KPT; k++) {
+      const int r = k * BLOCK + tid;
+      pidx[k] = r < nrows ? V.perm[cb + r] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < KPT; k++) {
+      const int r = k * BLOCK + tid;
+      if (r < nrows) {
+        cp_async16(&s_in[0][r], &V.q[0][pidx[k]]);
+        cp_async16(&s_in[1][r], &V.q[4][pidx[k]]);
+        cp_async16(&s_in[2][r], &V.q[5][pidx[k]]);
+        cp_async16(&s_in[3][r], &V.q[6][pidx[k]]);
+      }
+    }
+    cp_async_commit();
+  };
   for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
     const int tile = V.tile_id[slot];
     const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
+    const int begin = V.tile_begin[slot], end = V.tile_end[slot];
+    stage(begin, min(G2P_CH, end - begin));  // in flight while the grid nodes are rebuilt
     if (tid < 27) {
       int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
       int x = tx + ox, y = ty + oy, z = tz + oz;
@@ -526,85 +577,89 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P) {
       int a = n / 36, b = (n / 6) % 6, c = n % 6;
       int wx_ = a >> 2, wy_ = b >> 2, wz_ = c >> 2;  // owner tile offset (0/1)
       int lx = a & 3, ly = b & 3, lz = c & 3;
-      float4 g = gather_node(V.arena, lx, ly, lz, [&](int ox, int oy, int oz) {
+      float4 g = gather_node(V.arena, V.cap_tiles, lx, ly, lz, [&](int ox, int oy, int oz) {
         return s_nb[(wx_ - ox + 1) * 9 + (wy_ - oy + 1) * 3 + (wz_ - oz + 1)];
       });
       s_vel[n] = node_update(P, V.sdf4, g, tx * 4 + a, ty * 4 + b, tz * 4 + c);
     }
-    __syncthreads();
-    const int begin = V.tile_begin[slot], end = V.tile_end[slot];
-    for (int j = begin + tid; j < end; j += BLOCK) {
-      const uint32_t p = V.perm[j];
-      const float4 q0 = V.q[0][p], q4 = V.q[4][p], q5 = V.q[5][p], q6 = V.q[6][p];
-      const float mass = q0.w, vol = q6.z;
-      const uint32_t tag = __float_as_uint(q6.w);
-      const Material &mat = P.mats[tag >> 26];
-      int bx, by, bz;
-      float rx, ry, rz;
-      base_rel(q0.x, P.inv_dx, bx, rx);
-      base_rel(q0.y, P.inv_dx, by, ry);
-      base_rel(q0.z, P.inv_dx, bz, rz);
-      bx -= tx * 4; by -= ty * 4; bz -= tz * 4;
-      float wx[3], wy[3], wz[3];
-      bspline_weights(rx, wx);
-      bspline_weights(ry, wy);
-      bspline_weights(rz, wz);
-      // v = sum w g ; b = sum w g (x) (rel - node) = v (x) rel - [sum_i i S_i | sum_j j T_j | sum_k k R_k]
-      // (src/transfer.cpp:888-904), evaluated slab by slab: ~250 FMA instead of 27*16.
-      const float wz2x = 2.0f * wz[2], wy2x = 2.0f * wy[2], wx2x = 2.0f * wx[2];
-      float3 v = make_float3(0.f, 0.f, 0.f), colx = v, coly = v, colz = v;
+    for (int cb = begin; cb < end; cb += G2P_CH) {
+      const int nrows = min(G2P_CH, end - cb);
+      if (cb != begin) stage(cb, nrows);
+      cp_async_wait_all();
+      __syncthreads();
+      for (int r = tid; r < nrows; r += BLOCK) {
+        const int j = cb + r;
+        const size_t o = V.sorted_pos[j];  // (tile,cell)-sorted output position, consumed by the stores below
+        const float4 q0 = s_in[0][r], q4 = s_in[1][r], q5 = s_in[2][r], q6 = s_in[3][r];
+        const float mass = q0.w, vol = q6.z;
+        const uint32_t tag = __float_as_uint(q6.w);
+        const Material &mat = P.mats[tag >> 26];
+        int bx, by, bz;
+        float rx, ry, rz;
+        base_rel(q0.x, P.inv_dx, bx, rx);
+        base_rel(q0.y, P.inv_dx, by, ry);
+        base_rel(q0.z, P.inv_dx, bz, rz);
+        bx -= tx * 4; by -= ty * 4; bz -= tz * 4;
+        float wx[3], wy[3], wz[3];
+        bspline_weights(rx, wx);
+        bspline_weights(ry, wy);
+        bspline_weights(rz, wz);
+        // v = sum w g ; b = sum w g (x) (rel - node) = v (x) rel - [sum_i i S_i | sum_j j T_j | sum_k k R_k]
+        // (src/transfer.cpp:888-904), evaluated slab by slab: ~250 FMA instead of 27*16.
+        const float wz2x = 2.0f * wz[2], wy2x = 2.0f * wy[2], wx2x = 2.0f * wx[2];
+        float3 v = make_float3(0.f, 0.f, 0.f), colx = v, coly = v, colz = v;
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        float3 pi = make_float3(0.f, 0.f, 0.f), jy = pi, kz = pi;
+        for (int i = 0; i < 3; i++) {
+          float3 pi = make_float3(0.f, 0.f, 0.f), jy = pi, kz = pi;
 #pragma unroll
-        for (int jn = 0; jn < 3; jn++) {
-          const int row = ((bx + i) * 6 + (by + jn)) * 6 + bz;
-          const float4 g0 = s_vel[row], g1 = s_vel[row + 1], g2 = s_vel[row + 2];
-          float3 a, c;
-          a.x = fmaf(wz[2], g2.x, fmaf(wz[1], g1.x, wz[0] * g0.x));
-          a.y = fmaf(wz[2], g2.y, fmaf(wz[1], g1.y, wz[0] * g0.y));
-          a.z = fmaf(wz[2], g2.z, fmaf(wz[1], g1.z, wz[0] * g0.z));
-          c.x = fmaf(wz2x, g2.x, wz[1] * g1.x);
-          c.y = fmaf(wz2x, g2.y, wz[1] * g1.y);
-          c.z = fmaf(wz2x, g2.z, wz[1] * g1.z);
-          pi.x = fmaf(wy[jn], a.x, pi.x); pi.y = fmaf(wy[jn], a.y, pi.y); pi.z = fmaf(wy[jn], a.z, pi.z);
-          kz.x = fmaf(wy[jn], c.x, kz.x); kz.y = fmaf(wy[jn], c.y, kz.y); kz.z = fmaf(wy[jn], c.z, kz.z);
-          if (jn > 0) {
-            const float wj = jn == 1 ? wy[1] : wy2x;
-            jy.x = fmaf(wj, a.x, jy.x); jy.y = fmaf(wj, a.y, jy.y); jy.z = fmaf(wj, a.z, jy.z);
+          for (int jn = 0; jn < 3; jn++) {
+            const int row = ((bx + i) * 6 + (by + jn)) * 6 + bz;
+            const float4 g0 = s_vel[row], g1 = s_vel[row + 1], g2 = s_vel[row + 2];
+            float3 a, c;
+            a.x = fmaf(wz[2], g2.x, fmaf(wz[1], g1.x, wz[0] * g0.x));
+            a.y = fmaf(wz[2], g2.y, fmaf(wz[1], g1.y, wz[0] * g0.y));
+            a.z = fmaf(wz[2], g2.z, fmaf(wz[1], g1.z, wz[0] * g0.z));
+            c.x = fmaf(wz2x, g2.x, wz[1] * g1.x);
+            c.y = fmaf(wz2x, g2.y, wz[1] * g1.y);
+            c.z = fmaf(wz2x, g2.z, wz[1] * g1.z);
+            pi.x = fmaf(wy[jn], a.x, pi.x); pi.y = fmaf(wy[jn], a.y, pi.y); pi.z = fmaf(wy[jn], a.z, pi.z);
+            kz.x = fmaf(wy[jn], c.x, kz.x); kz.y = fmaf(wy[jn], c.y, kz.y); kz.z = fmaf(wy[jn], c.z, kz.z);
+            if (jn > 0) {
+              const float wj = jn == 1 ? wy[1] : wy2x;
+              jy.x = fmaf(wj, a.x, jy.x); jy.y = fmaf(wj, a.y, jy.y); jy.z = fmaf(wj, a.z, jy.z);
+            }
+          }
+          v.x = fmaf(wx[i], pi.x, v.x); v.y = fmaf(wx[i], pi.y, v.y); v.z = fmaf(wx[i], pi.z, v.z);
+          coly.x = fmaf(wx[i], jy.x, coly.x); coly.y = fmaf(wx[i], jy.y, coly.y); coly.z = fmaf(wx[i], jy.z, coly.z);
+          colz.x = fmaf(wx[i], kz.x, colz.x); colz.y = fmaf(wx[i], kz.y, colz.y); colz.z = fmaf(wx[i], kz.z, colz.z);
+          if (i > 0) {
+            const float wi = i == 1 ? wx[1] : wx2x;
+            colx.x = fmaf(wi, pi.x, colx.x); colx.y = fmaf(wi, pi.y, colx.y); colx.z = fmaf(wi, pi.z, colx.z);
           }
         }
-        v.x = fmaf(wx[i], pi.x, v.x); v.y = fmaf(wx[i], pi.y, v.y); v.z = fmaf(wx[i], pi.z, v.z);
-        coly.x = fmaf(wx[i], jy.x, coly.x); coly.y = fmaf(wx[i], jy.y, coly.y); coly.z = fmaf(wx[i], jy.z, coly.z);
-        colz.x = fmaf(wx[i], kz.x, colz.x); colz.y = fmaf(wx[i], kz.y, colz.y); colz.z = fmaf(wx[i], kz.z, colz.z);
-        if (i > 0) {
-          const float wi = i == 1 ? wx[1] : wx2x;
-          colx.x = fmaf(wi, pi.x, colx.x); colx.y = fmaf(wi, pi.y, colx.y); colx.z = fmaf(wi, pi.z, colx.z);
-        }
-      }
-      Mat3 B;
-      B.m[0] = fmaf(v.x, rx, -colx.x); B.m[1] = fmaf(v.y, rx, -colx.y); B.m[2] = fmaf(v.z, rx, -colx.z);
-      B.m[3] = fmaf(v.x, ry, -coly.x); B.m[4] = fmaf(v.y, ry, -coly.y); B.m[5] = fmaf(v.z, ry, -coly.z);
-      B.m[6] = fmaf(v.x, rz, -colz.x); B.m[7] = fmaf(v.y, rz, -colz.y); B.m[8] = fmaf(v.z, rz, -colz.z);
-      Mat3 cdg;  // cdg = I + (-4 inv_dx dt) b   (src/transfer.cpp:938-942)
+        Mat3 B;
+        B.m[0] = fmaf(v.x, rx, -colx.x); B.m[1] = fmaf(v.y, rx, -colx.y); B.m[2] = fmaf(v.z, rx, -colx.z);
+        B.m[3] = fmaf(v.x, ry, -coly.x); B.m[4] = fmaf(v.y, ry, -coly.y); B.m[5] = fmaf(v.z, ry, -coly.z);
+        B.m[6] = fmaf(v.x, rz, -colz.x); B.m[7] = fmaf(v.y, rz, -colz.y); B.m[8] = fmaf(v.z, rz, -colz.z);
+        Mat3 cdg;  // cdg = I + (-4 inv_dx dt) b   (src/transfer.cpp:938-942)
 #pragma unroll
-      for (int k = 0; k < 9; k++) cdg.m[k] = fmaf(scale, B.m[k], (k % 4 == 0) ? 1.f : 0.f);
-      Mat3 F;
-      F.m[0] = q4.x; F.m[1] = q4.y; F.m[2] = q4.z; F.m[3] = q4.w; F.m[4] = q5.x; F.m[5] = q5.y; F.m[6] = q5.z; F.m[7] = q5.w; F.m[8] = q6.x;
-      float ps = q6.y;
-      Mat3 force, A;
-      material_step(mat, cdg, F, ps, vol, force);
-      make_affine(force, B, mass, scale, A);
-      float3 x = make_float3(fmaf(v.x, P.dt, q0.x), fmaf(v.y, P.dt, q0.y), fmaf(v.z, P.dt, q0.z));  // 951
-      uint32_t key = make_key(P, x.x, x.y, x.z);
-      if (P.clean_boundary && reference_deletes(P, x, v)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
-      if (!(isfinite(x.x) && isfinite(x.y) && isfinite(x.z))) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
-      // write at the (tile,cell)-sorted position: storage order follows the sort
-      const size_t o = V.sorted_pos[j];
-      store_particle(V.qn, o, x, mass, v, A, F, ps, vol, tag, B);
-      V.keys_next[o] = key;
+        for (int k = 0; k < 9; k++) cdg.m[k] = fmaf(scale, B.m[k], (k % 4 == 0) ? 1.f : 0.f);
+        Mat3 F;
+        F.m[0] = q4.x; F.m[1] = q4.y; F.m[2] = q4.z; F.m[3] = q4.w; F.m[4] = q5.x; F.m[5] = q5.y; F.m[6] = q5.z; F.m[7] = q5.w; F.m[8] = q6.x;
+        float ps = q6.y;
+        Mat3 force, A;
+        material_step(mat, cdg, F, ps, vol, force);
+        make_affine(force, B, mass, scale, A);
+        float3 x = make_float3(fmaf(v.x, P.dt, q0.x), fmaf(v.y, P.dt, q0.y), fmaf(v.z, P.dt, q0.z));  // 951
+        uint32_t key = make_key(P, x.x, x.y, x.z);
+        if (P.clean_boundary && reference_deletes(P, x, v)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
+        if (!(isfinite(x.x) && isfinite(x.y) && isfinite(x.z))) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
+        // write at the (tile,cell)-sorted position: storage order follows the sort
+        store_particle(V.qn, o, x, mass, v, A, F, ps, vol, tag, B);
+        V.keys_next[o] = key;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -614,7 +669,7 @@ __global__ void k_dense_grid(View V, Params P, int which, float4 *dense) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int gz = (int)(i % P.nnode[2]), gy = (int)((i / P.nnode[2]) % P.nnode[1]), gx = (int)(i / ((size_t)P.nnode[2] * P.nnode[1]));
     int tx = gx >> 2, ty = gy >> 2, tz = gz >> 2;
-    float4 g = gather_node(V.arena, gx & 3, gy & 3, gz & 3, [&](int ox, int oy, int oz) {
+    float4 g = gather_node(V.arena, V.cap_tiles, gx & 3, gy & 3, gz & 3, [&](int ox, int oy, int oz) {
       int x = tx - ox, y = ty - oy, z = tz - oz;
       if (x < 0 || y < 0 || z < 0 || x >= P.nt[0] || y >= P.nt[1] || z >= P.nt[2]) return -1;
       return V.slot_map[(x * P.nt[1] + y) * P.nt[2] + z];
@@ -859,7 +914,8 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
   if (cudaMalloc(&h->tile_begin, sizeof(int) * cap_tiles) != cudaSuccess) return bail("cudaMalloc tile_begin");
   if (cudaMalloc(&h->tile_end, sizeof(int) * cap_tiles) != cudaSuccess) return bail("cudaMalloc tile_end");
   if (cudaMalloc(&h->slot_map, sizeof(int) * ntot) != cudaSuccess) return bail("cudaMalloc slot_map");
-  if (cudaMalloc(&h->arena, sizeof(float4) * ARENA * cap_tiles) != cudaSuccess) return bail("cudaMalloc arena");
+  if (cudaMalloc(&h->arena, sizeof(float4) * ARENA * (cap_tiles + 1)) != cudaSuccess) return bail("cudaMalloc arena");
+  cudaMemset(h->arena + (size_t)ARENA * cap_tiles, 0, sizeof(float4) * ARENA);  // the all-zero arena read for absent neighbours
   if (cudaMalloc(&h->cnt, sizeof(Counters)) != cudaSuccess) return bail("cudaMalloc counters");
   cudaMemset(h->slot_map, 0xFF, sizeof(int) * ntot);
   cudaMemset(h->cnt, 0, sizeof(Counters));

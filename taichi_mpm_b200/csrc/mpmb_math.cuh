@@ -29,6 +29,13 @@ struct Sym3 {  // symmetric 3x3
   float xx, yy, zz, xy, xz, yz;
 };
 
+// MUFU.RSQ without the denormal pre-scaling sequence rsqrtf() expands to.
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // One cyclic Jacobi rotation annihilating a_pq; (app,aqq,apq) the 2x2 pivot, (arp,arq) the
 // remaining off-diagonals, v*p/v*q the eigenvector columns p and q.
 // Half-angle form with two MUFU.RSQ and no division:
@@ -39,13 +46,13 @@ __device__ __forceinline__ void jacobi_rotate(float &app, float &aqq, float &apq
   const float d = aqq - app;
   const float b = 2.0f * apq;
   const float h2 = fmaf(d, d, b * b);
-  const float inv_h = h2 > 0.0f ? rsqrtf(h2) : 0.0f;
+  const float inv_h = h2 > 1e-36f ? rsqrt_fast(h2) : 0.0f;
   const float c2 = fmaf(0.5f * fabsf(d), inv_h, 0.5f);  // in [0.5,1]; h2 == 0 -> 0.5 with s = 0 below (A already diagonal here)
-  float rc = rsqrtf(c2);
+  float rc = rsqrt_fast(c2);
   rc = rc * fmaf(-0.5f * c2, rc * rc, 1.5f);  // one Newton step: c,s orthonormal to fp32 round-off
   float c = c2 * rc;
   float s = copysignf(0.5f, d) * b * inv_h * rc;
-  if (!(h2 > 0.0f)) { c = 1.0f; s = 0.0f; rc = 1.0f; }
+  if (!(h2 > 1e-36f)) { c = 1.0f; s = 0.0f; rc = 1.0f; }
   const float t = s * rc;
   app = fmaf(-t, apq, app);
   aqq = fmaf(t, apq, aqq);
