@@ -110,6 +110,44 @@ def build_workload(name, scale):
     return cfg
 
 
+def build_slab_workload(name, scale, rank, world):
+    """This rank's share of the weak-scaling version of a config: grid res x res x (res*world), block
+    cells x cells x (cells_z*world), cut into `world` z-slabs of equal particle count at tile layers."""
+    from taichi_mpm_b200 import slab
+    base = scenes.config(name, scale)
+    sc = dict(base["scene"])
+    res = sc["res"][0]
+    x0 = base["state"]["x"]
+    dx = sc["dx"]
+    lo = np.floor(x0.min(0) / dx + 1e-3).astype(np.int64)
+    hi = np.ceil(x0.max(0) / dx - 1e-3).astype(np.int64)
+    cells_z = int(hi[2] - lo[2])
+    zc_lo = (res * world - cells_z * world) // 2
+    sc["res"] = (res, res, res * world)
+    n_layers = slab.tile_layers(res * world)
+    # 1-D histogram of the base tile layer along z (all columns are statistically identical)
+    zs = (np.arange(zc_lo, zc_lo + cells_z * world)[:, None] + 0.5 + np.array([-0.25, 0.25])[None]).reshape(-1) * dx
+    cuts = slab.slab_partition(slab.base_tile_z(zs, dx), n_layers, world)
+    z0, z1 = cuts[rank]
+    # generate only the cells that can belong to this slab (+-2 cells), then keep what it owns
+    c_lo = max(zc_lo, z0 * 4 - 2)
+    c_hi = min(zc_lo + cells_z * world, z1 * 4 + 3)
+    xs, mass, vol = scenes.lattice_block(res, (lo[0], lo[1], c_lo), (hi[0], hi[1], c_hi), jitter=0.05, seed=20260922 + rank)
+    tz = slab.base_tile_z(xs[:, 2], dx)
+    keep = (tz >= z0) & (tz < z1)
+    st = scenes.make_state(xs[keep], mass[keep], vol[keep], base["meta"]["kind"])
+    import torch
+    import torch.distributed as dist
+    t = torch.zeros(world, dtype=torch.int64, device="cuda")
+    t[rank] = int(keep.sum())
+    dist.all_reduce(t)
+    counts = t.cpu().numpy()
+    meta = dict(base["meta"])
+    meta["res"] = res
+    cfg = dict(scene=sc, state=st, meta=meta)
+    return cfg, st, (z0, z1), int(counts.sum()), int(counts[:rank].sum())
+
+
 def cpu_run(cfg, n_particles_cap, budget_s, min_substeps=1, threads=None):
     """Times the oracle's OpenMP fast path on (a sub-block of) the workload."""
     from oracle import pyoracle as O
@@ -182,11 +220,11 @@ def run_reference(args):
 
 def workload_config(args, cfg, n_particles):
     m = cfg["meta"]
-    return {"workload": "%s: %d^3 grid, %d particles, %s, dt=%g, floor plane friction %g" % (
-        m["name"], m["res"], n_particles, ["linear", "jelly", "snow", "water", "sand"][m["kind"]], cfg["scene"]["dt"],
+    return {"workload": "%s: %s grid, %d particles, %s, dt=%g, floor plane friction %g" % (
+        m["name"], "x".join(str(r) for r in cfg["scene"]["res"]), n_particles, ["linear", "jelly", "snow", "water", "sand"][m["kind"]], cfg["scene"]["dt"],
         cfg["scene"]["friction"]),
         "l2": "inputs larger than L2 (particle state %.0f MB per buffer vs 126 MB L2)" % (n_particles * 112 / 1e6),
-        "parallelism": "1 GPU" if args.gpus == 1 else "z-slab x%d" % args.gpus}
+        "parallelism": "1 GPU" if args.gpus == 1 else "z-slab x%d (weak scaling: block and grid extended along z, one config-sized share per GPU)" % args.gpus}
 
 
 def run_ours(args):
@@ -202,16 +240,25 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
-    cfg = build_workload(args.workload, args.scale)
-    st, sc = cfg["state"], cfg["scene"]
+    from taichi_mpm_b200 import slab
+    if world == 1:
+        cfg = build_workload(args.workload, args.scale)
+        st, sc = cfg["state"], cfg["scene"]
+        eng = capi.Engine(sc["res"], sc["dx"], sc["dt"], sc["gravity"], sc["particle_gravity"], True, device=local)
+        n_total = len(st["x"])
+    else:
+        # weak scaling: the block and the domain grow along z with the rank count, every rank owns one
+        # config-sized share of a CONTIGUOUS block, so slab faces cut through the material
+        cfg, st, (z0, z1), n_total, id_base = build_slab_workload(args.workload, args.scale, rank, world)
+        sc = cfg["scene"]
+        eng = capi.Engine(sc["res"], sc["dx"], sc["dt"], sc["gravity"], sc["particle_gravity"], True, device=local, rank=rank, world=world,
+                          tile_z0=z0, tile_z1=z1, migrate_capacity=args.migrate_capacity, halo_capacity=args.halo_capacity)
+        eng.set_id_base(id_base)
     kind = cfg["meta"]["kind"]
-    if world > 1:
-        raise SystemExit("z-slab multi-GPU path is not built yet (DESIGN.md §7)")
     n = len(st["x"])
-
-    eng = capi.Engine(sc["res"], sc["dx"], sc["dt"], sc["gravity"], sc["particle_gravity"], True, device=local)
     stream = torch.cuda.current_stream(dev)
     eng.set_stream(stream.cuda_stream)
+    runner = slab.SlabRunner(slab.EngineAdapter(eng), rank, world, dev, dist=dist if world > 1 else None)
     eng.set_material(0, kind, sc["mat_params"][0])
     if sc["planes"] is not None:
         eng.set_planes(sc["planes"], sc["friction"])
@@ -243,8 +290,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    substep = (lambda k: eng.substep(k)) if world == 1 else (lambda k: runner.substep(k))
     # ---- device-resident throughput
-    eng.substep(args.warmup)
+    substep(args.warmup)
     barrier()
     c0 = eng.get_counters()
     eng.set_profiling(True)
@@ -254,7 +302,7 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    eng.substep(args.steps)
+    substep(args.steps)
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -267,6 +315,12 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        t = torch.tensor([float(alive), float(c1["kernel_launches"] - c0["kernel_launches"])], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        alive = int(t[0].item())
+        total_launches = int(t[1].item())
+    else:
+        total_launches = c1["kernel_launches"] - c0["kernel_launches"]
     value = alive * args.steps / (ms * 1e-3) / 1e6
 
     # ---- end to end through host buffers: frames of upload + substeps + download
@@ -274,21 +328,31 @@ def run_ours(args):
     n_alive = alive
     if args.frames > 0:
         upload()
-        eng.substep(3)
+        substep(3)
         download()
     t_e2e = []
     for _ in range(args.frames):
         barrier()
         t0 = time.perf_counter()
         upload()
-        eng.substep(frame_substeps)
+        substep(frame_substeps)
         n_alive = download()
         barrier()
         t_e2e.append(time.perf_counter() - t0)
+    if world > 1 and t_e2e:
+        t = torch.tensor([float(n_alive)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n_alive = int(t.item())
+        t = torch.tensor([float(np.mean(t_e2e))], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = [float(t.item())]
     e2e_s = float(np.mean(t_e2e)) if t_e2e else float("nan")
     e2e_value = n_alive * frame_substeps / e2e_s / 1e6 if t_e2e else None
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     peaks, peak_kind = measured_peaks()
     peak = float(peaks["hbm_gbs"])
@@ -296,7 +360,8 @@ def run_ours(args):
     kms = {"p2g": stage_ms[1] / max(args.steps, 1), "g2p": stage_ms[2] / max(args.steps, 1)}
     dom = max(kms, key=kms.get)
     kb = P2G_BYTES[kind] if dom == "p2g" else BYTES_PER_UPDATE[kind] - P2G_BYTES[kind]
-    achieved = kb * alive / (kms[dom] * 1e-3) / 1e9
+    alive_local = c1["alive"]  # the profiled kernels are this rank's: its own particle count
+    achieved = kb * alive_local / (kms[dom] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
@@ -306,9 +371,9 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
-                "algorithmic_bytes_per_launch": kb * alive, "kernel_ms": kms[dom],
-                "substep": {"bytes_per_update": BYTES_PER_UPDATE[kind], "achieved": BYTES_PER_UPDATE[kind] * value * 1e6 / 1e9,
-                            "frac": BYTES_PER_UPDATE[kind] * value * 1e6 / 1e9 / peak},
+                "algorithmic_bytes_per_launch": kb * alive_local, "kernel_ms": kms[dom],
+                "substep": {"bytes_per_update": BYTES_PER_UPDATE[kind], "achieved": BYTES_PER_UPDATE[kind] * value * 1e6 / 1e9 / world,
+                            "frac": BYTES_PER_UPDATE[kind] * value * 1e6 / 1e9 / world / peak, "note": "per GPU"},
                 "stage_ms_per_step": {STAGE_NAMES[i]: stage_ms[i] / max(args.steps, 1) for i in range(4)}}
 
     cpu = None
@@ -321,16 +386,20 @@ def run_ours(args):
     line = {
         "metric": "million particle-updates/s", "value": value, "unit": "M particle-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, n),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, n_total),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "M particle-updates/s", "h2d_bytes_per_step": h2d / frame_substeps,
                 "d2h_bytes_per_step": d2h / frame_substeps, "frame_substeps": frame_substeps, "frames": args.frames,
                 "frame_seconds": e2e_s},
-        "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+        "gpu_launches": total_launches,
         "alive_particles": alive, "active_tiles": c1["active_tiles"],
     }
+    if world > 1:
+        line["exchange"] = {"bytes_sent_per_step_rank0": runner.bytes_sent / max(1, args.warmup + args.steps + 3 + args.frames * frame_substeps),
+                            "transport": "torch.distributed NCCL point-to-point (batch_isend_irecv), fixed-size messages"}
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -346,6 +415,8 @@ def main():
     ap.add_argument("--frames", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--migrate-capacity", type=int, default=16384, help="particles per face per substep (z-slab message size)")
+    ap.add_argument("--halo-capacity", type=int, default=2048, help="active tiles per boundary layer (z-slab message size)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -74,7 +74,8 @@ typedef struct MpmbConfig {
   int32_t rank, world;
   int32_t tile_z0, tile_z1;
   int64_t migrate_capacity;  /* max particles leaving through one face per substep (world>1)      */
-  int32_t reserved[8];       /* must be 0                                                         */
+  int32_t halo_capacity;     /* max active tiles in one boundary layer; 0 = the whole cross-section */
+  int32_t reserved[7];       /* must be 0                                                         */
 } MpmbConfig;
 
 /* Byte offsets of the fields of one reference particle slot (ParticleContainer<3>, 320 B,
@@ -124,6 +125,9 @@ int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float 
  * default, group 0).  Replaces the resident set.  Particle k gets id k.                           */
 int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *v, const float *F, const float *b,
                           const float *mass, const float *vol, const float *scalar, const int32_t *group);
+/* Particle k of the next upload gets id `base + k` (default 0); z-slab ranks use disjoint ranges so
+ * that ids stay unique after migration.  Ids must stay below 2^26.                                 */
+int mpmb_set_id_base(MpmbHandle h, int64_t base);
 /* Same, reading the reference's own AoS pool: slot indices[k] of `pool` (ParticleAllocator::pool,
  * src/particle_allocator.h:39; MPM::particles index vector, src/mpm.h:116).  group[k] may be NULL. */
 int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slots, const uint32_t *indices,

@@ -20,7 +20,7 @@ MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, 
 # every symbol include/mpmb.h declares
 EXPORTS = [
     "mpmb_create", "mpmb_destroy", "mpmb_last_error", "mpmb_version", "mpmb_set_stream", "mpmb_synchronize",
-    "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes",
+    "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes", "mpmb_set_id_base",
     "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_num_particles", "mpmb_download_particles", "mpmb_download_aos",
     "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_download_grid",
     "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters",
@@ -43,7 +43,8 @@ class MpmbConfig(C.Structure):
         ("tile_z0", C.c_int32),
         ("tile_z1", C.c_int32),
         ("migrate_capacity", C.c_int64),
-        ("reserved", C.c_int32 * 8),
+        ("halo_capacity", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -74,6 +75,8 @@ def lib():
         L.mpmb_last_error.argtypes = [C.c_void_p]
         L.mpmb_halo_bytes.restype = C.c_int64
         L.mpmb_migrate_bytes.restype = C.c_int64
+        L.mpmb_halo_bytes.argtypes = [C.c_void_p]
+        L.mpmb_migrate_bytes.argtypes = [C.c_void_p]
         L.mpmb_create.argtypes = [C.POINTER(MpmbConfig), C.POINTER(C.c_void_p)]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError if a declared symbol is not exported
@@ -104,7 +107,7 @@ class Engine:
     """Thin object wrapper over one MpmbHandle."""
 
     def __init__(self, res, dx, dt, gravity=(0.0, -10.0, 0.0), particle_gravity=True, clean_boundary=True, device=0,
-                 capacity=0, rank=0, world=1, tile_z0=0, tile_z1=0, migrate_capacity=0):
+                 capacity=0, rank=0, world=1, tile_z0=0, tile_z1=0, migrate_capacity=0, halo_capacity=0):
         self.L = lib()
         cfg = MpmbConfig()
         if np.isscalar(res):
@@ -118,6 +121,7 @@ class Engine:
         cfg.capacity = int(capacity)
         cfg.rank, cfg.world, cfg.tile_z0, cfg.tile_z1 = int(rank), int(world), int(tile_z0), int(tile_z1)
         cfg.migrate_capacity = int(migrate_capacity)
+        cfg.halo_capacity = int(halo_capacity)
         self.res = tuple(int(r) for r in res)
         self.cfg = cfg
         self.h = C.c_void_p()
@@ -161,6 +165,9 @@ class Engine:
     def set_planes(self, planes4, friction):
         planes4 = _f32(planes4).reshape(-1, 4)
         self._check(self.L.mpmb_set_planes(self.h, C.c_int32(len(planes4)), _ptr(planes4), C.c_float(friction)))
+
+    def set_id_base(self, base):
+        self._check(self.L.mpmb_set_id_base(self.h, C.c_int64(int(base))))
 
     # --- particles
     def upload(self, x, v, mass, vol, F=None, b=None, scalar=None, group=None):
@@ -238,6 +245,25 @@ class Engine:
         g = np.zeros(tuple(r + 1 for r in self.res) + (4,), np.float32)
         self._check(self.L.mpmb_download_grid(self.h, C.c_int32(which), _ptr(g)))
         return g
+
+    # --- z-slab exchange (device pointers owned by the caller)
+    def halo_bytes(self):
+        return int(self.L.mpmb_halo_bytes(self.h))
+
+    def migrate_bytes(self):
+        return int(self.L.mpmb_migrate_bytes(self.h))
+
+    def halo_pack(self, face, dev_ptr):
+        self._check(self.L.mpmb_halo_pack(self.h, C.c_int32(face), C.c_void_p(int(dev_ptr))))
+
+    def halo_unpack(self, face, dev_ptr):
+        self._check(self.L.mpmb_halo_unpack(self.h, C.c_int32(face), C.c_void_p(int(dev_ptr))))
+
+    def migrate_pack(self, face, dev_ptr):
+        self._check(self.L.mpmb_migrate_pack(self.h, C.c_int32(face), C.c_void_p(int(dev_ptr))))
+
+    def migrate_unpack(self, face, dev_ptr):
+        self._check(self.L.mpmb_migrate_unpack(self.h, C.c_int32(face), C.c_void_p(int(dev_ptr))))
 
     # --- profiling
     def set_profiling(self, enabled):

@@ -57,8 +57,8 @@ struct Counters {  // device-resident
   int n_tiles;
   int n_ghost;      // ghost tiles appended after the owned ones (world>1)
   int error;        // sticky device-side error flags
-  int mig_count[2]; // particles packed for face 0 / 1
-  int pad[2];
+  int mig_in;       // particles appended by mpmb_migrate_unpack since the last sort
+  int pad[3];
 };
 enum { DEVERR_TILE_CAPACITY = 1, DEVERR_MIGRATE_CAPACITY = 2, DEVERR_PARTICLE_CAPACITY = 4 };
 
@@ -149,18 +149,18 @@ __global__ void k_iota(uint32_t *a, int n) {
   if (i < n) a[i] = (uint32_t)i;
 }
 
-__device__ __forceinline__ void pack_one(View &V, const Params &P, int i, float3 x, float3 v, Mat3 F, Mat3 b, float mass, float vol, float ps,
+__device__ __forceinline__ void pack_one(View &V, const Params &P, int i, uint32_t id_base, float3 x, float3 v, Mat3 F, Mat3 b, float mass, float vol, float ps,
                                          int g, uint32_t *keys) {
   Mat3 force, A;
   calculate_force(P.mats[g], F, ps, vol, force);
   make_affine(force, b, mass, -4.0f * P.inv_dx * P.dt, A);
-  store_particle(V.q, (size_t)i, x, mass, v, A, F, ps, vol, ((uint32_t)g << 26) | (uint32_t)i, b);
+  store_particle(V.q, (size_t)i, x, mass, v, A, F, ps, vol, ((uint32_t)g << 26) | (id_base + (uint32_t)i), b);
   keys[i] = make_key(P, x.x, x.y, x.z);
 }
 
 // Field-wise host arrays (staged on the device) -> q streams.
 __global__ void k_pack_particles(View V, Params P, int n, const float *x, const float *v, const float *F, const float *b,
-                                 const float *mass, const float *vol, const float *scalar, const int *group, uint32_t *keys) {
+                                 const float *mass, const float *vol, const float *scalar, const int *group, uint32_t *keys, uint32_t id_base) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Mat3 f, bb;
@@ -178,12 +178,12 @@ __global__ void k_pack_particles(View V, Params P, int n, const float *x, const 
   }
   float3 xx = make_float3(x[3 * (size_t)i], x[3 * (size_t)i + 1], x[3 * (size_t)i + 2]);
   float3 vv = make_float3(v[3 * (size_t)i], v[3 * (size_t)i + 1], v[3 * (size_t)i + 2]);
-  pack_one(V, P, i, xx, vv, f, bb, mass[i], vol[i], ps, g, keys);
+  pack_one(V, P, i, id_base, xx, vv, f, bb, mass[i], vol[i], ps, g, keys);
 }
 
 // Reference AoS slots (staged on the device) -> q streams.
 __global__ void k_pack_aos(View V, Params P, int n, const unsigned char *pool, const uint32_t *indices, MpmbAosLayout L,
-                           const int *group, uint32_t *keys) {
+                           const int *group, uint32_t *keys, uint32_t id_base) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned char *s = pool + (size_t)indices[i] * L.stride;
@@ -201,7 +201,7 @@ __global__ void k_pack_aos(View V, Params P, int n, const unsigned char *pool, c
   int g = group ? group[i] : 0;
   float vol = *(const float *)(s + L.off_vol);
   float ps = L.off_scalar >= 0 ? *(const float *)(s + L.off_scalar) : 0.f;
-  pack_one(V, P, i, make_float3(pos[0], pos[1], pos[2]), make_float3(vm[0], vm[1], vm[2]), f, bb, vm[3], vol, ps, g, keys);
+  pack_one(V, P, i, id_base, make_float3(pos[0], pos[1], pos[2]), make_float3(vm[0], vm[1], vm[2]), f, bb, vm[3], vol, ps, g, keys);
 }
 
 // q streams -> field-wise arrays, compacting live particles (storage order).
@@ -249,8 +249,7 @@ __global__ void k_reset_counters(Counters *c) {
   c->n_tiles = 0;
   c->n_ghost = 0;
   c->n_alive = 0;
-  c->mig_count[0] = 0;
-  c->mig_count[1] = 0;
+  c->mig_in = 0;
 }
 
 // Active-tile list = run heads of the sorted keys.  Replaces page_map / block_meta construction
@@ -694,6 +693,80 @@ __global__ void k_planes_to_sdf(Params P, int n_planes, const float4 *planes, fl
   }
 }
 
+// ------------------------------------------------------------------------------ z-slab exchange
+// Halo message: int4 header {count,0,0,0} | int tile_xy[cap_xy] | float4 arena[cap_xy][216].
+// Packs the arenas of the owned tiles of one tile layer (the partial sums of (p,m) the neighbour
+// rank's nodes need); the neighbour registers them as ghost tiles, so its G2P sums them in the
+// same fixed order as a single-GPU run would.
+__global__ void k_halo_pack(View V, Params P, int layer_z, int cap_xy, int *hdr, int *tile_xy, float4 *arenas) {
+  __shared__ int s_idx;
+  const int n_tiles = V.cnt->n_tiles;
+  for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
+    const int tile = V.tile_id[slot];
+    if (tile % P.nt[2] != layer_z) continue;  // uniform per CTA
+    if (threadIdx.x == 0) {
+      int idx = atomicAdd(&hdr[0], 1);
+      if (idx >= cap_xy) { atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY); idx = -1; }
+      else tile_xy[idx] = tile / P.nt[2];
+      s_idx = idx;
+    }
+    __syncthreads();
+    const int idx = s_idx;
+    if (idx >= 0)
+      for (int n = threadIdx.x; n < ARENA; n += blockDim.x) arenas[(size_t)idx * ARENA + n] = V.arena[(size_t)slot * ARENA + n];
+    __syncthreads();
+  }
+}
+
+__global__ void k_halo_unpack(View V, Params P, int layer_z, int cap_xy, const int *hdr, const int *tile_xy, const float4 *arenas) {
+  __shared__ int s_slot;
+  const int count = min(hdr[0], cap_xy);
+  for (int e = blockIdx.x; e < count; e += gridDim.x) {
+    if (threadIdx.x == 0) {
+      int slot = V.cnt->n_tiles + atomicAdd(&V.cnt->n_ghost, 1);
+      if (slot >= V.cap_tiles) { atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY); slot = -1; }
+      else {
+        const int tile = tile_xy[e] * P.nt[2] + layer_z;
+        V.tile_id[slot] = tile;
+        V.tile_begin[slot] = 0;
+        V.tile_end[slot] = 0;
+        V.slot_map[tile] = slot;
+      }
+      s_slot = slot;
+    }
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot >= 0)
+      for (int n = threadIdx.x; n < ARENA; n += blockDim.x) V.arena[(size_t)slot * ARENA + n] = arenas[(size_t)e * ARENA + n];
+    __syncthreads();
+  }
+}
+
+// Migration message: int4 header {count,0,0,0} | float4 record[cap][N_Q].
+__global__ void k_migrate_pack(View V, uint32_t *keys, int n, uint32_t key_face, uint32_t key_dead, int cap, int *hdr, float4 *rec) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || keys[i] != key_face) return;
+  int idx = atomicAdd(&hdr[0], 1);
+  keys[i] = key_dead;
+  if (idx >= cap) { atomicOr(&V.cnt->error, DEVERR_MIGRATE_CAPACITY); return; }
+#pragma unroll
+  for (int k = 0; k < N_Q; k++) rec[(size_t)idx * N_Q + k] = V.q[k][i];
+}
+
+__global__ void k_migrate_unpack(View V, Params P, uint32_t *keys, int cap_particles, int cap, const int *hdr, const float4 *rec) {
+  const int count = min(hdr[0], cap);
+  const int base = V.cnt->n_alive + V.cnt->mig_in;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+    const int dst = base + e;
+    if (dst >= cap_particles) { atomicOr(&V.cnt->error, DEVERR_PARTICLE_CAPACITY); continue; }
+    float4 r0 = rec[(size_t)e * N_Q];
+#pragma unroll
+    for (int k = 0; k < N_Q; k++) V.q[k][dst] = rec[(size_t)e * N_Q + k];
+    keys[dst] = make_key(P, r0.x, r0.y, r0.z);
+  }
+}
+__global__ void k_migrate_commit(Counters *c, const int *hdr, int cap) { c->mig_in += min(hdr[0], cap); }
+
 }  // namespace mpmb
 
 // =====================================================================================
@@ -726,6 +799,14 @@ struct MpmbEngine {
   Counters *cnt = nullptr;
 
   int stage = 0;  // 0 idle/after resample, 1 after sort, 2 after rasterize
+  // z-slab bookkeeping: n_alive is read back with a lag so the host never waits for the device
+  static constexpr int RING = 8;
+  int *alive_ring = nullptr;  // pinned
+  cudaEvent_t alive_ev[RING] = {};
+  int64_t alive_step[RING] = {};
+  int64_t sort_step = 0;
+  int64_t mig_cap = 0;
+  uint32_t id_base = 0;
   int num_sms = 148;
   int64_t launches = 0;
 
@@ -919,6 +1000,15 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
   if (cudaMalloc(&h->cnt, sizeof(Counters)) != cudaSuccess) return bail("cudaMalloc counters");
   cudaMemset(h->slot_map, 0xFF, sizeof(int) * ntot);
   cudaMemset(h->cnt, 0, sizeof(Counters));
+  h->mig_cap = h->cfg.world > 1 ? (cfg->migrate_capacity > 0 ? cfg->migrate_capacity : 65536) : 0;
+  if (h->cfg.world > 1) {
+    if (cfg->tile_z0 < 0 || cfg->tile_z1 > P.nt[2] || cfg->tile_z0 >= cfg->tile_z1) {
+      mpmb_destroy(h);
+      return fail(nullptr, MPMB_ERR_INVALID, "bad slab [%d,%d) for %d tile layers", cfg->tile_z0, cfg->tile_z1, P.nt[2]);
+    }
+    if (cudaMallocHost(&h->alive_ring, sizeof(int) * MpmbEngine::RING) != cudaSuccess) return bail("cudaMallocHost");
+    for (int i = 0; i < MpmbEngine::RING; i++) { cudaEventCreateWithFlags(&h->alive_ev[i], cudaEventDisableTiming); h->alive_step[i] = -1; }
+  }
   if (cfg->capacity > 0) {
     int rc = alloc_particles(h, cfg->capacity);
     if (rc != MPMB_OK) { g_create_error = h->err; mpmb_destroy(h); return rc; }
@@ -935,6 +1025,7 @@ int mpmb_destroy(MpmbHandle h) {
   cudaFree(h->tile_id); cudaFree(h->tile_begin); cudaFree(h->tile_end); cudaFree(h->slot_map);
   cudaFree(h->arena); cudaFree(h->sdf4); cudaFree(h->cnt);
   for (auto &e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  if (h->alive_ring) { cudaFreeHost(h->alive_ring); for (int i = 0; i < MpmbEngine::RING; i++) cudaEventDestroy(h->alive_ev[i]); }
   delete h;
   return MPMB_OK;
 }
@@ -963,6 +1054,13 @@ int mpmb_set_material(MpmbHandle h, int32_t group, int32_t kind, const float *pa
   if (n_params < 0 || n_params > MPMB_MAT_PARAMS || (n_params > 0 && !params)) return fail(h, MPMB_ERR_INVALID, "bad parameter vector");
   h->P.mats[group].kind = kind;
   for (int k = 0; k < 8; k++) h->P.mats[group].p[k] = k < n_params ? params[k] : 0.f;
+  return MPMB_OK;
+}
+
+int mpmb_set_id_base(MpmbHandle h, int64_t base) {
+  CHECK_HANDLE(h);
+  if (base < 0 || base >= (1ll << 26)) return fail(h, MPMB_ERR_INVALID, "id base %lld outside [0, 2^26)", (long long)base);
+  h->id_base = (uint32_t)base;
   return MPMB_OK;
 }
 
@@ -1000,7 +1098,7 @@ int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float 
 
 static int ensure_capacity(MpmbEngine *h, int64_t n) {
   int64_t want = n;
-  if (h->cfg.world > 1) want = n + 4 * (h->cfg.migrate_capacity > 0 ? h->cfg.migrate_capacity : 0) + n / 4;
+  if (h->cfg.world > 1) want = n + n / 4 + 2 * MpmbEngine::RING * 2 * h->mig_cap;
   if (h->cfg.capacity > 0) {
     if (n > h->cap) return fail(h, MPMB_ERR_CAPACITY, "%lld particles exceed the configured capacity %lld", (long long)n, (long long)h->cap);
     return MPMB_OK;
@@ -1014,6 +1112,8 @@ static int finish_upload(MpmbEngine *h, int64_t n) {
   if (h->cap > n) k_fill_u32<<<(unsigned)((h->cap - n + 255) / 256), 256, 0, h->stream>>>(h->keys[h->cur] + n, (int)(h->cap - n), h->key_dead);
   h->n_bound = (int)n;
   h->stage = 0;
+  h->sort_step = 0;
+  for (int i = 0; i < MpmbEngine::RING; i++) h->alive_step[i] = -1;
   CUDA_TRY(h, cudaMemsetAsync(&h->cnt->n_alive, 0, sizeof(int), h->stream));
   int nn = (int)n;
   CUDA_TRY(h, cudaMemcpyAsync(&h->cnt->n_alive, &nn, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1025,6 +1125,7 @@ int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *
                           const float *mass, const float *vol, const float *scalar, const int32_t *group) {
   CHECK_HANDLE(h);
   if (n < 0 || (n > 0 && (!x || !v || !mass || !vol))) return fail(h, MPMB_ERR_INVALID, "x, v, mass, vol are required");
+  if ((int64_t)h->id_base + n > (1ll << 26)) return fail(h, MPMB_ERR_CAPACITY, "particle ids exceed 2^26");
   int rc = ensure_capacity(h, n);
   if (rc != MPMB_OK) return rc;
   if (n == 0) return finish_upload(h, 0);
@@ -1044,7 +1145,7 @@ int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *
         *ds = put(scalar, n);
   int *dg = (int *)put(group, n);
   View V = make_view(h);
-  k_pack_particles<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(V, h->P, (int)n, dx_, dv, dF, db, dm, dvol, ds, dg, h->keys[h->cur]);
+  k_pack_particles<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(V, h->P, (int)n, dx_, dv, dF, db, dm, dvol, ds, dg, h->keys[h->cur], h->id_base);
   h->launches++;
   cudaError_t e = cudaStreamSynchronize(h->stream);
   cudaFree(stage);
@@ -1070,7 +1171,7 @@ int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slot
   cudaMemcpyAsync(d_idx, indices, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, h->stream);
   if (group) cudaMemcpyAsync(d_grp, group, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream);
   View V = make_view(h);
-  k_pack_aos<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(V, h->P, (int)n, d_pool, d_idx, *L, d_grp, h->keys[h->cur]);
+  k_pack_aos<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(V, h->P, (int)n, d_pool, d_idx, *L, d_grp, h->keys[h->cur], h->id_base);
   h->launches++;
   cudaError_t e = cudaStreamSynchronize(h->stream);
   cudaFree(d_pool); cudaFree(d_idx); cudaFree(d_grp);
@@ -1191,6 +1292,22 @@ int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *in
 int mpmb_sort_particles_and_populate_grid(MpmbHandle h) {
   CHECK_HANDLE(h);
   if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "sort must follow resample/upload");
+  if (h->cfg.world > 1 && h->sort_step > 0) {
+    // newest completed read-back of n_alive: live <= value + (steps since) * 2 * mig_cap
+    int best = -1;
+    for (int i = 0; i < MpmbEngine::RING; i++)
+      if (h->alive_step[i] >= 0 && (best < 0 || h->alive_step[i] > h->alive_step[best]) && cudaEventQuery(h->alive_ev[i]) == cudaSuccess) best = i;
+    if (best < 0) {  // nothing completed yet: wait for the oldest outstanding one
+      for (int i = 0; i < MpmbEngine::RING; i++)
+        if (h->alive_step[i] >= 0 && (best < 0 || h->alive_step[i] < h->alive_step[best])) best = i;
+      if (best >= 0) CUDA_TRY(h, cudaEventSynchronize(h->alive_ev[best]));
+    }
+    if (best >= 0) {
+      int64_t bound = (int64_t)h->alive_ring[best] + (h->sort_step - h->alive_step[best]) * 2 * h->mig_cap;
+      if (bound > h->cap) return fail(h, MPMB_ERR_CAPACITY, "slab particle bound %lld exceeds capacity %lld", (long long)bound, (long long)h->cap);
+      h->n_bound = (int)bound;
+    }
+  }
   prof_begin(h, 0);
   View V = make_view(h);
   k_clear_tiles<<<64, 256, 0, h->stream>>>(V);
@@ -1202,6 +1319,14 @@ int mpmb_sort_particles_and_populate_grid(MpmbHandle h) {
   }
   h->launches += 3;
   prof_end(h, 3);
+  if (h->cfg.world > 1) {
+    int r = (int)(h->sort_step % MpmbEngine::RING);
+    if (h->alive_step[r] >= 0) CUDA_TRY(h, cudaEventSynchronize(h->alive_ev[r]));  // slot reuse
+    CUDA_TRY(h, cudaMemcpyAsync(&h->alive_ring[r], &h->cnt->n_alive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->alive_ev[r], h->stream));
+    h->alive_step[r] = h->sort_step;
+  }
+  h->sort_step++;
   CUDA_TRY(h, cudaGetLastError());
   h->stage = 1;
   return MPMB_OK;
@@ -1227,7 +1352,8 @@ int mpmb_resample(MpmbHandle h) {
   View V = make_view(h);
   // slots the kernel does not write (dead tail) must carry dead keys
   if (h->n_bound > 0) {
-    k_fill_u32<<<(h->n_bound + 255) / 256, 256, 0, h->stream>>>(h->keys[h->cur ^ 1], h->n_bound, h->key_dead);
+    const int nfill = h->cfg.world > 1 ? (int)h->cap : h->n_bound;  // slab runs: n_bound moves, keep every unused slot dead
+    k_fill_u32<<<(nfill + 255) / 256, 256, 0, h->stream>>>(h->keys[h->cur ^ 1], nfill, h->key_dead);
     k_g2p<128><<<h->num_sms * 8, 128, 0, h->stream>>>(V, h->P);
   }
   h->launches += 2;
@@ -1298,12 +1424,92 @@ int mpmb_get_counters(MpmbHandle h, int64_t *active_tiles, int64_t *alive, int64
   return MPMB_OK;
 }
 
-// ------------------------------------------------------------------------------ multi-GPU (not built yet)
-int64_t mpmb_halo_bytes(MpmbHandle h) { (void)h; return 0; }
-int mpmb_halo_pack(MpmbHandle h, int32_t, void *) { return fail(h, MPMB_ERR_STATE, "z-slab exchange not implemented yet"); }
-int mpmb_halo_unpack(MpmbHandle h, int32_t, const void *) { return fail(h, MPMB_ERR_STATE, "z-slab exchange not implemented yet"); }
-int64_t mpmb_migrate_bytes(MpmbHandle h) { (void)h; return 0; }
-int mpmb_migrate_pack(MpmbHandle h, int32_t, void *) { return fail(h, MPMB_ERR_STATE, "z-slab exchange not implemented yet"); }
-int mpmb_migrate_unpack(MpmbHandle h, int32_t, const void *) { return fail(h, MPMB_ERR_STATE, "z-slab exchange not implemented yet"); }
+// ------------------------------------------------------------------------------ multi-GPU (z slabs)
+static int64_t halo_cap_xy(MpmbEngine *h) {
+  int64_t full = (int64_t)h->P.nt[0] * h->P.nt[1];
+  return (h->cfg.halo_capacity > 0 && h->cfg.halo_capacity < full) ? h->cfg.halo_capacity : full;
+}
+static int64_t halo_idx_bytes(MpmbEngine *h) { return (halo_cap_xy(h) * 4 + 15) / 16 * 16; }
+
+int64_t mpmb_halo_bytes(MpmbHandle h) {
+  if (!h || h->cfg.world <= 1) return 0;
+  return 16 + halo_idx_bytes(h) + halo_cap_xy(h) * ARENA * (int64_t)sizeof(float4);
+}
+
+int mpmb_halo_pack(MpmbHandle h, int32_t face, void *dev_buf) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1) return fail(h, MPMB_ERR_STATE, "halo exchange needs world > 1");
+  if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "halo_pack must follow rasterize");
+  if (!dev_buf || face < 0 || face > 1) return fail(h, MPMB_ERR_INVALID, "bad argument");
+  prof_begin(h, 3);
+  char *b = (char *)dev_buf;
+  CUDA_TRY(h, cudaMemsetAsync(b, 0, 16, h->stream));
+  View V = make_view(h);
+  const int layer = face == 0 ? h->P.tile_z0 : h->P.tile_z1 - 1;
+  k_halo_pack<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, layer, (int)halo_cap_xy(h), (int *)b, (int *)(b + 16),
+                                                     (float4 *)(b + 16 + halo_idx_bytes(h)));
+  h->launches++;
+  prof_end(h, 1);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
+
+int mpmb_halo_unpack(MpmbHandle h, int32_t face, const void *dev_buf) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1) return fail(h, MPMB_ERR_STATE, "halo exchange needs world > 1");
+  if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "halo_unpack must follow rasterize");
+  if (!dev_buf || face < 0 || face > 1) return fail(h, MPMB_ERR_INVALID, "bad argument");
+  const int layer = face == 0 ? h->P.tile_z0 - 1 : h->P.tile_z1;  // the neighbour's boundary layer
+  if (layer < 0 || layer >= h->P.nt[2]) return fail(h, MPMB_ERR_INVALID, "no neighbour through face %d", face);
+  prof_begin(h, 3);
+  const char *b = (const char *)dev_buf;
+  View V = make_view(h);
+  k_halo_unpack<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, layer, (int)halo_cap_xy(h), (const int *)b, (const int *)(b + 16),
+                                                       (const float4 *)(b + 16 + halo_idx_bytes(h)));
+  h->launches++;
+  prof_end(h, 1);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
+
+int64_t mpmb_migrate_bytes(MpmbHandle h) {
+  if (!h || h->cfg.world <= 1) return 0;
+  return 16 + h->mig_cap * N_Q * (int64_t)sizeof(float4);
+}
+
+int mpmb_migrate_pack(MpmbHandle h, int32_t face, void *dev_buf) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1) return fail(h, MPMB_ERR_STATE, "migration needs world > 1");
+  if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "migrate_pack must follow resample");
+  if (!dev_buf || face < 0 || face > 1) return fail(h, MPMB_ERR_INVALID, "bad argument");
+  prof_begin(h, 3);
+  char *b = (char *)dev_buf;
+  CUDA_TRY(h, cudaMemsetAsync(b, 0, 16, h->stream));
+  View V = make_view(h);
+  const int n = h->n_bound;
+  const uint32_t key_face = h->special_min + (face == 0 ? SPECIAL_MIG_DOWN : SPECIAL_MIG_UP);
+  if (n > 0)
+    k_migrate_pack<<<(n + 255) / 256, 256, 0, h->stream>>>(V, h->keys[h->cur], n, key_face, h->key_dead, (int)h->mig_cap, (int *)b, (float4 *)(b + 16));
+  h->launches++;
+  prof_end(h, 1);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
+
+int mpmb_migrate_unpack(MpmbHandle h, int32_t face, const void *dev_buf) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1) return fail(h, MPMB_ERR_STATE, "migration needs world > 1");
+  if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "migrate_unpack must follow resample");
+  if (!dev_buf || face < 0 || face > 1) return fail(h, MPMB_ERR_INVALID, "bad argument");
+  prof_begin(h, 3);
+  const char *b = (const char *)dev_buf;
+  View V = make_view(h);
+  k_migrate_unpack<<<64, 256, 0, h->stream>>>(V, h->P, h->keys[h->cur], (int)h->cap, (int)h->mig_cap, (const int *)b, (const float4 *)(b + 16));
+  k_migrate_commit<<<1, 1, 0, h->stream>>>(h->cnt, (const int *)b, (int)h->mig_cap);
+  h->launches += 2;
+  prof_end(h, 2);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
 
 }  // extern "C"
