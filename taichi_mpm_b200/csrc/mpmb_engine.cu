@@ -118,7 +118,7 @@ __device__ __forceinline__ bool reference_deletes(const Params &P, float3 x, flo
   float mn = fminf(X, fminf(Y, Z));
   float mx = fmaxf(X - (float)P.res[0], fmaxf(Y - (float)P.res[1], Z - (float)P.res[2]));
   bool bad = (mn < 7.0f) || (mx > -7.0f);
-  bad |= !(isfinite(x.x) && isfinite(x.y) && isfinite(x.z) && isfinite(v.x) && isfinite(v.y) && isfinite(v.z));
+  bad |= !isfinite((x.x + x.y + x.z) + (v.x + v.y + v.z));  // any inf/NaN poisons the sum (pos.abnormal() || v.abnormal())
   return bad;
 }
 
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P) {
         float3 x = make_float3(fmaf(v.x, P.dt, q0.x), fmaf(v.y, P.dt, q0.y), fmaf(v.z, P.dt, q0.z));  // 951
         uint32_t key = make_key(P, x.x, x.y, x.z);
         if (P.clean_boundary && reference_deletes(P, x, v)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
-        if (!(isfinite(x.x) && isfinite(x.y) && isfinite(x.z))) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
+        if (!isfinite(x.x + x.y + x.z)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
         // write at the (tile,cell)-sorted position: storage order follows the sort
         store_particle(V.qn, o, x, mass, v, A, F, ps, vol, tag, B);
         V.keys_next[o] = key;

@@ -342,6 +342,125 @@ __device__ __forceinline__ void store_sym(const Sym3 &T, Mat3 &out) {
   out.m[6] = T.xz; out.m[7] = T.yz; out.m[8] = T.zz;
 }
 
+// ---- symmetric 3x3 helpers for the decomposition-free sand path
+__device__ __forceinline__ Sym3 sym_mul_sym(const Sym3 &A, const Sym3 &B) {  // valid when A and B commute
+  Sym3 C;
+  C.xx = fmaf(A.xx, B.xx, fmaf(A.xy, B.xy, A.xz * B.xz));
+  C.yy = fmaf(A.xy, B.xy, fmaf(A.yy, B.yy, A.yz * B.yz));
+  C.zz = fmaf(A.xz, B.xz, fmaf(A.yz, B.yz, A.zz * B.zz));
+  C.xy = fmaf(A.xx, B.xy, fmaf(A.xy, B.yy, A.xz * B.yz));
+  C.xz = fmaf(A.xx, B.xz, fmaf(A.xy, B.yz, A.xz * B.zz));
+  C.yz = fmaf(A.xy, B.xz, fmaf(A.yy, B.yz, A.yz * B.zz));
+  return C;
+}
+__device__ __forceinline__ float sym_norm2(const Sym3 &A) {
+  return fmaf(A.xx, A.xx, fmaf(A.yy, A.yy, A.zz * A.zz)) + 2.0f * fmaf(A.xy, A.xy, fmaf(A.xz, A.xz, A.yz * A.yz));
+}
+
+// Largest value of `v` over the lanes currently executing together (loop trip counts are made
+// warp-uniform with it so that the series loops never diverge).
+__device__ __forceinline__ int warp_max_active(int v) { return __reduce_max_sync(__activemask(), v); }
+
+// L = log(I + E) for a small symmetric E by the Mercator series in Horner form,
+//   L = E (I - E (I/2 - E (I/3 - ...))),  n terms; n is chosen from |E| so that the truncation,
+// relative to |L| ~ |E|, |E|^(n-1)/(n+1) <= 1e-7, and is the same for the whole warp.
+// Caller guarantees |E|_F <= 0.15.
+__device__ __forceinline__ Sym3 sym_log1p_series(const Sym3 &E, float nrm2) {
+  int n = 3;
+  if (nrm2 > 4.0e-7f) n = 4;    // |E| > 6.3e-4
+  if (nrm2 > 6.2e-5f) n = 5;    // |E| > 7.9e-3
+  if (nrm2 > 7.8e-4f) n = 6;    // |E| > 2.8e-2
+  if (nrm2 > 3.5e-3f) n = 7;    // |E| > 5.9e-2
+  if (nrm2 > 9.2e-3f) n = 9;    // |E| > 9.6e-2 (up to 0.15)
+  n = warp_max_active(n);
+  float c = 1.0f / (float)n;
+  Sym3 S = {c, c, c, 0.f, 0.f, 0.f};
+  for (int k = n - 1; k >= 1; k--) {
+    Sym3 T = sym_mul_sym(E, S);
+    c = 1.0f / (float)k;
+    S.xx = c - T.xx; S.yy = c - T.yy; S.zz = c - T.zz;
+    S.xy = -T.xy; S.xz = -T.xz; S.yz = -T.yz;
+  }
+  return sym_mul_sym(E, S);
+}
+
+// exp(X) for a small symmetric X: I + X (I + X/2 (I + X/3 (...))); truncation relative to |X|,
+// |X|^n/(n+1)! <= 1e-7; warp-uniform term count.  Caller guarantees |X|_F <= 0.28.
+__device__ __forceinline__ Sym3 sym_exp_series(const Sym3 &X, float nrm2) {
+  int n = 3;
+  if (nrm2 > 1.7e-4f) n = 4;    // |X| > 1.3e-2
+  if (nrm2 > 3.5e-3f) n = 6;    // |X| > 5.9e-2 (up to 0.28)
+  n = warp_max_active(n);
+  Sym3 S = {1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
+  for (int k = n; k >= 1; k--) {
+    Sym3 T = sym_mul_sym(X, S);
+    const float c = 1.0f / (float)k;
+    S.xx = fmaf(c, T.xx, 1.f); S.yy = fmaf(c, T.yy, 1.f); S.zz = fmaf(c, T.zz, 1.f);
+    S.xy = c * T.xy; S.xz = c * T.xz; S.yz = c * T.yz;
+  }
+  return S;
+}
+
+// Drucker-Prager sand WITHOUT any matrix decomposition (valid while |F F^T - I| <= 0.15; returns
+// false for the lanes that must fall back to the eigen path).  SandParticle::project
+// (src/particles.cpp:599-626) acts on the principal log strains only through the invariants tr and
+// |hat|, with  hat_i = eps_i - tr/3,  tr = sum(eps) + logJp,  eps_i = ln s_i - c,  i.e. through the
+// TENSOR  Hat = dev(L) - (logJp/3) I,  L = 1/2 log(F F^T); the three cases read
+//   tr >= 0      : L' = c I                        F' = e^c exp(-L) Ft
+//   dgamma <= 0  : L' = L                          F' = Ft
+//   else         : L' = L - k Hat, k=dgamma/|Hat|   F' = exp(-k Hat) Ft
+// and calculate_force of the new state is -vol (2 mu L' + lambda tr(L') I)  (628-637).
+// All three cases run ONE instruction stream (selects, one exp series), so a warp whose lanes sit
+// in different cases does not diverge.
+__device__ __forceinline__ bool sand_step_series(const Material &mat, const Mat3 &Ft, Mat3 &F, float &ps, float vol, Mat3 &force) {
+  const Sym3 E = left_strain(Ft);
+  const float nE2 = sym_norm2(E);
+  const bool small = nE2 <= 0.0225f;
+  const float mu = mat.p[0], la = mat.p[1], alpha = mat.p[2], coh = mat.p[3], beta = mat.p[4];
+  Sym3 L = sym_log1p_series(E, small ? nE2 : 0.f);
+  L.xx *= 0.5f; L.yy *= 0.5f; L.zz *= 0.5f; L.xy *= 0.5f; L.xz *= 0.5f; L.yz *= 0.5f;
+  const float trL = L.xx + L.yy + L.zz;
+  const float sum = trL - 3.0f * coh;   // sum of eps_i
+  const float tr = sum + ps;
+  const float sh = (trL + ps) * (1.f / 3.f);
+  const Sym3 H = {L.xx - sh, L.yy - sh, L.zz - sh, L.xy, L.xz, L.yz};  // Hat = dev(L) - (ps/3) I
+  const float hn2 = sym_norm2(H);
+  const float hn = sqrtf(hn2);
+  const float dg = hn + (3.f * la + 2.f * mu) / (2.f * mu) * tr * alpha;
+  const bool expand = tr >= 0.f;
+  const bool project = !expand && dg > 0.f;
+  // X = -L (expansion), -k Hat (projection), 0 (elastic)
+  const float kf = expand ? 1.f : (project ? dg / hn : 0.f);
+  const Sym3 B = expand ? L : H;
+  const Sym3 X = {-kf * B.xx, -kf * B.yy, -kf * B.zz, -kf * B.xy, -kf * B.xz, -kf * B.yz};
+  const float nX2 = sym_norm2(X);
+  const bool ok = small && nX2 <= 0.078f;
+  if (__any_sync(__activemask(), kf != 0.f)) {
+    Sym3 M = sym_exp_series(X, ok ? nX2 : 0.f);
+    const float ec = expand ? __expf(coh) : 1.f;
+    M.xx *= ec; M.yy *= ec; M.zz *= ec; M.xy *= ec; M.xz *= ec; M.yz *= ec;
+    F = (kf != 0.f) ? sym_mul(M, Ft) : Ft;
+  } else {
+    F = Ft;
+  }
+  if (!ok) return false;
+  ps = expand ? fmaf(beta, sum, ps) : 0.f;
+  // log strain of the new state
+  Sym3 Ln;
+  Ln.xx = expand ? coh : L.xx + X.xx;
+  Ln.yy = expand ? coh : L.yy + X.yy;
+  Ln.zz = expand ? coh : L.zz + X.zz;
+  Ln.xy = expand ? 0.f : L.xy + X.xy;
+  Ln.xz = expand ? 0.f : L.xz + X.xz;
+  Ln.yz = expand ? 0.f : L.yz + X.yz;
+  const float t3 = la * (Ln.xx + Ln.yy + Ln.zz);
+  const float m2 = 2.f * mu;
+  const Sym3 T = {-vol * fmaf(m2, Ln.xx, t3), -vol * fmaf(m2, Ln.yy, t3), -vol * fmaf(m2, Ln.zz, t3), -vol * m2 * Ln.xy, -vol * m2 * Ln.xz,
+                  -vol * m2 * Ln.yz};
+  store_sym(T, force);
+  return true;
+}
+
 // G2P-side constitutive step: Particle::plasticity(cdg) (src/particles.cpp:222-242,340-344,413-416,
 // 469-478,639-647) followed by the value Particle::calculate_force() will return at the NEXT
 // rasterize for the updated state (src/particles.cpp:216-218,335-337,409-411,463-467,628-637).
@@ -359,6 +478,10 @@ __device__ __forceinline__ void material_step(const Material &mat, const Mat3 &c
     F = Ft;
     calculate_force(mat, F, ps, vol, force);
     return;
+  }
+  if (mat.kind == MAT_SAND) {
+    if (sand_step_series(mat, Ft, F, ps, vol, force)) return;
+    // large strain: principal-space evaluation below (F is recomputed from Ft, ps is untouched)
   }
   Mat3 U;
   float e[3];
