@@ -235,6 +235,10 @@ __global__ void k_alive_flags(const uint32_t *keys, int n, uint32_t special_min,
   if (i < n) flags[i] = keys[i] < special_min ? 1 : 0;
 }
 
+// dead keys for the slots G2P does not write: [n_alive, n) (n_alive is a device value)
+__global__ void k_fill_tail(uint32_t *a, const Counters *c, int n, uint32_t v) {
+  for (int i = c->n_alive + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = v;
+}
 __global__ void k_fill_u32(uint32_t *a, int n, uint32_t v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
@@ -483,19 +487,19 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
 // ------------------------------------------------------------------------------ grid node
 // Momentum/mass of global node g = fixed-order sum of the arenas that cover it:
 // owner tile T=(g>>2) holds it at local l=g&3; tile T-o (o in {0,1}^3) holds it at l+4o (needs l<=1).
-// Branch-free: absent contributions read the all-zero arena `zero_slot`, so the 8 loads are
-// independent and issue back to back.
+// The <=8 loads are predicated, not branched around, so they stay independent and issue back to back.
 template <class SlotOf>
 __device__ __forceinline__ float4 gather_node(const float4 *arena, int zero_slot, int lx, int ly, int lz, SlotOf slot_of) {
+  (void)zero_slot;
   float4 a[8];
 #pragma unroll
   for (int o = 0; o < 8; o++) {
     const int ox = o >> 2, oy = (o >> 1) & 1, oz = o & 1;
-    int slot = slot_of(ox, oy, oz);
-    const bool covered = !(ox && lx > 1) && !(oy && ly > 1) && !(oz && lz > 1);
-    if (!covered || slot < 0) slot = zero_slot;
-    const int idx = covered ? ((lx + 4 * ox) * 6 + (ly + 4 * oy)) * 6 + (lz + 4 * oz) : 0;
-    a[o] = arena[(size_t)slot * ARENA + idx];
+    const int slot = slot_of(ox, oy, oz);
+    const bool covered = !(ox && lx > 1) && !(oy && ly > 1) && !(oz && lz > 1) && slot >= 0;
+    const int idx = ((lx + 4 * ox) * 6 + (ly + 4 * oy)) * 6 + (lz + 4 * oz);
+    a[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (covered) a[o] = arena[(size_t)slot * ARENA + idx];
   }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -524,72 +528,113 @@ __device__ __forceinline__ float4 node_update(const Params &P, const float4 *sdf
   return g;
 }
 
-// ------------------------------------------------------------------------------ G2P
-// Replaces normalize_grid_and_apply_external_force + apply_grid_boundary_conditions +
-// MPM<3>::resample_optimized / block_op_normal (src/transfer.cpp:837-954) + Particle::plasticity +
-// clear_boundary_particles (src/mpm.cpp:583-633); produces the affine matrix of the NEXT rasterize
-// (calculate_force of the updated state) and the next substep's sort key.
-constexpr int G2P_CH = 512;  // particles staged per chunk
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P) {
-  __shared__ float4 s_vel[ARENA];
+// ------------------------------------------------------------------------------ grid update
+// Replaces normalize_grid_and_apply_external_force (src/mpm.cpp:277-294) + apply_grid_boundary_conditions
+// (src/mpm.cpp:296-372): for every active tile the 6x6x6 nodes its particles gather from are
+// rebuilt (fixed-order sum of the covering arenas), normalised, projected on the level set and
+// stored as one contiguous 3.4 KB block vel[slot][216].  Node-parallel, so the dependent
+// slot_map -> arena -> sdf loads are hidden by occupancy instead of stalling a G2P CTA.
+__global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel) {
   __shared__ int s_nb[27];
-  __shared__ float4 s_in[4][G2P_CH];
-  constexpr int KPT = G2P_CH / BLOCK;
   const int tid = threadIdx.x;
   const int n_tiles = V.cnt->n_tiles;
-  const float scale = -4.0f * P.inv_dx * P.dt;  // src/transfer.cpp:938
-  // gathers the G2P set (x|mass, F, scalar|vol|tag: 64 B/particle) of one chunk into shared memory
-  auto stage = [&](int cb, int nrows) {
-    uint32_t pidx[KPT];
-#pragma unroll
-    for (int k = 0; k < KPT; k++) {
-      const int r = k * BLOCK + tid;
-      pidx[k] = r < nrows ? V.perm[cb + r] : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < KPT; k++) {
-      const int r = k * BLOCK + tid;
-      if (r < nrows) {
-        cp_async16(&s_in[0][r], &V.q[0][pidx[k]]);
-        cp_async16(&s_in[1][r], &V.q[4][pidx[k]]);
-        cp_async16(&s_in[2][r], &V.q[5][pidx[k]]);
-        cp_async16(&s_in[3][r], &V.q[6][pidx[k]]);
-      }
-    }
-    cp_async_commit();
-  };
   for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
     const int tile = V.tile_id[slot];
     const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
-    const int begin = V.tile_begin[slot], end = V.tile_end[slot];
-    stage(begin, min(G2P_CH, end - begin));  // in flight while the grid nodes are rebuilt
     if (tid < 27) {
       int ox = tid / 9 - 1, oy = (tid / 3) % 3 - 1, oz = tid % 3 - 1;
       int x = tx + ox, y = ty + oy, z = tz + oz;
-      int s = -1;
-      if (x >= 0 && y >= 0 && z >= 0 && x < P.nt[0] && y < P.nt[1] && z < P.nt[2]) s = V.slot_map[(x * P.nt[1] + y) * P.nt[2] + z];
-      s_nb[tid] = s;
+      int sl = -1;
+      if (x >= 0 && y >= 0 && z >= 0 && x < P.nt[0] && y < P.nt[1] && z < P.nt[2]) sl = V.slot_map[(x * P.nt[1] + y) * P.nt[2] + z];
+      s_nb[tid] = sl;
     }
     __syncthreads();
-    for (int n = tid; n < ARENA; n += BLOCK) {
+    if (tid < ARENA) {
+      const int n = tid;
       int a = n / 36, b = (n / 6) % 6, c = n % 6;
       int wx_ = a >> 2, wy_ = b >> 2, wz_ = c >> 2;  // owner tile offset (0/1)
       int lx = a & 3, ly = b & 3, lz = c & 3;
       float4 g = gather_node(V.arena, V.cap_tiles, lx, ly, lz, [&](int ox, int oy, int oz) {
         return s_nb[(wx_ - ox + 1) * 9 + (wy_ - oy + 1) * 3 + (wz_ - oz + 1)];
       });
-      s_vel[n] = node_update(P, V.sdf4, g, tx * 4 + a, ty * 4 + b, tz * 4 + c);
+      vel[(size_t)slot * ARENA + n] = node_update(P, V.sdf4, g, tx * 4 + a, ty * 4 + b, tz * 4 + c);
     }
-    for (int cb = begin; cb < end; cb += G2P_CH) {
-      const int nrows = min(G2P_CH, end - cb);
-      if (cb != begin) stage(cb, nrows);
-      cp_async_wait_all();
-      __syncthreads();
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ G2P
+// Replaces MPM<3>::resample_optimized / block_op_normal (src/transfer.cpp:837-954) + Particle::plasticity +
+// clear_boundary_particles (src/mpm.cpp:583-633); produces the affine matrix of the NEXT rasterize
+// (calculate_force of the updated state) and the next substep's sort key.
+// Persistent CTAs walk their tiles chunk by chunk through a two-stage cp.async pipeline: while the
+// warps compute chunk i out of one shared buffer, the gathered rows (64 B/particle) of chunk i+1
+// and, at a tile change, that tile's 216 node velocities are already in flight into the other.
+constexpr int G2P_CH = 256;  // particles per pipeline stage
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4 *vel) {
+  __shared__ float4 s_vel[2][ARENA];
+  __shared__ float4 s_in[2][4][G2P_CH];
+  constexpr int KPT = G2P_CH / BLOCK;
+  const int tid = threadIdx.x;
+  const int n_tiles = V.cnt->n_tiles;
+  const float scale = -4.0f * P.inv_dx * P.dt;  // src/transfer.cpp:938
+  struct Item { int slot, cb, end, first; };
+  auto first_item = [&](int slot) {
+    Item it{slot, 0, 0, 1};
+    if (slot < n_tiles) { it.cb = V.tile_begin[slot]; it.end = V.tile_end[slot]; }
+    return it;
+  };
+  auto next_item = [&](const Item &it) {
+    if (it.cb + G2P_CH < it.end) return Item{it.slot, it.cb + G2P_CH, it.end, 0};
+    return first_item(it.slot + (int)gridDim.x);
+  };
+  // puts one item in flight: rows of the G2P set (x|mass, F, scalar|vol|tag) and, for the first chunk of
+  // a tile, the tile's node velocities
+  auto prefetch = [&](const Item &it, int buf, int vbuf) {
+    if (it.slot < n_tiles) {
+      const int nrows = min(G2P_CH, it.end - it.cb);
+      uint32_t pidx[KPT];
+#pragma unroll
+      for (int k = 0; k < KPT; k++) {
+        const int r = k * BLOCK + tid;
+        pidx[k] = r < nrows ? V.perm[it.cb + r] : 0u;
+      }
+      if (it.first) {
+        const float4 *src = vel + (size_t)it.slot * ARENA;
+        for (int n = tid; n < ARENA; n += BLOCK) cp_async16(&s_vel[vbuf][n], &src[n]);
+      }
+#pragma unroll
+      for (int k = 0; k < KPT; k++) {
+        const int r = k * BLOCK + tid;
+        if (r < nrows) {
+          cp_async16(&s_in[buf][0][r], &V.q[0][pidx[k]]);
+          cp_async16(&s_in[buf][1][r], &V.q[4][pidx[k]]);
+          cp_async16(&s_in[buf][2][r], &V.q[5][pidx[k]]);
+          cp_async16(&s_in[buf][3][r], &V.q[6][pidx[k]]);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  Item cur = first_item(blockIdx.x);
+  int buf = 0, vbuf = 0;
+  prefetch(cur, 0, 0);
+  while (cur.slot < n_tiles) {
+    const Item nxt = next_item(cur);
+    const int nvbuf = nxt.first ? (vbuf ^ 1) : vbuf;
+    prefetch(nxt, buf ^ 1, nvbuf);
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // the current item has landed, the next stays in flight
+    __syncthreads();
+    {
+      const int tile = V.tile_id[cur.slot];
+      const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
+      const int nrows = min(G2P_CH, cur.end - cur.cb);
+      const float4 *sv = s_vel[vbuf];
       for (int r = tid; r < nrows; r += BLOCK) {
-        const int j = cb + r;
+        const int j = cur.cb + r;
         const size_t o = V.sorted_pos[j];  // (tile,cell)-sorted output position, consumed by the stores below
-        const float4 q0 = s_in[0][r], q4 = s_in[1][r], q5 = s_in[2][r], q6 = s_in[3][r];
+        const float4 q0 = s_in[buf][0][r], q4 = s_in[buf][1][r], q5 = s_in[buf][2][r], q6 = s_in[buf][3][r];
         const float mass = q0.w, vol = q6.z;
         const uint32_t tag = __float_as_uint(q6.w);
         const Material &mat = P.mats[tag >> 26];
@@ -613,7 +658,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P) {
 #pragma unroll
           for (int jn = 0; jn < 3; jn++) {
             const int row = ((bx + i) * 6 + (by + jn)) * 6 + bz;
-            const float4 g0 = s_vel[row], g1 = s_vel[row + 1], g2 = s_vel[row + 2];
+            const float4 g0 = sv[row], g1 = sv[row + 1], g2 = sv[row + 2];
             float3 a, c;
             a.x = fmaf(wz[2], g2.x, fmaf(wz[1], g1.x, wz[0] * g0.x));
             a.y = fmaf(wz[2], g2.y, fmaf(wz[1], g1.y, wz[0] * g0.y));
@@ -657,9 +702,13 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P) {
         store_particle(V.qn, o, x, mass, v, A, F, ps, vol, tag, B);
         V.keys_next[o] = key;
       }
-      __syncthreads();
     }
+    __syncthreads();  // everyone is done with `buf` before the prefetch after next overwrites it
+    cur = nxt;
+    buf ^= 1;
+    vbuf = nvbuf;
   }
+  cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------------------ debug grid
@@ -795,6 +844,7 @@ struct MpmbEngine {
   int cap_tiles = 0;
   int *tile_id = nullptr, *tile_begin = nullptr, *tile_end = nullptr, *slot_map = nullptr;
   float4 *arena = nullptr;
+  float4 *vel = nullptr;  // node velocities per active tile (k_grid -> k_g2p)
   float4 *sdf4 = nullptr;
   Counters *cnt = nullptr;
 
@@ -997,6 +1047,7 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
   if (cudaMalloc(&h->slot_map, sizeof(int) * ntot) != cudaSuccess) return bail("cudaMalloc slot_map");
   if (cudaMalloc(&h->arena, sizeof(float4) * ARENA * (cap_tiles + 1)) != cudaSuccess) return bail("cudaMalloc arena");
   cudaMemset(h->arena + (size_t)ARENA * cap_tiles, 0, sizeof(float4) * ARENA);  // the all-zero arena read for absent neighbours
+  if (cudaMalloc(&h->vel, sizeof(float4) * ARENA * cap_tiles) != cudaSuccess) return bail("cudaMalloc vel");
   if (cudaMalloc(&h->cnt, sizeof(Counters)) != cudaSuccess) return bail("cudaMalloc counters");
   cudaMemset(h->slot_map, 0xFF, sizeof(int) * ntot);
   cudaMemset(h->cnt, 0, sizeof(Counters));
@@ -1023,7 +1074,7 @@ int mpmb_destroy(MpmbHandle h) {
   cudaDeviceSynchronize();
   free_particles(h);
   cudaFree(h->tile_id); cudaFree(h->tile_begin); cudaFree(h->tile_end); cudaFree(h->slot_map);
-  cudaFree(h->arena); cudaFree(h->sdf4); cudaFree(h->cnt);
+  cudaFree(h->arena); cudaFree(h->vel); cudaFree(h->sdf4); cudaFree(h->cnt);
   for (auto &e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (h->alive_ring) { cudaFreeHost(h->alive_ring); for (int i = 0; i < MpmbEngine::RING; i++) cudaEventDestroy(h->alive_ev[i]); }
   delete h;
@@ -1353,11 +1404,12 @@ int mpmb_resample(MpmbHandle h) {
   // slots the kernel does not write (dead tail) must carry dead keys
   if (h->n_bound > 0) {
     const int nfill = h->cfg.world > 1 ? (int)h->cap : h->n_bound;  // slab runs: n_bound moves, keep every unused slot dead
-    k_fill_u32<<<(nfill + 255) / 256, 256, 0, h->stream>>>(h->keys[h->cur ^ 1], nfill, h->key_dead);
-    k_g2p<128><<<h->num_sms * 8, 128, 0, h->stream>>>(V, h->P);
+    k_fill_tail<<<64, 256, 0, h->stream>>>(h->keys[h->cur ^ 1], h->cnt, nfill, h->key_dead);
+    k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel);
+    k_g2p<128><<<h->num_sms * 5, 128, 0, h->stream>>>(V, h->P, h->vel);
   }
-  h->launches += 2;
-  prof_end(h, 2);
+  h->launches += 3;
+  prof_end(h, 3);
   CUDA_TRY(h, cudaGetLastError());
   h->cur ^= 1;
   h->stage = 0;
