@@ -7,17 +7,23 @@
 //       state    q7=(b0..b3) q8=(b4..b7) q9=(b8,-,-,-)             b = apic_b
 //     A = calculate_force()*(-4 dt/dx) + apic_b*(4 m) is the affine matrix rasterize needs
 //     (src/transfer.cpp:503,521-522).  G2P produces it for the NEXT substep from the same
-//     eigen-decomposition as the return map, so P2G reads 64 B/particle and does no constitutive
-//     math, and each particle is factorised once per substep instead of twice.
-//   * order: u32 key = tile (4x4x4 nodes, z fastest), radix-sorted every substep (stable); P2G
-//     sorts each tile's run by cell in shared memory and G2P writes its output at that position,
-//     so storage stays (tile,cell)-ordered and the permutation read next substep is near-identity.
+//     constitutive evaluation as the return map, so P2G reads 64 B/particle and does no
+//     constitutive math, and each particle is factorised at most once per substep.
+//   * order: every active tile (4x4x4 nodes) owns a contiguous RUN of storage rows plus a short
+//     ARRIVAL list.  G2P writes each tile's particles (cell-sorted) into one contiguous run of the
+//     other buffer, so storage is re-compacted every substep for free; a particle whose base node
+//     left its tile (~0.5 % per substep) is appended to a mover list and re-binned by four tiny
+//     kernels (count, scan, place, rank).  There is NO per-substep radix sort and no permutation
+//     array: run rows are read with unit stride.  The radix sort runs once, at upload.
+//     This replaces sort_particles_and_populate_grid (src/mpm.cpp:770-918).
 //   * grid: no dense grid.  P2G leaves one 6x6x6 float4 "arena" (tile + the +2 stencil halo,
-//     the reference's GridCache footprint src/transfer.cpp:59-63) per active tile; G2P rebuilds
-//     each node as the fixed-order sum of the <=8 arenas covering it, normalises, applies the
-//     level-set boundary and keeps the result in shared memory.  No global float atomics, and no
-//     float atomics at all: results are bit-reproducible run to run.
+//     the reference's GridCache footprint src/transfer.cpp:59-63) per active tile; k_grid rebuilds
+//     each node as the fixed-order sum of the <=8 arenas covering it, normalises and applies the
+//     level-set boundary.  No global float atomics, no float atomics at all: single-GPU results
+//     are bit-reproducible run to run.
 #include <cuda_runtime.h>
+#include <cub/block/block_reduce.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -35,8 +41,9 @@ namespace mpmb {
 
 constexpr int ARENA = 216;  // 6*6*6 nodes
 constexpr int N_Q = 10;
-// keys: [0, ntiles_total) = tile index; specials sort last
+// keys: [0, ntiles_total) = tile index; ntiles_total + {0,1,2} = left through -z / +z face, dead
 enum { SPECIAL_MIG_DOWN = 0, SPECIAL_MIG_UP = 1, SPECIAL_DEAD = 2 };
+constexpr uint32_t ROW_HOLE = 0xFFFFFFFFu;  // outpos of a run row whose particle left the tile
 
 struct Params {
   int res[3];
@@ -53,28 +60,43 @@ struct Params {
 };
 
 struct Counters {  // device-resident
-  int n_alive;
-  int n_tiles;
-  int n_ghost;      // ghost tiles appended after the owned ones (world>1)
-  int error;        // sticky device-side error flags
-  int mig_in;       // particles appended by mpmb_migrate_unpack since the last sort
-  int pad[3];
+  int n_store;        // rows of the current storage that hold a particle record
+  int n_tiles;        // active tiles of this substep
+  int n_ghost;        // ghost tiles appended after the owned ones (world>1)
+  int error;          // sticky device-side error flags
+  int n_movers;       // mover list consumed by the next ordering
+  int n_movers_next;  // mover list being filled by G2P / migrate_unpack
+  int n_alive;        // particles binned by the last ordering
+  int pad;
 };
 enum { DEVERR_TILE_CAPACITY = 1, DEVERR_MIGRATE_CAPACITY = 2, DEVERR_PARTICLE_CAPACITY = 4 };
+
+struct TileMeta {  // one 32-byte record per active tile (slot)
+  int tile, run_begin, run_len, arr_off, arr_len, out_begin, pad0, pad1;
+};
 
 struct View {  // raw pointers handed to kernels
   float4 *q[N_Q];        // current (read) buffer
   float4 *qn[N_Q];       // next (written by G2P)
-  const uint32_t *keys_sorted;
-  const uint32_t *perm;
+  uint32_t *keys;        // tile of every current row (specials: dead / migrating)
   uint32_t *keys_next;
-  uint32_t *sorted_pos;  // per sorted index j: position inside [begin,end) after the in-tile cell sort
-  int *tile_id, *tile_begin, *tile_end;
+  uint32_t *outpos;      // per current row: its row in the next storage, ROW_HOLE for holes
+  // dense per-tile ordering state
+  int *run_begin, *run_len;      // run of the tile in the current storage
+  int *out_begin, *total;        // run of the tile in the next storage (= next substep's run)
+  int *stay_cnt, *stay_next;     // rows of the run still owned by the tile (now / after this G2P)
+  int *arr_cnt, *arr_off, *arr_len, *arr_cur;
   int *slot_map;
+  TileMeta *meta;                // [slot]
+  uint32_t *mover_dst, *mover_idx;      // consumed by the ordering
+  uint32_t *mover_dst_n, *mover_idx_n;  // produced by G2P
+  uint32_t *arrivals, *arrivals_sorted;
+  int *blocksum;
   float4 *arena;
   const float4 *sdf4;
   Counters *cnt;
   int cap_tiles;
+  int cap_particles;
 };
 
 // ------------------------------------------------------------------------------ helpers
@@ -244,53 +266,170 @@ __global__ void k_fill_u32(uint32_t *a, int n, uint32_t v) {
   if (i < n) a[i] = v;
 }
 
-// ------------------------------------------------------------------------------ tile list
-__global__ void k_clear_tiles(View V) {
-  int n = V.cnt->n_tiles + V.cnt->n_ghost;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) V.slot_map[V.tile_id[s]] = -1;
-}
-__global__ void k_reset_counters(Counters *c) {
-  c->n_tiles = 0;
-  c->n_ghost = 0;
-  c->n_alive = 0;
-  c->mig_in = 0;
+// ------------------------------------------------------------------------------ ordering
+// Replaces sort_particles_and_populate_grid (src/mpm.cpp:770-918) incrementally.
+//   k_mover_count : arr_cnt[dst]++ for every mover
+//   k_order_a/b/c : exclusive scans over the dense tile arrays of (stay+arrivals, arrivals, active)
+//                   -> next-run offsets, arrival-segment offsets, compact active-tile list + slot_map
+//   k_mover_place : movers into their tile's arrival segment (order arbitrary)
+//   k_mover_rank  : segment sorted by storage row => deterministic visiting order
+constexpr int ORD_B = 256, ORD_IPT = 4, ORD_TILE = ORD_B * ORD_IPT;
+
+__global__ void k_mover_count(View V, int ntot) {
+  const int n = V.cnt->n_movers;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+    const uint32_t d = V.mover_dst[m];
+    if (d < (uint32_t)ntot) atomicAdd(&V.arr_cnt[d], 1);
+  }
 }
 
-// Active-tile list = run heads of the sorted keys.  Replaces page_map / block_meta construction
-// (src/mpm.cpp:817-826,876-889) — on the device, no host page map.
-__global__ void k_build_tiles(View V, int n, uint32_t special_min) {
+// arrivals per tile straight from radix-sorted keys (upload path: every particle is an arrival)
+__global__ void k_count_sorted(View V, const uint32_t *keys_sorted, int n, int ntot) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t t = V.keys_sorted[i];
-  if (t >= special_min) {
-    if (i == 0 || V.keys_sorted[i - 1] < special_min) V.cnt->n_alive = i;
-    return;
-  }
-  if (i == n - 1) V.cnt->n_alive = n;
-  if (i > 0 && V.keys_sorted[i - 1] == t) return;
-  int slot = atomicAdd(&V.cnt->n_tiles, 1);
-  if (slot >= V.cap_tiles) {
-    atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY);
-    return;
-  }
-  int lo = i + 1, hi = n;  // end of the run: first index with a different key
+  const uint32_t t = keys_sorted[i];
+  if (t >= (uint32_t)ntot) return;
+  if (i > 0 && keys_sorted[i - 1] == t) return;
+  int lo = i + 1, hi = n;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
-    if (V.keys_sorted[mid] == t) lo = mid + 1;
+    if (keys_sorted[mid] == t) lo = mid + 1;
     else hi = mid;
   }
-  V.tile_id[slot] = (int)t;
-  V.tile_begin[slot] = i;
-  V.tile_end[slot] = lo;
-  V.slot_map[t] = slot;
+  V.arr_cnt[t] = lo - i;
+}
+
+__global__ void __launch_bounds__(ORD_B) k_order_a(View V, int ntot) {
+  typedef cub::BlockReduce<int, ORD_B> Red;
+  __shared__ typename Red::TempStorage tmp;
+  int s_tot = 0, s_arr = 0, s_act = 0;
+#pragma unroll
+  for (int k = 0; k < ORD_IPT; k++) {
+    const int t = blockIdx.x * ORD_TILE + threadIdx.x * ORD_IPT + k;
+    if (t < ntot) {
+      const int a = V.arr_cnt[t], tot = V.stay_cnt[t] + a;
+      s_tot += tot; s_arr += a; s_act += tot > 0;
+    }
+  }
+  s_tot = Red(tmp).Sum(s_tot); __syncthreads();
+  s_arr = Red(tmp).Sum(s_arr); __syncthreads();
+  s_act = Red(tmp).Sum(s_act);
+  if (threadIdx.x == 0) { V.blocksum[3 * blockIdx.x] = s_tot; V.blocksum[3 * blockIdx.x + 1] = s_arr; V.blocksum[3 * blockIdx.x + 2] = s_act; }
+}
+
+__global__ void __launch_bounds__(1024) k_order_b(View V, int nblocks) {
+  // single CTA: exclusive scan of the three block sums (nblocks is a few thousand at most)
+  typedef cub::BlockScan<int, 1024> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  int carry[3] = {0, 0, 0};
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      int v = i < nblocks ? V.blocksum[3 * i + c] : 0, ex, agg;
+      Scan(tmp).ExclusiveSum(v, ex, agg);
+      __syncthreads();
+      if (i < nblocks) V.blocksum[3 * i + c] = ex + carry[c];
+      carry[c] += agg;
+    }
+  }
+  if (threadIdx.x == 0) {
+    V.cnt->n_alive = carry[0];
+    V.cnt->n_tiles = carry[2];
+    V.cnt->n_ghost = 0;
+    if (carry[2] > V.cap_tiles) atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY);
+    if (carry[0] > V.cap_particles) atomicOr(&V.cnt->error, DEVERR_PARTICLE_CAPACITY);
+  }
+}
+
+__global__ void __launch_bounds__(ORD_B) k_order_c(View V, int ntot) {
+  typedef cub::BlockScan<int, ORD_B> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  int tot[ORD_IPT], arr[ORD_IPT], act[ORD_IPT];
+  int s_tot = 0, s_arr = 0, s_act = 0;
+#pragma unroll
+  for (int k = 0; k < ORD_IPT; k++) {
+    const int t = blockIdx.x * ORD_TILE + threadIdx.x * ORD_IPT + k;
+    tot[k] = arr[k] = act[k] = 0;
+    if (t < ntot) {
+      arr[k] = V.arr_cnt[t];
+      tot[k] = V.stay_cnt[t] + arr[k];
+      act[k] = tot[k] > 0;
+    }
+    s_tot += tot[k]; s_arr += arr[k]; s_act += act[k];
+  }
+  int e_tot, e_arr, e_act;
+  Scan(tmp).ExclusiveSum(s_tot, e_tot); __syncthreads();
+  Scan(tmp).ExclusiveSum(s_arr, e_arr); __syncthreads();
+  Scan(tmp).ExclusiveSum(s_act, e_act);
+  e_tot += V.blocksum[3 * blockIdx.x];
+  e_arr += V.blocksum[3 * blockIdx.x + 1];
+  e_act += V.blocksum[3 * blockIdx.x + 2];
+#pragma unroll
+  for (int k = 0; k < ORD_IPT; k++) {
+    const int t = blockIdx.x * ORD_TILE + threadIdx.x * ORD_IPT + k;
+    if (t < ntot) {
+      V.out_begin[t] = e_tot;
+      V.total[t] = tot[k];
+      V.arr_off[t] = e_arr;
+      V.arr_len[t] = arr[k];
+      V.arr_cnt[t] = 0;   // ready for the next substep's count
+      V.arr_cur[t] = 0;   // cursor of k_mover_place
+      V.stay_next[t] = 0; // G2P writes it for the tiles it visits
+      int slot = -1;
+      if (act[k] && e_act < V.cap_tiles) {
+        slot = e_act;
+        TileMeta m;
+        m.tile = t; m.run_begin = V.run_begin[t]; m.run_len = V.run_len[t]; m.arr_off = e_arr; m.arr_len = arr[k]; m.out_begin = e_tot;
+        m.pad0 = 0; m.pad1 = 0;
+        V.meta[slot] = m;
+      }
+      V.slot_map[t] = slot;
+    }
+    e_tot += tot[k]; e_arr += arr[k]; e_act += act[k];
+  }
+}
+
+__global__ void k_mover_place(View V, int ntot) {
+  const int n = V.cnt->n_movers;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+    const uint32_t d = V.mover_dst[m];
+    if (d < (uint32_t)ntot) {
+      const int pos = atomicAdd(&V.arr_cur[d], 1);
+      V.arrivals[V.arr_off[d] + pos] = V.mover_idx[m];
+    }
+  }
+}
+
+__global__ void k_mover_rank(View V, int ntot) {
+  const int n = V.cnt->n_movers;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+    const uint32_t d = V.mover_dst[m];
+    if (d < (uint32_t)ntot) {
+      const uint32_t idx = V.mover_idx[m];
+      const int off = V.arr_off[d], len = V.arr_len[d];
+      int rank = 0;
+      for (int e = 0; e < len; e++) rank += V.arrivals[off + e] < idx;
+      V.arrivals_sorted[off + rank] = idx;
+    }
+  }
+}
+
+// end of a substep: the lists and runs G2P produced become the current ones
+__global__ void k_step_commit(Counters *c) {
+  c->n_movers = c->n_movers_next;
+  c->n_movers_next = 0;
+  c->n_store = c->n_alive;  // G2P wrote one row per binned particle
 }
 
 // ------------------------------------------------------------------------------ P2G
 // Replaces MPM<3>::rasterize_optimized / block_op_normal (src/transfer.cpp:467-569).
-// One 64-thread CTA per active tile (persistent round-robin).  Per chunk of <=CH particles:
-//   1. stage: coalesced float4 loads of the P2G set (64 B/particle) into padded shared rows;
+// One 64-thread CTA per active tile (persistent round-robin).  A tile's rows are its run (unit
+// stride, holes where a particle left) followed by its arrivals.  Per chunk of <=CH rows:
+//   1. stage: 16-byte async copies (LDGSTS) of the P2G set (64 B/particle) into padded shared rows,
+//      all in flight at once;
 //   2. sort:  stable counting sort of the rows by cell (warp match + per-(pass,warp) histograms),
-//             bit-reproducible; the sorted position is also published for G2P's output order;
+//             bit-reproducible; publishes each particle's row in the next storage (outpos);
 //   3. accumulate: thread c owns cell c and streams that cell's particles, accumulating all
 //      27 nodes x (p_x,p_y,p_z,m) in 108 REGISTERS — every particle of a cell shares one stencil;
 //   4. flush: each warp adds its registers into the shared 6x6x6 arena, conflict-free by layout
@@ -313,49 +452,56 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
   const int n_tiles = V.cnt->n_tiles;
   const int cx = tid >> 4, cy = (tid >> 2) & 3, cz = tid & 3;
   for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
-    const int begin = V.tile_begin[slot], end = V.tile_end[slot];
-    const int tile = V.tile_id[slot];
+    const TileMeta tm = V.meta[slot];
+    const int tile = tm.tile;
+    const int nrow_tile = tm.run_len + tm.arr_len;
     const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
     const float fbx = (float)(tx * 4 + cx), fby = (float)(ty * 4 + cy), fbz = (float)(tz * 4 + cz);
     float acc[27][4];
 #pragma unroll
     for (int n = 0; n < 27; n++) { acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f; }
     for (int n = tid; n < AR_SIZE; n += P2G_T) { s_arena[0][n] = 0.f; s_arena[1][n] = 0.f; s_arena[2][n] = 0.f; s_arena[3][n] = 0.f; }
+    int vbase = 0;  // valid rows in the chunks already processed
+    // storage row of tile-row g: run rows first, then arrivals
+    auto row_of = [&](int g) -> uint32_t {
+      return g < tm.run_len ? (uint32_t)(tm.run_begin + g) : V.arrivals_sorted[tm.arr_off + (g - tm.run_len)];
+    };
 
-    for (int cb = begin; cb < end; cb += P2G_CH) {
-      const int nrows = min(P2G_CH, end - cb);
+    for (int cb = 0; cb < nrow_tile; cb += P2G_CH) {
+      const int nrows = min(P2G_CH, nrow_tile - cb);
 #pragma unroll
       for (int e = 0; e < P2G_K * 2; e++) s_hist[e][tid] = 0;
-      __syncthreads();
-      // ---- 1: stage rows: all gathers of the chunk in flight at once (perm, then 4 x 16 B per row)
-      {
-        uint32_t pidx[P2G_K];
+      // ---- 1: stage rows: all copies of the chunk in flight at once
+      uint32_t pidx[P2G_K];
+      bool valid[P2G_K];
 #pragma unroll
-        for (int k = 0; k < P2G_K; k++) {
-          const int r = k * P2G_T + tid;
-          pidx[k] = r < nrows ? V.perm[cb + r] : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < P2G_K; k++) {
-          const int r = k * P2G_T + tid;
-          if (r < nrows) {
-            const int ri = r + (r >> 3);
-            cp_async16(&s_rows[0][ri], &V.q[0][pidx[k]]);
-            cp_async16(&s_rows[1][ri], &V.q[1][pidx[k]]);
-            cp_async16(&s_rows[2][ri], &V.q[2][pidx[k]]);
-            cp_async16(&s_rows[3][ri], &V.q[3][pidx[k]]);
-          }
-        }
-        cp_async_commit();
-        cp_async_wait_all();
+      for (int k = 0; k < P2G_K; k++) {
+        const int r = k * P2G_T + tid;
+        pidx[k] = r < nrows ? row_of(cb + r) : 0u;
       }
+#pragma unroll
+      for (int k = 0; k < P2G_K; k++) {
+        const int r = k * P2G_T + tid;
+        valid[k] = false;
+        if (r < nrows) {
+          const int ri = r + (r >> 3);
+          cp_async16(&s_rows[0][ri], &V.q[0][pidx[k]]);
+          cp_async16(&s_rows[1][ri], &V.q[1][pidx[k]]);
+          cp_async16(&s_rows[2][ri], &V.q[2][pidx[k]]);
+          cp_async16(&s_rows[3][ri], &V.q[3][pidx[k]]);
+          valid[k] = (cb + r >= tm.run_len) || (V.keys[pidx[k]] == (uint32_t)tile);  // run rows may be holes
+        }
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+      __syncthreads();
       // ---- 2a: per-(pass,warp) cell histograms (each thread reads back its own rows)
       uint32_t cr[P2G_K];
 #pragma unroll
       for (int k = 0; k < P2G_K; k++) {
         const int r = k * P2G_T + tid;
-        int cell = 64 + warp;  // invalid rows: a private bucket
-        if (r < nrows) {
+        int cell = 64 + warp;  // holes and rows past the end: a private bucket
+        if (valid[k]) {
           const float4 a0 = s_rows[0][r + (r >> 3)];
           int bx, by, bz;
           float rr;
@@ -382,7 +528,6 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
           s_hist[e][c] = (unsigned short)run;
           run += h;
         }
-        // warp-level exclusive scan of `run` over the 64 cells
         int incl = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -396,7 +541,7 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
         __syncthreads();
         if (tid == 63) s_start[64] = base0 + incl;
       }
-      // ---- 2c: scatter row ids to their sorted position; publish it for G2P
+      // ---- 2c: scatter row ids to their sorted position; publish the output row for G2P
 #pragma unroll
       for (int k = 0; k < P2G_K; k++) {
         const int r = k * P2G_T + tid;
@@ -404,7 +549,9 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
         if (cell < 64) {
           const int pos = s_start[cell] + s_hist[k * 2 + warp][cell] + (int)(cr[k] & 0xffffu);
           s_order[pos] = (unsigned short)r;
-          V.sorted_pos[cb + r] = (uint32_t)(cb + pos);
+          V.outpos[pidx[k]] = (uint32_t)(tm.out_begin + vbase + pos);
+        } else if (r < nrows) {
+          V.outpos[pidx[k]] = ROW_HOLE;
         }
       }
       __syncthreads();
@@ -450,6 +597,7 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
           }
         }
       }
+      vbase += s_start[64];
       __syncthreads();  // rows / order / hist are reused by the next chunk
     }
     // ---- 4: flush registers to the shared arena, one warp at a time (deterministic order)
@@ -543,7 +691,7 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int n_tiles = V.cnt->n_tiles;
   for (int slot = gw; slot < n_tiles; slot += nw) {
-    const int tile = V.tile_id[slot];
+    const int tile = V.meta[slot].tile;
     const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
     int my_nb = -1;
     if (lane < 27) {
@@ -573,39 +721,46 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel) {
 // ------------------------------------------------------------------------------ G2P
 // Replaces MPM<3>::resample_optimized / block_op_normal (src/transfer.cpp:837-954) + Particle::plasticity +
 // clear_boundary_particles (src/mpm.cpp:583-633); produces the affine matrix of the NEXT rasterize
-// (calculate_force of the updated state) and the next substep's sort key.
+// (calculate_force of the updated state), writes the tile's particles cell-sorted into one contiguous
+// run of the other buffer, and appends the particles whose base node left the tile to the mover list.
 // Persistent CTAs walk their tiles chunk by chunk through a two-stage cp.async pipeline: while the
-// warps compute chunk i out of one shared buffer, the gathered rows (64 B/particle) of chunk i+1
-// and, at a tile change, that tile's 216 node velocities are already in flight into the other.
-constexpr int G2P_CH = 256;  // particles per pipeline stage
+// warps compute chunk i out of one shared buffer, the rows (64 B/particle) of chunk i+1 and, at a
+// tile change, that tile's 216 node velocities are already in flight into the other.
+constexpr int G2P_CH = 256;  // rows per pipeline stage
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4 *vel) {
   __shared__ float4 s_vel[2][ARENA];
   __shared__ float4 s_in[2][4][G2P_CH];
+  __shared__ uint32_t s_out[2][G2P_CH];  // output row of every staged row (ROW_HOLE = skip)
+  __shared__ int s_stay;
   constexpr int KPT = G2P_CH / BLOCK;
   const int tid = threadIdx.x;
   const int n_tiles = V.cnt->n_tiles;
   const float scale = -4.0f * P.inv_dx * P.dt;  // src/transfer.cpp:938
-  struct Item { int slot, cb, end, first; };
+  struct Item { int slot, rb, first; TileMeta tm; };
   auto first_item = [&](int slot) {
-    Item it{slot, 0, 0, 1};
-    if (slot < n_tiles) { it.cb = V.tile_begin[slot]; it.end = V.tile_end[slot]; }
+    Item it;
+    it.slot = slot; it.rb = 0; it.first = 1;
+    if (slot < n_tiles) it.tm = V.meta[slot];
+    else { it.tm.run_len = 0; it.tm.arr_len = 0; it.tm.tile = 0; it.tm.run_begin = 0; it.tm.arr_off = 0; it.tm.out_begin = 0; }
     return it;
   };
   auto next_item = [&](const Item &it) {
-    if (it.cb + G2P_CH < it.end) return Item{it.slot, it.cb + G2P_CH, it.end, 0};
+    if (it.rb + G2P_CH < it.tm.run_len + it.tm.arr_len) { Item n = it; n.rb += G2P_CH; n.first = 0; return n; }
     return first_item(it.slot + (int)gridDim.x);
   };
-  // puts one item in flight: rows of the G2P set (x|mass, F, scalar|vol|tag) and, for the first chunk of
-  // a tile, the tile's node velocities
+  // puts one item in flight: rows of the G2P set (x|mass, F, scalar|vol|tag), their output rows and, for
+  // the first chunk of a tile, the tile's node velocities
   auto prefetch = [&](const Item &it, int buf, int vbuf) {
     if (it.slot < n_tiles) {
-      const int nrows = min(G2P_CH, it.end - it.cb);
+      const int nrow_tile = it.tm.run_len + it.tm.arr_len;
+      const int nrows = min(G2P_CH, nrow_tile - it.rb);
       uint32_t pidx[KPT];
 #pragma unroll
       for (int k = 0; k < KPT; k++) {
-        const int r = k * BLOCK + tid;
-        pidx[k] = r < nrows ? V.perm[it.cb + r] : 0u;
+        const int r = k * BLOCK + tid, g = it.rb + r;
+        pidx[k] = 0u;
+        if (r < nrows) pidx[k] = g < it.tm.run_len ? (uint32_t)(it.tm.run_begin + g) : V.arrivals_sorted[it.tm.arr_off + (g - it.tm.run_len)];
       }
       if (it.first) {
         const float4 *src = vel + (size_t)it.slot * ARENA;
@@ -619,11 +774,14 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4
           cp_async16(&s_in[buf][1][r], &V.q[4][pidx[k]]);
           cp_async16(&s_in[buf][2][r], &V.q[5][pidx[k]]);
           cp_async16(&s_in[buf][3][r], &V.q[6][pidx[k]]);
+          unsigned d = (unsigned)__cvta_generic_to_shared(&s_out[buf][r]);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(&V.outpos[pidx[k]]));
         }
       }
     }
     cp_async_commit();
   };
+  if (tid == 0) s_stay = 0;
   Item cur = first_item(blockIdx.x);
   int buf = 0, vbuf = 0;
   prefetch(cur, 0, 0);
@@ -634,13 +792,15 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4
     asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // the current item has landed, the next stays in flight
     __syncthreads();
     {
-      const int tile = V.tile_id[cur.slot];
+      const int tile = cur.tm.tile;
       const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
-      const int nrows = min(G2P_CH, cur.end - cur.cb);
+      const int nrows = min(G2P_CH, cur.tm.run_len + cur.tm.arr_len - cur.rb);
       const float4 *sv = s_vel[vbuf];
+      int my_stay = 0;
       for (int r = tid; r < nrows; r += BLOCK) {
-        const int j = cur.cb + r;
-        const size_t o = V.sorted_pos[j];  // (tile,cell)-sorted output position, consumed by the stores below
+        const uint32_t orow = s_out[buf][r];
+        if (orow == ROW_HOLE) continue;  // the particle that was here now belongs to another tile
+        const size_t o = orow;
         const float4 q0 = s_in[buf][0][r], q4 = s_in[buf][1][r], q5 = s_in[buf][2][r], q6 = s_in[buf][3][r];
         const float mass = q0.w, vol = q6.z;
         const uint32_t tag = __float_as_uint(q6.w);
@@ -705,12 +865,23 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4
         uint32_t key = make_key(P, x.x, x.y, x.z);
         if (P.clean_boundary && reference_deletes(P, x, v)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
         if (!isfinite(x.x + x.y + x.z)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
-        // write at the (tile,cell)-sorted position: storage order follows the sort
+        // one contiguous, cell-sorted run per tile in the other buffer
         store_particle(V.qn, o, x, mass, v, A, F, ps, vol, tag, B);
         V.keys_next[o] = key;
+        if (key == (uint32_t)tile) {
+          my_stay++;
+        } else if (key != (uint32_t)(P.ntiles_total + SPECIAL_DEAD)) {
+          const int m = atomicAdd(&V.cnt->n_movers_next, 1);  // ~0.5 % of the particles per substep
+          V.mover_dst_n[m] = key;
+          V.mover_idx_n[m] = (uint32_t)o;
+        }
       }
+      if (my_stay) atomicAdd(&s_stay, my_stay);
     }
     __syncthreads();  // everyone is done with `buf` before the prefetch after next overwrites it
+    if (nxt.slot != cur.slot) {
+      if (tid == 0) { V.stay_next[cur.tm.tile] = s_stay; s_stay = 0; }
+    }
     cur = nxt;
     buf ^= 1;
     vbuf = nvbuf;
@@ -752,13 +923,13 @@ __global__ void k_planes_to_sdf(Params P, int n_planes, const float4 *planes, fl
 // ------------------------------------------------------------------------------ z-slab exchange
 // Halo message: int4 header {count,0,0,0} | int tile_xy[cap_xy] | float4 arena[cap_xy][216].
 // Packs the arenas of the owned tiles of one tile layer (the partial sums of (p,m) the neighbour
-// rank's nodes need); the neighbour registers them as ghost tiles, so its G2P sums them in the
-// same fixed order as a single-GPU run would.
+// rank's nodes need); the neighbour registers them as ghost tiles, so its grid update sums them in
+// the same fixed order as a single-GPU run would.
 __global__ void k_halo_pack(View V, Params P, int layer_z, int cap_xy, int *hdr, int *tile_xy, float4 *arenas) {
   __shared__ int s_idx;
   const int n_tiles = V.cnt->n_tiles;
   for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
-    const int tile = V.tile_id[slot];
+    const int tile = V.meta[slot].tile;
     if (tile % P.nt[2] != layer_z) continue;  // uniform per CTA
     if (threadIdx.x == 0) {
       int idx = atomicAdd(&hdr[0], 1);
@@ -781,13 +952,7 @@ __global__ void k_halo_unpack(View V, Params P, int layer_z, int cap_xy, const i
     if (threadIdx.x == 0) {
       int slot = V.cnt->n_tiles + atomicAdd(&V.cnt->n_ghost, 1);
       if (slot >= V.cap_tiles) { atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY); slot = -1; }
-      else {
-        const int tile = tile_xy[e] * P.nt[2] + layer_z;
-        V.tile_id[slot] = tile;
-        V.tile_begin[slot] = 0;
-        V.tile_end[slot] = 0;
-        V.slot_map[tile] = slot;
-      }
+      else V.slot_map[tile_xy[e] * P.nt[2] + layer_z] = slot;  // rewritten densely by the next ordering
       s_slot = slot;
     }
     __syncthreads();
@@ -798,30 +963,45 @@ __global__ void k_halo_unpack(View V, Params P, int layer_z, int cap_xy, const i
   }
 }
 
-// Migration message: int4 header {count,0,0,0} | float4 record[cap][N_Q].
-__global__ void k_migrate_pack(View V, uint32_t *keys, int n, uint32_t key_face, uint32_t key_dead, int cap, int *hdr, float4 *rec) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || keys[i] != key_face) return;
-  int idx = atomicAdd(&hdr[0], 1);
-  keys[i] = key_dead;
-  if (idx >= cap) { atomicOr(&V.cnt->error, DEVERR_MIGRATE_CAPACITY); return; }
+// Migration message: int4 header {count,0,0,0} | float4 record[cap][N_Q].  Emigrants are the movers
+// whose destination is the face's special key; their row in the (new) current storage is a hole
+// for everybody else, the key is set dead so that downloads skip it.
+__global__ void k_migrate_pack(View V, uint32_t key_face, uint32_t key_dead, int cap, int *hdr, float4 *rec) {
+  const int n = V.cnt->n_movers;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+    if (V.mover_dst[m] != key_face) continue;
+    const uint32_t i = V.mover_idx[m];
+    const int idx = atomicAdd(&hdr[0], 1);
+    V.keys[i] = key_dead;
+    V.mover_dst[m] = key_dead;
+    if (idx >= cap) { atomicOr(&V.cnt->error, DEVERR_MIGRATE_CAPACITY); continue; }
 #pragma unroll
-  for (int k = 0; k < N_Q; k++) rec[(size_t)idx * N_Q + k] = V.q[k][i];
+    for (int k = 0; k < N_Q; k++) rec[(size_t)idx * N_Q + k] = V.q[k][i];
+  }
 }
 
-__global__ void k_migrate_unpack(View V, Params P, uint32_t *keys, int cap_particles, int cap, const int *hdr, const float4 *rec) {
+// Immigrants are appended after the last row of the current storage and enter the mover list, so the
+// next ordering bins them like any other particle that changed tile.
+__global__ void k_migrate_unpack(View V, Params P, int cap, const int *hdr, const float4 *rec) {
   const int count = min(hdr[0], cap);
-  const int base = V.cnt->n_alive + V.cnt->mig_in;
+  const int base = V.cnt->n_store, mbase = V.cnt->n_movers;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
     const int dst = base + e;
-    if (dst >= cap_particles) { atomicOr(&V.cnt->error, DEVERR_PARTICLE_CAPACITY); continue; }
+    if (dst >= V.cap_particles) { atomicOr(&V.cnt->error, DEVERR_PARTICLE_CAPACITY); continue; }
     float4 r0 = rec[(size_t)e * N_Q];
 #pragma unroll
     for (int k = 0; k < N_Q; k++) V.q[k][dst] = rec[(size_t)e * N_Q + k];
-    keys[dst] = make_key(P, r0.x, r0.y, r0.z);
+    const uint32_t key = make_key(P, r0.x, r0.y, r0.z);
+    V.keys[dst] = key;
+    V.mover_dst[mbase + e] = key;
+    V.mover_idx[mbase + e] = (uint32_t)dst;
   }
 }
-__global__ void k_migrate_commit(Counters *c, const int *hdr, int cap) { c->mig_in += min(hdr[0], cap); }
+__global__ void k_migrate_commit(Counters *c, const int *hdr, int cap, int cap_particles) {
+  const int n = min(min(hdr[0], cap), max(cap_particles - c->n_store, 0));
+  c->n_store += n;
+  c->n_movers += n;
+}
 
 }  // namespace mpmb
 
@@ -837,31 +1017,34 @@ struct MpmbEngine {
   std::string err;
   bool sticky_cuda = false;
 
-  int64_t cap = 0;       // particle slots allocated
-  int n_bound = 0;       // slots that may hold live particles (host upper bound)
-  int cur = 0;           // which q buffer is current
+  int64_t cap = 0;       // particle rows allocated per buffer
+  int cur = 0;           // which q/keys buffer is current
+  int ord = 0;           // which (run,stay) set is current
+  int mov = 0;           // which mover list the next ordering consumes
+  bool fresh = false;    // storage was just uploaded: arrival lists come from the radix sort
   float4 *q[2][N_Q] = {};
-  uint32_t *keys[2] = {};       // keys in storage order (cur / next)
-  uint32_t *keys_sorted = nullptr, *perm = nullptr, *iota = nullptr, *sorted_pos = nullptr;
+  uint32_t *keys[2] = {};       // tile of every row (cur / next)
+  uint32_t *outpos = nullptr;
+  uint32_t *mover_dst[2] = {}, *mover_idx[2] = {};
+  uint32_t *arrivals = nullptr, *arrivals_sorted = nullptr;
+  uint32_t *keys_sorted = nullptr, *iota = nullptr;  // upload-time radix sort scratch
   uint32_t special_min = 0, key_dead = 0;
   void *cub_temp = nullptr;
   size_t cub_bytes = 0;
   int key_bits = 32;
 
   int cap_tiles = 0;
-  int *tile_id = nullptr, *tile_begin = nullptr, *tile_end = nullptr, *slot_map = nullptr;
+  int ntot = 0;           // tiles of the dense tile grid
+  int ord_blocks = 0;
+  int *run_begin[2] = {}, *run_len[2] = {}, *stay[2] = {};  // [ord]: current / next
+  int *arr_cnt = nullptr, *arr_off = nullptr, *arr_len = nullptr, *arr_cur = nullptr, *slot_map = nullptr, *blocksum = nullptr;
+  TileMeta *meta = nullptr;
   float4 *arena = nullptr;
   float4 *vel = nullptr;  // node velocities per active tile (k_grid -> k_g2p)
   float4 *sdf4 = nullptr;
   Counters *cnt = nullptr;
 
   int stage = 0;  // 0 idle/after resample, 1 after sort, 2 after rasterize
-  // z-slab bookkeeping: n_alive is read back with a lag so the host never waits for the device
-  static constexpr int RING = 8;
-  int *alive_ring = nullptr;  // pinned
-  cudaEvent_t alive_ev[RING] = {};
-  int64_t alive_step[RING] = {};
-  int64_t sort_step = 0;
   int64_t mig_cap = 0;
   uint32_t id_base = 0;
   int num_sms = 148;
@@ -911,18 +1094,33 @@ static View make_view(MpmbEngine *h) {
     V.q[k] = h->q[h->cur][k];
     V.qn[k] = h->q[h->cur ^ 1][k];
   }
-  V.keys_sorted = h->keys_sorted;
-  V.perm = h->perm;
+  V.keys = h->keys[h->cur];
   V.keys_next = h->keys[h->cur ^ 1];
-  V.sorted_pos = h->sorted_pos;
-  V.tile_id = h->tile_id;
-  V.tile_begin = h->tile_begin;
-  V.tile_end = h->tile_end;
+  V.outpos = h->outpos;
+  V.run_begin = h->run_begin[h->ord];
+  V.run_len = h->run_len[h->ord];
+  V.out_begin = h->run_begin[h->ord ^ 1];
+  V.total = h->run_len[h->ord ^ 1];
+  V.stay_cnt = h->stay[h->ord];
+  V.stay_next = h->stay[h->ord ^ 1];
+  V.arr_cnt = h->arr_cnt;
+  V.arr_off = h->arr_off;
+  V.arr_len = h->arr_len;
+  V.arr_cur = h->arr_cur;
   V.slot_map = h->slot_map;
+  V.meta = h->meta;
+  V.mover_dst = h->mover_dst[h->mov];
+  V.mover_idx = h->mover_idx[h->mov];
+  V.mover_dst_n = h->mover_dst[h->mov ^ 1];
+  V.mover_idx_n = h->mover_idx[h->mov ^ 1];
+  V.arrivals = h->arrivals;
+  V.arrivals_sorted = h->arrivals_sorted;
+  V.blocksum = h->blocksum;
   V.arena = h->arena;
   V.sdf4 = h->sdf4;
   V.cnt = h->cnt;
   V.cap_tiles = h->cap_tiles;
+  V.cap_particles = (int)h->cap;
   return V;
 }
 
@@ -957,9 +1155,11 @@ static int free_particles(MpmbEngine *h) {
   for (int b = 0; b < 2; b++) {
     for (int k = 0; k < N_Q; k++) { cudaFree(h->q[b][k]); h->q[b][k] = nullptr; }
     cudaFree(h->keys[b]); h->keys[b] = nullptr;
+    cudaFree(h->mover_dst[b]); cudaFree(h->mover_idx[b]);
+    h->mover_dst[b] = h->mover_idx[b] = nullptr;
   }
-  cudaFree(h->keys_sorted); cudaFree(h->perm); cudaFree(h->iota); cudaFree(h->cub_temp); cudaFree(h->sorted_pos);
-  h->keys_sorted = h->perm = h->iota = h->sorted_pos = nullptr;
+  cudaFree(h->outpos); cudaFree(h->arrivals); cudaFree(h->arrivals_sorted); cudaFree(h->keys_sorted); cudaFree(h->iota); cudaFree(h->cub_temp);
+  h->outpos = h->arrivals = h->arrivals_sorted = h->keys_sorted = h->iota = nullptr;
   h->cub_temp = nullptr;
   h->cap = 0;
   return 0;
@@ -968,18 +1168,21 @@ static int free_particles(MpmbEngine *h) {
 static int alloc_particles(MpmbEngine *h, int64_t cap) {
   free_particles(h);
   if (cap >= (1ll << 26)) return fail(h, MPMB_ERR_CAPACITY, "capacity %lld exceeds 2^26 particles per GPU", (long long)cap);
+  if (cap < 1) cap = 1;
   for (int b = 0; b < 2; b++) {
     for (int k = 0; k < N_Q; k++) CUDA_TRY(h, cudaMalloc(&h->q[b][k], sizeof(float4) * cap));
     CUDA_TRY(h, cudaMalloc(&h->keys[b], sizeof(uint32_t) * cap));
-    k_fill_u32<<<(unsigned)((cap + 255) / 256), 256, 0, h->stream>>>(h->keys[b], (int)cap, h->key_dead);
+    CUDA_TRY(h, cudaMalloc(&h->mover_dst[b], sizeof(uint32_t) * cap));
+    CUDA_TRY(h, cudaMalloc(&h->mover_idx[b], sizeof(uint32_t) * cap));
   }
+  CUDA_TRY(h, cudaMalloc(&h->outpos, sizeof(uint32_t) * cap));
+  CUDA_TRY(h, cudaMalloc(&h->arrivals, sizeof(uint32_t) * cap));
+  CUDA_TRY(h, cudaMalloc(&h->arrivals_sorted, sizeof(uint32_t) * cap));
   CUDA_TRY(h, cudaMalloc(&h->keys_sorted, sizeof(uint32_t) * cap));
-  CUDA_TRY(h, cudaMalloc(&h->perm, sizeof(uint32_t) * cap));
   CUDA_TRY(h, cudaMalloc(&h->iota, sizeof(uint32_t) * cap));
-  CUDA_TRY(h, cudaMalloc(&h->sorted_pos, sizeof(uint32_t) * cap));
   k_iota<<<(unsigned)((cap + 255) / 256), 256, 0, h->stream>>>(h->iota, (int)cap);
   h->cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, h->cub_bytes, h->keys[0], h->keys_sorted, h->iota, h->perm, (int)cap, 0, 32, h->stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, h->cub_bytes, h->keys[0], h->keys_sorted, h->iota, h->arrivals_sorted, (int)cap, 0, 32, h->stream);
   CUDA_TRY(h, cudaMalloc(&h->cub_temp, h->cub_bytes));
   h->cap = cap;
   return MPMB_OK;
@@ -1048,10 +1251,18 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
     mpmb_destroy(h);
     return fail(nullptr, MPMB_ERR_CUDA, "%s", msg.c_str());
   };
-  if (cudaMalloc(&h->tile_id, sizeof(int) * cap_tiles) != cudaSuccess) return bail("cudaMalloc tile_id");
-  if (cudaMalloc(&h->tile_begin, sizeof(int) * cap_tiles) != cudaSuccess) return bail("cudaMalloc tile_begin");
-  if (cudaMalloc(&h->tile_end, sizeof(int) * cap_tiles) != cudaSuccess) return bail("cudaMalloc tile_end");
-  if (cudaMalloc(&h->slot_map, sizeof(int) * ntot) != cudaSuccess) return bail("cudaMalloc slot_map");
+  h->ntot = (int)ntot;
+  h->ord_blocks = (int)((ntot + ORD_TILE - 1) / ORD_TILE);
+  {
+    int **dense[] = {&h->run_begin[0], &h->run_begin[1], &h->run_len[0], &h->run_len[1], &h->stay[0], &h->stay[1],
+                     &h->arr_cnt, &h->arr_off, &h->arr_len, &h->arr_cur, &h->slot_map};
+    for (int **pp : dense) {
+      if (cudaMalloc(pp, sizeof(int) * ntot) != cudaSuccess) return bail("cudaMalloc dense tile array");
+      cudaMemset(*pp, 0, sizeof(int) * ntot);
+    }
+  }
+  if (cudaMalloc(&h->blocksum, sizeof(int) * 3 * (h->ord_blocks + 1)) != cudaSuccess) return bail("cudaMalloc blocksum");
+  if (cudaMalloc(&h->meta, sizeof(TileMeta) * cap_tiles) != cudaSuccess) return bail("cudaMalloc meta");
   if (cudaMalloc(&h->arena, sizeof(float4) * ARENA * (cap_tiles + 1)) != cudaSuccess) return bail("cudaMalloc arena");
   cudaMemset(h->arena + (size_t)ARENA * cap_tiles, 0, sizeof(float4) * ARENA);  // the all-zero arena read for absent neighbours
   if (cudaMalloc(&h->vel, sizeof(float4) * ARENA * cap_tiles) != cudaSuccess) return bail("cudaMalloc vel");
@@ -1064,8 +1275,6 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
       mpmb_destroy(h);
       return fail(nullptr, MPMB_ERR_INVALID, "bad slab [%d,%d) for %d tile layers", cfg->tile_z0, cfg->tile_z1, P.nt[2]);
     }
-    if (cudaMallocHost(&h->alive_ring, sizeof(int) * MpmbEngine::RING) != cudaSuccess) return bail("cudaMallocHost");
-    for (int i = 0; i < MpmbEngine::RING; i++) { cudaEventCreateWithFlags(&h->alive_ev[i], cudaEventDisableTiming); h->alive_step[i] = -1; }
   }
   if (cfg->capacity > 0) {
     int rc = alloc_particles(h, cfg->capacity);
@@ -1080,10 +1289,12 @@ int mpmb_destroy(MpmbHandle h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   free_particles(h);
-  cudaFree(h->tile_id); cudaFree(h->tile_begin); cudaFree(h->tile_end); cudaFree(h->slot_map);
+  for (int b = 0; b < 2; b++) { cudaFree(h->run_begin[b]); cudaFree(h->run_len[b]); cudaFree(h->stay[b]); }
+  cudaFree(h->arr_cnt); cudaFree(h->arr_off); cudaFree(h->arr_len); cudaFree(h->arr_cur); cudaFree(h->slot_map); cudaFree(h->blocksum);
+  cudaFree(h->meta);
   cudaFree(h->arena); cudaFree(h->vel); cudaFree(h->sdf4); cudaFree(h->cnt);
   for (auto &e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-  if (h->alive_ring) { cudaFreeHost(h->alive_ring); for (int i = 0; i < MpmbEngine::RING; i++) cudaEventDestroy(h->alive_ev[i]); }
+
   delete h;
   return MPMB_OK;
 }
@@ -1156,7 +1367,7 @@ int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float 
 
 static int ensure_capacity(MpmbEngine *h, int64_t n) {
   int64_t want = n;
-  if (h->cfg.world > 1) want = n + n / 4 + 2 * MpmbEngine::RING * 2 * h->mig_cap;
+  if (h->cfg.world > 1) want = n + n / 4 + 16 * h->mig_cap;
   if (h->cfg.capacity > 0) {
     if (n > h->cap) return fail(h, MPMB_ERR_CAPACITY, "%lld particles exceed the configured capacity %lld", (long long)n, (long long)h->cap);
     return MPMB_OK;
@@ -1166,16 +1377,28 @@ static int ensure_capacity(MpmbEngine *h, int64_t n) {
 }
 
 static int finish_upload(MpmbEngine *h, int64_t n) {
-  // slots beyond n hold dead keys
-  if (h->cap > n) k_fill_u32<<<(unsigned)((h->cap - n + 255) / 256), 256, 0, h->stream>>>(h->keys[h->cur] + n, (int)(h->cap - n), h->key_dead);
-  h->n_bound = (int)n;
+  // Fresh storage in upload order: no runs yet, every particle is an "arrival" of its tile.  The
+  // one radix sort of the engine's life (per upload) groups the rows by tile; the ordinary
+  // ordering scan then lays out the first runs.
+  View V = make_view(h);
+  const size_t dense = sizeof(int) * (size_t)h->ntot;
+  CUDA_TRY(h, cudaMemsetAsync(h->run_begin[h->ord], 0, dense, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->run_len[h->ord], 0, dense, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->stay[h->ord], 0, dense, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->arr_cnt, 0, dense, h->stream));
+  Counters c{};
+  c.n_store = (int)n;
+  CUDA_TRY(h, cudaMemcpyAsync(h->cnt, &c, sizeof(int) * 3, cudaMemcpyHostToDevice, h->stream));          // n_store, n_tiles, n_ghost
+  CUDA_TRY(h, cudaMemsetAsync(&h->cnt->n_movers, 0, sizeof(int) * 3, h->stream));                          // n_movers, n_movers_next, n_alive
+  if (n > 0) {
+    cub::DeviceRadixSort::SortPairs(h->cub_temp, h->cub_bytes, h->keys[h->cur], h->keys_sorted, h->iota, h->arrivals_sorted, (int)n, 0, h->key_bits, h->stream);
+    k_count_sorted<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(V, h->keys_sorted, (int)n, h->ntot);
+    h->launches++;
+  }
+  h->fresh = true;
   h->stage = 0;
-  h->sort_step = 0;
-  for (int i = 0; i < MpmbEngine::RING; i++) h->alive_step[i] = -1;
-  CUDA_TRY(h, cudaMemsetAsync(&h->cnt->n_alive, 0, sizeof(int), h->stream));
-  int nn = (int)n;
-  CUDA_TRY(h, cudaMemcpyAsync(&h->cnt->n_alive, &nn, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaGetLastError());
   return MPMB_OK;
 }
 
@@ -1238,15 +1461,24 @@ int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slot
   return finish_upload(h, n);
 }
 
+static int read_n_store(MpmbEngine *h, int *n_store) {
+  Counters c;
+  CUDA_TRY(h, cudaMemcpy(&c, h->cnt, sizeof(c), cudaMemcpyDeviceToHost));
+  *n_store = c.n_store;
+  return MPMB_OK;
+}
+
 int mpmb_num_particles(MpmbHandle h, int64_t *n) {
   CHECK_HANDLE(h);
   if (!n) return fail(h, MPMB_ERR_INVALID, "null argument");
-  // live = storage-order keys that are not special
   int rc = mpmb_synchronize(h);
   if (rc != MPMB_OK) return rc;
-  if (h->n_bound == 0) { *n = 0; return MPMB_OK; }
-  std::vector<uint32_t> keys(h->n_bound);
-  CUDA_TRY(h, cudaMemcpy(keys.data(), h->keys[h->cur], sizeof(uint32_t) * h->n_bound, cudaMemcpyDeviceToHost));
+  int ns = 0;
+  if ((rc = read_n_store(h, &ns)) != MPMB_OK) return rc;
+  *n = 0;
+  if (ns == 0 || h->cap == 0) return MPMB_OK;
+  std::vector<uint32_t> keys(ns);
+  CUDA_TRY(h, cudaMemcpy(keys.data(), h->keys[h->cur], sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost));
   int64_t c = 0;
   for (uint32_t k : keys) c += (k < h->special_min);
   *n = c;
@@ -1259,9 +1491,10 @@ int mpmb_download_particles(MpmbHandle h, int64_t cap, int64_t *n_out, uint32_t 
   if (!n_out) return fail(h, MPMB_ERR_INVALID, "n_out is required");
   int rc = mpmb_synchronize(h);
   if (rc != MPMB_OK) return rc;
-  const int n = h->n_bound;
+  int n = 0;
+  if ((rc = read_n_store(h, &n)) != MPMB_OK) return rc;
   *n_out = 0;
-  if (n == 0) return MPMB_OK;
+  if (n == 0 || h->cap == 0) return MPMB_OK;
   // exclusive prefix of the alive flags (CUB scan)
   int *flags = nullptr, *prefix = nullptr;
   CUDA_TRY(h, cudaMalloc(&flags, sizeof(int) * n));
@@ -1315,7 +1548,9 @@ int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *in
                       int64_t *n_alive) {
   CHECK_HANDLE(h);
   if (!pool || !indices || !L || !n_alive) return fail(h, MPMB_ERR_INVALID, "null argument");
-  int64_t cap = h->n_bound, n = 0;
+  int ns_ = 0;
+  { int rc0 = mpmb_synchronize(h); if (rc0 != MPMB_OK) return rc0; rc0 = read_n_store(h, &ns_); if (rc0 != MPMB_OK) return rc0; }
+  int64_t cap = ns_ > 0 ? ns_ : 1, n = 0;
   std::vector<uint32_t> id(cap);
   std::vector<float> x(3 * cap), v(3 * cap), F(9 * cap), b(9 * cap), mass(cap), vol(cap), sc(cap);
   int rc = mpmb_download_particles(h, cap, &n, id.data(), x.data(), v.data(), F.data(), b.data(), mass.data(), vol.data(), sc.data(), nullptr);
@@ -1350,41 +1585,23 @@ int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *in
 int mpmb_sort_particles_and_populate_grid(MpmbHandle h) {
   CHECK_HANDLE(h);
   if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "sort must follow resample/upload");
-  if (h->cfg.world > 1 && h->sort_step > 0) {
-    // newest completed read-back of n_alive: live <= value + (steps since) * 2 * mig_cap
-    int best = -1;
-    for (int i = 0; i < MpmbEngine::RING; i++)
-      if (h->alive_step[i] >= 0 && (best < 0 || h->alive_step[i] > h->alive_step[best]) && cudaEventQuery(h->alive_ev[i]) == cudaSuccess) best = i;
-    if (best < 0) {  // nothing completed yet: wait for the oldest outstanding one
-      for (int i = 0; i < MpmbEngine::RING; i++)
-        if (h->alive_step[i] >= 0 && (best < 0 || h->alive_step[i] < h->alive_step[best])) best = i;
-      if (best >= 0) CUDA_TRY(h, cudaEventSynchronize(h->alive_ev[best]));
-    }
-    if (best >= 0) {
-      int64_t bound = (int64_t)h->alive_ring[best] + (h->sort_step - h->alive_step[best]) * 2 * h->mig_cap;
-      if (bound > h->cap) return fail(h, MPMB_ERR_CAPACITY, "slab particle bound %lld exceeds capacity %lld", (long long)bound, (long long)h->cap);
-      h->n_bound = (int)bound;
-    }
-  }
   prof_begin(h, 0);
-  View V = make_view(h);
-  k_clear_tiles<<<64, 256, 0, h->stream>>>(V);
-  k_reset_counters<<<1, 1, 0, h->stream>>>(h->cnt);
-  int n = h->n_bound;
-  if (n > 0) {
-    cub::DeviceRadixSort::SortPairs(h->cub_temp, h->cub_bytes, h->keys[h->cur], h->keys_sorted, h->iota, h->perm, n, 0, h->key_bits, h->stream);
-    k_build_tiles<<<(n + 255) / 256, 256, 0, h->stream>>>(V, n, h->special_min);
+  int nl = 3;
+  if (h->cap > 0) {
+    View V = make_view(h);
+    if (!h->fresh) { k_mover_count<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot); nl++; }
+    k_order_a<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot);
+    k_order_b<<<1, 1024, 0, h->stream>>>(V, h->ord_blocks);
+    k_order_c<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot);
+    if (!h->fresh) {
+      k_mover_place<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot);
+      k_mover_rank<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot);
+      nl += 2;
+    }
+    h->fresh = false;
   }
-  h->launches += 3;
-  prof_end(h, 3);
-  if (h->cfg.world > 1) {
-    int r = (int)(h->sort_step % MpmbEngine::RING);
-    if (h->alive_step[r] >= 0) CUDA_TRY(h, cudaEventSynchronize(h->alive_ev[r]));  // slot reuse
-    CUDA_TRY(h, cudaMemcpyAsync(&h->alive_ring[r], &h->cnt->n_alive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaEventRecord(h->alive_ev[r], h->stream));
-    h->alive_step[r] = h->sort_step;
-  }
-  h->sort_step++;
+  h->launches += nl;
+  prof_end(h, nl);
   CUDA_TRY(h, cudaGetLastError());
   h->stage = 1;
   return MPMB_OK;
@@ -1395,7 +1612,7 @@ int mpmb_rasterize(MpmbHandle h) {
   if (h->stage != 1) return fail(h, MPMB_ERR_STATE, "rasterize must follow sort_particles_and_populate_grid");
   prof_begin(h, 1);
   View V = make_view(h);
-  if (h->n_bound > 0) k_p2g<<<h->num_sms * 4, P2G_T, 0, h->stream>>>(V, h->P);  // 4 CTAs/SM resident (46 KB shared each)
+  if (h->cap > 0) k_p2g<<<h->num_sms * 4, P2G_T, 0, h->stream>>>(V, h->P);  // 4 CTAs/SM resident (46 KB shared each)
   h->launches += 1;
   prof_end(h, 1);
   CUDA_TRY(h, cudaGetLastError());
@@ -1408,17 +1625,17 @@ int mpmb_resample(MpmbHandle h) {
   if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "resample must follow rasterize");
   prof_begin(h, 2);
   View V = make_view(h);
-  // slots the kernel does not write (dead tail) must carry dead keys
-  if (h->n_bound > 0) {
-    const int nfill = h->cfg.world > 1 ? (int)h->cap : h->n_bound;  // slab runs: n_bound moves, keep every unused slot dead
-    k_fill_tail<<<64, 256, 0, h->stream>>>(h->keys[h->cur ^ 1], h->cnt, nfill, h->key_dead);
+  if (h->cap > 0) {
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel);
     k_g2p<128><<<h->num_sms * 5, 128, 0, h->stream>>>(V, h->P, h->vel);
+    k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt);
   }
   h->launches += 3;
   prof_end(h, 3);
   CUDA_TRY(h, cudaGetLastError());
-  h->cur ^= 1;
+  h->cur ^= 1;  // the buffer G2P wrote is the current storage ...
+  h->ord ^= 1;  // ... its runs / stay counts are the current ones ...
+  h->mov ^= 1;  // ... and its mover list feeds the next ordering
   h->stage = 0;
   return MPMB_OK;
 }
@@ -1545,10 +1762,8 @@ int mpmb_migrate_pack(MpmbHandle h, int32_t face, void *dev_buf) {
   char *b = (char *)dev_buf;
   CUDA_TRY(h, cudaMemsetAsync(b, 0, 16, h->stream));
   View V = make_view(h);
-  const int n = h->n_bound;
   const uint32_t key_face = h->special_min + (face == 0 ? SPECIAL_MIG_DOWN : SPECIAL_MIG_UP);
-  if (n > 0)
-    k_migrate_pack<<<(n + 255) / 256, 256, 0, h->stream>>>(V, h->keys[h->cur], n, key_face, h->key_dead, (int)h->mig_cap, (int *)b, (float4 *)(b + 16));
+  k_migrate_pack<<<h->num_sms * 2, 256, 0, h->stream>>>(V, key_face, h->key_dead, (int)h->mig_cap, (int *)b, (float4 *)(b + 16));
   h->launches++;
   prof_end(h, 1);
   CUDA_TRY(h, cudaGetLastError());
@@ -1563,8 +1778,8 @@ int mpmb_migrate_unpack(MpmbHandle h, int32_t face, const void *dev_buf) {
   prof_begin(h, 3);
   const char *b = (const char *)dev_buf;
   View V = make_view(h);
-  k_migrate_unpack<<<64, 256, 0, h->stream>>>(V, h->P, h->keys[h->cur], (int)h->cap, (int)h->mig_cap, (const int *)b, (const float4 *)(b + 16));
-  k_migrate_commit<<<1, 1, 0, h->stream>>>(h->cnt, (const int *)b, (int)h->mig_cap);
+  k_migrate_unpack<<<64, 256, 0, h->stream>>>(V, h->P, (int)h->mig_cap, (const int *)b, (const float4 *)(b + 16));
+  k_migrate_commit<<<1, 1, 0, h->stream>>>(h->cnt, (const int *)b, (int)h->mig_cap, (int)h->cap);
   h->launches += 2;
   prof_end(h, 2);
   CUDA_TRY(h, cudaGetLastError());
