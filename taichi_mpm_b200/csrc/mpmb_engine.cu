@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
 #pragma unroll
       for (int e = 0; e < P2G_K * 2; e++) s_hist[e][tid] = 0;
       // ---- 1: stage rows: all copies of the chunk in flight at once
-      uint32_t pidx[P2G_K];
+      uint32_t pidx[P2G_K], rkey[P2G_K];
       bool valid[P2G_K];
 #pragma unroll
       for (int k = 0; k < P2G_K; k++) {
@@ -482,16 +482,18 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
 #pragma unroll
       for (int k = 0; k < P2G_K; k++) {
         const int r = k * P2G_T + tid;
-        valid[k] = false;
+        rkey[k] = (uint32_t)tile;
         if (r < nrows) {
           const int ri = r + (r >> 3);
           cp_async16(&s_rows[0][ri], &V.q[0][pidx[k]]);
           cp_async16(&s_rows[1][ri], &V.q[1][pidx[k]]);
           cp_async16(&s_rows[2][ri], &V.q[2][pidx[k]]);
           cp_async16(&s_rows[3][ri], &V.q[3][pidx[k]]);
-          valid[k] = (cb + r >= tm.run_len) || (V.keys[pidx[k]] == (uint32_t)tile);  // run rows may be holes
+          if (cb + r < tm.run_len) rkey[k] = V.keys[pidx[k]];  // run rows may be holes; consumed after the wait
         }
       }
+#pragma unroll
+      for (int k = 0; k < P2G_K; k++) valid[k] = (k * P2G_T + tid < nrows) && rkey[k] == (uint32_t)tile;
       cp_async_commit();
       cp_async_wait_all();
       __syncthreads();
@@ -1048,6 +1050,7 @@ struct MpmbEngine {
   int64_t mig_cap = 0;
   uint32_t id_base = 0;
   int num_sms = 148;
+  int grid_p2g = 148 * 4, grid_g2p = 148 * 4;  // persistent grids = SMs x resident CTAs (queried)
   int64_t launches = 0;
 
   bool profiling = false;
@@ -1242,6 +1245,11 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, cfg->device);
   h->num_sms = prop.multiProcessorCount;
+  {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g, P2G_T, 0) == cudaSuccess && occ > 0) h->grid_p2g = h->num_sms * occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<128>, 128, 0) == cudaSuccess && occ > 0) h->grid_g2p = h->num_sms * occ;
+  }
   // tiles: every tile of the (slab of the) domain can be active
   int64_t slab_layers = (h->cfg.world > 1) ? (int64_t)(P.tile_z1 - P.tile_z0) + 2 : P.nt[2];
   int64_t cap_tiles = (int64_t)P.nt[0] * P.nt[1] * slab_layers;
@@ -1612,7 +1620,7 @@ int mpmb_rasterize(MpmbHandle h) {
   if (h->stage != 1) return fail(h, MPMB_ERR_STATE, "rasterize must follow sort_particles_and_populate_grid");
   prof_begin(h, 1);
   View V = make_view(h);
-  if (h->cap > 0) k_p2g<<<h->num_sms * 4, P2G_T, 0, h->stream>>>(V, h->P);  // 4 CTAs/SM resident (46 KB shared each)
+  if (h->cap > 0) k_p2g<<<h->grid_p2g, P2G_T, 0, h->stream>>>(V, h->P);
   h->launches += 1;
   prof_end(h, 1);
   CUDA_TRY(h, cudaGetLastError());
@@ -1627,7 +1635,7 @@ int mpmb_resample(MpmbHandle h) {
   View V = make_view(h);
   if (h->cap > 0) {
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel);
-    k_g2p<128><<<h->num_sms * 5, 128, 0, h->stream>>>(V, h->P, h->vel);
+    k_g2p<128><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel);
     k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt);
   }
   h->launches += 3;
