@@ -474,10 +474,15 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
       // ---- 1: stage rows: all copies of the chunk in flight at once
       uint32_t pidx[P2G_K], rkey[P2G_K];
       bool valid[P2G_K];
+      if (cb + nrows <= tm.run_len) {  // whole chunk inside the run (the common case): pure arithmetic, no loads
 #pragma unroll
-      for (int k = 0; k < P2G_K; k++) {
-        const int r = k * P2G_T + tid;
-        pidx[k] = r < nrows ? row_of(cb + r) : 0u;
+        for (int k = 0; k < P2G_K; k++) pidx[k] = (uint32_t)(tm.run_begin + cb + k * P2G_T + tid);
+      } else {
+#pragma unroll
+        for (int k = 0; k < P2G_K; k++) {
+          const int r = k * P2G_T + tid;
+          pidx[k] = r < nrows ? row_of(cb + r) : 0u;
+        }
       }
 #pragma unroll
       for (int k = 0; k < P2G_K; k++) {
@@ -758,11 +763,16 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4
       const int nrow_tile = it.tm.run_len + it.tm.arr_len;
       const int nrows = min(G2P_CH, nrow_tile - it.rb);
       uint32_t pidx[KPT];
+      if (it.rb + nrows <= it.tm.run_len) {  // whole chunk inside the run: no loads
 #pragma unroll
-      for (int k = 0; k < KPT; k++) {
-        const int r = k * BLOCK + tid, g = it.rb + r;
-        pidx[k] = 0u;
-        if (r < nrows) pidx[k] = g < it.tm.run_len ? (uint32_t)(it.tm.run_begin + g) : V.arrivals_sorted[it.tm.arr_off + (g - it.tm.run_len)];
+        for (int k = 0; k < KPT; k++) pidx[k] = (uint32_t)(it.tm.run_begin + it.rb + k * BLOCK + tid);
+      } else {
+#pragma unroll
+        for (int k = 0; k < KPT; k++) {
+          const int r = k * BLOCK + tid, g = it.rb + r;
+          pidx[k] = 0u;
+          if (r < nrows) pidx[k] = g < it.tm.run_len ? (uint32_t)(it.tm.run_begin + g) : V.arrivals_sorted[it.tm.arr_off + (g - it.tm.run_len)];
+        }
       }
       if (it.first) {
         const float4 *src = vel + (size_t)it.slot * ARENA;
