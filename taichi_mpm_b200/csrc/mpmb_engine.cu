@@ -238,7 +238,7 @@ __global__ void k_unpack_particles(View V, const uint32_t *keys, int n, uint32_t
   if (id) id[o] = tag & 0x3FFFFFFu;
   if (group) group[o] = (int)(tag >> 26);
   if (x) { x[3 * (size_t)o] = q0.x; x[3 * (size_t)o + 1] = q0.y; x[3 * (size_t)o + 2] = q0.z; }
-  if (mass) mass[o] = q0.w;
+  if (mass) mass[o] = fabsf(q0.w);
   if (v) { v[3 * (size_t)o] = q1.x; v[3 * (size_t)o + 1] = q1.y; v[3 * (size_t)o + 2] = q1.z; }
   if (F) {
     float *f = F + 9 * (size_t)o;
@@ -472,8 +472,7 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
 #pragma unroll
       for (int e = 0; e < P2G_K * 2; e++) s_hist[e][tid] = 0;
       // ---- 1: stage rows: all copies of the chunk in flight at once
-      uint32_t pidx[P2G_K], rkey[P2G_K];
-      bool valid[P2G_K];
+      uint32_t pidx[P2G_K];
       if (cb + nrows <= tm.run_len) {  // whole chunk inside the run (the common case): pure arithmetic, no loads
 #pragma unroll
         for (int k = 0; k < P2G_K; k++) pidx[k] = (uint32_t)(tm.run_begin + cb + k * P2G_T + tid);
@@ -487,18 +486,14 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
 #pragma unroll
       for (int k = 0; k < P2G_K; k++) {
         const int r = k * P2G_T + tid;
-        rkey[k] = (uint32_t)tile;
         if (r < nrows) {
           const int ri = r + (r >> 3);
           cp_async16(&s_rows[0][ri], &V.q[0][pidx[k]]);
           cp_async16(&s_rows[1][ri], &V.q[1][pidx[k]]);
           cp_async16(&s_rows[2][ri], &V.q[2][pidx[k]]);
           cp_async16(&s_rows[3][ri], &V.q[3][pidx[k]]);
-          if (cb + r < tm.run_len) rkey[k] = V.keys[pidx[k]];  // run rows may be holes; consumed after the wait
         }
       }
-#pragma unroll
-      for (int k = 0; k < P2G_K; k++) valid[k] = (k * P2G_T + tid < nrows) && rkey[k] == (uint32_t)tile;
       cp_async_commit();
       cp_async_wait_all();
       __syncthreads();
@@ -508,8 +503,11 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
       for (int k = 0; k < P2G_K; k++) {
         const int r = k * P2G_T + tid;
         int cell = 64 + warp;  // holes and rows past the end: a private bucket
-        if (valid[k]) {
-          const float4 a0 = s_rows[0][r + (r >> 3)];
+        float4 a0 = make_float4(0.f, 0.f, 0.f, -1.f);
+        if (r < nrows) a0 = s_rows[0][r + (r >> 3)];
+        // G2P stores the mass NEGATED when the particle's base node left the tile of the run it was
+        // written to: run rows with mass < 0 are holes (the particle is in another tile's arrivals)
+        if (r < nrows && (a0.w > 0.f || cb + r >= tm.run_len)) {
           int bx, by, bz;
           float rr;
           base_rel(a0.x, P.inv_dx, bx, rr);
@@ -568,7 +566,7 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
         const int r = s_order[it];
         const int ri = r + (r >> 3);
         const float4 a0 = s_rows[0][ri], a1 = s_rows[1][ri], a2 = s_rows[2][ri], a3 = s_rows[3][ri];
-        const float mass = a0.w;
+        const float mass = fabsf(a0.w);
         float vx = a1.x, vy = a1.y, vz = a1.z;
         if (P.particle_gravity) {  // src/transfer.cpp:485-487
           vx += P.gdt[0]; vy += P.gdt[1]; vz += P.gdt[2];
@@ -814,7 +812,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4
         if (orow == ROW_HOLE) continue;  // the particle that was here now belongs to another tile
         const size_t o = orow;
         const float4 q0 = s_in[buf][0][r], q4 = s_in[buf][1][r], q5 = s_in[buf][2][r], q6 = s_in[buf][3][r];
-        const float mass = q0.w, vol = q6.z;
+        const float mass = fabsf(q0.w), vol = q6.z;
         const uint32_t tag = __float_as_uint(q6.w);
         const Material &mat = P.mats[tag >> 26];
         int bx, by, bz;
@@ -878,7 +876,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4
         if (P.clean_boundary && reference_deletes(P, x, v)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
         if (!isfinite(x.x + x.y + x.z)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
         // one contiguous, cell-sorted run per tile in the other buffer
-        store_particle(V.qn, o, x, mass, v, A, F, ps, vol, tag, B);
+        store_particle(V.qn, o, x, key == (uint32_t)tile ? mass : -mass, v, A, F, ps, vol, tag, B);
         V.keys_next[o] = key;
         if (key == (uint32_t)tile) {
           my_stay++;
