@@ -43,7 +43,6 @@ constexpr int ARENA = 216;  // 6*6*6 nodes
 constexpr int N_Q = 10;
 // keys: [0, ntiles_total) = tile index; ntiles_total + {0,1,2} = left through -z / +z face, dead
 enum { SPECIAL_MIG_DOWN = 0, SPECIAL_MIG_UP = 1, SPECIAL_DEAD = 2 };
-constexpr uint32_t ROW_HOLE = 0xFFFFFFFFu;  // outpos of a run row whose particle left the tile
 
 struct Params {
   int res[3];
@@ -80,7 +79,7 @@ struct View {  // raw pointers handed to kernels
   float4 *qn[N_Q];       // next (written by G2P)
   uint32_t *keys;        // tile of every current row (specials: dead / migrating)
   uint32_t *keys_next;
-  uint32_t *outpos;      // per current row: its row in the next storage, ROW_HOLE for holes
+  uint32_t *outpos;      // per live current row: its row in the next storage (written by P2G)
   // dense per-tile ordering state
   int *run_begin, *run_len;      // run of the tile in the current storage
   int *out_begin, *total;        // run of the tile in the next storage (= next substep's run)
@@ -257,10 +256,6 @@ __global__ void k_alive_flags(const uint32_t *keys, int n, uint32_t special_min,
   if (i < n) flags[i] = keys[i] < special_min ? 1 : 0;
 }
 
-// dead keys for the slots G2P does not write: [n_alive, n) (n_alive is a device value)
-__global__ void k_fill_tail(uint32_t *a, const Counters *c, int n, uint32_t v) {
-  for (int i = c->n_alive + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = v;
-}
 __global__ void k_fill_u32(uint32_t *a, int n, uint32_t v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
@@ -555,9 +550,9 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
           const int pos = s_start[cell] + s_hist[k * 2 + warp][cell] + (int)(cr[k] & 0xffffu);
           s_order[pos] = (unsigned short)r;
           V.outpos[pidx[k]] = (uint32_t)(tm.out_begin + vbase + pos);
-        } else if (r < nrows) {
-          V.outpos[pidx[k]] = ROW_HOLE;
         }
+        // holes are NOT marked here: the same storage row is a hole of its old tile and an arrival of
+        // its new one, and two CTAs must not write different values to one outpos entry
       }
       __syncthreads();
       // ---- 3: accumulate my cell's run in registers
@@ -736,7 +731,7 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4 *vel) {
   __shared__ float4 s_vel[2][ARENA];
   __shared__ float4 s_in[2][4][G2P_CH];
-  __shared__ uint32_t s_out[2][G2P_CH];  // output row of every staged row (ROW_HOLE = skip)
+  __shared__ uint32_t s_out[2][G2P_CH];  // output row of every staged row
   __shared__ int s_stay;
   constexpr int KPT = G2P_CH / BLOCK;
   const int tid = threadIdx.x;
@@ -808,10 +803,11 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4
       const float4 *sv = s_vel[vbuf];
       int my_stay = 0;
       for (int r = tid; r < nrows; r += BLOCK) {
-        const uint32_t orow = s_out[buf][r];
-        if (orow == ROW_HOLE) continue;  // the particle that was here now belongs to another tile
-        const size_t o = orow;
         const float4 q0 = s_in[buf][0][r], q4 = s_in[buf][1][r], q5 = s_in[buf][2][r], q6 = s_in[buf][3][r];
+        // run rows with negative mass are holes (the particle now belongs to another tile's arrivals);
+        // same rule as k_p2g, so both kernels visit exactly the same particles
+        if (cur.rb + r < cur.tm.run_len && !(q0.w > 0.f)) continue;
+        const size_t o = s_out[buf][r];
         const float mass = fabsf(q0.w), vol = q6.z;
         const uint32_t tag = __float_as_uint(q6.w);
         const Material &mat = P.mats[tag >> 26];
@@ -1681,6 +1677,26 @@ int mpmb_download_grid(MpmbHandle h, int32_t which, float *dense4) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(d);
   CUDA_TRY(h, e);
+  return MPMB_OK;
+}
+
+// ------------------------------------------------------------------------------ debug (not part of mpmb.h)
+// which: 0 run_begin 1 run_len 2 stay 3 arr_len 4 out_begin 5 total 6 arr_off   (dense, ntot ints)
+extern "C" int mpmb_debug_dense(MpmbHandle h, int which, int *out) {
+  CHECK_HANDLE(h);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  View V = make_view(h);
+  const int *src[] = {V.run_begin, V.run_len, V.stay_cnt, V.arr_len, V.out_begin, V.total, V.arr_off};
+  CUDA_TRY(h, cudaMemcpy(out, src[which], sizeof(int) * h->ntot, cudaMemcpyDeviceToHost));
+  return h->ntot;
+}
+// keys and signed masses of the first n rows of the current storage; counters
+extern "C" int mpmb_debug_rows(MpmbHandle h, int n, uint32_t *keys, float *mass4, int *counters8) {
+  CHECK_HANDLE(h);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (keys) CUDA_TRY(h, cudaMemcpy(keys, h->keys[h->cur], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+  if (mass4) CUDA_TRY(h, cudaMemcpy(mass4, h->q[h->cur][0], sizeof(float4) * n, cudaMemcpyDeviceToHost));
+  if (counters8) CUDA_TRY(h, cudaMemcpy(counters8, h->cnt, sizeof(Counters), cudaMemcpyDeviceToHost));
   return MPMB_OK;
 }
 
