@@ -215,7 +215,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "M particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, cfg, n_particles):
@@ -397,13 +397,38 @@ def run_ours(args):
     if world > 1:
         line["exchange"] = {"bytes_sent_per_step_rank0": runner.bytes_sent / max(1, args.warmup + args.steps + 3 + args.frames * frame_substeps),
                             "transport": "torch.distributed NCCL point-to-point (batch_isend_irecv), fixed-size messages"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything libraries print to fd 1 (e.g. the NCCL version banner) goes to stderr; the ONE JSON
+    line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
