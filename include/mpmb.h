@@ -157,6 +157,14 @@ int mpmb_sort_particles_and_populate_grid(MpmbHandle h); /* src/mpm.cpp:770-918 
 int mpmb_rasterize(MpmbHandle h);                        /* src/transfer.cpp:361-581 (P2G)        */
 int mpmb_resample(MpmbHandle h);                         /* src/mpm.cpp:277-372 + src/transfer.cpp:702-970 + src/mpm.cpp:583-633 */
 
+/* z-slab runs (world>1): the same two stages, each in two launches — part 1 = the tiles of the
+ * slab's two boundary layers (they produce and consume halo data), part 2 = all other tiles — so
+ * that the host can overlap the halo exchange with the interior work:
+ *   sort; rasterize_part(1); halo_pack; [send/recv starts]; rasterize_part(2); resample_part(2);
+ *   [send/recv done]; halo_unpack; resample_part(1); migrate_*.                                     */
+int mpmb_rasterize_part(MpmbHandle h, int32_t part);
+int mpmb_resample_part(MpmbHandle h, int32_t part);
+
 /* Parity/debug: dense node grid [res0+1][res1+1][res2+1][4] on the host.
  * which=0: (p_x,p_y,p_z,m) after P2G; which=1: (v_x,v_y,v_z,m) after normalise + boundary.
  * Valid between mpmb_rasterize and the next mpmb_sort_particles_and_populate_grid.                 */

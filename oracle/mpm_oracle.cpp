@@ -83,7 +83,11 @@ template <class R> inline void mat_inverse(const R *a, R *out) {
 // One-sided Jacobi (Hestenes) SVD, A = U diag(s) V^T, s >= 0.  Stands in for the
 // taichi core's svd() (call sites src/particles.cpp:227,630,642).  Sign/ordering
 // conventions are NOT those of the core; only invariant results are compared.
+inline void svd3_fast(const float *A, float *U, float *s, float *V);
+template <class R> inline bool svd3_try_fast(const R *, R *, R *, R *) { return false; }
+template <> inline bool svd3_try_fast<float>(const float *A, float *U, float *s, float *V);
 template <class R> void svd3(const R *A, R *U, R *s, R *V) {
+  if (svd3_try_fast<R>(A, U, s, V)) return;
   R a[9];
   std::memcpy(a, A, sizeof(a));
   for (int i = 0; i < 9; i++) V[i] = (i % 4 == 0) ? R(1) : R(0);
@@ -150,6 +154,54 @@ template <class R> void svd3(const R *A, R *U, R *s, R *V) {
       s[k] = -s[k];
     }
   }
+}
+
+
+// ---- faster 3x3 SVD for the TIMED fast path only (the checker paths above keep the one-sided
+// Jacobi).  Stands in for the core's optimized svd() so that the CPU baseline is not dominated by
+// an unoptimised factorisation: symmetric cyclic Jacobi on F^T F (V, s^2), then U = F V S^-1.
+inline void svd3_fast(const float *A, float *U, float *s, float *V) {
+  float c00 = 0, c11 = 0, c22 = 0, c01 = 0, c02 = 0, c12 = 0;
+  for (int r = 0; r < 3; r++) {
+    const float a0 = at(A, r, 0), a1 = at(A, r, 1), a2 = at(A, r, 2);
+    c00 += a0 * a0; c11 += a1 * a1; c22 += a2 * a2; c01 += a0 * a1; c02 += a0 * a2; c12 += a1 * a2;
+  }
+  float v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  auto rot = [&](float &app, float &aqq, float &apq, float &arp, float &arq, int p, int q) {
+    if (apq == 0.f) return;
+    const float d = aqq - app, b = 2.f * apq;
+    const float h = std::sqrt(d * d + b * b);
+    const float t = b / (d + (d >= 0.f ? h : -h));
+    const float c = 1.f / std::sqrt(t * t + 1.f), sn = t * c;
+    app -= t * apq; aqq += t * apq; apq = 0.f;
+    const float nrp = c * arp - sn * arq, nrq = sn * arp + c * arq;
+    arp = nrp; arq = nrq;
+    for (int r = 0; r < 3; r++) {
+      const float vp = at(v, r, p), vq = at(v, r, q);
+      at(v, r, p) = c * vp - sn * vq;
+      at(v, r, q) = sn * vp + c * vq;
+    }
+  };
+  for (int sweep = 0; sweep < 6; sweep++) {
+    rot(c00, c11, c01, c02, c12, 0, 1);
+    rot(c00, c22, c02, c01, c12, 0, 2);
+    rot(c11, c22, c12, c01, c02, 1, 2);
+    const float off = c01 * c01 + c02 * c02 + c12 * c12, nrm = c00 * c00 + c11 * c11 + c22 * c22;
+    if (off <= 1e-14f * nrm) break;
+  }
+  s[0] = std::sqrt(std::max(c00, 0.f)); s[1] = std::sqrt(std::max(c11, 0.f)); s[2] = std::sqrt(std::max(c22, 0.f));
+  for (int i = 0; i < 9; i++) V[i] = v[i];
+  for (int c = 0; c < 3; c++) {
+    const float inv = s[c] > 1e-20f ? 1.f / s[c] : 0.f;
+    for (int r = 0; r < 3; r++) at(U, r, c) = (at(A, r, 0) * at(v, 0, c) + at(A, r, 1) * at(v, 1, c) + at(A, r, 2) * at(v, 2, c)) * inv;
+  }
+}
+// thread-local switch: the fast path routes svd3<float> through svd3_fast
+static thread_local bool g_use_fast_svd = false;
+template <> inline bool svd3_try_fast<float>(const float *A, float *U, float *s, float *V) {
+  if (!g_use_fast_svd) return false;
+  svd3_fast(A, U, s, V);
+  return true;
 }
 
 // polar_decomp(A, R, S): A = R S (usage src/particles.cpp:212-215,394; mls-mpm88.cpp:26)
@@ -685,6 +737,7 @@ void fast_substep(FastState &st, const Scene<float> &sc, Particles<float> &P, st
       alignas(64) float tile[360][4];
       std::memset(tile, 0, sizeof(tile));
       tile_io(b, tile, false);
+      g_use_fast_svd = true;
       for (int32_t pi = st.block_off[ob]; pi < st.block_off[ob + 1]; pi++) {
         int64_t i = st.order[pi];
         R *v = P.v + 3 * i;
@@ -759,6 +812,7 @@ void fast_substep(FastState &st, const Scene<float> &sc, Particles<float> &P, st
     alignas(64) float tile[360][4];
     std::memset(tile, 0, sizeof(tile));
     tile_io(b, tile, false);
+    g_use_fast_svd = true;
     for (int32_t pi = st.block_off[ob]; pi < st.block_off[ob + 1]; pi++) {
       int64_t i = st.order[pi];
       int base[3]; R rel[3];
@@ -1006,6 +1060,7 @@ ORACLE_API int64_t oracle_fast_substeps(void *h, int nsub, const int *res, float
   int64_t updates = 0;
   for (int s = 0; s < nsub; s++) {
     int64_t na = 0;
+#pragma omp parallel for reduction(+ : na) schedule(static)
     for (int64_t i = 0; i < n; i++) na += alive[i];
     updates += na;
     fast_substep(st, sc, P, alive);

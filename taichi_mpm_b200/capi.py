@@ -22,7 +22,8 @@ EXPORTS = [
     "mpmb_create", "mpmb_destroy", "mpmb_last_error", "mpmb_version", "mpmb_set_stream", "mpmb_synchronize",
     "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes", "mpmb_set_id_base",
     "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_num_particles", "mpmb_download_particles", "mpmb_download_aos",
-    "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_download_grid",
+    "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_rasterize_part",
+    "mpmb_resample_part", "mpmb_download_grid",
     "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters",
     "mpmb_halo_bytes", "mpmb_halo_pack", "mpmb_halo_unpack", "mpmb_migrate_bytes", "mpmb_migrate_pack", "mpmb_migrate_unpack",
 ]
@@ -240,6 +241,12 @@ class Engine:
 
     def resample(self):
         self._check(self.L.mpmb_resample(self.h))
+
+    def rasterize_part(self, part):
+        self._check(self.L.mpmb_rasterize_part(self.h, C.c_int32(part)))
+
+    def resample_part(self, part):
+        self._check(self.L.mpmb_resample_part(self.h, C.c_int32(part)))
 
     def download_grid(self, which):
         g = np.zeros(tuple(r + 1 for r in self.res) + (4,), np.float32)

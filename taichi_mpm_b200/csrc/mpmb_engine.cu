@@ -143,6 +143,16 @@ __device__ __forceinline__ bool reference_deletes(const Params &P, float3 x, flo
   return bad;
 }
 
+// z-slab runs split every tile kernel in two launches so that the halo exchange overlaps compute:
+// part 1 = tiles of the slab's boundary layers (they produce / consume halo data), part 2 = the rest,
+// part 0 = all tiles.
+__device__ __forceinline__ bool tile_in_part(const Params &P, int tile, int part) {
+  if (part == 0) return true;
+  const int tz = tile % P.nt[2];
+  const bool boundary = (P.world > 1) && (tz == P.tile_z0 || tz == P.tile_z1 - 1);
+  return part == 1 ? boundary : !boundary;
+}
+
 // affine = stress * (-4 inv_dx dt) + apic_b * (inv_D * mass)  (src/transfer.cpp:465,503,521-522)
 __device__ __forceinline__ void make_affine(const Mat3 &force, const Mat3 &b, float mass, float S, Mat3 &A) {
   const float bm = 4.0f * mass;
@@ -437,7 +447,7 @@ constexpr int P2G_ROWS = P2G_CH + P2G_CH / 8;  // padded row index r + (r>>3): c
 constexpr int AR_SX = 68, AR_SY = 8;           // arena strides in shared memory
 constexpr int AR_SIZE = 6 * AR_SX;
 
-__global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
+__global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
   __shared__ float4 s_rows[4][P2G_ROWS];
   __shared__ unsigned short s_order[P2G_CH];
   __shared__ unsigned short s_hist[P2G_K * 2][64];
@@ -449,6 +459,7 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P) {
   for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
     const TileMeta tm = V.meta[slot];
     const int tile = tm.tile;
+    if (!tile_in_part(P, tile, part)) continue;  // uniform per CTA
     const int nrow_tile = tm.run_len + tm.arr_len;
     const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
     const float fbx = (float)(tx * 4 + cx), fby = (float)(ty * 4 + cy), fbz = (float)(tz * 4 + cz);
@@ -684,7 +695,7 @@ __device__ __forceinline__ float4 node_update(const Params &P, const float4 *sdf
 // rebuilt (fixed-order sum of the covering arenas), normalised, projected on the level set and
 // stored as one contiguous 3.4 KB block vel[slot][216].  Node-parallel, so the dependent
 // slot_map -> arena -> sdf loads are hidden by occupancy instead of stalling a G2P CTA.
-__global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel) {
+__global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int part) {
   // one WARP per tile: the 27 neighbour slots live in lanes 0..26 and are fetched with shuffles, so
   // there is no block barrier and every warp of the grid has its own tile in flight
   const int lane = threadIdx.x & 31;
@@ -692,6 +703,7 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel) {
   const int n_tiles = V.cnt->n_tiles;
   for (int slot = gw; slot < n_tiles; slot += nw) {
     const int tile = V.meta[slot].tile;
+    if (!tile_in_part(P, tile, part)) continue;  // uniform per warp
     const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
     int my_nb = -1;
     if (lane < 27) {
@@ -728,7 +740,7 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel) {
 // tile change, that tile's 216 node velocities are already in flight into the other.
 constexpr int G2P_CH = 256;  // rows per pipeline stage
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4 *vel) {
+__global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4 *vel, int part) {
   __shared__ float4 s_vel[2][ARENA];
   __shared__ float4 s_in[2][4][G2P_CH];
   __shared__ uint32_t s_out[2][G2P_CH];  // output row of every staged row
@@ -740,7 +752,10 @@ __global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4
   struct Item { int slot, rb, first; TileMeta tm; };
   auto first_item = [&](int slot) {
     Item it;
-    it.slot = slot; it.rb = 0; it.first = 1;
+    it.rb = 0; it.first = 1;
+    if (part != 0)  // next tile of this CTA's round-robin share that belongs to the part
+      while (slot < n_tiles && !tile_in_part(P, V.meta[slot].tile, part)) slot += (int)gridDim.x;
+    it.slot = slot;
     if (slot < n_tiles) it.tm = V.meta[slot];
     else { it.tm.run_len = 0; it.tm.arr_len = 0; it.tm.tile = 0; it.tm.run_begin = 0; it.tm.arr_off = 0; it.tm.out_begin = 0; }
     return it;
@@ -1624,7 +1639,7 @@ int mpmb_rasterize(MpmbHandle h) {
   if (h->stage != 1) return fail(h, MPMB_ERR_STATE, "rasterize must follow sort_particles_and_populate_grid");
   prof_begin(h, 1);
   View V = make_view(h);
-  if (h->cap > 0) k_p2g<<<h->grid_p2g, P2G_T, 0, h->stream>>>(V, h->P);
+  if (h->cap > 0) k_p2g<<<h->grid_p2g, P2G_T, 0, h->stream>>>(V, h->P, 0);
   h->launches += 1;
   prof_end(h, 1);
   CUDA_TRY(h, cudaGetLastError());
@@ -1638,8 +1653,8 @@ int mpmb_resample(MpmbHandle h) {
   prof_begin(h, 2);
   View V = make_view(h);
   if (h->cap > 0) {
-    k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel);
-    k_g2p<128><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel);
+    k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, 0);
+    k_g2p<128><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
     k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt);
   }
   h->launches += 3;
@@ -1648,6 +1663,45 @@ int mpmb_resample(MpmbHandle h) {
   h->cur ^= 1;  // the buffer G2P wrote is the current storage ...
   h->ord ^= 1;  // ... its runs / stay counts are the current ones ...
   h->mov ^= 1;  // ... and its mover list feeds the next ordering
+  h->stage = 0;
+  return MPMB_OK;
+}
+
+// z-slab runs: the same two stages in two launches each, boundary-layer tiles (part 1) and the
+// rest (part 2), so that the host can put the halo exchange between them (include/mpmb.h).
+int mpmb_rasterize_part(MpmbHandle h, int32_t part) {
+  CHECK_HANDLE(h);
+  if (part != 1 && part != 2) return fail(h, MPMB_ERR_INVALID, "part must be 1 (boundary) or 2 (interior)");
+  if (!((part == 1 && h->stage == 1) || (part == 2 && h->stage == 11))) return fail(h, MPMB_ERR_STATE, "rasterize_part: boundary first, then interior, after sort");
+  prof_begin(h, 1);
+  View V = make_view(h);
+  if (h->cap > 0) k_p2g<<<h->grid_p2g, P2G_T, 0, h->stream>>>(V, h->P, part);
+  h->launches += 1;
+  prof_end(h, 1);
+  CUDA_TRY(h, cudaGetLastError());
+  h->stage = part == 1 ? 11 : 2;
+  return MPMB_OK;
+}
+
+int mpmb_resample_part(MpmbHandle h, int32_t part) {
+  CHECK_HANDLE(h);
+  if (part != 1 && part != 2) return fail(h, MPMB_ERR_INVALID, "part must be 1 (boundary) or 2 (interior)");
+  if (!((part == 2 && h->stage == 2) || (part == 1 && h->stage == 22))) return fail(h, MPMB_ERR_STATE, "resample_part: interior first, then boundary, after rasterize");
+  prof_begin(h, 2);
+  View V = make_view(h);
+  int nl = 2;
+  if (h->cap > 0) {
+    k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, part);
+    k_g2p<128><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part);
+    if (part == 1) { k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt); nl++; }
+  }
+  h->launches += nl;
+  prof_end(h, nl);
+  CUDA_TRY(h, cudaGetLastError());
+  if (part == 2) { h->stage = 22; return MPMB_OK; }
+  h->cur ^= 1;
+  h->ord ^= 1;
+  h->mov ^= 1;
   h->stage = 0;
   return MPMB_OK;
 }
@@ -1747,7 +1801,7 @@ int64_t mpmb_halo_bytes(MpmbHandle h) {
 int mpmb_halo_pack(MpmbHandle h, int32_t face, void *dev_buf) {
   CHECK_HANDLE(h);
   if (h->cfg.world <= 1) return fail(h, MPMB_ERR_STATE, "halo exchange needs world > 1");
-  if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "halo_pack must follow rasterize");
+  if (h->stage != 2 && h->stage != 11) return fail(h, MPMB_ERR_STATE, "halo_pack must follow rasterize (or its boundary part)");
   if (!dev_buf || face < 0 || face > 1) return fail(h, MPMB_ERR_INVALID, "bad argument");
   prof_begin(h, 3);
   char *b = (char *)dev_buf;
@@ -1765,7 +1819,7 @@ int mpmb_halo_pack(MpmbHandle h, int32_t face, void *dev_buf) {
 int mpmb_halo_unpack(MpmbHandle h, int32_t face, const void *dev_buf) {
   CHECK_HANDLE(h);
   if (h->cfg.world <= 1) return fail(h, MPMB_ERR_STATE, "halo exchange needs world > 1");
-  if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "halo_unpack must follow rasterize");
+  if (h->stage != 2 && h->stage != 22) return fail(h, MPMB_ERR_STATE, "halo_unpack must follow rasterize (and may follow the interior resample)");
   if (!dev_buf || face < 0 || face > 1) return fail(h, MPMB_ERR_INVALID, "bad argument");
   const int layer = face == 0 ? h->P.tile_z0 - 1 : h->P.tile_z1;  // the neighbour's boundary layer
   if (layer < 0 || layer >= h->P.nt[2]) return fail(h, MPMB_ERR_INVALID, "no neighbour through face %d", face);

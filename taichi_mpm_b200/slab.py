@@ -68,6 +68,12 @@ class EngineAdapter:
     def resample(self):
         self.e.resample()
 
+    def rasterize_part(self, part):
+        self.e.rasterize_part(part)
+
+    def resample_part(self, part):
+        self.e.resample_part(part)
+
     def halo_pack(self, face, buf):
         self.e.halo_pack(face, buf.data_ptr())
 
@@ -84,13 +90,18 @@ class EngineAdapter:
 class SlabRunner:
     """Runs substeps of one slab and exchanges with the ring neighbours (rank-1 below, rank+1 above)."""
 
-    def __init__(self, adapter, rank, world, device, dist=None, group=None):
+    def __init__(self, adapter, rank, world, device, dist=None, group=None, overlap=False):
         import torch
         self.torch = torch
         self.a = adapter
         self.rank, self.world = rank, world
         self.dist = dist
         self.group = group
+        # overlap=True splits every tile kernel into boundary-layer and interior launches and flies the
+        # halo during the interior work.  Measured on 2 x B200 (config 3 weak scaling): 0.979 ms/substep
+        # against 0.920 ms for the plain schedule — the partial launches cost more than the ~50 us of
+        # NVLink time they hide — so the plain schedule is the default.
+        self.overlap = overlap
         self.has_lo = rank > 0
         self.has_hi = rank < world - 1
         hb, mb = adapter.halo_bytes(), adapter.migrate_bytes()
@@ -101,8 +112,9 @@ class SlabRunner:
         self.mig_recv = [mk(mb), mk(mb)]
         self.bytes_sent = 0
 
-    def _exchange(self, send, recv):
-        """send[0] -> rank-1, send[1] -> rank+1 ; recv[0] <- rank-1, recv[1] <- rank+1."""
+    def _exchange(self, send, recv, wait=True):
+        """send[0] -> rank-1, send[1] -> rank+1 ; recv[0] <- rank-1, recv[1] <- rank+1.
+        wait=False returns the in-flight work handles (the caller overlaps compute, then waits)."""
         d = self.dist
         ops = []
         if self.has_lo:
@@ -111,17 +123,44 @@ class SlabRunner:
         if self.has_hi:
             ops.append(d.P2POp(d.isend, send[1], self.rank + 1, self.group))
             ops.append(d.P2POp(d.irecv, recv[1], self.rank + 1, self.group))
+        works = []
         if ops:
-            for w in d.batch_isend_irecv(ops):
-                w.wait()
+            works = d.batch_isend_irecv(ops)
             self.bytes_sent += sum(op.tensor.numel() for op in ops[::2])
+            if wait:
+                for w in works:
+                    w.wait()
+                works = []
+        return works
 
     def substep(self, n=1):
         a = self.a
         for _ in range(n):
             a.sort()
-            a.rasterize()
-            if self.world > 1:
+            if self.world == 1:
+                a.rasterize()
+                a.resample()
+                continue
+            if self.overlap:
+                # boundary-layer tiles first; their arenas fly to the neighbours while the interior
+                # tiles are rasterized and resampled; the boundary tiles are resampled last
+                a.rasterize_part(1)
+                if self.has_lo:
+                    a.halo_pack(0, self.halo_send[0])
+                if self.has_hi:
+                    a.halo_pack(1, self.halo_send[1])
+                works = self._exchange(self.halo_send, self.halo_recv, wait=False)
+                a.rasterize_part(2)
+                a.resample_part(2)
+                for w in works:
+                    w.wait()
+                if self.has_lo:
+                    a.halo_unpack(0, self.halo_recv[0])
+                if self.has_hi:
+                    a.halo_unpack(1, self.halo_recv[1])
+                a.resample_part(1)
+            else:
+                a.rasterize()
                 if self.has_lo:
                     a.halo_pack(0, self.halo_send[0])
                 if self.has_hi:
@@ -131,7 +170,7 @@ class SlabRunner:
                     a.halo_unpack(0, self.halo_recv[0])
                 if self.has_hi:
                     a.halo_unpack(1, self.halo_recv[1])
-            a.resample()
+                a.resample()
             if self.world > 1:
                 if self.has_lo:
                     a.migrate_pack(0, self.mig_send[0])

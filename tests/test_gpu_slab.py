@@ -148,11 +148,13 @@ def _run_two_slabs_one_process(scene, st, nsub, device=0):
     a0, a1 = adapters
     for _ in range(nsub):
         for a in adapters:
-            a.sort(); a.rasterize()
+            a.sort(); a.rasterize_part(1)
         a0.halo_pack(1, bufs[0]["halo"][1]); a1.halo_pack(0, bufs[1]["halo"][0])
+        for a in adapters:
+            a.rasterize_part(2); a.resample_part(2)
         a1.halo_unpack(0, bufs[0]["halo"][1]); a0.halo_unpack(1, bufs[1]["halo"][0])
         for a in adapters:
-            a.resample()
+            a.resample_part(1)
         a0.migrate_pack(1, bufs[0]["mig"][1]); a1.migrate_pack(0, bufs[1]["mig"][0])
         a1.migrate_unpack(0, bufs[0]["mig"][1]); a0.migrate_unpack(1, bufs[1]["mig"][0])
     torch.cuda.synchronize()

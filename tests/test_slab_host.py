@@ -62,6 +62,12 @@ class MockAdapter:
     def resample(self):
         self.log.append("g2p")
 
+    def rasterize_part(self, part):
+        self.log.append("p2g%d" % part)
+
+    def resample_part(self, part):
+        self.log.append("g2p%d" % part)
+
     def halo_pack(self, face, buf):
         buf.fill_(10 * self.rank + face)
         self.log.append("hp%d" % face)
@@ -79,12 +85,12 @@ class MockAdapter:
         self.log.append("mu%d" % face)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     a = MockAdapter(rank)
-    r = slab.SlabRunner(a, rank, world, torch.device("cpu"), dist=dist)
+    r = slab.SlabRunner(a, rank, world, torch.device("cpu"), dist=dist, overlap=overlap)
     r.substep(2)
     q.put((rank, a.log, a.received))
     dist.barrier()
@@ -99,12 +105,12 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_exchange_choreography_gloo(world):
+@pytest.mark.parametrize("world,overlap", [(2, False), (3, False), (2, True)])
+def test_exchange_choreography_gloo(world, overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, overlap)) for r in range(world)]
     for p in procs:
         p.start()
     out = {}
@@ -117,9 +123,12 @@ def test_exchange_choreography_gloo(world):
     for rank in range(world):
         log, recv = out[rank]
         lo, hi = rank > 0, rank < world - 1
-        step = ["sort", "p2g"] + (["hp0"] if lo else []) + (["hp1"] if hi else []) + (["hu0"] if lo else []) + (["hu1"] if hi else []) + \
-               ["g2p"] + (["mp0"] if lo else []) + (["mp1"] if hi else []) + (["mu0"] if lo else []) + (["mu1"] if hi else [])
-        assert log == step * 2
+        plain = ["sort", "p2g"] + (["hp0"] if lo else []) + (["hp1"] if hi else []) + (["hu0"] if lo else []) + (["hu1"] if hi else []) + \
+                ["g2p"] + (["mp0"] if lo else []) + (["mp1"] if hi else []) + (["mu0"] if lo else []) + (["mu1"] if hi else [])
+        # overlapped schedule: boundary P2G, pack, [exchange in flight] interior P2G + G2P, unpack, boundary G2P
+        step = ["sort", "p2g1"] + (["hp0"] if lo else []) + (["hp1"] if hi else []) + ["p2g2", "g2p2"] + (["hu0"] if lo else []) + \
+               (["hu1"] if hi else []) + ["g2p1"] + (["mp0"] if lo else []) + (["mp1"] if hi else []) + (["mu0"] if lo else []) + (["mu1"] if hi else [])
+        assert log == (step if overlap else plain) * 2
         # face 0 receives what rank-1 packed for ITS face 1 (its top layer); face 1 what rank+1 packed for its face 0
         exp = []
         for _ in range(2):
