@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int
       int x = tx + ox, y = ty + oy, z = tz + oz;
       if (x >= 0 && y >= 0 && z >= 0 && x < P.nt[0] && y < P.nt[1] && z < P.nt[2]) my_nb = V.slot_map[(x * P.nt[1] + y) * P.nt[2] + z];
     }
-#pragma unroll 1
+#pragma unroll 2
     for (int n0 = 0; n0 < ARENA; n0 += 32) {
       const int n = min(n0 + lane, ARENA - 1);  // the last pass is partial: clamp, store guarded
       int a = n / 36, b = (n / 6) % 6, c = n % 6;
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int
 // tile change, that tile's 216 node velocities are already in flight into the other.
 constexpr int G2P_CH = 256;  // rows per pipeline stage
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 4) k_g2p(View V, Params P, const float4 *vel, int part) {
+__global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4 *vel, int part) {
   __shared__ float4 s_vel[2][ARENA];
   __shared__ float4 s_in[2][4][G2P_CH];
   __shared__ uint32_t s_out[2][G2P_CH];  // output row of every staged row
