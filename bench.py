@@ -102,6 +102,43 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def usable_cpus():
+    """Host threads this process can really use: affinity mask, capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+def best_thread_count(sc, probe):
+    """Oversubscribed OpenMP teams collapse on shared boxes (measured: 128 threads were 200x slower
+    than 64 here), so the CPU arm probes a few team sizes on a small sample and keeps the fastest."""
+    from oracle import pyoracle as O
+    cand = sorted({max(1, usable_cpus() // d) for d in (1, 2, 4, 8)}, reverse=True)
+    best, best_rate = cand[-1], 0.0
+    for t in cand:
+        f = O.FastOracle(sc, probe, threads=t)
+        f.substeps(1)
+        t0 = time.perf_counter()
+        upd, _ = f.substeps(2)
+        rate = upd / (time.perf_counter() - t0)
+        del f
+        if rate > best_rate:
+            best, best_rate = t, rate
+    return best, best_rate
+
+
 def build_workload(name, scale):
     cfg = scenes.config(name, scale)
     sc = cfg["scene"]
@@ -159,6 +196,9 @@ def cpu_run(cfg, n_particles_cap, budget_s, min_substeps=1, threads=None):
         st = {k: v[order] for k, v in st.items()}
     if sc.get("planes") is not None:
         sc["sdf"] = scenes.planes_sdf(sc["res"], sc["planes"])
+    if threads is None:
+        probe = {k: v[: min(len(v), 300_000)] for k, v in st.items()}
+        threads, _ = best_thread_count(sc, probe)
     fast = O.FastOracle(sc, st, threads=threads)
     t0 = time.perf_counter()
     upd, tm = fast.substeps(1)  # first substep also pays first-touch of the buffers: untimed warm-up
@@ -183,20 +223,16 @@ def run_reference(args):
     st, sc = cfg["state"], dict(cfg["scene"])
     if sc.get("planes") is not None:
         sc["sdf"] = scenes.planes_sdf(sc["res"], sc["planes"])
-    # calibrate the sample so that (steps+warmup) substeps take about two minutes
-    probe_n = min(n_full, 1_000_000)
+    # pick the team size, then calibrate the sample so that (steps+warmup) substeps take about a minute
+    probe_n = min(n_full, 300_000)
     order = np.argsort(st["x"][:, 1], kind="stable")
     probe = {k: v[order[:probe_n]] for k, v in st.items()}
-    f = O.FastOracle(sc, probe)
-    f.substeps(1)
-    t0 = time.perf_counter()
-    f.substeps(2)
-    per_particle = (time.perf_counter() - t0) / 2 / probe_n
+    threads, rate = best_thread_count(sc, probe)
+    per_particle = 1.0 / rate
     total = args.steps + args.warmup
-    n_sample = int(min(n_full, max(100_000, 120.0 / (per_particle * total))))
+    n_sample = int(min(n_full, max(50_000, 60.0 / (per_particle * total))))
     sample = {k: v[order[:n_sample]] for k, v in st.items()}
-    del f
-    fast = O.FastOracle(sc, sample)
+    fast = O.FastOracle(sc, sample, threads=threads)
     fast.substeps(args.warmup)
     t0 = time.perf_counter()
     upd, tm = fast.substeps(args.steps)
@@ -428,6 +464,7 @@ def emit(line):
 
 def main():
     os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # idle OpenMP workers must not spin on a shared box
     _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
