@@ -160,6 +160,7 @@ __device__ __forceinline__ void make_affine(const Mat3 &force, const Mat3 &b, fl
   for (int k = 0; k < 9; k++) A.m[k] = fmaf(force.m[k], S, b.m[k] * bm);
 }
 
+template <bool STORE_B = true>
 __device__ __forceinline__ void store_particle(float4 *const *q, size_t i, float3 x, float mass, float3 v, const Mat3 &A, const Mat3 &F,
                                                float ps, float vol, uint32_t tag, const Mat3 &b) {
   q[0][i] = make_float4(x.x, x.y, x.z, mass);
@@ -169,9 +170,11 @@ __device__ __forceinline__ void store_particle(float4 *const *q, size_t i, float
   q[4][i] = make_float4(F.m[0], F.m[1], F.m[2], F.m[3]);
   q[5][i] = make_float4(F.m[4], F.m[5], F.m[6], F.m[7]);
   q[6][i] = make_float4(F.m[8], ps, vol, __uint_as_float(tag));
-  q[7][i] = make_float4(b.m[0], b.m[1], b.m[2], b.m[3]);
-  q[8][i] = make_float4(b.m[4], b.m[5], b.m[6], b.m[7]);
-  q[9][i] = make_float4(b.m[8], 0.f, 0.f, 0.f);
+  if (STORE_B) {
+    q[7][i] = make_float4(b.m[0], b.m[1], b.m[2], b.m[3]);
+    q[8][i] = make_float4(b.m[4], b.m[5], b.m[6], b.m[7]);
+    q[9][i] = make_float4(b.m[8], 0.f, 0.f, 0.f);
+  }
 }
 
 // ------------------------------------------------------------------------------ upload kernels
@@ -739,7 +742,10 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int
 // warps compute chunk i out of one shared buffer, the rows (64 B/particle) of chunk i+1 and, at a
 // tile change, that tile's 216 node velocities are already in flight into the other.
 constexpr int G2P_CH = 256;  // rows per pipeline stage
-template <int BLOCK>
+// STORE_B = false skips the apic_b streams (48 B/particle): no kernel reads apic_b — rasterize uses the
+// affine matrix A — so inside mpmb_substep(h, n) only the LAST substep has to leave it behind for the
+// host (downloads, visualize, save).
+template <int BLOCK, bool STORE_B>
 __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4 *vel, int part) {
   __shared__ float4 s_vel[2][ARENA];
   __shared__ float4 s_in[2][4][G2P_CH];
@@ -887,7 +893,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
         if (P.clean_boundary && reference_deletes(P, x, v)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
         if (!isfinite(x.x + x.y + x.z)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
         // one contiguous, cell-sorted run per tile in the other buffer
-        store_particle(V.qn, o, x, key == (uint32_t)tile ? mass : -mass, v, A, F, ps, vol, tag, B);
+        store_particle<STORE_B>(V.qn, o, x, key == (uint32_t)tile ? mass : -mass, v, A, F, ps, vol, tag, B);
         V.keys_next[o] = key;
         if (key == (uint32_t)tile) {
           my_stay++;
@@ -1067,6 +1073,9 @@ struct MpmbEngine {
 
   int stage = 0;  // 0 idle/after resample, 1 after sort, 2 after rasterize
   int64_t mig_cap = 0;
+  bool skip_b = false;        // intermediate substeps of mpmb_substep do not store apic_b
+  void *stage_buf = nullptr;  // cached staging buffer of the host<->device marshalling
+  size_t stage_bytes = 0;
   uint32_t id_base = 0;
   int num_sms = 148;
   int grid_p2g = 148 * 4, grid_g2p = 148 * 4;  // persistent grids = SMs x resident CTAs (queried)
@@ -1267,7 +1276,7 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
   {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g, P2G_T, 0) == cudaSuccess && occ > 0) h->grid_p2g = h->num_sms * occ;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<128>, 128, 0) == cudaSuccess && occ > 0) h->grid_g2p = h->num_sms * occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<128, true>, 128, 0) == cudaSuccess && occ > 0) h->grid_g2p = h->num_sms * occ;
   }
   // tiles: every tile of the (slab of the) domain can be active
   int64_t slab_layers = (h->cfg.world > 1) ? (int64_t)(P.tile_z1 - P.tile_z0) + 2 : P.nt[2];
@@ -1319,7 +1328,7 @@ int mpmb_destroy(MpmbHandle h) {
   for (int b = 0; b < 2; b++) { cudaFree(h->run_begin[b]); cudaFree(h->run_len[b]); cudaFree(h->stay[b]); }
   cudaFree(h->arr_cnt); cudaFree(h->arr_off); cudaFree(h->arr_len); cudaFree(h->arr_cur); cudaFree(h->slot_map); cudaFree(h->blocksum);
   cudaFree(h->meta);
-  cudaFree(h->arena); cudaFree(h->vel); cudaFree(h->sdf4); cudaFree(h->cnt);
+  cudaFree(h->arena); cudaFree(h->vel); cudaFree(h->sdf4); cudaFree(h->cnt); cudaFree(h->stage_buf);
   for (auto &e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
 
   delete h;
@@ -1440,7 +1449,14 @@ int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *
   // stage the field arrays on the device (one allocation)
   size_t fl = (size_t)n * (3 + 3 + (F ? 9 : 0) + (b ? 9 : 0) + 1 + 1 + (scalar ? 1 : 0)) + (group ? (size_t)n : 0);
   float *stage = nullptr;
-  CUDA_TRY(h, cudaMalloc(&stage, fl * sizeof(float)));
+  if (h->stage_bytes < fl * sizeof(float)) {
+    cudaFree(h->stage_buf);
+    h->stage_buf = nullptr;
+    h->stage_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->stage_buf, fl * sizeof(float)));
+    h->stage_bytes = fl * sizeof(float);
+  }
+  stage = (float *)h->stage_buf;
   float *p = stage;
   auto put = [&](const void *src, size_t count) -> float * {
     if (!src) return nullptr;
@@ -1456,7 +1472,6 @@ int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *
   k_pack_particles<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(V, h->P, (int)n, dx_, dv, dF, db, dm, dvol, ds, dg, h->keys[h->cur], h->id_base);
   h->launches++;
   cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(stage);
   CUDA_TRY(h, e);
   CUDA_TRY(h, cudaGetLastError());
   return finish_upload(h, n);
@@ -1544,7 +1559,14 @@ int mpmb_download_particles(MpmbHandle h, int64_t cap, int64_t *n_out, uint32_t 
   size_t fl = (size_t)alive * ((x ? 3 : 0) + (v ? 3 : 0) + (F ? 9 : 0) + (b ? 9 : 0) + (mass ? 1 : 0) + (vol ? 1 : 0) + (scalar ? 1 : 0) +
                                (id ? 1 : 0) + (group ? 1 : 0));
   float *stage = nullptr;
-  if (fl) CUDA_TRY(h, cudaMalloc(&stage, fl * sizeof(float)));
+  if (h->stage_bytes < fl * sizeof(float)) {
+    cudaFree(h->stage_buf);
+    h->stage_buf = nullptr;
+    h->stage_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->stage_buf, fl * sizeof(float)));
+    h->stage_bytes = fl * sizeof(float);
+  }
+  stage = (float *)h->stage_buf;
   float *p = stage;
   auto take = [&](bool want, size_t per) -> float * {
     if (!want) return nullptr;
@@ -1564,7 +1586,7 @@ int mpmb_download_particles(MpmbHandle h, int64_t cap, int64_t *n_out, uint32_t 
   get(x, dx_, 3); get(v, dv, 3); get(F, dF, 9); get(b, db, 9); get(mass, dm, 1); get(vol, dvol, 1); get(scalar, ds, 1);
   get(id, did, 1); get(group, dg, 1);
   cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(flags); cudaFree(prefix); cudaFree(tmp); cudaFree(stage);
+  cudaFree(flags); cudaFree(prefix); cudaFree(tmp);
   CUDA_TRY(h, e);
   CUDA_TRY(h, cudaGetLastError());
   *n_out = alive;
@@ -1654,7 +1676,8 @@ int mpmb_resample(MpmbHandle h) {
   View V = make_view(h);
   if (h->cap > 0) {
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, 0);
-    k_g2p<128><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
+    if (h->skip_b) k_g2p<128, false><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
+    else k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
     k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt);
   }
   h->launches += 3;
@@ -1692,7 +1715,7 @@ int mpmb_resample_part(MpmbHandle h, int32_t part) {
   int nl = 2;
   if (h->cap > 0) {
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, part);
-    k_g2p<128><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part);
+    k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part);
     if (part == 1) { k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt); nl++; }
   }
   h->launches += nl;
@@ -1712,7 +1735,10 @@ int mpmb_substep(MpmbHandle h, int32_t nsub) {
     int rc;
     if ((rc = mpmb_sort_particles_and_populate_grid(h)) != MPMB_OK) return rc;
     if ((rc = mpmb_rasterize(h)) != MPMB_OK) return rc;
-    if ((rc = mpmb_resample(h)) != MPMB_OK) return rc;
+    h->skip_b = (s + 1 < nsub) && h->cfg.world <= 1;  // apic_b only has to exist when control returns to the host
+    rc = mpmb_resample(h);
+    h->skip_b = false;
+    if (rc != MPMB_OK) return rc;
   }
   return MPMB_OK;
 }
