@@ -295,6 +295,8 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
     eng.set_stream(stream.cuda_stream)
     runner = slab.SlabRunner(slab.EngineAdapter(eng), rank, world, dev, dist=dist if world > 1 else None)
+    if world > 1 and args.exchange == "peer":
+        slab.connect_peers(eng, rank, world, dist)  # neighbours' receive buffers mapped over NVLink (CUDA IPC)
     eng.set_material(0, kind, sc["mat_params"][0])
     if sc["planes"] is not None:
         eng.set_planes(sc["planes"], sc["friction"])
@@ -326,7 +328,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    substep = (lambda k: eng.substep(k)) if world == 1 else (lambda k: runner.substep(k))
+    substep = (lambda k: eng.substep(k)) if (world == 1 or args.exchange == "peer") else (lambda k: runner.substep(k))
     # ---- device-resident throughput
     substep(args.warmup)
     barrier()
@@ -432,8 +434,12 @@ def run_ours(args):
         "alive_particles": alive, "active_tiles": c1["active_tiles"],
     }
     if world > 1:
-        line["exchange"] = {"bytes_sent_per_step_rank0": runner.bytes_sent / max(1, args.warmup + args.steps + 3 + args.frames * frame_substeps),
-                            "transport": "torch.distributed NCCL point-to-point (batch_isend_irecv), fixed-size messages"}
+        if args.exchange == "peer":
+            line["exchange"] = {"transport": "peer memory over NVLink (CUDA IPC): pack kernels store into the neighbour GPU, "
+                                             "seq flag release/acquire, no host transport, substeps run inside the C-ABI"}
+        else:
+            line["exchange"] = {"bytes_sent_per_step_rank0": runner.bytes_sent / max(1, args.warmup + args.steps + 3 + args.frames * frame_substeps),
+                                "transport": "torch.distributed NCCL point-to-point (batch_isend_irecv), fixed-size messages"}
     emit(line)
     if world > 1:
         dist.barrier()
@@ -479,6 +485,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--migrate-capacity", type=int, default=16384, help="particles per face per substep (z-slab message size)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="z-slab transport: NVLink peer memory (default) or NCCL send/recv")
     ap.add_argument("--halo-capacity", type=int, default=2048, help="active tiles per boundary layer (z-slab message size)")
     args = ap.parse_args()
     if args.impl == "reference":

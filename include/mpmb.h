@@ -193,6 +193,22 @@ int64_t mpmb_migrate_bytes(MpmbHandle h);
 int mpmb_migrate_pack(MpmbHandle h, int32_t face, void *dev_buf);
 int mpmb_migrate_unpack(MpmbHandle h, int32_t face, const void *dev_buf);
 
+/* Peer-memory exchange: with the neighbours' receive buffers mapped (CUDA IPC between processes, or
+ * plain pointers inside one process) the engine needs no host transport at all — the pack kernels
+ * store straight into the neighbour GPU over NVLink, a {count, seq} header is released system-wide
+ * and the neighbour's unpack waits on it.  mpmb_substep(h, n) then runs whole z-slab substeps,
+ * exchanges included, without returning to the host.
+ *   kind 0 = halo arenas, kind 1 = migrating particles.  Through face f a rank writes into the
+ *   neighbour's buffer of the OPPOSITE face.                                                        */
+int mpmb_xchg_buffer(MpmbHandle h, int32_t kind, int32_t face, void **dev_ptr);      /* my receive buffer   */
+int mpmb_xchg_ipc_handle(MpmbHandle h, int32_t kind, int32_t face, void *out64);     /* its 64-byte IPC handle */
+int mpmb_xchg_connect(MpmbHandle h, int32_t kind, int32_t face, const void *handle64, void *same_process_ptr);
+/* the four exchange steps of one substep, for hosts that drive the stages themselves */
+int mpmb_halo_send(MpmbHandle h, int32_t face);     /* after mpmb_rasterize                      */
+int mpmb_halo_recv(MpmbHandle h, int32_t face);     /* before mpmb_resample                      */
+int mpmb_migrate_send(MpmbHandle h, int32_t face);  /* after mpmb_resample                       */
+int mpmb_migrate_recv(MpmbHandle h, int32_t face);  /* before the next ordering                  */
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,7 @@ EXPORTS = [
     "mpmb_resample_part", "mpmb_download_grid",
     "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters",
     "mpmb_halo_bytes", "mpmb_halo_pack", "mpmb_halo_unpack", "mpmb_migrate_bytes", "mpmb_migrate_pack", "mpmb_migrate_unpack",
+    "mpmb_xchg_buffer", "mpmb_xchg_ipc_handle", "mpmb_xchg_connect", "mpmb_halo_send", "mpmb_halo_recv", "mpmb_migrate_send", "mpmb_migrate_recv",
 ]
 
 
@@ -271,6 +272,33 @@ class Engine:
 
     def migrate_unpack(self, face, dev_ptr):
         self._check(self.L.mpmb_migrate_unpack(self.h, C.c_int32(face), C.c_void_p(int(dev_ptr))))
+
+    # --- peer-memory exchange
+    def xchg_buffer(self, kind, face):
+        p = C.c_void_p()
+        self._check(self.L.mpmb_xchg_buffer(self.h, C.c_int32(kind), C.c_int32(face), C.byref(p)))
+        return p.value
+
+    def xchg_ipc_handle(self, kind, face):
+        buf = (C.c_ubyte * 64)()
+        self._check(self.L.mpmb_xchg_ipc_handle(self.h, C.c_int32(kind), C.c_int32(face), buf))
+        return bytes(buf)
+
+    def xchg_connect(self, kind, face, handle=None, ptr=None):
+        hb = (C.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        self._check(self.L.mpmb_xchg_connect(self.h, C.c_int32(kind), C.c_int32(face), hb, C.c_void_p(ptr) if ptr else None))
+
+    def halo_send(self, face):
+        self._check(self.L.mpmb_halo_send(self.h, C.c_int32(face)))
+
+    def halo_recv(self, face):
+        self._check(self.L.mpmb_halo_recv(self.h, C.c_int32(face)))
+
+    def migrate_send(self, face):
+        self._check(self.L.mpmb_migrate_send(self.h, C.c_int32(face)))
+
+    def migrate_recv(self, face):
+        self._check(self.L.mpmb_migrate_recv(self.h, C.c_int32(face)))
 
     # --- profiling
     def set_profiling(self, enabled):

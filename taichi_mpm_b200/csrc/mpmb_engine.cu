@@ -68,7 +68,7 @@ struct Counters {  // device-resident
   int n_alive;        // particles binned by the last ordering
   int pad;
 };
-enum { DEVERR_TILE_CAPACITY = 1, DEVERR_MIGRATE_CAPACITY = 2, DEVERR_PARTICLE_CAPACITY = 4 };
+enum { DEVERR_TILE_CAPACITY = 1, DEVERR_MIGRATE_CAPACITY = 2, DEVERR_PARTICLE_CAPACITY = 4, DEVERR_PEER_TIMEOUT = 8 };
 
 struct TileMeta {  // one 32-byte record per active tile (slot)
   int tile, run_begin, run_len, arr_off, arr_len, out_begin, pad0, pad1;
@@ -1024,6 +1024,30 @@ __global__ void k_migrate_unpack(View V, Params P, int cap, const int *hdr, cons
     V.mover_idx[mbase + e] = (uint32_t)dst;
   }
 }
+// Peer-memory exchange (no NCCL on the data path): the pack kernels store the payload straight into
+// the neighbour GPU's receive buffer over NVLink; k_xchg_publish then writes {count, seq} with a
+// system-scope release, and the neighbour's k_xchg_wait spins (acquire) on seq before its unpack
+// kernel runs.  One substep = one seq value; a bounded spin turns a lost peer into an error flag
+// instead of a hung GPU.
+__global__ void k_xchg_publish(const int *local_count, int *remote_hdr, int seq) {
+  remote_hdr[0] = local_count[0];
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote_hdr + 1), "r"(seq) : "memory");
+}
+__global__ void k_xchg_wait(const int *hdr, int seq, Counters *cnt) {
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(hdr + 1) : "memory");
+    if (v >= seq) return;
+    if (clock64() - t0 > 6000000000ll) {  // ~3 s at 2 GHz: give up loudly
+      atomicOr(&cnt->error, 8);
+      return;
+    }
+    __nanosleep(200);
+  }
+}
+
 __global__ void k_migrate_commit(Counters *c, const int *hdr, int cap, int cap_particles) {
   const int n = min(min(hdr[0], cap), max(cap_particles - c->n_store, 0));
   c->n_store += n;
@@ -1073,6 +1097,12 @@ struct MpmbEngine {
 
   int stage = 0;  // 0 idle/after resample, 1 after sort, 2 after rasterize
   int64_t mig_cap = 0;
+  // peer-memory exchange: rx = my receive buffers [kind 0 halo / 1 migration][face], tx = the
+  // neighbour's receive buffer I write into through face f (mapped by IPC or same-process pointer)
+  char *rx[2][2] = {}, *tx[2][2] = {};
+  bool tx_ipc[2][2] = {};
+  int *xcount = nullptr;  // local pack counters (int4 per [kind][face])
+  int xstep = 0;          // substeps completed since the peers were connected
   bool skip_b = false;        // intermediate substeps of mpmb_substep do not store apic_b
   void *stage_buf = nullptr;  // cached staging buffer of the host<->device marshalling
   size_t stage_bytes = 0;
@@ -1312,6 +1342,16 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
       return fail(nullptr, MPMB_ERR_INVALID, "bad slab [%d,%d) for %d tile layers", cfg->tile_z0, cfg->tile_z1, P.nt[2]);
     }
   }
+  if (h->cfg.world > 1) {
+    const int64_t bytes[2] = {mpmb_halo_bytes(h), mpmb_migrate_bytes(h)};
+    for (int k = 0; k < 2; k++)
+      for (int f = 0; f < 2; f++) {
+        if (cudaMalloc(&h->rx[k][f], bytes[k]) != cudaSuccess) return bail("cudaMalloc exchange buffer");
+        cudaMemset(h->rx[k][f], 0, 16);
+      }
+    if (cudaMalloc(&h->xcount, sizeof(int) * 16) != cudaSuccess) return bail("cudaMalloc exchange counters");
+    cudaMemset(h->xcount, 0, sizeof(int) * 16);
+  }
   if (cfg->capacity > 0) {
     int rc = alloc_particles(h, cfg->capacity);
     if (rc != MPMB_OK) { g_create_error = h->err; mpmb_destroy(h); return rc; }
@@ -1328,7 +1368,12 @@ int mpmb_destroy(MpmbHandle h) {
   for (int b = 0; b < 2; b++) { cudaFree(h->run_begin[b]); cudaFree(h->run_len[b]); cudaFree(h->stay[b]); }
   cudaFree(h->arr_cnt); cudaFree(h->arr_off); cudaFree(h->arr_len); cudaFree(h->arr_cur); cudaFree(h->slot_map); cudaFree(h->blocksum);
   cudaFree(h->meta);
-  cudaFree(h->arena); cudaFree(h->vel); cudaFree(h->sdf4); cudaFree(h->cnt); cudaFree(h->stage_buf);
+  cudaFree(h->arena); cudaFree(h->vel); cudaFree(h->sdf4); cudaFree(h->cnt); cudaFree(h->stage_buf); cudaFree(h->xcount);
+  for (int k = 0; k < 2; k++)
+    for (int f = 0; f < 2; f++) {
+      if (h->tx_ipc[k][f] && h->tx[k][f]) cudaIpcCloseMemHandle(h->tx[k][f]);
+      cudaFree(h->rx[k][f]);
+    }
   for (auto &e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
 
   delete h;
@@ -1349,6 +1394,7 @@ int mpmb_synchronize(MpmbHandle h) {
   if (c.error & DEVERR_TILE_CAPACITY) return fail(h, MPMB_ERR_CAPACITY, "active tile capacity exceeded");
   if (c.error & DEVERR_MIGRATE_CAPACITY) return fail(h, MPMB_ERR_CAPACITY, "migration buffer capacity exceeded");
   if (c.error & DEVERR_PARTICLE_CAPACITY) return fail(h, MPMB_ERR_CAPACITY, "particle capacity exceeded");
+  if (c.error & DEVERR_PEER_TIMEOUT) return fail(h, MPMB_ERR_STATE, "peer exchange timed out (neighbour rank not stepping)");
   return MPMB_OK;
 }
 
@@ -1686,9 +1732,16 @@ int mpmb_resample(MpmbHandle h) {
   h->cur ^= 1;  // the buffer G2P wrote is the current storage ...
   h->ord ^= 1;  // ... its runs / stay counts are the current ones ...
   h->mov ^= 1;  // ... and its mover list feeds the next ordering
+  h->xstep++;
   h->stage = 0;
   return MPMB_OK;
 }
+
+static bool peers_connected(MpmbEngine *h);
+int mpmb_halo_send(MpmbHandle h, int32_t face);
+int mpmb_halo_recv(MpmbHandle h, int32_t face);
+int mpmb_migrate_send(MpmbHandle h, int32_t face);
+int mpmb_migrate_recv(MpmbHandle h, int32_t face);
 
 // z-slab runs: the same two stages in two launches each, boundary-layer tiles (part 1) and the
 // rest (part 2), so that the host can put the halo exchange between them (include/mpmb.h).
@@ -1725,20 +1778,35 @@ int mpmb_resample_part(MpmbHandle h, int32_t part) {
   h->cur ^= 1;
   h->ord ^= 1;
   h->mov ^= 1;
+  h->xstep++;
   h->stage = 0;
   return MPMB_OK;
 }
 
 int mpmb_substep(MpmbHandle h, int32_t nsub) {
   CHECK_HANDLE(h);
+  const bool peers = peers_connected(h);
+  if (h->cfg.world > 1 && !peers) return fail(h, MPMB_ERR_STATE, "z-slab run: connect the peers (mpmb_xchg_connect) or drive the stages and move the buffers yourself");
   for (int s = 0; s < nsub; s++) {
     int rc;
     if ((rc = mpmb_sort_particles_and_populate_grid(h)) != MPMB_OK) return rc;
     if ((rc = mpmb_rasterize(h)) != MPMB_OK) return rc;
+    if (peers) {  // boundary-layer arenas straight into the neighbours' memory, then wait for theirs
+      for (int f = 0; f < 2; f++)
+        if (h->tx[0][f] && (rc = mpmb_halo_send(h, f)) != MPMB_OK) return rc;
+      for (int f = 0; f < 2; f++)
+        if (h->tx[0][f] && (rc = mpmb_halo_recv(h, f)) != MPMB_OK) return rc;
+    }
     h->skip_b = (s + 1 < nsub) && h->cfg.world <= 1;  // apic_b only has to exist when control returns to the host
     rc = mpmb_resample(h);
     h->skip_b = false;
     if (rc != MPMB_OK) return rc;
+    if (peers) {
+      for (int f = 0; f < 2; f++)
+        if (h->tx[1][f] && (rc = mpmb_migrate_send(h, f)) != MPMB_OK) return rc;
+      for (int f = 0; f < 2; f++)
+        if (h->tx[1][f] && (rc = mpmb_migrate_recv(h, f)) != MPMB_OK) return rc;
+    }
   }
   return MPMB_OK;
 }
@@ -1894,6 +1962,125 @@ int mpmb_migrate_unpack(MpmbHandle h, int32_t face, const void *dev_buf) {
   k_migrate_commit<<<1, 1, 0, h->stream>>>(h->cnt, (const int *)b, (int)h->mig_cap, (int)h->cap);
   h->launches += 2;
   prof_end(h, 2);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
+
+
+// ------------------------------------------------------------------------------ peer-memory exchange
+int mpmb_xchg_buffer(MpmbHandle h, int32_t kind, int32_t face, void **dev_ptr) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1 || kind < 0 || kind > 1 || face < 0 || face > 1 || !dev_ptr) return fail(h, MPMB_ERR_INVALID, "bad argument");
+  *dev_ptr = h->rx[kind][face];
+  return MPMB_OK;
+}
+
+int mpmb_xchg_ipc_handle(MpmbHandle h, int32_t kind, int32_t face, void *out64) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1 || kind < 0 || kind > 1 || face < 0 || face > 1 || !out64) return fail(h, MPMB_ERR_INVALID, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  CUDA_TRY(h, cudaIpcGetMemHandle(&hd, h->rx[kind][face]));
+  memcpy(out64, &hd, 64);
+  return MPMB_OK;
+}
+
+// Through face f this rank writes into the neighbour's receive buffer of the OPPOSITE face.  Give
+// either that buffer's IPC handle (another process) or its device pointer (same process).
+int mpmb_xchg_connect(MpmbHandle h, int32_t kind, int32_t face, const void *handle64, void *same_process_ptr) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1 || kind < 0 || kind > 1 || face < 0 || face > 1) return fail(h, MPMB_ERR_INVALID, "bad argument");
+  if (same_process_ptr) {
+    h->tx[kind][face] = (char *)same_process_ptr;
+    h->tx_ipc[kind][face] = false;
+  } else {
+    if (!handle64) return fail(h, MPMB_ERR_INVALID, "handle or pointer required");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    void *p = nullptr;
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->tx[kind][face] = (char *)p;
+    h->tx_ipc[kind][face] = true;
+  }
+  h->xstep = 0;
+  return MPMB_OK;
+}
+
+static bool peers_connected(MpmbEngine *h) {
+  if (h->cfg.world <= 1) return false;
+  const bool lo = h->P.tile_z0 > 0 && h->cfg.rank > 0, hi = h->cfg.rank + 1 < h->cfg.world;
+  for (int k = 0; k < 2; k++) {
+    if (lo && !h->tx[k][0]) return false;
+    if (hi && !h->tx[k][1]) return false;
+  }
+  return lo || hi;
+}
+
+int mpmb_halo_send(MpmbHandle h, int32_t face) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1 || face < 0 || face > 1 || !h->tx[0][face]) return fail(h, MPMB_ERR_STATE, "no connected peer through face %d", face);
+  if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "halo_send must follow rasterize");
+  prof_begin(h, 3);
+  char *b = h->tx[0][face];
+  int *cnt = h->xcount + 4 * face;
+  CUDA_TRY(h, cudaMemsetAsync(cnt, 0, 16, h->stream));
+  View V = make_view(h);
+  const int layer = face == 0 ? h->P.tile_z0 : h->P.tile_z1 - 1;
+  k_halo_pack<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, layer, (int)halo_cap_xy(h), cnt, (int *)(b + 16), (float4 *)(b + 16 + halo_idx_bytes(h)));
+  k_xchg_publish<<<1, 1, 0, h->stream>>>(cnt, (int *)b, h->xstep + 1);
+  h->launches += 2;
+  prof_end(h, 2);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
+
+int mpmb_halo_recv(MpmbHandle h, int32_t face) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1 || face < 0 || face > 1 || !h->tx[0][face]) return fail(h, MPMB_ERR_STATE, "no connected peer through face %d", face);
+  if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "halo_recv must follow rasterize");
+  prof_begin(h, 3);
+  const char *b = h->rx[0][face];
+  View V = make_view(h);
+  const int layer = face == 0 ? h->P.tile_z0 - 1 : h->P.tile_z1;
+  k_xchg_wait<<<1, 1, 0, h->stream>>>((const int *)b, h->xstep + 1, h->cnt);
+  k_halo_unpack<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, layer, (int)halo_cap_xy(h), (const int *)b, (const int *)(b + 16),
+                                                       (const float4 *)(b + 16 + halo_idx_bytes(h)));
+  h->launches += 2;
+  prof_end(h, 2);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
+
+int mpmb_migrate_send(MpmbHandle h, int32_t face) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1 || face < 0 || face > 1 || !h->tx[1][face]) return fail(h, MPMB_ERR_STATE, "no connected peer through face %d", face);
+  if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "migrate_send must follow resample");
+  prof_begin(h, 3);
+  char *b = h->tx[1][face];
+  int *cnt = h->xcount + 8 + 4 * face;
+  CUDA_TRY(h, cudaMemsetAsync(cnt, 0, 16, h->stream));
+  View V = make_view(h);
+  const uint32_t key_face = h->special_min + (face == 0 ? SPECIAL_MIG_DOWN : SPECIAL_MIG_UP);
+  k_migrate_pack<<<h->num_sms * 2, 256, 0, h->stream>>>(V, key_face, h->key_dead, (int)h->mig_cap, cnt, (float4 *)(b + 16));
+  k_xchg_publish<<<1, 1, 0, h->stream>>>(cnt, (int *)b, h->xstep);
+  h->launches += 2;
+  prof_end(h, 2);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
+
+int mpmb_migrate_recv(MpmbHandle h, int32_t face) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world <= 1 || face < 0 || face > 1 || !h->tx[1][face]) return fail(h, MPMB_ERR_STATE, "no connected peer through face %d", face);
+  if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "migrate_recv must follow resample");
+  prof_begin(h, 3);
+  const char *b = h->rx[1][face];
+  View V = make_view(h);
+  k_xchg_wait<<<1, 1, 0, h->stream>>>((const int *)b, h->xstep, h->cnt);
+  k_migrate_unpack<<<64, 256, 0, h->stream>>>(V, h->P, (int)h->mig_cap, (const int *)b, (const float4 *)(b + 16));
+  k_migrate_commit<<<1, 1, 0, h->stream>>>(h->cnt, (const int *)b, (int)h->mig_cap, (int)h->cap);
+  h->launches += 3;
+  prof_end(h, 3);
   CUDA_TRY(h, cudaGetLastError());
   return MPMB_OK;
 }

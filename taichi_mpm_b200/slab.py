@@ -181,3 +181,18 @@ class SlabRunner:
                     a.migrate_unpack(0, self.mig_recv[0])
                 if self.has_hi:
                     a.migrate_unpack(1, self.mig_recv[1])
+
+
+def connect_peers(engine, rank, world, dist):
+    """Maps the ring neighbours' receive buffers into `engine` with CUDA IPC (one process per GPU):
+    afterwards engine.substep(n) runs whole z-slab substeps, halo and migration included, with no
+    host transport.  Handles travel through torch.distributed once."""
+    mine = {(k, f): engine.xchg_ipc_handle(k, f) for k in (0, 1) for f in (0, 1)}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    for k in (0, 1):
+        if rank > 0:
+            engine.xchg_connect(k, 0, handle=everyone[rank - 1][(k, 1)])   # my face 0 -> lower neighbour's face-1 buffer
+        if rank < world - 1:
+            engine.xchg_connect(k, 1, handle=everyone[rank + 1][(k, 0)])   # my face 1 -> upper neighbour's face-0 buffer
+    dist.barrier()

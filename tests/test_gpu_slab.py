@@ -188,3 +188,114 @@ def test_two_slabs_on_one_gpu_match_single_run():
     in0 = set(parts[0]["gid"].tolist())
     started0 = set(np.nonzero(tz0 < cuts[0][1])[0].tolist())
     assert len(in0 - started0) > 0 and len(started0 - in0) > 0, "no migration happened in either direction"
+
+
+def test_two_slabs_peer_memory_exchange_one_gpu():
+    """Same two slabs, but the exchange runs through the engine's peer-memory path (pack kernels write
+    into the other engine's receive buffer, seq flag, wait kernel) instead of host-moved buffers."""
+    import torch
+    from taichi_mpm_b200 import capi, slab
+    from tests import common as T
+    scene, st = _scene()
+    nsub, world = 40, 2
+    tz = slab.base_tile_z(st["x"][:, 2], scene["dx"])
+    cuts = slab.slab_partition(tz, slab.tile_layers(scene["res"][2]), world)
+    counts = [int(((tz >= a) & (tz < b)).sum()) for a, b in cuts]
+    eng = []
+    for rank in range(world):
+        z0, z1 = cuts[rank]
+        e = capi.Engine(scene["res"], scene["dx"], scene["dt"], scene["gravity"], 1, True, device=0, rank=rank, world=world,
+                        tile_z0=z0, tile_z1=z1, migrate_capacity=4096, halo_capacity=64)
+        e.set_material(0, int(scene["mat_kind"][0]), scene["mat_params"][0])
+        e.set_planes(scene["planes"], scene["friction"])
+        e.set_id_base(sum(counts[:rank]))
+        mine = np.nonzero((tz >= z0) & (tz < z1))[0]
+        e.upload(*(st[k][mine] for k in ("x", "v", "mass", "vol", "F", "b", "ps", "group")))
+        eng.append(e)
+    e0, e1 = eng
+    for k in (0, 1):
+        e0.xchg_connect(k, 1, ptr=e1.xchg_buffer(k, 0))
+        e1.xchg_connect(k, 0, ptr=e0.xchg_buffer(k, 1))
+    for _ in range(nsub):   # one stream, one process: interleave the stages so that every wait finds its flag
+        for e in eng:
+            e.sort_particles_and_populate_grid(); e.rasterize()
+        e0.halo_send(1); e1.halo_send(0)
+        e0.halo_recv(1); e1.halo_recv(0)
+        for e in eng:
+            e.resample()
+        e0.migrate_send(1); e1.migrate_send(0)
+        e0.migrate_recv(1); e1.migrate_recv(0)
+    order = np.concatenate([np.nonzero((tz >= a) & (tz < b))[0] for a, b in cuts])
+    parts = []
+    for e in eng:
+        g = e.download()
+        g["gid"] = order[g["id"].astype(np.int64)]
+        parts.append(g)
+        e.close()
+    ref_e = T.make_engine(scene, st)
+    ref_e.substep(nsub)
+    ref = ref_e.download()
+    ref_e.close()
+    gid = np.concatenate([p["gid"] for p in parts])
+    o = np.argsort(gid)
+    assert np.array_equal(gid[o], ref["id"].astype(np.int64))
+    for k, tol in (("x", 2e-6), ("v", 5e-4), ("F", 5e-5)):
+        got = np.concatenate([p[k] for p in parts])[o]
+        scale = max(np.abs(ref[k]).max(), 1e-30) if k == "v" else 1.0
+        assert np.abs(got - ref[k]).max() <= tol * scale, k
+
+
+def _peer_worker(rank, world, port, nsub, out_path):
+    import torch
+    import torch.distributed as dist
+    from taichi_mpm_b200 import capi, slab
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    scene, st = _scene()
+    tz = slab.base_tile_z(st["x"][:, 2], scene["dx"])
+    cuts = slab.slab_partition(tz, slab.tile_layers(scene["res"][2]), world)
+    z0, z1 = cuts[rank]
+    mine = np.nonzero((tz >= z0) & (tz < z1))[0]
+    e = capi.Engine(scene["res"], scene["dx"], scene["dt"], scene["gravity"], 1, True, device=rank, rank=rank, world=world, tile_z0=z0, tile_z1=z1,
+                    migrate_capacity=4096, halo_capacity=64)
+    e.set_material(0, int(scene["mat_kind"][0]), scene["mat_params"][0])
+    e.set_planes(scene["planes"], scene["friction"])
+    counts = [int(((tz >= a) & (tz < b)).sum()) for a, b in cuts]
+    e.set_id_base(sum(counts[:rank]))
+    e.upload(*(st[k][mine] for k in ("x", "v", "mass", "vol", "F", "b", "ps", "group")))
+    slab.connect_peers(e, rank, world, dist)
+    e.substep(nsub)            # whole z-slab substeps inside the C-ABI, exchanges over NVLink peer memory
+    e.synchronize()
+    got = e.download()
+    order = np.concatenate([np.nonzero((tz >= a) & (tz < b))[0] for a, b in cuts])
+    got["gid"] = order[got["id"].astype(np.int64)]
+    np.savez(out_path % rank, **got)
+    dist.barrier()
+    e.close()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_peer_memory_exchange(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from tests import common as T
+    nsub = 60
+    out_path = str(tmp_path / "peer%d.npz")
+    mp.spawn(_peer_worker, args=(2, _free_port(), nsub, out_path), nprocs=2, join=True)
+    scene, st = _scene()
+    e = T.make_engine(scene, st)
+    e.substep(nsub)
+    ref = e.download()
+    e.close()
+    parts = [np.load(out_path % r) for r in range(2)]
+    gid = np.concatenate([p["gid"] for p in parts])
+    o = np.argsort(gid)
+    assert np.array_equal(gid[o], ref["id"].astype(np.int64))
+    for k, tol in (("x", 2e-6), ("v", 5e-4), ("F", 5e-5), ("ps", 1e-5)):
+        got = np.concatenate([p[k] for p in parts])[o]
+        scale = max(np.abs(ref[k]).max(), 1e-30) if k == "v" else 1.0
+        assert np.abs(got - ref[k]).max() <= tol * scale, k
