@@ -320,6 +320,8 @@ def run_ours(args):
                                  host["b"].data_ptr(), 0, 0, host["ps"].data_ptr(), 0)
 
     upload()
+    if world > 1:
+        dist.barrier()  # peer-memory waits are bounded: start the ranks together
     h2d = n * (3 + 3 + 9 + 9 + 1 + 1 + 1 + 1) * 4
     d2h = n * (1 + 3 + 3 + 9 + 9 + 1) * 4
 
@@ -373,6 +375,8 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         upload()
+        if world > 1:
+            dist.barrier()
         substep(frame_substeps)
         n_alive = download()
         barrier()

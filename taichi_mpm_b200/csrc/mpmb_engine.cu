@@ -1027,8 +1027,8 @@ __global__ void k_migrate_unpack(View V, Params P, int cap, const int *hdr, cons
 // Peer-memory exchange (no NCCL on the data path): the pack kernels store the payload straight into
 // the neighbour GPU's receive buffer over NVLink; k_xchg_publish then writes {count, seq} with a
 // system-scope release, and the neighbour's k_xchg_wait spins (acquire) on seq before its unpack
-// kernel runs.  One substep = one seq value; a bounded spin turns a lost peer into an error flag
-// instead of a hung GPU.
+// kernel runs.  One substep = one seq value; a bounded spin (~30 s) turns a lost peer into an error
+// flag instead of a hung GPU.
 __global__ void k_xchg_publish(const int *local_count, int *remote_hdr, int seq) {
   remote_hdr[0] = local_count[0];
   __threadfence_system();
@@ -1040,7 +1040,7 @@ __global__ void k_xchg_wait(const int *hdr, int seq, Counters *cnt) {
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(hdr + 1) : "memory");
     if (v >= seq) return;
-    if (clock64() - t0 > 6000000000ll) {  // ~3 s at 2 GHz: give up loudly
+    if (clock64() - t0 > 60000000000ll) {  // ~30 s at 2 GHz (ranks may start seconds apart): give up loudly
       atomicOr(&cnt->error, 8);
       return;
     }
