@@ -171,6 +171,7 @@ inline void svd3_fast(const float *A, float *U, float *s, float *V) {
     if (apq == 0.f) return;
     const float d = aqq - app, b = 2.f * apq;
     const float h = std::sqrt(d * d + b * b);
+    if (!(h > 0.f)) return;  // d == 0 and b*b underflowed: already diagonal to working precision
     const float t = b / (d + (d >= 0.f ? h : -h));
     const float c = 1.f / std::sqrt(t * t + 1.f), sn = t * c;
     app -= t * apq; aqq += t * apq; apq = 0.f;
