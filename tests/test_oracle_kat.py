@@ -273,3 +273,27 @@ def test_mpm88_2d_config1():
     xs, vs, Fs, Cs, Js, _ = O.mpm88_advance(n, 1e-4, x, v, F, C, Jp, plastic=False, dtype=np.float32)
     xd, vd, Fd, Cd, Jd, _ = O.mpm88_advance(n, 1e-4, x, v, F, C, Jp, plastic=False, dtype=np.float64)
     assert np.abs(xs - xd).max() < 1e-6 and np.abs(vs - vd).max() < 1e-5
+
+
+def test_fast_path_is_finite_for_resting_sand_next_to_water():
+    # regression: F = I exactly made the fast SVD's pivot underflow (NaN) — sand at rest is the
+    # headline scene's initial state
+    res = 32
+    xa, ma, va = scenes.lattice_block(res, (10, 10, 10), (16, 16, 16), 400.0, 0.05)
+    xb, mb, vb = scenes.lattice_block(res, (18, 11, 18), (22, 15, 22), 400.0, 0.0)
+    sa = scenes.make_state(xa, ma, va, scenes.MAT_SAND, 0)
+    sb = scenes.make_state(xb, mb, vb, scenes.MAT_WATER, 1)
+    st = {k: np.concatenate([sa[k], sb[k]]) for k in sa}
+    planes = np.array([[0, 1, 0, -10.0]], np.float32)
+    scene = dict(res=(res,) * 3, dx=1.0 / res, dt=2e-5, gravity=(0.0, -10.0, 0.0), particle_gravity=1,
+                 mat_kind=np.array([scenes.MAT_SAND, scenes.MAT_WATER], np.int32),
+                 mat_params=np.stack([scenes.material_params(scenes.MAT_SAND), scenes.material_params(scenes.MAT_WATER)]),
+                 sdf=scenes.planes_sdf(res, planes), friction=0.4)
+    f = O.FastOracle(scene, st, threads=2)
+    f.substeps(10)
+    ref = st
+    for _ in range(10):
+        ref, _, _ = O.substep(scene, ref, np.float32)
+    for k in ("x", "v", "F"):
+        assert np.isfinite(f.st[k]).all(), k
+        assert np.abs(f.st[k] - ref[k]).max() <= 2e-3 * max(np.abs(ref[k]).max(), 1e-6), k   # different fp32 SVDs, tiny velocities
