@@ -622,7 +622,7 @@ struct FastState {
   int res[3];
   int nb[3];                      // blocks per axis (4,4,8)
   std::vector<float> grid;        // [block][128][4]
-  std::vector<uint64_t> keys;
+  std::vector<uint64_t> keys, keys_tmp;
   std::vector<int32_t> order;
   std::vector<int32_t> block_ids; // occupied blocks
   std::vector<int32_t> block_off; // particle offsets per occupied block (+sentinel)
@@ -662,24 +662,47 @@ void fast_substep(FastState &st, const Scene<float> &sc, Particles<float> &P, st
     st.keys[i] = (((b << 7) | in) << 26) | uint64_t(i);
     n_alive++;
   }
-  // parallel sort: per-thread chunks + merge (stand-in for tbb::parallel_sort, 793-795)
+  // parallel sort (stand-in for tbb::parallel_sort, src/mpm.cpp:793-795): the keys carry the particle
+  // index in their low 26 bits and arrive in index order, so a STABLE LSD radix sort over the
+  // (block,node) bits alone yields the same order as sorting the full 64-bit keys.
   {
-    std::vector<uint64_t> &k = st.keys;
     int nt = 1;
 #ifdef _OPENMP
     nt = omp_get_max_threads();
 #endif
-    std::vector<size_t> cut(nt + 1);
-    for (int t = 0; t <= nt; t++) cut[t] = size_t(n) * t / nt;
-#pragma omp parallel for schedule(static, 1)
-    for (int t = 0; t < nt; t++) std::sort(k.begin() + cut[t], k.begin() + cut[t + 1]);
-    for (int width = 1; width < nt; width *= 2) {
-#pragma omp parallel for schedule(static, 1)
-      for (int t = 0; t < nt; t += 2 * width) {
-        int mid = std::min(t + width, nt), hi = std::min(t + 2 * width, nt);
-        std::inplace_merge(k.begin() + cut[t], k.begin() + cut[mid], k.begin() + cut[hi]);
-      }
+    const int RB = 11, NB = 1 << RB;
+    int top = 26 + 7;  // highest significant bit: block index range
+    {
+      uint64_t nblk = uint64_t(st.nb[0]) * st.nb[1] * st.nb[2];
+      while ((1ull << (top - 26 - 7)) < nblk) top++;
+      top += 1;  // dead keys (~0) must still sort last: handled by the clamp below
     }
+    st.keys_tmp.resize(n);
+    std::vector<uint32_t> hist(size_t(nt) * NB);
+    uint64_t *src = st.keys.data(), *dst = st.keys_tmp.data();
+    auto digit = [&](uint64_t k, int shift, bool last) -> uint32_t {
+      if (k == ~0ull) return last ? NB - 1 : (NB - 1);  // dead: always the last bucket
+      return uint32_t(k >> shift) & (NB - 1);
+    };
+    for (int shift = 26; shift < top; shift += RB) {
+      const bool last = shift + RB >= top;
+      std::fill(hist.begin(), hist.end(), 0u);
+#pragma omp parallel for schedule(static, 1)
+      for (int t = 0; t < nt; t++) {
+        uint32_t *h = &hist[size_t(t) * NB];
+        for (size_t i = size_t(n) * t / nt, e = size_t(n) * (t + 1) / nt; i < e; i++) h[digit(src[i], shift, last)]++;
+      }
+      uint32_t run = 0;
+      for (int d = 0; d < NB; d++)
+        for (int t = 0; t < nt; t++) { uint32_t c = hist[size_t(t) * NB + d]; hist[size_t(t) * NB + d] = run; run += c; }
+#pragma omp parallel for schedule(static, 1)
+      for (int t = 0; t < nt; t++) {
+        uint32_t *h = &hist[size_t(t) * NB];
+        for (size_t i = size_t(n) * t / nt, e = size_t(n) * (t + 1) / nt; i < e; i++) dst[h[digit(src[i], shift, last)]++] = src[i];
+      }
+      std::swap(src, dst);
+    }
+    if (src != st.keys.data()) st.keys.swap(st.keys_tmp);
   }
   st.order.resize(n_alive);
   st.block_ids.clear();
