@@ -103,23 +103,6 @@ def test_two_slabs_match_single_gpu(tmp_path):
     assert len(in0 - started0) > 0 and len(started0 - in0) > 0, "no migration happened in either direction"
 
 
-class _LocalLink:
-    """Stands in for torch.distributed between two engines living on the same GPU: messages are
-    handed over by pointer, in the order SlabRunner would send/receive them."""
-
-    def __init__(self):
-        self.box = {}
-
-    def P2POp(self, op, tensor, peer, group=None):
-        return (op, tensor, peer)
-
-    def isend(self):
-        pass
-
-    def irecv(self):
-        pass
-
-
 def _run_two_slabs_one_process(scene, st, nsub, device=0):
     """Both slabs of a 2-rank run in ONE process on one GPU (no NCCL): the exchange buffers are
     copied engine to engine.  Exercises halo ghost tiles and migration with the default 1-GPU suite."""
