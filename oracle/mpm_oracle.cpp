@@ -20,6 +20,8 @@
 // Matrices are column-major 3x3: m[c*3+r] is row r of column c (README.md:314,
 // src/transfer.cpp:503,929: `M[i]` is column i).
 // =====================================================================================
+#include <immintrin.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -629,6 +631,15 @@ struct FastState {
   std::vector<uint8_t> fat;       // dilated block flags
   std::vector<int32_t> fat_ids;
   double t_sort = 0, t_p2g = 0, t_grid = 0, t_g2p = 0;
+  // Physical re-ordering of the particle storage (sort_allocator, src/mpm.cpp:753-768, called when
+  // substep_counter % reorder_interval == 0, src/mpm.cpp:811-813).  0 = never (the parity tests:
+  // storage index == caller index, so ties in the sort break exactly as in the scalar oracle).
+  int reorder_interval = 0;
+  int64_t step = 0;
+  std::vector<int32_t> origin;  // storage slot -> caller index
+  std::vector<float> sx, sv, sF, sb, smass, svol, sps, stmp;
+  std::vector<int32_t> sgroup, itmp;
+  std::vector<uint8_t> salive, atmp;
 };
 
 inline double now_s() {
@@ -645,7 +656,44 @@ inline size_t fast_node_index(const FastState &st, int i, int j, int k) {
   return b * 128 + (i & 3) * 32 + (j & 3) * 8 + (k & 7);
 }
 
-void fast_substep(FastState &st, const Scene<float> &sc, Particles<float> &P, std::vector<uint8_t> &alive) {
+// Gather `width` floats per particle through `perm` (parallel); dst/src must not alias.
+template <typename T>
+inline void permute_rows(const std::vector<int32_t> &perm, int width, const T *src, T *dst) {
+  const int64_t n = int64_t(perm.size());
+#pragma omp parallel for schedule(static)
+  for (int64_t j = 0; j < n; j++) {
+    const T *s = src + size_t(perm[j]) * width;
+    T *d = dst + size_t(j) * width;
+    for (int c = 0; c < width; c++) d[c] = s[c];
+  }
+}
+
+// sort_allocator (src/mpm.cpp:753-768): storage slot j receives the particle the sort put at rank j
+// (dead particles, which the reference has already dropped, go to the tail); afterwards order = iota.
+inline void fast_reorder_storage(FastState &st, std::vector<uint8_t> &alive) {
+  const int64_t n = int64_t(alive.size()), na = int64_t(st.order.size());
+  std::vector<int32_t> perm(n);
+  std::copy(st.order.begin(), st.order.end(), perm.begin());
+  int64_t k = na;
+  for (int64_t i = 0; i < n; i++)
+    if (!alive[i]) perm[k++] = int32_t(i);
+  st.stmp.resize(size_t(n) * 9);
+  auto rows = [&](std::vector<float> &a, int w) {
+    permute_rows(perm, w, a.data(), st.stmp.data());
+    std::memcpy(a.data(), st.stmp.data(), size_t(n) * w * sizeof(float));
+  };
+  rows(st.sx, 3); rows(st.sv, 3); rows(st.sF, 9); rows(st.sb, 9); rows(st.smass, 1); rows(st.svol, 1); rows(st.sps, 1);
+  st.itmp.resize(n);
+  permute_rows(perm, 1, st.sgroup.data(), st.itmp.data());
+  std::memcpy(st.sgroup.data(), st.itmp.data(), size_t(n) * sizeof(int32_t));  // in place: Particles views stay valid
+  permute_rows(perm, 1, st.origin.data(), st.itmp.data()); st.origin.swap(st.itmp);
+  st.atmp.resize(n);
+  permute_rows(perm, 1, alive.data(), st.atmp.data()); alive.swap(st.atmp);
+#pragma omp parallel for schedule(static)
+  for (int64_t j = 0; j < na; j++) st.order[j] = int32_t(j);
+}
+
+void fast_substep(FastState &st, const Scene<float> &sc, Particles<float> &P, std::vector<uint8_t> &alive, bool reorder_now = false) {
   using R = float;
   const int64_t n = P.n;
   double t0 = now_s();
@@ -716,6 +764,7 @@ void fast_substep(FastState &st, const Scene<float> &sc, Particles<float> &P, st
     }
     st.block_off.push_back(int32_t(n_alive));
   }
+  if (reorder_now) fast_reorder_storage(st, alive);
   // fat page map = 3x3x3 dilation, then memset (src/mpm.cpp:831-874)
   const size_t nblocks = size_t(st.nb[0]) * st.nb[1] * st.nb[2];
   if (st.fat.size() != nblocks) st.fat.assign(nblocks, 0);
@@ -780,17 +829,21 @@ void fast_substep(FastState &st, const Scene<float> &sc, Particles<float> &P, st
         for (int k = 0; k < 9; k++) affine[k] = std::fma(stress[k], S, P.b[9 * i + k] * bm);
         R mv[3] = {mass * v[0], mass * v[1], mass * v[2]};
         int li = base[0] - bx * 4, lj = base[1] - by * 4, lk = base[2] - bz * 8;
+        // 4-wide SSE/FMA, one __m128 = (x,y,z,mass) per node, as the reference's LOOP macro
+        // (src/transfer.cpp:526-547): affine_prod = fmadd(A2,d2, fmadd(A1,d1, fmadd(A0,d0, mass_v)));
+        // contrib = blend(mass, affine_prod); g += weight * contrib.  Same rounding as the scalar form.
+        const __m128 A0 = _mm_set_ps(0.f, at(affine, 2, 0), at(affine, 1, 0), at(affine, 0, 0));
+        const __m128 A1 = _mm_set_ps(0.f, at(affine, 2, 1), at(affine, 1, 1), at(affine, 0, 1));
+        const __m128 A2 = _mm_set_ps(0.f, at(affine, 2, 2), at(affine, 1, 2), at(affine, 0, 2));
+        const __m128 MV = _mm_set_ps(mass, mv[2], mv[1], mv[0]);
         for (int a = 0; a < 3; a++)
           for (int bb = 0; bb < 3; bb++)
             for (int c = 0; c < 3; c++) {
-              R d0 = rel[0] - R(a), d1 = rel[1] - R(bb), d2 = rel[2] - R(c);
-              R w = w27[a * 9 + bb * 3 + c];
+              const __m128 d0 = _mm_set1_ps(rel[0] - R(a)), d1 = _mm_set1_ps(rel[1] - R(bb)), d2 = _mm_set1_ps(rel[2] - R(c));
+              const __m128 w = _mm_set1_ps(w27[a * 9 + bb * 3 + c]);
               float *gn = tile[((li + a) * 6 + (lj + bb)) * 10 + (lk + c)];
-              for (int r = 0; r < 3; r++) {
-                R ap = std::fma(at(affine, r, 2), d2, std::fma(at(affine, r, 1), d1, std::fma(at(affine, r, 0), d0, mv[r])));
-                gn[r] += w * ap;
-              }
-              gn[3] += w * mass;
+              const __m128 contrib = _mm_fmadd_ps(A2, d2, _mm_fmadd_ps(A1, d1, _mm_fmadd_ps(A0, d0, MV)));
+              _mm_store_ps(gn, _mm_add_ps(_mm_load_ps(gn), _mm_mul_ps(w, contrib)));
             }
       }
       tile_io(b, tile, true);
@@ -844,19 +897,26 @@ void fast_substep(FastState &st, const Scene<float> &sc, Particles<float> &P, st
       R w27[27];
       mls_fast_kernel(rel, w27);
       int li = base[0] - bx * 4, lj = base[1] - by * 4, lk = base[2] - bz * 8;
-      R vacc[3] = {0, 0, 0}, bmat[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int a = 0; a < 3; a++)
-        for (int bb = 0; bb < 3; bb++)
-          for (int c = 0; c < 3; c++) {
-            R d[3] = {rel[0] - R(a), rel[1] - R(bb), rel[2] - R(c)};
-            R w = w27[a * 9 + bb * 3 + c];
-            const float *gn = tile[((li + a) * 6 + (lj + bb)) * 10 + (lk + c)];
-            for (int r = 0; r < 3; r++) {
-              vacc[r] = std::fma(gn[r], w, vacc[r]);
-              R wg = w * gn[r];
-              for (int cc = 0; cc < 3; cc++) at(bmat, r, cc) = std::fma(wg, d[cc], at(bmat, r, cc));
+      R vacc[3], bmat[9];
+      {
+        // 4-wide SSE/FMA as the reference's LOOP macro (src/transfer.cpp:884-904):
+        // v_ = fmadd(grid_vel, w, v_); w_grid_vel = w * grid_vel; b_[r] = fmadd(w_grid_vel, dpos[r], b_[r])
+        __m128 v4 = _mm_setzero_ps(), b0 = v4, b1 = v4, b2 = v4;
+        for (int a = 0; a < 3; a++)
+          for (int bb = 0; bb < 3; bb++)
+            for (int c = 0; c < 3; c++) {
+              const __m128 w = _mm_set1_ps(w27[a * 9 + bb * 3 + c]);
+              const __m128 g = _mm_load_ps(tile[((li + a) * 6 + (lj + bb)) * 10 + (lk + c)]);
+              v4 = _mm_fmadd_ps(g, w, v4);
+              const __m128 wg = _mm_mul_ps(w, g);
+              b0 = _mm_fmadd_ps(wg, _mm_set1_ps(rel[0] - R(a)), b0);
+              b1 = _mm_fmadd_ps(wg, _mm_set1_ps(rel[1] - R(bb)), b1);
+              b2 = _mm_fmadd_ps(wg, _mm_set1_ps(rel[2] - R(c)), b2);
             }
-          }
+        alignas(16) float tv[4], t0[4], t1[4], t2[4];
+        _mm_store_ps(tv, v4); _mm_store_ps(t0, b0); _mm_store_ps(t1, b1); _mm_store_ps(t2, b2);
+        for (int r = 0; r < 3; r++) { vacc[r] = tv[r]; at(bmat, r, 0) = t0[r]; at(bmat, r, 1) = t1[r]; at(bmat, r, 2) = t2[r]; }
+      }
       std::memcpy(P.b + 9 * i, bmat, sizeof(bmat));
       for (int d = 0; d < 3; d++) P.v[3 * i + d] = vacc[d];
       R cdg[9];
@@ -1078,20 +1138,68 @@ ORACLE_API int64_t oracle_fast_substeps(void *h, int nsub, const int *res, float
                                         const int32_t *group, uint8_t *alive_io, double *timings) {
   FastState &st = *static_cast<FastState *>(h);
   Scene<float> sc = make_scene<float>(res, dx, dt, gravity, particle_gravity, mat_kind, mat_params, sdf, friction);
-  Particles<float> P{n, x, v, F, b, mass, vol, ps, group};
-  std::vector<uint8_t> alive(alive_io, alive_io + n);
   st.t_sort = st.t_p2g = st.t_grid = st.t_g2p = 0;
+  double t_io = 0;
   int64_t updates = 0;
-  for (int s = 0; s < nsub; s++) {
+  auto count_alive = [&](const std::vector<uint8_t> &alive) {
     int64_t na = 0;
 #pragma omp parallel for reduction(+ : na) schedule(static)
     for (int64_t i = 0; i < n; i++) na += alive[i];
-    updates += na;
-    fast_substep(st, sc, P, alive);
+    return na;
+  };
+  if (st.reorder_interval <= 0) {
+    Particles<float> P{n, x, v, F, b, mass, vol, ps, group};
+    std::vector<uint8_t> alive(alive_io, alive_io + n);
+    for (int s = 0; s < nsub; s++) {
+      updates += count_alive(alive);
+      fast_substep(st, sc, P, alive);
+      st.step++;
+    }
+    std::memcpy(alive_io, alive.data(), n);
+  } else {
+    // the engine owns a re-orderable copy of the particle storage, as the reference's allocator pool;
+    // the caller's arrays keep their indexing (gather on entry, scatter on exit through `origin`).
+    const double tio0 = now_s();
+    if (int64_t(st.origin.size()) != n) {
+      st.origin.resize(n);
+      for (int64_t i = 0; i < n; i++) st.origin[i] = int32_t(i);
+    }
+    st.sx.resize(size_t(n) * 3); st.sv.resize(size_t(n) * 3); st.sF.resize(size_t(n) * 9); st.sb.resize(size_t(n) * 9);
+    st.smass.resize(n); st.svol.resize(n); st.sps.resize(n); st.sgroup.resize(n); st.salive.resize(n);
+    permute_rows(st.origin, 3, x, st.sx.data()); permute_rows(st.origin, 3, v, st.sv.data());
+    permute_rows(st.origin, 9, F, st.sF.data()); permute_rows(st.origin, 9, b, st.sb.data());
+    permute_rows(st.origin, 1, mass, st.smass.data()); permute_rows(st.origin, 1, vol, st.svol.data());
+    permute_rows(st.origin, 1, ps, st.sps.data()); permute_rows(st.origin, 1, group, st.sgroup.data());
+    permute_rows(st.origin, 1, alive_io, st.salive.data());
+    t_io += now_s() - tio0;
+    for (int s = 0; s < nsub; s++) {
+      updates += count_alive(st.salive);
+      Particles<float> P{n, st.sx.data(), st.sv.data(), st.sF.data(), st.sb.data(), st.smass.data(), st.svol.data(), st.sps.data(), st.sgroup.data()};
+      fast_substep(st, sc, P, st.salive, st.step % st.reorder_interval == 0);
+      st.step++;
+    }
+    const double tio1 = now_s();
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < n; j++) {
+      const size_t o = size_t(st.origin[j]);
+      for (int c = 0; c < 3; c++) { x[o * 3 + c] = st.sx[size_t(j) * 3 + c]; v[o * 3 + c] = st.sv[size_t(j) * 3 + c]; }
+      for (int c = 0; c < 9; c++) { F[o * 9 + c] = st.sF[size_t(j) * 9 + c]; b[o * 9 + c] = st.sb[size_t(j) * 9 + c]; }
+      ps[o] = st.sps[j];
+      alive_io[o] = st.salive[j];
+    }
+    t_io += now_s() - tio1;
   }
-  std::memcpy(alive_io, alive.data(), n);
-  if (timings) { timings[0] = st.t_sort; timings[1] = st.t_p2g; timings[2] = st.t_grid; timings[3] = st.t_g2p; }
+  // timings[4]: copying between the caller's arrays and the re-orderable storage (a cost of this
+  // harness, not of the reference's algorithm: its pool IS the storage)
+  if (timings) { timings[0] = st.t_sort; timings[1] = st.t_p2g; timings[2] = st.t_grid; timings[3] = st.t_g2p; timings[4] = t_io; }
   return updates;
+}
+// Re-order interval of the fast path's particle storage (reference default 1000, src/mpm.cpp:45); 0 = off.
+ORACLE_API void oracle_fast_set_reorder(void *h, int interval) {
+  FastState &st = *static_cast<FastState *>(h);
+  st.reorder_interval = interval;
+  st.step = 0;
+  st.origin.clear();
 }
 // Dense copy of the fast path's blocked grid (parity of fast vs scalar oracle).
 ORACLE_API void oracle_fast_download_grid(void *h, float *dense /* [(res+1)^3][4] */) {

@@ -150,10 +150,15 @@ def substep(scene, state, dtype=np.float64, want_grids=True):
 class FastOracle:
     """fp32 OpenMP restatement of the reference's optimized CPU path (the timed CPU baseline)."""
 
-    def __init__(self, scene, state, threads=None):
+    def __init__(self, scene, state, threads=None, reorder_interval=0):
+        """reorder_interval: physical re-ordering of the particle storage every that many substeps
+        (sort_allocator, src/mpm.cpp:753-768,811; the reference's default is 1000); 0 keeps storage
+        index == caller index, which the parity tests rely on for identical tie order."""
         self.scene = scene
         self.res = np.asarray(scene["res"], np.int32)
         self.h = C.c_void_p(lib().oracle_fast_create(_p(self.res)))
+        if reorder_interval:
+            lib().oracle_fast_set_reorder(self.h, C.c_int(int(reorder_interval)))
         if threads:
             lib().oracle_fast_set_threads(C.c_int(threads))
         self.threads = lib().oracle_fast_num_threads()
@@ -168,8 +173,8 @@ class FastOracle:
         self.g = np.ascontiguousarray(scene["gravity"], f32)
 
     def substeps(self, nsub):
-        """Returns (particle_updates, timings[sort,p2g,grid,g2p] seconds)."""
-        t = np.zeros(4, np.float64)
+        """Returns (particle_updates, timings[sort,p2g,grid,g2p,harness_io] seconds)."""
+        t = np.zeros(5, np.float64)
         st = self.st
         sc = self.scene
         upd = lib().oracle_fast_substeps(

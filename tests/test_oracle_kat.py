@@ -12,6 +12,7 @@ import pytest
 
 from oracle import pyoracle as O
 from taichi_mpm_b200 import scenes
+from tests import common as T
 
 
 # ------------------------------------------------------------------ (1) reference tests restated
@@ -234,6 +235,26 @@ def test_fast_path_matches_scalar_oracle():
             scale = max(np.abs(ref[k]).max(), 1e-30)
             assert np.abs(fast.st[k] - ref[k]).max() <= 5e-5 * scale, (kind, k)
         assert np.array_equal(fast.st["alive"], ref["alive"])
+
+
+def test_fast_path_storage_reorder_keeps_caller_indexing():
+    # sort_allocator (src/mpm.cpp:753-768): physically re-ordered storage changes neither the
+    # caller-visible indexing nor (beyond fp32 summation order) the result; deleted particles stay deleted
+    scene, st = T.perturbed_scene(scenes.MAT_SAND, res=32, cells=8, seed=3)
+    res = scene["res"][0]
+    st["x"][5] = [6.5 / res, 0.5, 0.5]        # inside the deletion band
+    a = O.FastOracle(scene, st, threads=2)
+    b = O.FastOracle(scene, st, threads=2, reorder_interval=5)
+    na = nb = 0
+    for _ in range(3):                         # several calls: gather/scatter through `origin` each time
+        na += a.substeps(7)[0]
+        nb += b.substeps(7)[0]
+    assert na == nb
+    assert np.array_equal(a.st["alive"], b.st["alive"]) and a.st["alive"][5] == 0
+    live = a.st["alive"] > 0
+    for k in ("x", "v", "F", "b", "ps"):
+        scale = max(np.abs(a.st[k][live]).max(), 1e-30)
+        assert np.abs(a.st[k][live] - b.st[k][live]).max() <= 2e-5 * scale, k
 
 
 def test_clear_boundary_band():
