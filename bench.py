@@ -134,10 +134,12 @@ def best_thread_count(sc, probe):
     best, best_rate = cand[-1], 0.0
     for t in cand:
         f = O.FastOracle(sc, probe, threads=t, reorder_interval=REORDER_INTERVAL)
-        f.substeps(1)
-        t0 = time.perf_counter()
-        upd, tm = f.substeps(2)
-        rate = upd / (time.perf_counter() - t0 - tm[4])
+        f.substeps(2)  # team start-up, first touch and the storage re-order are not part of the rate
+        rate = 0.0
+        for _ in range(3):  # best of three short runs: the probe must not be decided by one hiccup
+            t0 = time.perf_counter()
+            upd, tm = f.substeps(2)
+            rate = max(rate, upd / (time.perf_counter() - t0 - tm[4]))
         del f
         if rate > best_rate:
             best, best_rate = t, rate
@@ -492,7 +494,10 @@ def emit(line):
 
 def main():
     os.environ.setdefault("NCCL_DEBUG", "WARN")
-    os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # idle OpenMP workers must not spin on a shared box
+    # OpenMP workers of the CPU arms: spin briefly between the (many, short) parallel regions, then
+    # sleep.  Unbounded spinning collapsed oversubscribed teams on a shared box (200x), a purely passive
+    # wait made the colour loops wake-up bound here (5x); measured with /tmp probes, see profiles/README.md
+    os.environ.setdefault("GOMP_SPINCOUNT", "20000")
     _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
