@@ -366,9 +366,26 @@ __device__ __forceinline__ float sym_norm2(const Sym3 &A) {
 __device__ __forceinline__ int warp_max_active(int v) { return __reduce_max_sync(__activemask(), v); }
 
 // L = log(I + E) for a small symmetric E by the Mercator series in Horner form,
-//   L = E (I - E (I/2 - E (I/3 - ...))),  n terms; n is chosen from |E| so that the truncation,
-// relative to |L| ~ |E|, |E|^(n-1)/(n+1) <= 1e-7, and is the same for the whole warp.
-// Caller guarantees |E|_F <= 0.15.
+//   L = E (I - E (I/2 - E (I/3 - ...))),  N terms, fully unrolled with immediate coefficients.
+// The innermost product E (I/N) is written as the scaling it is.
+template <int N>
+__device__ __forceinline__ Sym3 sym_log1p_horner(const Sym3 &E) {
+  float c = 1.0f / (float)N;
+  Sym3 T = {c * E.xx, c * E.yy, c * E.zz, c * E.xy, c * E.xz, c * E.yz};
+  Sym3 S;
+#pragma unroll
+  for (int k = N - 1; k >= 1; k--) {
+    c = 1.0f / (float)k;
+    S.xx = c - T.xx; S.yy = c - T.yy; S.zz = c - T.zz;
+    S.xy = -T.xy; S.xz = -T.xz; S.yz = -T.yz;
+    T = sym_mul_sym(E, S);
+  }
+  return T;
+}
+
+// n is chosen from |E| so that the truncation, relative to |L| ~ |E|, |E|^(n-1)/(n+1) <= 1e-7, and
+// is the same for the whole warp (one uniform branch, no divergence).  Caller guarantees
+// |E|_F <= 0.15.
 __device__ __forceinline__ Sym3 sym_log1p_series(const Sym3 &E, float nrm2) {
   int n = 3;
   if (nrm2 > 4.0e-7f) n = 4;    // |E| > 6.3e-4
@@ -377,32 +394,44 @@ __device__ __forceinline__ Sym3 sym_log1p_series(const Sym3 &E, float nrm2) {
   if (nrm2 > 3.5e-3f) n = 7;    // |E| > 5.9e-2
   if (nrm2 > 9.2e-3f) n = 9;    // |E| > 9.6e-2 (up to 0.15)
   n = warp_max_active(n);
-  float c = 1.0f / (float)n;
-  Sym3 S = {c, c, c, 0.f, 0.f, 0.f};
-  for (int k = n - 1; k >= 1; k--) {
-    Sym3 T = sym_mul_sym(E, S);
-    c = 1.0f / (float)k;
-    S.xx = c - T.xx; S.yy = c - T.yy; S.zz = c - T.zz;
-    S.xy = -T.xy; S.xz = -T.xz; S.yz = -T.yz;
+  switch (n) {
+    case 3: return sym_log1p_horner<3>(E);
+    case 4: return sym_log1p_horner<4>(E);
+    case 5: return sym_log1p_horner<5>(E);
+    case 6: return sym_log1p_horner<6>(E);
+    case 7: return sym_log1p_horner<7>(E);
+    default: return sym_log1p_horner<9>(E);
   }
-  return sym_mul_sym(E, S);
 }
 
-// exp(X) for a small symmetric X: I + X (I + X/2 (I + X/3 (...))); truncation relative to |X|,
-// |X|^n/(n+1)! <= 1e-7; warp-uniform term count.  Caller guarantees |X|_F <= 0.28.
+// exp(X) for a small symmetric X: I + X (I + X/2 (I + X/3 (...))), N terms unrolled; the innermost
+// factor (I + X/N) is formed directly.
+template <int N>
+__device__ __forceinline__ Sym3 sym_exp_horner(const Sym3 &X) {
+  float c = 1.0f / (float)N;
+  Sym3 S = {fmaf(c, X.xx, 1.f), fmaf(c, X.yy, 1.f), fmaf(c, X.zz, 1.f), c * X.xy, c * X.xz, c * X.yz};
+#pragma unroll
+  for (int k = N - 1; k >= 1; k--) {
+    const Sym3 T = sym_mul_sym(X, S);
+    c = 1.0f / (float)k;
+    S.xx = fmaf(c, T.xx, 1.f); S.yy = fmaf(c, T.yy, 1.f); S.zz = fmaf(c, T.zz, 1.f);
+    S.xy = c * T.xy; S.xz = c * T.xz; S.yz = c * T.yz;
+  }
+  return S;
+}
+
+// truncation relative to |X|, |X|^n/(n+1)! <= 1e-7; warp-uniform term count.  Caller guarantees
+// |X|_F <= 0.28.
 __device__ __forceinline__ Sym3 sym_exp_series(const Sym3 &X, float nrm2) {
   int n = 3;
   if (nrm2 > 1.7e-4f) n = 4;    // |X| > 1.3e-2
   if (nrm2 > 3.5e-3f) n = 6;    // |X| > 5.9e-2 (up to 0.28)
   n = warp_max_active(n);
-  Sym3 S = {1.f, 1.f, 1.f, 0.f, 0.f, 0.f};
-  for (int k = n; k >= 1; k--) {
-    Sym3 T = sym_mul_sym(X, S);
-    const float c = 1.0f / (float)k;
-    S.xx = fmaf(c, T.xx, 1.f); S.yy = fmaf(c, T.yy, 1.f); S.zz = fmaf(c, T.zz, 1.f);
-    S.xy = c * T.xy; S.xz = c * T.xz; S.yz = c * T.yz;
+  switch (n) {
+    case 3: return sym_exp_horner<3>(X);
+    case 4: return sym_exp_horner<4>(X);
+    default: return sym_exp_horner<6>(X);
   }
-  return S;
 }
 
 // Drucker-Prager sand WITHOUT any matrix decomposition (valid while |F F^T - I| <= 0.15; returns
@@ -429,12 +458,15 @@ __device__ __forceinline__ bool sand_step_series(const Material &mat, const Mat3
   const float sh = (trL + ps) * (1.f / 3.f);
   const Sym3 H = {L.xx - sh, L.yy - sh, L.zz - sh, L.xy, L.xz, L.yz};  // Hat = dev(L) - (ps/3) I
   const float hn2 = sym_norm2(H);
-  const float hn = sqrtf(hn2);
-  const float dg = hn + (3.f * la + 2.f * mu) / (2.f * mu) * tr * alpha;
+  // |Hat| and 1/|Hat| from one MUFU.RSQ (2 ulp; the clamp keeps rsqrt finite, and |Hat| = 0 then
+  // gives dg <= 0 whenever tr < 0, i.e. no projection, so 1/|Hat| is never used at the clamp)
+  const float rhn = rsqrt_fast(fmaxf(hn2, 1e-36f));
+  const float hn = hn2 * rhn;
+  const float dg = fmaf(fmaf(1.5f, __fdividef(la, mu), 1.f) * alpha, tr, hn);  // hn + (3la+2mu)/(2mu) tr alpha
   const bool expand = tr >= 0.f;
   const bool project = !expand && dg > 0.f;
   // X = -L (expansion), -k Hat (projection), 0 (elastic)
-  const float kf = expand ? 1.f : (project ? dg / hn : 0.f);
+  const float kf = expand ? 1.f : (project ? dg * rhn : 0.f);
   const Sym3 B = expand ? L : H;
   const Sym3 X = {-kf * B.xx, -kf * B.yy, -kf * B.zz, -kf * B.xy, -kf * B.xz, -kf * B.yz};
   const float nX2 = sym_norm2(X);

@@ -17,6 +17,7 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 // (glibc already declares __expf/__logf as internal names, hence macros)
 #define __expf(x) expf(x)
 #define __logf(x) logf(x)
+#define __fdividef(a, b) ((a) / (b))
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline unsigned __activemask() { return 1u; }
 static inline int __any_sync(unsigned, int p) { return p; }
