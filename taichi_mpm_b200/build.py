@@ -35,12 +35,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    """Compile libmpmb.so for sm_100a if it is missing or stale.  Returns the path."""
-    if not force and not needs_build():
-        return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SRC
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile libmpmb.so for sm_100a if it is missing or stale.  Returns the path.
+
+    `defines` / `out` build an A/B variant next to the product (e.g. defines=["MPMB_EXP_TILE_XYZ"],
+    out=".../lib/libmpmb_tile_xyz.so"; load it with MPMB_LIB=<path>); the default library is only
+    ever built without defines."""
+    lib = out or LIB
+    if not force and not defines and not needs_build():
+        return lib
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + SRC
     env = dict(os.environ)
     # this image exports CC/CXX pointing at a wrapper without OpenMP specs; nvcc should use the system g++
     env.pop("CC", None)
@@ -48,11 +53,17 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
-        raise RuntimeError("nvcc failed building libmpmb.so")
+        raise RuntimeError("nvcc failed building " + os.path.basename(lib))
     if verbose:
         sys.stderr.write(r.stdout)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m taichi_mpm_b200.build [--force] [-v] [--define NAME ... --out PATH]
+    argv = sys.argv[1:]
+    defs = [argv[i + 1] for i, a in enumerate(argv) if a == "--define" and i + 1 < len(argv)]
+    outp = next((argv[i + 1] for i, a in enumerate(argv) if a == "--out" and i + 1 < len(argv)), None)
+    if defs and not outp:
+        outp = os.path.join(_PKG, "lib", "libmpmb_" + "_".join(d.lower().replace("mpmb_exp_", "") for d in defs) + ".so")
+    print(build(force="--force" in argv or bool(defs), verbose="-v" in argv, defines=defs, out=outp))

@@ -62,7 +62,9 @@ _LIB = None
 
 
 def lib_path():
-    return _build.LIB
+    """The product library, or the A/B variant named by MPMB_LIB (a build of the same source with
+    experiment defines, `python -m taichi_mpm_b200.build --define ...`; kernel tuning only)."""
+    return os.environ.get("MPMB_LIB") or _build.LIB
 
 
 def lib():
@@ -70,6 +72,8 @@ def lib():
     global _LIB
     if _LIB is None:
         path = _build.build()
+        if os.environ.get("MPMB_LIB"):
+            path = os.environ["MPMB_LIB"]
         if not os.path.exists(path):
             raise RuntimeError("libmpmb.so is missing: the CUDA engine has not been built (python -m taichi_mpm_b200.build)")
         L = C.CDLL(path)

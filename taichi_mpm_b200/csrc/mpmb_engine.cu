@@ -73,6 +73,13 @@ enum { DEVERR_TILE_CAPACITY = 1, DEVERR_MIGRATE_CAPACITY = 2, DEVERR_PARTICLE_CA
 struct TileMeta {  // one 32-byte record per active tile (slot)
   int tile, run_begin, run_len, arr_off, arr_len, out_begin, pad0, pad1;
 };
+// Build-time experiments (off by default; A/B them on a GPU with `build.py --define NAME`):
+//   MPMB_EXP_TILE_XYZ    k_order_c decodes tile -> (x,y,z) once per tile into TileMeta::pad0/pad1
+//                        (x | y<<16, z); the tile kernels then skip two runtime integer divisions per
+//                        CTA per tile/chunk (42 instr/particle in k_g2p, 4.9 % of k_p2g's stall samples).
+//   MPMB_EXP_DUAL_ARENA  k_p2g: one shared arena per warp, both warps flush their registers at the
+//                        same time and the store sums the two (the warp-after-warp flush holds 11.9 %
+//                        of k_p2g's stall samples).
 
 struct View {  // raw pointers handed to kernels
   float4 *q[N_Q];        // current (read) buffer
@@ -350,7 +357,14 @@ __global__ void __launch_bounds__(1024) k_order_b(View V, int nblocks) {
   }
 }
 
+#ifdef MPMB_EXP_TILE_XYZ
+#define MPMB_TILE_XYZ(P, tm, tx, ty, tz) const int tx = (tm).pad0 & 0xffff, ty = (tm).pad0 >> 16, tz = (tm).pad1
+__global__ void __launch_bounds__(ORD_B) k_order_c(View V, int ntot, int nt1, int nt2) {
+#else
+#define MPMB_TILE_XYZ(P, tm, tx, ty, tz) \
+  const int tz = (tm).tile % (P).nt[2], ty = ((tm).tile / (P).nt[2]) % (P).nt[1], tx = (tm).tile / ((P).nt[2] * (P).nt[1])
 __global__ void __launch_bounds__(ORD_B) k_order_c(View V, int ntot) {
+#endif
   typedef cub::BlockScan<int, ORD_B> Scan;
   __shared__ typename Scan::TempStorage tmp;
   int tot[ORD_IPT], arr[ORD_IPT], act[ORD_IPT];
@@ -389,7 +403,11 @@ __global__ void __launch_bounds__(ORD_B) k_order_c(View V, int ntot) {
         slot = e_act;
         TileMeta m;
         m.tile = t; m.run_begin = V.run_begin[t]; m.run_len = V.run_len[t]; m.arr_off = e_arr; m.arr_len = arr[k]; m.out_begin = e_tot;
+#ifdef MPMB_EXP_TILE_XYZ
+        m.pad0 = (t / (nt2 * nt1)) | (((t / nt2) % nt1) << 16); m.pad1 = t % nt2;
+#else
         m.pad0 = 0; m.pad1 = 0;
+#endif
         V.meta[slot] = m;
       }
       V.slot_map[t] = slot;
@@ -464,7 +482,7 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
     const int tile = tm.tile;
     if (!tile_in_part(P, tile, part)) continue;  // uniform per CTA
     const int nrow_tile = tm.run_len + tm.arr_len;
-    const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
+    MPMB_TILE_XYZ(P, tm, tx, ty, tz);
     const float fbx = (float)(tx * 4 + cx), fby = (float)(ty * 4 + cy), fbz = (float)(tz * 4 + cz);
     float acc[27][4];
 #pragma unroll
@@ -614,6 +632,35 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
       vbase += s_start[64];
       __syncthreads();  // rows / order / hist are reused by the next chunk
     }
+#ifdef MPMB_EXP_DUAL_ARENA
+    // ---- 4: both warps flush at once, warp 0 into s_arena, warp 1 into a second arena laid over the
+    // row staging area (free after the last chunk's barrier; zeroed by warp 1 itself, so a __syncwarp
+    // is all it needs).  The store below sums the two in a fixed order: still bit-reproducible.
+    float (*ar1)[AR_SIZE] = reinterpret_cast<float (*)[AR_SIZE]>(&s_rows[0][0]);
+    {
+      if (warp == 1) {
+        for (int n = lane; n < 4 * AR_SIZE; n += 32) (&ar1[0][0])[n] = 0.f;
+        __syncwarp();
+      }
+      float (*ar)[AR_SIZE] = warp == 0 ? s_arena : ar1;
+      const int nb = cx * AR_SX + cy * AR_SY + cz;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const int node = nb + i * AR_SX + j * AR_SY + k;
+            const float *a = acc[i * 9 + j * 3 + k];
+            ar[0][node] += a[0];
+            ar[1][node] += a[1];
+            ar[2][node] += a[2];
+            ar[3][node] += a[3];
+            __syncwarp();
+          }
+    }
+    __syncthreads();
+#else
     // ---- 4: flush registers to the shared arena, one warp at a time (deterministic order)
 #pragma unroll 1
     for (int wsel = 0; wsel < 2; wsel++) {
@@ -638,11 +685,17 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
       }
       __syncthreads();
     }
+#endif
     float4 *out = V.arena + (size_t)slot * ARENA;
     for (int n = tid; n < ARENA; n += P2G_T) {
       const int a = n / 36, b = (n / 6) % 6, c = n % 6;
       const int node = a * AR_SX + b * AR_SY + c;
+#ifdef MPMB_EXP_DUAL_ARENA
+      out[n] = make_float4(s_arena[0][node] + ar1[0][node], s_arena[1][node] + ar1[1][node], s_arena[2][node] + ar1[2][node],
+                           s_arena[3][node] + ar1[3][node]);
+#else
       out[n] = make_float4(s_arena[0][node], s_arena[1][node], s_arena[2][node], s_arena[3][node]);
+#endif
     }
     __syncthreads();
   }
@@ -705,9 +758,14 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int n_tiles = V.cnt->n_tiles;
   for (int slot = gw; slot < n_tiles; slot += nw) {
-    const int tile = V.meta[slot].tile;
+#ifdef MPMB_EXP_TILE_XYZ
+    const TileMeta tmg = V.meta[slot];
+#else
+    struct { int tile; } tmg = {V.meta[slot].tile};
+#endif
+    const int tile = tmg.tile;
     if (!tile_in_part(P, tile, part)) continue;  // uniform per warp
-    const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
+    MPMB_TILE_XYZ(P, tmg, tx, ty, tz);
     int my_nb = -1;
     if (lane < 27) {
       int ox = lane / 9 - 1, oy = (lane / 3) % 3 - 1, oz = lane % 3 - 1;
@@ -763,7 +821,12 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
       while (slot < n_tiles && !tile_in_part(P, V.meta[slot].tile, part)) slot += (int)gridDim.x;
     it.slot = slot;
     if (slot < n_tiles) it.tm = V.meta[slot];
-    else { it.tm.run_len = 0; it.tm.arr_len = 0; it.tm.tile = 0; it.tm.run_begin = 0; it.tm.arr_off = 0; it.tm.out_begin = 0; }
+    else {
+      it.tm.run_len = 0; it.tm.arr_len = 0; it.tm.tile = 0; it.tm.run_begin = 0; it.tm.arr_off = 0; it.tm.out_begin = 0;
+#ifdef MPMB_EXP_TILE_XYZ
+      it.tm.pad0 = 0; it.tm.pad1 = 0;
+#endif
+    }
     return it;
   };
   auto next_item = [&](const Item &it) {
@@ -819,7 +882,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
     __syncthreads();
     {
       const int tile = cur.tm.tile;
-      const int tz = tile % P.nt[2], ty = (tile / P.nt[2]) % P.nt[1], tx = tile / (P.nt[2] * P.nt[1]);
+      MPMB_TILE_XYZ(P, cur.tm, tx, ty, tz);
       const int nrows = min(G2P_CH, cur.tm.run_len + cur.tm.arr_len - cur.rb);
       const float4 *sv = s_vel[vbuf];
       int my_stay = 0;
@@ -1687,7 +1750,11 @@ int mpmb_sort_particles_and_populate_grid(MpmbHandle h) {
     if (!h->fresh) { k_mover_count<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot); nl++; }
     k_order_a<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot);
     k_order_b<<<1, 1024, 0, h->stream>>>(V, h->ord_blocks);
+#ifdef MPMB_EXP_TILE_XYZ
+    k_order_c<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot, h->P.nt[1], h->P.nt[2]);
+#else
     k_order_c<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot);
+#endif
     if (!h->fresh) {
       k_mover_place<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot);
       k_mover_rank<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot);
