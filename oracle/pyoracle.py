@@ -210,3 +210,39 @@ def mpm88_advance(n, dt, x, v, F, C_, Jp, E=1e4, nu=0.2, hardening=10.0, gravity
         C.c_int(n), sc(dt), sc(E), sc(nu), sc(hardening), sc(gravity_y), C.c_int(int(plastic)), C.c_int64(len(Jp)),
         _p(x), _p(v), _p(F), _p(C_), _p(Jp), _p(grid))
     return x, v, F, C_, Jp, grid
+
+
+# ---- the reference's own frame writer (vendored Partio compiled from /root/reference, `make ref`)
+_PARTIO = None
+
+
+def partio_ref_available():
+    """True when oracle/_ref/libpartio_ref.so exists or can be built (the reference tree is present)."""
+    so = os.path.join(_HERE, "_ref", "libpartio_ref.so")
+    return os.path.exists(so) or os.path.isdir("/root/reference/external/partio/src")
+
+
+def partio_ref():
+    global _PARTIO
+    if _PARTIO is None:
+        so = os.path.join(_HERE, "_ref", "libpartio_ref.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        _PARTIO = C.CDLL(so)
+    return _PARTIO
+
+
+def ref_write_partio(path, pos, v, type_, index, limit, verbose=None):
+    """MPM<dim>::write_partio (src/visualize.cpp:16-100) through the reference's Partio.
+    verbose: None or dict(m, boundary_normal, debug, states, boundary_distance, near_boundary, apic_frobenius_norm)."""
+    f32, i32 = np.float32, np.int32
+    pos = np.ascontiguousarray(pos, f32); v = np.ascontiguousarray(v, f32)
+    type_ = np.ascontiguousarray(type_, i32); index = np.ascontiguousarray(index, i32); limit = np.ascontiguousarray(limit, i32)
+    extra = [None] * 7
+    if verbose is not None:
+        extra = [np.ascontiguousarray(verbose["m"], f32), np.ascontiguousarray(verbose["boundary_normal"], f32),
+                 np.ascontiguousarray(verbose["debug"], f32), np.ascontiguousarray(verbose["states"], i32),
+                 np.ascontiguousarray(verbose["boundary_distance"], f32), np.ascontiguousarray(verbose["near_boundary"], i32),
+                 np.ascontiguousarray(verbose["apic_frobenius_norm"], f32)]
+    partio_ref().ref_write_partio(str(path).encode(), C.c_int64(len(pos)), _p(pos), _p(v), _p(type_), _p(index), _p(limit),
+                                  C.c_int(0 if verbose is None else 1), *[None if e is None else _p(e) for e in extra])

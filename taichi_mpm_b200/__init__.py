@@ -1,7 +1,7 @@
 """B200-native MLS-MPM substep engine: drop-in for the P2G / grid update / G2P + constitutive hot
 path of yuanming-hu/taichi_mpm behind a C-ABI (include/mpmb.h).  See DESIGN.md."""
-from . import capi, scenes  # noqa: F401
+from . import bgeo, capi, scenes  # noqa: F401
 from .capi import Engine, MpmbError  # noqa: F401
 from .mpm import MPM, LevelSet  # noqa: F401
 
-__all__ = ["capi", "scenes", "Engine", "MpmbError", "MPM", "LevelSet"]
+__all__ = ["bgeo", "capi", "scenes", "Engine", "MpmbError", "MPM", "LevelSet"]

@@ -8,15 +8,37 @@ reference tree by scripts/async/async_mpm.py:17-300) and the `MPM<3>` plugin beh
     ls = mpm.create_levelset(); ls.add_plane((0,1,0), -0.1); ls.set_friction(0.4); mpm.set_levelset(ls)
     mpm.add_particles(type='sand', benchmark_block=(lo, hi), density=400)
     mpm.step(frame_dt)            # runs substeps on the GPU engine through the C-ABI
-    p = mpm.get_particles()       # what visualize() would dump (src/visualize.cpp:16-100)
+    mpm.visualize()               # frame_directory/0001.bgeo, the reference's bytes (src/visualize.cpp:16-100)
+    mpm.general_action(action='save', file_name='snap.npz')   # and action='load'
+    p = mpm.get_particles()       # the same data as numpy arrays
 
 Everything numerical happens in libmpmb.so (capi.Engine); this file is glue: kwargs -> MpmbConfig,
 registered particle type names -> material groups, level-set planes -> the engine's dense SDF.
 Only the fast path of the reference is mirrored (optimized=True, no rigid bodies, static level set).
 """
+import os
+
 import numpy as np
 
-from . import capi, scenes
+from . import bgeo, capi, scenes
+
+# MPMParticle::get_debug_info().y per registered type (src/particles.cpp:288-290,347-349,422-424,
+# 496-498,669-671); water also reports (j, 5, sticky)
+_DEBUG_CODE = {scenes.MAT_SNOW: 2.0, scenes.MAT_LINEAR: 3.0, scenes.MAT_JELLY: 4.0, scenes.MAT_WATER: 5.0, scenes.MAT_SAND: 6.0}
+
+
+def frame_attributes(p, group_kinds, verbose=False):
+    """Point attributes of one frame dump from a `download()` dict sorted by id — pure host code, so
+    the file layer is testable without a GPU.  group_kinds[g] = material kind of group g."""
+    debug = None
+    if verbose:
+        kinds = np.asarray(group_kinds, np.int64)[np.asarray(p["group"], np.int64)] if len(p["group"]) else np.zeros(0, np.int64)
+        debug = np.zeros((len(kinds), 3), np.float32)
+        for k, code in _DEBUG_CODE.items():
+            debug[kinds == k, 1] = code
+        water = kinds == scenes.MAT_WATER
+        debug[water, 0] = np.asarray(p["ps"], np.float32)[water]
+    return bgeo.reference_attributes(p, verbose=verbose, debug_code=debug)
 
 
 class LevelSet:
@@ -78,6 +100,9 @@ class MPM:
         self.update_counter = 0   # "Times of particle updating" (mpm.cpp:436,449)
         self.substep_counter = 0
         self._groups = []         # (kind, params) per material group
+        self.frame_directory = kwargs.get("frame_directory")                    # async_mpm.py:49, mpm.h:335
+        self.verbose_bgeo = bool(kwargs.get("verbose_bgeo", False))             # visualize.cpp:22
+        self.frame_count = 0                                                    # mpm.h:105
         self._host = None         # pending host-side particle set (dict of arrays)
         self._dirty = False
         self._n_uploaded = 0
@@ -197,3 +222,67 @@ class MPM:
     def num_particles(self):
         self._push()
         return self.engine.num_particles()
+
+    # ---- frame output and snapshots
+    def visualize(self):
+        """MPM<3>::visualize -> write_bgeo (src/visualize.cpp:156-159, src/mpm.h:333-343): the frame
+        counter is incremented first, the file is `<frame_directory>/<count:04>.bgeo`, particles in
+        id order with the attributes of write_partio.  Returns the file name."""
+        if not self.frame_directory:
+            raise ValueError("frame_directory was not given to MPM(...)")
+        self.frame_count += 1
+        os.makedirs(self.frame_directory, exist_ok=True)
+        fn = os.path.join(self.frame_directory, "%04d.bgeo" % self.frame_count)
+        p = self.get_particles()
+        bgeo.write_bgeo(fn, p["x"], frame_attributes(p, [k for k, _ in self._groups], self.verbose_bgeo))
+        return fn
+
+    def general_action(self, **kwargs):
+        """The actions of MPM<dim>::general_action (src/mpm.cpp:920-976) that concern the accelerated
+        state: 'save' / 'load' of a snapshot (the reference serialises itself with the taichi core's
+        binary format, which is not available here — this is a numpy .npz of the same state:
+        particles, material groups, clocks and counters; level sets are re-attached by the scene
+        script, as scripted rigid motion is in the reference, mpm.cpp:943-958)."""
+        action = kwargs["action"]
+        if action == "save":
+            p = self.get_particles()
+            kinds = np.array([k for k, _ in self._groups], np.int32)
+            params = np.stack([q for _, q in self._groups]).astype(np.float32) if self._groups else np.zeros((0, scenes.N_MAT_PARAMS), np.float32)
+            with open(kwargs["file_name"], "wb") as f:
+                np.savez(f, format=np.array("mpmb-snapshot-1"), res=np.array(self.res), delta_x=self.delta_x, base_delta_t=self.base_delta_t,
+                         gravity=np.array(self.gravity), current_t=self.current_t, request_t=self.request_t,
+                         counters=np.array([self.update_counter, self.substep_counter, self.frame_count], np.int64),
+                         mat_kind=kinds, mat_params=params, **{"p_" + k: v for k, v in p.items()})
+            return ""
+        if action == "load":
+            with np.load(kwargs["file_name"]) as z:
+                if str(z["format"]) != "mpmb-snapshot-1":
+                    raise ValueError("not an mpmb snapshot")
+                if tuple(int(r) for r in z["res"]) != self.res or abs(float(z["delta_x"]) - self.delta_x) > 0:
+                    raise ValueError("snapshot grid %s does not match this solver %s" % (tuple(z["res"]), self.res))
+                self._groups = []
+                for g, (k, q) in enumerate(zip(z["mat_kind"], z["mat_params"])):
+                    self._groups.append((int(k), np.asarray(q, np.float32)))
+                    self.engine.set_material(g, int(k), self._groups[-1][1])
+                self.current_t, self.request_t = float(z["current_t"]), float(z["request_t"])
+                self.update_counter, self.substep_counter, self.frame_count = (int(c) for c in z["counters"])
+                self._host = {k: np.ascontiguousarray(z["p_" + k]) for k in ("x", "v", "F", "b", "mass", "vol", "ps", "group")}
+                ids = np.ascontiguousarray(z["p_id"])
+            # ids are positions in the upload: keep the snapshot's ids by uploading in id order with the base id
+            self._dirty = True
+            self._push_with_ids(ids)
+            return ""
+        raise ValueError("Unknown action: %s" % action)  # TC_ERROR("Unknown action") mpm.cpp:974
+
+    def _push_with_ids(self, ids):
+        """Upload after 'load': the engine numbers particles id_base + position, so a snapshot whose
+        ids are not 0..n-1 (deleted particles) keeps them only if they are contiguous; otherwise the
+        particles are renumbered 0..n-1 in id order (the reference reloads its own ids)."""
+        h = self._host
+        order = np.argsort(ids, kind="stable")
+        h = {k: v[order] for k, v in h.items()}
+        ids = ids[order]
+        base = int(ids[0]) if len(ids) and np.array_equal(ids - ids[0], np.arange(len(ids), dtype=ids.dtype)) else 0
+        self.engine.set_id_base(base)
+        self._host = h
+        self._push()

@@ -1,0 +1,140 @@
+"""Host logic of the frame output / snapshot verbs of the mirror (MPM.visualize, general_action
+save/load) with the device engine replaced by an in-memory stand-in — no GPU, no arithmetic: what is
+checked is the glue (file names and counters as src/mpm.h:333-343, id order, material groups and
+clocks surviving a snapshot, unknown actions rejected as src/mpm.cpp:974)."""
+import numpy as np
+import pytest
+
+from taichi_mpm_b200 import bgeo, capi, mpm as mpm_mod
+
+
+class FakeEngine:
+    """Stores what is uploaded; substep() only advects x by v*dt*n so that state visibly changes."""
+
+    def __init__(self, res, dx, dt, gravity, particle_gravity, clean_boundary, device=0, capacity=0):
+        self.res, self.dt = tuple(res), dt
+        self.mats, self.id_base, self.p = {}, 0, None
+
+    def set_material(self, g, kind, params):
+        self.mats[g] = (kind, np.array(params, np.float32))
+
+    def set_sdf(self, *a):
+        pass
+
+    def set_planes(self, *a):
+        pass
+
+    def set_id_base(self, base):
+        self.id_base = int(base)
+
+    def upload(self, x, v, mass, vol, F, b, ps, group):
+        n = len(x)
+        self.p = dict(id=(self.id_base + np.arange(n)).astype(np.uint32), x=np.array(x, np.float32), v=np.array(v, np.float32),
+                      F=np.array(F, np.float32).reshape(n, 9), b=np.array(b, np.float32).reshape(n, 9), mass=np.array(mass, np.float32),
+                      vol=np.array(vol, np.float32), ps=np.array(ps, np.float32), group=np.array(group, np.int32))
+
+    def num_particles(self):
+        return 0 if self.p is None else len(self.p["x"])
+
+    def download(self):
+        if self.p is None:
+            return dict(id=np.zeros(0, np.uint32), x=np.zeros((0, 3), np.float32), v=np.zeros((0, 3), np.float32), F=np.zeros((0, 9), np.float32),
+                        b=np.zeros((0, 9), np.float32), mass=np.zeros(0, np.float32), vol=np.zeros(0, np.float32), ps=np.zeros(0, np.float32),
+                        group=np.zeros(0, np.int32))
+        rng = np.random.default_rng(0)
+        o = rng.permutation(len(self.p["x"]))          # device order is arbitrary; download() sorts by id
+        d = {k: a[o] for k, a in self.p.items()}
+        s = np.argsort(d["id"], kind="stable")
+        return {k: a[s].copy() for k, a in d.items()}
+
+    def substep(self, n):
+        self.p["x"] = (self.p["x"] + self.p["v"] * np.float32(self.dt * n)).astype(np.float32)
+
+    def drop(self, ids):
+        keep = ~np.isin(self.p["id"], ids)
+        self.p = {k: a[keep] for k, a in self.p.items()}
+
+
+@pytest.fixture
+def fake_engine(monkeypatch):
+    monkeypatch.setattr(capi, "Engine", FakeEngine)
+
+
+def _scene(tmp_path, **kw):
+    m = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=1e-4, frame_directory=str(tmp_path / "frames"), **kw)
+    m.add_particles(type="sand", benchmark_block=((10, 10, 10), (13, 13, 13)), initial_velocity=(0.1, 0.0, 0.0))
+    m.add_particles(type="water", benchmark_block=((16, 10, 10), (18, 12, 12)), k=1e4)
+    return m
+
+
+def test_visualize_names_counts_and_contents(tmp_path, fake_engine):
+    m = _scene(tmp_path, verbose_bgeo=True)
+    m.step(1e-3)
+    f1 = m.visualize()
+    m.step(1e-3)
+    f2 = m.visualize()
+    assert f1.endswith("frames/0001.bgeo") and f2.endswith("frames/0002.bgeo") and m.frame_count == 2   # counter first, then the name
+    p = m.get_particles()
+    pos, attrs = bgeo.read_bgeo(f2)
+    d = {a[0]: a[2] for a in attrs}
+    assert np.array_equal(pos, p["x"]) and np.array_equal(d["v"], p["v"])
+    assert np.array_equal(d["index"].ravel(), p["id"].astype(np.int32)) and (np.diff(d["index"].ravel()) > 0).all()
+    assert np.array_equal(d["m"].ravel(), p["mass"]) and (d["limit"] == 1).all() and not d["type"].any()
+    sand = p["group"] == 0
+    assert (d["debug"][sand, 1] == 6).all() and (d["debug"][~sand, 1] == 5).all()
+    pos1, _ = bgeo.read_bgeo(f1)
+    assert not np.array_equal(pos1, pos)                                                                 # a frame later
+    with pytest.raises(ValueError):
+        mpm_mod.MPM(res=(32, 32, 32)).visualize()                                                        # no frame_directory
+
+
+def test_snapshot_round_trip_restores_state_groups_and_clocks(tmp_path, fake_engine):
+    m = _scene(tmp_path)
+    m.step(1e-3)
+    m.visualize()
+    snap = str(tmp_path / "snap.npz")
+    assert m.general_action(action="save", file_name=snap) == ""
+    p = m.get_particles()
+    m2 = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=1e-4, frame_directory=str(tmp_path / "frames2"))
+    assert m2.general_action(action="load", file_name=snap) == ""
+    q = m2.get_particles()
+    for k in p:
+        assert np.array_equal(p[k], q[k]), k
+    assert (m2.current_t, m2.request_t, m2.substep_counter, m2.frame_count) == (m.current_t, m.request_t, m.substep_counter, 1)
+    assert [k for k, _ in m2._groups] == [k for k, _ in m._groups]
+    assert all(np.array_equal(a[1], b[1]) for a, b in zip(m._groups, m2._groups))
+    assert m2.engine.mats.keys() == m.engine.mats.keys()
+    m.step(1e-3); m2.step(1e-3)
+    assert np.array_equal(m.get_particles()["x"], m2.get_particles()["x"])
+    assert m2.visualize().endswith("0002.bgeo")
+    # adding particles of an already known material after a load reuses its group
+    m2.add_particles(type="water", benchmark_block=((20, 10, 10), (21, 11, 11)), k=1e4)
+    assert len(m2._groups) == 2 and m2.num_particles() == len(q["x"]) + 8
+
+
+def test_snapshot_keeps_contiguous_ids_and_renumbers_gapped_ones(tmp_path, fake_engine):
+    m = _scene(tmp_path)
+    m.step(1e-3)
+    n = m.num_particles()
+    m.engine.drop(np.arange(0, 5))                       # deletions at the front: ids 5..n-1 stay contiguous
+    snap = str(tmp_path / "a.npz")
+    m.general_action(action="save", file_name=snap)
+    m2 = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=1e-4)
+    m2.general_action(action="load", file_name=snap)
+    assert np.array_equal(m2.get_particles()["id"], np.arange(5, n, dtype=np.uint32))
+    m.engine.drop(np.array([40, 41]))                    # a gap: renumbered 0.. in id order
+    m.general_action(action="save", file_name=snap)
+    m3 = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=1e-4)
+    m3.general_action(action="load", file_name=snap)
+    q, p = m3.get_particles(), m.get_particles()
+    assert np.array_equal(q["id"], np.arange(n - 7, dtype=np.uint32)) and np.array_equal(q["x"], p["x"])
+
+
+def test_unknown_action_and_foreign_snapshot_are_rejected(tmp_path, fake_engine):
+    m = _scene(tmp_path)
+    with pytest.raises(ValueError):
+        m.general_action(action="cdf")
+    m.general_action(action="save", file_name=str(tmp_path / "s.npz"))
+    other = mpm_mod.MPM(res=(64, 64, 64), base_delta_t=1e-4)
+    with pytest.raises(ValueError):
+        other.general_action(action="load", file_name=str(tmp_path / "s.npz"))
