@@ -80,6 +80,9 @@ struct TileMeta {  // one 32-byte record per active tile (slot)
 //   MPMB_EXP_DUAL_ARENA  k_p2g: one shared arena per warp, both warps flush their registers at the
 //                        same time and the store sums the two (the warp-after-warp flush holds 11.9 %
 //                        of k_p2g's stall samples).
+//   MPMB_EXP_P2G_IPLANE  k_p2g with three threads per cell (one per stencil x-plane): 36 accumulators and
+//                        95 registers instead of 108 / 248, 18 warps per SM instead of 8 (k_p2g issues
+//                        on 45 % of its cycles at 8 warps).  Replaces the 64-thread kernel when defined.
 
 struct View {  // raw pointers handed to kernels
   float4 *q[N_Q];        // current (read) buffer
@@ -461,6 +464,205 @@ __global__ void k_step_commit(Counters *c) {
 //   4. flush: each warp adds its registers into the shared 6x6x6 arena, conflict-free by layout
 //      (node strides 68/8/1 put the 32 cells of a warp on 32 banks), warp after warp;
 // then one coalesced store of the arena.  No atomics on floats anywhere.
+#ifdef MPMB_EXP_P2G_IPLANE
+// EXPERIMENT (build with -DMPMB_EXP_P2G_IPLANE): three threads per cell, one per x-plane of the
+// 3x3x3 stencil.  Thread (cell, ip) accumulates the 9 nodes (ip, j, k) x (p,m) = 36 registers instead
+// of 108, so a CTA of 192 threads fits 3x per SM (18 warps instead of 8) at the price of re-reading
+// the cell's rows and recomputing wy, wz three times.  Each plane flushes into its own shared arena
+// (planes 1, 2: laid over the row staging area, free after the last chunk); within a plane the two
+// warps own disjoint x ranges, so the whole flush needs no ordering between warps.  The store sums
+// the three arenas in a fixed order: bit-reproducible, but a different rounding order than the
+// 64-thread kernel.
+constexpr int P2G_T = 192;         // 64 cells x 3 stencil planes
+constexpr int P2G_NW = P2G_T / 32;
+constexpr int P2G_CH = 512;        // particles staged per chunk
+constexpr int P2G_K = (P2G_CH + P2G_T - 1) / P2G_T;  // 3 passes, the last one partly idle
+constexpr int P2G_ROWS = P2G_CH + P2G_CH / 8;
+constexpr int AR_SX = 68, AR_SY = 8;
+constexpr int AR_SIZE = 6 * AR_SX;
+static_assert(2 * 4 * AR_SIZE <= 4 * P2G_ROWS * 4, "the two extra arenas must fit in the row staging area");
+
+__global__ void __launch_bounds__(P2G_T, 3) k_p2g(View V, Params P, int part) {
+  __shared__ float4 s_rows[4][P2G_ROWS];
+  __shared__ unsigned short s_order[P2G_CH];
+  __shared__ unsigned short s_hist[P2G_K * P2G_NW][64];
+  __shared__ int s_start[65];
+  __shared__ float s_arena[4][AR_SIZE];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cell_t = tid & 63, ip = tid >> 6;  // my cell and my stencil plane
+  const int n_tiles = V.cnt->n_tiles;
+  const int cx = cell_t >> 4, cy = (cell_t >> 2) & 3, cz = cell_t & 3;
+  float (*ar12)[4][AR_SIZE] = reinterpret_cast<float (*)[4][AR_SIZE]>(&s_rows[0][0]);  // arenas of planes 1 and 2
+  for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
+    const TileMeta tm = V.meta[slot];
+    const int tile = tm.tile;
+    if (!tile_in_part(P, tile, part)) continue;  // uniform per CTA
+    const int nrow_tile = tm.run_len + tm.arr_len;
+    MPMB_TILE_XYZ(P, tm, tx, ty, tz);
+    const float fbx = (float)(tx * 4 + cx), fby = (float)(ty * 4 + cy), fbz = (float)(tz * 4 + cz);
+    float acc[9][4];
+#pragma unroll
+    for (int n = 0; n < 9; n++) { acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f; }
+    for (int n = tid; n < 4 * AR_SIZE; n += P2G_T) (&s_arena[0][0])[n] = 0.f;
+    int vbase = 0;
+    auto row_of = [&](int g) -> uint32_t {
+      return g < tm.run_len ? (uint32_t)(tm.run_begin + g) : V.arrivals_sorted[tm.arr_off + (g - tm.run_len)];
+    };
+
+    for (int cb = 0; cb < nrow_tile; cb += P2G_CH) {
+      const int nrows = min(P2G_CH, nrow_tile - cb);
+      for (int n = tid; n < P2G_K * P2G_NW * 64; n += P2G_T) (&s_hist[0][0])[n] = 0;
+      // ---- 1: stage rows
+      uint32_t pidx[P2G_K];
+#pragma unroll
+      for (int k = 0; k < P2G_K; k++) {
+        const int r = k * P2G_T + tid;
+        pidx[k] = 0u;
+        if (r < nrows) pidx[k] = (cb + r < tm.run_len) ? (uint32_t)(tm.run_begin + cb + r) : row_of(cb + r);
+      }
+#pragma unroll
+      for (int k = 0; k < P2G_K; k++) {
+        const int r = k * P2G_T + tid;
+        if (r < nrows) {
+          const int ri = r + (r >> 3);
+          cp_async16(&s_rows[0][ri], &V.q[0][pidx[k]]);
+          cp_async16(&s_rows[1][ri], &V.q[1][pidx[k]]);
+          cp_async16(&s_rows[2][ri], &V.q[2][pidx[k]]);
+          cp_async16(&s_rows[3][ri], &V.q[3][pidx[k]]);
+        }
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+      __syncthreads();
+      // ---- 2a: per-(pass,warp) cell histograms
+      uint32_t cr[P2G_K];
+#pragma unroll
+      for (int k = 0; k < P2G_K; k++) {
+        const int r = k * P2G_T + tid;
+        int cell = 64 + warp;  // holes and rows past the end: a private bucket per warp
+        float4 a0 = make_float4(0.f, 0.f, 0.f, -1.f);
+        if (r < nrows) a0 = s_rows[0][r + (r >> 3)];
+        if (r < nrows && (a0.w > 0.f || cb + r >= tm.run_len)) {
+          int bx, by, bz;
+          float rr;
+          base_rel(a0.x, P.inv_dx, bx, rr);
+          base_rel(a0.y, P.inv_dx, by, rr);
+          base_rel(a0.z, P.inv_dx, bz, rr);
+          cell = (((bx - tx * 4) & 3) << 4) | (((by - ty * 4) & 3) << 2) | ((bz - tz * 4) & 3);
+        }
+        const unsigned m = __match_any_sync(0xffffffffu, cell);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        if (cell < 64 && rank == 0) s_hist[k * P2G_NW + warp][cell] = (unsigned short)__popc(m);
+        cr[k] = ((uint32_t)cell << 16) | (uint32_t)rank;
+      }
+      __syncthreads();
+      // ---- 2b: exclusive scan over (pass,warp) per cell, then over the 64 cells (warps 0 and 1)
+      int run = 0, incl = 0;
+      if (tid < 64) {
+#pragma unroll
+        for (int e = 0; e < P2G_K * P2G_NW; e++) {
+          const int h = s_hist[e][tid];
+          s_hist[e][tid] = (unsigned short)run;
+          run += h;
+        }
+        incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        if (tid == 31) s_start[64] = incl;  // total of warp 0, fixed up below
+      }
+      __syncthreads();
+      const int base0 = (tid >= 32 && tid < 64) ? s_start[64] : 0;
+      if (tid < 64) s_start[tid] = base0 + incl - run;
+      __syncthreads();
+      if (tid == 63) s_start[64] = base0 + incl;
+      // ---- 2c: scatter row ids to their sorted position; publish the output row for G2P
+#pragma unroll
+      for (int k = 0; k < P2G_K; k++) {
+        const int r = k * P2G_T + tid;
+        const int cell = (int)(cr[k] >> 16);
+        if (cell < 64) {
+          const int pos = s_start[cell] + s_hist[k * P2G_NW + warp][cell] + (int)(cr[k] & 0xffffu);
+          s_order[pos] = (unsigned short)r;
+          V.outpos[pidx[k]] = (uint32_t)(tm.out_begin + vbase + pos);
+        }
+      }
+      __syncthreads();
+      // ---- 3: accumulate my cell's run for my stencil plane
+      const int i0 = s_start[cell_t], i1 = s_start[cell_t + 1];
+      const float fi = (float)ip;
+      for (int it = i0; it < i1; it++) {
+        const int r = s_order[it];
+        const int ri = r + (r >> 3);
+        const float4 a0 = s_rows[0][ri], a1 = s_rows[1][ri], a2 = s_rows[2][ri], a3 = s_rows[3][ri];
+        const float mass = fabsf(a0.w);
+        float vx = a1.x, vy = a1.y, vz = a1.z;
+        if (P.particle_gravity) {
+          vx += P.gdt[0]; vy += P.gdt[1]; vz += P.gdt[2];
+        }
+        const float rx = __fsub_rn(__fmul_rn(a0.x, P.inv_dx), fbx), ry = __fsub_rn(__fmul_rn(a0.y, P.inv_dx), fby),
+                    rz = __fsub_rn(__fmul_rn(a0.z, P.inv_dx), fbz);
+        float wx[3], wy[3], wz[3];
+        bspline_weights(rx, wx);
+        bspline_weights(ry, wy);
+        bspline_weights(rz, wz);
+        const float wxi = ip == 0 ? wx[0] : (ip == 1 ? wx[1] : wx[2]);
+        const float q0 = fmaf(a3.y, rz, fmaf(a2.z, ry, fmaf(a1.w, rx, mass * vx)));
+        const float q1 = fmaf(a3.z, rz, fmaf(a2.w, ry, fmaf(a2.x, rx, mass * vy)));
+        const float q2 = fmaf(a3.w, rz, fmaf(a3.x, ry, fmaf(a2.y, rx, mass * vz)));
+        const float ux = q0 - fi * a1.w, uy = q1 - fi * a2.x, uz = q2 - fi * a2.y;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const float tx_ = ux - (float)j * a2.z, ty_ = uy - (float)j * a2.w, tz_ = uz - (float)j * a3.x;
+          const float wij = wxi * wy[j];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const float w = wij * wz[k];
+            float *a = acc[j * 3 + k];
+            a[0] = fmaf(w, tx_ - (float)k * a3.y, a[0]);
+            a[1] = fmaf(w, ty_ - (float)k * a3.z, a[1]);
+            a[2] = fmaf(w, tz_ - (float)k * a3.w, a[2]);
+            a[3] = fmaf(w, mass, a[3]);
+          }
+        }
+      }
+      vbase += s_start[64];
+      __syncthreads();  // rows / order / hist are reused by the next chunk (or by the arenas below)
+    }
+    // ---- 4: flush.  Planes 1 and 2 zero their arenas in the (now free) staging area first.
+    if (ip > 0)
+      for (int n = cell_t; n < 4 * AR_SIZE; n += 64) (&ar12[ip - 1][0][0])[n] = 0.f;
+    __syncthreads();
+    {
+      float (*ar)[AR_SIZE] = ip == 0 ? s_arena : ar12[ip - 1];
+      const int nb = (cx + ip) * AR_SX + cy * AR_SY + cz;
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const int node = nb + j * AR_SY + k;
+          const float *a = acc[j * 3 + k];
+          ar[0][node] += a[0];
+          ar[1][node] += a[1];
+          ar[2][node] += a[2];
+          ar[3][node] += a[3];
+          __syncwarp();
+        }
+    }
+    __syncthreads();
+    float4 *out = V.arena + (size_t)slot * ARENA;
+    for (int n = tid; n < ARENA; n += P2G_T) {
+      const int a = n / 36, b = (n / 6) % 6, c = n % 6;
+      const int node = a * AR_SX + b * AR_SY + c;
+      out[n] = make_float4((s_arena[0][node] + ar12[0][0][node]) + ar12[1][0][node], (s_arena[1][node] + ar12[0][1][node]) + ar12[1][1][node],
+                           (s_arena[2][node] + ar12[0][2][node]) + ar12[1][2][node], (s_arena[3][node] + ar12[0][3][node]) + ar12[1][3][node]);
+    }
+    __syncthreads();
+  }
+}
+#else
 constexpr int P2G_T = 64;          // threads = cells per tile
 constexpr int P2G_CH = 512;        // particles staged per chunk
 constexpr int P2G_K = P2G_CH / P2G_T;
@@ -700,6 +902,8 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
     __syncthreads();
   }
 }
+
+#endif  // MPMB_EXP_P2G_IPLANE
 
 // ------------------------------------------------------------------------------ grid node
 // Momentum/mass of global node g = fixed-order sum of the arenas that cover it:
