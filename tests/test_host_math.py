@@ -88,6 +88,9 @@ CASES = [
     (scenes.MAT_SAND, {}, 2e-4, 1e-4),      # the series path: resting-column strains
     (scenes.MAT_SAND, {}, 3e-3, 2e-3),      # larger strains: more series terms
     (scenes.MAT_SAND, {"cohesion": 1e-3}, 1e-3, 1e-3),
+    (scenes.MAT_SAND, {}, 1e-2, 5e-3),      # 5-6 log terms
+    (scenes.MAT_SAND, {}, 3e-2, 1e-2),      # 7-9 log terms, 6 exp terms
+    (scenes.MAT_SAND, {}, 0.1, 0.05),       # beyond the series' range: eigen fallback for most lanes
 ]
 
 
@@ -125,6 +128,25 @@ def test_device_two_call_form_matches_fused_step(hm, kind, kw, strain, rate):
     # strain), the fused step keeps it in registers: allow that strain error times stiffness * vol
     stiff = float(prm[0] * prm[1]) if kind == scenes.MAT_WATER else float(prm[0] + prm[1])
     assert np.abs(f1 - f2).max() <= 2e-4 * np.abs(f2).max() + 3e-6 * stiff * float(vol[0])
+
+
+def test_device_sand_large_strain_matches_oracle_for_non_inverted_elements(hm):
+    # |F-I| ~ 0.3-0.5: always the eigen path.  For det(F) < 0 the result depends on the sign convention of
+    # the SVD (the reference's svd() belongs to the missing core): the device keeps the
+    # reflection (ratios of |sigma|), the oracle's convention removes it; only det > 0 is compared, and
+    # only where the smallest singular value leaves fp32 a meaningful log
+    kind, n = scenes.MAT_SAND, 1500
+    F, cdg, ps, vol = _random_states(kind, n, 77, 0.4, 0.1)
+    prm = _params8(kind)
+    Fd, psd, force = _cm(F), ps.copy(), np.zeros((n, 9), np.float32)
+    hm.hm_material_step(C.c_int64(n), C.c_int(kind), _p(prm), _p(_cm(cdg)), _p(Fd), _p(psd), _p(vol), _p(force))
+    Fo, pso, fo = _oracle_step(kind, prm.astype(np.float64), cdg, F, ps, vol)
+    Ft = np.einsum("nij,njk->nik", cdg.astype(np.float64), F.astype(np.float64))
+    ok = (np.linalg.det(Ft) > 0) & (np.linalg.svd(Ft, compute_uv=False).min(1) > 0.05)
+    assert ok.sum() > n // 2
+    assert np.abs(_math(Fd) - Fo)[ok].max() <= 2e-5
+    assert np.abs(psd - pso)[ok].max() <= 1e-5
+    assert np.abs(_math(force) - fo)[ok].max() <= 2e-4 * np.abs(fo[ok]).max()
 
 
 def test_device_zero_stress_at_identity(hm):
