@@ -6,7 +6,11 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load this library.  The product (libmpmb.so) never links or calls it.
 //
-// PARITY STATUS: "parity unpinned" for transfers and constitutive models.  The
+// PARITY STATUS: the 2-D restatement (mpm88_advance, BASELINE config 1) is PINNED against the
+// reference's own lines mls-mpm88.cpp:16-69 executed here (oracle/mpm88_ref.cpp compiles that file
+// where it lies against a stand-in for its one missing header; tests/test_oracle_ref88.py, golden
+// vectors tests/golden/mpm88_ref.npz).  The 3-D path remains "parity unpinned" for transfers and
+// constitutive models.  The 3-D
 // reference cannot be compiled here (it is a plugin of the un-vendored taichi-legacy
 // core: src/transfer.cpp:6-12, src/particles.h:8-11), and its own tests pin only the
 // B-spline weights (src/tests.cpp:10-51, src/transfer.cpp:353-359,975-989).  Those

@@ -246,3 +246,38 @@ def ref_write_partio(path, pos, v, type_, index, limit, verbose=None):
                  np.ascontiguousarray(verbose["apic_frobenius_norm"], f32)]
     partio_ref().ref_write_partio(str(path).encode(), C.c_int64(len(pos)), _p(pos), _p(v), _p(type_), _p(index), _p(limit),
                                   C.c_int(0 if verbose is None else 1), *[None if e is None else _p(e) for e in extra])
+
+
+# ---- the reference's 88-line 2-D program executed here (oracle/mpm88_ref.cpp + taichi_stub/taichi.h)
+_REF88 = None
+
+
+def ref88_available():
+    so = os.path.join(_HERE, "_ref", "libmpm88_ref.so")
+    return os.path.exists(so) or os.path.exists("/root/reference/mls-mpm88.cpp")
+
+
+def ref88():
+    global _REF88
+    if _REF88 is None:
+        so = os.path.join(_HERE, "_ref", "libmpm88_ref.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        _REF88 = C.CDLL(so)
+    return _REF88
+
+
+def ref88_run(x, v, F, C_, Jp, steps, plastic):
+    """advance(dt) of /root/reference/mls-mpm88.cpp:16-69, `steps` times, on the given particles
+    (fp32; F, C row-major 2x2; n=80, dt=1e-4, E=1e4, nu=0.2, hardening=10 are the program's constants).
+    Returns x, v, F, C, Jp, grid[(n+1),(n+1),3]."""
+    L = ref88()
+    f32 = np.float32
+    x, v, F, C_, Jp = (np.ascontiguousarray(a, f32).copy() for a in (x, v, F, C_, Jp))
+    L.ref88_set(C.c_int64(len(x)), _p(x), _p(v), _p(F), _p(C_), _p(Jp), C.c_int(int(plastic)))
+    L.ref88_advance(C.c_int(int(steps)))
+    L.ref88_get(_p(x), _p(v), _p(F), _p(C_), _p(Jp))
+    n = L.ref88_n()
+    g = np.zeros((n + 1, n + 1, 3), f32)
+    L.ref88_grid(_p(g))
+    return x, v, F, C_, Jp, g
