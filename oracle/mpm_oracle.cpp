@@ -6,18 +6,21 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load this library.  The product (libmpmb.so) never links or calls it.
 //
-// PARITY STATUS: the 2-D restatement (mpm88_advance, BASELINE config 1) is PINNED against the
-// reference's own lines mls-mpm88.cpp:16-69 executed here (oracle/mpm88_ref.cpp compiles that file
-// where it lies against a stand-in for its one missing header; tests/test_oracle_ref88.py, golden
-// vectors tests/golden/mpm88_ref.npz).  The 3-D path remains "parity unpinned" for transfers and
-// constitutive models.  The 3-D
-// reference cannot be compiled here (it is a plugin of the un-vendored taichi-legacy
-// core: src/transfer.cpp:6-12, src/particles.h:8-11), and its own tests pin only the
-// B-spline weights (src/tests.cpp:10-51, src/transfer.cpp:353-359,975-989).  Those
-// weight tests ARE restated against this oracle (tests/test_oracle_kat.py).  svd() and
-// polar_decomp() live in the missing core (call sites src/particles.cpp:212,227,394,
-// 630,642); this file supplies its own one-sided-Jacobi SVD and compares only
-// convention-invariant quantities.
+// PARITY STATUS (what is pinned against the reference's OWN code executed here, `make -C oracle ref`):
+//   * mpm88_advance (2-D, BASELINE config 1): against mls-mpm88.cpp:16-69 (oracle/mpm88_ref.cpp);
+//   * calculate_force / plasticity of the five 3-D materials and friction_project: against
+//     src/particles.cpp and src/mpm_fwd.h:25-57 (oracle/particles_ref.cpp);
+//   both compile the reference's translation units where they lie against stand-ins for the
+//   un-vendored taichi core headers (oracle/taichi_stub/: vector/matrix vocabulary, Config, svd/polar —
+//   the stand-in's header states what it restates), golden vectors under tests/golden/;
+//   * the B-spline weights: the reference's own weight tests (src/tests.cpp:10-51,
+//     src/transfer.cpp:353-359,975-989) restated against this file (tests/test_oracle_kat.py).
+// Still "parity unpinned": the 3-D transfers (P2G/G2P loops, src/transfer.cpp), the grid update and
+// the ordering/deletion logic — their translation units need the whole solver class (SPGrid, TBB,
+// level sets, rigid bodies) and cannot be compiled here (src/transfer.cpp:6-12); they are covered by
+// convention-free known-answer tests (conservation, affine reproduction, moments).  svd() and
+// polar_decomp() live in the missing core (call sites src/particles.cpp:212,227,394,630,642); this
+// file supplies its own one-sided-Jacobi SVD and compares only convention-invariant quantities.
 //
 // Two precisions are instantiated: float (same operation order / FMA placement as the
 // reference's SSE path) and double (the accuracy arbiter for the GPU kernels).

@@ -281,3 +281,50 @@ def ref88_run(x, v, F, C_, Jp, steps, plastic):
     g = np.zeros((n + 1, n + 1, 3), f32)
     L.ref88_grid(_p(g))
     return x, v, F, C_, Jp, g
+
+
+# ---- the reference's constitutive models executed here (oracle/particles_ref.cpp + taichi_stub/taichi/*.h)
+_REFP = None
+
+
+def ref_particles_available():
+    so = os.path.join(_HERE, "_ref", "libparticles_ref.so")
+    return os.path.exists(so) or os.path.exists("/root/reference/src/particles.cpp")
+
+
+def ref_particles():
+    global _REFP
+    if _REFP is None:
+        so = os.path.join(_HERE, "_ref", "libparticles_ref.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        _REFP = C.CDLL(so)
+        _REFP.ref_sand_alpha.restype = C.c_float
+    return _REFP
+
+
+def ref_particle_step(kind, params, cdg, F, ps, vol, do_plasticity=True):
+    """<Type>Particle<3>::plasticity(cdg) (optional) followed by calculate_force() of the reference's
+    src/particles.cpp, fp32.  cdg, F: 3x3 math layout.  Returns F', ps', force (math layout)."""
+    prm = np.zeros(N_MAT_PARAMS, np.float32)
+    prm[: len(params)] = params
+    c = np.ascontiguousarray(np.asarray(cdg, np.float32).T).reshape(9)
+    f = np.ascontiguousarray(np.asarray(F, np.float32).T).reshape(9).copy()
+    s = np.array([ps], np.float32)
+    force = np.zeros(9, np.float32)
+    rc = ref_particles().ref_particle(C.c_int(kind), _p(prm), _p(c), _p(f), _p(s), C.c_float(vol), _p(force), C.c_int(int(do_plasticity)))
+    assert rc == 0
+    return f.reshape(3, 3).T.copy(), float(s[0]), force.reshape(3, 3).T.copy()
+
+
+def ref_default_params(kind):
+    out = np.zeros(N_MAT_PARAMS, np.float32)
+    assert ref_particles().ref_default_params(C.c_int(kind), _p(out)) == 0
+    return out
+
+
+def ref_friction_project(vel, base, n, friction):
+    vel, base, n = (np.ascontiguousarray(a, np.float32) for a in (vel, base, n))
+    out = np.zeros(3, np.float32)
+    ref_particles().ref_friction_project(_p(vel), _p(base), _p(n), C.c_float(friction), _p(out))
+    return out

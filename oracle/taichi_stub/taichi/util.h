@@ -1,0 +1,215 @@
+// TEST INFRASTRUCTURE.  Stand-in for the headers of the (un-vendored) taichi-legacy core that the
+// reference's constitutive models include (src/particles.h:8-12, src/particles.cpp:6-8,
+// src/mpm_fwd.h:8-12).  With it the reference's OWN translation unit src/particles.cpp compiles where
+// it lies (oracle/particles_ref.cpp, `make -C oracle ref`), so that calculate_force() / plasticity()
+// of its Snow/Linear/Jelly/Water/Sand particles and friction_project() — the reference's lines,
+// unmodified — run here and pin the oracle's restatement of them.
+//
+// Restated here is the VOCABULARY only, with the meaning the call sites require:
+//   VectorND<n,T>   n scalars, element-wise + - * /, scalar broadcast, dot/sum/length/abs/map;
+//                   3- and 4-vectors of float are 16 bytes (they hold an __m128 in the core,
+//                   src/particles.h:80-82) — GridState's size assert needs it
+//   MatrixND<n,T>   n columns, M[i] = column i (README.md:314); Matrix(s) = s*I, Matrix(v) = diag(v),
+//                   Matrix(c0,c1[,c2]) from columns; products, transpose(d), determinant, inverse,
+//                   diag/trace/frobenius_norm(2)/elementwise_product/sum
+//   svd(A,U,S,V)    A = U S V^T, U and V rotations, singular values descending in magnitude, the last
+//                   one negative when det A < 0 (the convention of the implicit-QR 3x3 SVDs graphics
+//                   codes use; the real core's convention cannot be checked, so tests compare only
+//                   what does not depend on it); polar_decomp(A,R,S): A = R S, R = U V^T
+//   Config          string -> number map with get(key, default) / has_key
+//   Unit, TC_* macros: registration / serialization / logging collapse to nothing.
+// Factorizations are computed in double and rounded, so that differences seen by the tests come from
+// the reference's formulas, not from this header's numerics.
+#pragma once
+#include <immintrin.h>
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#define TC_NAMESPACE_BEGIN namespace taichi {
+#define TC_NAMESPACE_END }
+#define TC_FORCE_INLINE inline __attribute__((always_inline))
+#define TC_NOT_IMPLEMENTED throw std::runtime_error("not implemented");
+#define TC_ERROR(...) throw std::runtime_error("TC_ERROR")
+#define TC_WARN(...) ((void)0)
+#define TC_INFO(...) ((void)0)
+#define TC_STOP std::abort()
+#define TC_IO_DEF_VIRT(...)
+#define TC_IO_DEF_WITH_BASE(...)
+#define TC_IO_DEF(...)
+#define TC_INTERFACE(T) static_assert(sizeof(T *) > 0, "")
+#define TC_INTERFACE_DEF(T, name) static_assert(sizeof(T *) > 0, "")
+#define TC_IMPLEMENTATION(base, derived, name) static_assert(sizeof(derived *) > 0, "")
+
+namespace taichi {
+using real = float;
+using float32 = float;
+using float64 = double;
+using int32 = int32_t;
+using uint8 = uint8_t;
+using uint16 = uint16_t;
+using uint32 = uint32_t;
+using uint64 = uint64_t;
+using int64 = int64_t;
+constexpr real operator"" _f(long double v) { return (real)v; }
+constexpr float64 operator"" _f64(long double v) { return (float64)v; }
+
+using std::abs;
+using std::max;
+using std::min;
+using std::pow;
+using std::sqrt;
+inline real clamp(real v, real lo, real hi) { return v < lo ? lo : (v > hi ? hi : v); }
+inline real sqr(real a) { return a * a; }
+template <int n, class T>
+inline T pow(T a) {
+  T r = 1;
+  for (int i = 0; i < n; i++) r *= a;
+  return r;
+}
+namespace math {
+inline real radians(real deg) { return deg * real(3.14159265358979323846 / 180.0); }
+inline real degrees(real rad) { return rad * real(180.0 / 3.14159265358979323846); }
+}  // namespace math
+
+class Config {
+  std::map<std::string, double> num;
+
+ public:
+  Config &set(const std::string &k, double v) { num[k] = v; return *this; }
+  bool has_key(const std::string &k) const { return num.count(k) != 0; }
+  template <class T>
+  T get(const std::string &k, const T &def) const {
+    auto it = num.find(k);
+    return it == num.end() ? def : (T)it->second;
+  }
+};
+
+class Unit {
+ public:
+  virtual void initialize(const Config &) {}
+  virtual std::string get_name() const { return "unit"; }
+  virtual ~Unit() {}
+};
+
+template <int n, class T>
+struct VectorND {
+  static constexpr int storage = (n == 3 && sizeof(T) == 4) ? 4 : n;
+  alignas((n >= 3 && sizeof(T) == 4) ? 16 : alignof(T)) T d[storage];
+  VectorND() { for (int i = 0; i < storage; i++) d[i] = 0; }
+  VectorND(T s) { for (int i = 0; i < storage; i++) d[i] = i < n ? s : 0; }
+  VectorND(T a, T b) : VectorND() { static_assert(n == 2, ""); d[0] = a; d[1] = b; }
+  VectorND(T a, T b, T c) : VectorND() { static_assert(n == 3, ""); d[0] = a; d[1] = b; d[2] = c; }
+  VectorND(T a, T b, T c, T e) : VectorND() { static_assert(n == 4, ""); d[0] = a; d[1] = b; d[2] = c; d[3] = e; }
+  VectorND(const VectorND<n - 1, T> &v, T last) : VectorND() { for (int i = 0; i < n - 1; i++) d[i] = v[i]; d[n - 1] = last; }
+  explicit VectorND(const VectorND<n + 1, T> &v) : VectorND() { for (int i = 0; i < n; i++) d[i] = v[i]; }
+  VectorND(__m128 v) : VectorND() { alignas(16) float t[4]; _mm_store_ps(t, v); for (int i = 0; i < n && i < 4; i++) d[i] = (T)t[i]; }
+  operator __m128() const { alignas(16) float t[4] = {0, 0, 0, 0}; for (int i = 0; i < n && i < 4; i++) t[i] = (float)d[i]; return _mm_load_ps(t); }
+  T &operator[](int i) { return d[i]; }
+  const T &operator[](int i) const { return d[i]; }
+  T dot(const VectorND &o) const { T s = 0; for (int i = 0; i < n; i++) s += d[i] * o.d[i]; return s; }
+  T sum() const { T s = 0; for (int i = 0; i < n; i++) s += d[i]; return s; }
+  T length() const { return std::sqrt(dot(*this)); }
+  T max() const { T m = d[0]; for (int i = 1; i < n; i++) m = std::max(m, d[i]); return m; }
+  VectorND abs() const { VectorND r; for (int i = 0; i < n; i++) r.d[i] = std::abs(d[i]); return r; }
+  template <class F>
+  VectorND map(F f) const { VectorND r; for (int i = 0; i < n; i++) r.d[i] = f(d[i]); return r; }
+  VectorND &operator+=(const VectorND &o) { for (int i = 0; i < n; i++) d[i] += o.d[i]; return *this; }
+  VectorND &operator-=(const VectorND &o) { for (int i = 0; i < n; i++) d[i] -= o.d[i]; return *this; }
+  VectorND &operator*=(T s) { for (int i = 0; i < n; i++) d[i] *= s; return *this; }
+  VectorND operator-() const { VectorND r; for (int i = 0; i < n; i++) r.d[i] = -d[i]; return r; }
+};
+#define TCSTUB_VEC_OP(op)                                                                                                         \
+  template <int n, class T> inline VectorND<n, T> operator op(const VectorND<n, T> &a, const VectorND<n, T> &b) {                 \
+    VectorND<n, T> r; for (int i = 0; i < n; i++) r[i] = a[i] op b[i]; return r; }                                               \
+  template <int n, class T> inline VectorND<n, T> operator op(const VectorND<n, T> &a, T s) {                                     \
+    VectorND<n, T> r; for (int i = 0; i < n; i++) r[i] = a[i] op s; return r; }                                                  \
+  template <int n, class T> inline VectorND<n, T> operator op(T s, const VectorND<n, T> &a) {                                     \
+    VectorND<n, T> r; for (int i = 0; i < n; i++) r[i] = s op a[i]; return r; }
+TCSTUB_VEC_OP(+)
+TCSTUB_VEC_OP(-)
+TCSTUB_VEC_OP(*)
+TCSTUB_VEC_OP(/)
+#undef TCSTUB_VEC_OP
+template <int n, class T> inline T dot(const VectorND<n, T> &a, const VectorND<n, T> &b) { return a.dot(b); }
+template <int n, class T> inline T length(const VectorND<n, T> &a) { return a.length(); }
+template <int n, class T> inline VectorND<n, T> normalized(const VectorND<n, T> &a) { return a * (T(1) / a.length()); }
+
+using Vector2 = VectorND<2, real>;
+using Vector3 = VectorND<3, real>;
+using Vector4 = VectorND<4, real>;
+using Vector2i = VectorND<2, int>;
+using Vector3i = VectorND<3, int>;
+
+template <int n, class T>
+struct MatrixND {
+  using Vec = VectorND<n, T>;
+  Vec c[n];  // columns
+  MatrixND() {}
+  MatrixND(T s) { for (int i = 0; i < n; i++) c[i][i] = s; }
+  explicit MatrixND(const Vec &diag) { for (int i = 0; i < n; i++) c[i][i] = diag[i]; }
+  MatrixND(const Vec &c0, const Vec &c1) { static_assert(n == 2, ""); c[0] = c0; c[1] = c1; }
+  MatrixND(const Vec &c0, const Vec &c1, const Vec &c2) { static_assert(n == 3, ""); c[0] = c0; c[1] = c1; c[2] = c2; }
+  Vec &operator[](int i) { return c[i]; }
+  const Vec &operator[](int i) const { return c[i]; }
+  Vec diag() const { Vec r; for (int i = 0; i < n; i++) r[i] = c[i][i]; return r; }
+  T trace() const { return diag().sum(); }
+  T sum() const { T s = 0; for (int i = 0; i < n; i++) s += c[i].sum(); return s; }
+  T frobenius_norm2() const { T s = 0; for (int i = 0; i < n; i++) s += c[i].dot(c[i]); return s; }
+  T frobenius_norm() const { return std::sqrt(frobenius_norm2()); }
+  MatrixND elementwise_product(const MatrixND &o) const { MatrixND r; for (int i = 0; i < n; i++) r.c[i] = c[i] * o.c[i]; return r; }
+  MatrixND transposed() const { MatrixND r; for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) r.c[i][j] = c[j][i]; return r; }
+  MatrixND operator-() const { MatrixND r; for (int i = 0; i < n; i++) r.c[i] = -c[i]; return r; }
+  MatrixND &operator+=(const MatrixND &o) { for (int i = 0; i < n; i++) c[i] += o.c[i]; return *this; }
+  MatrixND &operator-=(const MatrixND &o) { for (int i = 0; i < n; i++) c[i] -= o.c[i]; return *this; }
+  static MatrixND outer_product(const Vec &a, const Vec &b) { MatrixND r; for (int i = 0; i < n; i++) r.c[i] = a * b[i]; return r; }
+};
+template <int n, class T> inline MatrixND<n, T> operator+(const MatrixND<n, T> &a, const MatrixND<n, T> &b) { MatrixND<n, T> r; for (int i = 0; i < n; i++) r[i] = a[i] + b[i]; return r; }
+template <int n, class T> inline MatrixND<n, T> operator-(const MatrixND<n, T> &a, const MatrixND<n, T> &b) { MatrixND<n, T> r; for (int i = 0; i < n; i++) r[i] = a[i] - b[i]; return r; }
+template <int n, class T> inline MatrixND<n, T> operator*(const MatrixND<n, T> &a, T s) { MatrixND<n, T> r; for (int i = 0; i < n; i++) r[i] = a[i] * s; return r; }
+template <int n, class T> inline MatrixND<n, T> operator*(T s, const MatrixND<n, T> &a) { MatrixND<n, T> r; for (int i = 0; i < n; i++) r[i] = s * a[i]; return r; }
+template <int n, class T> inline VectorND<n, T> operator*(const MatrixND<n, T> &a, const VectorND<n, T> &v) { VectorND<n, T> r; for (int i = 0; i < n; i++) r += a[i] * v[i]; return r; }
+template <int n, class T> inline MatrixND<n, T> operator*(const MatrixND<n, T> &a, const MatrixND<n, T> &b) { MatrixND<n, T> r; for (int i = 0; i < n; i++) r[i] = a * b[i]; return r; }
+template <int n, class T> inline MatrixND<n, T> transposed(const MatrixND<n, T> &a) { return a.transposed(); }
+template <int n, class T> inline MatrixND<n, T> transpose(const MatrixND<n, T> &a) { return a.transposed(); }
+template <class T> inline T determinant(const MatrixND<2, T> &a) { return a[0][0] * a[1][1] - a[1][0] * a[0][1]; }
+template <class T> inline T determinant(const MatrixND<3, T> &a) {
+  return a[0][0] * (a[1][1] * a[2][2] - a[2][1] * a[1][2]) - a[1][0] * (a[0][1] * a[2][2] - a[2][1] * a[0][2]) +
+         a[2][0] * (a[0][1] * a[1][2] - a[1][1] * a[0][2]);
+}
+template <class T> inline MatrixND<2, T> inversed(const MatrixND<2, T> &a) {
+  T id = T(1) / determinant(a);
+  return MatrixND<2, T>(VectorND<2, T>(a[1][1] * id, -a[0][1] * id), VectorND<2, T>(-a[1][0] * id, a[0][0] * id));
+}
+template <class T> inline MatrixND<3, T> inversed(const MatrixND<3, T> &a) {
+  // adjugate / determinant, evaluated in double
+  double m[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m[j][i] = a[i][j];  // m[row][col]
+  double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+               m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+  double id = 1.0 / det;
+  MatrixND<3, T> r;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      double cof = m[j1][i1] * m[j2][i2] - m[j1][i2] * m[j2][i1];  // cofactor of (j,i) -> inverse entry (i,j)
+      r[j][i] = (T)(cof * id);                                      // r(row i, col j)
+    }
+  return r;
+}
+template <int n, class T> inline MatrixND<n, T> inverse(const MatrixND<n, T> &a) { return inversed(a); }
+
+template <int n>
+struct RegionND {};  // named by src/particles.h:22, unused on this path
+
+using Matrix2 = MatrixND<2, real>;
+using Matrix3 = MatrixND<3, real>;
+}  // namespace taichi

@@ -149,6 +149,35 @@ def test_device_sand_large_strain_matches_oracle_for_non_inverted_elements(hm):
     assert np.abs(_math(force) - fo)[ok].max() <= 2e-4 * np.abs(fo[ok]).max()
 
 
+@pytest.mark.skipif(not O.ref_particles_available(), reason="reference tree absent")
+@pytest.mark.parametrize("kind,strain,rate", [(scenes.MAT_LINEAR, 0.05, 0.01), (scenes.MAT_JELLY, 0.1, 0.01), (scenes.MAT_SNOW, 0.03, 0.01),
+                                              (scenes.MAT_WATER, 0.0, 0.01), (scenes.MAT_SAND, 2e-3, 1e-3), (scenes.MAT_SAND, 0.05, 0.02)])
+def test_device_material_step_matches_reference_particles_directly(hm, kind, strain, rate):
+    # the CUDA header's fused step against the REFERENCE's own plasticity() + calculate_force()
+    # (src/particles.cpp compiled in place with the stand-in core, oracle/particles_ref.cpp): no oracle in between
+    rng = np.random.default_rng(50 + kind)
+    prm = _params8(kind)
+    n, vol = 120, np.float32(1e-6)
+    worst_F = worst_ps = worst_f = scale = 0.0
+    for _ in range(n):
+        F = (np.eye(3) + rng.normal(size=(3, 3)) * strain).astype(np.float32)
+        cdg = (np.eye(3) + rng.normal(size=(3, 3)) * rate).astype(np.float32)
+        if np.linalg.det(F.astype(np.float64)) < 0.3:
+            continue
+        ps = np.float32({scenes.MAT_SNOW: 1 + rng.normal() * 0.05, scenes.MAT_WATER: 1 + rng.normal() * 0.02,
+                         scenes.MAT_SAND: abs(rng.normal()) * 2e-3 * (rng.random() < 0.5)}.get(kind, 0.0))
+        Fr, psr, fr = O.ref_particle_step(kind, prm, cdg, F, ps, float(vol))
+        Fd, psd, force = _cm(F[None]), np.array([ps], np.float32), np.zeros((1, 9), np.float32)
+        hm.hm_material_step(C.c_int64(1), C.c_int(kind), _p(prm), _p(_cm(cdg[None])), _p(Fd), _p(psd), _p(np.array([vol], np.float32)), _p(force))
+        if kind != scenes.MAT_WATER:
+            worst_F = max(worst_F, np.abs(_math(Fd)[0] - Fr).max())
+        worst_ps = max(worst_ps, abs(float(psd[0]) - psr))
+        worst_f = max(worst_f, np.abs(_math(force)[0] - fr).max())
+        scale = max(scale, np.abs(fr).max())
+    assert worst_F <= 2e-6 and worst_ps <= 3e-6
+    assert worst_f <= (2e-4 if kind == scenes.MAT_SAND else 2e-5) * scale   # the reference's fp32 log(sigma) at small strain
+
+
 def test_device_zero_stress_at_identity(hm):
     for kind in (scenes.MAT_LINEAR, scenes.MAT_JELLY, scenes.MAT_SNOW, scenes.MAT_WATER, scenes.MAT_SAND):
         prm = _params8(kind)
