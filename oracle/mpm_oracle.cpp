@@ -13,7 +13,8 @@
 //   both compile the reference's translation units where they lie against stand-ins for the
 //   un-vendored taichi core headers (oracle/taichi_stub/: vector/matrix vocabulary, Config, svd/polar —
 //   the stand-in's header states what it restates), golden vectors under tests/golden/;
-//   * the B-spline weights: the reference's own weight tests (src/tests.cpp:10-51,
+//   * the B-spline weights (quadratic, cubic, the 27-product fast kernel): against src/kernel.h
+//     (oracle/kernel_ref.cpp), and the reference's own weight tests (src/tests.cpp:10-51,
 //     src/transfer.cpp:353-359,975-989) restated against this file (tests/test_oracle_kat.py).
 // Still "parity unpinned": the 3-D transfers (P2G/G2P loops, src/transfer.cpp), the grid update and
 // the ordering/deletion logic — their translation units need the whole solver class (SPGrid, TBB,

@@ -328,3 +328,42 @@ def ref_friction_project(vel, base, n, friction):
     out = np.zeros(3, np.float32)
     ref_particles().ref_friction_project(_p(vel), _p(base), _p(n), C.c_float(friction), _p(out))
     return out
+
+
+# ---- the reference's interpolation kernels executed here (oracle/kernel_ref.cpp)
+_REFK = None
+
+
+def ref_kernel_available():
+    so = os.path.join(_HERE, "_ref", "libkernel_ref.so")
+    return os.path.exists(so) or os.path.exists("/root/reference/src/kernel.h")
+
+
+def ref_kernels():
+    global _REFK
+    if _REFK is None:
+        so = os.path.join(_HERE, "_ref", "libkernel_ref.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        _REFK = C.CDLL(so)
+        _REFK.ref_inv_D.restype = C.c_float
+    return _REFK
+
+
+def ref_kernel(order, pos, inv_dx=1.0):
+    """MPMKernel<3,order>(pos, inv_dx) of src/kernel.h: returns (stencil start[3], w[k,k,k], dw[k,k,k,3])."""
+    k = order + 1
+    pos = np.ascontiguousarray(pos, np.float32)
+    start = np.zeros(3, np.int32)
+    w = np.zeros(k ** 3, np.float32)
+    dw = np.zeros(k ** 3 * 3, np.float32)
+    assert ref_kernels().ref_kernel(C.c_int(order), _p(pos), C.c_float(inv_dx), _p(start), _p(w), _p(dw)) == 0
+    return start, w.reshape(k, k, k), dw.reshape(k, k, k, 3)
+
+
+def ref_fast_kernel32(pos, inv_dx=1.0):
+    pos = np.ascontiguousarray(pos, np.float32)
+    w = np.zeros(27, np.float32)
+    dw = np.zeros(81, np.float32)
+    ref_kernels().ref_fast_kernel32(_p(pos), C.c_float(inv_dx), _p(w), _p(dw))
+    return w.reshape(3, 3, 3), dw.reshape(3, 3, 3, 3)

@@ -42,6 +42,7 @@
 #define TC_WARN(...) ((void)0)
 #define TC_INFO(...) ((void)0)
 #define TC_STOP std::abort()
+#define TC_ALIGNED(x) alignas(x)
 #define TC_IO_DEF_VIRT(...)
 #define TC_IO_DEF_WITH_BASE(...)
 #define TC_IO_DEF(...)
@@ -111,6 +112,8 @@ struct VectorND {
   VectorND(T a, T b, T c, T e) : VectorND() { static_assert(n == 4, ""); d[0] = a; d[1] = b; d[2] = c; d[3] = e; }
   VectorND(const VectorND<n - 1, T> &v, T last) : VectorND() { for (int i = 0; i < n - 1; i++) d[i] = v[i]; d[n - 1] = last; }
   explicit VectorND(const VectorND<n + 1, T> &v) : VectorND() { for (int i = 0; i < n; i++) d[i] = v[i]; }
+  template <class F, class = decltype(std::declval<F>()(0))>
+  explicit VectorND(const F &f) : VectorND() { for (int i = 0; i < n; i++) d[i] = f(i); }  // VectorND([&](int i) { ... })
   VectorND(__m128 v) : VectorND() { alignas(16) float t[4]; _mm_store_ps(t, v); for (int i = 0; i < n && i < 4; i++) d[i] = (T)t[i]; }
   operator __m128() const { alignas(16) float t[4] = {0, 0, 0, 0}; for (int i = 0; i < n && i < 4; i++) t[i] = (float)d[i]; return _mm_load_ps(t); }
   T &operator[](int i) { return d[i]; }
@@ -125,6 +128,7 @@ struct VectorND {
   VectorND &operator+=(const VectorND &o) { for (int i = 0; i < n; i++) d[i] += o.d[i]; return *this; }
   VectorND &operator-=(const VectorND &o) { for (int i = 0; i < n; i++) d[i] -= o.d[i]; return *this; }
   VectorND &operator*=(T s) { for (int i = 0; i < n; i++) d[i] *= s; return *this; }
+  VectorND &operator*=(const VectorND &o) { for (int i = 0; i < n; i++) d[i] *= o.d[i]; return *this; }
   VectorND operator-() const { VectorND r; for (int i = 0; i < n; i++) r.d[i] = -d[i]; return r; }
 };
 #define TCSTUB_VEC_OP(op)                                                                                                         \
@@ -139,6 +143,20 @@ TCSTUB_VEC_OP(-)
 TCSTUB_VEC_OP(*)
 TCSTUB_VEC_OP(/)
 #undef TCSTUB_VEC_OP
+// integer 3-vectors also answer to .x .y .z (src/kernel.h:190-192)
+template <>
+struct VectorND<3, int> {
+  union {
+    int d[3];
+    struct { int x, y, z; };
+  };
+  VectorND() : d{0, 0, 0} {}
+  VectorND(int s) : d{s, s, s} {}
+  VectorND(int a, int b, int c) : d{a, b, c} {}
+  int &operator[](int i) { return d[i]; }
+  const int &operator[](int i) const { return d[i]; }
+};
+template <int n, class T> inline VectorND<n, T> fract(const VectorND<n, T> &a) { VectorND<n, T> r; for (int i = 0; i < n; i++) r[i] = a[i] - std::floor(a[i]); return r; }
 template <int n, class T> inline T dot(const VectorND<n, T> &a, const VectorND<n, T> &b) { return a.dot(b); }
 template <int n, class T> inline T length(const VectorND<n, T> &a) { return a.length(); }
 template <int n, class T> inline VectorND<n, T> normalized(const VectorND<n, T> &a) { return a * (T(1) / a.length()); }
