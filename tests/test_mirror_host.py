@@ -138,3 +138,72 @@ def test_unknown_action_and_foreign_snapshot_are_rejected(tmp_path, fake_engine)
     other = mpm_mod.MPM(res=(64, 64, 64), base_delta_t=1e-4)
     with pytest.raises(ValueError):
         other.general_action(action="load", file_name=str(tmp_path / "s.npz"))
+
+
+# ---- the stepping / seeding verbs of the mirror, same stand-in engine (host logic only)
+class CountingEngine(FakeEngine):
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.calls = []
+
+    def substep(self, n):
+        self.calls.append(n)
+        super().substep(n)
+
+
+def test_step_runs_the_reference_number_of_substeps(monkeypatch, tmp_path):
+    monkeypatch.setattr(capi, "Engine", CountingEngine)
+    m = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=1e-4)
+    m.add_particles(type="jelly", benchmark_block=((10, 10, 10), (12, 12, 12)))
+    # MPM<dim>::step (src/mpm.cpp:428-450): request_t += dt; while (current_t + base_delta_t < request_t) substep()
+    def reference_count(current_t, request_t, dt, h):
+        request_t += dt
+        n = 0
+        while current_t + h < request_t:
+            current_t += h
+            n += 1
+        return n, current_t, request_t
+    cur, req, total = 0.0, 0.0, 0
+    for dt in (1e-3, 1e-3, 2.5e-4, 1e-4, 5e-5, 3.3e-3):
+        n, cur, req = reference_count(cur, req, dt, 1e-4)
+        m.step(dt)
+        total += n
+        assert m.substep_counter == total and m.current_t == cur and m.request_t == req
+    assert sum(m.engine.calls) == total and all(c > 0 for c in m.engine.calls)      # one engine call per frame, never an empty one
+    m.step(-1.0)                                                                    # dt < 0: exactly one substep (src/mpm.cpp:429-432)
+    assert m.substep_counter == total + 1 and m.engine.calls[-1] == 1
+
+
+def test_add_particles_follows_the_reference_rules(fake_engine):
+    m = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=1e-4)
+    # particles within 7 cells of a face are ignored at seeding time (src/mpm.cpp:129-132, src/mpm.h:269-276)
+    m.add_particles(type="snow", benchmark_block=((5, 10, 10), (9, 12, 12)))
+    x = m.get_particles()["x"] * 32
+    assert len(x) and x[:, 0].min() >= 7.0 and len(x) < 4 * 2 * 2 * 8
+    n0 = m.num_particles()
+    # positions= path: volume dx^3 / maximum, mass = volume * density (src/mpm.cpp:134-135)
+    pts = np.array([[0.5, 0.5, 0.5], [0.51, 0.5, 0.5]], np.float32)
+    m.add_particles(type="water", positions=pts, density=1000.0, maximum=4)
+    p = m.get_particles()
+    new = p["group"] == 1
+    assert new.sum() == 2 and np.allclose(p["vol"][new], (1 / 32) ** 3 / 4) and np.allclose(p["mass"][new], (1 / 32) ** 3 / 4 * 1000.0)
+    assert np.allclose(p["ps"][new], 1.0) and m.num_particles() == n0 + 2           # water starts at j = 1
+    # same type + same parameters -> same material group; different parameters -> a new one
+    m.add_particles(type="water", positions=pts + 0.1, density=1000.0)
+    m.add_particles(type="water", positions=pts + 0.2, density=1000.0, k=5e3)
+    assert [k for k, _ in m._groups] == [mpm_mod.scenes.MAT_SNOW, mpm_mod.scenes.MAT_WATER, mpm_mod.scenes.MAT_WATER]
+    with pytest.raises(ValueError):
+        m.add_particles(type="von_mises", positions=pts)                            # registered in the reference, not accelerated
+    with pytest.raises(ValueError):
+        m.add_particles(type="rigid")
+
+
+def test_unsupported_solver_options_are_rejected_not_ignored(fake_engine):
+    for kw in (dict(optimized=False), dict(apic_damping=0.1), dict(rpic_damping=0.1), dict(penalty=1.0), dict(res=(64, 64))):
+        with pytest.raises(ValueError):
+            mpm_mod.MPM(**{"res": (32, 32, 32), **kw})
+    m = mpm_mod.MPM(res=(32, 32, 32))
+    with pytest.raises(ValueError):
+        m.set_levelset(m.create_levelset(), True)                                   # dynamic level set
+    assert m.base_delta_t == 1e-4 and m.gravity == (0.0, -10.0, 0.0)                # defaults of src/mpm.cpp:38,42
+    assert mpm_mod.MPM(res=(32, 32, 32), gravity=-5, base_delta_t=1e-3, dt_multiplier=0.5).gravity == (0.0, -5.0, 0.0)
