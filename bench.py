@@ -507,7 +507,7 @@ def main():
     ap.add_argument("--workload", default="sand256")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink grid and block together (debug only)")
     ap.add_argument("--frame-substeps", type=int, default=500, help="substeps per e2e frame (frame_dt/base_delta_t = 0.01/2e-5)")
-    ap.add_argument("--frames", type=int, default=3, help="e2e frames; the median frame time is reported (host-side noise on shared boxes)")
+    ap.add_argument("--frames", type=int, default=5, help="e2e frames; the median frame time is reported (host-side noise on shared boxes)")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--migrate-capacity", type=int, default=16384, help="particles per face per substep (z-slab message size)")
