@@ -16,10 +16,13 @@
 //   * the B-spline weights (quadratic, cubic, the 27-product fast kernel): against src/kernel.h
 //     (oracle/kernel_ref.cpp), and the reference's own weight tests (src/tests.cpp:10-51,
 //     src/transfer.cpp:353-359,975-989) restated against this file (tests/test_oracle_kat.py).
-// Still "parity unpinned": the 3-D transfers (P2G/G2P loops, src/transfer.cpp), the grid update and
-// the ordering/deletion logic — their translation units need the whole solver class (SPGrid, TBB,
-// level sets, rigid bodies) and cannot be compiled here (src/transfer.cpp:6-12); they are covered by
-// convention-free known-answer tests (conservation, affine reproduction, moments).  svd() and
+//   * the 3-D transfers (P2G and G2P, fast SSE path and scalar path): against src/transfer.cpp
+//     rasterize_optimized / resample_optimized / rasterize / resample with src/mpm.h,
+//     particle_allocator.h and the vendored SPGrid (oracle/transfer_ref.cpp).
+// Still "parity unpinned": the grid update between the transfers (normalisation + level-set boundary
+// condition; its friction_project is pinned), the ordering and the boundary deletion — they live in
+// src/mpm.cpp, which needs TBB, the level-set / rigid-body / mesh / texture libraries of the core and
+// is not compiled here; they are covered by convention-free known-answer tests.  svd() and
 // polar_decomp() live in the missing core (call sites src/particles.cpp:212,227,394,630,642); this
 // file supplies its own one-sided-Jacobi SVD and compares only convention-invariant quantities.
 //

@@ -367,3 +367,60 @@ def ref_fast_kernel32(pos, inv_dx=1.0):
     dw = np.zeros(81, np.float32)
     ref_kernels().ref_fast_kernel32(_p(pos), C.c_float(inv_dx), _p(w), _p(dw))
     return w.reshape(3, 3, 3), dw.reshape(3, 3, 3, 3)
+
+
+# ---- the reference's 3-D transfer loops executed here (oracle/transfer_ref.cpp)
+_REFT = None
+
+
+def ref_transfer_available():
+    so = os.path.join(_HERE, "_ref", "libtransfer_ref.so")
+    return os.path.exists(so) or os.path.exists("/root/reference/src/transfer.cpp")
+
+
+def ref_transfer():
+    global _REFT
+    if _REFT is None:
+        so = os.path.join(_HERE, "_ref", "libtransfer_ref.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        _REFT = C.CDLL(so)
+        _REFT.reft_create.restype = C.c_void_p
+        _REFT.reft_num_particles.restype = C.c_int64
+    return _REFT
+
+
+def ref_transfer_substep(scene, state, grid_vel, optimized=True):
+    """One substep's two transfers by the reference's own code (src/transfer.cpp), fp32:
+    P2G = rasterize_optimized / rasterize on the given particles -> dense node (momentum, mass);
+    then the node values are replaced by `grid_vel` (dense [(res+1)^3][4] velocities after the grid update,
+    which lives in src/mpm.cpp and is not part of this build) and G2P = resample_optimized / resample
+    moves the particles.  Single material group.  Returns grid_after_p2g, dict(x, v, F, b, ps)."""
+    L = ref_transfer()
+    f32 = np.float32
+    res = np.ascontiguousarray(scene["res"], np.int32)
+    g = np.ascontiguousarray(scene["gravity"], f32)
+    h = C.c_void_p(L.reft_create(_p(res), C.c_float(scene["dx"]), C.c_float(scene["dt"]), _p(g), C.c_int(int(scene.get("particle_gravity", 1)))))
+    try:
+        kind = int(scene["mat_kind"][0])
+        prm = np.zeros(N_MAT_PARAMS, f32)
+        prm[: len(scene["mat_params"][0])] = scene["mat_params"][0]
+        st = {k: np.ascontiguousarray(state[k], f32) for k in ("x", "v", "F", "b", "mass", "vol", "ps")}
+        n = len(st["x"])
+        for i in range(n):
+            pid = L.reft_add_particle(h, C.c_int(kind), _p(prm), _p(st["x"][i]), _p(st["v"][i]), C.c_float(st["mass"][i]), C.c_float(st["vol"][i]),
+                                      _p(st["F"][i]), _p(st["b"][i]), C.c_float(st["ps"][i]))
+            assert pid == i
+        L.reft_p2g(h, C.c_int(int(optimized)))
+        nn = tuple(int(r) + 1 for r in res)
+        grid = np.zeros(nn + (4,), f32)
+        L.reft_get_grid(h, _p(grid))
+        gv = np.ascontiguousarray(grid_vel, f32)
+        assert gv.shape == grid.shape
+        L.reft_set_grid(h, _p(gv))
+        L.reft_g2p(h, C.c_int(int(optimized)))
+        out = dict(x=np.zeros((n, 3), f32), v=np.zeros((n, 3), f32), F=np.zeros((n, 9), f32), b=np.zeros((n, 9), f32), ps=np.zeros(n, f32))
+        L.reft_get_particles(h, _p(out["x"]), _p(out["v"]), _p(out["F"]), _p(out["b"]), _p(out["ps"]))
+        return grid, out
+    finally:
+        L.reft_destroy(h)

@@ -24,6 +24,10 @@
 #include <immintrin.h>
 
 #include <algorithm>
+#include <array>
+#include <functional>
+#include <memory>
+#include <type_traits>
 #include <cassert>
 #include <cmath>
 #include <cstdint>
@@ -46,9 +50,25 @@
 #define TC_IO_DEF_VIRT(...)
 #define TC_IO_DEF_WITH_BASE(...)
 #define TC_IO_DEF(...)
+#define TC_IO(...)
+#define TC_IO_DECL template <class S> void io(S &serializer) const
+#define TC_IO_DECL_VIRT template <class S> void io(S &serializer) const
+#define TC_SERIALIZER_IS(T) false
+#define TC_P(x) ((void)0)
+#define TC_TRACE(...) ((void)0)
+#define TC_DEBUG(...) ((void)0)
+#define TC_ASSERT(x) assert(x)
+#define TC_ASSERT_INFO(x, ...) assert(x)
+#define TC_STATIC_ASSERT(x) static_assert((x), "")
+#define TC_STUB_CAT_(a, b) a##b
+#define TC_STUB_CAT(a, b) TC_STUB_CAT_(a, b)
 #define TC_INTERFACE(T) static_assert(sizeof(T *) > 0, "")
 #define TC_INTERFACE_DEF(T, name) static_assert(sizeof(T *) > 0, "")
-#define TC_IMPLEMENTATION(base, derived, name) static_assert(sizeof(derived *) > 0, "")
+// registration by name for create_instance_placement (src/particle_allocator.h:62,71)
+#define TC_IMPLEMENTATION(base, derived, name)                  \
+  static int TC_STUB_CAT(tc_stub_registrar_, __COUNTER__) =     \
+      (taichi::InterfaceRegistry<base>::map()[name] = [](void *place) -> base * { return new (place) derived(); }, 0)
+#define CHECK(x) ((void)(x))
 
 namespace taichi {
 using real = float;
@@ -71,15 +91,31 @@ using std::sqrt;
 inline real clamp(real v, real lo, real hi) { return v < lo ? lo : (v > hi ? hi : v); }
 inline real sqr(real a) { return a * a; }
 template <int n, class T>
-inline T pow(T a) {
+constexpr T pow(T a) {
   T r = 1;
   for (int i = 0; i < n; i++) r *= a;
   return r;
 }
+constexpr real eps = 1e-6f;
 namespace math {
 inline real radians(real deg) { return deg * real(3.14159265358979323846 / 180.0); }
 inline real degrees(real rad) { return rad * real(180.0 / 3.14159265358979323846); }
 }  // namespace math
+
+template <class T>
+struct InterfaceRegistry {
+  static std::map<std::string, std::function<T *(void *)>> &map() {
+    static std::map<std::string, std::function<T *(void *)>> m;
+    return m;
+  }
+};
+template <class T>
+inline T *create_instance_placement(const std::string &alias, void *place) {
+  auto &m = InterfaceRegistry<T>::map();
+  auto it = m.find(alias);
+  if (it == m.end()) throw std::runtime_error("unknown implementation: " + alias);
+  return it->second(place);
+}
 
 class Config {
   std::map<std::string, double> num;
@@ -92,6 +128,13 @@ class Config {
     auto it = num.find(k);
     return it == num.end() ? def : (T)it->second;
   }
+  template <class T> T get(const std::string &) const { return T(); }
+  template <class T> T *get_ptr(const std::string &) const { return nullptr; }
+  std::string get_string(const std::string &) const { return ""; }
+};
+
+struct ThreadedTaskManager {  // parallel for i in [0, n) (src/mpm.h:218-219): serial here, the pin wants a fixed order
+  template <class F> static void run(int n, int, const F &f) { for (int i = 0; i < n; i++) f(i); }
 };
 
 class Unit {
@@ -101,10 +144,25 @@ class Unit {
   virtual ~Unit() {}
 };
 
+template <int n, class T, bool simd = (sizeof(T) == 4 && std::is_floating_point<T>::value && (n == 3 || n == 4))>
+struct VecStorage {
+  static constexpr int storage = n;
+  T d[n];
+};
 template <int n, class T>
-struct VectorND {
-  static constexpr int storage = (n == 3 && sizeof(T) == 4) ? 4 : n;
-  alignas((n >= 3 && sizeof(T) == 4) ? 16 : alignof(T)) T d[storage];
+struct VecStorage<n, T, true> {  // float 3-/4-vectors ARE an __m128 in the core (`.v`, src/transfer.cpp:490,503,929,951)
+  static constexpr int storage = 4;
+  union {
+    T d[4];
+    __m128 v;
+    struct { T x, y, z, w; };
+  };
+};
+
+template <int n, class T>
+struct VectorND : public VecStorage<n, T> {
+  using VecStorage<n, T>::d;
+  using VecStorage<n, T>::storage;
   VectorND() { for (int i = 0; i < storage; i++) d[i] = 0; }
   VectorND(T s) { for (int i = 0; i < storage; i++) d[i] = i < n ? s : 0; }
   VectorND(T a, T b) : VectorND() { static_assert(n == 2, ""); d[0] = a; d[1] = b; }
@@ -112,6 +170,17 @@ struct VectorND {
   VectorND(T a, T b, T c, T e) : VectorND() { static_assert(n == 4, ""); d[0] = a; d[1] = b; d[2] = c; d[3] = e; }
   VectorND(const VectorND<n - 1, T> &v, T last) : VectorND() { for (int i = 0; i < n - 1; i++) d[i] = v[i]; d[n - 1] = last; }
   explicit VectorND(const VectorND<n + 1, T> &v) : VectorND() { for (int i = 0; i < n; i++) d[i] = v[i]; }
+  explicit VectorND(const VectorND<n - 1, T> &v) : VectorND() { for (int i = 0; i < n - 1; i++) d[i] = v[i]; }   // pad with 0
+  template <class U, class = typename std::enable_if<!std::is_same<U, T>::value>::type>
+  explicit VectorND(const VectorND<n, U> &v) : VectorND() { for (int i = 0; i < n; i++) d[i] = (T)v[i]; }
+  explicit VectorND(const std::array<T, n> &a) : VectorND() { for (int i = 0; i < n; i++) d[i] = a[i]; }
+  template <class U> VectorND<n, U> cast() const { VectorND<n, U> r; for (int i = 0; i < n; i++) r[i] = (U)d[i]; return r; }
+  T min() const { T m = d[0]; for (int i = 1; i < n; i++) m = std::min(m, d[i]); return m; }
+  VectorND clamp(const VectorND &lo, const VectorND &hi) const { VectorND r; for (int i = 0; i < n; i++) r.d[i] = std::min(std::max(d[i], lo.d[i]), hi.d[i]); return r; }
+  bool abnormal() const { for (int i = 0; i < n; i++) if (!(d[i] == d[i]) || std::abs((double)d[i]) > 1e30) return true; return false; }
+  static VectorND axis(int k) { VectorND r; r.d[k] = 1; return r; }
+  static VectorND rand() { VectorND r; for (int i = 0; i < n; i++) r.d[i] = (T)std::rand() / (T)RAND_MAX; return r; }
+  VectorND cross(const VectorND &o) const { static_assert(n == 3, ""); VectorND r; r.d[0] = d[1] * o.d[2] - d[2] * o.d[1]; r.d[1] = d[2] * o.d[0] - d[0] * o.d[2]; r.d[2] = d[0] * o.d[1] - d[1] * o.d[0]; return r; }
   template <class F, class = decltype(std::declval<F>()(0))>
   explicit VectorND(const F &f) : VectorND() { for (int i = 0; i < n; i++) d[i] = f(i); }  // VectorND([&](int i) { ... })
   VectorND(__m128 v) : VectorND() { alignas(16) float t[4]; _mm_store_ps(t, v); for (int i = 0; i < n && i < 4; i++) d[i] = (T)t[i]; }
@@ -153,10 +222,20 @@ struct VectorND<3, int> {
   VectorND() : d{0, 0, 0} {}
   VectorND(int s) : d{s, s, s} {}
   VectorND(int a, int b, int c) : d{a, b, c} {}
+  explicit VectorND(const std::array<int, 3> &a) : d{a[0], a[1], a[2]} {}
+  template <class F, class = decltype(std::declval<F>()(0))>
+  explicit VectorND(const F &f) : d{0, 0, 0} { for (int i = 0; i < 3; i++) d[i] = f(i); }
   int &operator[](int i) { return d[i]; }
   const int &operator[](int i) const { return d[i]; }
+  template <class U> VectorND<3, U> cast() const { VectorND<3, U> r; for (int i = 0; i < 3; i++) r[i] = (U)d[i]; return r; }
+  int min() const { return std::min(d[0], std::min(d[1], d[2])); }
+  int max() const { return std::max(d[0], std::max(d[1], d[2])); }
 };
+template <int n, class T> inline std::array<T, n> to_std_array(const VectorND<n, T> &v) { std::array<T, n> a; for (int i = 0; i < n; i++) a[i] = v[i]; return a; }
 template <int n, class T> inline VectorND<n, T> fract(const VectorND<n, T> &a) { VectorND<n, T> r; for (int i = 0; i < n; i++) r[i] = a[i] - std::floor(a[i]); return r; }
+template <int n, class T> inline VectorND<n, T> fused_mul_add(const VectorND<n, T> &a, const VectorND<n, T> &b, const VectorND<n, T> &c) {
+  VectorND<n, T> r; for (int i = 0; i < n; i++) r[i] = std::fma(a[i], b[i], c[i]); return r;
+}
 template <int n, class T> inline T dot(const VectorND<n, T> &a, const VectorND<n, T> &b) { return a.dot(b); }
 template <int n, class T> inline T length(const VectorND<n, T> &a) { return a.length(); }
 template <int n, class T> inline VectorND<n, T> normalized(const VectorND<n, T> &a) { return a * (T(1) / a.length()); }
@@ -164,6 +243,8 @@ template <int n, class T> inline VectorND<n, T> normalized(const VectorND<n, T> 
 using Vector2 = VectorND<2, real>;
 using Vector3 = VectorND<3, real>;
 using Vector4 = VectorND<4, real>;
+using Vector3f = VectorND<3, float>;
+using Vector4f = VectorND<4, float>;
 using Vector2i = VectorND<2, int>;
 using Vector3i = VectorND<3, int>;
 
@@ -225,9 +306,41 @@ template <class T> inline MatrixND<3, T> inversed(const MatrixND<3, T> &a) {
 }
 template <int n, class T> inline MatrixND<n, T> inverse(const MatrixND<n, T> &a) { return inversed(a); }
 
-template <int n>
-struct RegionND {};  // named by src/particles.h:22, unused on this path
+
+template <int dim>
+struct IndexND {
+  VectorND<dim, int> i;
+  VectorND<dim, int> get_ipos() const { return i; }
+};
+// iteration space [lo, hi) in lexicographic order, last axis fastest (stencil node n <-> (n/9, n/3%3, n%3), src/transfer.cpp:353-359)
+template <int dim>
+struct RegionND {
+  VectorND<dim, int> lo, hi;
+  RegionND() {}
+  RegionND(const VectorND<dim, int> &l, const VectorND<dim, int> &h) : lo(l), hi(h) {}
+  struct iterator {
+    IndexND<dim> idx;
+    const RegionND *r;
+    bool done;
+    IndexND<dim> &operator*() { return idx; }
+    bool operator!=(const iterator &o) const { return done != o.done; }
+    iterator &operator++() {
+      for (int a = dim - 1; a >= 0; a--) {
+        if (++idx.i[a] < r->hi[a]) return *this;
+        idx.i[a] = r->lo[a];
+      }
+      done = true;
+      return *this;
+    }
+  };
+  iterator begin() const { iterator it; it.idx.i = lo; it.r = this; it.done = false; for (int a = 0; a < dim; a++) if (lo[a] >= hi[a]) it.done = true; return it; }
+  iterator end() const { iterator it; it.r = this; it.done = true; return it; }
+};
+
 
 using Matrix2 = MatrixND<2, real>;
 using Matrix3 = MatrixND<3, real>;
 }  // namespace taichi
+namespace fmt {
+template <class... A> inline std::string format(const char *, A &&...) { return std::string(); }
+}  // namespace fmt

@@ -1,0 +1,236 @@
+// TEST INFRASTRUCTURE.  The reference's OWN transfer loops — src/transfer.cpp (P2G: rasterize /
+// rasterize_optimized, G2P: resample / resample_optimized) with src/mpm.h, particle_allocator.h,
+// kernel.h, particles.cpp and the vendored SPGrid, all included where they lie, unmodified — compiled
+// against the stand-in core headers oracle/taichi_stub/taichi/*.h, so that the oracle's restatement of
+// the 3-D transfers can be pinned against the reference's lines executed here.
+//
+// What this file adds is scaffolding only:
+//   * empty bodies for the solver's virtual members that live in src/mpm.cpp (not compiled: it needs
+//     TBB, mesh/texture sampling, the level-set and rigid-body libraries), so that an MPM<3> object exists;
+//   * populate(): the particle ordering / page maps / per-node counts that
+//     sort_particles_and_populate_grid builds (src/mpm.cpp:770-918), restated with the real SPGrid
+//     calls — the optimized transfers read them; the scalar transfers do not need them;
+//   * C entry points that load particles, run one transfer, and read or write the node values.
+#include REF_TRANSFER_SOURCE
+#include REF_PARTICLES_SOURCE
+#include <cstdint>
+#include <cstring>
+
+namespace taichi {
+template <> void MPM<3>::initialize(const Config &) {}
+template <> std::string MPM<3>::add_particles(const Config &) { return ""; }
+template <> void MPM<3>::step(real) {}
+template <> std::vector<RenderParticle> MPM<3>::get_render_particles() const { return {}; }
+template <> void MPM<3>::visualize() const {}
+template <> void MPM<3>::add_rigid_particle(Config) {}
+template <> std::string MPM<3>::get_debug_information() { return ""; }
+template <> std::string MPM<3>::general_action(const Config &) { return ""; }
+template <> bool MPM<3>::test() const { return true; }
+template <> void MPM<3>::sort_allocator() {}
+template <> MPM<3>::~MPM() {}
+}  // namespace taichi
+
+namespace {
+using namespace taichi;
+using Solver = MPM<3>;
+using Mask = Solver::SparseMask;
+
+struct Harness {
+  Solver m;
+  std::vector<int> kind;  // per allocator slot
+};
+
+// src/mpm.cpp:770-918 with std::sort instead of tbb::parallel_sort, no periodic pool re-pack
+void populate(Solver &m) {
+  constexpr int index_bits = 32 - Mask::block_bits;
+  const size_t n = m.particles.size();
+  m.particle_sorter.resize(n);
+  auto grid_array = m.grid->Get_Array();
+  for (size_t i = 0; i < n; i++) {
+    uint64 offset = Mask::Linear_Offset(to_std_array(m.get_grid_base_pos(m.allocator[m.particles[i]]->pos * m.inv_delta_x)));
+    m.particle_sorter[i] = ((offset >> Mask::data_bits) << index_bits) + i;
+  }
+  std::sort(m.particle_sorter.begin(), m.particle_sorter.end());
+  std::swap(m.particles, m.particles_);
+  m.particles.resize(m.particles_.size());
+  for (size_t i = 0; i < n; i++) m.particles[i] = m.particles_[m.particle_sorter[i] & ((1ll << index_bits) - 1)];
+  m.page_map->Clear();
+  for (size_t i = 0; i < n; i++) m.page_map->Set_Page((m.particle_sorter[i] >> index_bits) << Mask::data_bits);
+  m.page_map->Update_Block_Offsets();
+  auto blocks = m.page_map->Get_Blocks();
+  m.fat_page_map->Clear();
+  for (int b = 0; b < (int)blocks.second; b++) {
+    auto base_offset = blocks.first[b];
+    auto x = 1 << Mask::block_xbits, y = 1 << Mask::block_ybits, z = 1 << Mask::block_zbits;
+    auto c = Mask::LinearToCoord(base_offset);
+    for (int i = -1 + (c[0] == 0); i < 2; i++)
+      for (int j = -1 + (c[1] == 0); j < 2; j++)
+        for (int k = -1 + (c[2] == 0); k < 2; k++)
+          m.fat_page_map->Set_Page(Mask::Packed_Add(base_offset, Mask::Linear_Offset(x * i, y * j, z * k)));
+  }
+  m.fat_page_map->Update_Block_Offsets();
+  auto fat_blocks = m.fat_page_map->Get_Blocks();
+  for (int i = 0; i < (int)fat_blocks.second; i++) std::memset(&grid_array(fat_blocks.first[i]), 0, 1 << Solver::log2_size);
+  m.block_meta.clear();
+  uint64 last_offset = -1;
+  for (uint32 i = 0; i < n; i++) {
+    if (last_offset != (m.particle_sorter[i] >> 32)) m.block_meta.push_back({i, 0});
+    last_offset = m.particle_sorter[i] >> 32;
+  }
+  m.block_meta.push_back({(uint32)n, 0});
+  for (int b = 0; b < (int)blocks.second; b++) {
+    GridState<3> *g = reinterpret_cast<GridState<3> *>(&grid_array(blocks.first[b]));
+    for (uint32 i = m.block_meta[b].particle_offset; i < m.block_meta[b + 1].particle_offset; i++) {
+      auto base_pos = m.get_grid_base_pos(m.allocator[m.particles[i]]->pos * m.inv_delta_x);
+      uint64 offset = Mask::Linear_Offset(to_std_array(base_pos));
+      g[(offset >> Mask::data_bits) & ((1 << Mask::block_bits) - 1)].particle_count += 1;
+    }
+  }
+  m.rigid_page_map->Clear();  // no rigid bodies: every block takes block_op_normal (src/transfer.cpp:570-575)
+  m.rigid_page_map->Update_Block_Offsets();
+}
+
+MatrixND<3, real> load(const float *a) {
+  MatrixND<3, real> r;
+  for (int c = 0; c < 3; c++) for (int q = 0; q < 3; q++) r[c][q] = a[c * 3 + q];
+  return r;
+}
+void store(const MatrixND<3, real> &a, float *o) {
+  for (int c = 0; c < 3; c++) for (int q = 0; q < 3; q++) o[c * 3 + q] = a[c][q];
+}
+}  // namespace
+
+extern "C" {
+void *reft_create(const int *res, float dx, float dt, const float *gravity, int particle_gravity) {
+  Harness *h = new Harness();
+  Solver &m = h->m;
+  m.res = VectorND<3, int>(res[0], res[1], res[2]);
+  m.delta_x = dx;
+  m.inv_delta_x = 1.0f / dx;
+  m.base_delta_t = dt;
+  m.gravity = VectorND<3, real>(gravity[0], gravity[1], gravity[2]);
+  m.particle_gravity = particle_gravity != 0;
+  m.apic = true;
+  m.apic_damping = m.rpic_damping = m.affine_damping = m.penalty = 0;
+  m.pushing_force = 20000.0f;
+  m.cutting_counter = m.plasticity_counter = 0;
+  m.reorder_interval = 0;
+  m.spgrid_size = 4096;                                   // src/mpm.cpp:50-54
+  while (m.spgrid_size / 2 > (m.res.max() + 1)) m.spgrid_size /= 2;
+  m.grid = std::make_unique<Solver::SparseGrid>(m.spgrid_size, m.spgrid_size, m.spgrid_size);
+  m.page_map = std::make_unique<Solver::PageMap>(*m.grid);
+  m.rigid_page_map = std::make_unique<Solver::PageMap>(*m.grid);
+  m.fat_page_map = std::make_unique<Solver::PageMap>(*m.grid);
+  return h;
+}
+void reft_destroy(void *hp) { delete static_cast<Harness *>(hp); }
+
+// kind / params: the oracle's numbering and parameter vectors.  Returns the particle's id.
+int reft_add_particle(void *hp, int kind, const float *params, const float *x, const float *v, float mass, float vol, const float *F,
+                      const float *b, float ps) {
+  Harness *h = static_cast<Harness *>(hp);
+  static const char *names[5] = {"linear", "jelly", "snow", "water", "sand"};
+  if (kind < 0 || kind > 4) return -1;
+  auto alloc = h->m.allocator.allocate_particle(names[kind]);
+  MPMParticle<3> *p = alloc.second;
+  Config cfg;
+  switch (kind) {
+    case 0: p->initialize(cfg); static_cast<LinearParticle<3> *>(p)->mu = params[0]; static_cast<LinearParticle<3> *>(p)->lambda = params[1]; break;
+    case 1: p->initialize(cfg); static_cast<JellyParticle<3> *>(p)->mu = params[0]; static_cast<JellyParticle<3> *>(p)->lambda = params[1]; break;
+    case 2:
+      cfg.set("mu_0", params[0]).set("lambda_0", params[1]).set("hardening", params[2]).set("theta_c", params[3]).set("theta_s", params[4])
+          .set("min_Jp", params[5]).set("max_Jp", params[6]).set("Jp", ps);
+      p->initialize(cfg);
+      break;
+    case 3: cfg.set("k", params[0]).set("gamma", params[1]); p->initialize(cfg); static_cast<WaterParticle<3> *>(p)->j = ps; break;
+    case 4:
+      cfg.set("mu_0", params[0]).set("lambda_0", params[1]).set("cohesion", params[3]).set("beta", params[4]);
+      p->initialize(cfg);
+      static_cast<SandParticle<3> *>(p)->alpha = params[2];
+      static_cast<SandParticle<3> *>(p)->logJp = ps;
+      break;
+  }
+  p->pos = VectorND<3, real>(x[0], x[1], x[2]);
+  p->set_mass(mass);
+  p->set_velocity(VectorND<3, real>(v[0], v[1], v[2]));
+  p->vol = vol;
+  p->dg_e = load(F);
+  p->apic_b = load(b);
+  h->m.particles.push_back(alloc.first);
+  h->kind.push_back(kind);
+  return (int)p->id;
+}
+
+// P2G of one substep: ordering + cleared fat blocks, then rasterize(dt) (scalar, src/transfer.cpp:193-278)
+// or rasterize_optimized(dt) (src/transfer.cpp:361-581)
+void reft_p2g(void *hp, int optimized) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  populate(m);
+  if (optimized) m.rasterize_optimized(m.base_delta_t);
+  else m.rasterize(m.base_delta_t, true);
+}
+// dense [(res+1)^3][4] copy of velocity_and_mass (momentum, mass after P2G)
+void reft_get_grid(void *hp, float *out) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  const int nx = m.res[0] + 1, ny = m.res[1] + 1, nz = m.res[2] + 1;
+  auto fat = m.fat_page_map->Get_Blocks();
+  std::memset(out, 0, sizeof(float) * 4 * size_t(nx) * ny * nz);
+  auto grid_array = m.grid->Get_Array();
+  for (int b = 0; b < (int)fat.second; b++) {
+    auto c = Mask::LinearToCoord(fat.first[b]);
+    for (int i = 0; i < (1 << Mask::block_xbits); i++)
+      for (int j = 0; j < (1 << Mask::block_ybits); j++)
+        for (int k = 0; k < (1 << Mask::block_zbits); k++) {
+          int X = c[0] + i, Y = c[1] + j, Z = c[2] + k;
+          if (X >= nx || Y >= ny || Z >= nz) continue;
+          const GridState<3> &g = grid_array(std::array<int, 3>{X, Y, Z});
+          float *o = out + 4 * ((size_t(X) * ny + Y) * nz + Z);
+          for (int q = 0; q < 4; q++) o[q] = g.velocity_and_mass[q];
+        }
+  }
+}
+// overwrite velocity_and_mass of every node of the fat blocks from a dense array (node velocities before G2P)
+void reft_set_grid(void *hp, const float *in) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  const int nx = m.res[0] + 1, ny = m.res[1] + 1, nz = m.res[2] + 1;
+  auto fat = m.fat_page_map->Get_Blocks();
+  auto grid_array = m.grid->Get_Array();
+  for (int b = 0; b < (int)fat.second; b++) {
+    auto c = Mask::LinearToCoord(fat.first[b]);
+    for (int i = 0; i < (1 << Mask::block_xbits); i++)
+      for (int j = 0; j < (1 << Mask::block_ybits); j++)
+        for (int k = 0; k < (1 << Mask::block_zbits); k++) {
+          int X = c[0] + i, Y = c[1] + j, Z = c[2] + k;
+          if (X >= nx || Y >= ny || Z >= nz) continue;
+          GridState<3> &g = grid_array(std::array<int, 3>{X, Y, Z});
+          const float *o = in + 4 * ((size_t(X) * ny + Y) * nz + Z);
+          for (int q = 0; q < 4; q++) g.velocity_and_mass[q] = o[q];
+        }
+  }
+}
+// G2P of one substep: resample() (scalar, src/transfer.cpp:585-687) or resample_optimized() (702-968)
+void reft_g2p(void *hp, int optimized) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  if (optimized) m.resample_optimized();
+  else m.resample();
+}
+int64_t reft_num_particles(void *hp) { return (int64_t) static_cast<Harness *>(hp)->m.particles.size(); }
+// particle state by id (= order of reft_add_particle)
+void reft_get_particles(void *hp, float *x, float *v, float *F, float *b, float *ps) {
+  Harness *h = static_cast<Harness *>(hp);
+  Solver &m = h->m;
+  for (auto ptr : m.particles) {
+    MPMParticle<3> *p = m.allocator[ptr];
+    const int id = p->id;
+    for (int d = 0; d < 3; d++) { x[3 * id + d] = p->pos[d]; v[3 * id + d] = p->get_velocity()[d]; }
+    store(p->dg_e, F + 9 * id);
+    store(p->apic_b, b + 9 * id);
+    switch (h->kind[id]) {
+      case 2: ps[id] = static_cast<SnowParticle<3> *>(p)->Jp; break;
+      case 3: ps[id] = static_cast<WaterParticle<3> *>(p)->j; break;
+      case 4: ps[id] = static_cast<SandParticle<3> *>(p)->logJp; break;
+      default: ps[id] = 0;
+    }
+  }
+}
+}

@@ -1,0 +1,86 @@
+"""Pin of the oracle's 3-D transfers against the REFERENCE's own loops: src/transfer.cpp
+rasterize_optimized / resample_optimized (block_op_normal, the SSE fast path the accelerated path
+replaces) and the scalar rasterize / resample, compiled where they lie with src/mpm.h,
+particle_allocator.h, kernel.h, particles.cpp and the vendored SPGrid (oracle/transfer_ref.cpp; the
+stand-in core headers oracle/taichi_stub/taichi/*.h and the harness say what is scaffolding).
+P2G: the node (momentum, mass) the reference scatters == the oracle's.  G2P: from the same node
+velocities, the particle state the reference gathers (v, apic_b, F through plasticity, plastic scalar,
+x) == the oracle's.  Golden vectors of that run are committed (tests/golden/transfer_ref.npz); where
+the reference tree is present the loops also run live.  The grid update between the two transfers
+lives in src/mpm.cpp (not buildable here); its friction_project is pinned in
+tests/test_oracle_ref_particles.py."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from taichi_mpm_b200 import scenes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_transfer_golden", os.path.join(HERE, "golden", "make_transfer_golden.py"))
+G = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(G)
+
+# measured against the fp64 oracle: grid 6e-7, x 3e-8, v 4e-7, F 3e-7, apic_b 8e-6, plastic scalar 5e-7
+TOL = dict(grid=3e-6, x=2e-7, v=3e-6, F=2e-6, b=4e-5, ps=3e-6)
+
+
+def _compare(scene, st, grid_ref, p_ref):
+    new, grid_rast, _ = O.substep(scene, st, np.float64)
+    pmax = max(np.abs(grid_rast[..., :3]).max(), grid_rast[..., 3].max())
+    assert np.abs(grid_ref - grid_rast).max() <= TOL["grid"] * pmax
+    assert (grid_ref[..., 3] > 0).sum() == (grid_rast[..., 3] > 0).sum()             # the same set of touched nodes
+    assert np.abs(p_ref["x"] - new["x"]).max() <= TOL["x"]
+    assert np.abs(p_ref["v"] - new["v"]).max() <= TOL["v"] * np.abs(new["v"]).max()
+    assert np.abs(p_ref["b"] - new["b"]).max() <= TOL["b"] * np.abs(new["b"]).max()
+    if int(scene["mat_kind"][0]) != scenes.MAT_WATER:                                # water carries no F
+        assert np.abs(p_ref["F"] - new["F"]).max() <= TOL["F"]
+    assert np.abs(p_ref["ps"] - new["ps"]).max() <= TOL["ps"]
+
+
+@pytest.mark.parametrize("kind", G.KINDS)
+@pytest.mark.parametrize("tag", ["opt", "scalar"])
+def test_oracle_transfers_match_golden_run_of_reference_loops(kind, tag):
+    z = np.load(os.path.join(HERE, "golden", "transfer_ref.npz"))
+    scene, st = G.golden_scene(kind)
+    # the node velocities the golden G2P started from are the ones the oracle produces today
+    gv_in = G.dense(z["k%d_grid_vel_in_idx" % kind], z["k%d_grid_vel_in_val" % kind])
+    assert np.abs(G.oracle_grid_vel(scene, st) - gv_in).max() <= 1e-6 * max(np.abs(gv_in).max(), 1)
+    p_ref = {k: z["k%d_%s_%s" % (kind, tag, k)] for k in ("x", "v", "F", "b", "ps")}
+    _compare(scene, st, G.dense(z["k%d_%s_grid_idx" % (kind, tag)], z["k%d_%s_grid_val" % (kind, tag)]), p_ref)
+
+
+def test_reference_fast_path_equals_its_scalar_path_in_the_golden_run():
+    # "optimized" and readable versions of the reference agree with each other (same math)
+    z = np.load(os.path.join(HERE, "golden", "transfer_ref.npz"))
+    for kind in G.KINDS:
+        g0 = G.dense(z["k%d_opt_grid_idx" % kind], z["k%d_opt_grid_val" % kind])
+        g1 = G.dense(z["k%d_scalar_grid_idx" % kind], z["k%d_scalar_grid_val" % kind])
+        assert np.abs(g0 - g1).max() <= 2e-6 * np.abs(g1).max()
+        for k in ("x", "v", "F", "ps"):
+            a, b = z["k%d_opt_%s" % (kind, k)], z["k%d_scalar_%s" % (kind, k)]
+            assert np.abs(a - b).max() <= 3e-6 * max(np.abs(b).max(), 1.0), (kind, k)
+
+
+@pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent: golden vectors only")
+@pytest.mark.parametrize("kind", [scenes.MAT_JELLY, scenes.MAT_SNOW, scenes.MAT_SAND])
+def test_oracle_transfers_match_reference_loops_live(kind):
+    from tests import common as T
+    scene, st = T.perturbed_scene(kind, res=32, cells=6, seed=91 + kind)      # 1728 particles, other seeds than the golden run
+    gv = G.oracle_grid_vel(scene, st)
+    for opt in (True, False):
+        grid, p = O.ref_transfer_substep(scene, st, gv, optimized=opt)
+        _compare(scene, st, grid, p)
+
+
+@pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent")
+def test_reference_loops_without_particle_gravity_live():
+    # particle_gravity = false: P2G does not touch the particle velocity (src/transfer.cpp:485-487)
+    from tests import common as T
+    scene, st = T.perturbed_scene(scenes.MAT_JELLY, res=24, cells=4, seed=5)
+    scene["particle_gravity"] = 0
+    gv = G.oracle_grid_vel(scene, st)
+    grid, p = O.ref_transfer_substep(scene, st, gv, optimized=True)
+    _compare(scene, st, grid, p)
