@@ -19,12 +19,13 @@
 //   * the 3-D transfers (P2G and G2P, fast SSE path and scalar path): against src/transfer.cpp
 //     rasterize_optimized / resample_optimized / rasterize / resample with src/mpm.h,
 //     particle_allocator.h and the vendored SPGrid (oracle/transfer_ref.cpp).
-// Still "parity unpinned": the grid update between the transfers (normalisation + level-set boundary
-// condition; its friction_project is pinned), the ordering and the boundary deletion — they live in
-// src/mpm.cpp, which needs TBB, the level-set / rigid-body / mesh / texture libraries of the core and
-// is not compiled here; they are covered by convention-free known-answer tests.  svd() and
-// polar_decomp() live in the missing core (call sites src/particles.cpp:212,227,394,630,642); this
-// file supplies its own one-sided-Jacobi SVD and compares only convention-invariant quantities.
+//   * the rest of the substep — grid normalisation, level-set boundary condition, ordering, boundary
+//     deletion — and MPM<3>::substep() as a whole: against src/mpm.cpp compiled the same way
+//     (oracle/transfer_ref.cpp): same survivors, same trajectories over 10-25 substeps.
+// What the stand-in core supplies instead of the reference is stated in oracle/taichi_stub/taichi/util.h;
+// the one piece with a free convention is svd()/polar_decomp() (call sites src/particles.cpp:212,227,
+// 394,630,642): this file has its own one-sided-Jacobi SVD and only convention-invariant quantities are
+// compared (det F > 0).
 //
 // Two precisions are instantiated: float (same operation order / FMA placement as the
 // reference's SSE path) and double (the accuracy arbiter for the GPU kernels).

@@ -390,37 +390,92 @@ def ref_transfer():
     return _REFT
 
 
-def ref_transfer_substep(scene, state, grid_vel, optimized=True):
-    """One substep's two transfers by the reference's own code (src/transfer.cpp), fp32:
-    P2G = rasterize_optimized / rasterize on the given particles -> dense node (momentum, mass);
-    then the node values are replaced by `grid_vel` (dense [(res+1)^3][4] velocities after the grid update,
-    which lives in src/mpm.cpp and is not part of this build) and G2P = resample_optimized / resample
-    moves the particles.  Single material group.  Returns grid_after_p2g, dict(x, v, F, b, ps)."""
-    L = ref_transfer()
-    f32 = np.float32
-    res = np.ascontiguousarray(scene["res"], np.int32)
-    g = np.ascontiguousarray(scene["gravity"], f32)
-    h = C.c_void_p(L.reft_create(_p(res), C.c_float(scene["dx"]), C.c_float(scene["dt"]), _p(g), C.c_int(int(scene.get("particle_gravity", 1)))))
-    try:
-        kind = int(scene["mat_kind"][0])
+class RefSolver:
+    """The reference's MPM<3> object with particles loaded directly (oracle/transfer_ref.cpp): single transfers,
+    the grid update, or whole substeps by MPM<3>::substep().  Single material group; fp32."""
+
+    def __init__(self, scene, state):
+        L = ref_transfer()
+        L.reft_substep.restype = C.c_int64
+        f32 = np.float32
+        self.L = L
+        self.res = np.ascontiguousarray(scene["res"], np.int32)
+        g = np.ascontiguousarray(scene["gravity"], f32)
+        self.h = C.c_void_p(L.reft_create(_p(self.res), C.c_float(scene["dx"]), C.c_float(scene["dt"]), _p(g),
+                                          C.c_int(int(scene.get("particle_gravity", 1)))))
+        self.kind = int(scene["mat_kind"][0])
         prm = np.zeros(N_MAT_PARAMS, f32)
         prm[: len(scene["mat_params"][0])] = scene["mat_params"][0]
         st = {k: np.ascontiguousarray(state[k], f32) for k in ("x", "v", "F", "b", "mass", "vol", "ps")}
-        n = len(st["x"])
-        for i in range(n):
-            pid = L.reft_add_particle(h, C.c_int(kind), _p(prm), _p(st["x"][i]), _p(st["v"][i]), C.c_float(st["mass"][i]), C.c_float(st["vol"][i]),
-                                      _p(st["F"][i]), _p(st["b"][i]), C.c_float(st["ps"][i]))
+        self.n = len(st["x"])
+        for i in range(self.n):
+            pid = L.reft_add_particle(self.h, C.c_int(self.kind), _p(prm), _p(st["x"][i]), _p(st["v"][i]), C.c_float(st["mass"][i]),
+                                      C.c_float(st["vol"][i]), _p(st["F"][i]), _p(st["b"][i]), C.c_float(st["ps"][i]))
             assert pid == i
-        L.reft_p2g(h, C.c_int(int(optimized)))
-        nn = tuple(int(r) + 1 for r in res)
-        grid = np.zeros(nn + (4,), f32)
-        L.reft_get_grid(h, _p(grid))
-        gv = np.ascontiguousarray(grid_vel, f32)
-        assert gv.shape == grid.shape
-        L.reft_set_grid(h, _p(gv))
-        L.reft_g2p(h, C.c_int(int(optimized)))
+        if scene.get("planes") is not None:      # grid units, (n, d) per plane — what scenes.planes_sdf rasterises
+            pl = np.ascontiguousarray(scene["planes"], f32).reshape(-1, 4)
+            L.reft_set_planes(self.h, C.c_int(len(pl)), _p(pl), C.c_float(scene.get("friction", 0.0)))
+
+    def p2g(self, optimized=True):
+        self.L.reft_p2g(self.h, C.c_int(int(optimized)))
+
+    def grid_update(self):
+        """normalize_grid_and_apply_external_force + apply_grid_boundary_conditions (src/mpm.cpp:277-372)"""
+        self.L.reft_grid_update(self.h)
+
+    def g2p(self, optimized=True):
+        self.L.reft_g2p(self.h, C.c_int(int(optimized)))
+
+    def get_grid(self):
+        grid = np.zeros(tuple(int(r) + 1 for r in self.res) + (4,), np.float32)
+        self.L.reft_get_grid(self.h, _p(grid))
+        return grid
+
+    def set_grid(self, grid):
+        gv = np.ascontiguousarray(grid, np.float32)
+        assert gv.shape == tuple(int(r) + 1 for r in self.res) + (4,)
+        self.L.reft_set_grid(self.h, _p(gv))
+
+    def substep(self, n=1):
+        """MPM<3>::substep() n times (src/mpm.cpp:452-575).  Returns the number of live particles."""
+        return int(self.L.reft_substep(self.h, C.c_int(int(n))))
+
+    def particles(self):
+        """dict(x, v, F, b, ps) indexed by particle id (rows of deleted particles are zero) + alive ids."""
+        n, f32 = self.n, np.float32
         out = dict(x=np.zeros((n, 3), f32), v=np.zeros((n, 3), f32), F=np.zeros((n, 9), f32), b=np.zeros((n, 9), f32), ps=np.zeros(n, f32))
-        L.reft_get_particles(h, _p(out["x"]), _p(out["v"]), _p(out["F"]), _p(out["b"]), _p(out["ps"]))
-        return grid, out
+        self.L.reft_get_particles(self.h, _p(out["x"]), _p(out["v"]), _p(out["F"]), _p(out["b"]), _p(out["ps"]))
+        na = int(self.L.reft_num_particles(self.h))
+        ids = np.zeros(na, np.int32)
+        self.L.reft_alive_ids(self.h, _p(ids))
+        out["alive_ids"] = np.sort(ids)
+        return out
+
+    def close(self):
+        if self.h is not None:
+            self.L.reft_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ref_transfer_substep(scene, state, grid_vel, optimized=True):
+    """One substep's two transfers by the reference's own code (src/transfer.cpp), fp32:
+    P2G = rasterize_optimized / rasterize on the given particles -> dense node (momentum, mass);
+    then the node values are replaced by `grid_vel` (dense [(res+1)^3][4] node velocities) and
+    G2P = resample_optimized / resample moves the particles.  Returns grid_after_p2g, dict(x, v, F, b, ps)."""
+    s = RefSolver(scene, state)
+    try:
+        s.p2g(optimized)
+        grid = s.get_grid()
+        s.set_grid(grid_vel)
+        s.g2p(optimized)
+        p = s.particles()
+        p.pop("alive_ids")
+        return grid, p
     finally:
-        L.reft_destroy(h)
+        s.close()

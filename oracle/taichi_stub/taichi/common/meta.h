@@ -16,7 +16,9 @@ template <> struct StaticIf<false> {
 };
 }  // namespace stub_meta
 }  // namespace taichi
-#define TC_STATIC_IF(x) taichi::stub_meta::StaticIf<(x)>([&](const auto &tc_stub_id) -> void {
-#define TC_STATIC_ELSE }).else_([&](const auto &tc_stub_id) -> void {
-#define TC_STATIC_END_IF });
+// C++17: the untaken branch of a value-dependent condition is not instantiated, which is what the call sites
+// rely on (e.g. a 2-argument Linear_Offset inside TC_STATIC_IF(dim == 2), src/mpm.cpp:836-846)
+#define TC_STATIC_IF(x) if constexpr (x) {
+#define TC_STATIC_ELSE } else {
+#define TC_STATIC_END_IF }
 #define TC_REPEAT27(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16) M(17) M(18) M(19) M(20) M(21) M(22) M(23) M(24) M(25) M(26)

@@ -12,6 +12,11 @@ struct RigidBody {
   real frictions[2] = {0, 0};
   Vector velocity;
   int pos_func_id = -1, rot_func_id = -1;
+  using PositionFunctionType = std::function<Vector(real)>;
+  using RotationFunctionType = std::function<Vector(real)>;
+  PositionFunctionType pos_func;
+  RotationFunctionType rot_func;
+  void set_as_background() {}
   void reset_tmp_velocity() {}
   void apply_tmp_velocity() {}
   Vector get_velocity_at(const Vector &) const { return Vector(0.0f); }

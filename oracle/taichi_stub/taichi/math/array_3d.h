@@ -1,2 +1,2 @@
 #pragma once
-#include <taichi/util.h>
+#include <taichi/stub_more.h>

@@ -62,15 +62,15 @@
 #define TC_STATIC_ASSERT(x) static_assert((x), "")
 #define TC_STUB_CAT_(a, b) a##b
 #define TC_STUB_CAT(a, b) TC_STUB_CAT_(a, b)
-#define TC_INTERFACE(T) static_assert(sizeof(T *) > 0, "")
+#define TC_INTERFACE(T) template <> struct stub_registers<T> { static constexpr bool value = true; }
 #define TC_INTERFACE_DEF(T, name) static_assert(sizeof(T *) > 0, "")
 // registration by name for create_instance_placement (src/particle_allocator.h:62,71)
-#define TC_IMPLEMENTATION(base, derived, name)                  \
-  static int TC_STUB_CAT(tc_stub_registrar_, __COUNTER__) =     \
-      (taichi::InterfaceRegistry<base>::map()[name] = [](void *place) -> base * { return new (place) derived(); }, 0)
+#define TC_IMPLEMENTATION(base, derived, name) \
+  static int TC_STUB_CAT(tc_stub_registrar_, __COUNTER__) = taichi::RegisterIf<taichi::stub_registers<base>::value, base, derived>::run(name)
 #define CHECK(x) ((void)(x))
 
 namespace taichi {
+template <class T> struct stub_registers { static constexpr bool value = false; };
 using real = float;
 using float32 = float;
 using float64 = double;
@@ -81,6 +81,7 @@ using uint32 = uint32_t;
 using uint64 = uint64_t;
 using int64 = int64_t;
 constexpr real operator"" _f(long double v) { return (real)v; }
+constexpr real operator"" _f(unsigned long long v) { return (real)v; }
 constexpr float64 operator"" _f64(long double v) { return (float64)v; }
 
 using std::abs;
@@ -109,6 +110,15 @@ struct InterfaceRegistry {
     return m;
   }
 };
+// only the particle interfaces are really registered (create_instance_placement needs them); registering the
+// solver itself would instantiate every virtual member of MPM<2> and MPM<3>
+template <bool enable, class Base, class Derived> struct RegisterIf { static int run(const std::string &) { return 0; } };
+template <class Base, class Derived> struct RegisterIf<true, Base, Derived> {
+  static int run(const std::string &name) {
+    InterfaceRegistry<Base>::map()[name] = [](void *place) -> Base * { return new (place) Derived(); };
+    return 0;
+  }
+};
 template <class T>
 inline T *create_instance_placement(const std::string &alias, void *place) {
   auto &m = InterfaceRegistry<T>::map();
@@ -122,6 +132,8 @@ class Config {
 
  public:
   Config &set(const std::string &k, double v) { num[k] = v; return *this; }
+  template <class T, class = typename std::enable_if<!std::is_arithmetic<T>::value>::type>
+  Config &set(const std::string &, const T &) { return *this; }   // pointers, strings, vectors: accepted, not stored
   bool has_key(const std::string &k) const { return num.count(k) != 0; }
   template <class T>
   T get(const std::string &k, const T &def) const {
@@ -141,6 +153,7 @@ class Unit {
  public:
   virtual void initialize(const Config &) {}
   virtual std::string get_name() const { return "unit"; }
+  template <class S> void binary_io(S &) const {}
   virtual ~Unit() {}
 };
 
@@ -148,6 +161,14 @@ template <int n, class T, bool simd = (sizeof(T) == 4 && std::is_floating_point<
 struct VecStorage {
   static constexpr int storage = n;
   T d[n];
+};
+template <class T>
+struct VecStorage<2, T, false> {
+  static constexpr int storage = 2;
+  union {
+    T d[2];
+    struct { T x, y; };
+  };
 };
 template <int n, class T>
 struct VecStorage<n, T, true> {  // float 3-/4-vectors ARE an __m128 in the core (`.v`, src/transfer.cpp:490,503,929,951)
@@ -178,6 +199,11 @@ struct VectorND : public VecStorage<n, T> {
   T min() const { T m = d[0]; for (int i = 1; i < n; i++) m = std::min(m, d[i]); return m; }
   VectorND clamp(const VectorND &lo, const VectorND &hi) const { VectorND r; for (int i = 0; i < n; i++) r.d[i] = std::min(std::max(d[i], lo.d[i]), hi.d[i]); return r; }
   bool abnormal() const { for (int i = 0; i < n; i++) if (!(d[i] == d[i]) || std::abs((double)d[i]) > 1e30) return true; return false; }
+  operator std::array<T, n>() const { std::array<T, n> a; for (int i = 0; i < n; i++) a[i] = d[i]; return a; }
+  bool operator==(const VectorND &o) const { for (int i = 0; i < n; i++) if (!(d[i] == o.d[i])) return false; return true; }
+  bool operator!=(const VectorND &o) const { return !(*this == o); }
+  bool operator<(const VectorND &o) const { for (int i = 0; i < n; i++) if (!(d[i] < o.d[i])) return false; return true; }
+  bool operator<=(const VectorND &o) const { for (int i = 0; i < n; i++) if (!(d[i] <= o.d[i])) return false; return true; }
   static VectorND axis(int k) { VectorND r; r.d[k] = 1; return r; }
   static VectorND rand() { VectorND r; for (int i = 0; i < n; i++) r.d[i] = (T)std::rand() / (T)RAND_MAX; return r; }
   VectorND cross(const VectorND &o) const { static_assert(n == 3, ""); VectorND r; r.d[0] = d[1] * o.d[2] - d[2] * o.d[1]; r.d[1] = d[2] * o.d[0] - d[0] * o.d[2]; r.d[2] = d[0] * o.d[1] - d[1] * o.d[0]; return r; }
@@ -190,6 +216,7 @@ struct VectorND : public VecStorage<n, T> {
   T dot(const VectorND &o) const { T s = 0; for (int i = 0; i < n; i++) s += d[i] * o.d[i]; return s; }
   T sum() const { T s = 0; for (int i = 0; i < n; i++) s += d[i]; return s; }
   T length() const { return std::sqrt(dot(*this)); }
+  T length2() const { return dot(*this); }
   T max() const { T m = d[0]; for (int i = 1; i < n; i++) m = std::max(m, d[i]); return m; }
   VectorND abs() const { VectorND r; for (int i = 0; i < n; i++) r.d[i] = std::abs(d[i]); return r; }
   template <class F>
@@ -212,6 +239,7 @@ TCSTUB_VEC_OP(-)
 TCSTUB_VEC_OP(*)
 TCSTUB_VEC_OP(/)
 #undef TCSTUB_VEC_OP
+template <int dim> struct IndexND;
 // integer 3-vectors also answer to .x .y .z (src/kernel.h:190-192)
 template <>
 struct VectorND<3, int> {
@@ -228,6 +256,12 @@ struct VectorND<3, int> {
   int &operator[](int i) { return d[i]; }
   const int &operator[](int i) const { return d[i]; }
   template <class U> VectorND<3, U> cast() const { VectorND<3, U> r; for (int i = 0; i < 3; i++) r[i] = (U)d[i]; return r; }
+  explicit VectorND(const IndexND<3> &idx);
+  operator std::array<int, 3>() const { return std::array<int, 3>{d[0], d[1], d[2]}; }
+  bool operator==(const VectorND &o) const { return d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2]; }
+  bool operator!=(const VectorND &o) const { return !(*this == o); }
+  bool operator<(const VectorND &o) const { return d[0] < o.d[0] && d[1] < o.d[1] && d[2] < o.d[2]; }
+  bool operator<=(const VectorND &o) const { return d[0] <= o.d[0] && d[1] <= o.d[1] && d[2] <= o.d[2]; }
   int min() const { return std::min(d[0], std::min(d[1], d[2])); }
   int max() const { return std::max(d[0], std::max(d[1], d[2])); }
 };
@@ -238,6 +272,8 @@ template <int n, class T> inline VectorND<n, T> fused_mul_add(const VectorND<n, 
 }
 template <int n, class T> inline T dot(const VectorND<n, T> &a, const VectorND<n, T> &b) { return a.dot(b); }
 template <int n, class T> inline T length(const VectorND<n, T> &a) { return a.length(); }
+template <int n, class T> inline T length2(const VectorND<n, T> &a) { return a.length2(); }
+template <int n> struct Element {};
 template <int n, class T> inline VectorND<n, T> normalized(const VectorND<n, T> &a) { return a * (T(1) / a.length()); }
 
 using Vector2 = VectorND<2, real>;
@@ -310,14 +346,19 @@ template <int n, class T> inline MatrixND<n, T> inverse(const MatrixND<n, T> &a)
 template <int dim>
 struct IndexND {
   VectorND<dim, int> i;
+  VectorND<dim, real> storage_offset = VectorND<dim, real>(0.5f);
   VectorND<dim, int> get_ipos() const { return i; }
+  VectorND<dim, real> get_pos() const { return i.template cast<real>() + storage_offset; }  // cell centre unless the region says otherwise
 };
 // iteration space [lo, hi) in lexicographic order, last axis fastest (stencil node n <-> (n/9, n/3%3, n%3), src/transfer.cpp:353-359)
+template <int dim> inline VectorND<dim, int> operator+(const IndexND<dim> &a, const VectorND<dim, int> &b) { return a.get_ipos() + b; }
 template <int dim>
 struct RegionND {
   VectorND<dim, int> lo, hi;
+  VectorND<dim, real> storage_offset = VectorND<dim, real>(0.5f);
   RegionND() {}
   RegionND(const VectorND<dim, int> &l, const VectorND<dim, int> &h) : lo(l), hi(h) {}
+  RegionND(const VectorND<dim, int> &l, const VectorND<dim, int> &h, const VectorND<dim, real> &o) : lo(l), hi(h), storage_offset(o) {}
   struct iterator {
     IndexND<dim> idx;
     const RegionND *r;
@@ -333,10 +374,11 @@ struct RegionND {
       return *this;
     }
   };
-  iterator begin() const { iterator it; it.idx.i = lo; it.r = this; it.done = false; for (int a = 0; a < dim; a++) if (lo[a] >= hi[a]) it.done = true; return it; }
+  iterator begin() const { iterator it; it.idx.i = lo; it.idx.storage_offset = storage_offset; it.r = this; it.done = false; for (int a = 0; a < dim; a++) if (lo[a] >= hi[a]) it.done = true; return it; }
   iterator end() const { iterator it; it.r = this; it.done = true; return it; }
 };
 
+inline VectorND<3, int>::VectorND(const IndexND<3> &idx) : d{idx.i[0], idx.i[1], idx.i[2]} {}
 
 using Matrix2 = MatrixND<2, real>;
 using Matrix3 = MatrixND<3, real>;

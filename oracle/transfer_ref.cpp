@@ -5,29 +5,43 @@
 // the 3-D transfers can be pinned against the reference's lines executed here.
 //
 // What this file adds is scaffolding only:
-//   * empty bodies for the solver's virtual members that live in src/mpm.cpp (not compiled: it needs
-//     TBB, mesh/texture sampling, the level-set and rigid-body libraries), so that an MPM<3> object exists;
-//   * populate(): the particle ordering / page maps / per-node counts that
-//     sort_particles_and_populate_grid builds (src/mpm.cpp:770-918), restated with the real SPGrid
-//     calls — the optimized transfers read them; the scalar transfers do not need them;
-//   * C entry points that load particles, run one transfer, and read or write the node values.
+//   * src/mpm.cpp is compiled too (ordering, grid normalisation, level-set boundary condition, boundary
+//     deletion, substep); what it needs from the core beyond the vector vocabulary — TBB loops, textures,
+//     meshes, images, serialization — exists in the stand-in only so that those parts COMPILE;
+//   * empty bodies for the solver members defined in translation units outside this build (frame output,
+//     rigid coupling) and for add_particles (the harness loads particles directly);
+//   * populate(): the ordering / page maps / per-node counts of sort_particles_and_populate_grid
+//     (src/mpm.cpp:770-918) restated with the real SPGrid calls, used by the single-transfer entry points;
+//     reft_substep calls the reference's own sort_particles_and_populate_grid instead;
+//   * C entry points that load particles, run one transfer or whole substeps, and read or write node values.
 #include REF_TRANSFER_SOURCE
+namespace taichi {
+// declared before src/mpm.cpp is seen, so that its generic add_particles (textures, meshes, Poisson-disk
+// sampling from asset files) is never instantiated for the 3-D solver: the harness loads particles itself
+template <> std::string MPM<3>::add_particles(const Config &);
+}  // namespace taichi
+#include REF_MPM_SOURCE
 #include REF_PARTICLES_SOURCE
 #include <cstdint>
 #include <cstring>
 
 namespace taichi {
-template <> void MPM<3>::initialize(const Config &) {}
+// members of the solver that live in translation units which are not part of this build (src/visualize.cpp,
+// src/rigid_transfer.cpp, ...): empty, and unreachable on the pinned path (no rigid bodies, no frame output)
 template <> std::string MPM<3>::add_particles(const Config &) { return ""; }
-template <> void MPM<3>::step(real) {}
-template <> std::vector<RenderParticle> MPM<3>::get_render_particles() const { return {}; }
 template <> void MPM<3>::visualize() const {}
 template <> void MPM<3>::add_rigid_particle(Config) {}
-template <> std::string MPM<3>::get_debug_information() { return ""; }
-template <> std::string MPM<3>::general_action(const Config &) { return ""; }
-template <> bool MPM<3>::test() const { return true; }
-template <> void MPM<3>::sort_allocator() {}
-template <> MPM<3>::~MPM() {}
+template <> void MPM<3>::rigidify(real) {}
+template <> void MPM<3>::advect_rigid_bodies(real) {}
+template <> void MPM<3>::rasterize_rigid_boundary() {}
+template <> void MPM<3>::gather_cdf() {}
+template <> void MPM<3>::rigid_body_levelset_collision(real, real) {}
+// src/mpm.cpp instantiates parts of the 2-D solver explicitly (general_action); the same members, never called
+template <> void MPM<2>::rigidify(real) {}
+template <> void MPM<2>::advect_rigid_bodies(real) {}
+template <> void MPM<2>::rasterize_rigid_boundary() {}
+template <> void MPM<2>::gather_cdf() {}
+template <> void MPM<2>::rigid_body_levelset_collision(real, real) {}
 }  // namespace taichi
 
 namespace {
@@ -114,7 +128,7 @@ void *reft_create(const int *res, float dx, float dt, const float *gravity, int 
   m.apic_damping = m.rpic_damping = m.affine_damping = m.penalty = 0;
   m.pushing_force = 20000.0f;
   m.cutting_counter = m.plasticity_counter = 0;
-  m.reorder_interval = 0;
+  m.reorder_interval = 1000;                               // src/mpm.cpp:45
   m.spgrid_size = 4096;                                   // src/mpm.cpp:50-54
   while (m.spgrid_size / 2 > (m.res.max() + 1)) m.spgrid_size /= 2;
   m.grid = std::make_unique<Solver::SparseGrid>(m.spgrid_size, m.spgrid_size, m.spgrid_size);
@@ -213,6 +227,36 @@ void reft_g2p(void *hp, int optimized) {
   Solver &m = static_cast<Harness *>(hp)->m;
   if (optimized) m.resample_optimized();
   else m.resample();
+}
+// static level set of half-spaces, grid units: phi(X) = n.X + d (planes4[k] = nx, ny, nz, d), friction as set_friction
+void reft_set_planes(void *hp, int n, const float *planes4, float friction) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  auto ls = std::make_shared<LevelSet<3>>();
+  ls->friction = friction;
+  for (int k = 0; k < n; k++) ls->planes.push_back(VectorND<4, real>(planes4[4 * k], planes4[4 * k + 1], planes4[4 * k + 2], planes4[4 * k + 3]));
+  m.levelset.levelset0 = ls;
+}
+// the grid update between the transfers, as substep() does it (src/mpm.cpp:519-540): normalisation (+ gravity on
+// the grid when particle_gravity is off), then the level-set boundary condition
+void reft_grid_update(void *hp) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  VectorND<3, real> inc = m.gravity * m.base_delta_t;
+  if (m.particle_gravity) inc = VectorND<3, real>(0.0f);
+  m.normalize_grid_and_apply_external_force(inc);
+  if (m.levelset.levelset0) m.apply_grid_boundary_conditions(m.levelset, m.current_t);
+}
+// n whole substeps by MPM<3>::substep() itself (src/mpm.cpp:452-575): its own ordering, optimized transfers,
+// grid update and boundary deletion.  Returns the number of live particles.
+int64_t reft_substep(void *hp, int n) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  if (!m.levelset.levelset0) m.levelset.levelset0 = std::make_shared<LevelSet<3>>();  // no planes: phi = +inf everywhere
+  for (int i = 0; i < n; i++) m.substep();
+  return (int64_t)m.particles.size();
+}
+// ids of the live particles, in the solver's current order
+void reft_alive_ids(void *hp, int32_t *ids) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  for (size_t k = 0; k < m.particles.size(); k++) ids[k] = m.allocator[m.particles[k]]->id;
 }
 int64_t reft_num_particles(void *hp) { return (int64_t) static_cast<Harness *>(hp)->m.particles.size(); }
 // particle state by id (= order of reft_add_particle)

@@ -1,4 +1,4 @@
-"""Pin of the oracle's 3-D transfers against the REFERENCE's own loops: src/transfer.cpp
+"""Pin of the oracle's 3-D substep against the REFERENCE's own solver core.  Transfers: src/transfer.cpp
 rasterize_optimized / resample_optimized (block_op_normal, the SSE fast path the accelerated path
 replaces) and the scalar rasterize / resample, compiled where they lie with src/mpm.h,
 particle_allocator.h, kernel.h, particles.cpp and the vendored SPGrid (oracle/transfer_ref.cpp; the
@@ -6,9 +6,12 @@ stand-in core headers oracle/taichi_stub/taichi/*.h and the harness say what is 
 P2G: the node (momentum, mass) the reference scatters == the oracle's.  G2P: from the same node
 velocities, the particle state the reference gathers (v, apic_b, F through plasticity, plastic scalar,
 x) == the oracle's.  Golden vectors of that run are committed (tests/golden/transfer_ref.npz); where
-the reference tree is present the loops also run live.  The grid update between the two transfers
-lives in src/mpm.cpp (not buildable here); its friction_project is pinned in
-tests/test_oracle_ref_particles.py."""
+the reference tree is present the loops also run live.
+src/mpm.cpp is compiled the same way, so the rest of the substep is pinned too: the grid update
+(normalize_grid_and_apply_external_force + apply_grid_boundary_conditions against a plane level set
+with Coulomb friction), and whole substeps by MPM<3>::substep() itself — its own
+sort_particles_and_populate_grid, optimized transfers, grid update and clear_boundary_particles — against
+the oracle's substep(): the same survivors, the same trajectories."""
 import importlib.util
 import os
 
@@ -62,6 +65,63 @@ def test_reference_fast_path_equals_its_scalar_path_in_the_golden_run():
         for k in ("x", "v", "F", "ps"):
             a, b = z["k%d_opt_%s" % (kind, k)], z["k%d_scalar_%s" % (kind, k)]
             assert np.abs(a - b).max() <= 3e-6 * max(np.abs(b).max(), 1.0), (kind, k)
+
+
+# after 10 substeps (fp32 reference vs fp64 oracle; measured x 3e-7, v 8e-7, F 2e-6, scalar 2e-6)
+TOL_SUB = dict(x=2e-6, v=1e-5, F=1.5e-5, b=2e-4, ps=1.5e-5)
+
+
+def _compare_substeps(scene, st, n_sub, alive, p_ref):
+    cur = st
+    for _ in range(n_sub):
+        cur, _, _ = O.substep(scene, cur, np.float64)
+    oa = np.nonzero(cur["alive"])[0]
+    assert alive == len(oa) and np.array_equal(p_ref["alive_ids"], oa)               # the same particles were deleted
+    assert alive < len(st["x"])                                                      # ... and some were
+    s = oa
+    assert np.abs(p_ref["x"][s] - cur["x"][s]).max() <= TOL_SUB["x"]
+    assert np.abs(p_ref["v"][s] - cur["v"][s]).max() <= TOL_SUB["v"] * np.abs(cur["v"][s]).max()
+    assert np.abs(p_ref["b"][s] - cur["b"][s]).max() <= TOL_SUB["b"] * np.abs(cur["b"][s]).max()
+    if int(scene["mat_kind"][0]) != scenes.MAT_WATER:
+        assert np.abs(p_ref["F"][s] - cur["F"][s]).max() <= TOL_SUB["F"]
+    assert np.abs(p_ref["ps"][s] - cur["ps"][s]).max() <= TOL_SUB["ps"]
+
+
+@pytest.mark.parametrize("kind", G.KINDS)
+def test_oracle_grid_update_matches_golden_run_of_reference(kind):
+    # normalize_grid_and_apply_external_force + apply_grid_boundary_conditions (src/mpm.cpp:277-372) on the reference's own P2G
+    z = np.load(os.path.join(HERE, "golden", "transfer_ref.npz"))
+    scene, st = G.golden_scene(kind)
+    ref = G.dense(z["k%d_gridupd_idx" % kind], z["k%d_gridupd_val" % kind])
+    _, grid_rast, grid_vel = O.substep(scene, st, np.float64)
+    act = grid_rast[..., 3] > 0
+    assert np.abs(ref[..., :3] - grid_vel[..., :3])[act].max() <= 5e-6 * np.abs(grid_vel[..., :3]).max()
+    assert np.abs(ref[..., 3] - grid_rast[..., 3]).max() <= 3e-6 * grid_rast[..., 3].max()    # the mass slot is kept
+    # the floor really acted: some node normal velocities were projected
+    free = grid_rast[..., :3][act] / grid_rast[..., 3][act][:, None]
+    assert np.abs(free - grid_vel[..., :3][act]).max() > 1e-3
+
+
+@pytest.mark.parametrize("kind", G.KINDS)
+def test_oracle_substeps_match_golden_run_of_reference_substep(kind):
+    z = np.load(os.path.join(HERE, "golden", "transfer_ref.npz"))
+    scene, st = G.substep_scene(kind)
+    p_ref = {k: z["k%d_sub_%s" % (kind, k)] for k in ("x", "v", "F", "b", "ps", "alive_ids")}
+    _compare_substeps(scene, st, G.SUBSTEPS, int(z["k%d_sub_alive" % kind]), p_ref)
+
+
+@pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent: golden vectors only")
+@pytest.mark.parametrize("kind", [scenes.MAT_JELLY, scenes.MAT_SAND])
+def test_oracle_substeps_match_reference_substep_live(kind):
+    from tests import common as T
+    scene, st = T.perturbed_scene(kind, res=32, cells=6, seed=7 + kind)
+    st["x"][3] = [0.5, 6.2 / 32, 0.5]
+    st["x"][4] = [(32 - 6.9) / 32, 0.5, 0.5]
+    s = O.RefSolver(scene, st)
+    alive = s.substep(25)
+    p = s.particles()
+    s.close()
+    _compare_substeps(scene, st, 25, alive, p)
 
 
 @pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent: golden vectors only")
