@@ -451,6 +451,10 @@ class RefSolver:
         out["alive_ids"] = np.sort(ids)
         return out
 
+    def write_partio(self, path):
+        """MPM<3>::write_partio (src/visualize.cpp:16-100) on the solver's current particles."""
+        self.L.reft_write_partio(self.h, str(path).encode())
+
     def close(self):
         if self.h is not None:
             self.L.reft_destroy(self.h)

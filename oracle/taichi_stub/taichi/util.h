@@ -385,4 +385,5 @@ using Matrix3 = MatrixND<3, real>;
 }  // namespace taichi
 namespace fmt {
 template <class... A> inline std::string format(const char *, A &&...) { return std::string(); }
+template <class... A> inline void print(FILE *, const char *, A &&...) {}
 }  // namespace fmt

@@ -21,15 +21,15 @@ namespace taichi {
 template <> std::string MPM<3>::add_particles(const Config &);
 }  // namespace taichi
 #include REF_MPM_SOURCE
+#include REF_VISUALIZE_SOURCE
 #include REF_PARTICLES_SOURCE
 #include <cstdint>
 #include <cstring>
 
 namespace taichi {
-// members of the solver that live in translation units which are not part of this build (src/visualize.cpp,
-// src/rigid_transfer.cpp, ...): empty, and unreachable on the pinned path (no rigid bodies, no frame output)
+// members of the solver that live in translation units which are not part of this build (src/rigid_transfer.cpp,
+// ...): empty, and unreachable on the pinned path (no rigid bodies)
 template <> std::string MPM<3>::add_particles(const Config &) { return ""; }
-template <> void MPM<3>::visualize() const {}
 template <> void MPM<3>::add_rigid_particle(Config) {}
 template <> void MPM<3>::rigidify(real) {}
 template <> void MPM<3>::advect_rigid_bodies(real) {}
@@ -258,6 +258,8 @@ void reft_alive_ids(void *hp, int32_t *ids) {
   Solver &m = static_cast<Harness *>(hp)->m;
   for (size_t k = 0; k < m.particles.size(); k++) ids[k] = m.allocator[m.particles[k]]->id;
 }
+// frame dump by MPM<3>::write_partio itself (src/visualize.cpp:16-100) through the vendored Partio
+void reft_write_partio(void *hp, const char *file_name) { static_cast<Harness *>(hp)->m.write_partio(file_name); }
 int64_t reft_num_particles(void *hp) { return (int64_t) static_cast<Harness *>(hp)->m.particles.size(); }
 // particle state by id (= order of reft_add_particle)
 void reft_get_particles(void *hp, float *x, float *v, float *F, float *b, float *ps) {

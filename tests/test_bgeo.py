@@ -57,6 +57,29 @@ def test_writer_equals_reference_writer_live(tmp_path, n, verbose):
     assert mine.read_bytes() == ref.read_bytes()
 
 
+@pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent")
+def test_writer_equals_write_partio_of_the_reference_solver_live(tmp_path):
+    # the reference's MPM<3> (oracle/transfer_ref.cpp) steps a scene, deletes a particle, and dumps the frame with
+    # its own write_partio; the product's writer, given the same particle state, produces the same bytes
+    from tests import common as T
+    from taichi_mpm_b200 import scenes
+    scene, st = T.perturbed_scene(scenes.MAT_SAND, res=24, cells=3, seed=2)
+    st["x"][0] = [6.5 / 24, 0.5, 0.5]
+    s = O.RefSolver(scene, st)
+    alive = s.substep(5)
+    ref = tmp_path / "ref.bgeo"
+    s.write_partio(ref)
+    p = s.particles()
+    s.close()
+    ids = p["alive_ids"]
+    assert alive == len(ids) == len(st["x"]) - 1
+    d = dict(id=ids.astype(np.uint32), x=p["x"][ids], v=p["v"][ids], b=p["b"][ids], mass=st["mass"][ids], ps=p["ps"][ids],
+             group=np.zeros(len(ids), np.int32))
+    mine = tmp_path / "mine.bgeo"
+    bgeo.write_bgeo(str(mine), d["x"], mpm.frame_attributes(d, [scenes.MAT_SAND], verbose=False))
+    assert mine.read_bytes() == ref.read_bytes()
+
+
 def test_read_rejects_other_files(tmp_path):
     f = tmp_path / "x.bgeo"
     f.write_bytes(b"PK\x03\x04 not a bgeo")
