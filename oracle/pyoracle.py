@@ -392,7 +392,7 @@ def ref_transfer():
 
 class RefSolver:
     """The reference's MPM<3> object with particles loaded directly (oracle/transfer_ref.cpp): single transfers,
-    the grid update, or whole substeps by MPM<3>::substep().  Single material group; fp32."""
+    the grid update, or whole substeps by MPM<3>::substep().  fp32; material groups as in the oracle's scenes."""
 
     def __init__(self, scene, state):
         L = ref_transfer()
@@ -403,13 +403,16 @@ class RefSolver:
         g = np.ascontiguousarray(scene["gravity"], f32)
         self.h = C.c_void_p(L.reft_create(_p(self.res), C.c_float(scene["dx"]), C.c_float(scene["dt"]), _p(g),
                                           C.c_int(int(scene.get("particle_gravity", 1)))))
-        self.kind = int(scene["mat_kind"][0])
-        prm = np.zeros(N_MAT_PARAMS, f32)
-        prm[: len(scene["mat_params"][0])] = scene["mat_params"][0]
+        kinds = np.asarray(scene["mat_kind"], np.int32)
+        prms = np.zeros((len(kinds), N_MAT_PARAMS), f32)
+        for g, q in enumerate(scene["mat_params"]):
+            prms[g, : len(q)] = q
         st = {k: np.ascontiguousarray(state[k], f32) for k in ("x", "v", "F", "b", "mass", "vol", "ps")}
+        group = np.asarray(state.get("group", np.zeros(len(st["x"]), np.int32)), np.int64)
         self.n = len(st["x"])
         for i in range(self.n):
-            pid = L.reft_add_particle(self.h, C.c_int(self.kind), _p(prm), _p(st["x"][i]), _p(st["v"][i]), C.c_float(st["mass"][i]),
+            g = int(group[i])
+            pid = L.reft_add_particle(self.h, C.c_int(int(kinds[g])), _p(prms[g]), _p(st["x"][i]), _p(st["v"][i]), C.c_float(st["mass"][i]),
                                       C.c_float(st["vol"][i]), _p(st["F"][i]), _p(st["b"][i]), C.c_float(st["ps"][i]))
             assert pid == i
         if scene.get("planes") is not None:      # grid units, (n, d) per plane — what scenes.planes_sdf rasterises

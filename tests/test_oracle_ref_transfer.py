@@ -110,6 +110,56 @@ def test_oracle_substeps_match_golden_run_of_reference_substep(kind):
     _compare_substeps(scene, st, G.SUBSTEPS, int(z["k%d_sub_alive" % kind]), p_ref)
 
 
+@pytest.mark.parametrize("kind", G.KINDS)
+def test_timed_cpu_port_matches_golden_run_of_reference_substep(kind):
+    # the fp32 OpenMP fast path that bench.py times as the CPU baseline (tile cache, 8-colour passes, SSE node
+    # loops, periodic pool re-pack) is the reference's arithmetic: fp32 vs fp32, 10 substeps
+    z = np.load(os.path.join(HERE, "golden", "transfer_ref.npz"))
+    scene, st = G.substep_scene(kind)
+    f = O.FastOracle(scene, st, threads=2, reorder_interval=1000)
+    f.substeps(G.SUBSTEPS)
+    ids = np.nonzero(f.st["alive"])[0]
+    assert np.array_equal(ids, z["k%d_sub_alive_ids" % kind])
+    ref = {k: z["k%d_sub_%s" % (kind, k)][ids] for k in ("x", "v", "F", "b", "ps")}
+    assert np.abs(f.st["x"][ids] - ref["x"]).max() <= 5e-7
+    assert np.abs(f.st["v"][ids] - ref["v"]).max() <= 5e-5 * np.abs(ref["v"]).max()
+    assert np.abs(f.st["b"][ids] - ref["b"]).max() <= 3e-4 * np.abs(ref["b"]).max()
+    assert np.abs(f.st["F"][ids] - ref["F"]).max() <= 3e-5
+    assert np.abs(f.st["ps"][ids] - ref["ps"]).max() <= 5e-5
+
+
+@pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent")
+def test_two_materials_in_one_scene_match_reference_substep_live():
+    # sand resting next to water, each with its own registered particle type in the reference's allocator
+    res = 32
+    xa, ma, va = scenes.lattice_block(res, (10, 10, 10), (15, 15, 15), 400.0, 0.05)
+    xb, mb, vb = scenes.lattice_block(res, (15, 10, 10), (19, 14, 14), 400.0, 0.05, seed=5)
+    sa = scenes.make_state(xa, ma, va, scenes.MAT_SAND, 0)
+    sb = scenes.make_state(xb, mb, vb, scenes.MAT_WATER, 1)
+    st = {k: np.concatenate([sa[k], sb[k]]) for k in sa}
+    rng = np.random.default_rng(12)
+    st["v"] = (rng.normal(size=st["x"].shape) * 0.3).astype(np.float32)
+    planes = np.array([[0, 1, 0, -10.4]], np.float32)
+    scene = dict(res=(res,) * 3, dx=1.0 / res, dt=2e-5, gravity=(0.0, -10.0, 0.0), particle_gravity=1,
+                 mat_kind=np.array([scenes.MAT_SAND, scenes.MAT_WATER], np.int32),
+                 mat_params=np.stack([scenes.material_params(scenes.MAT_SAND), scenes.material_params(scenes.MAT_WATER)]),
+                 planes=planes, sdf=scenes.planes_sdf(res, planes), friction=0.4)
+    s = O.RefSolver(scene, st)
+    alive = s.substep(15)
+    p = s.particles()
+    s.close()
+    cur = st
+    for _ in range(15):
+        cur, _, _ = O.substep(scene, cur, np.float64)
+    ids = np.nonzero(cur["alive"])[0]
+    assert alive == len(ids) == len(st["x"]) and np.array_equal(p["alive_ids"], ids)
+    assert np.abs(p["x"] - cur["x"]).max() <= TOL_SUB["x"]
+    assert np.abs(p["v"] - cur["v"]).max() <= TOL_SUB["v"] * np.abs(cur["v"]).max()
+    sand = st["group"] == 0
+    assert np.abs(p["F"][sand] - cur["F"][sand]).max() <= TOL_SUB["F"]
+    assert np.abs(p["ps"] - cur["ps"]).max() <= TOL_SUB["ps"]
+
+
 @pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent: golden vectors only")
 @pytest.mark.parametrize("kind", [scenes.MAT_JELLY, scenes.MAT_SAND])
 def test_oracle_substeps_match_reference_substep_live(kind):
