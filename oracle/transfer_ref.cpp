@@ -1,19 +1,24 @@
-// TEST INFRASTRUCTURE.  The reference's OWN transfer loops — src/transfer.cpp (P2G: rasterize /
-// rasterize_optimized, G2P: resample / resample_optimized) with src/mpm.h, particle_allocator.h,
-// kernel.h, particles.cpp and the vendored SPGrid, all included where they lie, unmodified — compiled
-// against the stand-in core headers oracle/taichi_stub/taichi/*.h, so that the oracle's restatement of
-// the 3-D transfers can be pinned against the reference's lines executed here.
+// TEST INFRASTRUCTURE.  The reference's OWN solver core, every file included where it lies and unmodified:
+//   src/transfer.cpp   P2G (rasterize / rasterize_optimized) and G2P (resample / resample_optimized)
+//   src/mpm.cpp        ordering and page maps, grid normalisation, level-set boundary condition, boundary
+//                      deletion, MPM<3>::substep() and step()
+//   src/visualize.cpp  write_partio (frame dump through the vendored Partio)
+//   src/particles.cpp  the registered particle types (constitutive models)
+//   src/mpm.h, particle_allocator.h, kernel.h, mpm_fwd.h, articulation.h, boundary_particle.h,
+//   poisson_disk_sampler.h, external/SPGrid, external/partio
+// compiled against the stand-in core headers oracle/taichi_stub/taichi/*.h (their header says what they restate),
+// so that the oracle's restatement is pinned against the reference's lines executed here — stage by stage and as
+// whole substeps.
 //
-// What this file adds is scaffolding only:
-//   * src/mpm.cpp is compiled too (ordering, grid normalisation, level-set boundary condition, boundary
-//     deletion, substep); what it needs from the core beyond the vector vocabulary — TBB loops, textures,
-//     meshes, images, serialization — exists in the stand-in only so that those parts COMPILE;
-//   * empty bodies for the solver members defined in translation units outside this build (frame output,
-//     rigid coupling) and for add_particles (the harness loads particles directly);
+// What THIS file adds is scaffolding only:
+//   * empty bodies for the solver members defined in translation units outside this build (rigid coupling:
+//     src/rigid_transfer.cpp etc.) and for add_particles (seeding from textures / meshes / Poisson-disk asset
+//     files; the harness loads particles directly) — none is reachable on the pinned path;
 //   * populate(): the ordering / page maps / per-node counts of sort_particles_and_populate_grid
-//     (src/mpm.cpp:770-918) restated with the real SPGrid calls, used by the single-transfer entry points;
-//     reft_substep calls the reference's own sort_particles_and_populate_grid instead;
-//   * C entry points that load particles, run one transfer or whole substeps, and read or write node values.
+//     (src/mpm.cpp:770-918) restated with the real SPGrid calls, used only by the single-transfer entry points
+//     (reft_p2g / reft_g2p); reft_substep runs the reference's own sort_particles_and_populate_grid;
+//   * C entry points that load particles, set a plane level set, run one stage or whole substeps, read or write
+//     node values, and dump a frame.
 #include REF_TRANSFER_SOURCE
 namespace taichi {
 // declared before src/mpm.cpp is seen, so that its generic add_particles (textures, meshes, Poisson-disk
