@@ -186,6 +186,26 @@ def test_oracle_transfers_match_reference_loops_live(kind):
 
 
 @pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent")
+@pytest.mark.parametrize("friction", [-1.0, -2.0, -2.3, 0.0, 0.4, 5.0])
+@pytest.mark.parametrize("particle_gravity", [1, 0])
+def test_grid_update_modes_match_reference_live(friction, particle_gravity):
+    # sticky (-1), slip (<= -2, with friction -mu-2), separate with Coulomb friction (>= 0): src/mpm_fwd.h:25-57 as
+    # apply_grid_boundary_conditions uses it (src/mpm.cpp:296-372); gravity on the grid when particle_gravity is
+    # off (src/mpm.cpp:519-527)
+    from tests import common as T
+    scene, st = T.perturbed_scene(scenes.MAT_JELLY, res=24, cells=4, seed=41, friction=friction)
+    scene["particle_gravity"] = particle_gravity
+    _, grid_rast, grid_vel = O.substep(scene, st, np.float64)
+    s = O.RefSolver(scene, st)
+    s.p2g(True)
+    s.grid_update()
+    g = s.get_grid()
+    s.close()
+    act = grid_rast[..., 3] > 0
+    assert np.abs(g[..., :3] - grid_vel[..., :3])[act].max() <= 5e-6 * np.abs(grid_vel[..., :3]).max()
+
+
+@pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent")
 def test_reference_loops_without_particle_gravity_live():
     # particle_gravity = false: P2G does not touch the particle velocity (src/transfer.cpp:485-487)
     from tests import common as T
