@@ -1,5 +1,5 @@
 """Host-side logic of the z-slab multi-GPU path on CPU: partitioning, and the exchange
-choreography with world_size-2/3 gloo processes and a mock engine (no CUDA here)."""
+choreography with world_size-2/3/8 gloo processes and a mock engine (no CUDA here)."""
 import os
 import socket
 
@@ -105,7 +105,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,overlap", [(2, False), (3, False), (2, True)])
+@pytest.mark.parametrize("world,overlap", [(2, False), (3, False), (2, True), (8, False)])
 def test_exchange_choreography_gloo(world, overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
