@@ -2100,6 +2100,9 @@ int mpmb_download_grid(MpmbHandle h, int32_t which, float *dense4) {
 }
 
 // ------------------------------------------------------------------------------ debug (not part of mpmb.h)
+// Only in builds with -DMPMB_DEBUG_EXPORTS (python -m taichi_mpm_b200.build --define MPMB_DEBUG_EXPORTS --out ...):
+// the product library exports exactly what include/mpmb.h declares.
+#ifdef MPMB_DEBUG_EXPORTS
 // which: 0 run_begin 1 run_len 2 stay 3 arr_len 4 out_begin 5 total 6 arr_off   (dense, ntot ints)
 extern "C" int mpmb_debug_dense(MpmbHandle h, int which, int *out) {
   CHECK_HANDLE(h);
@@ -2118,6 +2121,7 @@ extern "C" int mpmb_debug_rows(MpmbHandle h, int n, uint32_t *keys, float *mass4
   if (counters8) CUDA_TRY(h, cudaMemcpy(counters8, h->cnt, sizeof(Counters), cudaMemcpyDeviceToHost));
   return MPMB_OK;
 }
+#endif  // MPMB_DEBUG_EXPORTS
 
 // ------------------------------------------------------------------------------ profiling
 int mpmb_set_profiling(MpmbHandle h, int32_t enabled) {
