@@ -26,6 +26,11 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), "libmpmb.so does not export %s" % name
     assert sorted(capi.EXPORTS) == declared
+    # ... and nothing else under the mpmb_ prefix (debug readers exist only in -DMPMB_DEBUG_EXPORTS builds)
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", path], stdout=subprocess.PIPE, text=True).stdout
+    exported = sorted(line.split()[-1] for line in out.splitlines() if line.split()[-1].startswith("mpmb_"))
+    assert exported == declared
 
 
 def test_version_and_struct_sizes():
