@@ -37,3 +37,35 @@ def test_engine_matches_reference_substeps(kind):
     if kind != scenes.MAT_WATER:
         assert np.abs(got["F"] - ref["F"]).max() <= 2e-4
     assert np.abs(got["ps"] - ref["ps"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("kind", G.KINDS)
+def test_engine_single_substep_matches_reference_transfers(kind):
+    """Per-substep grid momenta and particle state against the reference's transfer.cpp on identical inputs:
+    the node (momentum, mass) after mpmb_rasterize vs rasterize_optimized, and the particle state after
+    mpmb_resample vs resample_optimized (golden run; its G2P started from the oracle's node velocities)."""
+    from tests import common as T
+    from taichi_mpm_b200 import scenes
+    z = np.load(os.path.join(HERE, "golden", "transfer_ref.npz"))
+    scene, st = G.golden_scene(kind)
+    e = T.make_engine(scene, st)
+    e.sort_particles_and_populate_grid()
+    e.rasterize()
+    g0 = e.download_grid(0)
+    ref_grid = G.dense(z["k%d_opt_grid_idx" % kind], z["k%d_opt_grid_val" % kind])
+    pmax = max(np.abs(ref_grid[..., :3]).max(), ref_grid[..., 3].max())
+    assert np.abs(g0 - ref_grid).max() <= T.TOL_GRID_REL * pmax
+    m_ref = ref_grid[..., 3]
+    assert (g0[..., 3][m_ref > 1e-9 * m_ref.max()] > 0).all() and not g0[m_ref == 0].any()   # the same nodes are touched
+    e.resample()
+    got = e.download()
+    e.close()
+    ids = got["id"].astype(np.int64)
+    assert len(ids) == len(st["x"])
+    ref = {k: z["k%d_opt_%s" % (kind, k)][ids] for k in ("x", "v", "F", "b", "ps")}
+    assert np.abs(got["x"] - ref["x"]).max() <= 2 * T.TOL_X_ABS
+    assert np.abs(got["v"] - ref["v"]).max() <= 2 * T.TOL_V_REL * np.abs(ref["v"]).max()
+    assert np.abs(got["b"] - ref["b"]).max() <= 2 * T.TOL_V_REL * np.abs(ref["b"]).max()
+    if kind != scenes.MAT_WATER:
+        assert np.abs(got["F"] - ref["F"]).max() <= 2 * T.TOL_F_ABS
+    assert np.abs(got["ps"] - ref["ps"]).max() <= 2 * T.TOL_PS_ABS
