@@ -1,25 +1,37 @@
 // TEST INFRASTRUCTURE.  Stand-in for the headers of the (un-vendored) taichi-legacy core that the
-// reference's constitutive models include (src/particles.h:8-12, src/particles.cpp:6-8,
-// src/mpm_fwd.h:8-12).  With it the reference's OWN translation unit src/particles.cpp compiles where
-// it lies (oracle/particles_ref.cpp, `make -C oracle ref`), so that calculate_force() / plasticity()
-// of its Snow/Linear/Jelly/Water/Sand particles and friction_project() — the reference's lines,
-// unmodified — run here and pin the oracle's restatement of them.
+// reference's hot-path sources include (src/particles.h:8-12, src/mpm_fwd.h:8-12, src/mpm.h:15-22,
+// src/transfer.cpp:6-12, src/mpm.cpp:10-16).  With it the reference's OWN translation units compile
+// where they lie, unmodified (oracle/particles_ref.cpp, kernel_ref.cpp, transfer_ref.cpp; `make -C
+// oracle ref`), so that their lines — calculate_force() / plasticity(), friction_project(), the
+// interpolation kernels, the P2G / G2P loops, the grid update, ordering, deletion, substep() — run
+// here and pin the oracle's restatement of them.
 //
 // Restated here is the VOCABULARY only, with the meaning the call sites require:
-//   VectorND<n,T>   n scalars, element-wise + - * /, scalar broadcast, dot/sum/length/abs/map;
-//                   3- and 4-vectors of float are 16 bytes (they hold an __m128 in the core,
-//                   src/particles.h:80-82) — GridState's size assert needs it
+//   VectorND<n,T>   n scalars, element-wise + - * /, scalar broadcast, dot/sum/length/abs/map/min/max/
+//                   clamp/cast; 3- and 4-vectors of float are 16 bytes and expose `.v` (they hold an
+//                   __m128 in the core: src/particles.h:80-82, src/transfer.cpp:490,503,929,951) —
+//                   GridState's power-of-two size assert and the SSE loops need it
 //   MatrixND<n,T>   n columns, M[i] = column i (README.md:314); Matrix(s) = s*I, Matrix(v) = diag(v),
 //                   Matrix(c0,c1[,c2]) from columns; products, transpose(d), determinant, inverse,
 //                   diag/trace/frobenius_norm(2)/elementwise_product/sum
-//   svd(A,U,S,V)    A = U S V^T, U and V rotations, singular values descending in magnitude, the last
-//                   one negative when det A < 0 (the convention of the implicit-QR 3x3 SVDs graphics
-//                   codes use; the real core's convention cannot be checked, so tests compare only
-//                   what does not depend on it); polar_decomp(A,R,S): A = R S, R = U V^T
-//   Config          string -> number map with get(key, default) / has_key
-//   Unit, TC_* macros: registration / serialization / logging collapse to nothing.
-// Factorizations are computed in double and rounded, so that differences seen by the tests come from
-// the reference's formulas, not from this header's numerics.
+//   svd(A,U,S,V)    (math/svd.h) A = U S V^T, U and V rotations, singular values descending in
+//                   magnitude, the last one negative when det A < 0 (the convention of the implicit-QR
+//                   3x3 SVDs graphics codes use; the real core's convention cannot be checked, so tests
+//                   compare only what does not depend on it); polar_decomp(A,R,S): A = R S, R = U V^T;
+//                   computed in double and rounded, so that differences seen by the tests come from the
+//                   reference's formulas, not from this header's numerics
+//   IndexND/RegionND  integer index boxes iterated last-axis-fastest (the stencil order of
+//                   src/transfer.cpp:353-359)
+//   Config          string -> number map with get(key, default) / has_key; other value types are
+//                   accepted and dropped (the harness sets the solver's fields directly)
+//   Unit, TC_IMPLEMENTATION / create_instance_placement  a name -> placement-constructor registry for the
+//                   particle types (src/particle_allocator.h:62,71); the solver classes are not registered
+//   ThreadedTaskManager::run, tbb::parallel_for/sort (stub_more.h)  SERIAL loops / std::sort: a fixed
+//                   order for the pin, no threading claims
+//   TC_STATIC_IF    (common/meta.h) `if constexpr`
+//   logging / serialization / profiling macros collapse to nothing; textures, meshes, images, assets,
+//   rigid bodies (dynamics/rigid_body.h) and the level set (dynamics/simulation.h: half-spaces in grid
+//   units) exist so that the code naming them compiles — only the level set has behaviour.
 #pragma once
 #include <immintrin.h>
 
