@@ -270,29 +270,33 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "M particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    rb = reference_build_rate(sc, sample)
+    rb = reference_build_rate(sc, sample, fast.threads)
     if rb is not None:
         line["cpu_baseline"]["reference_build"] = rb
     emit(line)
 
 
-def reference_build_rate(sc, sample, n=60_000, substeps=3):
-    """The reference's OWN solver sources compiled in place (oracle/_ref/libtransfer_ref.so) on a
-    small sample, for the record next to the timed port.  It is the parity checker, not a tuned build: its core is
-    the stand-in one (serial task loops, double-precision SVD), so it is slower than the port and is not the
-    baseline the speed-up is quoted against."""
+def reference_build_rate(sc, sample, threads, n=400_000, substeps=3):
+    """The reference's OWN solver sources compiled in place (oracle/_ref/libtransfer_ref.so), timed on
+    a sample with the same number of threads as the port: MPM<3>::substep() itself, its 8-colour P2G and block-parallel
+    G2P running on the stand-in's OpenMP task loops.  It is the parity checker, not a tuned build (stand-in core:
+    double-precision SVD, generic matrix code), so it is slower than the port; the port stays the quoted baseline."""
     try:
         from oracle import pyoracle as O
         if not O.ref_transfer_available():
             return None
         small = {k: v[:n] for k, v in sample.items()}
         s = O.RefSolver(sc, small)
-        s.substep(1)
-        t0 = time.perf_counter()
-        alive = s.substep(substeps)
-        dt = time.perf_counter() - t0
-        s.close()
-        return {"value": alive * substeps / dt / 1e6, "unit": "M particle-updates/s", "cores": 1, "kind": "reference",
+        try:
+            s.set_threads(threads)
+            s.substep(1)
+            t0 = time.perf_counter()
+            alive = s.substep(substeps)
+            dt = time.perf_counter() - t0
+        finally:
+            s.set_threads(1)
+            s.close()
+        return {"value": alive * substeps / dt / 1e6, "unit": "M particle-updates/s", "cores": int(threads), "kind": "reference",
                 "sample": "%d particles, %d substeps of MPM<3>::substep()" % (len(small["x"]), substeps),
                 "note": "reference sources compiled in place against the stand-in core (checker build, not the baseline)"}
     except Exception as ex:  # the checker build is optional for the bench

@@ -410,16 +410,27 @@ class RefSolver:
         st = {k: np.ascontiguousarray(state[k], f32) for k in ("x", "v", "F", "b", "mass", "vol", "ps")}
         group = np.asarray(state.get("group", np.zeros(len(st["x"]), np.int32)), np.int64)
         self.n = len(st["x"])
-        for i in range(self.n):
-            g = int(group[i])
-            pid = L.reft_add_particle(self.h, C.c_int(int(kinds[g])), _p(prms[g]), _p(st["x"][i]), _p(st["v"][i]), C.c_float(st["mass"][i]),
-                                      C.c_float(st["vol"][i]), _p(st["F"][i]), _p(st["b"][i]), C.c_float(st["ps"][i]))
-            assert pid == i
+        L.reft_add_particles.restype = C.c_int64
+        if self.n and (group == group[0]).all():          # one material: bulk loader
+            g = int(group[0])
+            assert L.reft_add_particles(self.h, C.c_int(int(kinds[g])), _p(prms[g]), C.c_int64(self.n), _p(st["x"]), _p(st["v"]), _p(st["mass"]),
+                                        _p(st["vol"]), _p(st["F"]), _p(st["b"]), _p(st["ps"])) == self.n
+        else:
+            for i in range(self.n):
+                g = int(group[i])
+                pid = L.reft_add_particle(self.h, C.c_int(int(kinds[g])), _p(prms[g]), _p(st["x"][i]), _p(st["v"][i]), C.c_float(st["mass"][i]),
+                                          C.c_float(st["vol"][i]), _p(st["F"][i]), _p(st["b"][i]), C.c_float(st["ps"][i]))
+                assert pid == i
         if scene.get("planes") is not None:      # grid units, (n, d) per plane — what scenes.planes_sdf rasterises
             pl = np.ascontiguousarray(scene["planes"], f32).reshape(-1, 4)
             L.reft_set_planes(self.h, C.c_int(len(pl)), _p(pl), C.c_float(scene.get("friction", 0.0)))
 
+    def set_threads(self, n):
+        """Threads of the stand-in's parallel loops; 1 (default) = serial, what every pin runs with."""
+        self.L.reft_set_threads(self.h, C.c_int(int(n)))
+
     def p2g(self, optimized=True):
+        """Ordering + P2G.  g2p() must follow a p2g() of the same particle positions (it reads that ordering)."""
         self.L.reft_p2g(self.h, C.c_int(int(optimized)))
 
     def grid_update(self):

@@ -7,6 +7,10 @@
 #include <fstream>
 #include <mutex>
 #include <numeric>
+#if defined(_OPENMP)
+#include <omp.h>
+#include <parallel/algorithm>
+#endif
 namespace taichi {
 struct Texture {
   template <int d> VectorND<4, real> sample(const VectorND<d, real> &) const { return VectorND<4, real>(0.0f); }
@@ -51,7 +55,19 @@ template <class T> inline std::unique_ptr<T> create_instance_unique(const std::s
 }  // namespace taichi
 
 namespace tbb {
-template <class I, class F> inline void parallel_for(I b, I e, const F &f) { for (I i = b; i < e; i++) f(i); }
-template <class It> inline void parallel_sort(It b, It e) { std::sort(b, e); }
+template <class I, class F> inline void parallel_for(I b, I e, const F &f) {
+  const int nt = taichi::stub_num_threads();
+  if (nt <= 1) { for (I i = b; i < e; i++) f(i); return; }
+#if defined(_OPENMP)
+#pragma omp parallel for num_threads(nt) schedule(static)
+#endif
+  for (I i = b; i < e; i++) f(i);
+}
+template <class It> inline void parallel_sort(It b, It e) {
+#if defined(_OPENMP) && defined(_GLIBCXX_PARALLEL_ALGORITHM_H)
+  if (taichi::stub_num_threads() > 1) { __gnu_parallel::sort(b, e); return; }
+#endif
+  std::sort(b, e);
+}
 }  // namespace tbb
 #define TC_LOAD_CONFIG(name, default_val) this->name = config.get(#name, default_val)

@@ -26,8 +26,9 @@
 //                   accepted and dropped (the harness sets the solver's fields directly)
 //   Unit, TC_IMPLEMENTATION / create_instance_placement  a name -> placement-constructor registry for the
 //                   particle types (src/particle_allocator.h:62,71); the solver classes are not registered
-//   ThreadedTaskManager::run, tbb::parallel_for/sort (stub_more.h)  SERIAL loops / std::sort: a fixed
-//                   order for the pin, no threading claims
+//   ThreadedTaskManager::run, tbb::parallel_for/sort (stub_more.h)  serial loops / std::sort by default
+//                   (a fixed order: every pin runs this way); OpenMP loops only when a harness raises
+//                   stub_num_threads() to TIME the reference's loops
 //   TC_STATIC_IF    (common/meta.h) `if constexpr`
 //   logging / serialization / profiling macros collapse to nothing; textures, meshes, images, assets,
 //   rigid bodies (dynamics/rigid_body.h) and the level set (dynamics/simulation.h: half-spaces in grid
@@ -157,8 +158,18 @@ class Config {
   std::string get_string(const std::string &) const { return ""; }
 };
 
-struct ThreadedTaskManager {  // parallel for i in [0, n) (src/mpm.h:218-219): serial here, the pin wants a fixed order
-  template <class F> static void run(int n, int, const F &f) { for (int i = 0; i < n; i++) f(i); }
+// number of threads the stand-in's parallel loops use: 1 (the default) = plain serial loops in index order, which
+// is what the pin tests run; > 1 only when a harness asks for it to TIME the reference's loops
+inline int &stub_num_threads() { static int n = 1; return n; }
+struct ThreadedTaskManager {  // parallel for i in [0, n) (src/mpm.h:218-219)
+  template <class F> static void run(int n, int num_threads, const F &f) {
+    const int nt = std::min(num_threads, stub_num_threads());
+    if (nt <= 1) { for (int i = 0; i < n; i++) f(i); return; }
+#if defined(_OPENMP)
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 8)
+#endif
+    for (int i = 0; i < n; i++) f(i);
+  }
 };
 
 class Unit {

@@ -143,6 +143,17 @@ void *reft_create(const int *res, float dx, float dt, const float *gravity, int 
   return h;
 }
 void reft_destroy(void *hp) { delete static_cast<Harness *>(hp); }
+// threads for the stand-in's parallel loops (ThreadedTaskManager / tbb): 1 = serial (the pins); more only to time
+void reft_set_threads(void *hp, int n) {
+  static_cast<Harness *>(hp)->m.num_threads = n < 1 ? 1 : n;
+  stub_num_threads() = n < 1 ? 1 : n;
+#if defined(_OPENMP)
+  omp_set_num_threads(n < 1 ? 1 : n);
+#endif
+}
+// bulk loader: n particles of one kind (same arguments as reft_add_particle, arrays)
+int64_t reft_add_particles(void *hp, int kind, const float *params, int64_t n, const float *x, const float *v, const float *mass,
+                           const float *vol, const float *F, const float *b, const float *ps);
 
 // kind / params: the oracle's numbering and parameter vectors.  Returns the particle's id.
 int reft_add_particle(void *hp, int kind, const float *params, const float *x, const float *v, float mass, float vol, const float *F,
@@ -178,6 +189,13 @@ int reft_add_particle(void *hp, int kind, const float *params, const float *x, c
   h->m.particles.push_back(alloc.first);
   h->kind.push_back(kind);
   return (int)p->id;
+}
+
+int64_t reft_add_particles(void *hp, int kind, const float *params, int64_t n, const float *x, const float *v, const float *mass,
+                           const float *vol, const float *F, const float *b, const float *ps) {
+  for (int64_t i = 0; i < n; i++)
+    if (reft_add_particle(hp, kind, params, x + 3 * i, v + 3 * i, mass[i], vol[i], F + 9 * i, b + 9 * i, ps[i]) < 0) return -1;
+  return n;
 }
 
 // P2G of one substep: ordering + cleared fat blocks, then rasterize(dt) (scalar, src/transfer.cpp:193-278)
