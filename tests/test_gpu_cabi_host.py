@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.needs_cuda]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 

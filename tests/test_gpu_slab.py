@@ -7,6 +7,17 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+SIMT = os.environ.get("MPMB_SIMT", "") == "1"   # the SIMT emulator build: device memory is host memory, no torch CUDA
+
+
+class _HostBuf:
+    """numpy-backed stand-in for a torch CUDA byte tensor (emulator runs)"""
+
+    def __init__(self, n):
+        self.a = np.zeros(n, np.uint8)
+
+    def data_ptr(self):
+        return self.a.ctypes.data
 
 
 def _scene():
@@ -69,6 +80,7 @@ def _free_port():
     return p
 
 
+@pytest.mark.needs_cuda
 def test_two_slabs_match_single_gpu(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
@@ -106,19 +118,21 @@ def test_two_slabs_match_single_gpu(tmp_path):
 def _run_two_slabs_one_process(scene, st, nsub, device=0):
     """Both slabs of a 2-rank run in ONE process on one GPU (no NCCL): the exchange buffers are
     copied engine to engine.  Exercises halo ghost tiles and migration with the default 1-GPU suite."""
-    import torch
+    if not SIMT:
+        import torch
     from taichi_mpm_b200 import capi, slab
     world = 2
     tz = slab.base_tile_z(st["x"][:, 2], scene["dx"])
     cuts = slab.slab_partition(tz, slab.tile_layers(scene["res"][2]), world)
     counts = [int(((tz >= a) & (tz < b)).sum()) for a, b in cuts]
     engines, adapters, bufs = [], [], []
-    dev = torch.device("cuda", device)
+    dev = None if SIMT else torch.device("cuda", device)
     for rank in range(world):
         z0, z1 = cuts[rank]
         e = capi.Engine(scene["res"], scene["dx"], scene["dt"], scene["gravity"], 1, True, device=device, rank=rank, world=world,
                         tile_z0=z0, tile_z1=z1, migrate_capacity=4096, halo_capacity=64)
-        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        if not SIMT:
+            e.set_stream(torch.cuda.current_stream().cuda_stream)
         e.set_material(0, int(scene["mat_kind"][0]), scene["mat_params"][0])
         e.set_planes(scene["planes"], scene["friction"])
         e.set_id_base(sum(counts[:rank]))
@@ -126,7 +140,7 @@ def _run_two_slabs_one_process(scene, st, nsub, device=0):
         e.upload(*(st[k][mine] for k in ("x", "v", "mass", "vol", "F", "b", "ps", "group")))
         engines.append(e)
         adapters.append(slab.EngineAdapter(e))
-        mk = lambda n: torch.zeros(max(int(n), 16), dtype=torch.uint8, device=dev)
+        mk = (lambda n: _HostBuf(max(int(n), 16))) if SIMT else (lambda n: torch.zeros(max(int(n), 16), dtype=torch.uint8, device=dev))
         bufs.append(dict(halo=[mk(e.halo_bytes()), mk(e.halo_bytes())], mig=[mk(e.migrate_bytes()), mk(e.migrate_bytes())]))
     a0, a1 = adapters
     for _ in range(nsub):
@@ -140,7 +154,8 @@ def _run_two_slabs_one_process(scene, st, nsub, device=0):
             a.resample_part(1)
         a0.migrate_pack(1, bufs[0]["mig"][1]); a1.migrate_pack(0, bufs[1]["mig"][0])
         a1.migrate_unpack(0, bufs[0]["mig"][1]); a0.migrate_unpack(1, bufs[1]["mig"][0])
-    torch.cuda.synchronize()
+    if not SIMT:
+        torch.cuda.synchronize()
     order = np.concatenate([np.nonzero((tz >= a) & (tz < b))[0] for a, b in cuts])
     parts = []
     for e in engines:
@@ -176,7 +191,6 @@ def test_two_slabs_on_one_gpu_match_single_run():
 def test_two_slabs_peer_memory_exchange_one_gpu():
     """Same two slabs, but the exchange runs through the engine's peer-memory path (pack kernels write
     into the other engine's receive buffer, seq flag, wait kernel) instead of host-moved buffers."""
-    import torch
     from taichi_mpm_b200 import capi, slab
     from tests import common as T
     scene, st = _scene()
@@ -260,6 +274,7 @@ def _peer_worker(rank, world, port, nsub, out_path):
     dist.destroy_process_group()
 
 
+@pytest.mark.needs_cuda
 def test_two_ranks_peer_memory_exchange(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:

@@ -5,7 +5,7 @@ same upload are bit-identical (no atomics on floats anywhere)."""
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.needs_cuda]
 
 
 def test_config3_full_size_invariants():

@@ -1,0 +1,45 @@
+"""The engine's CUDA source on a CPU: tests/simt compiles taichi_mpm_b200/csrc/mpmb_engine.cu (kernels, device math
+AND the C-ABI host code; only kernel launches and inline PTX are rewritten, see tests/simt/build_simt.py) on top of
+a small SIMT emulator — CUDA threads as coroutines, real __syncthreads / warp-collective rendezvous, shared memory,
+atomics, cp.async as plain copies.  The gpu-marked parity tests then run against that library through the same
+ctypes binding (MPMB_SIMT=1).  This checks kernel LOGIC (indexing, barriers, orderings, host orchestration), not
+codegen, timing or memory-model races: the `-m gpu` run on a B200 stays the parity gate; this run means a logic
+error is caught in the CPU suite, and build-time kernel experiments can be debugged without GPU minutes:
+
+    MPMB_SIMT=1 MPMB_SIMT_DEFINES=MPMB_EXP_P2G_IPLANE python -m pytest tests -m gpu -q
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra_env, args):
+    env = dict(os.environ, MPMB_SIMT="1", **extra_env)
+    env.pop("MPMB_LIB", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + args, cwd=ROOT, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    tail = "\n".join(r.stdout.strip().splitlines()[-15:])
+    assert r.returncode == 0, tail
+    return tail
+
+
+def test_gpu_parity_suite_passes_on_the_simt_emulator():
+    # everything that does not need a real device, minus the two longest multi-step runs (they pass too: ~1 min more)
+    tail = _run({}, ["tests/test_gpu_parity.py", "tests/test_gpu_zz_reference_golden.py", "tests/test_gpu_mpm_mirror.py",
+                     "tests/test_gpu_zz_frame_io.py", "-k", "not many_movers and not multi_step_invariants"])
+    assert " passed" in tail and "failed" not in tail
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("defines", ["MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE", "MPMB_EXP_DUAL_ARENA"])
+def test_build_time_kernel_experiments_pass_parity_on_the_simt_emulator(defines):
+    # the off-by-default kernel variants are at least LOGICALLY right: single-substep parity, the
+    # reference's golden 10-substep run, deletion, multi-chunk tiles
+    tail = _run({"MPMB_SIMT_DEFINES": defines},
+                ["tests/test_gpu_zz_reference_golden.py", "tests/test_gpu_parity.py", "-k",
+                 "single_substep or reference or deletion or dense_tiles or two_materials"])
+    assert " passed" in tail and "failed" not in tail
