@@ -242,6 +242,76 @@ def test_two_slabs_peer_memory_exchange_one_gpu():
         assert np.abs(got - ref[k]).max() <= tol * scale, k
 
 
+def test_four_slabs_peer_memory_exchange_one_process():
+    """Four slabs in one process on one device: the two middle ranks exchange halos and migrating particles with BOTH
+    neighbours every substep (the topology of the 4- and 8-GPU runs), through the peer-memory path."""
+    from taichi_mpm_b200 import capi, slab
+    from tests import common as T
+    scene, st = _scene()
+    nsub, world = 25, 4
+    tz = slab.base_tile_z(st["x"][:, 2], scene["dx"])
+    cuts = slab.slab_partition(tz, slab.tile_layers(scene["res"][2]), world)
+    counts = [int(((tz >= a) & (tz < b)).sum()) for a, b in cuts]
+    assert min(counts) > 0
+    eng = []
+    for rank in range(world):
+        z0, z1 = cuts[rank]
+        e = capi.Engine(scene["res"], scene["dx"], scene["dt"], scene["gravity"], 1, True, device=0, rank=rank, world=world,
+                        tile_z0=z0, tile_z1=z1, migrate_capacity=4096, halo_capacity=64)
+        e.set_material(0, int(scene["mat_kind"][0]), scene["mat_params"][0])
+        e.set_planes(scene["planes"], scene["friction"])
+        e.set_id_base(sum(counts[:rank]))
+        mine = np.nonzero((tz >= z0) & (tz < z1))[0]
+        e.upload(*(st[k][mine] for k in ("x", "v", "mass", "vol", "F", "b", "ps", "group")))
+        eng.append(e)
+    for r in range(world - 1):                      # my face 1 -> upper neighbour's face-0 buffer, and back
+        for k in (0, 1):
+            eng[r].xchg_connect(k, 1, ptr=eng[r + 1].xchg_buffer(k, 0))
+            eng[r + 1].xchg_connect(k, 0, ptr=eng[r].xchg_buffer(k, 1))
+    faces = [[f for f in (0, 1) if 0 <= r + (1 if f else -1) < world] for r in range(world)]
+    for _ in range(nsub):                           # one stream, one process: every wait finds its flag already published
+        for e in eng:
+            e.sort_particles_and_populate_grid(); e.rasterize()
+        for r, e in enumerate(eng):
+            for f in faces[r]:
+                e.halo_send(f)
+        for r, e in enumerate(eng):
+            for f in faces[r]:
+                e.halo_recv(f)
+        for e in eng:
+            e.resample()
+        for r, e in enumerate(eng):
+            for f in faces[r]:
+                e.migrate_send(f)
+        for r, e in enumerate(eng):
+            for f in faces[r]:
+                e.migrate_recv(f)
+    order = np.concatenate([np.nonzero((tz >= a) & (tz < b))[0] for a, b in cuts])
+    parts = []
+    for e in eng:
+        g = e.download()
+        g["gid"] = order[g["id"].astype(np.int64)]
+        parts.append(g)
+        e.close()
+    ref_e = T.make_engine(scene, st)
+    ref_e.substep(nsub)
+    ref = ref_e.download()
+    ref_e.close()
+    gid = np.concatenate([p["gid"] for p in parts])
+    o = np.argsort(gid)
+    assert np.array_equal(gid[o], ref["id"].astype(np.int64))
+    for k, tol in (("x", 2e-6), ("v", 5e-4), ("F", 5e-5)):
+        got = np.concatenate([p[k] for p in parts])[o]
+        scale = max(np.abs(ref[k]).max(), 1e-30) if k == "v" else 1.0
+        assert np.abs(got - ref[k]).max() <= tol * scale, k
+    # the middle ranks really traded particles with both neighbours
+    start = [set(np.nonzero((tz >= a) & (tz < b))[0].tolist()) for a, b in cuts]
+    for r in (1, 2):
+        now = set(parts[r]["gid"].tolist())
+        came = now - start[r]
+        assert came & start[r - 1] and came & start[r + 1], "rank %d did not receive from both sides" % r
+
+
 def _peer_worker(rank, world, port, nsub, out_path):
     import torch
     import torch.distributed as dist
