@@ -12,6 +12,16 @@ long long g_clock = 0;
 static const size_t kStack = 256 * 1024;
 static std::vector<char *> g_stacks;
 
+// MPMB_SIMT_ORDER: 0 = CTAs and threads in index order (default), 1 = both reversed, 2 = CTAs in a pseudo-random
+// order (different per launch) and threads reversed on odd launches.  A kernel whose result depends on which CTA or
+// thread runs first — an inter-CTA race, an unordered reduction — gives different bits under different orders.
+static int sched_order() {
+  static int o = -1;
+  if (o < 0) { const char *e = getenv("MPMB_SIMT_ORDER"); o = e ? atoi(e) : 0; }
+  return o;
+}
+static unsigned long long g_launch_no = 0;
+
 static void trampoline() {
   Block *b = g_blk;
   b->body();
@@ -41,7 +51,17 @@ void run(unsigned grid, unsigned block, const std::function<void()> &body) {
   g_gridDim = dim3(grid);
   Block *prev = g_blk;
   g_blk = &blk;
-  for (unsigned bid = 0; bid < grid; bid++) {
+  const int order = sched_order();
+  const unsigned long long launch = g_launch_no++;
+  std::vector<unsigned> bids(grid);
+  for (unsigned i = 0; i < grid; i++) bids[i] = order == 1 ? grid - 1 - i : i;
+  if (order == 2) {  // Fisher-Yates with a per-launch LCG
+    unsigned long long st = 0x9E3779B97F4A7C15ull * (launch + 1);
+    for (unsigned i = grid; i > 1; i--) { st = st * 6364136223846793005ull + 1442695040888963407ull; std::swap(bids[i - 1], bids[(st >> 33) % i]); }
+  }
+  const bool rev_threads = order == 1 || (order == 2 && (launch & 1));
+  for (unsigned bi = 0; bi < grid; bi++) {
+    const unsigned bid = bids[bi];
     g_blockIdx.x = bid; g_blockIdx.y = g_blockIdx.z = 0;
     blk.at_barrier = blk.done = 0;
     for (auto &w : blk.warps) { w.phase = 0; w.arrived = w.released = 0; w.exited = 0; }
@@ -59,7 +79,8 @@ void run(unsigned grid, unsigned block, const std::function<void()> &body) {
     unsigned long long rounds_without_progress = 0;
     while (blk.done < block) {
       unsigned progressed = 0;
-      for (unsigned t = 0; t < block; t++) {
+      for (unsigned tt = 0; tt < block; tt++) {
+        const unsigned t = rev_threads ? block - 1 - tt : tt;
         Thread &th = blk.th[t];
         if (th.state != 0) continue;
         blk.cur = (int)t;

@@ -43,3 +43,39 @@ def test_build_time_kernel_experiments_pass_parity_on_the_simt_emulator(defines)
                 ["tests/test_gpu_zz_reference_golden.py", "tests/test_gpu_parity.py", "-k",
                  "single_substep or reference or deletion or dense_tiles or two_materials"])
     assert " passed" in tail and "failed" not in tail
+
+
+_ORDER_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np
+from tests.simt import build_simt
+defines = [d for d in os.environ.get("MPMB_SIMT_DEFINES", "").split(",") if d]
+os.environ["MPMB_LIB"] = build_simt.build(defines)
+from tests import common as T
+from tests.test_gpu_slab import _scene
+scene, st = _scene()           # fast motion: dozens of particles change tile every substep
+e = T.make_engine(scene, st)
+e.substep(10)
+d = e.download()
+e.close()
+np.savez(sys.argv[1], **d)
+"""
+
+
+@pytest.mark.parametrize("defines", ["", "MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE"])
+def test_results_do_not_depend_on_cta_or_thread_scheduling_order(tmp_path, defines):
+    # the emulator runs CTAs and threads in index order, reversed, or pseudo-randomly shuffled per launch
+    # (MPMB_SIMT_ORDER): a result that depended on who runs first — an inter-CTA race such as two CTAs writing one
+    # outpos entry, an unordered float reduction — would change bits.  The engine claims bit-reproducibility.
+    import numpy as np
+    outs = []
+    for order in ("0", "1", "2"):
+        out = str(tmp_path / ("order%s.npz" % order))
+        env = dict(os.environ, MPMB_SIMT="1", MPMB_SIMT_ORDER=order, MPMB_SIMT_DEFINES=defines)
+        env.pop("MPMB_LIB", None)
+        r = subprocess.run([sys.executable, "-c", _ORDER_SCRIPT % ROOT, out], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-2000:]
+        outs.append(np.load(out))
+    for k in outs[0].files:
+        assert np.array_equal(outs[0][k], outs[1][k]) and np.array_equal(outs[0][k], outs[2][k]), k
