@@ -63,7 +63,7 @@ np.savez(sys.argv[1], **d)
 """
 
 
-@pytest.mark.parametrize("defines", ["", "MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE"])
+@pytest.mark.parametrize("defines", ["", "MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE", "MPMB_EXP_DUAL_ARENA"])
 def test_results_do_not_depend_on_cta_or_thread_scheduling_order(tmp_path, defines):
     # the emulator runs CTAs and threads in index order, reversed, or pseudo-randomly shuffled per launch
     # (MPMB_SIMT_ORDER): a result that depended on who runs first — an inter-CTA race such as two CTAs writing one
