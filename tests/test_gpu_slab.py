@@ -242,13 +242,25 @@ def test_two_slabs_peer_memory_exchange_one_gpu():
         assert np.abs(got - ref[k]).max() <= tol * scale, k
 
 
-def test_four_slabs_peer_memory_exchange_one_process():
-    """Four slabs in one process on one device: the two middle ranks exchange halos and migrating particles with BOTH
-    neighbours every substep (the topology of the 4- and 8-GPU runs), through the peer-memory path."""
+def _long_scene():
+    """The same kind of block, four times longer in z (25 tile layers): room for eight slabs."""
+    from taichi_mpm_b200 import scenes
+    res = (32, 32, 128)
+    dx = 1.0 / 32
+    x, mass, vol = scenes.lattice_block(32, (12, 9, 14), (20, 15, 114), jitter=0.2, seed=7)
+    st = scenes.make_state(x, mass, vol, scenes.MAT_SAND)
+    rng = np.random.default_rng(8)
+    n = len(x)
+    vz = np.where(x[:, 0] < 0.5, 2.5, -2.5)
+    st["v"] = np.stack([0.3 * rng.normal(size=n), 0.3 * rng.normal(size=n), vz + 0.2 * rng.normal(size=n)], 1).astype(np.float32)
+    scene = dict(res=res, dx=dx, dt=1e-4, gravity=(0.0, -10.0, 0.0), particle_gravity=1, mat_kind=np.array([scenes.MAT_SAND], np.int32),
+                 mat_params=scenes.material_params(scenes.MAT_SAND)[None], planes=np.array([[0.0, 1.0, 0.0, -9.6]], np.float32), friction=0.4)
+    return scene, st
+
+
+def _run_slabs_peer_one_process(scene, st, world, nsub):
     from taichi_mpm_b200 import capi, slab
     from tests import common as T
-    scene, st = _scene()
-    nsub, world = 25, 4
     tz = slab.base_tile_z(st["x"][:, 2], scene["dx"])
     cuts = slab.slab_partition(tz, slab.tile_layers(scene["res"][2]), world)
     counts = [int(((tz >= a) & (tz < b)).sum()) for a, b in cuts]
@@ -304,12 +316,24 @@ def test_four_slabs_peer_memory_exchange_one_process():
         got = np.concatenate([p[k] for p in parts])[o]
         scale = max(np.abs(ref[k]).max(), 1e-30) if k == "v" else 1.0
         assert np.abs(got - ref[k]).max() <= tol * scale, k
-    # the middle ranks really traded particles with both neighbours
+    # every interior rank really traded particles with both neighbours
     start = [set(np.nonzero((tz >= a) & (tz < b))[0].tolist()) for a, b in cuts]
-    for r in (1, 2):
-        now = set(parts[r]["gid"].tolist())
-        came = now - start[r]
+    for r in range(1, world - 1):
+        came = set(parts[r]["gid"].tolist()) - start[r]
         assert came & start[r - 1] and came & start[r + 1], "rank %d did not receive from both sides" % r
+
+
+def test_four_slabs_peer_memory_exchange_one_process():
+    """Four slabs in one process on one device: the two middle ranks exchange halos and migrating particles with BOTH
+    neighbours every substep (the topology of the 4- and 8-GPU runs), through the peer-memory path."""
+    scene, st = _scene()
+    _run_slabs_peer_one_process(scene, st, world=4, nsub=25)
+
+
+def test_eight_slabs_peer_memory_exchange_one_process():
+    """Eight slabs (the 8-GPU topology: id bases, cuts, six interior ranks) on a four times longer block."""
+    scene, st = _long_scene()
+    _run_slabs_peer_one_process(scene, st, world=8, nsub=15)
 
 
 def _peer_worker(rank, world, port, nsub, out_path):
