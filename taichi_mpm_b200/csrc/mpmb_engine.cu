@@ -80,6 +80,8 @@ struct TileMeta {  // one 32-byte record per active tile (slot)
 //   MPMB_EXP_DUAL_ARENA  k_p2g: one shared arena per warp, both warps flush their registers at the
 //                        same time and the store sums the two (the warp-after-warp flush holds 11.9 %
 //                        of k_p2g's stall samples).
+//   MPMB_EXP_SDF_FLAGS   k_grid reads the level set only for tiles whose node footprint touches the band
+//                        -3 <= phi <= 0 (a byte per tile, computed when the level set is set).
 //   MPMB_EXP_P2G_IPLANE  k_p2g with three threads per cell (one per stencil x-plane): 36 accumulators and
 //                        95 registers instead of 108 / 248, 18 warps per SM instead of 8 (k_p2g issues
 //                        on 45 % of its cycles at 8 warps).  Replaces the 64-thread kernel when defined.
@@ -930,7 +932,7 @@ __device__ __forceinline__ float4 gather_node(const float4 *arena, int zero_slot
 
 // normalize_grid_and_apply_external_force (src/mpm.cpp:277-294) + apply_grid_boundary_conditions
 // (src/mpm.cpp:296-372, static level set) for one node.
-__device__ __forceinline__ float4 node_update(const Params &P, const float4 *sdf4, float4 g, int gx, int gy, int gz) {
+__device__ __forceinline__ float4 node_update(const Params &P, const float4 *sdf4, float4 g, int gx, int gy, int gz, bool use_sdf = true) {
   float m = g.w;
   if (m > 0.f) {
     float inv = 1.0f / m;
@@ -939,7 +941,7 @@ __device__ __forceinline__ float4 node_update(const Params &P, const float4 *sdf
     g.y = fmaf(g.y, inv, iy);
     g.z = fmaf(g.z, inv, iz);
   }
-  if (P.has_sdf && m != 0.f && gx < P.nnode[0] && gy < P.nnode[1] && gz < P.nnode[2]) {
+  if (P.has_sdf && use_sdf && m != 0.f && gx < P.nnode[0] && gy < P.nnode[1] && gz < P.nnode[2]) {
     float4 s = sdf4[((size_t)gx * P.nnode[1] + gy) * P.nnode[2] + gz];
     if (!(s.w < -3.0f || 0.0f < s.w)) {
       float3 v = friction_project0(make_float3(g.x, g.y, g.z), make_float3(s.x, s.y, s.z), P.friction);
@@ -955,7 +957,29 @@ __device__ __forceinline__ float4 node_update(const Params &P, const float4 *sdf
 // rebuilt (fixed-order sum of the covering arenas), normalised, projected on the level set and
 // stored as one contiguous 3.4 KB block vel[slot][216].  Node-parallel, so the dependent
 // slot_map -> arena -> sdf loads are hidden by occupancy instead of stalling a G2P CTA.
+#ifdef MPMB_EXP_SDF_FLAGS
+// EXPERIMENT: one byte per tile = "some node of the tile's 6x6x6 footprint has -3 <= phi <= 0", computed when the
+// level set is set.  k_grid then reads the level set only for those tiles (at config 3: the bottom tile layers of
+// the column), which removes 16 B/node of reads and one dependent load from every other node.  Same results.
+__global__ void k_tile_sdf_flags(Params P, const float4 *sdf4, unsigned char *flags, int ntot) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += gridDim.x * blockDim.x) {
+    const int tz = t % P.nt[2], ty = (t / P.nt[2]) % P.nt[1], tx = t / (P.nt[2] * P.nt[1]);
+    bool near = false;
+    for (int a = 0; a < 6 && !near; a++)
+      for (int b = 0; b < 6 && !near; b++)
+        for (int c = 0; c < 6; c++) {
+          const int gx = tx * 4 + a, gy = ty * 4 + b, gz = tz * 4 + c;
+          if (gx >= P.nnode[0] || gy >= P.nnode[1] || gz >= P.nnode[2]) continue;
+          const float phi = sdf4[((size_t)gx * P.nnode[1] + gy) * P.nnode[2] + gz].w;
+          if (!(phi < -3.0f || 0.0f < phi)) { near = true; break; }
+        }
+    flags[t] = near ? 1 : 0;
+  }
+}
+__global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int part, const unsigned char *tile_near) {
+#else
 __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int part) {
+#endif
   // one WARP per tile: the 27 neighbour slots live in lanes 0..26 and are fetched with shuffles, so
   // there is no block barrier and every warp of the grid has its own tile in flight
   const int lane = threadIdx.x & 31;
@@ -989,7 +1013,11 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int
         sl[o] = __shfl_sync(0xffffffffu, my_nb, (wx_ - ox + 1) * 9 + (wy_ - oy + 1) * 3 + (wz_ - oz + 1));
       }
       float4 g = gather_node(V.arena, V.cap_tiles, lx, ly, lz, [&](int ox, int oy, int oz) { return sl[ox * 4 + oy * 2 + oz]; });
+#ifdef MPMB_EXP_SDF_FLAGS
+      g = node_update(P, V.sdf4, g, tx * 4 + a, ty * 4 + b, tz * 4 + c, P.has_sdf && tile_near[tile] != 0);  // no level set: no flag array
+#else
       g = node_update(P, V.sdf4, g, tx * 4 + a, ty * 4 + b, tz * 4 + c);
+#endif
       if (n0 + lane < ARENA) vel[(size_t)slot * ARENA + n] = g;
     }
   }
@@ -1360,6 +1388,9 @@ struct MpmbEngine {
   float4 *arena = nullptr;
   float4 *vel = nullptr;  // node velocities per active tile (k_grid -> k_g2p)
   float4 *sdf4 = nullptr;
+#ifdef MPMB_EXP_SDF_FLAGS
+  unsigned char *tile_near = nullptr;  // [ntot] tiles whose node footprint touches the level-set band
+#endif
   Counters *cnt = nullptr;
 
   int stage = 0;  // 0 idle/after resample, 1 after sort, 2 after rasterize
@@ -1636,6 +1667,9 @@ int mpmb_destroy(MpmbHandle h) {
   cudaFree(h->arr_cnt); cudaFree(h->arr_off); cudaFree(h->arr_len); cudaFree(h->arr_cur); cudaFree(h->slot_map); cudaFree(h->blocksum);
   cudaFree(h->meta);
   cudaFree(h->arena); cudaFree(h->vel); cudaFree(h->sdf4); cudaFree(h->cnt); cudaFree(h->stage_buf); cudaFree(h->xcount);
+#ifdef MPMB_EXP_SDF_FLAGS
+  cudaFree(h->tile_near);
+#endif
   for (int k = 0; k < 2; k++)
     for (int f = 0; f < 2; f++) {
       if (h->tx_ipc[k][f] && h->tx[k][f]) cudaIpcCloseMemHandle(h->tx[k][f]);
@@ -1691,6 +1725,11 @@ int mpmb_set_sdf(MpmbHandle h, const float *sdf4, float friction) {
   }
   if (!h->sdf4) CUDA_TRY(h, cudaMalloc(&h->sdf4, sizeof(float4) * n));
   CUDA_TRY(h, cudaMemcpyAsync(h->sdf4, sdf4, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+#ifdef MPMB_EXP_SDF_FLAGS
+  if (!h->tile_near) CUDA_TRY(h, cudaMalloc(&h->tile_near, (size_t)h->ntot));
+  k_tile_sdf_flags<<<h->num_sms * 8, 256, 0, h->stream>>>(h->P, h->sdf4, h->tile_near, h->ntot);
+  h->launches++;
+#endif
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->P.has_sdf = 1;
   h->P.friction = friction;
@@ -1707,6 +1746,11 @@ int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float 
   CUDA_TRY(h, cudaMemcpyAsync(d_planes, planes4, sizeof(float4) * n_planes, cudaMemcpyHostToDevice, h->stream));
   k_planes_to_sdf<<<h->num_sms * 8, 256, 0, h->stream>>>(h->P, n_planes, d_planes, h->sdf4);
   h->launches++;
+#ifdef MPMB_EXP_SDF_FLAGS
+  if (!h->tile_near) CUDA_TRY(h, cudaMalloc(&h->tile_near, (size_t)h->ntot));
+  k_tile_sdf_flags<<<h->num_sms * 8, 256, 0, h->stream>>>(h->P, h->sdf4, h->tile_near, h->ntot);
+  h->launches++;
+#endif
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   cudaFree(d_planes);
   h->P.has_sdf = 1;
@@ -1992,7 +2036,11 @@ int mpmb_resample(MpmbHandle h) {
   prof_begin(h, 2);
   View V = make_view(h);
   if (h->cap > 0) {
+#ifdef MPMB_EXP_SDF_FLAGS
+    k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, 0, h->tile_near);
+#else
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, 0);
+#endif
     if (h->skip_b) k_g2p<128, false><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
     else k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
     k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt);
@@ -2038,7 +2086,11 @@ int mpmb_resample_part(MpmbHandle h, int32_t part) {
   View V = make_view(h);
   int nl = 2;
   if (h->cap > 0) {
+#ifdef MPMB_EXP_SDF_FLAGS
+    k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, part, h->tile_near);
+#else
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, part);
+#endif
     k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part);
     if (part == 1) { k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt); nl++; }
   }

@@ -35,7 +35,7 @@ def test_gpu_parity_suite_passes_on_the_simt_emulator():
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("defines", ["MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE", "MPMB_EXP_DUAL_ARENA"])
+@pytest.mark.parametrize("defines", ["MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE,MPMB_EXP_SDF_FLAGS", "MPMB_EXP_DUAL_ARENA"])
 def test_build_time_kernel_experiments_pass_parity_on_the_simt_emulator(defines):
     # the off-by-default kernel variants are at least LOGICALLY right: single-substep parity, the
     # reference's golden 10-substep run, deletion, multi-chunk tiles
@@ -63,7 +63,7 @@ np.savez(sys.argv[1], **d)
 """
 
 
-@pytest.mark.parametrize("defines", ["", "MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE", "MPMB_EXP_DUAL_ARENA"])
+@pytest.mark.parametrize("defines", ["", "MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE,MPMB_EXP_SDF_FLAGS", "MPMB_EXP_DUAL_ARENA"])
 def test_results_do_not_depend_on_cta_or_thread_scheduling_order(tmp_path, defines):
     # the emulator runs CTAs and threads in index order, reversed, or pseudo-randomly shuffled per launch
     # (MPMB_SIMT_ORDER): a result that depended on who runs first — an inter-CTA race such as two CTAs writing one
