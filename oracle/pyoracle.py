@@ -497,3 +497,23 @@ def ref_transfer_substep(scene, state, grid_vel, optimized=True):
         return grid, p
     finally:
         s.close()
+
+
+def ref_benchmark_particles(res, type_name="sand", benchmark=125, density=400.0):
+    """MPM<3>::add_particles with `benchmark` (src/mpm.cpp:155-186) run by the reference itself: returns
+    dict(x, v, F, mass, vol) of the lattice it seeds (benchmark 125: a cube of res*0.2 cells, 8000: res*0.8)."""
+    L = ref_transfer()
+    L.reft_add_benchmark.restype = C.c_int64
+    f32 = np.float32
+    r = np.array([res] * 3, np.int32)
+    g = np.array([0, -10, 0], f32)
+    h = C.c_void_p(L.reft_create(_p(r), C.c_float(1.0 / res), C.c_float(1e-4), _p(g), C.c_int(1)))
+    try:
+        n = int(L.reft_add_benchmark(h, type_name.encode(), C.c_int(benchmark), C.c_float(density)))
+        out = dict(x=np.zeros((n, 3), f32), v=np.zeros((n, 3), f32), F=np.zeros((n, 9), f32), mass=np.zeros(n, f32), vol=np.zeros(n, f32))
+        b, ps = np.zeros((n, 9), f32), np.zeros(n, f32)
+        L.reft_get_particles(h, _p(out["x"]), _p(out["v"]), _p(out["F"]), _p(b), _p(ps))
+        L.reft_get_mass_vol(h, _p(out["mass"]), _p(out["vol"]))
+        return out
+    finally:
+        L.reft_destroy(h)

@@ -142,20 +142,28 @@ inline T *create_instance_placement(const std::string &alias, void *place) {
 
 class Config {
   std::map<std::string, double> num;
+  std::map<std::string, std::string> str;
 
  public:
+  Config &set(const std::string &k, const std::string &v) { str[k] = v; return *this; }
+  Config &set(const std::string &k, const char *v) { str[k] = v; return *this; }
   Config &set(const std::string &k, double v) { num[k] = v; return *this; }
-  template <class T, class = typename std::enable_if<!std::is_arithmetic<T>::value>::type>
-  Config &set(const std::string &, const T &) { return *this; }   // pointers, strings, vectors: accepted, not stored
+  template <class T, class = typename std::enable_if<!std::is_arithmetic<T>::value && !std::is_convertible<T, std::string>::value>::type>
+  Config &set(const std::string &, const T &) { return *this; }   // pointers, vectors: accepted, not stored
   bool has_key(const std::string &k) const { return num.count(k) != 0; }
   template <class T>
   T get(const std::string &k, const T &def) const {
     auto it = num.find(k);
     return it == num.end() ? def : (T)it->second;
   }
-  template <class T> T get(const std::string &) const { return T(); }
+  template <class T> T get(const std::string &k) const { return get_impl(k, (T *)nullptr); }
+  template <class T> T get_impl(const std::string &k, T *) const { auto it = num.find(k); return it == num.end() ? T() : stub_cast<T>(it->second); }
+  std::string get_impl(const std::string &k, std::string *) const { auto it = str.find(k); return it == str.end() ? std::string() : it->second; }
+  template <class T> static typename std::enable_if<std::is_arithmetic<T>::value, T>::type stub_cast(double v) { return (T)v; }
+  template <class T> static typename std::enable_if<!std::is_arithmetic<T>::value, T>::type stub_cast(double) { return T(); }
   template <class T> T *get_ptr(const std::string &) const { return nullptr; }
-  std::string get_string(const std::string &) const { return ""; }
+  std::string get_string(const std::string &k) const { auto it = str.find(k); return it == str.end() ? std::string() : it->second; }
+  bool has_key_str(const std::string &k) const { return str.count(k) != 0; }
 };
 
 // number of threads the stand-in's parallel loops use: 1 (the default) = plain serial loops in index order, which
@@ -371,6 +379,9 @@ struct IndexND {
   VectorND<dim, int> i;
   VectorND<dim, real> storage_offset = VectorND<dim, real>(0.5f);
   VectorND<dim, int> get_ipos() const { return i; }
+  int &operator[](int k) { return i[k]; }
+  int operator[](int k) const { return i[k]; }
+  IndexND &operator=(const VectorND<dim, int> &v) { i = v; return *this; }
   VectorND<dim, real> get_pos() const { return i.template cast<real>() + storage_offset; }  // cell centre unless the region says otherwise
 };
 // iteration space [lo, hi) in lexicographic order, last axis fastest (stencil node n <-> (n/9, n/3%3, n%3), src/transfer.cpp:353-359)

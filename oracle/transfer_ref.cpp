@@ -12,19 +12,15 @@
 //
 // What THIS file adds is scaffolding only:
 //   * empty bodies for the solver members defined in translation units outside this build (rigid coupling:
-//     src/rigid_transfer.cpp etc.) and for add_particles (seeding from textures / meshes / Poisson-disk asset
-//     files; the harness loads particles directly) — none is reachable on the pinned path;
+//     src/rigid_transfer.cpp etc.) — none is reachable on the pinned path; add_particles is the reference's own
+//     (its texture / mesh / Poisson-disk branches only compile; reft_add_benchmark drives its `benchmark` lattice
+//     branch, src/mpm.cpp:155-186, everything else loads particles directly);
 //   * populate(): the ordering / page maps / per-node counts of sort_particles_and_populate_grid
 //     (src/mpm.cpp:770-918) restated with the real SPGrid calls, used only by the single-transfer entry points
 //     (reft_p2g / reft_g2p); reft_substep runs the reference's own sort_particles_and_populate_grid;
 //   * C entry points that load particles, set a plane level set, run one stage or whole substeps, read or write
 //     node values, and dump a frame.
 #include REF_TRANSFER_SOURCE
-namespace taichi {
-// declared before src/mpm.cpp is seen, so that its generic add_particles (textures, meshes, Poisson-disk
-// sampling from asset files) is never instantiated for the 3-D solver: the harness loads particles itself
-template <> std::string MPM<3>::add_particles(const Config &);
-}  // namespace taichi
 #include REF_MPM_SOURCE
 #include REF_VISUALIZE_SOURCE
 #include REF_PARTICLES_SOURCE
@@ -34,7 +30,6 @@ template <> std::string MPM<3>::add_particles(const Config &);
 namespace taichi {
 // members of the solver that live in translation units which are not part of this build (src/rigid_transfer.cpp,
 // ...): empty, and unreachable on the pinned path (no rigid bodies)
-template <> std::string MPM<3>::add_particles(const Config &) { return ""; }
 template <> void MPM<3>::add_rigid_particle(Config) {}
 template <> void MPM<3>::rigidify(real) {}
 template <> void MPM<3>::advect_rigid_bodies(real) {}
@@ -280,6 +275,25 @@ int64_t reft_substep(void *hp, int n) {
 void reft_alive_ids(void *hp, int32_t *ids) {
   Solver &m = static_cast<Harness *>(hp)->m;
   for (size_t k = 0; k < m.particles.size(); k++) ids[k] = m.allocator[m.particles[k]]->id;
+}
+// the reference's own benchmark seeding (add_particles with benchmark = 125 | 8000, src/mpm.cpp:155-186): a cube of
+// res*0.2 (resp. res*0.8) cells per axis, 8 particles per cell.  type = registered particle name.  Returns the count.
+int64_t reft_add_benchmark(void *hp, const char *type, int benchmark, float density) {
+  Harness *h = static_cast<Harness *>(hp);
+  Config cfg;
+  cfg.set("type", std::string(type)).set("benchmark", benchmark).set("density", density);
+  const size_t before = h->m.particles.size();
+  h->m.add_particles(cfg);
+  static const char *names[5] = {"linear", "jelly", "snow", "water", "sand"};
+  int kind = -1;
+  for (int k = 0; k < 5; k++) if (std::string(type) == names[k]) kind = k;
+  for (size_t i = before; i < h->m.particles.size(); i++) h->kind.push_back(kind);
+  return (int64_t)(h->m.particles.size() - before);
+}
+// mass and volume by id (what add_particles assigned)
+void reft_get_mass_vol(void *hp, float *mass, float *vol) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  for (auto ptr : m.particles) { MPMParticle<3> *p = m.allocator[ptr]; mass[p->id] = p->get_mass(); vol[p->id] = p->vol; }
 }
 // frame dump by MPM<3>::write_partio itself (src/visualize.cpp:16-100) through the vendored Partio
 void reft_write_partio(void *hp, const char *file_name) { static_cast<Harness *>(hp)->m.write_partio(file_name); }

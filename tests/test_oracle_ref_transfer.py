@@ -206,6 +206,23 @@ def test_grid_update_modes_match_reference_live(friction, particle_gravity):
 
 
 @pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent")
+def test_lattice_generator_matches_reference_benchmark_seeding_live():
+    # the synthetic BASELINE scenes use the reference's deterministic lattice (src/mpm.cpp:164-180): the reference's own
+    # add_particles(benchmark=125) produces the same positions in the same order as scenes.lattice_block; its benchmark
+    # path passes maximum = 1, i.e. vol = dx^3 per particle (an 8x over-dense block) — BASELINE.md keeps the positions
+    # and uses the texture-seeding convention vol = dx^3 / 8 instead
+    res = 40
+    ref = O.ref_benchmark_particles(res, "sand", 125, 400.0)
+    lo, hi = int(round(res * 0.4)), int(round(res * 0.4)) + int(round(res * 0.2))
+    x, mass, vol = scenes.lattice_block(res, (lo,) * 3, (hi,) * 3, 400.0, 0.0)
+    assert len(ref["x"]) == len(x) == 8 ** 3 * 8
+    assert np.abs(ref["x"] - x).max() <= 1.2e-7                      # same lattice, same order (1 ulp)
+    assert np.allclose(ref["vol"], (1.0 / res) ** 3, rtol=1e-6) and np.allclose(vol, (1.0 / res) ** 3 / 8, rtol=1e-6)
+    assert np.allclose(ref["mass"], ref["vol"] * 400.0, rtol=1e-6) and np.allclose(mass, vol * 400.0, rtol=1e-6)
+    assert not ref["v"].any() and np.array_equal(ref["F"], np.tile(np.eye(3, dtype=np.float32).reshape(9), (len(x), 1)))
+
+
+@pytest.mark.skipif(not O.ref_transfer_available(), reason="reference tree absent")
 def test_reference_loops_without_particle_gravity_live():
     # particle_gravity = false: P2G does not touch the particle velocity (src/transfer.cpp:485-487)
     from tests import common as T
