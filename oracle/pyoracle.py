@@ -425,6 +425,21 @@ class RefSolver:
             pl = np.ascontiguousarray(scene["planes"], f32).reshape(-1, 4)
             L.reft_set_planes(self.h, C.c_int(len(pl)), _p(pl), C.c_float(scene.get("friction", 0.0)))
 
+    @classmethod
+    def from_benchmark(cls, res, dt, gravity, type_name, benchmark=125, density=400.0, particle_gravity=1):
+        """A solver seeded by the reference's own add_particles(type=..., benchmark=...) (src/mpm.cpp:155-186), the way
+        scripts/benchmark/benchmark_3d.py sets its scene up."""
+        L = ref_transfer()
+        L.reft_substep.restype = C.c_int64
+        L.reft_add_benchmark.restype = C.c_int64
+        self = cls.__new__(cls)
+        self.L = L
+        self.res = np.array([res] * 3, np.int32)
+        g = np.ascontiguousarray(gravity, np.float32)
+        self.h = C.c_void_p(L.reft_create(_p(self.res), C.c_float(1.0 / res), C.c_float(dt), _p(g), C.c_int(int(particle_gravity))))
+        self.n = int(L.reft_add_benchmark(self.h, type_name.encode(), C.c_int(int(benchmark)), C.c_float(density)))
+        return self
+
     def set_threads(self, n):
         """Threads of the stand-in's parallel loops; 1 (default) = serial, what every pin runs with."""
         self.L.reft_set_threads(self.h, C.c_int(int(n)))

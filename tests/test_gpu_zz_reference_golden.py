@@ -69,3 +69,32 @@ def test_engine_single_substep_matches_reference_transfers(kind):
     if kind != scenes.MAT_WATER:
         assert np.abs(got["F"] - ref["F"]).max() <= 2 * T.TOL_F_ABS
     assert np.abs(got["ps"] - ref["ps"]).max() <= 2 * T.TOL_PS_ABS
+
+
+def test_same_script_on_the_mirror_and_on_the_reference_solver():
+    """The drop-in claim end to end: the verbs of a reference scene script (scripts/benchmark/benchmark_3d.py: create the
+    solver, add_particles, step) run (a) on the reference's OWN MPM<3> object — its add_particles(benchmark=125), its
+    substep(), compiled in place for the CPU (oracle/transfer_ref.cpp) — and (b) on the mirror MPM driving the CUDA
+    engine through the C-ABI.  Same particles, same motion."""
+    from oracle import pyoracle as O
+    if not O.ref_transfer_available():
+        pytest.skip("reference build (oracle/_ref) not available")
+    from taichi_mpm_b200 import MPM, scenes
+    res, dt, nsub = 40, 1e-4, 20
+    ref = O.RefSolver.from_benchmark(res, dt, (0.0, -10.0, 0.0), "jelly", benchmark=125, density=400.0)
+    n = ref.n
+    ref.substep(nsub)
+    r = ref.particles()
+    ref.close()
+    lo = int(round(res * 0.4)); hi = lo + int(round(res * 0.2))
+    x0, _, _ = scenes.lattice_block(res, (lo,) * 3, (hi,) * 3, 400.0, 0.0)
+    m = MPM(res=(res, res, res), base_delta_t=dt, gravity=(0, -10, 0))
+    m.add_particles(type="jelly", positions=x0, maximum=1, density=400.0)      # the benchmark path's volume: dx^3 / 1
+    assert m.num_particles() == n == 8 ** 3 * 8
+    for _ in range(nsub):
+        m.step(-1.0)                                                           # dt < 0: exactly one substep
+    p = m.get_particles()
+    assert np.array_equal(p["id"], np.arange(n, dtype=p["id"].dtype)) and len(r["alive_ids"]) == n
+    assert np.abs(p["x"] - r["x"]).max() <= 1e-5
+    assert np.abs(p["v"] - r["v"]).max() <= 1e-3 * np.abs(r["v"]).max()
+    assert np.abs(p["F"] - r["F"]).max() <= 2e-4
