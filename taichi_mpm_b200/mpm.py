@@ -223,6 +223,17 @@ class MPM:
         self._push()
         return self.engine.num_particles()
 
+    def get_debug_information(self):
+        """MPM<dim>::get_debug_information (src/mpm.cpp:635-639): the reference returns an empty string."""
+        return ""
+
+    def test(self):
+        """MPM<dim>::test (src/mpm.cpp:577-580)."""
+        return True
+
+    def get_name(self):
+        return "mpm"                                                            # src/mpm.h:487, TC_IMPLEMENTATION(..., "mpm")
+
     # ---- frame output and snapshots (SURVEY §8f row 1)
     def visualize(self):
         """MPM<3>::visualize -> write_bgeo (src/visualize.cpp:156-159, src/mpm.h:333-343): the frame

@@ -206,4 +206,5 @@ def test_unsupported_solver_options_are_rejected_not_ignored(fake_engine):
     with pytest.raises(ValueError):
         m.set_levelset(m.create_levelset(), True)                                   # dynamic level set
     assert m.base_delta_t == 1e-4 and m.gravity == (0.0, -10.0, 0.0)                # defaults of src/mpm.cpp:38,42
+    assert m.get_debug_information() == "" and m.test() is True and m.get_name() == "mpm"   # the remaining verbs of the plugin surface
     assert mpm_mod.MPM(res=(32, 32, 32), gravity=-5, base_delta_t=1e-3, dt_multiplier=0.5).gravity == (0.0, -5.0, 0.0)
