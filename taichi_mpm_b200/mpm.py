@@ -206,6 +206,9 @@ class MPM:
             t += self.base_delta_t
             n += 1
         if n:
+            # "Times of particle updating" (src/mpm.cpp:436,449): particles.size() per substep; counted with the
+            # population at the start of the call (exact unless particles are deleted inside it)
+            self.update_counter += n * self.engine.num_particles()
             self.engine.substep(n)
             self.current_t = t
             self.substep_counter += n
