@@ -469,6 +469,18 @@ class RefSolver:
         """MPM<3>::substep() n times (src/mpm.cpp:452-575).  Returns the number of live particles."""
         return int(self.L.reft_substep(self.h, C.c_int(int(n))))
 
+    def substep_via_mpmb(self, lib_path, n=1):
+        """The drop-in, executed: the reference's MPM<3> object hands its AoS pool to libmpmb through the
+        C-ABI (mpmb_upload_aos with the slot layout taken by offsetof on the reference's own classes), the engine runs n
+        substeps, and pool + index vector are refreshed (mpmb_download_aos).  lib_path: libmpmb.so or its SIMT-emulator
+        build.  Single material.  Returns the number of survivors."""
+        self.L.reft_substep_via_mpmb.restype = C.c_int64
+        err = C.create_string_buffer(512)
+        r = int(self.L.reft_substep_via_mpmb(self.h, str(lib_path).encode(), C.c_int(int(n)), err, C.c_int(512)))
+        if r < 0:
+            raise RuntimeError("mpmb through the reference's pool failed (%d): %s" % (r, err.value.decode(errors="replace")))
+        return r
+
     def particles(self):
         """dict(x, v, F, b, ps) indexed by particle id (rows of deleted particles are zero) + alive ids."""
         n, f32 = self.n, np.float32

@@ -20,12 +20,36 @@
 //     (reft_p2g / reft_g2p); reft_substep runs the reference's own sort_particles_and_populate_grid;
 //   * C entry points that load particles, set a plane level set, run one stage or whole substeps, read or write
 //     node values, and dump a frame.
+// standard / stand-in / Partio headers first, so that the `private` trick below only touches the reference's classes
+#include <taichi/util.h>
+#include <taichi/stub_more.h>
+#include <taichi/math/svd.h>
+#include <taichi/dynamics/simulation.h>
+#include <taichi/dynamics/rigid_body.h>
+#include <Partio.h>
+#include <array>
+#include <atomic>
+#include <bitset>
+#include <chrono>
+#include <iostream>
+#include <set>
+#include <sstream>
+#include <thread>
+#include <unordered_map>
+#include <sys/mman.h>
+#include <SPGrid/Core/SPGrid_Allocator.h>
+#include <SPGrid/Core/SPGrid_Page_Map.h>
+#define private public   // the integration patch lives inside the reference's classes: offsetof(v_and_m)
 #include REF_TRANSFER_SOURCE
 #include REF_MPM_SOURCE
 #include REF_VISUALIZE_SOURCE
 #include REF_PARTICLES_SOURCE
+#undef private
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <dlfcn.h>
+#include "../include/mpmb.h"
 
 namespace taichi {
 // members of the solver that live in translation units which are not part of this build (src/rigid_transfer.cpp,
@@ -295,6 +319,73 @@ void reft_get_mass_vol(void *hp, float *mass, float *vol) {
   Solver &m = static_cast<Harness *>(hp)->m;
   for (auto ptr : m.particles) { MPMParticle<3> *p = m.allocator[ptr]; mass[p->id] = p->get_mass(); vol[p->id] = p->vol; }
 }
+// ---- the drop-in, executed: INTEGRATION.md §2.  The reference's own MPM<3> object hands its AoS particle pool to
+// libmpmb through the C-ABI (slot layout by offsetof on the reference's own types), the engine runs `n` substeps,
+// and the pool and the `particles` index vector are refreshed from the device — after which the reference goes on
+// (substep(), write_partio, ...) as if it had stepped itself.  `lib_path`: libmpmb.so (B200) or its SIMT-emulator
+// build (tests/simt); loaded with dlopen so that this checker library does not link the product.
+// Single material per call (MpmbAosLayout carries one plastic-scalar offset).  Returns survivors, or a negative status.
+int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, int err_len) {
+  Harness *h = static_cast<Harness *>(hp);
+  Solver &m = h->m;
+  auto fail = [&](const char *msg, int code) -> int64_t { if (err && err_len > 0) { std::strncpy(err, msg, err_len - 1); err[err_len - 1] = 0; } return code; };
+  if (m.particles.empty()) return 0;
+  void *lib = dlopen(lib_path, RTLD_NOW | RTLD_LOCAL);
+  if (!lib) return fail(dlerror(), -100);
+#define SYM(name) auto name##_ = reinterpret_cast<decltype(&name)>(dlsym(lib, #name)); if (!name##_) return fail("missing symbol " #name, -101)
+  SYM(mpmb_create); SYM(mpmb_destroy); SYM(mpmb_last_error); SYM(mpmb_set_material); SYM(mpmb_set_planes); SYM(mpmb_upload_aos);
+  SYM(mpmb_substep); SYM(mpmb_download_aos);
+#undef SYM
+  MpmbConfig c{};
+  for (int d = 0; d < 3; d++) { c.res[d] = m.res[d]; c.gravity[d] = m.gravity[d]; }
+  c.dx = m.delta_x; c.dt = m.base_delta_t;
+  c.particle_gravity = m.particle_gravity;
+  c.clean_boundary = m.config_backup.get("clean_boundary", true);
+  c.device = 0; c.world = 1;
+  MpmbHandle e = nullptr;
+  if (mpmb_create_(&c, &e) != MPMB_OK) return fail(mpmb_last_error_(nullptr), -102);
+  // one material group: kind and parameters read back from the first particle (all are of one registered type here)
+  const int kind = h->kind[m.allocator[m.particles[0]]->id];
+  float prm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  using P3 = MPMParticle<3>;
+  MpmbAosLayout L{};
+  L.stride = (int32_t)sizeof(ParticleContainer<3>);
+  L.off_pos = (int32_t)offsetof(P3, pos);
+  L.off_v_and_m = (int32_t)offsetof(P3, v_and_m);
+  L.off_dg_e = (int32_t)offsetof(P3, dg_e);
+  L.off_apic_b = (int32_t)offsetof(P3, apic_b);
+  L.col_pitch = (int32_t)sizeof(VectorND<3, real>);
+  L.off_vol = (int32_t)offsetof(P3, vol);
+  L.off_scalar = -1;
+  P3 *p0 = m.allocator[m.particles[0]];
+  switch (kind) {
+    case 0: prm[0] = static_cast<LinearParticle<3> *>(p0)->mu; prm[1] = static_cast<LinearParticle<3> *>(p0)->lambda; break;
+    case 1: prm[0] = static_cast<JellyParticle<3> *>(p0)->mu; prm[1] = static_cast<JellyParticle<3> *>(p0)->lambda; break;
+    case 2: { auto *q = static_cast<SnowParticle<3> *>(p0); prm[0] = q->mu_0; prm[1] = q->lambda_0; prm[2] = q->hardening; prm[3] = q->theta_c; prm[4] = q->theta_s;
+              prm[5] = q->min_Jp; prm[6] = q->max_Jp; L.off_scalar = (int32_t)offsetof(SnowParticle<3>, Jp); break; }
+    case 3: { auto *q = static_cast<WaterParticle<3> *>(p0); prm[0] = q->k; prm[1] = q->gamma; L.off_scalar = (int32_t)offsetof(WaterParticle<3>, j); break; }
+    case 4: { auto *q = static_cast<SandParticle<3> *>(p0); prm[0] = q->mu_0; prm[1] = q->lambda_0; prm[2] = q->alpha; prm[3] = q->cohesion; prm[4] = q->beta;
+              L.off_scalar = (int32_t)offsetof(SandParticle<3>, logJp); break; }
+    default: mpmb_destroy_(e); return fail("unknown particle type", -103);
+  }
+  int rc = mpmb_set_material_(e, 0, kind, prm, 8);
+  if (rc == MPMB_OK && m.levelset.levelset0 && !m.levelset.levelset0->planes.empty()) {
+    std::vector<float> pl;
+    for (auto &q : m.levelset.levelset0->planes) for (int k = 0; k < 4; k++) pl.push_back(q[k]);
+    rc = mpmb_set_planes_(e, (int32_t)m.levelset.levelset0->planes.size(), pl.data(), m.levelset.levelset0->friction);
+  }
+  if (rc == MPMB_OK) rc = mpmb_upload_aos_(e, (int64_t)m.particles.size(), m.allocator.pool.data(), (int64_t)m.allocator.pool.size(), m.particles.data(), &L, nullptr);
+  if (rc == MPMB_OK) rc = mpmb_substep_(e, n);
+  int64_t alive = 0;
+  if (rc == MPMB_OK) rc = mpmb_download_aos_(e, m.allocator.pool.data(), (int64_t)m.allocator.pool.size(), m.particles.data(), (int64_t)m.particles.size(), &L, &alive);
+  if (rc != MPMB_OK) { fail(mpmb_last_error_(e), rc); mpmb_destroy_(e); return rc; }
+  m.particles.resize((size_t)alive);                      // == what clear_boundary_particles leaves (src/mpm.cpp:583-633)
+  m.current_t += n * m.base_delta_t;
+  m.substep_counter += n;
+  mpmb_destroy_(e);
+  return alive;
+}
+
 // frame dump by MPM<3>::write_partio itself (src/visualize.cpp:16-100) through the vendored Partio
 void reft_write_partio(void *hp, const char *file_name) { static_cast<Harness *>(hp)->m.write_partio(file_name); }
 int64_t reft_num_particles(void *hp) { return (int64_t) static_cast<Harness *>(hp)->m.particles.size(); }

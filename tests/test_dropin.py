@@ -1,0 +1,50 @@
+"""The drop-in boundary, executed: the reference's OWN MPM<3> object
+(src/mpm.cpp, transfer.cpp, particles.cpp compiled in place, oracle/transfer_ref.cpp) steps a scene twice —
+once by itself (MPM<3>::substep) and once by handing its AoS particle pool to libmpmb through the C-ABI: mpmb_create
+from the solver's fields, mpmb_set_material from the particle's parameters, mpmb_upload_aos with the slot layout taken by
+offsetof on the reference's own classes, mpmb_substep, mpmb_download_aos back into the pool and the `particles` index
+vector.  Afterwards both objects go on with the reference's own substep() and write_partio.  Here the library is the
+SIMT-emulator build of the CUDA source (tests/simt); tests/test_gpu_zz_reference_golden.py does the same on the B200."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from taichi_mpm_b200 import scenes
+
+pytestmark = pytest.mark.skipif(not O.ref_transfer_available(), reason="reference build (oracle/_ref) not available")
+
+
+def run_dropin(lib_path, kind, tmp_path, nsub=12):
+    from tests import common as T
+    scene, st = T.perturbed_scene(kind, res=32, cells=5, seed=9 + kind)
+    st["x"][0] = [6.5 / 32, 0.5, 0.5]                       # one particle in the deletion band
+    a, b = O.RefSolver(scene, st), O.RefSolver(scene, st)
+    na = a.substep(nsub)                                    # the reference steps itself
+    nb = b.substep_via_mpmb(lib_path, nsub)                 # the reference steps through the C-ABI
+    pa, pb = a.particles(), b.particles()
+    ids = pa["alive_ids"]
+    assert na == nb == len(st["x"]) - 1 and np.array_equal(ids, pb["alive_ids"])
+    assert np.abs(pa["x"][ids] - pb["x"][ids]).max() <= 2e-6
+    assert np.abs(pa["v"][ids] - pb["v"][ids]).max() <= 2e-4 * np.abs(pa["v"][ids]).max()
+    assert np.abs(pa["b"][ids] - pb["b"][ids]).max() <= 5e-4 * np.abs(pa["b"][ids]).max()
+    if kind != scenes.MAT_WATER:
+        assert np.abs(pa["F"][ids] - pb["F"][ids]).max() <= 5e-5
+    assert np.abs(pa["ps"][ids] - pb["ps"][ids]).max() <= 5e-5
+    # the pool is a valid reference state again: both go on with MPM<3>::substep and dump a frame with write_partio
+    assert a.substep(3) == b.substep(3) == na
+    qa, qb = a.particles(), b.particles()
+    assert np.abs(qa["x"][ids] - qb["x"][ids]).max() <= 3e-6
+    fa, fb = tmp_path / "a.bgeo", tmp_path / "b.bgeo"
+    a.write_partio(fa); b.write_partio(fb)
+    a.close(); b.close()
+    from taichi_mpm_b200 import bgeo
+    xa, aa = bgeo.read_bgeo(str(fa))
+    xb, ab = bgeo.read_bgeo(str(fb))
+    assert np.array_equal(dict((n, v) for n, _, v in aa)["index"], dict((n, v) for n, _, v in ab)["index"])
+    assert np.abs(xa - xb).max() <= 3e-6
+
+
+@pytest.mark.parametrize("kind", [scenes.MAT_SAND, scenes.MAT_SNOW, scenes.MAT_WATER, scenes.MAT_JELLY, scenes.MAT_LINEAR])
+def test_reference_solver_steps_through_the_c_abi_on_the_emulator(kind, tmp_path):
+    from tests.simt import build_simt
+    run_dropin(build_simt.build(), kind, tmp_path)

@@ -98,3 +98,15 @@ def test_same_script_on_the_mirror_and_on_the_reference_solver():
     assert np.abs(p["x"] - r["x"]).max() <= 1e-5
     assert np.abs(p["v"] - r["v"]).max() <= 1e-3 * np.abs(r["v"]).max()
     assert np.abs(p["F"] - r["F"]).max() <= 2e-4
+
+
+def test_reference_solver_object_steps_through_libmpmb(tmp_path):
+    """INTEGRATION.md §2 executed on the device: the reference's own MPM<3> object (CPU build, oracle/_ref) hands its AoS
+    pool to libmpmb.so through the C-ABI and gets it back — against the same object stepping itself."""
+    from oracle import pyoracle as O
+    if not O.ref_transfer_available():
+        pytest.skip("reference build (oracle/_ref) not available")
+    from taichi_mpm_b200 import capi, scenes
+    from tests.test_dropin import run_dropin
+    capi.lib()
+    run_dropin(capi.lib_path(), scenes.MAT_SAND, tmp_path)
