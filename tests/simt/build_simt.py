@@ -42,8 +42,9 @@ def build(defines=(), force=False, asan=None):
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 (a memory checker without a GPU)."""
     if asan is None:
         asan = os.environ.get("MPMB_SIMT_ASAN", "") == "1"
+    ubsan = os.environ.get("MPMB_SIMT_UBSAN", "") == "1"   # UndefinedBehaviorSanitizer (LD_PRELOAD libubsan.so)
     deps = [SRC, MATH, os.path.join(HERE, "simt.h"), os.path.join(HERE, "simt.cpp"), os.path.join(HERE, "stub", "cub", "simt_cub.h"), __file__]
-    tag = "_".join([d.lower().replace("mpmb_exp_", "") for d in defines] + (["asan"] if asan else []))
+    tag = "_".join([d.lower().replace("mpmb_exp_", "") for d in defines] + (["asan"] if asan else []) + (["ubsan"] if ubsan else []))
     lib = LIB if not tag else LIB.replace(".so", "_" + tag + ".so")
     if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
         return lib
@@ -54,7 +55,8 @@ def build(defines=(), force=False, asan=None):
         f.write(transform(open(SRC).read()))
     cmd = ["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-march=x86-64-v3", "-mfma", "-w",
            "-I" + os.path.join(HERE, "stub"), "-I" + os.path.dirname(SRC), "-I" + os.path.join(ROOT, "include")] + ["-D" + d for d in defines] + (
-           ["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []) + [
+           ["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []) + (
+           ["-fsanitize=undefined", "-fno-sanitize-recover=undefined"] if ubsan else []) + [
            gen, os.path.join(HERE, "simt.cpp"), "-o", lib]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
