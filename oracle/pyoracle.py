@@ -469,6 +469,14 @@ class RefSolver:
         """MPM<3>::substep() n times (src/mpm.cpp:452-575).  Returns the number of live particles."""
         return int(self.L.reft_substep(self.h, C.c_int(int(n))))
 
+    def step(self, dt):
+        """MPM<3>::step(dt) (src/mpm.cpp:428-450).  Returns (substep_counter, current_t, request_t), the clocks as the
+        reference's `real` (float32) members hold them."""
+        self.L.reft_step.restype = C.c_int64
+        cur, req = C.c_float(0), C.c_float(0)
+        n = int(self.L.reft_step(self.h, C.c_float(float(dt)), C.byref(cur), C.byref(req)))
+        return n, np.float32(cur.value), np.float32(req.value)
+
     def substep_via_mpmb(self, lib_path, n=1):
         """The drop-in, executed: the reference's MPM<3> object hands its AoS pool to libmpmb through the
         C-ABI (mpmb_upload_aos with the slot layout taken by offsetof on the reference's own classes), the engine runs n

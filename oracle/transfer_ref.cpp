@@ -386,6 +386,16 @@ int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, 
   return alive;
 }
 
+// MPM<3>::step(dt) itself (src/mpm.cpp:428-450): `real` = float clocks decide how many substeps a frame runs
+// (request_t += dt; while (current_t + base_delta_t < request_t) substep()).  Returns the substep counter.
+int64_t reft_step(void *hp, float dt, float *current_t, float *request_t) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  m.step(dt);
+  if (current_t) *current_t = m.current_t;
+  if (request_t) *request_t = m.request_t;
+  return (int64_t)m.substep_counter;
+}
+
 // frame dump by MPM<3>::write_partio itself (src/visualize.cpp:16-100) through the vendored Partio
 void reft_write_partio(void *hp, const char *file_name) { static_cast<Harness *>(hp)->m.write_partio(file_name); }
 int64_t reft_num_particles(void *hp) { return (int64_t) static_cast<Harness *>(hp)->m.particles.size(); }

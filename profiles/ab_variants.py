@@ -20,13 +20,14 @@ from taichi_mpm_b200 import build  # noqa: E402
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     steps = next((sys.argv[i + 1] for i, a in enumerate(sys.argv) if a == "--steps"), "200")
-    args = [a for a in args if a != steps]
+    reps = next((sys.argv[i + 1] for i, a in enumerate(sys.argv) if a == "--reps"), "2")
+    args = [a for a in args if a not in (steps, reps)]
     libs = {"default": build.build()}
     for v in args:
         defs = ["MPMB_EXP_" + n for n in v.split("+")]
         libs[v] = build.build(defines=defs, out=os.path.join(os.path.dirname(build.LIB), "libmpmb_" + v.lower().replace("+", "_") + ".so"))
     rows = {k: [] for k in libs}
-    for rep in range(2):
+    for rep in range(int(reps)):
         for name, lib in libs.items():
             env = dict(os.environ, MPMB_LIB=lib)
             if "--parity" in sys.argv and rep == 0 and name != "default":

@@ -28,10 +28,11 @@ def nvcc_path():
     return "nvcc"
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def needs_build(lib=None):
+    lib = lib or LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
@@ -42,7 +43,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     out=".../lib/libmpmb_tile_xyz.so"; load it with MPMB_LIB=<path>); the default library is only
     ever built without defines."""
     lib = out or LIB
-    if not force and not defines and not needs_build():
+    if not force and not needs_build(lib):   # a variant's file name encodes its defines
         return lib
     os.makedirs(os.path.dirname(lib), exist_ok=True)
     cmd = [nvcc_path()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + SRC
@@ -66,4 +67,4 @@ if __name__ == "__main__":
     outp = next((argv[i + 1] for i, a in enumerate(argv) if a == "--out" and i + 1 < len(argv)), None)
     if defs and not outp:
         outp = os.path.join(_PKG, "lib", "libmpmb_" + "_".join(d.lower().replace("mpmb_exp_", "") for d in defs) + ".so")
-    print(build(force="--force" in argv or bool(defs), verbose="-v" in argv, defines=defs, out=outp))
+    print(build(force="--force" in argv, verbose="-v" in argv, defines=defs, out=outp))

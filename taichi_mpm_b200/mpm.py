@@ -80,7 +80,9 @@ class MPM:
             raise ValueError("the accelerated path is MPM<3>; 2D scenes run on the CPU reference")
         self.res = tuple(int(r) for r in res)
         self.delta_x = float(kwargs.get("delta_x", 1.0 / self.res[0]))          # async_mpm.py:40-41
-        self.base_delta_t = float(kwargs.get("base_delta_t", 1e-4)) * float(kwargs.get("dt_multiplier", 1.0))  # mpm.cpp:42-43
+        # the reference's clocks are `real` = float (src/mpm.h:100, src/mpm.cpp:42-43,428-450,573): carried as float32 so
+        # that a frame runs exactly the reference's number of substeps
+        self.base_delta_t = float(np.float32(np.float32(kwargs.get("base_delta_t", 1e-4)) * np.float32(kwargs.get("dt_multiplier", 1.0))))
         g = kwargs.get("gravity", (0.0, -10.0, 0.0))                            # mpm.cpp:38
         if np.isscalar(g):
             g = (0.0, float(g), 0.0)
@@ -95,8 +97,8 @@ class MPM:
                 raise ValueError("%s != 0 is outside the accelerated fast path" % key)
         self.engine = capi.Engine(self.res, self.delta_x, self.base_delta_t, self.gravity, self.particle_gravity,
                                   self.clean_boundary, device=int(kwargs.get("device", 0)), capacity=int(kwargs.get("capacity", 0)))
-        self.current_t = 0.0
-        self.request_t = 0.0
+        self.current_t = np.float32(0.0)
+        self.request_t = np.float32(0.0)
         self.update_counter = 0   # "Times of particle updating" (mpm.cpp:436,449)
         self.substep_counter = 0
         self._groups = []         # (kind, params) per material group
@@ -189,7 +191,7 @@ class MPM:
     def substep(self):
         self._push()
         self.engine.substep(1)
-        self.current_t += self.base_delta_t
+        self.current_t = np.float32(self.current_t + np.float32(self.base_delta_t))   # src/mpm.cpp:573, float
         self.substep_counter += 1
 
     def step(self, dt):
@@ -199,11 +201,14 @@ class MPM:
             self.substep()
             self.request_t = self.current_t
             return
-        self.request_t += dt
+        # float32 compare-and-accumulate, as the reference's `real` members do (29996 substeps for 60 frames of
+        # 0.01 at base_delta_t = 2e-5, not 30000: pinned against MPM<3>::step itself, tests/test_mirror_host.py)
+        h = np.float32(self.base_delta_t)
+        self.request_t = np.float32(self.request_t + np.float32(dt))
         n = 0
-        t = self.current_t
-        while t + self.base_delta_t < self.request_t:
-            t += self.base_delta_t
+        t = np.float32(self.current_t)
+        while np.float32(t + h) < self.request_t:
+            t = np.float32(t + h)
             n += 1
         if n:
             # "Times of particle updating" (src/mpm.cpp:436,449): particles.size() per substep; counted with the
@@ -278,7 +283,7 @@ class MPM:
                 for g, (k, q) in enumerate(zip(z["mat_kind"], z["mat_params"])):
                     self._groups.append((int(k), np.asarray(q, np.float32)))
                     self.engine.set_material(g, int(k), self._groups[-1][1])
-                self.current_t, self.request_t = float(z["current_t"]), float(z["request_t"])
+                self.current_t, self.request_t = np.float32(z["current_t"]), np.float32(z["request_t"])
                 self.update_counter, self.substep_counter, self.frame_count = (int(c) for c in z["counters"])
                 self._host = {k: np.ascontiguousarray(z["p_" + k]) for k in ("x", "v", "F", "b", "mass", "vol", "ps", "group")}
                 ids = np.ascontiguousarray(z["p_id"])

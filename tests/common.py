@@ -11,18 +11,15 @@ TOL_X_ABS = 1e-6        # times the domain size (=1)
 TOL_PS_ABS = 1e-5
 
 
-def perturbed_scene(kind, res=32, cells=8, seed=0, strain=0.02, vel=0.5, with_floor=True, friction=0.4, dt=None, **matkw):
-    """A small block with random affine velocity field, random apic_b and random F perturbation."""
+def perturb_state(st, kind, dx, seed=0, strain=0.02, vel=0.5):
+    """Random affine velocity field, random apic_b, random F perturbation and plastic scalars on top of a
+    lattice state (in place): every term of P2G, the grid update and G2P + return map is exercised."""
     rng = np.random.default_rng(seed)
-    lo = np.array([(res - cells) // 2, 9, (res - cells) // 2])
-    hi = lo + cells
-    x, mass, vol = scenes.lattice_block(res, lo, hi, jitter=0.2, seed=seed + 1)
-    st = scenes.make_state(x, mass, vol, kind)
+    x = st["x"]
     n = len(x)
     A = rng.normal(size=(3, 3)) * vel * 4
     a = rng.normal(size=3) * vel
     st["v"] = (a + (x - x.mean(0)) @ A.T + rng.normal(size=(n, 3)) * 0.05 * vel).astype(np.float32)
-    dx = 1.0 / res
     st["b"] = (rng.normal(size=(n, 9)) * vel * dx * 0.1).astype(np.float32)
     if kind != scenes.MAT_WATER:
         G = rng.normal(size=(n, 9)) * strain
@@ -33,6 +30,17 @@ def perturbed_scene(kind, res=32, cells=8, seed=0, strain=0.02, vel=0.5, with_fl
         st["ps"] = (1.0 + rng.normal(size=n) * 0.01).astype(np.float32)
     if kind == scenes.MAT_SAND:
         st["ps"] = (np.abs(rng.normal(size=n)) * 1e-3 * (rng.random(n) < 0.3)).astype(np.float32)
+    return st
+
+
+def perturbed_scene(kind, res=32, cells=8, seed=0, strain=0.02, vel=0.5, with_floor=True, friction=0.4, dt=None, **matkw):
+    """A small block with random affine velocity field, random apic_b and random F perturbation."""
+    lo = np.array([(res - cells) // 2, 9, (res - cells) // 2])
+    hi = lo + cells
+    x, mass, vol = scenes.lattice_block(res, lo, hi, jitter=0.2, seed=seed + 1)
+    st = scenes.make_state(x, mass, vol, kind)
+    dx = 1.0 / res
+    perturb_state(st, kind, dx, seed, strain, vel)
     if dt is None:
         dt = {scenes.MAT_SAND: 2e-5, scenes.MAT_WATER: 5e-5}.get(kind, 1e-4)
     planes = np.array([[0.0, 1.0, 0.0, -(lo[1] + 0.6)]], np.float32) if with_floor else None

@@ -155,15 +155,18 @@ def test_step_runs_the_reference_number_of_substeps(monkeypatch, tmp_path):
     monkeypatch.setattr(capi, "Engine", CountingEngine)
     m = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=1e-4)
     m.add_particles(type="jelly", benchmark_block=((10, 10, 10), (12, 12, 12)))
-    # MPM<dim>::step (src/mpm.cpp:428-450): request_t += dt; while (current_t + base_delta_t < request_t) substep()
+    # MPM<dim>::step (src/mpm.cpp:428-450): request_t += dt; while (current_t + base_delta_t < request_t) substep(),
+    # every clock a `real` = float (src/mpm.h:100)
+    f32 = np.float32
+
     def reference_count(current_t, request_t, dt, h):
-        request_t += dt
+        request_t = f32(request_t + f32(dt))
         n = 0
-        while current_t + h < request_t:
-            current_t += h
+        while f32(current_t + f32(h)) < request_t:
+            current_t = f32(current_t + f32(h))
             n += 1
         return n, current_t, request_t
-    cur, req, total = 0.0, 0.0, 0
+    cur, req, total = f32(0.0), f32(0.0), 0
     for dt in (1e-3, 1e-3, 2.5e-4, 1e-4, 5e-5, 3.3e-3):
         n, cur, req = reference_count(cur, req, dt, 1e-4)
         m.step(dt)
@@ -172,6 +175,43 @@ def test_step_runs_the_reference_number_of_substeps(monkeypatch, tmp_path):
     assert sum(m.engine.calls) == total and all(c > 0 for c in m.engine.calls)      # one engine call per frame, never an empty one
     m.step(-1.0)                                                                    # dt < 0: exactly one substep (src/mpm.cpp:429-432)
     assert m.substep_counter == total + 1 and m.engine.calls[-1] == 1
+
+
+def _mirror_counts(monkeypatch, h, dt, frames):
+    monkeypatch.setattr(capi, "Engine", CountingEngine)
+    m = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=h)
+    m.add_particles(type="jelly", benchmark_block=((10, 10, 10), (11, 11, 11)))
+    out = []
+    for _ in range(frames):
+        before = m.substep_counter
+        m.step(dt)
+        out.append(m.substep_counter - before)
+    return np.array(out, np.int32), m
+
+
+def test_step_counts_match_the_reference_step_golden(monkeypatch):
+    """Substeps per frame against MPM<3>::step of the reference sources compiled in place (tests/golden/make_step_golden.py):
+    float clocks give 29996 substeps for 60 frames of 0.01 at base_delta_t = 2e-5, a double-precision loop 30000."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_ref.npz"))
+    i = 0
+    while "case%d" % i in z:
+        h, dt, frames = z["case%d" % i]
+        got, m = _mirror_counts(monkeypatch, float(h), float(dt), int(frames))
+        assert np.array_equal(got, z["counts%d" % i]), (h, dt, got.sum(), z["counts%d" % i].sum())
+        assert m.current_t == z["clocks%d" % i][0] and m.request_t == z["clocks%d" % i][1]
+        i += 1
+    assert i >= 4 and int(z["counts0"].sum()) == 29996
+
+
+def test_step_counts_match_the_reference_step_live(monkeypatch):
+    from oracle import pyoracle as O
+    if not O.ref_transfer_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from tests.golden import make_step_golden as G
+    want, cur, req = G.reference_counts(2e-5, 0.004, 25)
+    got, m = _mirror_counts(monkeypatch, 2e-5, 0.004, 25)
+    assert np.array_equal(got, want) and m.current_t == cur and m.request_t == req
 
 
 def test_add_particles_follows_the_reference_rules(fake_engine):
@@ -205,6 +245,6 @@ def test_unsupported_solver_options_are_rejected_not_ignored(fake_engine):
     m = mpm_mod.MPM(res=(32, 32, 32))
     with pytest.raises(ValueError):
         m.set_levelset(m.create_levelset(), True)                                   # dynamic level set
-    assert m.base_delta_t == 1e-4 and m.gravity == (0.0, -10.0, 0.0)                # defaults of src/mpm.cpp:38,42
+    assert m.base_delta_t == float(np.float32(1e-4)) and m.gravity == (0.0, -10.0, 0.0)                # defaults of src/mpm.cpp:38,42
     assert m.get_debug_information() == "" and m.test() is True and m.get_name() == "mpm"   # the remaining verbs of the plugin surface
     assert mpm_mod.MPM(res=(32, 32, 32), gravity=-5, base_delta_t=1e-3, dt_multiplier=0.5).gravity == (0.0, -5.0, 0.0)
