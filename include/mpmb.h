@@ -126,14 +126,19 @@ int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float 
 int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *v, const float *F, const float *b,
                           const float *mass, const float *vol, const float *scalar, const int32_t *group);
 /* Particle k of the next upload gets id `base + k` (default 0); z-slab ranks use disjoint ranges so
- * that ids stay unique after migration.  Ids must stay below 2^26.                                 */
+ * that ids stay unique after migration.  Ids must stay below 2^28.                                 */
 int mpmb_set_id_base(MpmbHandle h, int64_t base);
 /* Same, reading the reference's own AoS pool: slot indices[k] of `pool` (ParticleAllocator::pool,
  * src/particle_allocator.h:39; MPM::particles index vector, src/mpm.h:116).  group[k] may be NULL. */
 int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slots, const uint32_t *indices,
                     const MpmbAosLayout *layout, const int32_t *group);
-/* Number of live particles (device value; synchronises).  Reference: particles.size().           */
+/* Number of live particles, counted on the device (4 bytes cross the bus; synchronises).
+ * Reference: particles.size().                                                                    */
 int mpmb_num_particles(MpmbHandle h, int64_t *n);
+/* Sum over all substeps so far of the particles each one updated — the reference's `update_counter +=
+ * particles.size()` per substep (src/mpm.cpp:436,449), counted on the device (exact when particles are
+ * deleted in the middle of a frame).                                                               */
+int mpmb_get_update_count(MpmbHandle h, int64_t *updates);
 /* Copies the live particles out, any pointer may be NULL.  Row k of every array belongs to the
  * particle whose id (upload index) is id[k]; rows are in the engine's storage order.  `cap` rows
  * are available in each array; *n_out receives the number written.                                */

@@ -21,7 +21,7 @@ MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, 
 EXPORTS = [
     "mpmb_create", "mpmb_destroy", "mpmb_last_error", "mpmb_version", "mpmb_set_stream", "mpmb_synchronize",
     "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes", "mpmb_set_id_base",
-    "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_num_particles", "mpmb_download_particles", "mpmb_download_aos",
+    "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_num_particles", "mpmb_get_update_count", "mpmb_download_particles", "mpmb_download_aos",
     "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_rasterize_part",
     "mpmb_resample_part", "mpmb_download_grid",
     "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters",
@@ -215,6 +215,12 @@ class Engine:
     def num_particles(self):
         n = C.c_int64(0)
         self._check(self.L.mpmb_num_particles(self.h, C.byref(n)))
+        return n.value
+
+    def update_count(self):
+        """Particle updates so far, as the reference's update_counter counts them (src/mpm.cpp:436)."""
+        n = C.c_int64(0)
+        self._check(self.L.mpmb_get_update_count(self.h, C.byref(n)))
         return n.value
 
     def download(self, cap=None, sort_by_id=True):

@@ -3,7 +3,7 @@
 // Data layout in HBM:
 //   * particles: SoA of ten float4 streams (160 B/particle), double buffered.
 //       P2G set  q0=(x,y,z,mass) q1=(vx,vy,vz,A0) q2=(A1..A4) q3=(A5..A8)
-//       G2P set  q4=(F0..F3) q5=(F4..F7) q6=(F8,scalar,vol,tag)     tag = group<<26 | id
+//       G2P set  q4=(F0..F3) q5=(F4..F7) q6=(F8,scalar,vol,tag)     tag = group<<28 | id
 //       state    q7=(b0..b3) q8=(b4..b7) q9=(b8,-,-,-)             b = apic_b
 //     A = calculate_force()*(-4 dt/dx) + apic_b*(4 m) is the affine matrix rasterize needs
 //     (src/transfer.cpp:503,521-522).  G2P produces it for the NEXT substep from the same
@@ -41,13 +41,21 @@ namespace mpmb {
 
 constexpr int ARENA = 216;  // 6*6*6 nodes
 constexpr int N_Q = 10;
+// tag = group << TAG_ID_BITS | id: MPMB_MAX_GROUPS = 16 groups, ids below 2^28 = 268 M (BASELINE config 5 holds 64 M)
+constexpr int TAG_ID_BITS = 28;
+constexpr uint32_t TAG_ID_MASK = (1u << TAG_ID_BITS) - 1u;
+static_assert(MPMB_MAX_GROUPS <= (1 << (32 - TAG_ID_BITS)), "group bits");
 // keys: [0, ntiles_total) = tile index; ntiles_total + {0,1,2} = left through -z / +z face, dead
 enum { SPECIAL_MIG_DOWN = 0, SPECIAL_MIG_UP = 1, SPECIAL_DEAD = 2 };
 
 struct Params {
   int res[3];
   int nnode[3];
+  // DENSE tile grid of this engine.  world == 1: the whole domain.  z-slab rank: its own tile layers plus one ghost
+  // layer on each side, i.e. local layer l holds global layer l + tz_off — the ordering scans, the slot map and the
+  // keys are slab-local, so their cost does not grow with the number of ranks.
   int nt[3];
+  int tz_off;
   int ntiles_total;
   float dx, inv_dx, dt;
   float gdt[3];
@@ -66,25 +74,19 @@ struct Counters {  // device-resident
   int n_movers;       // mover list consumed by the next ordering
   int n_movers_next;  // mover list being filled by G2P / migrate_unpack
   int n_alive;        // particles binned by the last ordering
-  int pad;
+  int n_live;         // scratch of k_count_live (mpmb_num_particles)
+  unsigned long long updates;  // sum over substeps of the particles binned: the reference's update_counter (src/mpm.cpp:436)
 };
-enum { DEVERR_TILE_CAPACITY = 1, DEVERR_MIGRATE_CAPACITY = 2, DEVERR_PARTICLE_CAPACITY = 4, DEVERR_PEER_TIMEOUT = 8 };
+enum { DEVERR_TILE_CAPACITY = 1, DEVERR_MIGRATE_CAPACITY = 2, DEVERR_PARTICLE_CAPACITY = 4, DEVERR_PEER_TIMEOUT = 8, DEVERR_BAD_INPUT = 16 };
 
 struct TileMeta {  // one 32-byte record per active tile (slot)
-  int tile, run_begin, run_len, arr_off, arr_len, out_begin, pad0, pad1;
+  int tile, run_begin, run_len, arr_off, arr_len, out_begin, xy, z;  // xy = tile x | y << 16, z = GLOBAL tile layer
 };
-// Build-time experiments (off by default; A/B them on a GPU with `build.py --define NAME`):
-//   MPMB_EXP_TILE_XYZ    k_order_c decodes tile -> (x,y,z) once per tile into TileMeta::pad0/pad1
-//                        (x | y<<16, z); the tile kernels then skip two runtime integer divisions per
-//                        CTA per tile/chunk (42 instr/particle in k_g2p, 4.9 % of k_p2g's stall samples).
-//   MPMB_EXP_DUAL_ARENA  k_p2g: one shared arena per warp, both warps flush their registers at the
-//                        same time and the store sums the two (the warp-after-warp flush holds 11.9 %
-//                        of k_p2g's stall samples).
-//   MPMB_EXP_SDF_FLAGS   k_grid reads the level set only for tiles whose node footprint touches the band
-//                        -3 <= phi <= 0 (a byte per tile, computed when the level set is set).
-//   MPMB_EXP_P2G_IPLANE  k_p2g with three threads per cell (one per stencil x-plane): 36 accumulators and
-//                        95 registers instead of 108 / 248, 18 warps per SM instead of 8 (k_p2g issues
-//                        on 45 % of its cycles at 8 warps).  Replaces the 64-thread kernel when defined.
+// TileMeta::pad0/pad1 carry the tile's (x | y<<16, z) coordinates, decoded once per tile by k_order_c, so the tile
+// kernels skip two runtime integer divisions per CTA per tile/chunk.
+// Measured A/B of round 2 (profiles/README.md): kept TILE_XYZ (-0.017 ms/substep) and the per-warp P2G arenas
+// (-0.018 ms); dropped the 192-thread x-plane P2G (0.317 vs 0.283 ms: +16 % instructions and 3x row reads cost
+// more than 18 warps/SM hide) and the per-tile level-set flags for k_grid (no change: the band test is not its limiter).
 
 struct View {  // raw pointers handed to kernels
   float4 *q[N_Q];        // current (read) buffer
@@ -142,7 +144,7 @@ __device__ __forceinline__ uint32_t make_key(const Params &P, float x, float y, 
     if (tz < P.tile_z0) return (uint32_t)(P.ntiles_total + SPECIAL_MIG_DOWN);
     if (tz >= P.tile_z1) return (uint32_t)(P.ntiles_total + SPECIAL_MIG_UP);
   }
-  return (uint32_t)((tx * P.nt[1] + ty) * P.nt[2] + tz);
+  return (uint32_t)((tx * P.nt[1] + ty) * P.nt[2] + (tz - P.tz_off));
 }
 
 // near_boundary + abnormal (src/mpm.h:269-276, src/mpm.cpp:595-598)
@@ -160,7 +162,7 @@ __device__ __forceinline__ bool reference_deletes(const Params &P, float3 x, flo
 // part 0 = all tiles.
 __device__ __forceinline__ bool tile_in_part(const Params &P, int tile, int part) {
   if (part == 0) return true;
-  const int tz = tile % P.nt[2];
+  const int tz = tile % P.nt[2] + P.tz_off;
   const bool boundary = (P.world > 1) && (tz == P.tile_z0 || tz == P.tile_z1 - 1);
   return part == 1 ? boundary : !boundary;
 }
@@ -197,10 +199,16 @@ __global__ void k_iota(uint32_t *a, int n) {
 
 __device__ __forceinline__ void pack_one(View &V, const Params &P, int i, uint32_t id_base, float3 x, float3 v, Mat3 F, Mat3 b, float mass, float vol, float ps,
                                          int g, uint32_t *keys) {
+  // a hole is encoded by the sign of the mass and the group by 4 tag bits: reject what cannot be represented
+  if (g < 0 || g >= MPMB_MAX_GROUPS || !(mass > 0.f)) {
+    atomicOr(&V.cnt->error, DEVERR_BAD_INPUT);
+    g = min(max(g, 0), MPMB_MAX_GROUPS - 1);
+    mass = 1e-30f;
+  }
   Mat3 force, A;
   calculate_force(P.mats[g], F, ps, vol, force);
   make_affine(force, b, mass, -4.0f * P.inv_dx * P.dt, A);
-  store_particle(V.q, (size_t)i, x, mass, v, A, F, ps, vol, ((uint32_t)g << 26) | (id_base + (uint32_t)i), b);
+  store_particle(V.q, (size_t)i, x, mass, v, A, F, ps, vol, ((uint32_t)g << TAG_ID_BITS) | (id_base + (uint32_t)i), b);
   keys[i] = make_key(P, x.x, x.y, x.z);
 }
 
@@ -259,8 +267,8 @@ __global__ void k_unpack_particles(View V, const uint32_t *keys, int n, uint32_t
   int o = prefix[i];
   float4 q0 = V.q[0][i], q1 = V.q[1][i], q4 = V.q[4][i], q5 = V.q[5][i], q6 = V.q[6][i], q7 = V.q[7][i], q8 = V.q[8][i], q9 = V.q[9][i];
   uint32_t tag = __float_as_uint(q6.w);
-  if (id) id[o] = tag & 0x3FFFFFFu;
-  if (group) group[o] = (int)(tag >> 26);
+  if (id) id[o] = tag & TAG_ID_MASK;
+  if (group) group[o] = (int)(tag >> TAG_ID_BITS);
   if (x) { x[3 * (size_t)o] = q0.x; x[3 * (size_t)o + 1] = q0.y; x[3 * (size_t)o + 2] = q0.z; }
   if (mass) mass[o] = fabsf(q0.w);
   if (v) { v[3 * (size_t)o] = q1.x; v[3 * (size_t)o + 1] = q1.y; v[3 * (size_t)o + 2] = q1.z; }
@@ -274,6 +282,17 @@ __global__ void k_unpack_particles(View V, const uint32_t *keys, int n, uint32_t
     float *p = b + 9 * (size_t)o;
     p[0] = q7.x; p[1] = q7.y; p[2] = q7.z; p[3] = q7.w; p[4] = q8.x; p[5] = q8.y; p[6] = q8.z; p[7] = q8.w; p[8] = q9.x;
   }
+}
+
+// live rows of the current storage (keys below the specials), reduced on the device: mpmb_num_particles reads 4 bytes
+__global__ void __launch_bounds__(256) k_count_live(const uint32_t *keys, uint32_t special_min, Counters *cnt) {
+  typedef cub::BlockReduce<int, 256> Red;
+  __shared__ typename Red::TempStorage tmp;
+  const int n = cnt->n_store;
+  int c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += keys[i] < special_min;
+  c = Red(tmp).Sum(c);
+  if (threadIdx.x == 0 && c) atomicAdd(&cnt->n_live, c);
 }
 
 __global__ void k_alive_flags(const uint32_t *keys, int n, uint32_t special_min, int *flags) {
@@ -355,6 +374,7 @@ __global__ void __launch_bounds__(1024) k_order_b(View V, int nblocks) {
   }
   if (threadIdx.x == 0) {
     V.cnt->n_alive = carry[0];
+    V.cnt->updates += (unsigned long long)carry[0];
     V.cnt->n_tiles = carry[2];
     V.cnt->n_ghost = 0;
     if (carry[2] > V.cap_tiles) atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY);
@@ -362,14 +382,8 @@ __global__ void __launch_bounds__(1024) k_order_b(View V, int nblocks) {
   }
 }
 
-#ifdef MPMB_EXP_TILE_XYZ
-#define MPMB_TILE_XYZ(P, tm, tx, ty, tz) const int tx = (tm).pad0 & 0xffff, ty = (tm).pad0 >> 16, tz = (tm).pad1
-__global__ void __launch_bounds__(ORD_B) k_order_c(View V, int ntot, int nt1, int nt2) {
-#else
-#define MPMB_TILE_XYZ(P, tm, tx, ty, tz) \
-  const int tz = (tm).tile % (P).nt[2], ty = ((tm).tile / (P).nt[2]) % (P).nt[1], tx = (tm).tile / ((P).nt[2] * (P).nt[1])
-__global__ void __launch_bounds__(ORD_B) k_order_c(View V, int ntot) {
-#endif
+#define MPMB_TILE_XYZ(P, tm, tx, ty, tz) const int tx = (tm).xy & 0xffff, ty = (tm).xy >> 16, tz = (tm).z
+__global__ void __launch_bounds__(ORD_B) k_order_c(View V, int ntot, int nt1, int nt2, int tz_off) {
   typedef cub::BlockScan<int, ORD_B> Scan;
   __shared__ typename Scan::TempStorage tmp;
   int tot[ORD_IPT], arr[ORD_IPT], act[ORD_IPT];
@@ -408,11 +422,7 @@ __global__ void __launch_bounds__(ORD_B) k_order_c(View V, int ntot) {
         slot = e_act;
         TileMeta m;
         m.tile = t; m.run_begin = V.run_begin[t]; m.run_len = V.run_len[t]; m.arr_off = e_arr; m.arr_len = arr[k]; m.out_begin = e_tot;
-#ifdef MPMB_EXP_TILE_XYZ
-        m.pad0 = (t / (nt2 * nt1)) | (((t / nt2) % nt1) << 16); m.pad1 = t % nt2;
-#else
-        m.pad0 = 0; m.pad1 = 0;
-#endif
+        m.xy = (t / (nt2 * nt1)) | (((t / nt2) % nt1) << 16); m.z = t % nt2 + tz_off;
         V.meta[slot] = m;
       }
       V.slot_map[t] = slot;
@@ -466,205 +476,6 @@ __global__ void k_step_commit(Counters *c) {
 //   4. flush: each warp adds its registers into the shared 6x6x6 arena, conflict-free by layout
 //      (node strides 68/8/1 put the 32 cells of a warp on 32 banks), warp after warp;
 // then one coalesced store of the arena.  No atomics on floats anywhere.
-#ifdef MPMB_EXP_P2G_IPLANE
-// EXPERIMENT (build with -DMPMB_EXP_P2G_IPLANE): three threads per cell, one per x-plane of the
-// 3x3x3 stencil.  Thread (cell, ip) accumulates the 9 nodes (ip, j, k) x (p,m) = 36 registers instead
-// of 108, so a CTA of 192 threads fits 3x per SM (18 warps instead of 8) at the price of re-reading
-// the cell's rows and recomputing wy, wz three times.  Each plane flushes into its own shared arena
-// (planes 1, 2: laid over the row staging area, free after the last chunk); within a plane the two
-// warps own disjoint x ranges, so the whole flush needs no ordering between warps.  The store sums
-// the three arenas in a fixed order: bit-reproducible, but a different rounding order than the
-// 64-thread kernel.
-constexpr int P2G_T = 192;         // 64 cells x 3 stencil planes
-constexpr int P2G_NW = P2G_T / 32;
-constexpr int P2G_CH = 512;        // particles staged per chunk
-constexpr int P2G_K = (P2G_CH + P2G_T - 1) / P2G_T;  // 3 passes, the last one partly idle
-constexpr int P2G_ROWS = P2G_CH + P2G_CH / 8;
-constexpr int AR_SX = 68, AR_SY = 8;
-constexpr int AR_SIZE = 6 * AR_SX;
-static_assert(2 * 4 * AR_SIZE <= 4 * P2G_ROWS * 4, "the two extra arenas must fit in the row staging area");
-
-__global__ void __launch_bounds__(P2G_T, 3) k_p2g(View V, Params P, int part) {
-  __shared__ float4 s_rows[4][P2G_ROWS];
-  __shared__ unsigned short s_order[P2G_CH];
-  __shared__ unsigned short s_hist[P2G_K * P2G_NW][64];
-  __shared__ int s_start[65];
-  __shared__ float s_arena[4][AR_SIZE];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cell_t = tid & 63, ip = tid >> 6;  // my cell and my stencil plane
-  const int n_tiles = V.cnt->n_tiles;
-  const int cx = cell_t >> 4, cy = (cell_t >> 2) & 3, cz = cell_t & 3;
-  float (*ar12)[4][AR_SIZE] = reinterpret_cast<float (*)[4][AR_SIZE]>(&s_rows[0][0]);  // arenas of planes 1 and 2
-  for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
-    const TileMeta tm = V.meta[slot];
-    const int tile = tm.tile;
-    if (!tile_in_part(P, tile, part)) continue;  // uniform per CTA
-    const int nrow_tile = tm.run_len + tm.arr_len;
-    MPMB_TILE_XYZ(P, tm, tx, ty, tz);
-    const float fbx = (float)(tx * 4 + cx), fby = (float)(ty * 4 + cy), fbz = (float)(tz * 4 + cz);
-    float acc[9][4];
-#pragma unroll
-    for (int n = 0; n < 9; n++) { acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f; }
-    for (int n = tid; n < 4 * AR_SIZE; n += P2G_T) (&s_arena[0][0])[n] = 0.f;
-    int vbase = 0;
-    auto row_of = [&](int g) -> uint32_t {
-      return g < tm.run_len ? (uint32_t)(tm.run_begin + g) : V.arrivals_sorted[tm.arr_off + (g - tm.run_len)];
-    };
-
-    for (int cb = 0; cb < nrow_tile; cb += P2G_CH) {
-      const int nrows = min(P2G_CH, nrow_tile - cb);
-      for (int n = tid; n < P2G_K * P2G_NW * 64; n += P2G_T) (&s_hist[0][0])[n] = 0;
-      // ---- 1: stage rows
-      uint32_t pidx[P2G_K];
-#pragma unroll
-      for (int k = 0; k < P2G_K; k++) {
-        const int r = k * P2G_T + tid;
-        pidx[k] = 0u;
-        if (r < nrows) pidx[k] = (cb + r < tm.run_len) ? (uint32_t)(tm.run_begin + cb + r) : row_of(cb + r);
-      }
-#pragma unroll
-      for (int k = 0; k < P2G_K; k++) {
-        const int r = k * P2G_T + tid;
-        if (r < nrows) {
-          const int ri = r + (r >> 3);
-          cp_async16(&s_rows[0][ri], &V.q[0][pidx[k]]);
-          cp_async16(&s_rows[1][ri], &V.q[1][pidx[k]]);
-          cp_async16(&s_rows[2][ri], &V.q[2][pidx[k]]);
-          cp_async16(&s_rows[3][ri], &V.q[3][pidx[k]]);
-        }
-      }
-      cp_async_commit();
-      cp_async_wait_all();
-      __syncthreads();
-      // ---- 2a: per-(pass,warp) cell histograms
-      uint32_t cr[P2G_K];
-#pragma unroll
-      for (int k = 0; k < P2G_K; k++) {
-        const int r = k * P2G_T + tid;
-        int cell = 64 + warp;  // holes and rows past the end: a private bucket per warp
-        float4 a0 = make_float4(0.f, 0.f, 0.f, -1.f);
-        if (r < nrows) a0 = s_rows[0][r + (r >> 3)];
-        if (r < nrows && (a0.w > 0.f || cb + r >= tm.run_len)) {
-          int bx, by, bz;
-          float rr;
-          base_rel(a0.x, P.inv_dx, bx, rr);
-          base_rel(a0.y, P.inv_dx, by, rr);
-          base_rel(a0.z, P.inv_dx, bz, rr);
-          cell = (((bx - tx * 4) & 3) << 4) | (((by - ty * 4) & 3) << 2) | ((bz - tz * 4) & 3);
-        }
-        const unsigned m = __match_any_sync(0xffffffffu, cell);
-        const int rank = __popc(m & ((1u << lane) - 1u));
-        if (cell < 64 && rank == 0) s_hist[k * P2G_NW + warp][cell] = (unsigned short)__popc(m);
-        cr[k] = ((uint32_t)cell << 16) | (uint32_t)rank;
-      }
-      __syncthreads();
-      // ---- 2b: exclusive scan over (pass,warp) per cell, then over the 64 cells (warps 0 and 1)
-      int run = 0, incl = 0;
-      if (tid < 64) {
-#pragma unroll
-        for (int e = 0; e < P2G_K * P2G_NW; e++) {
-          const int h = s_hist[e][tid];
-          s_hist[e][tid] = (unsigned short)run;
-          run += h;
-        }
-        incl = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += y;
-        }
-        if (tid == 31) s_start[64] = incl;  // total of warp 0, fixed up below
-      }
-      __syncthreads();
-      const int base0 = (tid >= 32 && tid < 64) ? s_start[64] : 0;
-      if (tid < 64) s_start[tid] = base0 + incl - run;
-      __syncthreads();
-      if (tid == 63) s_start[64] = base0 + incl;
-      // ---- 2c: scatter row ids to their sorted position; publish the output row for G2P
-#pragma unroll
-      for (int k = 0; k < P2G_K; k++) {
-        const int r = k * P2G_T + tid;
-        const int cell = (int)(cr[k] >> 16);
-        if (cell < 64) {
-          const int pos = s_start[cell] + s_hist[k * P2G_NW + warp][cell] + (int)(cr[k] & 0xffffu);
-          s_order[pos] = (unsigned short)r;
-          V.outpos[pidx[k]] = (uint32_t)(tm.out_begin + vbase + pos);
-        }
-      }
-      __syncthreads();
-      // ---- 3: accumulate my cell's run for my stencil plane
-      const int i0 = s_start[cell_t], i1 = s_start[cell_t + 1];
-      const float fi = (float)ip;
-      for (int it = i0; it < i1; it++) {
-        const int r = s_order[it];
-        const int ri = r + (r >> 3);
-        const float4 a0 = s_rows[0][ri], a1 = s_rows[1][ri], a2 = s_rows[2][ri], a3 = s_rows[3][ri];
-        const float mass = fabsf(a0.w);
-        float vx = a1.x, vy = a1.y, vz = a1.z;
-        if (P.particle_gravity) {
-          vx += P.gdt[0]; vy += P.gdt[1]; vz += P.gdt[2];
-        }
-        const float rx = __fsub_rn(__fmul_rn(a0.x, P.inv_dx), fbx), ry = __fsub_rn(__fmul_rn(a0.y, P.inv_dx), fby),
-                    rz = __fsub_rn(__fmul_rn(a0.z, P.inv_dx), fbz);
-        float wx[3], wy[3], wz[3];
-        bspline_weights(rx, wx);
-        bspline_weights(ry, wy);
-        bspline_weights(rz, wz);
-        const float wxi = ip == 0 ? wx[0] : (ip == 1 ? wx[1] : wx[2]);
-        const float q0 = fmaf(a3.y, rz, fmaf(a2.z, ry, fmaf(a1.w, rx, mass * vx)));
-        const float q1 = fmaf(a3.z, rz, fmaf(a2.w, ry, fmaf(a2.x, rx, mass * vy)));
-        const float q2 = fmaf(a3.w, rz, fmaf(a3.x, ry, fmaf(a2.y, rx, mass * vz)));
-        const float ux = q0 - fi * a1.w, uy = q1 - fi * a2.x, uz = q2 - fi * a2.y;
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-          const float tx_ = ux - (float)j * a2.z, ty_ = uy - (float)j * a2.w, tz_ = uz - (float)j * a3.x;
-          const float wij = wxi * wy[j];
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            const float w = wij * wz[k];
-            float *a = acc[j * 3 + k];
-            a[0] = fmaf(w, tx_ - (float)k * a3.y, a[0]);
-            a[1] = fmaf(w, ty_ - (float)k * a3.z, a[1]);
-            a[2] = fmaf(w, tz_ - (float)k * a3.w, a[2]);
-            a[3] = fmaf(w, mass, a[3]);
-          }
-        }
-      }
-      vbase += s_start[64];
-      __syncthreads();  // rows / order / hist are reused by the next chunk (or by the arenas below)
-    }
-    // ---- 4: flush.  Planes 1 and 2 zero their arenas in the (now free) staging area first.
-    if (ip > 0)
-      for (int n = cell_t; n < 4 * AR_SIZE; n += 64) (&ar12[ip - 1][0][0])[n] = 0.f;
-    __syncthreads();
-    {
-      float (*ar)[AR_SIZE] = ip == 0 ? s_arena : ar12[ip - 1];
-      const int nb = (cx + ip) * AR_SX + cy * AR_SY + cz;
-#pragma unroll
-      for (int j = 0; j < 3; j++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const int node = nb + j * AR_SY + k;
-          const float *a = acc[j * 3 + k];
-          ar[0][node] += a[0];
-          ar[1][node] += a[1];
-          ar[2][node] += a[2];
-          ar[3][node] += a[3];
-          __syncwarp();
-        }
-    }
-    __syncthreads();
-    float4 *out = V.arena + (size_t)slot * ARENA;
-    for (int n = tid; n < ARENA; n += P2G_T) {
-      const int a = n / 36, b = (n / 6) % 6, c = n % 6;
-      const int node = a * AR_SX + b * AR_SY + c;
-      out[n] = make_float4((s_arena[0][node] + ar12[0][0][node]) + ar12[1][0][node], (s_arena[1][node] + ar12[0][1][node]) + ar12[1][1][node],
-                           (s_arena[2][node] + ar12[0][2][node]) + ar12[1][2][node], (s_arena[3][node] + ar12[0][3][node]) + ar12[1][3][node]);
-    }
-    __syncthreads();
-  }
-}
-#else
 constexpr int P2G_T = 64;          // threads = cells per tile
 constexpr int P2G_CH = 512;        // particles staged per chunk
 constexpr int P2G_K = P2G_CH / P2G_T;
@@ -836,7 +647,6 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
       vbase += s_start[64];
       __syncthreads();  // rows / order / hist are reused by the next chunk
     }
-#ifdef MPMB_EXP_DUAL_ARENA
     // ---- 4: both warps flush at once, warp 0 into s_arena, warp 1 into a second arena laid over the
     // row staging area (free after the last chunk's barrier; zeroed by warp 1 itself, so a __syncwarp
     // is all it needs).  The store below sums the two in a fixed order: still bit-reproducible.
@@ -864,48 +674,17 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
           }
     }
     __syncthreads();
-#else
-    // ---- 4: flush registers to the shared arena, one warp at a time (deterministic order)
-#pragma unroll 1
-    for (int wsel = 0; wsel < 2; wsel++) {
-      if (warp == wsel) {
-        const int nb = cx * AR_SX + cy * AR_SY + cz;
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-              const int node = nb + i * AR_SX + j * AR_SY + k;
-              const float *a = acc[i * 9 + j * 3 + k];
-              // plain read-modify-write: shared float atomics cost ~2 cycles per LANE on this part
-              // (measured: the same flush with atomicAdd made the kernel 1.8x slower)
-              s_arena[0][node] += a[0];
-              s_arena[1][node] += a[1];
-              s_arena[2][node] += a[2];
-              s_arena[3][node] += a[3];
-              __syncwarp();
-            }
-      }
-      __syncthreads();
-    }
-#endif
     float4 *out = V.arena + (size_t)slot * ARENA;
     for (int n = tid; n < ARENA; n += P2G_T) {
       const int a = n / 36, b = (n / 6) % 6, c = n % 6;
       const int node = a * AR_SX + b * AR_SY + c;
-#ifdef MPMB_EXP_DUAL_ARENA
       out[n] = make_float4(s_arena[0][node] + ar1[0][node], s_arena[1][node] + ar1[1][node], s_arena[2][node] + ar1[2][node],
                            s_arena[3][node] + ar1[3][node]);
-#else
-      out[n] = make_float4(s_arena[0][node], s_arena[1][node], s_arena[2][node], s_arena[3][node]);
-#endif
     }
     __syncthreads();
   }
 }
 
-#endif  // MPMB_EXP_P2G_IPLANE
 
 // ------------------------------------------------------------------------------ grid node
 // Momentum/mass of global node g = fixed-order sum of the arenas that cover it:
@@ -957,47 +736,21 @@ __device__ __forceinline__ float4 node_update(const Params &P, const float4 *sdf
 // rebuilt (fixed-order sum of the covering arenas), normalised, projected on the level set and
 // stored as one contiguous 3.4 KB block vel[slot][216].  Node-parallel, so the dependent
 // slot_map -> arena -> sdf loads are hidden by occupancy instead of stalling a G2P CTA.
-#ifdef MPMB_EXP_SDF_FLAGS
-// EXPERIMENT: one byte per tile = "some node of the tile's 6x6x6 footprint has -3 <= phi <= 0", computed when the
-// level set is set.  k_grid then reads the level set only for those tiles (at config 3: the bottom tile layers of
-// the column), which removes 16 B/node of reads and one dependent load from every other node.  Same results.
-__global__ void k_tile_sdf_flags(Params P, const float4 *sdf4, unsigned char *flags, int ntot) {
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += gridDim.x * blockDim.x) {
-    const int tz = t % P.nt[2], ty = (t / P.nt[2]) % P.nt[1], tx = t / (P.nt[2] * P.nt[1]);
-    bool near = false;
-    for (int a = 0; a < 6 && !near; a++)
-      for (int b = 0; b < 6 && !near; b++)
-        for (int c = 0; c < 6; c++) {
-          const int gx = tx * 4 + a, gy = ty * 4 + b, gz = tz * 4 + c;
-          if (gx >= P.nnode[0] || gy >= P.nnode[1] || gz >= P.nnode[2]) continue;
-          const float phi = sdf4[((size_t)gx * P.nnode[1] + gy) * P.nnode[2] + gz].w;
-          if (!(phi < -3.0f || 0.0f < phi)) { near = true; break; }
-        }
-    flags[t] = near ? 1 : 0;
-  }
-}
-__global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int part, const unsigned char *tile_near) {
-#else
 __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int part) {
-#endif
   // one WARP per tile: the 27 neighbour slots live in lanes 0..26 and are fetched with shuffles, so
   // there is no block barrier and every warp of the grid has its own tile in flight
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int n_tiles = V.cnt->n_tiles;
   for (int slot = gw; slot < n_tiles; slot += nw) {
-#ifdef MPMB_EXP_TILE_XYZ
     const TileMeta tmg = V.meta[slot];
-#else
-    struct { int tile; } tmg = {V.meta[slot].tile};
-#endif
     const int tile = tmg.tile;
     if (!tile_in_part(P, tile, part)) continue;  // uniform per warp
     MPMB_TILE_XYZ(P, tmg, tx, ty, tz);
     int my_nb = -1;
     if (lane < 27) {
       int ox = lane / 9 - 1, oy = (lane / 3) % 3 - 1, oz = lane % 3 - 1;
-      int x = tx + ox, y = ty + oy, z = tz + oz;
+      int x = tx + ox, y = ty + oy, z = tz + oz - P.tz_off;  // z: local layer
       if (x >= 0 && y >= 0 && z >= 0 && x < P.nt[0] && y < P.nt[1] && z < P.nt[2]) my_nb = V.slot_map[(x * P.nt[1] + y) * P.nt[2] + z];
     }
 #pragma unroll 2
@@ -1013,11 +766,7 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int
         sl[o] = __shfl_sync(0xffffffffu, my_nb, (wx_ - ox + 1) * 9 + (wy_ - oy + 1) * 3 + (wz_ - oz + 1));
       }
       float4 g = gather_node(V.arena, V.cap_tiles, lx, ly, lz, [&](int ox, int oy, int oz) { return sl[ox * 4 + oy * 2 + oz]; });
-#ifdef MPMB_EXP_SDF_FLAGS
-      g = node_update(P, V.sdf4, g, tx * 4 + a, ty * 4 + b, tz * 4 + c, P.has_sdf && tile_near[tile] != 0);  // no level set: no flag array
-#else
       g = node_update(P, V.sdf4, g, tx * 4 + a, ty * 4 + b, tz * 4 + c);
-#endif
       if (n0 + lane < ARENA) vel[(size_t)slot * ARENA + n] = g;
     }
   }
@@ -1055,9 +804,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
     if (slot < n_tiles) it.tm = V.meta[slot];
     else {
       it.tm.run_len = 0; it.tm.arr_len = 0; it.tm.tile = 0; it.tm.run_begin = 0; it.tm.arr_off = 0; it.tm.out_begin = 0;
-#ifdef MPMB_EXP_TILE_XYZ
-      it.tm.pad0 = 0; it.tm.pad1 = 0;
-#endif
+      it.tm.xy = 0; it.tm.z = 0;
     }
     return it;
   };
@@ -1126,7 +873,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
         const size_t o = s_out[buf][r];
         const float mass = fabsf(q0.w), vol = q6.z;
         const uint32_t tag = __float_as_uint(q6.w);
-        const Material &mat = P.mats[tag >> 26];
+        const Material &mat = P.mats[tag >> TAG_ID_BITS];
         int bx, by, bz;
         float rx, ry, rz;
         base_rel(q0.x, P.inv_dx, bx, rx);
@@ -1218,7 +965,7 @@ __global__ void k_dense_grid(View V, Params P, int which, float4 *dense) {
     int gz = (int)(i % P.nnode[2]), gy = (int)((i / P.nnode[2]) % P.nnode[1]), gx = (int)(i / ((size_t)P.nnode[2] * P.nnode[1]));
     int tx = gx >> 2, ty = gy >> 2, tz = gz >> 2;
     float4 g = gather_node(V.arena, V.cap_tiles, gx & 3, gy & 3, gz & 3, [&](int ox, int oy, int oz) {
-      int x = tx - ox, y = ty - oy, z = tz - oz;
+      int x = tx - ox, y = ty - oy, z = tz - oz - P.tz_off;  // z: local layer
       if (x < 0 || y < 0 || z < 0 || x >= P.nt[0] || y >= P.nt[1] || z >= P.nt[2]) return -1;
       return V.slot_map[(x * P.nt[1] + y) * P.nt[2] + z];
     });
@@ -1247,6 +994,7 @@ __global__ void k_planes_to_sdf(Params P, int n_planes, const float4 *planes, fl
 // Packs the arenas of the owned tiles of one tile layer (the partial sums of (p,m) the neighbour
 // rank's nodes need); the neighbour registers them as ghost tiles, so its grid update sums them in
 // the same fixed order as a single-GPU run would.
+// layer_z: LOCAL tile layer (global layer - P.tz_off)
 __global__ void k_halo_pack(View V, Params P, int layer_z, int cap_xy, int *hdr, int *tile_xy, float4 *arenas) {
   __shared__ int s_idx;
   const int n_tiles = V.cnt->n_tiles;
@@ -1336,7 +1084,7 @@ __global__ void k_xchg_wait(const int *hdr, int seq, Counters *cnt) {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(hdr + 1) : "memory");
     if (v >= seq) return;
     if (clock64() - t0 > 60000000000ll) {  // ~30 s at 2 GHz (ranks may start seconds apart): give up loudly
-      atomicOr(&cnt->error, 8);
+      atomicOr(&cnt->error, DEVERR_PEER_TIMEOUT);
       return;
     }
     __nanosleep(200);
@@ -1388,9 +1136,6 @@ struct MpmbEngine {
   float4 *arena = nullptr;
   float4 *vel = nullptr;  // node velocities per active tile (k_grid -> k_g2p)
   float4 *sdf4 = nullptr;
-#ifdef MPMB_EXP_SDF_FLAGS
-  unsigned char *tile_near = nullptr;  // [ntot] tiles whose node footprint touches the level-set band
-#endif
   Counters *cnt = nullptr;
 
   int stage = 0;  // 0 idle/after resample, 1 after sort, 2 after rasterize
@@ -1406,6 +1151,7 @@ struct MpmbEngine {
   size_t stage_bytes = 0;
   uint32_t id_base = 0;
   int num_sms = 148;
+  int nt2_global = 0;  // tile layers of the whole domain (P.nt[2] is slab-local)
   int grid_p2g = 148 * 4, grid_g2p = 148 * 4;  // persistent grids = SMs x resident CTAs (queried)
   int64_t launches = 0;
 
@@ -1526,7 +1272,7 @@ static int free_particles(MpmbEngine *h) {
 
 static int alloc_particles(MpmbEngine *h, int64_t cap) {
   free_particles(h);
-  if (cap >= (1ll << 26)) return fail(h, MPMB_ERR_CAPACITY, "capacity %lld exceeds 2^26 particles per GPU", (long long)cap);
+  if (cap >= (1ll << 30)) return fail(h, MPMB_ERR_CAPACITY, "capacity %lld exceeds 2^30 particle rows per GPU", (long long)cap);
   if (cap < 1) cap = 1;
   for (int b = 0; b < 2; b++) {
     for (int k = 0; k < N_Q; k++) CUDA_TRY(h, cudaMalloc(&h->q[b][k], sizeof(float4) * cap));
@@ -1573,8 +1319,19 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
     P.nnode[d] = cfg->res[d] + 1;
     P.nt[d] = (P.nnode[d] + 3) / 4 + 1;
     P.gdt[d] = cfg->gravity[d] * cfg->dt;
-    ntot *= (size_t)P.nt[d];
   }
+  h->nt2_global = P.nt[2];
+  P.tz_off = 0;
+  if (h->cfg.world > 1) {
+    if (cfg->tile_z0 < 0 || cfg->tile_z1 > P.nt[2] || cfg->tile_z0 >= cfg->tile_z1) {
+      const int n2 = P.nt[2];
+      delete h;
+      return fail(nullptr, MPMB_ERR_INVALID, "bad slab [%d,%d) for %d tile layers", cfg->tile_z0, cfg->tile_z1, n2);
+    }
+    P.tz_off = cfg->tile_z0 - 1;                   // one ghost layer below ...
+    P.nt[2] = cfg->tile_z1 - cfg->tile_z0 + 2;     // ... and one above the owned layers
+  }
+  for (int d = 0; d < 3; d++) ntot *= (size_t)P.nt[d];
   P.ntiles_total = (int)ntot;
   P.dx = cfg->dx;
   P.inv_dx = 1.0f / cfg->dx;
@@ -1607,8 +1364,7 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<128, true>, 128, 0) == cudaSuccess && occ > 0) h->grid_g2p = h->num_sms * occ;
   }
   // tiles: every tile of the (slab of the) domain can be active
-  int64_t slab_layers = (h->cfg.world > 1) ? (int64_t)(P.tile_z1 - P.tile_z0) + 2 : P.nt[2];
-  int64_t cap_tiles = (int64_t)P.nt[0] * P.nt[1] * slab_layers;
+  int64_t cap_tiles = (int64_t)ntot;
   h->cap_tiles = (int)cap_tiles;
   auto bail = [&](const char *what) {
     std::string msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
@@ -1634,12 +1390,6 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
   cudaMemset(h->slot_map, 0xFF, sizeof(int) * ntot);
   cudaMemset(h->cnt, 0, sizeof(Counters));
   h->mig_cap = h->cfg.world > 1 ? (cfg->migrate_capacity > 0 ? cfg->migrate_capacity : 65536) : 0;
-  if (h->cfg.world > 1) {
-    if (cfg->tile_z0 < 0 || cfg->tile_z1 > P.nt[2] || cfg->tile_z0 >= cfg->tile_z1) {
-      mpmb_destroy(h);
-      return fail(nullptr, MPMB_ERR_INVALID, "bad slab [%d,%d) for %d tile layers", cfg->tile_z0, cfg->tile_z1, P.nt[2]);
-    }
-  }
   if (h->cfg.world > 1) {
     const int64_t bytes[2] = {mpmb_halo_bytes(h), mpmb_migrate_bytes(h)};
     for (int k = 0; k < 2; k++)
@@ -1667,9 +1417,6 @@ int mpmb_destroy(MpmbHandle h) {
   cudaFree(h->arr_cnt); cudaFree(h->arr_off); cudaFree(h->arr_len); cudaFree(h->arr_cur); cudaFree(h->slot_map); cudaFree(h->blocksum);
   cudaFree(h->meta);
   cudaFree(h->arena); cudaFree(h->vel); cudaFree(h->sdf4); cudaFree(h->cnt); cudaFree(h->stage_buf); cudaFree(h->xcount);
-#ifdef MPMB_EXP_SDF_FLAGS
-  cudaFree(h->tile_near);
-#endif
   for (int k = 0; k < 2; k++)
     for (int f = 0; f < 2; f++) {
       if (h->tx_ipc[k][f] && h->tx[k][f]) cudaIpcCloseMemHandle(h->tx[k][f]);
@@ -1696,6 +1443,7 @@ int mpmb_synchronize(MpmbHandle h) {
   if (c.error & DEVERR_MIGRATE_CAPACITY) return fail(h, MPMB_ERR_CAPACITY, "migration buffer capacity exceeded");
   if (c.error & DEVERR_PARTICLE_CAPACITY) return fail(h, MPMB_ERR_CAPACITY, "particle capacity exceeded");
   if (c.error & DEVERR_PEER_TIMEOUT) return fail(h, MPMB_ERR_STATE, "peer exchange timed out (neighbour rank not stepping)");
+  if (c.error & DEVERR_BAD_INPUT) return fail(h, MPMB_ERR_INVALID, "uploaded particles with group outside [0,%d) or mass <= 0", MPMB_MAX_GROUPS);
   return MPMB_OK;
 }
 
@@ -1711,7 +1459,7 @@ int mpmb_set_material(MpmbHandle h, int32_t group, int32_t kind, const float *pa
 
 int mpmb_set_id_base(MpmbHandle h, int64_t base) {
   CHECK_HANDLE(h);
-  if (base < 0 || base >= (1ll << 26)) return fail(h, MPMB_ERR_INVALID, "id base %lld outside [0, 2^26)", (long long)base);
+  if (base < 0 || base >= (1ll << TAG_ID_BITS)) return fail(h, MPMB_ERR_INVALID, "id base %lld outside [0, 2^%d)", (long long)base, TAG_ID_BITS);
   h->id_base = (uint32_t)base;
   return MPMB_OK;
 }
@@ -1725,11 +1473,6 @@ int mpmb_set_sdf(MpmbHandle h, const float *sdf4, float friction) {
   }
   if (!h->sdf4) CUDA_TRY(h, cudaMalloc(&h->sdf4, sizeof(float4) * n));
   CUDA_TRY(h, cudaMemcpyAsync(h->sdf4, sdf4, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
-#ifdef MPMB_EXP_SDF_FLAGS
-  if (!h->tile_near) CUDA_TRY(h, cudaMalloc(&h->tile_near, (size_t)h->ntot));
-  k_tile_sdf_flags<<<h->num_sms * 8, 256, 0, h->stream>>>(h->P, h->sdf4, h->tile_near, h->ntot);
-  h->launches++;
-#endif
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->P.has_sdf = 1;
   h->P.friction = friction;
@@ -1746,11 +1489,6 @@ int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float 
   CUDA_TRY(h, cudaMemcpyAsync(d_planes, planes4, sizeof(float4) * n_planes, cudaMemcpyHostToDevice, h->stream));
   k_planes_to_sdf<<<h->num_sms * 8, 256, 0, h->stream>>>(h->P, n_planes, d_planes, h->sdf4);
   h->launches++;
-#ifdef MPMB_EXP_SDF_FLAGS
-  if (!h->tile_near) CUDA_TRY(h, cudaMalloc(&h->tile_near, (size_t)h->ntot));
-  k_tile_sdf_flags<<<h->num_sms * 8, 256, 0, h->stream>>>(h->P, h->sdf4, h->tile_near, h->ntot);
-  h->launches++;
-#endif
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   cudaFree(d_planes);
   h->P.has_sdf = 1;
@@ -1799,7 +1537,7 @@ int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *
                           const float *mass, const float *vol, const float *scalar, const int32_t *group) {
   CHECK_HANDLE(h);
   if (n < 0 || (n > 0 && (!x || !v || !mass || !vol))) return fail(h, MPMB_ERR_INVALID, "x, v, mass, vol are required");
-  if ((int64_t)h->id_base + n > (1ll << 26)) return fail(h, MPMB_ERR_CAPACITY, "particle ids exceed 2^26");
+  if ((int64_t)h->id_base + n > (1ll << TAG_ID_BITS)) return fail(h, MPMB_ERR_CAPACITY, "particle ids exceed 2^%d", TAG_ID_BITS);
   int rc = ensure_capacity(h, n);
   if (rc != MPMB_OK) return rc;
   if (n == 0) return finish_upload(h, 0);
@@ -1838,6 +1576,7 @@ int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slot
                     const MpmbAosLayout *L, const int32_t *group) {
   CHECK_HANDLE(h);
   if (n < 0 || !pool || !indices || !L || L->stride <= 0) return fail(h, MPMB_ERR_INVALID, "pool, indices and layout are required");
+  if ((int64_t)h->id_base + n > (1ll << TAG_ID_BITS)) return fail(h, MPMB_ERR_CAPACITY, "particle ids exceed 2^%d", TAG_ID_BITS);
   int rc = ensure_capacity(h, n);
   if (rc != MPMB_OK) return rc;
   if (n == 0) return finish_upload(h, 0);
@@ -1870,17 +1609,27 @@ static int read_n_store(MpmbEngine *h, int *n_store) {
 int mpmb_num_particles(MpmbHandle h, int64_t *n) {
   CHECK_HANDLE(h);
   if (!n) return fail(h, MPMB_ERR_INVALID, "null argument");
+  *n = 0;
+  if (h->cap == 0) return MPMB_OK;
+  CUDA_TRY(h, cudaMemsetAsync(&h->cnt->n_live, 0, sizeof(int), h->stream));
+  k_count_live<<<h->num_sms * 4, 256, 0, h->stream>>>(h->keys[h->cur], h->special_min, h->cnt);
+  h->launches++;
   int rc = mpmb_synchronize(h);
   if (rc != MPMB_OK) return rc;
-  int ns = 0;
-  if ((rc = read_n_store(h, &ns)) != MPMB_OK) return rc;
-  *n = 0;
-  if (ns == 0 || h->cap == 0) return MPMB_OK;
-  std::vector<uint32_t> keys(ns);
-  CUDA_TRY(h, cudaMemcpy(keys.data(), h->keys[h->cur], sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost));
-  int64_t c = 0;
-  for (uint32_t k : keys) c += (k < h->special_min);
-  *n = c;
+  int live = 0;
+  CUDA_TRY(h, cudaMemcpy(&live, &h->cnt->n_live, sizeof(int), cudaMemcpyDeviceToHost));
+  *n = live;
+  return MPMB_OK;
+}
+
+int mpmb_get_update_count(MpmbHandle h, int64_t *updates) {
+  CHECK_HANDLE(h);
+  if (!updates) return fail(h, MPMB_ERR_INVALID, "null argument");
+  int rc = mpmb_synchronize(h);
+  if (rc != MPMB_OK) return rc;
+  unsigned long long u = 0;
+  CUDA_TRY(h, cudaMemcpy(&u, &h->cnt->updates, sizeof(u), cudaMemcpyDeviceToHost));
+  *updates = (int64_t)u;
   return MPMB_OK;
 }
 
@@ -1998,11 +1747,7 @@ int mpmb_sort_particles_and_populate_grid(MpmbHandle h) {
     if (!h->fresh) { k_mover_count<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot); nl++; }
     k_order_a<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot);
     k_order_b<<<1, 1024, 0, h->stream>>>(V, h->ord_blocks);
-#ifdef MPMB_EXP_TILE_XYZ
-    k_order_c<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot, h->P.nt[1], h->P.nt[2]);
-#else
-    k_order_c<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot);
-#endif
+    k_order_c<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot, h->P.nt[1], h->P.nt[2], h->P.tz_off);
     if (!h->fresh) {
       k_mover_place<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot);
       k_mover_rank<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot);
@@ -2036,11 +1781,7 @@ int mpmb_resample(MpmbHandle h) {
   prof_begin(h, 2);
   View V = make_view(h);
   if (h->cap > 0) {
-#ifdef MPMB_EXP_SDF_FLAGS
-    k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, 0, h->tile_near);
-#else
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, 0);
-#endif
     if (h->skip_b) k_g2p<128, false><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
     else k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
     k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt);
@@ -2086,11 +1827,7 @@ int mpmb_resample_part(MpmbHandle h, int32_t part) {
   View V = make_view(h);
   int nl = 2;
   if (h->cap > 0) {
-#ifdef MPMB_EXP_SDF_FLAGS
-    k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, part, h->tile_near);
-#else
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, part);
-#endif
     k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part);
     if (part == 1) { k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt); nl++; }
   }
@@ -2228,7 +1965,7 @@ int mpmb_halo_pack(MpmbHandle h, int32_t face, void *dev_buf) {
   char *b = (char *)dev_buf;
   CUDA_TRY(h, cudaMemsetAsync(b, 0, 16, h->stream));
   View V = make_view(h);
-  const int layer = face == 0 ? h->P.tile_z0 : h->P.tile_z1 - 1;
+  const int layer = (face == 0 ? h->P.tile_z0 : h->P.tile_z1 - 1) - h->P.tz_off;
   k_halo_pack<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, layer, (int)halo_cap_xy(h), (int *)b, (int *)(b + 16),
                                                      (float4 *)(b + 16 + halo_idx_bytes(h)));
   h->launches++;
@@ -2242,8 +1979,9 @@ int mpmb_halo_unpack(MpmbHandle h, int32_t face, const void *dev_buf) {
   if (h->cfg.world <= 1) return fail(h, MPMB_ERR_STATE, "halo exchange needs world > 1");
   if (h->stage != 2 && h->stage != 22) return fail(h, MPMB_ERR_STATE, "halo_unpack must follow rasterize (and may follow the interior resample)");
   if (!dev_buf || face < 0 || face > 1) return fail(h, MPMB_ERR_INVALID, "bad argument");
-  const int layer = face == 0 ? h->P.tile_z0 - 1 : h->P.tile_z1;  // the neighbour's boundary layer
-  if (layer < 0 || layer >= h->P.nt[2]) return fail(h, MPMB_ERR_INVALID, "no neighbour through face %d", face);
+  const int glayer = face == 0 ? h->P.tile_z0 - 1 : h->P.tile_z1;  // the neighbour's boundary layer
+  if (glayer < 0 || glayer >= h->nt2_global) return fail(h, MPMB_ERR_INVALID, "no neighbour through face %d", face);
+  const int layer = glayer - h->P.tz_off;
   prof_begin(h, 3);
   const char *b = (const char *)dev_buf;
   View V = make_view(h);
@@ -2352,7 +2090,7 @@ int mpmb_halo_send(MpmbHandle h, int32_t face) {
   int *cnt = h->xcount + 4 * face;
   CUDA_TRY(h, cudaMemsetAsync(cnt, 0, 16, h->stream));
   View V = make_view(h);
-  const int layer = face == 0 ? h->P.tile_z0 : h->P.tile_z1 - 1;
+  const int layer = (face == 0 ? h->P.tile_z0 : h->P.tile_z1 - 1) - h->P.tz_off;
   k_halo_pack<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, layer, (int)halo_cap_xy(h), cnt, (int *)(b + 16), (float4 *)(b + 16 + halo_idx_bytes(h)));
   k_xchg_publish<<<1, 1, 0, h->stream>>>(cnt, (int *)b, h->xstep + 1);
   h->launches += 2;
@@ -2368,7 +2106,7 @@ int mpmb_halo_recv(MpmbHandle h, int32_t face) {
   prof_begin(h, 3);
   const char *b = h->rx[0][face];
   View V = make_view(h);
-  const int layer = face == 0 ? h->P.tile_z0 - 1 : h->P.tile_z1;
+  const int layer = (face == 0 ? h->P.tile_z0 - 1 : h->P.tile_z1) - h->P.tz_off;
   k_xchg_wait<<<1, 1, 0, h->stream>>>((const int *)b, h->xstep + 1, h->cnt);
   k_halo_unpack<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, layer, (int)halo_cap_xy(h), (const int *)b, (const int *)(b + 16),
                                                        (const float4 *)(b + 16 + halo_idx_bytes(h)));

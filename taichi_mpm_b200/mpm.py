@@ -99,7 +99,8 @@ class MPM:
                                   self.clean_boundary, device=int(kwargs.get("device", 0)), capacity=int(kwargs.get("capacity", 0)))
         self.current_t = np.float32(0.0)
         self.request_t = np.float32(0.0)
-        self.update_counter = 0   # "Times of particle updating" (mpm.cpp:436,449)
+        self._update_counter = 0   # "Times of particle updating" (mpm.cpp:436,449): summed on the device, read lazily
+        self._update_seen = 0
         self.substep_counter = 0
         self._groups = []         # (kind, params) per material group
         self.frame_directory = kwargs.get("frame_directory")                    # async_mpm.py:49, mpm.h:335
@@ -211,13 +212,25 @@ class MPM:
             t = np.float32(t + h)
             n += 1
         if n:
-            # "Times of particle updating" (src/mpm.cpp:436,449): particles.size() per substep; counted with the
-            # population at the start of the call (exact unless particles are deleted inside it)
-            self.update_counter += n * self.engine.num_particles()
+            # "Times of particle updating" (src/mpm.cpp:436,449) = particles.size() per substep: the engine sums the
+            # particles every ordering bins (exact when particles are deleted inside the frame); see update_counter
             self.engine.substep(n)
             self.current_t = t
             self.substep_counter += n
         self._host = None
+
+    @property
+    def update_counter(self):
+        """MPM::update_counter (src/mpm.cpp:436,449), read from the device counter on demand (no sync inside step())."""
+        seen = self.engine.update_count()
+        self._update_counter += seen - self._update_seen
+        self._update_seen = seen
+        return self._update_counter
+
+    @update_counter.setter
+    def update_counter(self, value):
+        self._update_seen = self.engine.update_count()
+        self._update_counter = int(value)
 
     def get_current_time(self):
         return self.current_t

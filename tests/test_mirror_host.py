@@ -14,6 +14,7 @@ class FakeEngine:
     def __init__(self, res, dx, dt, gravity, particle_gravity, clean_boundary, device=0, capacity=0):
         self.res, self.dt = tuple(res), dt
         self.mats, self.id_base, self.p = {}, 0, None
+        self.updates = 0
 
     def set_material(self, g, kind, params):
         self.mats[g] = (kind, np.array(params, np.float32))
@@ -49,6 +50,10 @@ class FakeEngine:
 
     def substep(self, n):
         self.p["x"] = (self.p["x"] + self.p["v"] * np.float32(self.dt * n)).astype(np.float32)
+        self.updates += n * len(self.p["x"])
+
+    def update_count(self):
+        return self.updates
 
     def drop(self, ids):
         keep = ~np.isin(self.p["id"], ids)

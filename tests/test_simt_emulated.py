@@ -6,7 +6,7 @@ ctypes binding (MPMB_SIMT=1).  This checks kernel LOGIC (indexing, barriers, ord
 codegen, timing or memory-model races: the `-m gpu` run on a B200 stays the parity gate; this run means a logic
 error is caught in the CPU suite, and build-time kernel experiments can be debugged without GPU minutes:
 
-    MPMB_SIMT=1 MPMB_SIMT_DEFINES=MPMB_EXP_P2G_IPLANE python -m pytest tests -m gpu -q
+    MPMB_SIMT=1 MPMB_SIMT_DEFINES=<NAME> python -m pytest tests -m gpu -q
 """
 import os
 import subprocess
@@ -35,16 +35,6 @@ def test_gpu_parity_suite_passes_on_the_simt_emulator():
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("defines", ["MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE,MPMB_EXP_SDF_FLAGS", "MPMB_EXP_DUAL_ARENA"])
-def test_build_time_kernel_experiments_pass_parity_on_the_simt_emulator(defines):
-    # the off-by-default kernel variants are at least LOGICALLY right: single-substep parity, the
-    # reference's golden 10-substep run, deletion, multi-chunk tiles
-    tail = _run({"MPMB_SIMT_DEFINES": defines},
-                ["tests/test_gpu_zz_reference_golden.py", "tests/test_gpu_parity.py", "-k",
-                 "single_substep or reference or deletion or dense_tiles or two_materials"])
-    assert " passed" in tail and "failed" not in tail
-
-
 _ORDER_SCRIPT = r"""
 import os, sys
 sys.path.insert(0, %r)
@@ -63,7 +53,7 @@ np.savez(sys.argv[1], **d)
 """
 
 
-@pytest.mark.parametrize("defines", ["", "MPMB_EXP_TILE_XYZ,MPMB_EXP_P2G_IPLANE,MPMB_EXP_SDF_FLAGS", "MPMB_EXP_DUAL_ARENA"])
+@pytest.mark.parametrize("defines", [""])   # build-time variants (MPMB_SIMT_DEFINES) can be added here while they are being developed
 def test_results_do_not_depend_on_cta_or_thread_scheduling_order(tmp_path, defines):
     # the emulator runs CTAs and threads in index order, reversed, or pseudo-randomly shuffled per launch
     # (MPMB_SIMT_ORDER): a result that depended on who runs first — an inter-CTA race such as two CTAs writing one
