@@ -132,6 +132,16 @@ int mpmb_set_id_base(MpmbHandle h, int64_t base);
  * src/particle_allocator.h:39; MPM::particles index vector, src/mpm.h:116).  group[k] may be NULL. */
 int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slots, const uint32_t *indices,
                     const MpmbAosLayout *layout, const int32_t *group);
+/* Replaces the `benchmark` branch of MPM<3>::add_particles (src/mpm.cpp:149-186: 8 particles per cell of the
+ * block [lo_cell, hi_cell) at the cell centre +- 0.25 dx, F = I, apic_b = 0, velocity v0) ON THE DEVICE — no host
+ * array, which is what makes 10^7..10^8-particle scenes start in milliseconds.  `vol` / `mass` are the per-particle
+ * values the caller derives as add_particles does (vol = dx^3 / maximum, mass = vol * density, src/mpm.cpp:134-135).
+ * `jitter` (grid units, < 0.25; 0 = the reference's lattice) displaces every particle by a hash of its lattice index
+ * and `seed`, so positions do not depend on the z-slab partition.  Particle ids are id_base + lattice index
+ * (((ix*ny + iy)*nz + iz)*8 + corner, cells relative to lo_cell); a z-slab rank keeps the particles it owns;
+ * particles within 7 cells of a face are not created (src/mpm.cpp:129-132).  Replaces the resident set.           */
+int mpmb_seed_lattice(MpmbHandle h, const int32_t lo_cell[3], const int32_t hi_cell[3], float vol, float mass, float jitter,
+                      uint32_t seed, int32_t group, const float v0[3], int64_t *n_seeded);
 /* Number of live particles, counted on the device (4 bytes cross the bus; synchronises).
  * Reference: particles.size().                                                                    */
 int mpmb_num_particles(MpmbHandle h, int64_t *n);
@@ -145,8 +155,12 @@ int mpmb_get_update_count(MpmbHandle h, int64_t *updates);
 int mpmb_download_particles(MpmbHandle h, int64_t cap, int64_t *n_out, uint32_t *id, float *x, float *v, float *F,
                             float *b, float *mass, float *vol, float *scalar, int32_t *group);
 /* Writes the live particles back into the reference's AoS pool (slot = indices[id]); returns the
- * number of survivors and compacts `indices` to the survivors, which is what
- * clear_boundary_particles (src/mpm.cpp:583-633) leaves in MPM::particles.                         */
+ * number of survivors and compacts `indices` to the survivors (in id order), which is what
+ * clear_boundary_particles (src/mpm.cpp:583-633) leaves in MPM::particles.  The scatter runs on the
+ * device into the image of the pool kept since mpmb_upload_aos, and the image comes back with ONE
+ * contiguous copy: bytes of a slot outside the layout's fields (vptr, flags, ...) return as uploaded,
+ * so the pool must not be modified between the two calls (the device owns the particles during
+ * step()).  Without a preceding mpmb_upload_aos of the same pool the image is read first. */
 int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *indices, int64_t n_indices,
                       const MpmbAosLayout *layout, int64_t *n_alive);
 
@@ -176,7 +190,7 @@ int mpmb_resample_part(MpmbHandle h, int32_t part);
 int mpmb_download_grid(MpmbHandle h, int32_t which, float *dense4);
 
 /* ------------------------------------------------------------------------------ profiling */
-#define MPMB_N_STAGES 4 /* 0 sort+tiles, 1 P2G, 2 G2P(+grid update), 3 exchange pack/unpack */
+#define MPMB_N_STAGES 5 /* 0 sort+tiles, 1 P2G, 2 G2P, 3 exchange pack/unpack, 4 grid update */
 /* When enabled, CUDA events bracket every stage on the engine's stream.                          */
 int mpmb_set_profiling(MpmbHandle h, int32_t enabled);
 /* Accumulated milliseconds and launch counts per stage since the last reset (synchronises).      */

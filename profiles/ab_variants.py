@@ -24,8 +24,12 @@ def main():
     args = [a for a in args if a not in (steps, reps)]
     libs = {"default": build.build()}
     for v in args:
-        defs = ["MPMB_EXP_" + n for n in v.split("+")]
-        libs[v] = build.build(defines=defs, out=os.path.join(os.path.dirname(build.LIB), "libmpmb_" + v.lower().replace("+", "_") + ".so"))
+        if ":" in v:   # DEFINE[+DEFINE...]:libname  (full macro names, NAME=VALUE allowed)
+            dd, name = v.split(":")
+            defs = dd.split("+")
+        else:
+            defs, name = ["MPMB_EXP_" + n for n in v.split("+")], v.lower().replace("+", "_")
+        libs[v] = build.build(defines=defs, out=os.path.join(os.path.dirname(build.LIB), "libmpmb_" + name + ".so"))
     rows = {k: [] for k in libs}
     for rep in range(int(reps)):
         for name, lib in libs.items():

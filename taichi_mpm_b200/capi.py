@@ -13,7 +13,7 @@ from . import build as _build
 
 MPMB_MAX_GROUPS = 16
 MPMB_MAT_PARAMS = 8
-MPMB_N_STAGES = 4
+MPMB_N_STAGES = 5
 MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND = range(5)
 MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, "water": MAT_WATER, "sand": MAT_SAND}
 
@@ -21,7 +21,7 @@ MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, 
 EXPORTS = [
     "mpmb_create", "mpmb_destroy", "mpmb_last_error", "mpmb_version", "mpmb_set_stream", "mpmb_synchronize",
     "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes", "mpmb_set_id_base",
-    "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_num_particles", "mpmb_get_update_count", "mpmb_download_particles", "mpmb_download_aos",
+    "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_seed_lattice", "mpmb_num_particles", "mpmb_get_update_count", "mpmb_download_particles", "mpmb_download_aos",
     "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_rasterize_part",
     "mpmb_resample_part", "mpmb_download_grid",
     "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters",
@@ -195,6 +195,16 @@ class Engine:
         n = C.c_int64(0)
         self._check(self.L.mpmb_download_particles(self.h, C.c_int64(cap), C.byref(n), vp(id_), vp(x), vp(v), vp(F), vp(b), vp(mass),
                                                    vp(vol), vp(scalar), vp(group)))
+        return n.value
+
+    def seed_lattice(self, lo_cell, hi_cell, vol, mass, jitter=0.0, seed=0, group=0, v0=(0.0, 0.0, 0.0)):
+        """Device-side `benchmark` lattice (src/mpm.cpp:149-186); returns the number of particles this engine created."""
+        lo = (C.c_int32 * 3)(*[int(v) for v in lo_cell])
+        hi = (C.c_int32 * 3)(*[int(v) for v in hi_cell])
+        vv = (C.c_float * 3)(*[float(v) for v in v0])
+        n = C.c_int64(0)
+        self._check(self.L.mpmb_seed_lattice(self.h, lo, hi, C.c_float(vol), C.c_float(mass), C.c_float(jitter), C.c_uint32(int(seed)),
+                                             C.c_int32(group), vv, C.byref(n)))
         return n.value
 
     def upload_aos(self, pool, indices, layout, group=None):

@@ -122,6 +122,84 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: ONE elected thread moves a whole unit-stride
+// run chunk (4 KB per stream) or a tile's 3.4 KB node block global -> shared; nobody computes addresses per row, and the
+// consumers wait on the barrier's phase parity instead of on their own copy groups.
+#ifndef MPMB_SIMT_HOST
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// the elected thread's arrival + the number of bytes the copies of this phase will deliver
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#else
+// SIMT emulator (tests/simt): a phase completes at the elected thread's arrival (the word counts completed phases and a
+// waiter yields to the other coroutines until the phase of its parity is over), but the bulk copies LAND LATE — they are
+// queued and performed by the first thread that waits on their barrier — so a consumer that reads without waiting, or
+// another copy that races with a bulk copy's bytes, shows up in the emulated parity runs.
+struct SimtBulk { void *dst; const void *src; unsigned bytes; uint64_t *bar; };
+static std::vector<SimtBulk> g_simt_bulk;
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned) { *bar = 0; }
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned) { *bar += 1; }
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+  g_simt_bulk.push_back(SimtBulk{smem_dst, gmem_src, bytes, bar});
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  while ((unsigned)(*(volatile uint64_t *)bar & 1u) == parity) simt::yield();
+  for (size_t i = 0; i < g_simt_bulk.size();) {
+    if (g_simt_bulk[i].bar == bar) {
+      memcpy(g_simt_bulk[i].dst, g_simt_bulk[i].src, g_simt_bulk[i].bytes);
+      g_simt_bulk.erase(g_simt_bulk.begin() + i);
+    } else {
+      i++;
+    }
+  }
+}
+#endif
+
+// A float4 quantity (x, y | z, w) and its weights as pairs.  The pair form was written for Blackwell's packed fp32
+// (FFMA2 / FMUL2 / FADD2, `fma.rn.f32x2`); measured on a B200 (profiles/README.md, round 2) the packed instructions were
+// SLOWER than the scalar ones in both tile kernels (k_p2g 0.253 vs 0.241 ms, k_g2p 0.354 vs 0.346 ms: FFMA2 occupies
+// the fma pipe for two issue slots and the aligned register pairs cost k_g2p 28 registers), so the operations below
+// are the scalar fmaf / mul / sub — the node loops keep the pair structure, which the scalar code generator likes
+// (-0.017 ms in k_p2g against the float[27][4] accumulators of round 1).
+struct F4 {
+  float2 lo, hi;  // (x, y), (z, w)
+};
+__device__ __forceinline__ float2 bc2(float w) { return make_float2(w, w); }
+__device__ __forceinline__ F4 f4_load(const float4 &v) { return F4{make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
+__device__ __forceinline__ F4 f4_zero() { return F4{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}; }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ F4 f4_fma(float2 w, const F4 &a, const F4 &c) {
+  return F4{make_float2(fmaf(w.x, a.lo.x, c.lo.x), fmaf(w.y, a.lo.y, c.lo.y)), make_float2(fmaf(w.x, a.hi.x, c.hi.x), fmaf(w.y, a.hi.y, c.hi.y))};
+}
+__device__ __forceinline__ F4 f4_mul(float2 w, const F4 &a) { return F4{make_float2(w.x * a.lo.x, w.y * a.lo.y), make_float2(w.x * a.hi.x, w.y * a.hi.y)}; }
+__device__ __forceinline__ F4 f4_sub(const F4 &a, const F4 &b) {
+  return F4{make_float2(a.lo.x - b.lo.x, a.lo.y - b.lo.y), make_float2(a.hi.x - b.hi.x, a.hi.y - b.hi.y)};
+}
+
 __device__ __forceinline__ void base_rel(float x, float inv_dx, int &base, float &rel) {
   // pos_ = p.pos * inv_delta_x (src/transfer.cpp:490); base = int(x - 0.5f) (src/kernel.h:119-121).
   // Explicit round-to-nearest ops so that no FMA contraction changes the cell assignment.
@@ -303,6 +381,104 @@ __global__ void k_alive_flags(const uint32_t *keys, int n, uint32_t special_min,
 __global__ void k_fill_u32(uint32_t *a, int n, uint32_t v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
+}
+
+// ------------------------------------------------------------------------------ device-side seeding
+// Replaces the `benchmark` lattice of MPM<3>::add_particles (src/mpm.cpp:149-186: 8 particles per cell at the cell
+// centre +- 0.25 dx) without a host array: optional jitter from a counter-based hash of the particle's LATTICE index, so
+// the same particle gets the same position whatever the z-slab partition (and from the numpy twin
+// scenes.lattice_block_hashed, the parity reference).  id = lattice index; a z-slab rank keeps the particles whose base
+// node lies in its tile layers; particles in the 7-cell boundary band are not created (src/mpm.cpp:129-132).
+struct SeedBox {
+  int lo[3], n[3];      // first cell and number of cells of the whole block
+  int z_first, z_count; // candidate cell layers of this rank (relative to lo[2])
+  float jitter, vol, mass, v0[3];
+  float ps;             // plastic scalar of the material's fresh state
+  uint32_t seed, id_base;
+  int group;
+};
+__host__ __device__ __forceinline__ uint32_t seed_hash(uint32_t idx, uint32_t axis, uint32_t seed) {
+  uint32_t h = (idx * 3u + axis) ^ seed;
+  h *= 0x9E3779B1u; h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+// candidate c -> lattice index, position; returns whether this rank creates the particle
+__device__ __forceinline__ bool seed_candidate(const Params &P, const SeedBox &B, size_t c, uint32_t &lattice, float3 &x, uint32_t &key) {
+  const int corner = (int)(c & 7u);
+  size_t cell = c >> 3;
+  const int kz = (int)(cell % (size_t)B.z_count) + B.z_first;
+  cell /= (size_t)B.z_count;
+  const int ky = (int)(cell % (size_t)B.n[1]), kx = (int)(cell / (size_t)B.n[1]);
+  lattice = (uint32_t)((((size_t)kx * B.n[1] + ky) * B.n[2] + kz) * 8u + corner);
+  const int ic[3] = {B.lo[0] + kx, B.lo[1] + ky, B.lo[2] + kz};
+  float X[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float off = ((corner >> a) & 1) ? 0.75f : 0.25f;
+    const float u = __fsub_rn((float)(seed_hash(lattice, (uint32_t)a, B.seed) >> 8) * (1.0f / 8388608.0f), 1.0f);  // [-1, 1)
+    X[a] = __fadd_rn(__fadd_rn((float)ic[a], off), __fmul_rn(B.jitter, u));                                        // grid units
+  }
+  x = make_float3(__fmul_rn(X[0], P.dx), __fmul_rn(X[1], P.dx), __fmul_rn(X[2], P.dx));
+  const float mn = fminf(X[0], fminf(X[1], X[2]));
+  const float mx = fmaxf(X[0] - (float)P.res[0], fmaxf(X[1] - (float)P.res[1], X[2] - (float)P.res[2]));
+  if (mn < 7.0f || mx > -7.0f) return false;  // near_boundary (src/mpm.h:269-276)
+  key = make_key(P, x.x, x.y, x.z);
+  return key < (uint32_t)P.ntiles_total;      // owned by this rank (not a migration / dead key)
+}
+__global__ void k_seed_flags(Params P, SeedBox B, size_t n_cand, int *flags) {
+  for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n_cand; c += (size_t)gridDim.x * blockDim.x) {
+    uint32_t lattice, key;
+    float3 x;
+    flags[c] = seed_candidate(P, B, c, lattice, x, key) ? 1 : 0;
+  }
+}
+__global__ void k_seed_write(View V, Params P, SeedBox B, size_t n_cand, const int *flags, const int *prefix, uint32_t *keys) {
+  for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n_cand; c += (size_t)gridDim.x * blockDim.x) {
+    if (!flags[c]) continue;
+    uint32_t lattice, key;
+    float3 x;
+    seed_candidate(P, B, c, lattice, x, key);
+    Mat3 F, b, force, A;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { F.m[k] = (k % 4 == 0) ? 1.f : 0.f; b.m[k] = 0.f; }
+    calculate_force(P.mats[B.group], F, B.ps, B.vol, force);
+    make_affine(force, b, B.mass, -4.0f * P.inv_dx * P.dt, A);
+    const size_t o = (size_t)prefix[c];
+    store_particle(V.q, o, x, B.mass, make_float3(B.v0[0], B.v0[1], B.v0[2]), A, F, B.ps, B.vol, ((uint32_t)B.group << TAG_ID_BITS) | (B.id_base + lattice), b);
+    keys[o] = key;
+  }
+}
+
+// ------------------------------------------------------------------------------ AoS write-back
+// mpmb_download_aos on the device: every live row goes back into its slot of the (device image of the) reference's
+// pool and raises the alive flag of its id; the survivors' slots, in id order, are then one stream compaction away.
+__global__ void k_aos_scatter(View V, const uint32_t *keys, int n, uint32_t special_min, unsigned char *pool, const uint32_t *indices,
+                              int64_t n_indices, int64_t pool_slots, MpmbAosLayout L, uint32_t id_base, int *alive_flag, Counters *cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (keys[i] >= special_min) return;
+  const float4 q0 = V.q[0][i], q1 = V.q[1][i], q4 = V.q[4][i], q5 = V.q[5][i], q6 = V.q[6][i], q7 = V.q[7][i], q8 = V.q[8][i], q9 = V.q[9][i];
+  const uint32_t id = (__float_as_uint(q6.w) & TAG_ID_MASK) - id_base;
+  if ((int64_t)id >= n_indices) { atomicOr(&cnt->error, DEVERR_BAD_INPUT); return; }
+  const uint32_t slot = indices[id];
+  if ((int64_t)slot >= pool_slots) { atomicOr(&cnt->error, DEVERR_BAD_INPUT); return; }
+  alive_flag[id] = 1;
+  unsigned char *sl = pool + (size_t)slot * L.stride;
+  float *pos = (float *)(sl + L.off_pos), *vm = (float *)(sl + L.off_v_and_m);
+  pos[0] = q0.x; pos[1] = q0.y; pos[2] = q0.z;
+  vm[0] = q1.x; vm[1] = q1.y; vm[2] = q1.z; vm[3] = fabsf(q0.w);
+  const float Fm[9] = {q4.x, q4.y, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, q6.x}, bm[9] = {q7.x, q7.y, q7.z, q7.w, q8.x, q8.y, q8.z, q8.w, q9.x};
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    float *fc = (float *)(sl + L.off_dg_e + c * L.col_pitch), *bc = (float *)(sl + L.off_apic_b + c * L.col_pitch);
+#pragma unroll
+    for (int r = 0; r < 3; r++) { fc[r] = Fm[c * 3 + r]; bc[r] = bm[c * 3 + r]; }
+  }
+  if (L.off_scalar >= 0) *(float *)(sl + L.off_scalar) = q6.y;
+}
+__global__ void k_compact_survivors(const uint32_t *indices, const int *alive_flag, const int *prefix, int64_t n, uint32_t *out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && alive_flag[i]) out[prefix[i]] = indices[i];
 }
 
 // ------------------------------------------------------------------------------ ordering
@@ -499,9 +675,9 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
     const int nrow_tile = tm.run_len + tm.arr_len;
     MPMB_TILE_XYZ(P, tm, tx, ty, tz);
     const float fbx = (float)(tx * 4 + cx), fby = (float)(ty * 4 + cy), fbz = (float)(tz * 4 + cz);
-    float acc[27][4];
+    F4 acc[27];  // (p_x, p_y | p_z, m) of the 27 nodes of my cell's stencil
 #pragma unroll
-    for (int n = 0; n < 27; n++) { acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f; }
+    for (int n = 0; n < 27; n++) acc[n] = f4_zero();
     for (int n = tid; n < AR_SIZE; n += P2G_T) { s_arena[0][n] = 0.f; s_arena[1][n] = 0.f; s_arena[2][n] = 0.f; s_arena[3][n] = 0.f; }
     int vbase = 0;  // valid rows in the chunks already processed
     // storage row of tile-row g: run rows first, then arrivals
@@ -625,21 +801,25 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
         const float q0 = fmaf(a3.y, rz, fmaf(a2.z, ry, fmaf(a1.w, rx, mass * vx)));
         const float q1 = fmaf(a3.z, rz, fmaf(a2.w, ry, fmaf(a2.x, rx, mass * vy)));
         const float q2 = fmaf(a3.w, rz, fmaf(a3.x, ry, fmaf(a2.y, rx, mass * vz)));
+        // (momentum | mass) as register pairs; the mass lane rides along with zero column entries
+        const F4 Q = {make_float2(q0, q1), make_float2(q2, mass)};
+        const F4 c0 = {make_float2(a1.w, a2.x), make_float2(a2.y, 0.f)}, c1 = {make_float2(a2.z, a2.w), make_float2(a3.x, 0.f)},
+                 c2 = {make_float2(a3.y, a3.z), make_float2(a3.w, 0.f)};
+        const float2 m2 = bc2(-2.0f);
+        const float2 wx2[3] = {bc2(wx[0]), bc2(wx[1]), bc2(wx[2])}, wy2[3] = {bc2(wy[0]), bc2(wy[1]), bc2(wy[2])},
+                     wz2[3] = {bc2(wz[0]), bc2(wz[1]), bc2(wz[2])};
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-          const float ux = q0 - (float)i * a1.w, uy = q1 - (float)i * a2.x, uz = q2 - (float)i * a2.y;
+          const F4 U = i == 0 ? Q : (i == 1 ? f4_sub(Q, c0) : f4_fma(m2, c0, Q));    // q - i c0
 #pragma unroll
           for (int j = 0; j < 3; j++) {
-            const float tx_ = ux - (float)j * a2.z, ty_ = uy - (float)j * a2.w, tz_ = uz - (float)j * a3.x;
-            const float wij = wx[i] * wy[j];
+            const F4 T = j == 0 ? U : (j == 1 ? f4_sub(U, c1) : f4_fma(m2, c1, U));  // ... - j c1
+            const float2 wij = mul2(wx2[i], wy2[j]);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-              const float w = wij * wz[k];
-              float *a = acc[i * 9 + j * 3 + k];
-              a[0] = fmaf(w, tx_ - (float)k * a3.y, a[0]);
-              a[1] = fmaf(w, ty_ - (float)k * a3.z, a[1]);
-              a[2] = fmaf(w, tz_ - (float)k * a3.w, a[2]);
-              a[3] = fmaf(w, mass, a[3]);
+              const float2 w = mul2(wij, wz2[k]);
+              const F4 N = k == 0 ? T : (k == 1 ? f4_sub(T, c2) : f4_fma(m2, c2, T));  // ... - k c2
+              acc[i * 9 + j * 3 + k] = f4_fma(w, N, acc[i * 9 + j * 3 + k]);
             }
           }
         }
@@ -665,11 +845,11 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
 #pragma unroll
           for (int k = 0; k < 3; k++) {
             const int node = nb + i * AR_SX + j * AR_SY + k;
-            const float *a = acc[i * 9 + j * 3 + k];
-            ar[0][node] += a[0];
-            ar[1][node] += a[1];
-            ar[2][node] += a[2];
-            ar[3][node] += a[3];
+            const F4 &a = acc[i * 9 + j * 3 + k];
+            ar[0][node] += a.lo.x;
+            ar[1][node] += a.lo.y;
+            ar[2][node] += a.hi.x;
+            ar[3][node] += a.hi.y;
             __syncwarp();
           }
     }
@@ -786,9 +966,12 @@ constexpr int G2P_CH = 256;  // rows per pipeline stage
 // host (downloads, visualize, save).
 template <int BLOCK, bool STORE_B>
 __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4 *vel, int part) {
-  __shared__ float4 s_vel[2][ARENA];
-  __shared__ float4 s_in[2][4][G2P_CH];
-  __shared__ uint32_t s_out[2][G2P_CH];  // output row of every staged row
+  __shared__ __align__(16) float4 s_vel[2][ARENA];
+  __shared__ __align__(16) float4 s_in[2][4][G2P_CH];
+  // output row of every staged row: run rows at [sh + r] (sh = 16-byte alignment shift of the run's outpos words),
+  // arrival rows at [r + 8] — clear of the up to 3 words by which the bulk copy of the run part is rounded up
+  __shared__ __align__(16) uint32_t s_out[2][G2P_CH + 8];
+  __shared__ __align__(8) uint64_t s_bar[2];               // one mbarrier per pipeline stage
   __shared__ int s_stay;
   constexpr int KPT = G2P_CH / BLOCK;
   const int tid = threadIdx.x;
@@ -812,68 +995,81 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
     if (it.rb + G2P_CH < it.tm.run_len + it.tm.arr_len) { Item n = it; n.rb += G2P_CH; n.first = 0; return n; }
     return first_item(it.slot + (int)gridDim.x);
   };
-  // puts one item in flight: rows of the G2P set (x|mass, F, scalar|vol|tag), their output rows and, for
-  // the first chunk of a tile, the tile's node velocities
+  // rows of the chunk that lie inside the tile's run (unit stride in storage) / alignment shift of their outpos words
+  auto run_rows = [&](const Item &it) { return max(0, min(G2P_CH, it.tm.run_len - it.rb)); };
+  auto out_shift = [&](const Item &it) { return run_rows(it) > 0 ? (int)((uint32_t)(it.tm.run_begin + it.rb) & 3u) : 0; };
+  // puts one item in flight: rows of the G2P set (x|mass, F, scalar|vol|tag), their output rows and, for the first
+  // chunk of a tile, the tile's node velocities.  The run part of the chunk and the node block are TMA bulk copies
+  // issued by thread 0 and tracked by the stage's mbarrier; the (few) arrival rows are gathered with 16-byte
+  // LDGSTS copies by the thread that will consume them, tracked by its own copy groups.
   auto prefetch = [&](const Item &it, int buf, int vbuf) {
     if (it.slot < n_tiles) {
       const int nrow_tile = it.tm.run_len + it.tm.arr_len;
       const int nrows = min(G2P_CH, nrow_tile - it.rb);
-      uint32_t pidx[KPT];
-      if (it.rb + nrows <= it.tm.run_len) {  // whole chunk inside the run: no loads
-#pragma unroll
-        for (int k = 0; k < KPT; k++) pidx[k] = (uint32_t)(it.tm.run_begin + it.rb + k * BLOCK + tid);
-      } else {
+      const int nrun = run_rows(it);
+      const int sh = out_shift(it);
+      if (tid == 0) {
+        const uint32_t r0 = (uint32_t)(it.tm.run_begin + it.rb);
+        const unsigned row_bytes = (unsigned)nrun * 16u, out_bytes = nrun > 0 ? (((unsigned)(sh + nrun) * 4u + 15u) & ~15u) : 0u;
+        mbar_arrive_expect_tx(&s_bar[buf], 4u * row_bytes + out_bytes + (it.first ? (unsigned)(ARENA * sizeof(float4)) : 0u));
+        if (nrun > 0) {
+          bulk_g2s(&s_in[buf][0][0], &V.q[0][r0], row_bytes, &s_bar[buf]);
+          bulk_g2s(&s_in[buf][1][0], &V.q[4][r0], row_bytes, &s_bar[buf]);
+          bulk_g2s(&s_in[buf][2][0], &V.q[5][r0], row_bytes, &s_bar[buf]);
+          bulk_g2s(&s_in[buf][3][0], &V.q[6][r0], row_bytes, &s_bar[buf]);
+          bulk_g2s(&s_out[buf][0], &V.outpos[r0 - (uint32_t)sh], out_bytes, &s_bar[buf]);
+        }
+        if (it.first) bulk_g2s(&s_vel[vbuf][0], vel + (size_t)it.slot * ARENA, (unsigned)(ARENA * sizeof(float4)), &s_bar[buf]);
+      }
+      if (nrun < nrows) {
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
-          const int r = k * BLOCK + tid, g = it.rb + r;
-          pidx[k] = 0u;
-          if (r < nrows) pidx[k] = g < it.tm.run_len ? (uint32_t)(it.tm.run_begin + g) : V.arrivals_sorted[it.tm.arr_off + (g - it.tm.run_len)];
-        }
-      }
-      if (it.first) {
-        const float4 *src = vel + (size_t)it.slot * ARENA;
-        for (int n = tid; n < ARENA; n += BLOCK) cp_async16(&s_vel[vbuf][n], &src[n]);
-      }
-#pragma unroll
-      for (int k = 0; k < KPT; k++) {
-        const int r = k * BLOCK + tid;
-        if (r < nrows) {
-          cp_async16(&s_in[buf][0][r], &V.q[0][pidx[k]]);
-          cp_async16(&s_in[buf][1][r], &V.q[4][pidx[k]]);
-          cp_async16(&s_in[buf][2][r], &V.q[5][pidx[k]]);
-          cp_async16(&s_in[buf][3][r], &V.q[6][pidx[k]]);
-          unsigned d = (unsigned)__cvta_generic_to_shared(&s_out[buf][r]);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(&V.outpos[pidx[k]]));
+          const int r = k * BLOCK + tid;
+          if (r >= nrun && r < nrows) {
+            const uint32_t pidx = V.arrivals_sorted[it.tm.arr_off + (it.rb + r - it.tm.run_len)];
+            cp_async16(&s_in[buf][0][r], &V.q[0][pidx]);
+            cp_async16(&s_in[buf][1][r], &V.q[4][pidx]);
+            cp_async16(&s_in[buf][2][r], &V.q[5][pidx]);
+            cp_async16(&s_in[buf][3][r], &V.q[6][pidx]);
+            unsigned d = (unsigned)__cvta_generic_to_shared(&s_out[buf][r + 8]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(&V.outpos[pidx]));
+          }
         }
       }
     }
     cp_async_commit();
   };
-  if (tid == 0) s_stay = 0;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_init_fence();
+    s_stay = 0;
+  }
+  __syncthreads();
   Item cur = first_item(blockIdx.x);
   int buf = 0, vbuf = 0;
+  unsigned phase = 0;  // bit b = parity of the phase stage b's barrier is in
   prefetch(cur, 0, 0);
   while (cur.slot < n_tiles) {
     const Item nxt = next_item(cur);
     const int nvbuf = nxt.first ? (vbuf ^ 1) : vbuf;
     prefetch(nxt, buf ^ 1, nvbuf);
-    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // the current item has landed, the next stays in flight
-    __syncthreads();
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // my arrival rows of the current item have landed; the next item stays in flight
+    mbar_wait(&s_bar[buf], (phase >> buf) & 1u);              // ... and so have its bulk copies (every thread reads only rows it waited for)
+    phase ^= 1u << buf;
     {
       const int tile = cur.tm.tile;
+      const int sh = out_shift(cur), nrun = run_rows(cur);
       MPMB_TILE_XYZ(P, cur.tm, tx, ty, tz);
       const int nrows = min(G2P_CH, cur.tm.run_len + cur.tm.arr_len - cur.rb);
       const float4 *sv = s_vel[vbuf];
       int my_stay = 0;
       for (int r = tid; r < nrows; r += BLOCK) {
-        const float4 q0 = s_in[buf][0][r], q4 = s_in[buf][1][r], q5 = s_in[buf][2][r], q6 = s_in[buf][3][r];
+        const float4 q0 = s_in[buf][0][r];
         // run rows with negative mass are holes (the particle now belongs to another tile's arrivals);
         // same rule as k_p2g, so both kernels visit exactly the same particles
         if (cur.rb + r < cur.tm.run_len && !(q0.w > 0.f)) continue;
-        const size_t o = s_out[buf][r];
-        const float mass = fabsf(q0.w), vol = q6.z;
-        const uint32_t tag = __float_as_uint(q6.w);
-        const Material &mat = P.mats[tag >> TAG_ID_BITS];
+        const float mass = fabsf(q0.w);
         int bx, by, bz;
         float rx, ry, rz;
         base_rel(q0.x, P.inv_dx, bx, rx);
@@ -886,37 +1082,38 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
         bspline_weights(rz, wz);
         // v = sum w g ; b = sum w g (x) (rel - node) = v (x) rel - [sum_i i S_i | sum_j j T_j | sum_k k R_k]
         // (src/transfer.cpp:888-904), evaluated slab by slab: ~250 FMA instead of 27*16.
-        const float wz2x = 2.0f * wz[2], wy2x = 2.0f * wy[2], wx2x = 2.0f * wx[2];
-        float3 v = make_float3(0.f, 0.f, 0.f), colx = v, coly = v, colz = v;
+        // every node value (v_x,v_y | v_z,m) as two pairs; the mass lane of the sums is never read
+        const float2 wz0 = bc2(wz[0]), wz1 = bc2(wz[1]), wz2 = bc2(wz[2]), wz2x = bc2(2.0f * wz[2]);
+        const float2 wy2[3] = {bc2(wy[0]), bc2(wy[1]), bc2(wy[2])}, wx2[3] = {bc2(wx[0]), bc2(wx[1]), bc2(wx[2])};
+        const float2 wyj[3] = {wy2[0], wy2[1], bc2(2.0f * wy[2])}, wxi[3] = {wx2[0], wx2[1], bc2(2.0f * wx[2])};
+        F4 V4 = f4_zero(), CX = f4_zero(), CY = f4_zero(), CZ = f4_zero();
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-          float3 pi = make_float3(0.f, 0.f, 0.f), jy = pi, kz = pi;
+          F4 pi = f4_zero(), jy = f4_zero(), kz = f4_zero();
 #pragma unroll
           for (int jn = 0; jn < 3; jn++) {
             const int row = ((bx + i) * 6 + (by + jn)) * 6 + bz;
-            const float4 g0 = sv[row], g1 = sv[row + 1], g2 = sv[row + 2];
-            float3 a, c;
-            a.x = fmaf(wz[2], g2.x, fmaf(wz[1], g1.x, wz[0] * g0.x));
-            a.y = fmaf(wz[2], g2.y, fmaf(wz[1], g1.y, wz[0] * g0.y));
-            a.z = fmaf(wz[2], g2.z, fmaf(wz[1], g1.z, wz[0] * g0.z));
-            c.x = fmaf(wz2x, g2.x, wz[1] * g1.x);
-            c.y = fmaf(wz2x, g2.y, wz[1] * g1.y);
-            c.z = fmaf(wz2x, g2.z, wz[1] * g1.z);
-            pi.x = fmaf(wy[jn], a.x, pi.x); pi.y = fmaf(wy[jn], a.y, pi.y); pi.z = fmaf(wy[jn], a.z, pi.z);
-            kz.x = fmaf(wy[jn], c.x, kz.x); kz.y = fmaf(wy[jn], c.y, kz.y); kz.z = fmaf(wy[jn], c.z, kz.z);
-            if (jn > 0) {
-              const float wj = jn == 1 ? wy[1] : wy2x;
-              jy.x = fmaf(wj, a.x, jy.x); jy.y = fmaf(wj, a.y, jy.y); jy.z = fmaf(wj, a.z, jy.z);
-            }
+            const F4 g0 = f4_load(sv[row]), g1 = f4_load(sv[row + 1]), g2 = f4_load(sv[row + 2]);
+            const F4 a = f4_fma(wz2, g2, f4_fma(wz1, g1, f4_mul(wz0, g0)));
+            const F4 c = f4_fma(wz2x, g2, f4_mul(wz1, g1));
+            pi = f4_fma(wy2[jn], a, pi);
+            kz = f4_fma(wy2[jn], c, kz);
+            if (jn > 0) jy = f4_fma(wyj[jn], a, jy);
           }
-          v.x = fmaf(wx[i], pi.x, v.x); v.y = fmaf(wx[i], pi.y, v.y); v.z = fmaf(wx[i], pi.z, v.z);
-          coly.x = fmaf(wx[i], jy.x, coly.x); coly.y = fmaf(wx[i], jy.y, coly.y); coly.z = fmaf(wx[i], jy.z, coly.z);
-          colz.x = fmaf(wx[i], kz.x, colz.x); colz.y = fmaf(wx[i], kz.y, colz.y); colz.z = fmaf(wx[i], kz.z, colz.z);
-          if (i > 0) {
-            const float wi = i == 1 ? wx[1] : wx2x;
-            colx.x = fmaf(wi, pi.x, colx.x); colx.y = fmaf(wi, pi.y, colx.y); colx.z = fmaf(wi, pi.z, colx.z);
-          }
+          V4 = f4_fma(wx2[i], pi, V4);
+          CY = f4_fma(wx2[i], jy, CY);
+          CZ = f4_fma(wx2[i], kz, CZ);
+          if (i > 0) CX = f4_fma(wxi[i], pi, CX);
         }
+        const float3 v = make_float3(V4.lo.x, V4.lo.y, V4.hi.x), colx = make_float3(CX.lo.x, CX.lo.y, CX.hi.x),
+                     coly = make_float3(CY.lo.x, CY.lo.y, CY.hi.x), colz = make_float3(CZ.lo.x, CZ.lo.y, CZ.hi.x);
+        // the rest of the particle's row is read only now: nothing of it is live across the gather (registers)
+        asm volatile("" ::: "memory");
+        const float4 q4 = s_in[buf][1][r], q5 = s_in[buf][2][r], q6 = s_in[buf][3][r];
+        const size_t o = s_out[buf][r < nrun ? sh + r : r + 8];
+        const float vol = q6.z;
+        const uint32_t tag = __float_as_uint(q6.w);
+        const Material &mat = P.mats[tag >> TAG_ID_BITS];
         Mat3 B;
         B.m[0] = fmaf(v.x, rx, -colx.x); B.m[1] = fmaf(v.y, rx, -colx.y); B.m[2] = fmaf(v.z, rx, -colx.z);
         B.m[3] = fmaf(v.x, ry, -coly.x); B.m[4] = fmaf(v.y, ry, -coly.y); B.m[5] = fmaf(v.z, ry, -coly.z);
@@ -1149,6 +1346,16 @@ struct MpmbEngine {
   bool skip_b = false;        // intermediate substeps of mpmb_substep do not store apic_b
   void *stage_buf = nullptr;  // cached staging buffer of the host<->device marshalling
   size_t stage_bytes = 0;
+  // device image of the reference's AoS pool + index vector, kept from mpmb_upload_aos to mpmb_download_aos
+  unsigned char *aos_pool = nullptr;
+  uint32_t *aos_idx = nullptr;
+  size_t aos_pool_bytes = 0, aos_idx_cap = 0;
+  const void *aos_host_pool = nullptr;  // identity of the image: host pool pointer, slots and particle count
+  int64_t aos_slots = 0, aos_n = 0;
+  int *scan_a = nullptr, *scan_b = nullptr;  // flags / prefix scratch (downloads, seeding)
+  size_t scan_cap = 0;
+  void *scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
   uint32_t id_base = 0;
   int num_sms = 148;
   int nt2_global = 0;  // tile layers of the whole domain (P.nt[2] is slab-local)
@@ -1280,7 +1487,7 @@ static int alloc_particles(MpmbEngine *h, int64_t cap) {
     CUDA_TRY(h, cudaMalloc(&h->mover_dst[b], sizeof(uint32_t) * cap));
     CUDA_TRY(h, cudaMalloc(&h->mover_idx[b], sizeof(uint32_t) * cap));
   }
-  CUDA_TRY(h, cudaMalloc(&h->outpos, sizeof(uint32_t) * cap));
+  CUDA_TRY(h, cudaMalloc(&h->outpos, sizeof(uint32_t) * (cap + 8)));  // the bulk copy of a run's words is widened to 16-byte bounds
   CUDA_TRY(h, cudaMalloc(&h->arrivals, sizeof(uint32_t) * cap));
   CUDA_TRY(h, cudaMalloc(&h->arrivals_sorted, sizeof(uint32_t) * cap));
   CUDA_TRY(h, cudaMalloc(&h->keys_sorted, sizeof(uint32_t) * cap));
@@ -1417,6 +1624,7 @@ int mpmb_destroy(MpmbHandle h) {
   cudaFree(h->arr_cnt); cudaFree(h->arr_off); cudaFree(h->arr_len); cudaFree(h->arr_cur); cudaFree(h->slot_map); cudaFree(h->blocksum);
   cudaFree(h->meta);
   cudaFree(h->arena); cudaFree(h->vel); cudaFree(h->sdf4); cudaFree(h->cnt); cudaFree(h->stage_buf); cudaFree(h->xcount);
+  cudaFree(h->aos_pool); cudaFree(h->aos_idx); cudaFree(h->scan_a); cudaFree(h->scan_b); cudaFree(h->scan_tmp);
   for (int k = 0; k < 2; k++)
     for (int f = 0; f < 2; f++) {
       if (h->tx_ipc[k][f] && h->tx[k][f]) cudaIpcCloseMemHandle(h->tx[k][f]);
@@ -1538,6 +1746,7 @@ int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *
   CHECK_HANDLE(h);
   if (n < 0 || (n > 0 && (!x || !v || !mass || !vol))) return fail(h, MPMB_ERR_INVALID, "x, v, mass, vol are required");
   if ((int64_t)h->id_base + n > (1ll << TAG_ID_BITS)) return fail(h, MPMB_ERR_CAPACITY, "particle ids exceed 2^%d", TAG_ID_BITS);
+  h->aos_host_pool = nullptr;
   int rc = ensure_capacity(h, n);
   if (rc != MPMB_OK) return rc;
   if (n == 0) return finish_upload(h, 0);
@@ -1572,6 +1781,55 @@ int mpmb_upload_particles(MpmbHandle h, int64_t n, const float *x, const float *
   return finish_upload(h, n);
 }
 
+// flags / exclusive prefix scratch for n items (grow-only) and the CUB scan over them
+static int scan_reserve(MpmbEngine *h, size_t n) {
+  if (n + 1 > h->scan_cap) {
+    cudaFree(h->scan_a); cudaFree(h->scan_b);
+    h->scan_a = h->scan_b = nullptr;
+    h->scan_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&h->scan_a, sizeof(int) * (n + 1)));
+    CUDA_TRY(h, cudaMalloc(&h->scan_b, sizeof(int) * (n + 1)));
+    h->scan_cap = n + 1;
+  }
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, h->scan_a, h->scan_b, (int)(n + 1), h->stream);
+  if (need > h->scan_tmp_bytes) {
+    cudaFree(h->scan_tmp);
+    h->scan_tmp = nullptr;
+    h->scan_tmp_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->scan_tmp, need));
+    h->scan_tmp_bytes = need;
+  }
+  return MPMB_OK;
+}
+// prefix = exclusive scan of flags over n (+1 so that prefix[n] is the total); returns the total
+static int scan_flags(MpmbEngine *h, size_t n, int *total) {
+  CUDA_TRY(h, cudaMemsetAsync(h->scan_a + n, 0, sizeof(int), h->stream));
+  size_t bytes = h->scan_tmp_bytes;
+  cub::DeviceScan::ExclusiveSum(h->scan_tmp, bytes, h->scan_a, h->scan_b, (int)(n + 1), h->stream);
+  CUDA_TRY(h, cudaMemcpyAsync(total, h->scan_b + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPMB_OK;
+}
+
+static int aos_reserve(MpmbEngine *h, size_t pool_bytes, size_t n_idx) {
+  if (pool_bytes > h->aos_pool_bytes) {
+    cudaFree(h->aos_pool);
+    h->aos_pool = nullptr;
+    h->aos_pool_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->aos_pool, pool_bytes));
+    h->aos_pool_bytes = pool_bytes;
+  }
+  if (n_idx > h->aos_idx_cap) {
+    cudaFree(h->aos_idx);
+    h->aos_idx = nullptr;
+    h->aos_idx_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&h->aos_idx, sizeof(uint32_t) * n_idx));
+    h->aos_idx_cap = n_idx;
+  }
+  return MPMB_OK;
+}
+
 int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slots, const uint32_t *indices,
                     const MpmbAosLayout *L, const int32_t *group) {
   CHECK_HANDLE(h);
@@ -1579,24 +1837,82 @@ int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slot
   if ((int64_t)h->id_base + n > (1ll << TAG_ID_BITS)) return fail(h, MPMB_ERR_CAPACITY, "particle ids exceed 2^%d", TAG_ID_BITS);
   int rc = ensure_capacity(h, n);
   if (rc != MPMB_OK) return rc;
+  h->aos_host_pool = nullptr;
   if (n == 0) return finish_upload(h, 0);
-  unsigned char *d_pool = nullptr;
-  uint32_t *d_idx = nullptr;
+  // the pool's device image and the index vector stay resident (grow-only buffers): mpmb_download_aos scatters the
+  // results into the image and returns it with one contiguous copy
+  const size_t pool_bytes = (size_t)pool_slots * L->stride;
+  if ((rc = aos_reserve(h, pool_bytes, (size_t)n)) != MPMB_OK) return rc;
   int *d_grp = nullptr;
-  CUDA_TRY(h, cudaMalloc(&d_pool, (size_t)pool_slots * L->stride));
-  CUDA_TRY(h, cudaMalloc(&d_idx, sizeof(uint32_t) * n));
-  if (group) CUDA_TRY(h, cudaMalloc(&d_grp, sizeof(int) * n));
-  cudaMemcpyAsync(d_pool, pool, (size_t)pool_slots * L->stride, cudaMemcpyHostToDevice, h->stream);
-  cudaMemcpyAsync(d_idx, indices, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, h->stream);
-  if (group) cudaMemcpyAsync(d_grp, group, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream);
+  if (group) {
+    if (h->stage_bytes < sizeof(int) * (size_t)n) {
+      cudaFree(h->stage_buf);
+      h->stage_buf = nullptr;
+      h->stage_bytes = 0;
+      CUDA_TRY(h, cudaMalloc(&h->stage_buf, sizeof(int) * (size_t)n));
+      h->stage_bytes = sizeof(int) * (size_t)n;
+    }
+    d_grp = (int *)h->stage_buf;
+    CUDA_TRY(h, cudaMemcpyAsync(d_grp, group, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->aos_idx, indices, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->aos_pool, pool, pool_bytes, cudaMemcpyHostToDevice, h->stream));
   View V = make_view(h);
-  k_pack_aos<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(V, h->P, (int)n, d_pool, d_idx, *L, d_grp, h->keys[h->cur], h->id_base);
+  k_pack_aos<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(V, h->P, (int)n, h->aos_pool, h->aos_idx, *L, d_grp, h->keys[h->cur], h->id_base);
   h->launches++;
-  cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_pool); cudaFree(d_idx); cudaFree(d_grp);
-  CUDA_TRY(h, e);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   CUDA_TRY(h, cudaGetLastError());
+  h->aos_host_pool = pool;
+  h->aos_slots = pool_slots;
+  h->aos_n = n;
   return finish_upload(h, n);
+}
+
+int mpmb_seed_lattice(MpmbHandle h, const int32_t lo_cell[3], const int32_t hi_cell[3], float vol, float mass, float jitter, uint32_t seed,
+                      int32_t group, const float v0[3], int64_t *n_seeded) {
+  CHECK_HANDLE(h);
+  if (!lo_cell || !hi_cell) return fail(h, MPMB_ERR_INVALID, "null argument");
+  if (group < 0 || group >= MPMB_MAX_GROUPS || !(mass > 0.f) || !(vol > 0.f)) return fail(h, MPMB_ERR_INVALID, "bad group, mass or volume");
+  SeedBox B{};
+  size_t cells = 1;
+  for (int d = 0; d < 3; d++) {
+    B.lo[d] = lo_cell[d];
+    B.n[d] = hi_cell[d] - lo_cell[d];
+    if (B.n[d] <= 0 || lo_cell[d] < 0 || hi_cell[d] > h->P.res[d]) return fail(h, MPMB_ERR_INVALID, "empty or out-of-domain cell block");
+    cells *= (size_t)B.n[d];
+    B.v0[d] = v0 ? v0[d] : 0.f;
+  }
+  if (cells * 8 + (size_t)h->id_base > (size_t)(1ll << TAG_ID_BITS)) return fail(h, MPMB_ERR_CAPACITY, "lattice ids exceed 2^%d", TAG_ID_BITS);
+  // candidate cell layers: a particle of cell layer kz has its base node in layer kz-1 or kz (|jitter| < 0.25)
+  B.z_first = 0;
+  B.z_count = B.n[2];
+  if (h->cfg.world > 1) {
+    const int c0 = std::max(B.lo[2], 4 * h->P.tile_z0 - 1), c1 = std::min(B.lo[2] + B.n[2], 4 * h->P.tile_z1 + 2);
+    B.z_first = c0 - B.lo[2];
+    B.z_count = std::max(0, c1 - c0);
+  }
+  B.jitter = jitter; B.vol = vol; B.mass = mass; B.seed = seed; B.id_base = h->id_base; B.group = group;
+  const int kind = h->P.mats[group].kind;
+  B.ps = (kind == MAT_SNOW || kind == MAT_WATER) ? 1.0f : 0.0f;
+  const size_t n_cand = (size_t)B.n[0] * B.n[1] * (size_t)B.z_count * 8;
+  h->aos_host_pool = nullptr;
+  if (n_cand >= (size_t)0x7fffffff) return fail(h, MPMB_ERR_CAPACITY, "too many candidate particles for one rank");
+  int total = 0, rc;
+  if (n_cand > 0) {
+    if ((rc = scan_reserve(h, n_cand)) != MPMB_OK) return rc;
+    k_seed_flags<<<h->num_sms * 8, 256, 0, h->stream>>>(h->P, B, n_cand, h->scan_a);
+    if ((rc = scan_flags(h, n_cand, &total)) != MPMB_OK) return rc;
+  }
+  if ((rc = ensure_capacity(h, total)) != MPMB_OK) return rc;
+  if (total > 0) {
+    View V = make_view(h);
+    k_seed_write<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, B, n_cand, h->scan_a, h->scan_b, h->keys[h->cur]);
+    h->launches += 2;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  if (n_seeded) *n_seeded = total;
+  return finish_upload(h, total);
 }
 
 static int read_n_store(MpmbEngine *h, int *n_store) {
@@ -1702,37 +2018,41 @@ int mpmb_download_particles(MpmbHandle h, int64_t cap, int64_t *n_out, uint32_t 
 int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *indices, int64_t n_indices, const MpmbAosLayout *L,
                       int64_t *n_alive) {
   CHECK_HANDLE(h);
-  if (!pool || !indices || !L || !n_alive) return fail(h, MPMB_ERR_INVALID, "null argument");
-  int ns_ = 0;
-  { int rc0 = mpmb_synchronize(h); if (rc0 != MPMB_OK) return rc0; rc0 = read_n_store(h, &ns_); if (rc0 != MPMB_OK) return rc0; }
-  int64_t cap = ns_ > 0 ? ns_ : 1, n = 0;
-  std::vector<uint32_t> id(cap);
-  std::vector<float> x(3 * cap), v(3 * cap), F(9 * cap), b(9 * cap), mass(cap), vol(cap), sc(cap);
-  int rc = mpmb_download_particles(h, cap, &n, id.data(), x.data(), v.data(), F.data(), b.data(), mass.data(), vol.data(), sc.data(), nullptr);
-  if (rc != MPMB_OK) return rc;
-  std::vector<uint32_t> survivors;
-  survivors.reserve(n);
-  std::vector<std::pair<uint32_t, int64_t>> by_id(n);
-  for (int64_t k = 0; k < n; k++) by_id[k] = {id[k], k};
-  std::sort(by_id.begin(), by_id.end());
-  for (auto &pr : by_id) {
-    if ((int64_t)pr.first >= n_indices) return fail(h, MPMB_ERR_INVALID, "particle id %u outside the index vector", pr.first);
-    uint32_t slot = indices[pr.first];
-    if ((int64_t)slot >= pool_slots) return fail(h, MPMB_ERR_INVALID, "slot %u outside the pool", slot);
-    int64_t k = pr.second;
-    unsigned char *s = (unsigned char *)pool + (size_t)slot * L->stride;
-    float *pos = (float *)(s + L->off_pos), *vm = (float *)(s + L->off_v_and_m);
-    for (int d = 0; d < 3; d++) { pos[d] = x[3 * k + d]; vm[d] = v[3 * k + d]; }
-    vm[3] = mass[k];
-    for (int c = 0; c < 3; c++) {
-      float *fc = (float *)(s + L->off_dg_e + c * L->col_pitch), *bc = (float *)(s + L->off_apic_b + c * L->col_pitch);
-      for (int r = 0; r < 3; r++) { fc[r] = F[9 * k + c * 3 + r]; bc[r] = b[9 * k + c * 3 + r]; }
-    }
-    if (L->off_scalar >= 0) *(float *)(s + L->off_scalar) = sc[k];
-    survivors.push_back(slot);
+  if (!pool || !indices || !L || !n_alive || L->stride <= 0 || n_indices < 0) return fail(h, MPMB_ERR_INVALID, "null argument");
+  int ns = 0, rc;
+  if ((rc = mpmb_synchronize(h)) != MPMB_OK) return rc;
+  if ((rc = read_n_store(h, &ns)) != MPMB_OK) return rc;
+  *n_alive = 0;
+  if (n_indices == 0) return MPMB_OK;
+  const size_t pool_bytes = (size_t)pool_slots * L->stride;
+  // the device image of the pool: still resident from mpmb_upload_aos of the same pool, else brought in now
+  const bool resident = h->aos_host_pool == pool && h->aos_slots == pool_slots && h->aos_n == n_indices && h->aos_pool;
+  if (!resident) {
+    if ((rc = aos_reserve(h, pool_bytes, (size_t)n_indices)) != MPMB_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->aos_idx, indices, sizeof(uint32_t) * n_indices, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->aos_pool, pool, pool_bytes, cudaMemcpyHostToDevice, h->stream));
   }
-  for (size_t k = 0; k < survivors.size(); k++) indices[k] = survivors[k];
-  *n_alive = n;
+  if ((rc = scan_reserve(h, (size_t)n_indices)) != MPMB_OK) return rc;
+  CUDA_TRY(h, cudaMemsetAsync(h->scan_a, 0, sizeof(int) * (size_t)n_indices, h->stream));
+  if (ns > 0 && h->cap > 0) {
+    View V = make_view(h);
+    k_aos_scatter<<<(ns + 127) / 128, 128, 0, h->stream>>>(V, h->keys[h->cur], ns, h->special_min, h->aos_pool, h->aos_idx, n_indices, pool_slots, *L,
+                                                           h->id_base, h->scan_a, h->cnt);
+    h->launches++;
+  }
+  int alive = 0;
+  if ((rc = scan_flags(h, (size_t)n_indices, &alive)) != MPMB_OK) return rc;
+  // survivors' slots in id order == what clear_boundary_particles leaves in MPM::particles (src/mpm.cpp:618-622)
+  uint32_t *d_surv = (uint32_t *)h->keys_sorted;  // upload-time scratch, free between uploads; cap >= n rows
+  if ((int64_t)h->cap < n_indices) return fail(h, MPMB_ERR_CAPACITY, "index vector longer than the particle capacity");
+  k_compact_survivors<<<(unsigned)((n_indices + 255) / 256), 256, 0, h->stream>>>(h->aos_idx, h->scan_a, h->scan_b, n_indices, d_surv);
+  h->launches++;
+  CUDA_TRY(h, cudaMemcpyAsync(pool, h->aos_pool, pool_bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (alive > 0) CUDA_TRY(h, cudaMemcpyAsync(indices, d_surv, sizeof(uint32_t) * (size_t)alive, cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = mpmb_synchronize(h)) != MPMB_OK) return rc;   // also surfaces ids / slots outside the vectors
+  CUDA_TRY(h, cudaGetLastError());
+  h->aos_host_pool = nullptr;   // the host owns the pool again: the next upload refreshes the image
+  *n_alive = alive;
   return MPMB_OK;
 }
 
@@ -1778,16 +2098,18 @@ int mpmb_rasterize(MpmbHandle h) {
 int mpmb_resample(MpmbHandle h) {
   CHECK_HANDLE(h);
   if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "resample must follow rasterize");
-  prof_begin(h, 2);
   View V = make_view(h);
+  prof_begin(h, 4);
+  if (h->cap > 0) k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, 0);
+  prof_end(h, 1);
+  prof_begin(h, 2);
   if (h->cap > 0) {
-    k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, 0);
     if (h->skip_b) k_g2p<128, false><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
     else k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
     k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt);
   }
   h->launches += 3;
-  prof_end(h, 3);
+  prof_end(h, 2);
   CUDA_TRY(h, cudaGetLastError());
   h->cur ^= 1;  // the buffer G2P wrote is the current storage ...
   h->ord ^= 1;  // ... its runs / stay counts are the current ones ...

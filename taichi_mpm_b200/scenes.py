@@ -70,6 +70,47 @@ def lattice_block(res, lo_cell, hi_cell, density=400.0, jitter=0.0, seed=2026092
     return x, mass, vol
 
 
+def seed_hash(idx, axis, seed):
+    """Counter-based hash of (lattice index, axis, seed) -> uint32; the numpy twin of seed_hash in csrc/mpmb_engine.cu."""
+    with np.errstate(over="ignore"):
+        h = (idx.astype(np.uint32) * np.uint32(3) + np.uint32(axis)) ^ np.uint32(seed)
+        h = h * np.uint32(0x9E3779B1)
+        h ^= h >> np.uint32(16)
+        h = h * np.uint32(0x85EBCA6B)
+        h ^= h >> np.uint32(13)
+        h = h * np.uint32(0xC2B2AE35)
+        h ^= h >> np.uint32(16)
+    return h
+
+
+def lattice_block_hashed(res, lo_cell, hi_cell, density=400.0, jitter=0.0, seed=20260922, z_cells=None):
+    """The `benchmark` lattice of MPM<3>::add_particles (src/mpm.cpp:149-186) with a jitter that is a hash of the
+    particle's lattice index — the host twin of mpmb_seed_lattice (device-side seeding), float32 operation for float32
+    operation, so both produce the same bits whatever the z-slab partition.  Returns (ids, x, mass, vol); particles in
+    the 7-cell boundary band are dropped as add_particles drops them (src/mpm.cpp:129-132).
+    z_cells = (k0, k1): only the cell layers lo[2]+k0 .. lo[2]+k1-1 (a slab's share), ids unchanged."""
+    if np.isscalar(res):
+        res = (res, res, res)
+    f32 = np.float32
+    dx = f32(1.0 / res[0])
+    lo = np.asarray(lo_cell, np.int64)
+    n = np.asarray(hi_cell, np.int64) - lo
+    k0, k1 = (0, int(n[2])) if z_cells is None else z_cells
+    kx, ky, kz, c = np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(k0, k1), np.arange(8), indexing="ij")
+    kx, ky, kz, c = (a.reshape(-1) for a in (kx, ky, kz, c))
+    lattice = (((kx * n[1] + ky) * n[2] + kz) * 8 + c).astype(np.uint32)
+    X = np.empty((len(lattice), 3), f32)
+    for a, k in enumerate((kx, ky, kz)):
+        off = np.where((c >> a) & 1, f32(0.75), f32(0.25)).astype(f32)
+        u = (seed_hash(lattice, a, seed) >> np.uint32(8)).astype(f32) * f32(1.0 / 8388608.0) - f32(1.0)
+        X[:, a] = ((lo[a] + k).astype(f32) + off) + f32(jitter) * u
+    x = X * dx
+    keep = (X.min(1) >= f32(7.0)) & ((X - np.asarray(res, f32)).max(1) <= f32(-7.0))
+    vol = np.full(int(keep.sum()), (1.0 / res[0]) ** 3 / 8.0, f32)
+    mass = (vol * f32(density)).astype(f32)
+    return lattice[keep], x[keep], mass, vol
+
+
 def make_state(x, mass, vol, kind, group=0, v0=(0.0, 0.0, 0.0)):
     n = len(x)
     F = np.zeros((n, 9), np.float32)

@@ -1,7 +1,8 @@
 """Builds tests/simt/_build/libmpmb_simt.so: the engine's CUDA source compiled for the HOST on top of the SIMT
 emulator (simt.h).  The product source is not modified; two kinds of sites are rewritten in a temporary copy:
   * kernel launches   name<<<grid, block, smem, stream>>>(args)  ->  SIMT_LAUNCH((name), grid, block, smem, stream)(args)
-  * inline PTX        cp.async copies / commit / wait, the system-scope release store and acquire load
+  * inline PTX        cp.async copies / commit / wait, the system-scope release store and acquire load; the mbarrier /
+                      TMA bulk-copy helpers carry their own emulator twins behind `#ifndef MPMB_SIMT_HOST ... #else`
 Everything else — kernels, device math, the C-ABI host code — is compiled as it stands, with <cuda_runtime.h> and
 <cub/...> resolving to the emulator's headers."""
 import os
@@ -19,6 +20,7 @@ LIB = os.path.join(OUT_DIR, "libmpmb_simt.so")
 RULES = [
     (re.compile(r'\b([A-Za-z_]\w*(?:<[^<>;]*>)?)<<<(.*?)>>>\('), r'SIMT_LAUNCH((\1), \2)('),
     (re.compile(r'asm volatile\("cp\.async\.c[ag]\.shared\.global \[%0\], \[%1\], (\d+);\\n" ::"r"\((\w+)\), "l"\((.*)\)\);'), r'simt::cp_async(\2, \3, \1);'),
+    (re.compile(r'asm volatile\("" ::: "memory"\);'), ';'),   # compiler-only barrier
     (re.compile(r'asm volatile\("cp\.async\.commit_group;\\n" ::\);'), ';'),
     (re.compile(r'asm volatile\("cp\.async\.wait_group \d+;\\n" ::: "memory"\);'), ';'),
     (re.compile(r'asm volatile\("st\.release\.sys\.global\.s32 \[%0\], %1;" ::"l"\((.*?)\), "r"\((.*?)\) : "memory"\);'), r'*(\1) = (\2);'),
@@ -26,7 +28,27 @@ RULES = [
 ]
 
 
+def drop_device_only(text):
+    """`#ifndef MPMB_SIMT_HOST ... #else` regions hold device-only inline PTX (mbarrier / TMA bulk copies) whose emulator
+    twins follow the #else: the device half is cut out before the rewrite rules and the leftover-asm check run."""
+    out, skip = [], False
+    for line in text.split("\n"):
+        st = line.strip()
+        if st == "#ifndef MPMB_SIMT_HOST":
+            skip = True
+            out.append("#if 1  // MPMB_SIMT_HOST: device half removed by build_simt.py")
+            continue
+        if skip:
+            if st == "#else":
+                skip = False
+            out.append("")      # keep line numbers
+            continue
+        out.append(line)
+    return "\n".join(out)
+
+
 def transform(text):
+    text = drop_device_only(text)
     for rx, rep in RULES:
         text = rx.sub(rep, text)
     left = [l for l in text.splitlines() if "<<<" in l or re.search(r"\basm\b", l)]

@@ -27,6 +27,7 @@
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __restrict__ __restrict
+#define __align__(n) __attribute__((aligned(n)))
 
 // ---- vector types
 struct alignas(8) float2 { float x, y; };
@@ -42,6 +43,11 @@ static inline float3 make_float3(float x, float y, float z) { return float3{x, y
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline int3 make_int3(int x, int y, int z) { return int3{x, y, z}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+
+// packed fp32 intrinsics of sm_100 (crt/sm_100_rt.h): per component the scalar IEEE operation
+static inline float2 __ffma2_rn(float2 x, float2 y, float2 z) { return float2{fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y)}; }
+static inline float2 __fmul2_rn(float2 x, float2 y) { return float2{x.x * y.x, x.y * y.y}; }
+static inline float2 __fadd2_rn(float2 x, float2 y) { return float2{x.x + y.x, x.y + y.y}; }
 
 namespace simt {
 struct Thread {
