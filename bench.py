@@ -4,13 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sand256]
 
 A "step" is one substep (sort -> P2G -> grid update -> G2P+constitutive -> delete) over the whole
-synthetic particle set.  Workload at N=1 = BASELINE config 3 (256^3 grid, 8 M Drucker-Prager sand),
-the config the metric is quoted on.  Prints ONE JSON line (rank 0).
+synthetic particle set.  Workload = BASELINE config 3 (256^3 grid, 8 M Drucker-Prager sand), the config
+the metric is quoted on; --gpus N cuts the SAME scene into N z-slabs (strong scaling, the metric's
+"1/2/4/8 GPU"; `weak_scaling` is reported beside it).  Prints ONE JSON line (rank 0).
 
-  value     whole-job M particle-updates/s, state resident in HBM, CUDA-event timed, max over ranks
-  e2e       same metric through the reference-facing call with HOST buffers: one frame =
-            upload of the particle set from pinned host memory + frame_substeps substeps +
-            download of the result (the drop-in adapter's per-frame contract)
+  value     whole-job M particle-updates/s, state resident in HBM, CUDA-event timed, max over ranks:
+            the SLOWER of two states of the same scene — the column at rest and a developed collapse
+            (`states`: movers per substep, active tiles, hole fraction of each)
+  parity_check (N > 1)  a reduced scene on the N-rank exchange path against one engine, per particle id,
+            BEFORE any timing; a mismatch ends the run with rc 3
+  e2e       same metric through the drop-in's own calls with HOST buffers: one frame = mpmb_upload_aos of
+            the reference's 320-byte-slot pool from pinned host memory + frame_substeps substeps +
+            mpmb_download_aos back into it (the adapter's per-frame contract)
   roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs measured HBM peak
   cpu_baseline  the OpenMP restatement of the reference's optimized CPU path (oracle "port"),
             timed on this box's host cores on a bounded sample
@@ -35,7 +40,6 @@ BYTES_PER_UPDATE = {scenes.MAT_LINEAR: 208, scenes.MAT_JELLY: 208, scenes.MAT_SA
 # split of the per-update figure between the two hot kernels: P2G reads the state
 # (+mass, vol) and writes half of the grid traffic, G2P writes the state and reads the other half.
 P2G_BYTES = {scenes.MAT_LINEAR: 108, scenes.MAT_JELLY: 108, scenes.MAT_SAND: 112, scenes.MAT_SNOW: 112, scenes.MAT_WATER: 76}
-STAGE_NAMES = ["sort+tiles", "p2g", "g2p", "exchange"]
 
 
 def measured_peaks():
@@ -146,50 +150,43 @@ def best_thread_count(sc, probe):
     return best, best_rate
 
 
-def build_workload(name, scale):
-    cfg = scenes.config(name, scale)
+def build_workload(name, scale, state=True):
+    cfg = scenes.config(name, scale, state=state)
     sc = cfg["scene"]
     if sc["planes"] is not None:
         sc["sdf"] = None  # engine builds the dense level set on the device from the planes
     return cfg
 
 
-def build_slab_workload(name, scale, rank, world):
-    """This rank's share of the weak-scaling version of a config: grid res x res x (res*world), block
-    cells x cells x (cells_z*world), cut into `world` z-slabs of equal particle count at tile layers."""
+# slot layout of the reference's particle pool: offsetof() on MPMParticle<3> / SandParticle<3> ... in the in-place build
+# of the reference sources (oracle/transfer_ref.cpp: reft_aos_layout) — stride, pos, v_and_m, dg_e,
+# apic_b, column pitch, vol, plastic scalar per kind
+AOS_SLOT = dict(stride=320, off_pos=32, off_v_and_m=16, off_dg_e=48, off_apic_b=96, col_pitch=16, off_vol=164)
+AOS_SCALAR = {scenes.MAT_LINEAR: -1, scenes.MAT_JELLY: -1, scenes.MAT_SNOW: 196, scenes.MAT_WATER: 204, scenes.MAT_SAND: 216}
+
+
+def slab_cuts(meta, res_z, world, weak):
+    """Tile-layer cuts [(z0, z1)] * world by particle count: 1-D histogram of the base tile layer of the block's cell
+    layers (all columns are statistically identical).  weak: the block is `world` times longer along z."""
     from taichi_mpm_b200 import slab
-    base = scenes.config(name, scale)
-    sc = dict(base["scene"])
-    res = sc["res"][0]
-    x0 = base["state"]["x"]
-    dx = sc["dx"]
-    lo = np.floor(x0.min(0) / dx + 1e-3).astype(np.int64)
-    hi = np.ceil(x0.max(0) / dx - 1e-3).astype(np.int64)
-    cells_z = int(hi[2] - lo[2])
-    zc_lo = (res * world - cells_z * world) // 2
-    sc["res"] = (res, res, res * world)
-    n_layers = slab.tile_layers(res * world)
-    # 1-D histogram of the base tile layer along z (all columns are statistically identical)
-    zs = (np.arange(zc_lo, zc_lo + cells_z * world)[:, None] + 0.5 + np.array([-0.25, 0.25])[None]).reshape(-1) * dx
-    cuts = slab.slab_partition(slab.base_tile_z(zs, dx), n_layers, world)
-    z0, z1 = cuts[rank]
-    # generate only the cells that can belong to this slab (+-2 cells), then keep what it owns
-    c_lo = max(zc_lo, z0 * 4 - 2)
-    c_hi = min(zc_lo + cells_z * world, z1 * 4 + 3)
-    xs, mass, vol = scenes.lattice_block(res, (lo[0], lo[1], c_lo), (hi[0], hi[1], c_hi), jitter=0.05, seed=20260922 + rank)
-    tz = slab.base_tile_z(xs[:, 2], dx)
-    keep = (tz >= z0) & (tz < z1)
-    st = scenes.make_state(xs[keep], mass[keep], vol[keep], base["meta"]["kind"])
-    import torch
-    import torch.distributed as dist
-    t = torch.zeros(world, dtype=torch.int64, device="cuda")
-    t[rank] = int(keep.sum())
-    dist.all_reduce(t)
-    counts = t.cpu().numpy()
-    meta = dict(base["meta"])
-    meta["res"] = res
-    cfg = dict(scene=sc, state=st, meta=meta)
-    return cfg, st, (z0, z1), int(counts.sum()), int(counts[:rank].sum())
+    dx = 1.0 / meta["res"]
+    lo_z, hi_z = meta["lo"][2], meta["hi"][2]
+    zs = (np.arange(lo_z, hi_z)[:, None] + 0.5 + np.array([-0.25, 0.25])[None]).reshape(-1) * dx
+    return slab.slab_partition(slab.base_tile_z(zs, dx), slab.tile_layers(res_z), world)
+
+
+def weak_variant(cfg, world):
+    """The weak-scaling version of a config: grid res x res x (res*world), block cells x cells x (cells_z*world)."""
+    cfg = dict(scene=dict(cfg["scene"]), state=None, meta=dict(cfg["meta"]))
+    res = cfg["meta"]["res"]
+    lo, hi = list(cfg["meta"]["lo"]), list(cfg["meta"]["hi"])
+    cells_z = hi[2] - lo[2]
+    lo[2] = (res * world - cells_z * world) // 2
+    hi[2] = lo[2] + cells_z * world
+    cfg["scene"]["res"] = (res, res, res * world)
+    cfg["meta"]["lo"], cfg["meta"]["hi"] = tuple(lo), tuple(hi)
+    cfg["meta"]["n"] = cfg["meta"]["n"] * world
+    return cfg
 
 
 def cpu_run(cfg, n_particles_cap, budget_s, min_substeps=1, threads=None):
@@ -262,8 +259,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "million particle-updates/s", "value": val, "unit": "M particle-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, cfg, n_sample),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg, n_full, args.gpus, args.scaling == "weak"),
         "cpu_baseline": {"value": val, "unit": "M particle-updates/s", "cores": fast.threads, "kind": "port", "sample": sample_txt,
                          "ns_per_particle": {"sort": tm[0] / upd * 1e9, "p2g": tm[1] / upd * 1e9, "grid": tm[2] / upd * 1e9,
                                              "g2p": tm[3] / upd * 1e9}},
@@ -303,143 +300,250 @@ def reference_build_rate(sc, sample, threads, n=400_000, substeps=3):
         return {"unavailable": str(ex)[:200]}
 
 
-def workload_config(args, cfg, n_particles):
+def workload_config(args, cfg, n_particles, world=1, weak=False):
     m = cfg["meta"]
+    if world == 1:
+        par = "1 GPU"
+    elif weak:
+        par = "z-slab x%d (weak scaling: block and grid extended along z, one config-sized share per GPU)" % world
+    else:
+        par = "z-slab x%d (strong scaling: the SAME %d-particle scene cut into %d slabs of equal particle count)" % (world, n_particles, world)
     return {"workload": "%s: %s grid, %d particles, %s, dt=%g, floor plane friction %g" % (
         m["name"], "x".join(str(r) for r in cfg["scene"]["res"]), n_particles, ["linear", "jelly", "snow", "water", "sand"][m["kind"]], cfg["scene"]["dt"],
         cfg["scene"]["friction"]),
-        "l2": "inputs larger than L2 (particle state %.0f MB per buffer vs 126 MB L2)" % (n_particles * 112 / 1e6),
-        "parallelism": "1 GPU" if args.gpus == 1 else "z-slab x%d (weak scaling: block and grid extended along z, one config-sized share per GPU)" % args.gpus}
+        "l2": "inputs larger than L2 (particle state %.0f MB per buffer per GPU vs 126 MB L2)" % (n_particles * 112 / 1e6 / world),
+        "parallelism": par}
+
+
+class SlabJob:
+    """One rank's engine over (its slab of) a config, seeded on the device (mpmb_seed_lattice): no host particle arrays."""
+
+    def __init__(self, args, cfg, rank, world, local, dist, weak=False, v0=(0.0, 0.0, 0.0)):
+        import torch
+        from taichi_mpm_b200 import capi, slab
+        self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        self.cfg = weak_variant(cfg, world) if (weak and world > 1) else cfg
+        sc, m = self.cfg["scene"], self.cfg["meta"]
+        self.dev = torch.device("cuda", local)
+        self.stream = torch.cuda.current_stream(self.dev)
+        if world == 1:
+            self.eng = capi.Engine(sc["res"], sc["dx"], sc["dt"], sc["gravity"], sc["particle_gravity"], True, device=local)
+        else:
+            z0, z1 = slab_cuts(m, sc["res"][2], world, weak)[rank]
+            self.eng = capi.Engine(sc["res"], sc["dx"], sc["dt"], sc["gravity"], sc["particle_gravity"], True, device=local, rank=rank, world=world,
+                                   tile_z0=z0, tile_z1=z1, migrate_capacity=args.migrate_capacity, halo_capacity=args.halo_capacity)
+        e = self.eng
+        e.set_stream(self.stream.cuda_stream)
+        if world > 1:
+            if args.exchange == "peer":
+                slab.connect_peers(e, rank, world, dist)  # neighbours' receive buffers mapped over NVLink (CUDA IPC)
+            else:
+                self.runner = slab.SlabRunner(slab.EngineAdapter(e), rank, world, self.dev, dist=dist)
+        self.peer = world == 1 or args.exchange == "peer"
+        e.set_material(0, m["kind"], sc["mat_params"][0])
+        if sc["planes"] is not None:
+            e.set_planes(sc["planes"], sc["friction"])
+        self.n_local = e.seed_lattice(m["lo"], m["hi"], m["vol"], m["mass"], jitter=m["jitter"], seed=m["seed"], v0=v0)
+        self.n_total = int(self.allsum([self.n_local])[0])
+        self.barrier()  # peer-memory waits are bounded: start the ranks together
+
+    def allsum(self, vals, op=None):
+        t = self.torch.tensor([float(v) for v in vals], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=op or self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+    def allmax(self, vals):
+        return self.allsum(vals, op=self.dist.ReduceOp.MAX if self.world > 1 else None)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def substep(self, k):
+        if k <= 0:
+            return
+        if self.peer:
+            self.eng.substep(k)
+        else:
+            self.runner.substep(k)
+
+    def timed(self, steps, warmup, sample_clocks=True):
+        """W untimed + K timed substeps, barrier + synchronize on both sides, CUDA events, max over ranks."""
+        torch, e = self.torch, self.eng
+        self.substep(warmup)
+        self.barrier()
+        c0 = e.get_counters()
+        e.set_profiling(True)
+        e.get_profile(reset=True)
+        sampler = ClockSampler(self.dev.index)
+        if sample_clocks:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record(self.stream)
+        self.substep(steps)
+        ev1.record(self.stream)
+        self.barrier()
+        clocks = sampler.stop() if sample_clocks else None
+        ms_local = ev0.elapsed_time(ev1)
+        stage_ms, _ = e.get_profile(reset=True)
+        e.set_profiling(False)
+        c1 = e.get_counters()
+        st = e.get_ordering_stats()
+        ms = self.allmax([ms_local])[0]
+        alive, launches, tiles, movers, rows = self.allsum([c1["alive"], c1["kernel_launches"] - c0["kernel_launches"], c1["active_tiles"], st["movers"], st["rows"]])
+        per = [v / max(steps, 1) for v in stage_ms]
+        return dict(ms=ms, ms_per_step=ms / steps, value=alive * steps / (ms * 1e-3) / 1e6, alive=int(alive), alive_local=c1["alive"], launches=int(launches),
+                    active_tiles=int(tiles), movers_per_substep=int(movers), hole_fraction=movers / max(rows, 1.0),
+                    stage_ms_per_step={"sort+tiles": per[0], "p2g": per[1], "g2p": per[2], "exchange": per[3], "grid": per[4]}, clocks=clocks)
+
+    def gather_particles(self, keys=("id", "x", "v", "F", "ps")):
+        d = self.eng.download(sort_by_id=False)
+        mine = {k: d[k] for k in keys}
+        if self.world == 1:
+            return mine
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, mine)
+        return {k: np.concatenate([p[k] for p in parts]) for k in keys} if self.rank == 0 else None
+
+    def close(self):
+        self.eng.close()
+
+
+def multi_gpu_parity_check(args, rank, world, local, dist):
+    """Before any timing at N > 1: a reduced scene on the N-rank path (halo exchange + migration, the transport the bench
+    times) against ONE engine on rank 0, per particle id.  Uniform initial velocity along +z so that particles cross
+    every slab face.  Tolerances = tests/test_gpu_slab.py (the visiting order of arrivals differs between partitions)."""
+    scale, nsub = 0.5, 60
+    cfg = build_workload(args.workload, scale, state=False)
+    v0 = (0.5, 0.0, 12.0)
+    job = SlabJob(args, cfg, rank, world, local, dist, weak=False, v0=v0)
+    n0 = job.n_local
+    job.substep(nsub)
+    got = job.gather_particles()
+    n1 = job.eng.num_particles()
+    crossed = job.allsum([abs(n1 - n0)])[0]
+    job.close()
+    res = None
+    if rank == 0:
+        one = SlabJob(args, cfg, 0, 1, local, None, v0=v0)
+        one.substep(nsub)
+        ref = one.gather_particles()
+        one.close()
+        o, r = np.argsort(got["id"], kind="stable"), np.argsort(ref["id"], kind="stable")
+        same_ids = len(o) == len(r) and np.array_equal(got["id"][o], ref["id"][r])
+        err = {}
+        if same_ids:
+            vmax = max(float(np.abs(ref["v"]).max()), 1e-30)
+            err = {"x": float(np.abs(got["x"][o] - ref["x"][r]).max()), "v_rel": float(np.abs(got["v"][o] - ref["v"][r]).max() / vmax),
+                   "F": float(np.abs(got["F"][o] - ref["F"][r]).max()), "ps": float(np.abs(got["ps"][o] - ref["ps"][r]).max())}
+        tol = {"x": 2e-6, "v_rel": 5e-4, "F": 5e-5, "ps": 1e-5}
+        ok = bool(same_ids and all(err[k] <= tol[k] for k in tol) and crossed > 0)
+        res = {"ok": ok, "particles": int(len(r)), "substeps": nsub, "ranks": world, "same_ids": bool(same_ids), "max_err": err, "tol": tol,
+               "net_particles_exchanged": int(crossed), "scene": "%s x%g, v0=%s, %s exchange vs one engine on rank 0" % (args.workload, scale, v0, args.exchange)}
+    flag = job.torch.tensor([1.0 if (res is None or res["ok"]) else 0.0], device=job.dev)
+    dist.broadcast(flag, 0)
+    return res, bool(flag.item() > 0)
+
+
+def aos_e2e(job, args, kind):
+    """End to end through the drop-in's own calls (N = 1): the reference's 320-byte-slot pool in pinned host memory,
+    mpmb_upload_aos -> frame_substeps substeps -> mpmb_download_aos per frame."""
+    import torch
+    from taichi_mpm_b200 import capi
+    e = job.eng
+    n = e.num_particles()
+    L = capi.MpmbAosLayout()
+    for k, v in AOS_SLOT.items():
+        setattr(L, k, v)
+    L.off_scalar = AOS_SCALAR[kind]
+    pool_t = torch.zeros(n * L.stride, dtype=torch.uint8, pin_memory=True)
+    idx_t = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    pool, idx = pool_t.numpy(), idx_t.numpy().view(np.uint32)
+    # the host pool starts as the engine's current state: ids -> slots 0..n-1 in id order
+    d_id = np.sort(e.download(sort_by_id=False)["id"])
+    remap = np.full(int(d_id.max()) + 1 if n else 1, 0, np.uint32)
+    remap[d_id] = np.arange(n, dtype=np.uint32)
+    idx_full = remap            # id -> slot
+    nn = e.download_aos(pool, idx_full, L)  # (not resident: reads the zero pool, scatters, returns it)
+    assert nn == n
+    idx[:] = np.arange(n, dtype=np.uint32)
+    times = []
+    alive = n
+    for f in range(args.frames + 1):
+        job.barrier()
+        t0 = time.perf_counter()
+        e.upload_aos(pool, idx[:alive], L)
+        e.substep(args.frame_substeps)
+        alive = e.download_aos(pool, idx[:alive], L)
+        job.barrier()
+        if f > 0:   # frame 0 warms the staging buffers
+            times.append(time.perf_counter() - t0)
+    sec = float(np.median(times))
+    return dict(value=alive * args.frame_substeps / sec / 1e6, frame_seconds=sec, frame_seconds_all=[float(t) for t in times],
+                h2d=n * (L.stride + 4), d2h=n * (L.stride + 4), alive=alive,
+                path="mpmb_upload_aos -> mpmb_substep(%d) -> mpmb_download_aos on a pinned pool of %d-byte slots" % (args.frame_substeps, L.stride))
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from taichi_mpm_b200 import capi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-
-    from taichi_mpm_b200 import slab
-    if world == 1:
-        cfg = build_workload(args.workload, args.scale)
-        st, sc = cfg["state"], cfg["scene"]
-        eng = capi.Engine(sc["res"], sc["dx"], sc["dt"], sc["gravity"], sc["particle_gravity"], True, device=local)
-        n_total = len(st["x"])
-    else:
-        # weak scaling: the block and the domain grow along z with the rank count, every rank owns one
-        # config-sized share of a CONTIGUOUS block, so slab faces cut through the material
-        cfg, st, (z0, z1), n_total, id_base = build_slab_workload(args.workload, args.scale, rank, world)
-        sc = cfg["scene"]
-        eng = capi.Engine(sc["res"], sc["dx"], sc["dt"], sc["gravity"], sc["particle_gravity"], True, device=local, rank=rank, world=world,
-                          tile_z0=z0, tile_z1=z1, migrate_capacity=args.migrate_capacity, halo_capacity=args.halo_capacity)
-        eng.set_id_base(id_base)
+    weak = args.scaling == "weak"
+    cfg = build_workload(args.workload, args.scale, state=False)
     kind = cfg["meta"]["kind"]
-    n = len(st["x"])
-    stream = torch.cuda.current_stream(dev)
-    eng.set_stream(stream.cuda_stream)
-    runner = slab.SlabRunner(slab.EngineAdapter(eng), rank, world, dev, dist=dist if world > 1 else None)
-    if world > 1 and args.exchange == "peer":
-        slab.connect_peers(eng, rank, world, dist)  # neighbours' receive buffers mapped over NVLink (CUDA IPC)
-    eng.set_material(0, kind, sc["mat_params"][0])
-    if sc["planes"] is not None:
-        eng.set_planes(sc["planes"], sc["friction"])
 
-    # pinned host copies of the particle set: the host side of the drop-in boundary
-    host = {}
-    for k, shape, dt_ in (("x", (n, 3), torch.float32), ("v", (n, 3), torch.float32), ("F", (n, 9), torch.float32),
-                          ("b", (n, 9), torch.float32), ("mass", (n,), torch.float32), ("vol", (n,), torch.float32),
-                          ("ps", (n,), torch.float32), ("group", (n,), torch.int32)):
-        t = torch.empty(shape, dtype=dt_, pin_memory=True)
-        t.numpy()[...] = st[k]
-        host[k] = t
-    host["id"] = torch.empty((n,), dtype=torch.int32, pin_memory=True)
-
-    def upload():
-        eng.upload_ptrs(n, host["x"].data_ptr(), host["v"].data_ptr(), host["F"].data_ptr(), host["b"].data_ptr(),
-                        host["mass"].data_ptr(), host["vol"].data_ptr(), host["ps"].data_ptr(), host["group"].data_ptr())
-
-    def download():
-        return eng.download_ptrs(n, host["id"].data_ptr(), host["x"].data_ptr(), host["v"].data_ptr(), host["F"].data_ptr(),
-                                 host["b"].data_ptr(), 0, 0, host["ps"].data_ptr(), 0)
-
-    upload()
-    if world > 1:
-        dist.barrier()  # peer-memory waits are bounded: start the ranks together
-    h2d = n * (3 + 3 + 9 + 9 + 1 + 1 + 1 + 1) * 4
-    d2h = n * (1 + 3 + 3 + 9 + 9 + 1) * 4
-
-    def barrier():
-        if world > 1:
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity, ok = multi_gpu_parity_check(args, rank, world, local, dist)
+        if not ok:
+            if rank == 0:
+                emit({"error": "multi-GPU parity check failed", "parity_check": parity})
             dist.barrier()
-        torch.cuda.synchronize(dev)
+            dist.destroy_process_group()
+            sys.exit(3)
 
-    substep = (lambda k: eng.substep(k)) if (world == 1 or args.exchange == "peer") else (lambda k: runner.substep(k))
-    # ---- device-resident throughput
-    substep(args.warmup)
-    barrier()
-    c0 = eng.get_counters()
-    eng.set_profiling(True)
-    eng.get_profile(reset=True)
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    substep(args.steps)
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    stage_ms, stage_launches = eng.get_profile(reset=True)
-    eng.set_profiling(False)
-    c1 = eng.get_counters()
-    alive = c1["alive"]
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        t = torch.tensor([float(alive), float(c1["kernel_launches"] - c0["kernel_launches"])], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        alive = int(t[0].item())
-        total_launches = int(t[1].item())
-    else:
-        total_launches = c1["kernel_launches"] - c0["kernel_launches"]
-    value = alive * args.steps / (ms * 1e-3) / 1e6
+    job = SlabJob(args, cfg, rank, world, local, dist if world > 1 else None, weak=weak)
+    n_total = job.n_total
+    # ---- device-resident throughput, column at rest (the round-1 regime) ...
+    quiet = job.timed(args.steps, args.warmup)
+    # ---- ... and in a developed collapse: advance the same engine `develop` substeps, then time again
+    flowing = None
+    if args.develop > 0:
+        job.substep(args.develop)
+        flowing = job.timed(args.steps, args.warmup)
+        flowing["developed_substeps"] = args.develop + args.warmup + args.steps
+    head = quiet if (flowing is None or quiet["value"] <= flowing["value"]) else flowing
+    head_name = "quiescent" if head is quiet else "flowing"
 
-    # ---- end to end through host buffers: frames of upload + substeps + download
-    frame_substeps = args.frame_substeps
-    n_alive = alive
+    # ---- end to end through host buffers
+    e2e = None
     if args.frames > 0:
-        upload()
-        substep(3)
-        download()
-    t_e2e = []
-    for _ in range(args.frames):
-        barrier()
-        t0 = time.perf_counter()
-        upload()
-        if world > 1:
-            dist.barrier()
-        substep(frame_substeps)
-        n_alive = download()
-        barrier()
-        t_e2e.append(time.perf_counter() - t0)
-    if world > 1 and t_e2e:
-        t = torch.tensor([float(n_alive)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        n_alive = int(t.item())
-        t = torch.tensor(t_e2e, device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)      # per frame: the slowest rank
-        t_e2e = [float(v) for v in t.cpu()]
-    frame_times = [float(t) for t in t_e2e]
-    e2e_s = float(np.median(t_e2e)) if t_e2e else float("nan")
-    e2e_value = n_alive * frame_substeps / e2e_s / 1e6 if t_e2e else None
+        if world == 1:
+            r = aos_e2e(job, args, kind)
+            e2e = {"value": r["value"], "unit": "M particle-updates/s", "h2d_bytes_per_step": r["h2d"] / args.frame_substeps,
+                   "d2h_bytes_per_step": r["d2h"] / args.frame_substeps, "frame_substeps": args.frame_substeps, "frames": args.frames,
+                   "frame_seconds": r["frame_seconds"], "frame_seconds_all": r["frame_seconds_all"], "path": r["path"],
+                   "state": "flowing" if flowing else "quiescent"}
+        else:
+            e2e = soa_e2e(job, args)
+
+    # ---- secondary: weak scaling of the same config (N > 1, default run only)
+    weak_line = None
+    if world > 1 and not weak and args.also_weak:
+        wjob = SlabJob(args, cfg, rank, world, local, dist, weak=True)
+        w = wjob.timed(args.steps, args.warmup, sample_clocks=False)
+        weak_line = {"value": w["value"], "ms_per_step": w["ms_per_step"], "particles": wjob.n_total, "stage_ms_per_step": w["stage_ms_per_step"],
+                     "config": workload_config(args, wjob.cfg, wjob.n_total, world, True)["workload"]}
+        wjob.close()
 
     if rank != 0:
         if world > 1:
@@ -448,12 +552,11 @@ def run_ours(args):
         return
     peaks, peak_kind = measured_peaks()
     peak = float(peaks["hbm_gbs"])
-    # dominant kernel of the substep
-    kms = {"p2g": stage_ms[1] / max(args.steps, 1), "g2p": stage_ms[2] / max(args.steps, 1)}
+    # dominant kernel of the (headline state's) substep on rank 0
+    kms = {"p2g": head["stage_ms_per_step"]["p2g"], "g2p": head["stage_ms_per_step"]["g2p"]}
     dom = max(kms, key=kms.get)
     kb = P2G_BYTES[kind] if dom == "p2g" else BYTES_PER_UPDATE[kind] - P2G_BYTES[kind]
-    alive_local = c1["alive"]  # the profiled kernels are this rank's: its own particle count
-    achieved = kb * alive_local / (kms[dom] * 1e-3) / 1e9
+    achieved = kb * head["alive_local"] / (kms[dom] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
@@ -461,42 +564,84 @@ def run_ours(args):
             traffic = json.load(open(tp)).get(dom)
         except Exception:
             traffic = None
+    value = head["value"]
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
-                "algorithmic_bytes_per_launch": kb * alive_local, "kernel_ms": kms[dom],
+                "algorithmic_bytes_per_launch": kb * head["alive_local"], "kernel_ms": kms[dom],
                 "substep": {"bytes_per_update": BYTES_PER_UPDATE[kind], "achieved": BYTES_PER_UPDATE[kind] * value * 1e6 / 1e9 / world,
                             "frac": BYTES_PER_UPDATE[kind] * value * 1e6 / 1e9 / world / peak, "note": "per GPU"},
-                "stage_ms_per_step": {STAGE_NAMES[i]: stage_ms[i] / max(args.steps, 1) for i in range(4)}}
+                "stage_ms_per_step": head["stage_ms_per_step"], "state": head_name}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_run(cfg, args.cpu_sample, budget_s=15.0)
+        hcfg = build_workload(args.workload, args.scale, state=True)
+        r = cpu_run(hcfg, args.cpu_sample, budget_s=15.0)
         cpu = {"value": r["value"], "unit": "M particle-updates/s", "cores": r["threads"], "kind": "port",
-               "sample": "%d of %d particles (lowest layers of the column), %d substeps, %.1f s" % (r["particles"], n, r["substeps"], r["seconds"]),
+               "sample": "%d of %d particles (lowest layers of the column), %d substeps, %.1f s" % (r["particles"], n_total, r["substeps"], r["seconds"]),
                "ns_per_particle": r["ns_per_particle"], "single_thread_value": r["single_thread"]}
+
+    def state_line(t):
+        return {k: t[k] for k in ("value", "ms_per_step", "alive", "active_tiles", "movers_per_substep", "hole_fraction", "stage_ms_per_step") if k in t} | (
+            {"developed_substeps": t["developed_substeps"]} if "developed_substeps" in t else {})
 
     line = {
         "metric": "million particle-updates/s", "value": value, "unit": "M particle-updates/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, n_total),
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "M particle-updates/s", "h2d_bytes_per_step": h2d / frame_substeps,
-                "d2h_bytes_per_step": d2h / frame_substeps, "frame_substeps": frame_substeps, "frames": args.frames,
-                "frame_seconds": e2e_s, "frame_seconds_all": frame_times if world == 1 else t_e2e},
-        "gpu_launches": total_launches,
-        "alive_particles": alive, "active_tiles": c1["active_tiles"],
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (device-seeded lattice, mpmb_seed_lattice)",
+        "config": workload_config(args, job.cfg, n_total, world, weak),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": head["clocks"], "e2e": e2e,
+        "gpu_launches": head["launches"], "alive_particles": head["alive"], "active_tiles": head["active_tiles"],
+        "states": {"headline": head_name + " (the slower of the two)", "quiescent": state_line(quiet), "flowing": state_line(flowing) if flowing else None},
     }
+    if parity is not None:
+        line["parity_check"] = parity
+    if weak_line is not None:
+        line["weak_scaling"] = weak_line
     if world > 1:
-        if args.exchange == "peer":
-            line["exchange"] = {"transport": "peer memory over NVLink (CUDA IPC): pack kernels store into the neighbour GPU, "
-                                             "seq flag release/acquire, no host transport, substeps run inside the C-ABI"}
-        else:
-            line["exchange"] = {"bytes_sent_per_step_rank0": runner.bytes_sent / max(1, args.warmup + args.steps + 3 + args.frames * frame_substeps),
-                                "transport": "torch.distributed NCCL point-to-point (batch_isend_irecv), fixed-size messages"}
+        line["exchange"] = {"transport": "peer memory over NVLink (CUDA IPC): pack kernels store into the neighbour GPU, seq flag release/acquire, "
+                                         "substeps run inside the C-ABI" if args.exchange == "peer" else "torch.distributed NCCL point-to-point"}
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def soa_e2e(job, args):
+    """N > 1: per-rank frames of field-wise upload + substeps + download through pinned host buffers (the AoS pool
+    adapter is the single-process drop-in; z-slab ranks hold sparse subsets of the ids)."""
+    import torch
+    e = job.eng
+    d = e.download(sort_by_id=False)
+    n = len(d["id"])
+    host = {}
+    for k, shape, dt_ in (("x", (n, 3), torch.float32), ("v", (n, 3), torch.float32), ("F", (n, 9), torch.float32), ("b", (n, 9), torch.float32),
+                          ("mass", (n,), torch.float32), ("vol", (n,), torch.float32), ("ps", (n,), torch.float32), ("group", (n,), torch.int32)):
+        t = torch.empty(shape, dtype=dt_, pin_memory=True)
+        t.numpy()[...] = d[k]
+        host[k] = t
+    host["id"] = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+    times, alive = [], n
+    # NB ids are renumbered by the field-wise upload (id_base + row); the frames below only time the path
+    for f in range(args.frames + 1):
+        job.barrier()
+        t0 = time.perf_counter()
+        e.upload_ptrs(n, host["x"].data_ptr(), host["v"].data_ptr(), host["F"].data_ptr(), host["b"].data_ptr(), host["mass"].data_ptr(),
+                      host["vol"].data_ptr(), host["ps"].data_ptr(), host["group"].data_ptr())
+        job.barrier()
+        job.substep(args.frame_substeps)
+        alive = e.download_ptrs(n, host["id"].data_ptr(), host["x"].data_ptr(), host["v"].data_ptr(), host["F"].data_ptr(), host["b"].data_ptr(), 0, 0,
+                                host["ps"].data_ptr(), 0)
+        job.barrier()
+        if f > 0:
+            times.append(time.perf_counter() - t0)
+    tmax = [job.allmax([t])[0] for t in times]
+    tot = job.allsum([alive])[0]
+    sec = float(np.median(tmax))
+    h2d = job.allsum([n * 28 * 4])[0]
+    d2h = job.allsum([n * 26 * 4])[0]
+    return {"value": tot * args.frame_substeps / sec / 1e6, "unit": "M particle-updates/s", "h2d_bytes_per_step": h2d / args.frame_substeps,
+            "d2h_bytes_per_step": d2h / args.frame_substeps, "frame_substeps": args.frame_substeps, "frames": args.frames, "frame_seconds": sec,
+            "frame_seconds_all": tmax, "path": "per rank: mpmb_upload_particles -> substeps -> mpmb_download_particles (pinned field arrays)"}
 
 
 _REAL_STDOUT = None
@@ -537,7 +682,12 @@ def main():
     ap.add_argument("--workload", default="sand256")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink grid and block together (debug only)")
     ap.add_argument("--frame-substeps", type=int, default=500, help="substeps per e2e frame (frame_dt/base_delta_t = 0.01/2e-5)")
-    ap.add_argument("--frames", type=int, default=5, help="e2e frames; the median frame time is reported (host-side noise on shared boxes)")
+    ap.add_argument("--frames", type=int, default=3, help="e2e frames; the median frame time is reported (host-side noise on shared boxes)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the SAME scene cut into N z-slabs (what the metric quotes), weak = block and grid extended along z")
+    ap.add_argument("--also-weak", type=int, default=1, help="N > 1 strong runs also report the weak-scaling figure as `weak_scaling`")
+    ap.add_argument("--develop", type=int, default=20000, help="substeps run before the `flowing` measurement (0 = quiescent only)")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the reduced-scene comparison with one engine")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--migrate-capacity", type=int, default=16384, help="particles per face per substep (z-slab message size)")

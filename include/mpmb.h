@@ -198,6 +198,10 @@ int mpmb_get_profile(MpmbHandle h, double ms[MPMB_N_STAGES], int64_t launches[MP
 /* Device counters: active tiles of the last substep, live particles, kernels launched so far.    */
 int mpmb_get_counters(MpmbHandle h, int64_t *active_tiles, int64_t *alive, int64_t *kernel_launches);
 
+/* State of the incremental ordering: rows of the current storage, particles that changed tile in the last substep
+ * (they are holes of their old runs until the next ordering re-bins them), ghost tiles received from the neighbours. */
+int mpmb_get_ordering_stats(MpmbHandle h, int64_t *rows, int64_t *movers, int64_t *ghost_tiles);
+
 /* ------------------------------------------------------------------------------ multi-GPU */
 /* z-slab runs (world>1).  The host moves the bytes; the engine packs and unpacks on the device.
  * Halo: after mpmb_rasterize, face 0 (-z) / 1 (+z) tile-layer partial sums of (p,m) are packed

@@ -386,6 +386,21 @@ int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, 
   return alive;
 }
 
+// offsetof() on the reference's own particle classes (src/particles.h, src/particles.cpp): the slot layout the drop-in
+// adapter hands to mpmb_upload_aos.  out[8] = stride, pos, v_and_m, dg_e, apic_b, col_pitch, vol, scalar(kind) (-1: none)
+void reft_aos_layout(int kind, int32_t *out) {
+  using P3 = MPMParticle<3>;
+  out[0] = (int32_t)sizeof(ParticleContainer<3>);
+  out[1] = (int32_t)offsetof(P3, pos);
+  out[2] = (int32_t)offsetof(P3, v_and_m);
+  out[3] = (int32_t)offsetof(P3, dg_e);
+  out[4] = (int32_t)offsetof(P3, apic_b);
+  out[5] = (int32_t)sizeof(VectorND<3, real>);
+  out[6] = (int32_t)offsetof(P3, vol);
+  out[7] = kind == 2 ? (int32_t)offsetof(SnowParticle<3>, Jp) : kind == 3 ? (int32_t)offsetof(WaterParticle<3>, j)
+           : kind == 4 ? (int32_t)offsetof(SandParticle<3>, logJp) : -1;
+}
+
 // MPM<3>::step(dt) itself (src/mpm.cpp:428-450): `real` = float clocks decide how many substeps a frame runs
 // (request_t += dt; while (current_t + base_delta_t < request_t) substep()).  Returns the substep counter.
 int64_t reft_step(void *hp, float dt, float *current_t, float *request_t) {

@@ -24,7 +24,7 @@ EXPORTS = [
     "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_seed_lattice", "mpmb_num_particles", "mpmb_get_update_count", "mpmb_download_particles", "mpmb_download_aos",
     "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_rasterize_part",
     "mpmb_resample_part", "mpmb_download_grid",
-    "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters",
+    "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters", "mpmb_get_ordering_stats",
     "mpmb_halo_bytes", "mpmb_halo_pack", "mpmb_halo_unpack", "mpmb_migrate_bytes", "mpmb_migrate_pack", "mpmb_migrate_unpack",
     "mpmb_xchg_buffer", "mpmb_xchg_ipc_handle", "mpmb_xchg_connect", "mpmb_halo_send", "mpmb_halo_recv", "mpmb_migrate_send", "mpmb_migrate_recv",
 ]
@@ -329,6 +329,11 @@ class Engine:
         ln = (C.c_int64 * MPMB_N_STAGES)()
         self._check(self.L.mpmb_get_profile(self.h, ms, ln, C.c_int32(int(reset))))
         return list(ms), list(ln)
+
+    def get_ordering_stats(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self.L.mpmb_get_ordering_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(rows=a.value, movers=b.value, ghost_tiles=c.value)
 
     def get_counters(self):
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)

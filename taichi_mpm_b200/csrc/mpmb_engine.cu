@@ -1264,27 +1264,159 @@ __global__ void k_migrate_unpack(View V, Params P, int cap, const int *hdr, cons
     V.mover_idx[mbase + e] = (uint32_t)dst;
   }
 }
-// Peer-memory exchange (no NCCL on the data path): the pack kernels store the payload straight into
-// the neighbour GPU's receive buffer over NVLink; k_xchg_publish then writes {count, seq} with a
-// system-scope release, and the neighbour's k_xchg_wait spins (acquire) on seq before its unpack
-// kernel runs.  One substep = one seq value; a bounded spin (~30 s) turns a lost peer into an error
-// flag instead of a hung GPU.
-__global__ void k_xchg_publish(const int *local_count, int *remote_hdr, int seq) {
-  remote_hdr[0] = local_count[0];
-  __threadfence_system();
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote_hdr + 1), "r"(seq) : "memory");
-}
-__global__ void k_xchg_wait(const int *hdr, int seq, Counters *cnt) {
+// ---- peer-memory exchange (no NCCL on the data path): the sending kernels store the payload straight into the neighbour
+// GPU's receive buffer over NVLink and release {count, seq} system-wide; the receiving kernels acquire seq before they
+// read.  One substep = one seq value; a bounded spin turns a lost peer into an error flag instead of a hung GPU.
+// What mpmb_substep launches on a z-slab rank is fused:  one kernel per direction handles BOTH faces,
+// resets its own counters and publishes from its last CTA; the receiving kernel waits for the neighbours' sequence
+// numbers itself.  4 launches per substep instead of 22 (round 1: memset + pack + publish and wait + unpack (+ commit)
+// per face and per message kind, each a 2-3 us launch on a stream whose real work is ~100 us at 8 ranks).
+struct XFace {     // one face of one message kind, as the kernels see it
+  char *tx;        // the neighbour's receive buffer (peer memory) — header | payload
+  const char *rx;  // my receive buffer for this face
+  int layer;       // halo: LOCAL tile layer packed (send) / registered as ghosts (recv)
+  uint32_t key;    // migration: the special key of this face
+};
+__device__ __forceinline__ void xchg_spin(const int *hdr, int seq, Counters *cnt) {
   const long long t0 = clock64();
   for (;;) {
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(hdr + 1) : "memory");
     if (v >= seq) return;
-    if (clock64() - t0 > 60000000000ll) {  // ~30 s at 2 GHz (ranks may start seconds apart): give up loudly
+    if (clock64() - t0 > 60000000000ll) {  // ~30 s: a lost peer becomes an error flag, not a hung GPU
       atomicOr(&cnt->error, DEVERR_PEER_TIMEOUT);
       return;
     }
     __nanosleep(200);
+  }
+}
+// last CTA of a sending kernel: header {count, seq} of every face, counters back to zero for the next substep
+__device__ __forceinline__ void xchg_publish_last(int *xcount, int *done, XFace f0, XFace f1, int mask, int seq) {
+  __threadfence_system();  // my payload stores are visible system-wide before the CTA is counted as done
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
+      __threadfence_system();
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        if (!((mask >> f) & 1)) continue;
+        int *hdr = (int *)(f == 0 ? f0.tx : f1.tx);
+        hdr[0] = atomicAdd(&xcount[4 * f], 0);
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hdr + 1), "r"(seq) : "memory");
+        xcount[4 * f] = 0;
+      }
+      *done = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_halo_send2(View V, Params P, int cap_xy, int idx_bytes, XFace f0, XFace f1, int mask, int *xcount, int *done, int seq) {
+  __shared__ int s_idx[2];
+  const int n_tiles = V.cnt->n_tiles;
+  for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
+    const int tile = V.meta[slot].tile, lz = tile % P.nt[2];
+    const bool to0 = (mask & 1) && lz == f0.layer, to1 = (mask & 2) && lz == f1.layer;  // a one-layer slab sends the tile both ways
+    if (!to0 && !to1) continue;                                                          // uniform per CTA
+    if (threadIdx.x < 2) {
+      int idx = -1;
+      if (threadIdx.x == 0 ? to0 : to1) {
+        idx = atomicAdd(&xcount[4 * threadIdx.x], 1);
+        if (idx >= cap_xy) { atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY); idx = -1; }
+        else ((int *)((threadIdx.x == 0 ? f0.tx : f1.tx) + 16))[idx] = tile / P.nt[2];
+      }
+      s_idx[threadIdx.x] = idx;
+    }
+    __syncthreads();
+    const float4 *src = V.arena + (size_t)slot * ARENA;
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      const int idx = s_idx[f];
+      if (idx < 0) continue;
+      float4 *dst = (float4 *)((f == 0 ? f0.tx : f1.tx) + 16 + idx_bytes) + (size_t)idx * ARENA;
+      for (int n = threadIdx.x; n < ARENA; n += blockDim.x) dst[n] = src[n];
+    }
+    __syncthreads();
+  }
+  xchg_publish_last(xcount, done, f0, f1, mask, seq);
+}
+
+__global__ void __launch_bounds__(128) k_halo_recv2(View V, Params P, int cap_xy, int idx_bytes, XFace f0, XFace f1, int mask, int seq) {
+  __shared__ int s_slot;
+  if (threadIdx.x == 0) {
+    if (mask & 1) xchg_spin((const int *)f0.rx, seq, V.cnt);
+    if (mask & 2) xchg_spin((const int *)f1.rx, seq, V.cnt);
+  }
+  __syncthreads();
+  const int c0 = (mask & 1) ? min(((const int *)f0.rx)[0], cap_xy) : 0, c1 = (mask & 2) ? min(((const int *)f1.rx)[0], cap_xy) : 0;
+  for (int e = blockIdx.x; e < c0 + c1; e += gridDim.x) {
+    const bool lo = e < c0;
+    const char *b = lo ? f0.rx : f1.rx;
+    const int k = lo ? e : e - c0, layer = lo ? f0.layer : f1.layer;
+    if (threadIdx.x == 0) {
+      int slot = V.cnt->n_tiles + atomicAdd(&V.cnt->n_ghost, 1);
+      if (slot >= V.cap_tiles) { atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY); slot = -1; }
+      else V.slot_map[((const int *)(b + 16))[k] * P.nt[2] + layer] = slot;  // rewritten densely by the next ordering
+      s_slot = slot;
+    }
+    __syncthreads();
+    const int slot = s_slot;
+    const float4 *src = (const float4 *)(b + 16 + idx_bytes) + (size_t)k * ARENA;
+    if (slot >= 0)
+      for (int n = threadIdx.x; n < ARENA; n += blockDim.x) V.arena[(size_t)slot * ARENA + n] = src[n];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_migrate_send2(View V, uint32_t key_dead, int cap, XFace f0, XFace f1, int mask, int *xcount, int *done, int seq) {
+  const int n = V.cnt->n_movers;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+    const uint32_t d = V.mover_dst[m];
+    const int f = ((mask & 1) && d == f0.key) ? 0 : (((mask & 2) && d == f1.key) ? 1 : -1);
+    if (f < 0) continue;
+    const uint32_t i = V.mover_idx[m];
+    const int idx = atomicAdd(&xcount[4 * f], 1);
+    V.keys[i] = key_dead;
+    V.mover_dst[m] = key_dead;
+    if (idx >= cap) { atomicOr(&V.cnt->error, DEVERR_MIGRATE_CAPACITY); continue; }
+    float4 *rec = (float4 *)((f == 0 ? f0.tx : f1.tx) + 16);
+#pragma unroll
+    for (int k = 0; k < N_Q; k++) rec[(size_t)idx * N_Q + k] = V.q[k][i];
+  }
+  xchg_publish_last(xcount, done, f0, f1, mask, seq);
+}
+
+// one CTA: waits for both neighbours, appends the immigrants of both faces after the last storage row, enters them in the
+// mover list and commits the counts
+__global__ void __launch_bounds__(1024) k_migrate_recv2(View V, Params P, int cap, XFace f0, XFace f1, int mask, int seq) {
+  __shared__ int s_n[2];
+  if (threadIdx.x == 0) {
+    if (mask & 1) xchg_spin((const int *)f0.rx, seq, V.cnt);
+    if (mask & 2) xchg_spin((const int *)f1.rx, seq, V.cnt);
+    int c0 = (mask & 1) ? min(((const int *)f0.rx)[0], cap) : 0, c1 = (mask & 2) ? min(((const int *)f1.rx)[0], cap) : 0;
+    if (c0 > cap || c1 > cap) atomicOr(&V.cnt->error, DEVERR_MIGRATE_CAPACITY);
+    const int room = max(V.cap_particles - V.cnt->n_store, 0);
+    if (c0 + c1 > room) { atomicOr(&V.cnt->error, DEVERR_PARTICLE_CAPACITY); c0 = min(c0, room); c1 = min(c1, room - c0); }
+    s_n[0] = c0; s_n[1] = c1;
+  }
+  __syncthreads();
+  const int c0 = s_n[0], c1 = s_n[1];
+  const int base = V.cnt->n_store, mbase = V.cnt->n_movers;
+  for (int e = threadIdx.x; e < c0 + c1; e += blockDim.x) {
+    const float4 *rec = (const float4 *)((e < c0 ? f0.rx : f1.rx) + 16) + (size_t)(e < c0 ? e : e - c0) * N_Q;
+    const int dst = base + e;
+    const float4 r0 = rec[0];
+#pragma unroll
+    for (int k = 0; k < N_Q; k++) V.q[k][dst] = rec[k];
+    const uint32_t key = make_key(P, r0.x, r0.y, r0.z);
+    V.keys[dst] = key;
+    V.mover_dst[mbase + e] = key;
+    V.mover_idx[mbase + e] = (uint32_t)dst;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    V.cnt->n_store = base + c0 + c1;
+    V.cnt->n_movers = mbase + c0 + c1;
   }
 }
 
@@ -1604,8 +1736,8 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
         if (cudaMalloc(&h->rx[k][f], bytes[k]) != cudaSuccess) return bail("cudaMalloc exchange buffer");
         cudaMemset(h->rx[k][f], 0, 16);
       }
-    if (cudaMalloc(&h->xcount, sizeof(int) * 16) != cudaSuccess) return bail("cudaMalloc exchange counters");
-    cudaMemset(h->xcount, 0, sizeof(int) * 16);
+    if (cudaMalloc(&h->xcount, sizeof(int) * 32) != cudaSuccess) return bail("cudaMalloc exchange counters");
+    cudaMemset(h->xcount, 0, sizeof(int) * 32);  // [0],[4] halo counts, [8],[12] migration counts, [16],[20] finished-CTA counters
   }
   if (cfg->capacity > 0) {
     int rc = alloc_particles(h, cfg->capacity);
@@ -2120,6 +2252,8 @@ int mpmb_resample(MpmbHandle h) {
 }
 
 static bool peers_connected(MpmbEngine *h);
+static int xchg_halo_fused(MpmbEngine *h);
+static int xchg_migrate_fused(MpmbEngine *h);
 int mpmb_halo_send(MpmbHandle h, int32_t face);
 int mpmb_halo_recv(MpmbHandle h, int32_t face);
 int mpmb_migrate_send(MpmbHandle h, int32_t face);
@@ -2173,22 +2307,12 @@ int mpmb_substep(MpmbHandle h, int32_t nsub) {
     int rc;
     if ((rc = mpmb_sort_particles_and_populate_grid(h)) != MPMB_OK) return rc;
     if ((rc = mpmb_rasterize(h)) != MPMB_OK) return rc;
-    if (peers) {  // boundary-layer arenas straight into the neighbours' memory, then wait for theirs
-      for (int f = 0; f < 2; f++)
-        if (h->tx[0][f] && (rc = mpmb_halo_send(h, f)) != MPMB_OK) return rc;
-      for (int f = 0; f < 2; f++)
-        if (h->tx[0][f] && (rc = mpmb_halo_recv(h, f)) != MPMB_OK) return rc;
-    }
+    if (peers && (rc = xchg_halo_fused(h)) != MPMB_OK) return rc;  // boundary-layer arenas into the neighbours' memory, theirs in as ghosts
     h->skip_b = (s + 1 < nsub) && h->cfg.world <= 1;  // apic_b only has to exist when control returns to the host
     rc = mpmb_resample(h);
     h->skip_b = false;
     if (rc != MPMB_OK) return rc;
-    if (peers) {
-      for (int f = 0; f < 2; f++)
-        if (h->tx[1][f] && (rc = mpmb_migrate_send(h, f)) != MPMB_OK) return rc;
-      for (int f = 0; f < 2; f++)
-        if (h->tx[1][f] && (rc = mpmb_migrate_recv(h, f)) != MPMB_OK) return rc;
-    }
+    if (peers && (rc = xchg_migrate_fused(h)) != MPMB_OK) return rc;
   }
   return MPMB_OK;
 }
@@ -2263,6 +2387,19 @@ int mpmb_get_counters(MpmbHandle h, int64_t *active_tiles, int64_t *alive, int64
   if (active_tiles) *active_tiles = c.n_tiles;
   if (alive) *alive = c.n_alive;
   if (kernel_launches) *kernel_launches = h->launches;
+  return MPMB_OK;
+}
+
+// rows of the current storage, movers waiting for the next ordering (= holes of their old runs), ghost tiles
+int mpmb_get_ordering_stats(MpmbHandle h, int64_t *rows, int64_t *movers, int64_t *ghost_tiles) {
+  CHECK_HANDLE(h);
+  int rc = mpmb_synchronize(h);
+  if (rc != MPMB_OK) return rc;
+  Counters c;
+  CUDA_TRY(h, cudaMemcpy(&c, h->cnt, sizeof(c), cudaMemcpyDeviceToHost));
+  if (rows) *rows = c.n_store;
+  if (movers) *movers = c.n_movers;
+  if (ghost_tiles) *ghost_tiles = c.n_ghost;
   return MPMB_OK;
 }
 
@@ -2389,6 +2526,9 @@ int mpmb_xchg_connect(MpmbHandle h, int32_t kind, int32_t face, const void *hand
     h->tx[kind][face] = (char *)p;
     h->tx_ipc[kind][face] = true;
   }
+  // a (re)connection restarts the sequence: my own receive headers of this kind must not hold an old, larger seq
+  for (int f = 0; f < 2; f++)
+    if (h->rx[kind][f]) CUDA_TRY(h, cudaMemset(h->rx[kind][f], 0, 16));
   h->xstep = 0;
   return MPMB_OK;
 }
@@ -2403,73 +2543,102 @@ static bool peers_connected(MpmbEngine *h) {
   return lo || hi;
 }
 
+// both faces of one message kind as the fused kernels take them
+static void xfaces(MpmbEngine *h, int kind, XFace f[2], int *mask) {
+  *mask = 0;
+  for (int k = 0; k < 2; k++) {
+    f[k].tx = h->tx[kind][k];
+    f[k].rx = h->rx[kind][k];
+    f[k].layer = 0;
+    f[k].key = h->special_min + (k == 0 ? SPECIAL_MIG_DOWN : SPECIAL_MIG_UP);
+    if (h->tx[kind][k]) *mask |= 1 << k;
+  }
+}
+
+static int xchg_halo_launch(MpmbEngine *h, int mask_send, int mask_recv) {
+  XFace s[2], r[2];
+  int mask;
+  xfaces(h, 0, s, &mask);
+  xfaces(h, 0, r, &mask);
+  s[0].layer = h->P.tile_z0 - h->P.tz_off;      s[1].layer = h->P.tile_z1 - 1 - h->P.tz_off;  // my boundary layers
+  r[0].layer = h->P.tile_z0 - 1 - h->P.tz_off;  r[1].layer = h->P.tile_z1 - h->P.tz_off;      // the neighbours'
+  prof_begin(h, 3);
+  View V = make_view(h);
+  int nl = 0;
+  if (mask_send & mask) {
+    k_halo_send2<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, (int)halo_cap_xy(h), (int)halo_idx_bytes(h), s[0], s[1], mask_send & mask, h->xcount,
+                                                         h->xcount + 16, h->xstep + 1);
+    nl++;
+  }
+  if (mask_recv & mask) {
+    k_halo_recv2<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, (int)halo_cap_xy(h), (int)halo_idx_bytes(h), r[0], r[1], mask_recv & mask, h->xstep + 1);
+    nl++;
+  }
+  h->launches += nl;
+  prof_end(h, nl);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
+
+static int xchg_migrate_launch(MpmbEngine *h, int mask_send, int mask_recv) {
+  XFace f[2];
+  int mask;
+  xfaces(h, 1, f, &mask);
+  prof_begin(h, 3);
+  View V = make_view(h);
+  int nl = 0;
+  if (mask_send & mask) {
+    k_migrate_send2<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->key_dead, (int)h->mig_cap, f[0], f[1], mask_send & mask, h->xcount + 8, h->xcount + 20,
+                                                           h->xstep);
+    nl++;
+  }
+  if (mask_recv & mask) {
+    k_migrate_recv2<<<1, 1024, 0, h->stream>>>(V, h->P, (int)h->mig_cap, f[0], f[1], mask_recv & mask, h->xstep);
+    nl++;
+  }
+  h->launches += nl;
+  prof_end(h, nl);
+  CUDA_TRY(h, cudaGetLastError());
+  return MPMB_OK;
+}
+
+// what mpmb_substep runs on a z-slab rank: both faces per launch
+static int xchg_halo_fused(MpmbEngine *h) {
+  if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "halo exchange must follow rasterize");
+  return xchg_halo_launch(h, 3, 3);
+}
+static int xchg_migrate_fused(MpmbEngine *h) {
+  if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "migration must follow resample");
+  return xchg_migrate_launch(h, 3, 3);
+}
+
+// the same steps one face at a time, for hosts that drive the stages themselves (same kernels, one-face masks)
 int mpmb_halo_send(MpmbHandle h, int32_t face) {
   CHECK_HANDLE(h);
   if (h->cfg.world <= 1 || face < 0 || face > 1 || !h->tx[0][face]) return fail(h, MPMB_ERR_STATE, "no connected peer through face %d", face);
   if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "halo_send must follow rasterize");
-  prof_begin(h, 3);
-  char *b = h->tx[0][face];
-  int *cnt = h->xcount + 4 * face;
-  CUDA_TRY(h, cudaMemsetAsync(cnt, 0, 16, h->stream));
-  View V = make_view(h);
-  const int layer = (face == 0 ? h->P.tile_z0 : h->P.tile_z1 - 1) - h->P.tz_off;
-  k_halo_pack<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, layer, (int)halo_cap_xy(h), cnt, (int *)(b + 16), (float4 *)(b + 16 + halo_idx_bytes(h)));
-  k_xchg_publish<<<1, 1, 0, h->stream>>>(cnt, (int *)b, h->xstep + 1);
-  h->launches += 2;
-  prof_end(h, 2);
-  CUDA_TRY(h, cudaGetLastError());
-  return MPMB_OK;
+  return xchg_halo_launch(h, 1 << face, 0);
 }
 
 int mpmb_halo_recv(MpmbHandle h, int32_t face) {
   CHECK_HANDLE(h);
   if (h->cfg.world <= 1 || face < 0 || face > 1 || !h->tx[0][face]) return fail(h, MPMB_ERR_STATE, "no connected peer through face %d", face);
   if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "halo_recv must follow rasterize");
-  prof_begin(h, 3);
-  const char *b = h->rx[0][face];
-  View V = make_view(h);
-  const int layer = (face == 0 ? h->P.tile_z0 - 1 : h->P.tile_z1) - h->P.tz_off;
-  k_xchg_wait<<<1, 1, 0, h->stream>>>((const int *)b, h->xstep + 1, h->cnt);
-  k_halo_unpack<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, layer, (int)halo_cap_xy(h), (const int *)b, (const int *)(b + 16),
-                                                       (const float4 *)(b + 16 + halo_idx_bytes(h)));
-  h->launches += 2;
-  prof_end(h, 2);
-  CUDA_TRY(h, cudaGetLastError());
-  return MPMB_OK;
+  return xchg_halo_launch(h, 0, 1 << face);
 }
 
 int mpmb_migrate_send(MpmbHandle h, int32_t face) {
   CHECK_HANDLE(h);
   if (h->cfg.world <= 1 || face < 0 || face > 1 || !h->tx[1][face]) return fail(h, MPMB_ERR_STATE, "no connected peer through face %d", face);
   if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "migrate_send must follow resample");
-  prof_begin(h, 3);
-  char *b = h->tx[1][face];
-  int *cnt = h->xcount + 8 + 4 * face;
-  CUDA_TRY(h, cudaMemsetAsync(cnt, 0, 16, h->stream));
-  View V = make_view(h);
-  const uint32_t key_face = h->special_min + (face == 0 ? SPECIAL_MIG_DOWN : SPECIAL_MIG_UP);
-  k_migrate_pack<<<h->num_sms * 2, 256, 0, h->stream>>>(V, key_face, h->key_dead, (int)h->mig_cap, cnt, (float4 *)(b + 16));
-  k_xchg_publish<<<1, 1, 0, h->stream>>>(cnt, (int *)b, h->xstep);
-  h->launches += 2;
-  prof_end(h, 2);
-  CUDA_TRY(h, cudaGetLastError());
-  return MPMB_OK;
+  return xchg_migrate_launch(h, 1 << face, 0);
 }
 
 int mpmb_migrate_recv(MpmbHandle h, int32_t face) {
   CHECK_HANDLE(h);
   if (h->cfg.world <= 1 || face < 0 || face > 1 || !h->tx[1][face]) return fail(h, MPMB_ERR_STATE, "no connected peer through face %d", face);
   if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "migrate_recv must follow resample");
-  prof_begin(h, 3);
-  const char *b = h->rx[1][face];
-  View V = make_view(h);
-  k_xchg_wait<<<1, 1, 0, h->stream>>>((const int *)b, h->xstep, h->cnt);
-  k_migrate_unpack<<<64, 256, 0, h->stream>>>(V, h->P, (int)h->mig_cap, (const int *)b, (const float4 *)(b + 16));
-  k_migrate_commit<<<1, 1, 0, h->stream>>>(h->cnt, (const int *)b, (int)h->mig_cap, (int)h->cap);
-  h->launches += 3;
-  prof_end(h, 3);
-  CUDA_TRY(h, cudaGetLastError());
-  return MPMB_OK;
+  return xchg_migrate_launch(h, 0, 1 << face);
 }
 
 }  // extern "C"

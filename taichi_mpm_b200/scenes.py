@@ -149,10 +149,11 @@ def planes_sdf(res, planes, dtype=np.float32):
     return out.astype(dtype)
 
 
-def config(name, scale=1.0):
+def config(name, scale=1.0, state=True):
     """The BASELINE.json configs as dict(scene=..., state=..., meta=...).
 
     `scale` < 1 shrinks grid and block together (parity-test sizes); 1.0 is the quoted size.
+    state=False: no host particle arrays (meta carries the block for device-side seeding, mpmb_seed_lattice).
     scene: res, dx, dt, gravity, particle_gravity, mat_kind, mat_params, planes, friction
     """
     if name == "jelly128":      # config 2: 3D fixed-corotated block, 128^3 grid, 1M particles
@@ -193,9 +194,16 @@ def config(name, scale=1.0):
             lo[2] = (res - 2 * cells) // 2
             hi[2] = lo[2] + 2 * cells
         gravity = (0.0, -10.0, 0.0)
-    x, mass, vol = lattice_block(res, lo, hi, jitter=0.05, seed=20260922)
-    state = make_state(x, mass, vol, kind)
+    n_block = int(np.prod(hi - lo)) * 8
+    st = None
+    if state:
+        x, mass, vol = lattice_block(res, lo, hi, jitter=0.05, seed=20260922)
+        st = make_state(x, mass, vol, kind)
+        n_block = len(x)
     planes = None if floor_cells is None else np.array([[0.0, 1.0, 0.0, -floor_cells]], np.float32)
     scene = dict(res=(res, res, res), dx=dx, dt=dt, gravity=gravity, particle_gravity=1, mat_kind=np.array([kind], np.int32),
                  mat_params=material_params(kind, **kw)[None], planes=planes, friction=friction if planes is not None else 0.0)
-    return dict(scene=scene, state=state, meta=dict(name=name, res=res, n=len(x), kind=kind))
+    vol1 = np.float32((1.0 / res) ** 3 / 8.0)
+    meta = dict(name=name, res=res, n=n_block, kind=kind, lo=tuple(int(v) for v in lo), hi=tuple(int(v) for v in hi), density=400.0,
+                vol=float(vol1), mass=float(np.float32(vol1 * np.float32(400.0))), jitter=0.05, seed=20260922)
+    return dict(scene=scene, state=st, meta=meta)
