@@ -686,14 +686,17 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the SAME scene cut into N z-slabs (what the metric quotes), weak = block and grid extended along z")
     ap.add_argument("--also-weak", type=int, default=1, help="N > 1 strong runs also report the weak-scaling figure as `weak_scaling`")
-    ap.add_argument("--develop", type=int, default=20000, help="substeps run before the `flowing` measurement (0 = quiescent only)")
+    ap.add_argument("--develop", type=int, default=-1, help="substeps run before the `flowing` measurement (0 = quiescent only; "
+                    "default 20000 for sand256 = 0.4 s of collapse, 2000 for the other workloads)")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the reduced-scene comparison with one engine")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--migrate-capacity", type=int, default=16384, help="particles per face per substep (z-slab message size)")
+    ap.add_argument("--migrate-capacity", type=int, default=65536, help="particles per face per substep (z-slab message size)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="z-slab transport: NVLink peer memory (default) or NCCL send/recv")
-    ap.add_argument("--halo-capacity", type=int, default=2048, help="active tiles per boundary layer (z-slab message size)")
+    ap.add_argument("--halo-capacity", type=int, default=0, help="active tiles per boundary layer (z-slab message size); 0 = the whole cross-section")
     args = ap.parse_args()
+    if args.develop < 0:
+        args.develop = 20000 if args.workload == "sand256" else 2000
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -76,7 +76,18 @@ struct Counters {  // device-resident
   int n_alive;        // particles binned by the last ordering
   int n_live;         // scratch of k_count_live (mpmb_num_particles)
   unsigned long long updates;  // sum over substeps of the particles binned: the reference's update_counter (src/mpm.cpp:436)
+  int g2p_done;       // CTAs of the running k_g2p that have finished (the last one commits the substep)
+  int pad;
+  int chk[8];         // MPMB_CHECKED builds: first violated index check {site, a, b, c, ...}
 };
+// Bounds-checked debug build (-DMPMB_CHECKED): an index that would leave its array is recorded (first one wins) and the
+// access skipped, so a corrupted ordering shows up as a report (mpmb_debug_check) instead of an illegal-address fault.
+#ifdef MPMB_CHECKED
+#define MPMB_CHK(cnt, cond, site, a, b, c)                                                                        \
+  ((cond) ? true : (atomicCAS(&(cnt)->chk[0], 0, (site)) == 0 ? ((cnt)->chk[1] = (int)(a), (cnt)->chk[2] = (int)(b), (cnt)->chk[3] = (int)(c), false) : false))
+#else
+#define MPMB_CHK(cnt, cond, site, a, b, c) true
+#endif
 enum { DEVERR_TILE_CAPACITY = 1, DEVERR_MIGRATE_CAPACITY = 2, DEVERR_PARTICLE_CAPACITY = 4, DEVERR_PEER_TIMEOUT = 8, DEVERR_BAD_INPUT = 16 };
 
 struct TileMeta {  // one 32-byte record per active tile (slot)
@@ -483,21 +494,15 @@ __global__ void k_compact_survivors(const uint32_t *indices, const int *alive_fl
 
 // ------------------------------------------------------------------------------ ordering
 // Replaces sort_particles_and_populate_grid (src/mpm.cpp:770-918) incrementally.
-//   k_mover_count : arr_cnt[dst]++ for every mover
+//   (arr_cnt[dst]++ for every mover is done where the mover is appended: k_g2p, the migration unpack kernels)
 //   k_order_a/b/c : exclusive scans over the dense tile arrays of (stay+arrivals, arrivals, active)
 //                   -> next-run offsets, arrival-segment offsets, compact active-tile list + slot_map
 //   k_mover_place : movers into their tile's arrival segment (order arbitrary)
 //   k_mover_rank  : segment sorted by storage row => deterministic visiting order
 constexpr int ORD_B = 256, ORD_IPT = 4, ORD_TILE = ORD_B * ORD_IPT;
 
-__global__ void k_mover_count(View V, int ntot) {
-  const int n = V.cnt->n_movers;
-  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
-    const uint32_t d = V.mover_dst[m];
-    if (d < (uint32_t)ntot) atomicAdd(&V.arr_cnt[d], 1);
-  }
-}
-
+// arrival counted where the mover is appended (k_g2p, the migration unpack kernels): no counting pass in the ordering
+#define MPMB_COUNT_ARRIVAL(V, P, key) if ((key) < (uint32_t)(P).ntiles_total) atomicAdd(&(V).arr_cnt[key], 1)
 // arrivals per tile straight from radix-sorted keys (upload path: every particle is an arrival)
 __global__ void k_count_sorted(View V, const uint32_t *keys_sorted, int n, int ntot) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -613,6 +618,7 @@ __global__ void k_mover_place(View V, int ntot) {
     const uint32_t d = V.mover_dst[m];
     if (d < (uint32_t)ntot) {
       const int pos = atomicAdd(&V.arr_cur[d], 1);
+      if (!MPMB_CHK(V.cnt, pos < V.arr_len[d] && V.arr_off[d] + pos < V.cap_particles && V.mover_idx[m] < (uint32_t)V.cap_particles, 1, d, pos, V.arr_len[d])) continue;
       V.arrivals[V.arr_off[d] + pos] = V.mover_idx[m];
     }
   }
@@ -627,17 +633,33 @@ __global__ void k_mover_rank(View V, int ntot) {
       const int off = V.arr_off[d], len = V.arr_len[d];
       int rank = 0;
       for (int e = 0; e < len; e++) rank += V.arrivals[off + e] < idx;
+      if (!MPMB_CHK(V.cnt, off + rank < V.cap_particles && rank < len, 2, d, rank, len)) continue;
       V.arrivals_sorted[off + rank] = idx;
     }
   }
 }
 
-// end of a substep: the lists and runs G2P produced become the current ones
-__global__ void k_step_commit(Counters *c) {
-  c->n_movers = c->n_movers_next;
-  c->n_movers_next = 0;
-  c->n_store = c->n_alive;  // G2P wrote one row per binned particle
+#ifdef MPMB_VALIDATE
+// debug: after the ordering every tile must have received exactly the arrivals that were counted for it, its arrival
+// rows must be live storage rows, and the runs must tile the next storage without overlap
+__global__ void k_validate_order(View V, int ntot) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += gridDim.x * blockDim.x) {
+    if (V.arr_cur[t] != V.arr_len[t]) {
+      if (atomicCAS(&V.cnt->chk[0], 0, 20) == 0) { V.cnt->chk[1] = t; V.cnt->chk[2] = V.arr_cur[t]; V.cnt->chk[3] = V.arr_len[t]; }
+    }
+    if (V.run_begin[t] + V.run_len[t] > V.cnt->n_store || V.run_len[t] < V.stay_cnt[t]) {
+      if (atomicCAS(&V.cnt->chk[0], 0, 21) == 0) { V.cnt->chk[1] = t; V.cnt->chk[2] = V.run_len[t]; V.cnt->chk[3] = V.stay_cnt[t]; }
+    }
+    for (int e = 0; e < V.arr_len[t]; e++) {
+      const uint32_t row = V.arrivals_sorted[V.arr_off[t] + e];
+      if (row >= (uint32_t)V.cnt->n_store || V.keys[row] != (uint32_t)t || (e > 0 && V.arrivals_sorted[V.arr_off[t] + e - 1] >= row)) {
+        if (atomicCAS(&V.cnt->chk[0], 0, 22) == 0) { V.cnt->chk[1] = t; V.cnt->chk[2] = (int)row; V.cnt->chk[3] = row < (uint32_t)V.cnt->n_store ? (int)V.keys[row] : -7; }
+      }
+    }
+  }
 }
+extern "C" int mpmb_debug_check(MpmbHandle h, int *out8);
+#endif
 
 // ------------------------------------------------------------------------------ P2G
 // Replaces MPM<3>::rasterize_optimized / block_op_normal (src/transfer.cpp:467-569).
@@ -653,14 +675,27 @@ __global__ void k_step_commit(Counters *c) {
 //      (node strides 68/8/1 put the 32 cells of a warp on 32 banks), warp after warp;
 // then one coalesced store of the arena.  No atomics on floats anywhere.
 constexpr int P2G_T = 64;          // threads = cells per tile
-constexpr int P2G_CH = 512;        // particles staged per chunk
+// particles staged per chunk: a full interior tile is 512 rows at 8 particles per cell, and in a developed flow a quarter
+// of the tiles sit a little above that (profiles/r02_flow_stats.jsonl: p90 526, max ~630 rows) — 576 keeps most of them
+// in ONE chunk at 4 CTAs per SM; the per-row passes below skip the empty tail of a short chunk
+#ifndef MPMB_P2G_CH
+#define MPMB_P2G_CH 576
+#endif
+constexpr int P2G_CH = MPMB_P2G_CH;
 constexpr int P2G_K = P2G_CH / P2G_T;
 constexpr int P2G_ROWS = P2G_CH + P2G_CH / 8;  // padded row index r + (r>>3): cell-run reads hit distinct banks
+constexpr int P2G_DYN_BYTES = 4 * P2G_ROWS * (int)sizeof(float4);
 constexpr int AR_SX = 68, AR_SY = 8;           // arena strides in shared memory
 constexpr int AR_SIZE = 6 * AR_SX;
 
 __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
-  __shared__ float4 s_rows[4][P2G_ROWS];
+  // the row staging area is dynamic shared memory (static + dynamic = 51.7 KB, above the 48 KB static limit)
+#ifndef MPMB_SIMT_HOST
+  extern __shared__ __align__(16) unsigned char p2g_dyn[];
+#else
+  __shared__ __align__(16) unsigned char p2g_dyn[P2G_DYN_BYTES];
+#endif
+  float4 (*s_rows)[P2G_ROWS] = reinterpret_cast<float4 (*)[P2G_ROWS]>(p2g_dyn);
   __shared__ unsigned short s_order[P2G_CH];
   __shared__ unsigned short s_hist[P2G_K * 2][64];
   __shared__ int s_start[65];
@@ -673,6 +708,8 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
     const int tile = tm.tile;
     if (!tile_in_part(P, tile, part)) continue;  // uniform per CTA
     const int nrow_tile = tm.run_len + tm.arr_len;
+    if (!MPMB_CHK(V.cnt, tm.run_begin >= 0 && tm.run_len >= 0 && tm.arr_len >= 0 && tm.run_begin + tm.run_len <= V.cap_particles && tm.arr_off + tm.arr_len <= V.cap_particles &&
+                             tm.out_begin + nrow_tile <= V.cap_particles, 3, slot, tm.run_begin, tm.run_len)) continue;
     MPMB_TILE_XYZ(P, tm, tx, ty, tz);
     const float fbx = (float)(tx * 4 + cx), fby = (float)(ty * 4 + cy), fbz = (float)(tz * 4 + cz);
     F4 acc[27];  // (p_x, p_y | p_z, m) of the 27 nodes of my cell's stencil
@@ -699,6 +736,7 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
         for (int k = 0; k < P2G_K; k++) {
           const int r = k * P2G_T + tid;
           pidx[k] = r < nrows ? row_of(cb + r) : 0u;
+          if (!MPMB_CHK(V.cnt, pidx[k] < (uint32_t)V.cap_particles, 4, slot, pidx[k], cb + r)) pidx[k] = 0u;
         }
       }
 #pragma unroll
@@ -721,6 +759,10 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
       for (int k = 0; k < P2G_K; k++) {
         const int r = k * P2G_T + tid;
         int cell = 64 + warp;  // holes and rows past the end: a private bucket
+        if (k * P2G_T >= nrows) {  // uniform: nothing staged for this pass
+          cr[k] = (uint32_t)cell << 16;
+          continue;
+        }
         float4 a0 = make_float4(0.f, 0.f, 0.f, -1.f);
         if (r < nrows) a0 = s_rows[0][r + (r >> 3)];
         // G2P stores the mass NEGATED when the particle's base node left the tile of the run it was
@@ -932,6 +974,7 @@ __global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int
       int ox = lane / 9 - 1, oy = (lane / 3) % 3 - 1, oz = lane % 3 - 1;
       int x = tx + ox, y = ty + oy, z = tz + oz - P.tz_off;  // z: local layer
       if (x >= 0 && y >= 0 && z >= 0 && x < P.nt[0] && y < P.nt[1] && z < P.nt[2]) my_nb = V.slot_map[(x * P.nt[1] + y) * P.nt[2] + z];
+      if (!MPMB_CHK(V.cnt, my_nb >= -1 && my_nb < V.cap_tiles, 5, slot, my_nb, lane)) my_nb = -1;
     }
 #pragma unroll 2
     for (int n0 = 0; n0 < ARENA; n0 += 32) {
@@ -965,14 +1008,18 @@ constexpr int G2P_CH = 256;  // rows per pipeline stage
 // affine matrix A — so inside mpmb_substep(h, n) only the LAST substep has to leave it behind for the
 // host (downloads, visualize, save).
 template <int BLOCK, bool STORE_B>
-__global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4 *vel, int part) {
+__global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4 *vel, int part, int commit) {
   __shared__ __align__(16) float4 s_vel[2][ARENA];
   __shared__ __align__(16) float4 s_in[2][4][G2P_CH];
   // output row of every staged row: run rows at [sh + r] (sh = 16-byte alignment shift of the run's outpos words),
   // arrival rows at [r + 8] — clear of the up to 3 words by which the bulk copy of the run part is rounded up
   __shared__ __align__(16) uint32_t s_out[2][G2P_CH + 8];
   __shared__ __align__(8) uint64_t s_bar[2];               // one mbarrier per pipeline stage
-  __shared__ int s_stay;
+  // particles of the current tile that stay in it.  TWO slots, alternating per tile: thread 0 reads and clears a tile's
+  // slot after the tile's last barrier while the other warps are already adding to the next tile's slot — with one slot
+  // (round 1, when a barrier at the top of the loop covered it) a late warp 0 folded the next tile's first additions
+  // into this tile's count: stay counts drifted, runs overlapped (found on a B200 with -DMPMB_VALIDATE, round 2)
+  __shared__ int s_stay[2];
   constexpr int KPT = G2P_CH / BLOCK;
   const int tid = threadIdx.x;
   const int n_tiles = V.cnt->n_tiles;
@@ -1026,7 +1073,8 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
         for (int k = 0; k < KPT; k++) {
           const int r = k * BLOCK + tid;
           if (r >= nrun && r < nrows) {
-            const uint32_t pidx = V.arrivals_sorted[it.tm.arr_off + (it.rb + r - it.tm.run_len)];
+            uint32_t pidx = V.arrivals_sorted[it.tm.arr_off + (it.rb + r - it.tm.run_len)];
+            if (!MPMB_CHK(V.cnt, pidx < (uint32_t)V.cap_particles, 6, it.slot, pidx, r)) pidx = 0u;
             cp_async16(&s_in[buf][0][r], &V.q[0][pidx]);
             cp_async16(&s_in[buf][1][r], &V.q[4][pidx]);
             cp_async16(&s_in[buf][2][r], &V.q[5][pidx]);
@@ -1043,11 +1091,12 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     mbar_init_fence();
-    s_stay = 0;
+    s_stay[0] = 0;
+    s_stay[1] = 0;
   }
   __syncthreads();
   Item cur = first_item(blockIdx.x);
-  int buf = 0, vbuf = 0;
+  int buf = 0, vbuf = 0, sp = 0;
   unsigned phase = 0;  // bit b = parity of the phase stage b's barrier is in
   prefetch(cur, 0, 0);
   while (cur.slot < n_tiles) {
@@ -1076,6 +1125,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
         base_rel(q0.y, P.inv_dx, by, ry);
         base_rel(q0.z, P.inv_dx, bz, rz);
         bx -= tx * 4; by -= ty * 4; bz -= tz * 4;
+        if (!MPMB_CHK(V.cnt, (unsigned)bx < 4u && (unsigned)by < 4u && (unsigned)bz < 4u, 8, cur.slot, (bx & 255) | ((by & 255) << 8) | ((bz & 255) << 16), cur.rb + r)) continue;
         float wx[3], wy[3], wz[3];
         bspline_weights(rx, wx);
         bspline_weights(ry, wy);
@@ -1111,6 +1161,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
         asm volatile("" ::: "memory");
         const float4 q4 = s_in[buf][1][r], q5 = s_in[buf][2][r], q6 = s_in[buf][3][r];
         const size_t o = s_out[buf][r < nrun ? sh + r : r + 8];
+        if (!MPMB_CHK(V.cnt, o < (size_t)V.cap_particles && (int)o >= cur.tm.out_begin && (int)o < cur.tm.out_begin + cur.tm.run_len + cur.tm.arr_len, 7, cur.slot, o, r)) continue;
         const float vol = q6.z;
         const uint32_t tag = __float_as_uint(q6.w);
         const Material &mat = P.mats[tag >> TAG_ID_BITS];
@@ -1138,21 +1189,40 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
           my_stay++;
         } else if (key != (uint32_t)(P.ntiles_total + SPECIAL_DEAD)) {
           const int m = atomicAdd(&V.cnt->n_movers_next, 1);  // ~0.5 % of the particles per substep
+          if (!MPMB_CHK(V.cnt, m < V.cap_particles, 9, m, key, 0)) continue;
           V.mover_dst_n[m] = key;
           V.mover_idx_n[m] = (uint32_t)o;
+          MPMB_COUNT_ARRIVAL(V, P, key);  // the next ordering's arrival count of that tile
         }
       }
-      if (my_stay) atomicAdd(&s_stay, my_stay);
+      if (my_stay) atomicAdd(&s_stay[sp], my_stay);
     }
     __syncthreads();  // everyone is done with `buf` before the prefetch after next overwrites it
     if (nxt.slot != cur.slot) {
-      if (tid == 0) { V.stay_next[cur.tm.tile] = s_stay; s_stay = 0; }
+      if (tid == 0) { V.stay_next[cur.tm.tile] = s_stay[sp]; s_stay[sp] = 0; }
+      sp ^= 1;
     }
     cur = nxt;
     buf ^= 1;
     vbuf = nvbuf;
   }
   cp_async_wait_all();
+  // end of the substep: the lists and runs this kernel produced become the current ones — done by the last CTA to
+  // finish (no separate 1-thread launch)
+  if (commit) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(&V.cnt->g2p_done, 1) == (int)gridDim.x - 1) {
+        __threadfence();
+        Counters *c = V.cnt;
+        c->n_movers = atomicAdd(&c->n_movers_next, 0);
+        c->n_movers_next = 0;
+        c->n_store = c->n_alive;  // G2P wrote one row per binned particle
+        c->g2p_done = 0;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------ debug grid
@@ -1219,7 +1289,7 @@ __global__ void k_halo_unpack(View V, Params P, int layer_z, int cap_xy, const i
     if (threadIdx.x == 0) {
       int slot = V.cnt->n_tiles + atomicAdd(&V.cnt->n_ghost, 1);
       if (slot >= V.cap_tiles) { atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY); slot = -1; }
-      else V.slot_map[tile_xy[e] * P.nt[2] + layer_z] = slot;  // rewritten densely by the next ordering
+      else if (MPMB_CHK(V.cnt, (unsigned)tile_xy[e] < (unsigned)(P.nt[0] * P.nt[1]), 10, e, tile_xy[e], count)) V.slot_map[tile_xy[e] * P.nt[2] + layer_z] = slot;  // rewritten densely by the next ordering
       s_slot = slot;
     }
     __syncthreads();
@@ -1262,6 +1332,7 @@ __global__ void k_migrate_unpack(View V, Params P, int cap, const int *hdr, cons
     V.keys[dst] = key;
     V.mover_dst[mbase + e] = key;
     V.mover_idx[mbase + e] = (uint32_t)dst;
+    MPMB_COUNT_ARRIVAL(V, P, key);
   }
 }
 // ---- peer-memory exchange (no NCCL on the data path): the sending kernels store the payload straight into the neighbour
@@ -1356,7 +1427,8 @@ __global__ void __launch_bounds__(128) k_halo_recv2(View V, Params P, int cap_xy
     if (threadIdx.x == 0) {
       int slot = V.cnt->n_tiles + atomicAdd(&V.cnt->n_ghost, 1);
       if (slot >= V.cap_tiles) { atomicOr(&V.cnt->error, DEVERR_TILE_CAPACITY); slot = -1; }
-      else V.slot_map[((const int *)(b + 16))[k] * P.nt[2] + layer] = slot;  // rewritten densely by the next ordering
+      else if (MPMB_CHK(V.cnt, (unsigned)((const int *)(b + 16))[k] < (unsigned)(P.nt[0] * P.nt[1]), 11, k, ((const int *)(b + 16))[k], c0 + c1))
+        V.slot_map[((const int *)(b + 16))[k] * P.nt[2] + layer] = slot;  // rewritten densely by the next ordering
       s_slot = slot;
     }
     __syncthreads();
@@ -1412,6 +1484,7 @@ __global__ void __launch_bounds__(1024) k_migrate_recv2(View V, Params P, int ca
     V.keys[dst] = key;
     V.mover_dst[mbase + e] = key;
     V.mover_idx[mbase + e] = (uint32_t)dst;
+    MPMB_COUNT_ARRIVAL(V, P, key);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1699,7 +1772,8 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
   h->num_sms = prop.multiProcessorCount;
   {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g, P2G_T, 0) == cudaSuccess && occ > 0) h->grid_p2g = h->num_sms * occ;
+    cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_DYN_BYTES);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g, P2G_T, P2G_DYN_BYTES) == cudaSuccess && occ > 0) h->grid_p2g = h->num_sms * occ;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<128, true>, 128, 0) == cudaSuccess && occ > 0) h->grid_g2p = h->num_sms * occ;
   }
   // tiles: every tile of the (slab of the) domain can be active
@@ -2196,7 +2270,6 @@ int mpmb_sort_particles_and_populate_grid(MpmbHandle h) {
   int nl = 3;
   if (h->cap > 0) {
     View V = make_view(h);
-    if (!h->fresh) { k_mover_count<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot); nl++; }
     k_order_a<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot);
     k_order_b<<<1, 1024, 0, h->stream>>>(V, h->ord_blocks);
     k_order_c<<<h->ord_blocks, ORD_B, 0, h->stream>>>(V, h->ntot, h->P.nt[1], h->P.nt[2], h->P.tz_off);
@@ -2205,6 +2278,9 @@ int mpmb_sort_particles_and_populate_grid(MpmbHandle h) {
       k_mover_rank<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot);
       nl += 2;
     }
+#ifdef MPMB_VALIDATE
+    if (!h->fresh) k_validate_order<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot);
+#endif
     h->fresh = false;
   }
   h->launches += nl;
@@ -2219,7 +2295,7 @@ int mpmb_rasterize(MpmbHandle h) {
   if (h->stage != 1) return fail(h, MPMB_ERR_STATE, "rasterize must follow sort_particles_and_populate_grid");
   prof_begin(h, 1);
   View V = make_view(h);
-  if (h->cap > 0) k_p2g<<<h->grid_p2g, P2G_T, 0, h->stream>>>(V, h->P, 0);
+  if (h->cap > 0) k_p2g<<<h->grid_p2g, P2G_T, P2G_DYN_BYTES, h->stream>>>(V, h->P, 0);
   h->launches += 1;
   prof_end(h, 1);
   CUDA_TRY(h, cudaGetLastError());
@@ -2236,12 +2312,11 @@ int mpmb_resample(MpmbHandle h) {
   prof_end(h, 1);
   prof_begin(h, 2);
   if (h->cap > 0) {
-    if (h->skip_b) k_g2p<128, false><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
-    else k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0);
-    k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt);
+    if (h->skip_b) k_g2p<128, false><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0, 1);
+    else k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0, 1);
   }
-  h->launches += 3;
-  prof_end(h, 2);
+  h->launches += 2;
+  prof_end(h, 1);
   CUDA_TRY(h, cudaGetLastError());
   h->cur ^= 1;  // the buffer G2P wrote is the current storage ...
   h->ord ^= 1;  // ... its runs / stay counts are the current ones ...
@@ -2267,7 +2342,7 @@ int mpmb_rasterize_part(MpmbHandle h, int32_t part) {
   if (!((part == 1 && h->stage == 1) || (part == 2 && h->stage == 11))) return fail(h, MPMB_ERR_STATE, "rasterize_part: boundary first, then interior, after sort");
   prof_begin(h, 1);
   View V = make_view(h);
-  if (h->cap > 0) k_p2g<<<h->grid_p2g, P2G_T, 0, h->stream>>>(V, h->P, part);
+  if (h->cap > 0) k_p2g<<<h->grid_p2g, P2G_T, P2G_DYN_BYTES, h->stream>>>(V, h->P, part);
   h->launches += 1;
   prof_end(h, 1);
   CUDA_TRY(h, cudaGetLastError());
@@ -2284,8 +2359,7 @@ int mpmb_resample_part(MpmbHandle h, int32_t part) {
   int nl = 2;
   if (h->cap > 0) {
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, part);
-    k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part);
-    if (part == 1) { k_step_commit<<<1, 1, 0, h->stream>>>(h->cnt); nl++; }
+    k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part, part == 1 ? 1 : 0);
   }
   h->launches += nl;
   prof_end(h, nl);
@@ -2308,7 +2382,13 @@ int mpmb_substep(MpmbHandle h, int32_t nsub) {
     if ((rc = mpmb_sort_particles_and_populate_grid(h)) != MPMB_OK) return rc;
     if ((rc = mpmb_rasterize(h)) != MPMB_OK) return rc;
     if (peers && (rc = xchg_halo_fused(h)) != MPMB_OK) return rc;  // boundary-layer arenas into the neighbours' memory, theirs in as ghosts
-    h->skip_b = (s + 1 < nsub) && h->cfg.world <= 1;  // apic_b only has to exist when control returns to the host
+    // apic_b only has to exist when control returns to the host: no kernel reads it (rasterize uses the affine matrix), so
+    // the intermediate substeps skip its three streams — on z-slab ranks too: an emigrant's record then carries stale
+    // apic_b words, which the receiving rank's own next G2P overwrites before anybody can look at them
+    h->skip_b = (s + 1 < nsub);
+#ifdef MPMB_CHECKED
+    { static const char *dbg = getenv("MPMB_DBG_SKIPB"); if (dbg) h->skip_b = dbg[0] == '1'; }   // debug: force one k_g2p instantiation
+#endif
     rc = mpmb_resample(h);
     h->skip_b = false;
     if (rc != MPMB_OK) return rc;
@@ -2337,6 +2417,17 @@ int mpmb_download_grid(MpmbHandle h, int32_t which, float *dense4) {
 // ------------------------------------------------------------------------------ debug (not part of mpmb.h)
 // Only in builds with -DMPMB_DEBUG_EXPORTS (python -m taichi_mpm_b200.build --define MPMB_DEBUG_EXPORTS --out ...):
 // the product library exports exactly what include/mpmb.h declares.
+#if defined(MPMB_CHECKED) || defined(MPMB_VALIDATE)
+extern "C" int mpmb_debug_check(MpmbHandle h, int *out8) {
+  CHECK_HANDLE(h);
+  cudaStreamSynchronize(h->stream);
+  Counters c;
+  if (cudaMemcpy(&c, h->cnt, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return MPMB_ERR_CUDA;
+  for (int k = 0; k < 8; k++) out8[k] = c.chk[k];
+  out8[4] = c.n_store; out8[5] = c.n_alive; out8[6] = c.n_movers; out8[7] = c.n_tiles;
+  return MPMB_OK;
+}
+#endif
 #ifdef MPMB_DEBUG_EXPORTS
 // which: 0 run_begin 1 run_len 2 stay 3 arr_len 4 out_begin 5 total 6 arr_off   (dense, ntot ints)
 extern "C" int mpmb_debug_dense(MpmbHandle h, int which, int *out) {
