@@ -613,13 +613,14 @@ def soa_e2e(job, args):
     e = job.eng
     d = e.download(sort_by_id=False)
     n = len(d["id"])
+    cap = n + n // 4 + 65536     # a rank's population changes during a frame (migration): room for the download
     host = {}
-    for k, shape, dt_ in (("x", (n, 3), torch.float32), ("v", (n, 3), torch.float32), ("F", (n, 9), torch.float32), ("b", (n, 9), torch.float32),
-                          ("mass", (n,), torch.float32), ("vol", (n,), torch.float32), ("ps", (n,), torch.float32), ("group", (n,), torch.int32)):
+    for k, shape, dt_ in (("x", (cap, 3), torch.float32), ("v", (cap, 3), torch.float32), ("F", (cap, 9), torch.float32), ("b", (cap, 9), torch.float32),
+                          ("mass", (cap,), torch.float32), ("vol", (cap,), torch.float32), ("ps", (cap,), torch.float32), ("group", (cap,), torch.int32)):
         t = torch.empty(shape, dtype=dt_, pin_memory=True)
-        t.numpy()[...] = d[k]
+        t.numpy()[:n] = d[k]
         host[k] = t
-    host["id"] = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+    host["id"] = torch.empty((cap,), dtype=torch.int32, pin_memory=True)
     times, alive = [], n
     # NB ids are renumbered by the field-wise upload (id_base + row); the frames below only time the path
     for f in range(args.frames + 1):
@@ -629,7 +630,7 @@ def soa_e2e(job, args):
                       host["vol"].data_ptr(), host["ps"].data_ptr(), host["group"].data_ptr())
         job.barrier()
         job.substep(args.frame_substeps)
-        alive = e.download_ptrs(n, host["id"].data_ptr(), host["x"].data_ptr(), host["v"].data_ptr(), host["F"].data_ptr(), host["b"].data_ptr(), 0, 0,
+        alive = e.download_ptrs(cap, host["id"].data_ptr(), host["x"].data_ptr(), host["v"].data_ptr(), host["F"].data_ptr(), host["b"].data_ptr(), 0, 0,
                                 host["ps"].data_ptr(), 0)
         job.barrier()
         if f > 0:

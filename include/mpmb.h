@@ -108,6 +108,9 @@ int mpmb_synchronize(MpmbHandle h);
 /* Replaces Particle::initialize(config) of the registered type (e.g. SandParticle::initialize,
  * src/particles.cpp:587-597) for every particle of `group`.                                      */
 int mpmb_set_material(MpmbHandle h, int32_t group, int32_t kind, const float *params, int32_t n_params);
+/* (Called with particles of `group` already resident — between substeps — it also rebuilds their cached
+ * affine matrices, so the next rasterize uses the new material's stress; apic_b must be current, i.e. the
+ * call follows an upload or a completed mpmb_substep / mpmb_resample.)                              */
 /* Replaces Simulation::set_levelset + DynamicLevelSet::sample/get_spatial_gradient as used by
  * apply_grid_boundary_conditions (src/mpm.cpp:296-372) for a static level set.  `sdf4` is a host
  * array [res0+1][res1+1][res2+1][4] = (n_x,n_y,n_z,phi), phi in grid units at the node, n the
@@ -163,6 +166,13 @@ int mpmb_download_particles(MpmbHandle h, int64_t cap, int64_t *n_out, uint32_t 
  * step()).  Without a preceding mpmb_upload_aos of the same pool the image is read first. */
 int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *indices, int64_t n_indices,
                       const MpmbAosLayout *layout, int64_t *n_alive);
+
+/* Frame dump without a host pass over the particles: the per-point records of MPM<3>::write_partio through Partio's
+ * BGEO writer (src/visualize.cpp:16-100, external/partio/src/io/BGEO.cpp:131-150) — big-endian words position xyz,
+ * w = 1, type = 0, index = id, limit = (1,1,1), v xyz: 48 bytes per particle, non-verbose dump — packed on the device in
+ * id order and copied into `records` (cap_records x 48 bytes).  `id_range`: ids are below id_base + id_range.  The caller
+ * writes the file header and trailer around the block (taichi_mpm_b200/bgeo.py does).                              */
+int mpmb_download_bgeo_points(MpmbHandle h, int64_t id_range, void *records, int64_t cap_records, int64_t *n_out);
 
 /* ------------------------------------------------------------------------------ hot path  */
 /* The whole of MPM<3>::substep() on the fast path, `nsub` times (src/mpm.cpp:452-575):

@@ -21,7 +21,7 @@ MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, 
 EXPORTS = [
     "mpmb_create", "mpmb_destroy", "mpmb_last_error", "mpmb_version", "mpmb_set_stream", "mpmb_synchronize",
     "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes", "mpmb_set_id_base",
-    "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_seed_lattice", "mpmb_num_particles", "mpmb_get_update_count", "mpmb_download_particles", "mpmb_download_aos",
+    "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_seed_lattice", "mpmb_num_particles", "mpmb_get_update_count", "mpmb_download_bgeo_points", "mpmb_download_particles", "mpmb_download_aos",
     "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_rasterize_part",
     "mpmb_resample_part", "mpmb_download_grid",
     "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters", "mpmb_get_ordering_stats",
@@ -226,6 +226,15 @@ class Engine:
         n = C.c_int64(0)
         self._check(self.L.mpmb_num_particles(self.h, C.byref(n)))
         return n.value
+
+    def download_bgeo_points(self, id_range, cap=None):
+        """Device-packed BGEO point block (48 big-endian bytes per particle, id order): (n, bytes ndarray)."""
+        if cap is None:
+            cap = max(self.num_particles(), 1)
+        buf = np.empty(cap * 48, np.uint8)
+        n = C.c_int64(0)
+        self._check(self.L.mpmb_download_bgeo_points(self.h, C.c_int64(int(id_range)), _ptr(buf), C.c_int64(cap), C.byref(n)))
+        return n.value, buf[: n.value * 48]
 
     def update_count(self):
         """Particle updates so far, as the reference's update_counter counts them (src/mpm.cpp:436)."""

@@ -460,6 +460,50 @@ __global__ void k_seed_write(View V, Params P, SeedBox B, size_t n_cand, const i
   }
 }
 
+// mpmb_set_material on RESIDENT particles: the cached affine matrix A (q1.w..q3) was computed with the old parameters
+// (pack_one at upload, or the last G2P); rebuild it from (F, scalar, vol, apic_b) for the rows of that group so that
+// the next rasterize uses the new material's stress (src/transfer.cpp:503,509,521-522).
+__global__ void k_refresh_affine(View V, Params P, const uint32_t *keys, int n, uint32_t special_min, int group) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || keys[i] >= special_min) return;
+  const float4 q6 = V.q[6][i];
+  if ((int)(__float_as_uint(q6.w) >> TAG_ID_BITS) != group) return;
+  const float4 q0 = V.q[0][i], q1 = V.q[1][i], q4 = V.q[4][i], q5 = V.q[5][i], q7 = V.q[7][i], q8 = V.q[8][i], q9 = V.q[9][i];
+  Mat3 F, b, force, A;
+  F.m[0] = q4.x; F.m[1] = q4.y; F.m[2] = q4.z; F.m[3] = q4.w; F.m[4] = q5.x; F.m[5] = q5.y; F.m[6] = q5.z; F.m[7] = q5.w; F.m[8] = q6.x;
+  b.m[0] = q7.x; b.m[1] = q7.y; b.m[2] = q7.z; b.m[3] = q7.w; b.m[4] = q8.x; b.m[5] = q8.y; b.m[6] = q8.z; b.m[7] = q8.w; b.m[8] = q9.x;
+  calculate_force(P.mats[group], F, q6.y, q6.z, force);
+  make_affine(force, b, fabsf(q0.w), -4.0f * P.inv_dx * P.dt, A);
+  V.q[1][i] = make_float4(q1.x, q1.y, q1.z, A.m[0]);
+  V.q[2][i] = make_float4(A.m[1], A.m[2], A.m[3], A.m[4]);
+  V.q[3][i] = make_float4(A.m[5], A.m[6], A.m[7], A.m[8]);
+}
+
+// ------------------------------------------------------------------------------ frame dump
+// The per-point records of MPM<3>::write_partio -> Partio's BGEO writer (src/visualize.cpp:16-100,
+// external/partio/src/io/BGEO.cpp:131-150) packed on the device: big-endian 4-byte words
+//   position xyz, w = 1.0f, type = 0 (is_rigid), index = id, limit = (1,1,1), v xyz        (12 words, non-verbose dump)
+// in id order, which is the order the reference sorts its particles into before writing (visualize.cpp:39-43).
+__device__ __forceinline__ uint32_t be32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+__global__ void k_id_flags(View V, const uint32_t *keys, int n, uint32_t special_min, uint32_t id_base, int64_t id_range, int *flags, Counters *cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || keys[i] >= special_min) return;
+  const uint32_t id = (__float_as_uint(V.q[6][i].w) & TAG_ID_MASK) - id_base;
+  if ((int64_t)id >= id_range) { atomicOr(&cnt->error, DEVERR_BAD_INPUT); return; }
+  flags[id] = 1;
+}
+__global__ void k_bgeo_points(View V, const uint32_t *keys, int n, uint32_t special_min, uint32_t id_base, int64_t id_range, const int *prefix, uint32_t *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || keys[i] >= special_min) return;
+  const float4 q0 = V.q[0][i], q1 = V.q[1][i];
+  const uint32_t gid = __float_as_uint(V.q[6][i].w) & TAG_ID_MASK, id = gid - id_base;
+  if ((int64_t)id >= id_range) return;
+  uint4 *rec = reinterpret_cast<uint4 *>(out + (size_t)prefix[id] * 12);
+  rec[0] = make_uint4(be32(__float_as_uint(q0.x)), be32(__float_as_uint(q0.y)), be32(__float_as_uint(q0.z)), be32(__float_as_uint(1.0f)));
+  rec[1] = make_uint4(0u, be32(gid), be32(1u), be32(1u));
+  rec[2] = make_uint4(be32(1u), be32(__float_as_uint(q1.x)), be32(__float_as_uint(q1.y)), be32(__float_as_uint(q1.z)));
+}
+
 // ------------------------------------------------------------------------------ AoS write-back
 // mpmb_download_aos on the device: every live row goes back into its slot of the (device image of the) reference's
 // pool and raises the alive flag of its id; the survivors' slots, in id order, are then one stream compaction away.
@@ -1707,6 +1751,8 @@ static int alloc_particles(MpmbEngine *h, int64_t cap) {
 
 extern "C" {
 
+static int read_n_store(MpmbEngine *h, int *n_store);
+
 int mpmb_version(void) { return MPMB_VERSION; }
 
 const char *mpmb_last_error(MpmbHandle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -1868,6 +1914,18 @@ int mpmb_set_material(MpmbHandle h, int32_t group, int32_t kind, const float *pa
   if (n_params < 0 || n_params > MPMB_MAT_PARAMS || (n_params > 0 && !params)) return fail(h, MPMB_ERR_INVALID, "bad parameter vector");
   h->P.mats[group].kind = kind;
   for (int k = 0; k < 8; k++) h->P.mats[group].p[k] = k < n_params ? params[k] : 0.f;
+  // particles of this group already resident: their cached affine matrix belongs to the old material
+  if (h->cap > 0 && h->stage == 0) {
+    int ns = 0;
+    int rc = read_n_store(h, &ns);
+    if (rc != MPMB_OK) return rc;
+    if (ns > 0) {
+      View V = make_view(h);
+      k_refresh_affine<<<(ns + 127) / 128, 128, 0, h->stream>>>(V, h->P, h->keys[h->cur], ns, h->special_min, group);
+      h->launches++;
+      CUDA_TRY(h, cudaGetLastError());
+    }
+  }
   return MPMB_OK;
 }
 
@@ -2259,6 +2317,38 @@ int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *in
   CUDA_TRY(h, cudaGetLastError());
   h->aos_host_pool = nullptr;   // the host owns the pool again: the next upload refreshes the image
   *n_alive = alive;
+  return MPMB_OK;
+}
+
+int mpmb_download_bgeo_points(MpmbHandle h, int64_t id_range, void *records, int64_t cap_records, int64_t *n_out) {
+  CHECK_HANDLE(h);
+  if (!records || !n_out || id_range <= 0) return fail(h, MPMB_ERR_INVALID, "bad argument");
+  int ns = 0, rc;
+  if ((rc = mpmb_synchronize(h)) != MPMB_OK) return rc;
+  if ((rc = read_n_store(h, &ns)) != MPMB_OK) return rc;
+  *n_out = 0;
+  if (ns == 0 || h->cap == 0) return MPMB_OK;
+  if ((rc = scan_reserve(h, (size_t)id_range)) != MPMB_OK) return rc;
+  CUDA_TRY(h, cudaMemsetAsync(h->scan_a, 0, sizeof(int) * (size_t)id_range, h->stream));
+  View V = make_view(h);
+  k_id_flags<<<(ns + 255) / 256, 256, 0, h->stream>>>(V, h->keys[h->cur], ns, h->special_min, h->id_base, id_range, h->scan_a, h->cnt);
+  int alive = 0;
+  if ((rc = scan_flags(h, (size_t)id_range, &alive)) != MPMB_OK) return rc;
+  if (alive > cap_records) return fail(h, MPMB_ERR_CAPACITY, "%d live particles do not fit in the %lld records provided", alive, (long long)cap_records);
+  const size_t bytes = (size_t)alive * 48;
+  if (h->stage_bytes < bytes) {
+    cudaFree(h->stage_buf);
+    h->stage_buf = nullptr;
+    h->stage_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->stage_buf, bytes));
+    h->stage_bytes = bytes;
+  }
+  k_bgeo_points<<<(ns + 127) / 128, 128, 0, h->stream>>>(V, h->keys[h->cur], ns, h->special_min, h->id_base, id_range, h->scan_b, (uint32_t *)h->stage_buf);
+  h->launches += 2;
+  CUDA_TRY(h, cudaMemcpyAsync(records, h->stage_buf, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = mpmb_synchronize(h)) != MPMB_OK) return rc;
+  CUDA_TRY(h, cudaGetLastError());
+  *n_out = alive;
   return MPMB_OK;
 }
 

@@ -265,9 +265,19 @@ class MPM:
         self.frame_count += 1
         os.makedirs(self.frame_directory, exist_ok=True)
         fn = os.path.join(self.frame_directory, "%04d.bgeo" % self.frame_count)
+        if not self.verbose_bgeo and hasattr(self.engine, "download_bgeo_points"):
+            # non-verbose dump: the point records are packed on the device in id order (48 B per particle cross the bus
+            # instead of the full state, and no host pass over the particles)
+            self._push()
+            n, block = self.engine.download_bgeo_points(self._id_range())
+            bgeo.write_bgeo_packed(fn, n, block)
+            return fn
         p = self.get_particles()
         bgeo.write_bgeo(fn, p["x"], frame_attributes(p, [k for k, _ in self._groups], self.verbose_bgeo))
         return fn
+
+    def _id_range(self):
+        return max(int(self._n_uploaded), 1)
 
     def general_action(self, **kwargs):
         """The actions of MPM<dim>::general_action (src/mpm.cpp:920-976) that concern the accelerated

@@ -37,6 +37,15 @@ struct int2 { int x, y; };
 struct int3 { int x, y, z; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+// PRMT: result byte k = byte sel[k] of the 8-byte value {y:x}
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+  unsigned long long v = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int k = 0; k < 4; k++) r |= (unsigned)((v >> (8 * ((s >> (4 * k)) & 7))) & 0xff) << (8 * k);
+  return r;
+}
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
