@@ -121,6 +121,23 @@ int mpmb_set_sdf(MpmbHandle h, const float *sdf4, float friction);
  * phi = min_i phi_i, n = n of the minimiser (levelset.add_plane in scripts/mls-cpic/sand_sweep.py:13-19). */
 int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float friction);
 
+/* The level set rasterised on the device from analytic solids (what the reference's scripts build with
+ * levelset.add_plane / add_sphere / add_cuboid, e.g. scripts/mls-cpic/sand_sweep.py:13-19, scripts/async/sand.py:35,
+ * scripts/mls-cpic/sand_stir.py:9): phi = min over the shapes of their signed distance in GRID units (negative inside
+ * the obstacle), n = unit gradient of the minimiser; inside_out makes a container of a solid.  Parameters (grid units):
+ *   PLANE  p = {n_x, n_y, n_z, d}       phi = n.X + d  (n unit)
+ *   SPHERE p = {c_x, c_y, c_z, r}       phi = |X - c| - r
+ *   CUBOID p = {lo_x, lo_y, lo_z, hi_x, hi_y, hi_z}   exact box distance
+ * The shape formulas of the reference live in its un-vendored core (LevelSet3D): planes are pinned by the in-place build
+ * (DESIGN.md §2), sphere and cuboid follow the published signed-distance definitions — parity unpinned for those two. */
+typedef enum MpmbShapeKind { MPMB_SHAPE_PLANE = 0, MPMB_SHAPE_SPHERE = 1, MPMB_SHAPE_CUBOID = 2 } MpmbShapeKind;
+typedef struct MpmbShape {
+  int32_t kind;        /* MpmbShapeKind */
+  int32_t inside_out;  /* 0: the solid is the obstacle; 1: its complement is (a container) */
+  float p[6];
+} MpmbShape;
+int mpmb_set_levelset_shapes(MpmbHandle h, int32_t n_shapes, const MpmbShape *shapes, float friction);
+
 /* ------------------------------------------------------------------------------ particles */
 /* Replaces MPM<3>::add_particles' writes into the particle pool (src/mpm.cpp:93-148) for n
  * particles given field-wise: x[n][3], v[n][3], F[n][9], b[n][9] (apic_b), mass[n], vol[n],

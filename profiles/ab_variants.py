@@ -42,7 +42,9 @@ def main():
                                env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
             try:
                 line = json.loads(r.stdout.strip().splitlines()[-1])
-                rows[name].append((line["ms_per_step"], line["roofline"]["stage_ms_per_step"]))
+                st = line.get("states") or {}
+                both = {k: (round(v["ms_per_step"], 4), {a: round(b, 4) for a, b in v["stage_ms_per_step"].items()}) for k, v in st.items() if isinstance(v, dict)}
+                rows[name].append((line["ms_per_step"], both or line["roofline"]["stage_ms_per_step"]))
             except Exception:
                 rows[name].append((None, r.stderr[-300:]))
             print(name, rows[name][-1], flush=True)

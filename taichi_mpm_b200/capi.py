@@ -20,7 +20,7 @@ MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, 
 # every symbol include/mpmb.h declares
 EXPORTS = [
     "mpmb_create", "mpmb_destroy", "mpmb_last_error", "mpmb_version", "mpmb_set_stream", "mpmb_synchronize",
-    "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes", "mpmb_set_id_base",
+    "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes", "mpmb_set_levelset_shapes", "mpmb_set_id_base",
     "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_seed_lattice", "mpmb_num_particles", "mpmb_get_update_count", "mpmb_download_bgeo_points", "mpmb_download_particles", "mpmb_download_aos",
     "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_rasterize_part",
     "mpmb_resample_part", "mpmb_download_grid",
@@ -58,6 +58,11 @@ class MpmbAosLayout(C.Structure):
     ]
 
 
+class MpmbShape(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("inside_out", C.c_int32), ("p", C.c_float * 6)]
+
+
+SHAPE_PLANE, SHAPE_SPHERE, SHAPE_CUBOID = range(3)
 _LIB = None
 
 
@@ -171,6 +176,15 @@ class Engine:
     def set_planes(self, planes4, friction):
         planes4 = _f32(planes4).reshape(-1, 4)
         self._check(self.L.mpmb_set_planes(self.h, C.c_int32(len(planes4)), _ptr(planes4), C.c_float(friction)))
+
+    def set_levelset_shapes(self, shapes, friction):
+        """shapes: [(kind, inside_out, params[<=6])] in GRID units (mpmb.h)."""
+        arr = (MpmbShape * len(shapes))()
+        for k, (kind, io, prm) in enumerate(shapes):
+            arr[k].kind, arr[k].inside_out = int(kind), int(bool(io))
+            for j, v in enumerate(prm):
+                arr[k].p[j] = float(v)
+        self._check(self.L.mpmb_set_levelset_shapes(self.h, C.c_int32(len(shapes)), arr, C.c_float(friction)))
 
     def set_id_base(self, base):
         self._check(self.L.mpmb_set_id_base(self.h, C.c_int64(int(base))))

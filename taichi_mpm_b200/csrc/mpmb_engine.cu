@@ -864,7 +864,10 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
         // its new one, and two CTAs must not write different values to one outpos entry
       }
       __syncthreads();
-      // ---- 3: accumulate my cell's run in registers
+      // ---- 3: accumulate my cell's run in registers.  A warp iterates as long as its fullest cell has particles; in a
+      // developed flow (cells hold 0..30 particles: mean/max per warp 0.56, profiles/r02_flow_stats.jsonl) that is the
+      // kernel's cost.  Measured and rejected (round 2): capping the loop and adding the excess particles with one lane
+      // per stencil node — 0.403 instead of 0.329 ms, the serialised excess pass costs more than the idle tail.
       const int i0 = s_start[tid], i1 = s_start[tid + 1];
       for (int it = i0; it < i1; it++) {
         const int r = s_order[it];
@@ -1297,6 +1300,58 @@ __global__ void k_planes_to_sdf(Params P, int n_planes, const float4 *planes, fl
       if (phi < best) { best = phi; out = make_float4(pl.x, pl.y, pl.z, phi); }
     }
     sdf4[i] = out;
+  }
+}
+
+// Level set rasterised on the device from analytic solids (the scripts build theirs with
+// levelset.add_plane / add_cuboid / add_sphere, scripts/mls-cpic/sand_sweep.py:13-19, scripts/async/sand.py:35,
+// scripts/mls-cpic/sand_stir.py:9): phi = min over the shapes of their signed distance (grid units, negative inside the
+// obstacle), n = the unit gradient of the minimiser.  inside_out turns a solid into a container.
+//   plane   p = (n_x, n_y, n_z, d):      phi = n.X + d
+//   sphere  p = (c_x, c_y, c_z, r):      phi = |X - c| - r
+//   cuboid  p = (lo_xyz, hi_xyz):        phi = exact box distance (outside: to the nearest face/edge/corner; inside: -depth)
+__device__ __forceinline__ float4 shape_sdf(const MpmbShape &S, float x, float y, float z) {
+  float4 o;  // (n, phi)
+  if (S.kind == MPMB_SHAPE_PLANE) {
+    o = make_float4(S.p[0], S.p[1], S.p[2], S.p[0] * x + S.p[1] * y + S.p[2] * z + S.p[3]);
+  } else if (S.kind == MPMB_SHAPE_SPHERE) {
+    const float dx = x - S.p[0], dy = y - S.p[1], dz = z - S.p[2];
+    const float r = sqrtf(dx * dx + dy * dy + dz * dz), inv = r > 1e-20f ? 1.0f / r : 0.f;
+    o = make_float4(dx * inv, dy * inv, dz * inv, r - S.p[3]);
+    if (!(r > 1e-20f)) o.x = 1.f;
+  } else {
+    const float X[3] = {x, y, z};
+    float q[3], out2 = 0.f, depth = 1e30f;
+    int amax = 0;
+    float sgn[3];
+    for (int a = 0; a < 3; a++) {
+      const float c = 0.5f * (S.p[a] + S.p[3 + a]), hw = 0.5f * (S.p[3 + a] - S.p[a]);
+      const float d = X[a] - c;
+      sgn[a] = d < 0.f ? -1.f : 1.f;
+      q[a] = fabsf(d) - hw;                  // > 0 outside along this axis
+      if (q[a] > 0.f) out2 += q[a] * q[a];
+      if (-q[a] < depth) { depth = -q[a]; amax = a; }
+    }
+    if (out2 > 0.f) {
+      const float r = sqrtf(out2), inv = 1.0f / r;
+      o = make_float4(q[0] > 0.f ? sgn[0] * q[0] * inv : 0.f, q[1] > 0.f ? sgn[1] * q[1] * inv : 0.f, q[2] > 0.f ? sgn[2] * q[2] * inv : 0.f, r);
+    } else {
+      o = make_float4(amax == 0 ? sgn[0] : 0.f, amax == 1 ? sgn[1] : 0.f, amax == 2 ? sgn[2] : 0.f, -depth);
+    }
+  }
+  if (S.inside_out) o = make_float4(-o.x, -o.y, -o.z, -o.w);
+  return o;
+}
+__global__ void k_shapes_to_sdf(Params P, int n_shapes, const MpmbShape *shapes, float4 *sdf4) {
+  size_t n = (size_t)P.nnode[0] * P.nnode[1] * P.nnode[2];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int gz = (int)(i % P.nnode[2]), gy = (int)((i / P.nnode[2]) % P.nnode[1]), gx = (int)(i / ((size_t)P.nnode[2] * P.nnode[1]));
+    float4 best = make_float4(1.f, 0.f, 0.f, 1e30f);
+    for (int k = 0; k < n_shapes; k++) {
+      const float4 c = shape_sdf(shapes[k], (float)gx, (float)gy, (float)gz);
+      if (c.w < best.w) best = c;
+    }
+    sdf4[i] = best;
   }
 }
 
@@ -1963,6 +2018,26 @@ int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float 
   h->launches++;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   cudaFree(d_planes);
+  h->P.has_sdf = 1;
+  h->P.friction = friction;
+  return MPMB_OK;
+}
+
+int mpmb_set_levelset_shapes(MpmbHandle h, int32_t n_shapes, const MpmbShape *shapes, float friction) {
+  CHECK_HANDLE(h);
+  if (n_shapes <= 0 || n_shapes > 64 || !shapes) return fail(h, MPMB_ERR_INVALID, "need 1..64 shapes");
+  for (int k = 0; k < n_shapes; k++)
+    if (shapes[k].kind < MPMB_SHAPE_PLANE || shapes[k].kind > MPMB_SHAPE_CUBOID) return fail(h, MPMB_ERR_INVALID, "unknown shape kind %d", shapes[k].kind);
+  size_t n = (size_t)h->P.nnode[0] * h->P.nnode[1] * h->P.nnode[2];
+  if (!h->sdf4) CUDA_TRY(h, cudaMalloc(&h->sdf4, sizeof(float4) * n));
+  MpmbShape *d_shapes = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d_shapes, sizeof(MpmbShape) * n_shapes));
+  CUDA_TRY(h, cudaMemcpyAsync(d_shapes, shapes, sizeof(MpmbShape) * n_shapes, cudaMemcpyHostToDevice, h->stream));
+  k_shapes_to_sdf<<<h->num_sms * 8, 256, 0, h->stream>>>(h->P, n_shapes, d_shapes, h->sdf4);
+  h->launches++;
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_shapes);
+  CUDA_TRY(h, e);
   h->P.has_sdf = 1;
   h->P.friction = friction;
   return MPMB_OK;

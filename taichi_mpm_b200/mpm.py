@@ -49,6 +49,7 @@ class LevelSet:
         self.res = tuple(res)
         self.delta_x = delta_x
         self.planes = []
+        self.shapes = []      # (kind, inside_out, params) in WORLD units, in the order they were added
         self.friction = 0.0
         self.dense = None
 
@@ -57,8 +58,22 @@ class LevelSet:
         n = n / np.linalg.norm(n)
         self.planes.append((n[0], n[1], n[2], float(d)))
 
+    def add_sphere(self, center, radius, inside_out=False):
+        """tc LevelSet3D.add_sphere (scripts/mls-cpic/sand_stir.py:9)."""
+        self.shapes.append((capi.SHAPE_SPHERE, bool(inside_out), [float(c) for c in center] + [float(radius)]))
+
+    def add_cuboid(self, lower, upper, inside_out=False):
+        """tc LevelSet3D.add_cuboid (scripts/async/sand.py:35)."""
+        self.shapes.append((capi.SHAPE_CUBOID, bool(inside_out), [float(c) for c in lower] + [float(c) for c in upper]))
+
     def set_friction(self, f):
         self.friction = float(f)
+
+    def shapes_grid_units(self):
+        """Planes and solids as the engine takes them: lengths divided by dx (plane normals are unit)."""
+        out = [(capi.SHAPE_PLANE, False, [p[0], p[1], p[2], p[3] / self.delta_x]) for p in self.planes]
+        out += [(k, io, [v / self.delta_x for v in prm]) for k, io, prm in self.shapes]
+        return out
 
     def set_dense(self, sdf4):
         """Arbitrary static level set sampled at the nodes: [nx][ny][nz][4] = (n, phi in grid units)."""
@@ -119,6 +134,8 @@ class MPM:
             raise ValueError("dynamic level sets are outside the accelerated fast path")
         if levelset.dense is not None:
             self.engine.set_sdf(levelset.dense, levelset.friction)
+        elif levelset.shapes:
+            self.engine.set_levelset_shapes(levelset.shapes_grid_units(), levelset.friction)
         elif levelset.planes:
             self.engine.set_planes(levelset.planes_grid_units(), levelset.friction)
         else:

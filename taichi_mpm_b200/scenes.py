@@ -149,6 +149,54 @@ def planes_sdf(res, planes, dtype=np.float32):
     return out.astype(dtype)
 
 
+def shapes_sdf(res, shapes, dtype=np.float32):
+    """Numpy twin of mpmb_set_levelset_shapes (include/mpmb.h): dense node level set (n, phi) in grid units from
+    [(kind, inside_out, params)], kind 0 plane / 1 sphere / 2 cuboid; phi = min over shapes."""
+    if np.isscalar(res):
+        res = (res, res, res)
+    nn = [r + 1 for r in res]
+    X = np.stack(np.meshgrid(*[np.arange(n, dtype=np.float32) for n in nn], indexing="ij"), -1)
+    best = np.full(nn, 1e30, np.float32)
+    out = np.zeros(tuple(nn) + (4,), np.float32)
+    out[..., 0] = 1.0
+    out[..., 3] = 1e30
+    f32 = np.float32
+    for kind, io, prm in shapes:
+        p = np.asarray(list(prm) + [0.0] * (6 - len(prm)), np.float32)
+        if kind == 0:
+            n = np.broadcast_to(p[:3], X.shape).copy()
+            phi = p[0] * X[..., 0] + p[1] * X[..., 1] + p[2] * X[..., 2] + p[3]
+        elif kind == 1:
+            d = X - p[:3]
+            r = np.sqrt((d * d).sum(-1, dtype=np.float32))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                n = np.where(r[..., None] > 1e-20, d * (f32(1.0) / r)[..., None], np.array([1.0, 0.0, 0.0], np.float32))
+            phi = r - p[3]
+        else:
+            c, hw = f32(0.5) * (p[:3] + p[3:6]), f32(0.5) * (p[3:6] - p[:3])
+            d = X - c
+            sgn = np.where(d < 0, f32(-1), f32(1))
+            q = np.abs(d) - hw
+            qp = np.where(q > 0, q, f32(0))
+            out2 = (qp * qp).sum(-1, dtype=np.float32)
+            r = np.sqrt(out2)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                n_out = sgn * qp * (f32(1.0) / r)[..., None]
+            amax = np.argmin(-q, -1)            # first axis of least depth
+            n_in = np.zeros_like(d)
+            np.put_along_axis(n_in, amax[..., None], np.take_along_axis(sgn, amax[..., None], -1), -1)
+            outside = out2 > 0
+            n = np.where(outside[..., None], n_out, n_in)
+            phi = np.where(outside, r, -(-q).min(-1))
+        if io:
+            n, phi = -n, -phi
+        m = phi < best
+        best = np.where(m, phi, best)
+        out[..., :3] = np.where(m[..., None], n, out[..., :3])
+        out[..., 3] = best
+    return out.astype(dtype)
+
+
 def config(name, scale=1.0, state=True):
     """The BASELINE.json configs as dict(scene=..., state=..., meta=...).
 

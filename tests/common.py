@@ -57,7 +57,9 @@ def make_engine(scene, state, **kw):
                     kw.pop("clean_boundary", True), **kw)
     for g, (k, p) in enumerate(zip(scene["mat_kind"], scene["mat_params"])):
         e.set_material(g, int(k), p)
-    if scene.get("sdf_dense_upload") is not None:
+    if scene.get("shapes") is not None:
+        e.set_levelset_shapes(scene["shapes"], scene["friction"])
+    elif scene.get("sdf_dense_upload") is not None:
         e.set_sdf(scene["sdf_dense_upload"], scene["friction"])
     elif scene.get("planes") is not None:
         e.set_planes(scene["planes"], scene["friction"])

@@ -64,12 +64,13 @@ void run(unsigned grid, unsigned block, const std::function<void()> &body) {
     const unsigned bid = bids[bi];
     g_blockIdx.x = bid; g_blockIdx.y = g_blockIdx.z = 0;
     blk.at_barrier = blk.done = 0;
+    blk.or_acc[0] = blk.or_acc[1] = 0;
     for (auto &w : blk.warps) { w.phase = 0; w.arrived = w.released = 0; w.exited = 0; }
     // lanes that do not exist count as exited
     if (block % 32) blk.warps.back().exited = ~0u << (block % 32);
     for (unsigned t = 0; t < block; t++) {
       Thread &th = blk.th[t];
-      th.tid = t; th.state = 0; th.stack = g_stacks[t];
+      th.tid = t; th.state = 0; th.stack = g_stacks[t]; th.or_gen = 0;
       getcontext(&th.ctx);
       th.ctx.uc_stack.ss_sp = th.stack;
       th.ctx.uc_stack.ss_size = kStack;
@@ -140,6 +141,17 @@ void __syncthreads() {
   t.state = 1;
   b->at_barrier++;
   simt::yield();
+}
+int __syncthreads_or(int pred) {
+  simt::Block *b = simt::g_blk;
+  simt::Thread &t = b->th[b->cur];
+  const int g = t.or_gen;
+  t.or_gen ^= 1;
+  if (pred) b->or_acc[g] = 1;
+  __syncthreads();
+  const int r = b->or_acc[g];
+  b->or_acc[g ^ 1] = 0;  // the other accumulator: everybody has read its last value (they all passed this barrier)
+  return r;
 }
 void __syncwarp(unsigned mask) {
   unsigned part;

@@ -64,6 +64,7 @@ struct Thread {
   char *stack = nullptr;
   int state = 0;  // 0 runnable, 1 at block barrier, 2 done
   unsigned tid = 0;
+  int or_gen = 0;  // which of the block's two __syncthreads_or accumulators this thread uses next
 };
 struct Warp {
   // collective in flight: phase 0 = collecting, 1 = releasing
@@ -75,6 +76,7 @@ struct Block {
   std::vector<Thread> th;
   std::vector<Warp> warps;
   unsigned n = 0, at_barrier = 0, done = 0;
+  int or_acc[2] = {0, 0};
   std::function<void()> body;
   ucontext_t main;
   int cur = -1;
@@ -116,6 +118,7 @@ inline Launch<K> make_launch(K k, G g, B b, S, St) { return Launch<K>{k, (unsign
 
 // ---- synchronisation and warp collectives
 void __syncthreads();
+int __syncthreads_or(int pred);
 void __syncwarp(unsigned mask = 0xffffffffu);
 static inline unsigned __activemask() { return 0u; }   // 0 = "whoever is here": collectives given it act per lane (see below)
 static inline int __shfl_sync(unsigned mask, int v, int src) {

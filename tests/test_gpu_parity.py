@@ -280,6 +280,37 @@ def test_dense_tiles_need_several_chunks():
     e.close()
 
 
+def test_a_few_overfull_cells_among_ordinary_ones():
+    """The cell-owner loop of k_p2g runs as long as the fullest cell of a warp has particles: a regular 8-per-cell block
+    plus three cells holding 30..45 particles (what a developed flow looks like locally) — node momenta and mass must
+    still match the fp64 oracle, and the ordering must keep the crowded cells consistent."""
+    res = 32
+    rng = np.random.default_rng(31)
+    x, mass, vol = scenes.lattice_block(res, (10, 9, 10), (18, 17, 18), jitter=0.1, seed=30)
+    extra = []
+    for cell, n in (((11, 10, 12), 45), ((13, 12, 15), 30), ((16, 15, 11), 37)):     # base nodes inside different tiles / warps
+        extra.append(((np.asarray(cell) + 0.55 + 0.9 * rng.random((n, 3))) / res).astype(np.float32))
+    xe = np.concatenate(extra)
+    x = np.concatenate([x, xe]); mass = np.concatenate([mass, np.full(len(xe), mass[0] * 0.2, np.float32)])
+    vol = np.concatenate([vol, np.full(len(xe), vol[0] * 0.2, np.float32)])
+    st = scenes.make_state(x, mass, vol, scenes.MAT_SAND)
+    T.perturb_state(st, scenes.MAT_SAND, 1.0 / res, seed=32, strain=0.01, vel=0.5)
+    planes = np.array([[0.0, 1.0, 0.0, -9.6]], np.float32)
+    scene = dict(res=(res,) * 3, dx=1.0 / res, dt=2e-5, gravity=(0.0, -10.0, 0.0), particle_gravity=1,
+                 mat_kind=np.array([scenes.MAT_SAND], np.int32), mat_params=scenes.material_params(scenes.MAT_SAND)[None],
+                 planes=planes, friction=0.4, sdf=scenes.planes_sdf(res, planes))
+    base = (x * res - 0.5).astype(np.int32)
+    per_cell = np.unique(base[:, 0] * 10000 + base[:, 1] * 100 + base[:, 2], return_counts=True)[1]
+    assert per_cell.max() >= 38 and np.sort(per_cell)[-4] <= 14          # three overfull cells, the rest ordinary
+    e = T.make_engine(scene, st)
+    err, got, ref = T.compare_substep(e, scene, st)
+    assert err["alive_match"] and err["grid_rast"] <= T.TOL_GRID_REL and err["grid_vel"] <= 1e-4, err
+    assert err["v"] <= T.TOL_V_REL and err["F"] <= T.TOL_F_ABS and err["x"] <= T.TOL_X_ABS, err
+    e.substep(20)                                                         # and the ordering keeps them consistent
+    assert e.num_particles() == len(x)
+    e.close()
+
+
 def test_reupload_replaces_the_resident_set():
     # the drop-in adapter re-uploads after host-side changes (add_particles, load): same engine, new set
     sc1, st1 = T.perturbed_scene(scenes.MAT_SAND, res=32, cells=6, seed=31)

@@ -68,3 +68,42 @@ def test_boundary_band_is_not_seeded_and_slabs_partition_the_lattice():
     o = np.argsort(both["id"], kind="stable")
     assert np.array_equal(both["id"][o], ids) and np.array_equal(both["x"][o], x)
     assert len(parts[0]["id"]) > 0 and len(parts[1]["id"]) > 0
+
+
+@pytest.mark.parametrize("friction", [0.4, -1.0])
+def test_levelset_shapes_rasterised_on_the_device_match_the_host_twin(friction):
+    """mpmb_set_levelset_shapes (plane + sphere + inside-out cuboid container) against its numpy twin scenes.shapes_sdf
+    fed to the fp64 oracle as a dense level set: same node velocities after the boundary projection, same particles."""
+    from taichi_mpm_b200 import capi
+    res = 32
+    scene, st = T.perturbed_scene(scenes.MAT_SAND, res=res, cells=8, seed=9, vel=1.0, friction=friction)
+    shapes = [(capi.SHAPE_PLANE, False, [0.0, 1.0, 0.0, -9.6]),
+              (capi.SHAPE_SPHERE, False, [16.0, 6.0, 16.0, 5.2]),                       # a ball poking into the block from below
+              (capi.SHAPE_CUBOID, True, [10.3, 8.0, 10.5, 21.4, 24.0, 21.6])]           # a container: walls inside the block's edge cells
+    scene = dict(scene, planes=None, shapes=shapes, sdf=scenes.shapes_sdf(res, shapes))
+    band = (scene["sdf"][..., 3] >= -3.0) & (scene["sdf"][..., 3] <= 0.0)
+    assert band.sum() > 2000                                                            # the boundary band really crosses the scene
+    e = T.make_engine(scene, st)
+    err, got, ref = T.compare_substep(e, scene, st)
+    e.close()
+    print("shapes friction %g:" % friction, {k: float(v) for k, v in err.items() if not isinstance(v, bool)})
+    assert err["alive_match"]
+    assert err["grid_vel"] <= 1e-4 and err["v"] <= T.TOL_V_REL and err["x"] <= T.TOL_X_ABS and err["F"] <= T.TOL_F_ABS
+
+
+def test_mirror_levelset_verbs_reach_the_engine_in_grid_units():
+    from taichi_mpm_b200 import MPM, capi
+    m = MPM(res=(32, 32, 32), base_delta_t=2e-5)
+    ls = m.create_levelset()
+    ls.add_plane((0, 1, 0), -0.3)
+    ls.add_sphere((0.5, 0.55, 0.5), 0.3, True)          # scripts/mls-cpic/sand_stir.py:9
+    ls.add_cuboid((0, 0.2, 0.05), (0.95, 0.95, 0.95), True)   # scripts/async/sand.py:35
+    ls.set_friction(0.5)
+    g = ls.shapes_grid_units()
+    assert [s[0] for s in g] == [capi.SHAPE_PLANE, capi.SHAPE_SPHERE, capi.SHAPE_CUBOID]
+    assert np.allclose(g[0][2], [0, 1, 0, -0.3 * 32]) and np.allclose(g[1][2], [16, 17.6, 16, 9.6]) and g[1][1] and g[2][1]
+    assert np.allclose(g[2][2], [0, 6.4, 1.6, 30.4, 30.4, 30.4])
+    m.set_levelset(ls, False)                            # rasterised on the device (mpmb_set_levelset_shapes)
+    m.add_particles(type="sand", benchmark_block=((12, 12, 12), (16, 16, 16)), density=400)
+    m.step(1e-4)
+    assert m.num_particles() == 4 * 4 * 4 * 8

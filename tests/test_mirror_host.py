@@ -25,6 +25,9 @@ class FakeEngine:
     def set_planes(self, *a):
         pass
 
+    def set_levelset_shapes(self, shapes, friction):
+        self.shapes = (shapes, friction)
+
     def set_id_base(self, base):
         self.id_base = int(base)
 
