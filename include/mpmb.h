@@ -177,10 +177,12 @@ int mpmb_download_particles(MpmbHandle h, int64_t cap, int64_t *n_out, uint32_t 
 /* Writes the live particles back into the reference's AoS pool (slot = indices[id]); returns the
  * number of survivors and compacts `indices` to the survivors (in id order), which is what
  * clear_boundary_particles (src/mpm.cpp:583-633) leaves in MPM::particles.  The scatter runs on the
- * device into the image of the pool kept since mpmb_upload_aos, and the image comes back with ONE
- * contiguous copy: bytes of a slot outside the layout's fields (vptr, flags, ...) return as uploaded,
- * so the pool must not be modified between the two calls (the device owns the particles during
- * step()).  Without a preceding mpmb_upload_aos of the same pool the image is read first. */
+ * device into the image of the pool kept since mpmb_upload_aos; both directions move only the window of
+ * every slot that holds the layout's fields (a 2-D copy with the slot stride as pitch: 204 of the
+ * reference's 320 bytes), so bytes outside it (vptr, flags, ...) are never touched on the host.  Fields
+ * inside the window that the engine does not own (e.g. boundary_normal) return as uploaded: do not
+ * modify the pool between the two calls (the device owns the particles during step()).
+ * Without a preceding mpmb_upload_aos of the same pool the image is read first.                      */
 int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *indices, int64_t n_indices,
                       const MpmbAosLayout *layout, int64_t *n_alive);
 

@@ -1005,7 +1005,9 @@ __device__ __forceinline__ float4 node_update(const Params &P, const float4 *sdf
 // rebuilt (fixed-order sum of the covering arenas), normalised, projected on the level set and
 // stored as one contiguous 3.4 KB block vel[slot][216].  Node-parallel, so the dependent
 // slot_map -> arena -> sdf loads are hidden by occupancy instead of stalling a G2P CTA.
-__global__ void __launch_bounds__(256) k_grid(View V, Params P, float4 *vel, int part) {
+// launch bound (256, 1): 64 registers, 0.058 ms; capping at 40 / 32 registers for 6 / 8 CTAs per SM spills and is not
+// faster (0.064 / 0.056 ms, profiles/r02_ab_grid_occupancy.log)
+__global__ void __launch_bounds__(256, 1) k_grid(View V, Params P, float4 *vel, int part) {
   // one WARP per tile: the 27 neighbour slots live in lanes 0..26 and are fetched with shuffles, so
   // there is no block barrier and every warp of the grid has its own tile in flight
   const int lane = threadIdx.x & 31;
@@ -2151,6 +2153,19 @@ static int scan_flags(MpmbEngine *h, size_t n, int *total) {
   return MPMB_OK;
 }
 
+// byte range [lo, hi) of a slot that the layout's fields occupy: only that window of every slot crosses the bus (a 2-D
+// copy with the slot stride as pitch) — 204 of the reference's 320 bytes
+static void aos_window(const MpmbAosLayout *L, int *lo, int *hi) {
+  const int mat = 2 * L->col_pitch + 12;  // three padded columns, the last one 3 floats long
+  int a = std::min(std::min(L->off_pos, L->off_v_and_m), std::min(L->off_dg_e, L->off_apic_b));
+  int b = std::max(std::max(L->off_pos + 12, L->off_v_and_m + 16), std::max(L->off_dg_e + mat, L->off_apic_b + mat));
+  a = std::min(a, L->off_vol);
+  b = std::max(b, L->off_vol + 4);
+  if (L->off_scalar >= 0) { a = std::min(a, L->off_scalar); b = std::max(b, L->off_scalar + 4); }
+  *lo = std::max(0, a & ~15);
+  *hi = std::min(L->stride, (b + 15) & ~15);
+}
+
 static int aos_reserve(MpmbEngine *h, size_t pool_bytes, size_t n_idx) {
   if (pool_bytes > h->aos_pool_bytes) {
     cudaFree(h->aos_pool);
@@ -2195,7 +2210,12 @@ int mpmb_upload_aos(MpmbHandle h, int64_t n, const void *pool, int64_t pool_slot
     CUDA_TRY(h, cudaMemcpyAsync(d_grp, group, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
   }
   CUDA_TRY(h, cudaMemcpyAsync(h->aos_idx, indices, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(h->aos_pool, pool, pool_bytes, cudaMemcpyHostToDevice, h->stream));
+  {
+    int lo, hi;
+    aos_window(L, &lo, &hi);
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->aos_pool + lo, (size_t)L->stride, (const char *)pool + lo, (size_t)L->stride, (size_t)(hi - lo), (size_t)pool_slots,
+                                  cudaMemcpyHostToDevice, h->stream));
+  }
   View V = make_view(h);
   k_pack_aos<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(V, h->P, (int)n, h->aos_pool, h->aos_idx, *L, d_grp, h->keys[h->cur], h->id_base);
   h->launches++;
@@ -2371,6 +2391,7 @@ int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *in
     CUDA_TRY(h, cudaMemcpyAsync(h->aos_idx, indices, sizeof(uint32_t) * n_indices, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->aos_pool, pool, pool_bytes, cudaMemcpyHostToDevice, h->stream));
   }
+  (void)pool_bytes;
   if ((rc = scan_reserve(h, (size_t)n_indices)) != MPMB_OK) return rc;
   CUDA_TRY(h, cudaMemsetAsync(h->scan_a, 0, sizeof(int) * (size_t)n_indices, h->stream));
   if (ns > 0 && h->cap > 0) {
@@ -2386,7 +2407,12 @@ int mpmb_download_aos(MpmbHandle h, void *pool, int64_t pool_slots, uint32_t *in
   if ((int64_t)h->cap < n_indices) return fail(h, MPMB_ERR_CAPACITY, "index vector longer than the particle capacity");
   k_compact_survivors<<<(unsigned)((n_indices + 255) / 256), 256, 0, h->stream>>>(h->aos_idx, h->scan_a, h->scan_b, n_indices, d_surv);
   h->launches++;
-  CUDA_TRY(h, cudaMemcpyAsync(pool, h->aos_pool, pool_bytes, cudaMemcpyDeviceToHost, h->stream));
+  {  // only the window of every slot that holds the layout's fields comes back; the rest of the host pool is untouched
+    int lo, hi;
+    aos_window(L, &lo, &hi);
+    CUDA_TRY(h, cudaMemcpy2DAsync((char *)pool + lo, (size_t)L->stride, h->aos_pool + lo, (size_t)L->stride, (size_t)(hi - lo), (size_t)pool_slots,
+                                  cudaMemcpyDeviceToHost, h->stream));
+  }
   if (alive > 0) CUDA_TRY(h, cudaMemcpyAsync(indices, d_surv, sizeof(uint32_t) * (size_t)alive, cudaMemcpyDeviceToHost, h->stream));
   if ((rc = mpmb_synchronize(h)) != MPMB_OK) return rc;   // also surfaces ids / slots outside the vectors
   CUDA_TRY(h, cudaGetLastError());
