@@ -77,7 +77,8 @@ struct Counters {  // device-resident
   int n_live;         // scratch of k_count_live (mpmb_num_particles)
   unsigned long long updates;  // sum over substeps of the particles binned: the reference's update_counter (src/mpm.cpp:436)
   int g2p_done;       // CTAs of the running k_g2p that have finished (the last one commits the substep)
-  int pad;
+  int xstep;          // substeps completed since the peers were connected: the sequence number of the peer exchange
+                      // (kept on the device so that a captured CUDA graph of a substep stays valid from replay to replay)
   int chk[8];         // MPMB_CHECKED builds: first violated index check {site, a, b, c, ...}
 };
 // Bounds-checked debug build (-DMPMB_CHECKED): an index that would leave its array is recorded (first one wins) and the
@@ -1268,6 +1269,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
         c->n_movers = atomicAdd(&c->n_movers_next, 0);
         c->n_movers_next = 0;
         c->n_store = c->n_alive;  // G2P wrote one row per binned particle
+        c->xstep += 1;
         c->g2p_done = 0;
       }
     }
@@ -1483,8 +1485,9 @@ __device__ __forceinline__ void xchg_publish_last(int *xcount, int *done, XFace 
   }
 }
 
-__global__ void __launch_bounds__(128) k_halo_send2(View V, Params P, int cap_xy, int idx_bytes, XFace f0, XFace f1, int mask, int *xcount, int *done, int seq) {
+__global__ void __launch_bounds__(128) k_halo_send2(View V, Params P, int cap_xy, int idx_bytes, XFace f0, XFace f1, int mask, int *xcount, int *done) {
   __shared__ int s_idx[2];
+  const int seq = V.cnt->xstep + 1;  // this substep's halo
   const int n_tiles = V.cnt->n_tiles;
   for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
     const int tile = V.meta[slot].tile, lz = tile % P.nt[2];
@@ -1513,8 +1516,9 @@ __global__ void __launch_bounds__(128) k_halo_send2(View V, Params P, int cap_xy
   xchg_publish_last(xcount, done, f0, f1, mask, seq);
 }
 
-__global__ void __launch_bounds__(128) k_halo_recv2(View V, Params P, int cap_xy, int idx_bytes, XFace f0, XFace f1, int mask, int seq) {
+__global__ void __launch_bounds__(128) k_halo_recv2(View V, Params P, int cap_xy, int idx_bytes, XFace f0, XFace f1, int mask) {
   __shared__ int s_slot;
+  const int seq = V.cnt->xstep + 1;
   if (threadIdx.x == 0) {
     if (mask & 1) xchg_spin((const int *)f0.rx, seq, V.cnt);
     if (mask & 2) xchg_spin((const int *)f1.rx, seq, V.cnt);
@@ -1541,8 +1545,9 @@ __global__ void __launch_bounds__(128) k_halo_recv2(View V, Params P, int cap_xy
   }
 }
 
-__global__ void __launch_bounds__(256) k_migrate_send2(View V, uint32_t key_dead, int cap, XFace f0, XFace f1, int mask, int *xcount, int *done, int seq) {
+__global__ void __launch_bounds__(256) k_migrate_send2(View V, uint32_t key_dead, int cap, XFace f0, XFace f1, int mask, int *xcount, int *done) {
   const int n = V.cnt->n_movers;
+  const int seq = V.cnt->xstep;  // k_g2p has committed this substep
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
     const uint32_t d = V.mover_dst[m];
     const int f = ((mask & 1) && d == f0.key) ? 0 : (((mask & 2) && d == f1.key) ? 1 : -1);
@@ -1561,8 +1566,9 @@ __global__ void __launch_bounds__(256) k_migrate_send2(View V, uint32_t key_dead
 
 // one CTA: waits for both neighbours, appends the immigrants of both faces after the last storage row, enters them in the
 // mover list and commits the counts
-__global__ void __launch_bounds__(1024) k_migrate_recv2(View V, Params P, int cap, XFace f0, XFace f1, int mask, int seq) {
+__global__ void __launch_bounds__(1024) k_migrate_recv2(View V, Params P, int cap, XFace f0, XFace f1, int mask) {
   __shared__ int s_n[2];
+  const int seq = V.cnt->xstep;
   if (threadIdx.x == 0) {
     if (mask & 1) xchg_spin((const int *)f0.rx, seq, V.cnt);
     if (mask & 2) xchg_spin((const int *)f1.rx, seq, V.cnt);
@@ -1668,6 +1674,13 @@ struct MpmbEngine {
   int grid_p2g = 148 * 4, grid_g2p = 148 * 4;  // persistent grids = SMs x resident CTAs (queried)
   int64_t launches = 0;
 
+  // two substeps captured as one CUDA graph per buffer parity: mpmb_substep replays it instead of re-launching
+  // 16 (1 GPU) / 24 (z-slab rank) kernels from the host; invalidated by anything that changes a kernel argument
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  int graph_launches = 0;
+  cudaStream_t cap_stream = nullptr;
+  bool use_graph = true;
+
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int stage; };
   std::vector<Ev> events;
@@ -1705,6 +1718,11 @@ static int fail(MpmbEngine *h, int code, const char *fmt, ...) {
     cudaError_t e0_ = cudaSetDevice((h)->cfg.device);                         \
     if (e0_ != cudaSuccess) return fail((h), MPMB_ERR_CUDA, "cudaSetDevice"); \
   } while (0)
+
+static void graph_reset(MpmbEngine *h) {
+  for (int p = 0; p < 2; p++)
+    if (h->graph_exec[p]) { cudaGraphExecDestroy(h->graph_exec[p]); h->graph_exec[p] = nullptr; }
+}
 
 static View make_view(MpmbEngine *h) {
   View V{};
@@ -1770,6 +1788,7 @@ static void prof_collect(MpmbEngine *h) {
 }
 
 static int free_particles(MpmbEngine *h) {
+  graph_reset(h);
   for (int b = 0; b < 2; b++) {
     for (int k = 0; k < N_Q; k++) { cudaFree(h->q[b][k]); h->q[b][k] = nullptr; }
     cudaFree(h->keys[b]); h->keys[b] = nullptr;
@@ -1864,6 +1883,7 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
     P.mats[g].p[0] = 1e5f / (2.f * 1.3f);
     P.mats[g].p[1] = 1e5f * 0.3f / (1.3f * 0.4f);
   }
+  if (const char *g = getenv("MPMB_GRAPH")) h->use_graph = g[0] != '0';   // MPMB_GRAPH=0: launch every kernel from the host (A/B, debugging)
   h->special_min = (uint32_t)ntot;
   h->key_dead = (uint32_t)ntot + SPECIAL_DEAD;
   h->key_bits = 1;
@@ -1940,6 +1960,8 @@ int mpmb_destroy(MpmbHandle h) {
       cudaFree(h->rx[k][f]);
     }
   for (auto &e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  graph_reset(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
 
   delete h;
   return MPMB_OK;
@@ -1971,6 +1993,7 @@ int mpmb_set_material(MpmbHandle h, int32_t group, int32_t kind, const float *pa
   if (n_params < 0 || n_params > MPMB_MAT_PARAMS || (n_params > 0 && !params)) return fail(h, MPMB_ERR_INVALID, "bad parameter vector");
   h->P.mats[group].kind = kind;
   for (int k = 0; k < 8; k++) h->P.mats[group].p[k] = k < n_params ? params[k] : 0.f;
+  graph_reset(h);
   // particles of this group already resident: their cached affine matrix belongs to the old material
   if (h->cap > 0 && h->stage == 0) {
     int ns = 0;
@@ -1998,6 +2021,7 @@ int mpmb_set_sdf(MpmbHandle h, const float *sdf4, float friction) {
   size_t n = (size_t)h->P.nnode[0] * h->P.nnode[1] * h->P.nnode[2];
   if (!sdf4) {
     h->P.has_sdf = 0;
+    graph_reset(h);
     return MPMB_OK;
   }
   if (!h->sdf4) CUDA_TRY(h, cudaMalloc(&h->sdf4, sizeof(float4) * n));
@@ -2005,6 +2029,7 @@ int mpmb_set_sdf(MpmbHandle h, const float *sdf4, float friction) {
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->P.has_sdf = 1;
   h->P.friction = friction;
+  graph_reset(h);
   return MPMB_OK;
 }
 
@@ -2022,6 +2047,7 @@ int mpmb_set_planes(MpmbHandle h, int32_t n_planes, const float *planes4, float 
   cudaFree(d_planes);
   h->P.has_sdf = 1;
   h->P.friction = friction;
+  graph_reset(h);
   return MPMB_OK;
 }
 
@@ -2042,6 +2068,7 @@ int mpmb_set_levelset_shapes(MpmbHandle h, int32_t n_shapes, const MpmbShape *sh
   CUDA_TRY(h, e);
   h->P.has_sdf = 1;
   h->P.friction = friction;
+  graph_reset(h);
   return MPMB_OK;
 }
 
@@ -2564,27 +2591,80 @@ int mpmb_resample_part(MpmbHandle h, int32_t part) {
   return MPMB_OK;
 }
 
+// one substep; skip_b: do not store apic_b (an intermediate substep of mpmb_substep)
+static int substep_once(MpmbEngine *h, bool peers, bool skip_b) {
+  int rc;
+  if ((rc = mpmb_sort_particles_and_populate_grid(h)) != MPMB_OK) return rc;
+  if ((rc = mpmb_rasterize(h)) != MPMB_OK) return rc;
+  if (peers && (rc = xchg_halo_fused(h)) != MPMB_OK) return rc;  // boundary-layer arenas into the neighbours' memory, theirs in as ghosts
+  h->skip_b = skip_b;
+#ifdef MPMB_CHECKED
+  { static const char *dbg = getenv("MPMB_DBG_SKIPB"); if (dbg) h->skip_b = dbg[0] == '1'; }   // debug: force one k_g2p instantiation
+#endif
+  rc = mpmb_resample(h);
+  h->skip_b = false;
+  if (rc != MPMB_OK) return rc;
+  if (peers && (rc = xchg_migrate_fused(h)) != MPMB_OK) return rc;
+  return MPMB_OK;
+}
+
+// Captures two substeps (both buffer parities) into a graph for the parity the engine is in, and leaves the engine's
+// host-side state as if they had run; the caller launches the graph.  Any failure turns graphs off for this handle.
+static int graph_capture_pair(MpmbEngine *h, bool peers) {
+  const int par = h->cur;
+  if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { h->use_graph = false; cudaGetLastError(); return MPMB_OK; }
+  cudaStream_t user = h->stream;
+  const int64_t l0 = h->launches;
+  const int cur0 = h->cur, ord0 = h->ord, mov0 = h->mov, x0 = h->xstep;
+  h->stream = h->cap_stream;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
+  int rc = MPMB_OK;
+  if (e == cudaSuccess) {
+    rc = substep_once(h, peers, true);
+    if (rc == MPMB_OK) rc = substep_once(h, peers, true);
+    e = cudaStreamEndCapture(h->cap_stream, &g);
+  }
+  h->stream = user;
+  if (e == cudaSuccess && rc == MPMB_OK && g) e = cudaGraphInstantiate(&h->graph_exec[par], g, 0);
+  if (g) cudaGraphDestroy(g);
+  if (e != cudaSuccess || rc != MPMB_OK || !h->graph_exec[par]) {
+    cudaGetLastError();
+    h->graph_exec[par] = nullptr;
+    h->use_graph = false;
+    h->cur = cur0; h->ord = ord0; h->mov = mov0; h->xstep = x0; h->stage = 0; h->launches = l0;   // nothing has run
+    h->sticky_cuda = false;
+    return MPMB_OK;
+  }
+  h->graph_launches = (int)(h->launches - l0);
+  h->cur = cur0; h->ord = ord0; h->mov = mov0; h->xstep = x0; h->launches = l0;   // the caller's launch accounts for them
+  return MPMB_OK;
+}
+
 int mpmb_substep(MpmbHandle h, int32_t nsub) {
   CHECK_HANDLE(h);
   const bool peers = peers_connected(h);
   if (h->cfg.world > 1 && !peers) return fail(h, MPMB_ERR_STATE, "z-slab run: connect the peers (mpmb_xchg_connect) or drive the stages and move the buffers yourself");
-  for (int s = 0; s < nsub; s++) {
-    int rc;
-    if ((rc = mpmb_sort_particles_and_populate_grid(h)) != MPMB_OK) return rc;
-    if ((rc = mpmb_rasterize(h)) != MPMB_OK) return rc;
-    if (peers && (rc = xchg_halo_fused(h)) != MPMB_OK) return rc;  // boundary-layer arenas into the neighbours' memory, theirs in as ghosts
-    // apic_b only has to exist when control returns to the host: no kernel reads it (rasterize uses the affine matrix), so
-    // the intermediate substeps skip its three streams — on z-slab ranks too: an emigrant's record then carries stale
-    // apic_b words, which the receiving rank's own next G2P overwrites before anybody can look at them
-    h->skip_b = (s + 1 < nsub);
-#ifdef MPMB_CHECKED
-    { static const char *dbg = getenv("MPMB_DBG_SKIPB"); if (dbg) h->skip_b = dbg[0] == '1'; }   // debug: force one k_g2p instantiation
-#endif
-    rc = mpmb_resample(h);
-    h->skip_b = false;
-    if (rc != MPMB_OK) return rc;
-    if (peers && (rc = xchg_migrate_fused(h)) != MPMB_OK) return rc;
+  int s = 0, rc;
+  // the first substep after an upload takes the radix-sorted arrival lists (a different ordering launch): never in a graph
+  if (h->fresh && nsub > 0) {
+    if ((rc = substep_once(h, peers, nsub > 1)) != MPMB_OK) return rc;
+    s = 1;
   }
+  // pairs of intermediate substeps through the captured graph; the last substep (it stores apic_b) always runs directly
+  while (h->use_graph && !h->profiling && h->cap > 0 && h->stage == 0 && nsub - s >= 3) {
+    const int par = h->cur;
+    if (!h->graph_exec[par]) {
+      if ((rc = graph_capture_pair(h, peers)) != MPMB_OK) return rc;
+      if (!h->graph_exec[par]) break;
+    }
+    CUDA_TRY(h, cudaGraphLaunch(h->graph_exec[par], h->stream));
+    h->launches += h->graph_launches;
+    h->xstep += 2;   // cur / ord / mov flip twice: unchanged
+    s += 2;
+  }
+  for (; s < nsub; s++)
+    if ((rc = substep_once(h, peers, s + 1 < nsub)) != MPMB_OK) return rc;
   return MPMB_OK;
 }
 
@@ -2811,7 +2891,9 @@ int mpmb_xchg_connect(MpmbHandle h, int32_t kind, int32_t face, const void *hand
   // a (re)connection restarts the sequence: my own receive headers of this kind must not hold an old, larger seq
   for (int f = 0; f < 2; f++)
     if (h->rx[kind][f]) CUDA_TRY(h, cudaMemset(h->rx[kind][f], 0, 16));
+  CUDA_TRY(h, cudaMemset(&h->cnt->xstep, 0, sizeof(int)));
   h->xstep = 0;
+  graph_reset(h);
   return MPMB_OK;
 }
 
@@ -2849,11 +2931,11 @@ static int xchg_halo_launch(MpmbEngine *h, int mask_send, int mask_recv) {
   int nl = 0;
   if (mask_send & mask) {
     k_halo_send2<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, (int)halo_cap_xy(h), (int)halo_idx_bytes(h), s[0], s[1], mask_send & mask, h->xcount,
-                                                         h->xcount + 16, h->xstep + 1);
+                                                         h->xcount + 16);
     nl++;
   }
   if (mask_recv & mask) {
-    k_halo_recv2<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, (int)halo_cap_xy(h), (int)halo_idx_bytes(h), r[0], r[1], mask_recv & mask, h->xstep + 1);
+    k_halo_recv2<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, (int)halo_cap_xy(h), (int)halo_idx_bytes(h), r[0], r[1], mask_recv & mask);
     nl++;
   }
   h->launches += nl;
@@ -2870,12 +2952,11 @@ static int xchg_migrate_launch(MpmbEngine *h, int mask_send, int mask_recv) {
   View V = make_view(h);
   int nl = 0;
   if (mask_send & mask) {
-    k_migrate_send2<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->key_dead, (int)h->mig_cap, f[0], f[1], mask_send & mask, h->xcount + 8, h->xcount + 20,
-                                                           h->xstep);
+    k_migrate_send2<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->key_dead, (int)h->mig_cap, f[0], f[1], mask_send & mask, h->xcount + 8, h->xcount + 20);
     nl++;
   }
   if (mask_recv & mask) {
-    k_migrate_recv2<<<1, 1024, 0, h->stream>>>(V, h->P, (int)h->mig_cap, f[0], f[1], mask_recv & mask, h->xstep);
+    k_migrate_recv2<<<1, 1024, 0, h->stream>>>(V, h->P, (int)h->mig_cap, f[0], f[1], mask_recv & mask);
     nl++;
   }
   h->launches += nl;
