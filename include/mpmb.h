@@ -75,7 +75,9 @@ typedef struct MpmbConfig {
   int32_t tile_z0, tile_z1;
   int64_t migrate_capacity;  /* max particles leaving through one face per substep (world>1)      */
   int32_t halo_capacity;     /* max active tiles in one boundary layer; 0 = the whole cross-section */
-  int32_t reserved[7];       /* must be 0                                                         */
+  int32_t no_graph;          /* 1: launch every kernel from the host; 0 (default): mpmb_substep replays pairs of
+                              * substeps as a CUDA graph (same kernels, same order, same results)              */
+  int32_t reserved[6];       /* must be 0                                                         */
 } MpmbConfig;
 
 /* Byte offsets of the fields of one reference particle slot (ParticleContainer<3>, 320 B,

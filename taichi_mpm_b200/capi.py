@@ -46,7 +46,8 @@ class MpmbConfig(C.Structure):
         ("tile_z1", C.c_int32),
         ("migrate_capacity", C.c_int64),
         ("halo_capacity", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("no_graph", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -118,7 +119,7 @@ class Engine:
     """Thin object wrapper over one MpmbHandle."""
 
     def __init__(self, res, dx, dt, gravity=(0.0, -10.0, 0.0), particle_gravity=True, clean_boundary=True, device=0,
-                 capacity=0, rank=0, world=1, tile_z0=0, tile_z1=0, migrate_capacity=0, halo_capacity=0):
+                 capacity=0, rank=0, world=1, tile_z0=0, tile_z1=0, migrate_capacity=0, halo_capacity=0, no_graph=False):
         self.L = lib()
         cfg = MpmbConfig()
         if np.isscalar(res):
@@ -133,6 +134,7 @@ class Engine:
         cfg.rank, cfg.world, cfg.tile_z0, cfg.tile_z1 = int(rank), int(world), int(tile_z0), int(tile_z1)
         cfg.migrate_capacity = int(migrate_capacity)
         cfg.halo_capacity = int(halo_capacity)
+        cfg.no_graph = int(bool(no_graph))
         self.res = tuple(int(r) for r in res)
         self.cfg = cfg
         self.h = C.c_void_p()

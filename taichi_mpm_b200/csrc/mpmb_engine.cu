@@ -1883,6 +1883,7 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
     P.mats[g].p[0] = 1e5f / (2.f * 1.3f);
     P.mats[g].p[1] = 1e5f * 0.3f / (1.3f * 0.4f);
   }
+  h->use_graph = cfg->no_graph == 0;
   if (const char *g = getenv("MPMB_GRAPH")) h->use_graph = g[0] != '0';   // MPMB_GRAPH=0: launch every kernel from the host (A/B, debugging)
   h->special_min = (uint32_t)ntot;
   h->key_dead = (uint32_t)ntot + SPECIAL_DEAD;

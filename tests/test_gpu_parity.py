@@ -15,7 +15,7 @@ KINDS = [("linear", scenes.MAT_LINEAR), ("jelly", scenes.MAT_JELLY), ("snow", sc
 def _assert_parity(err):
     assert err["alive_match"]
     assert err["grid_rast"] <= T.TOL_GRID_REL, err
-    assert err["grid_vel"] <= 5 * T.TOL_GRID_REL, err   # v = p/m amplifies the relative error of tiny masses
+    assert err["grid_vel"] <= T.TOL_GRID_REL, err       # node velocities after normalise + boundary: same 2e-5 bound (measured 1e-6..5e-6 on a B200)
     assert err["grid_mass_outside"] == 0.0, err
     assert err["x"] <= T.TOL_X_ABS, err
     assert err["v"] <= T.TOL_V_REL, err
@@ -351,3 +351,28 @@ def test_multi_step_other_materials(name, kind):
     assert np.abs(got["x"] - fast.st["x"][ids]).max() < 1e-4
     assert np.isfinite(got["F"]).all()
     e.close()
+
+
+def test_graph_replay_is_bit_identical_to_host_launches_and_follows_state_changes():
+    """mpmb_substep replays pairs of substeps as a CUDA graph (captured per buffer parity).  Same kernels in the same
+    order: results must be bit-identical to launching every kernel from the host, across odd/even call lengths, a
+    material change, a level-set change and a re-upload (each of which must invalidate the captured graphs)."""
+    scene, st = T.perturbed_scene(scenes.MAT_SAND, res=32, cells=8, seed=41, vel=1.5)
+    out = []
+    for no_graph in (False, True):
+        e = T.make_engine(scene, st, no_graph=no_graph)
+        e.substep(9)                                           # fresh + pairs + last
+        e.substep(4)
+        e.set_material(0, scenes.MAT_SAND, scenes.material_params(scenes.MAT_SAND, friction_angle=40.0))
+        e.substep(7)
+        e.set_planes(np.array([[0.0, 1.0, 0.0, -9.9]], np.float32), 0.2)
+        e.substep(6)
+        a = e.download()
+        e.upload(st["x"], st["v"], st["mass"], st["vol"], st["F"], st["b"], st["ps"], st["group"])   # same capacity: no realloc
+        e.substep(8)
+        b = e.download()
+        out.append((a, b))
+        e.close()
+    for k in ("id", "x", "v", "F", "ps", "b"):
+        assert np.array_equal(out[0][0][k], out[1][0][k]), k
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
