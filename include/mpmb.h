@@ -43,20 +43,28 @@ typedef enum MpmbStatus {
 } MpmbStatus;
 
 /* Material kinds = the registered particle type names of the reference
- * (TC_REGISTER_MPM_PARTICLE, src/particles.cpp:845-856).  Parameter vectors (unused entries 0):
+ * (TC_REGISTER_MPM_PARTICLE, src/particles.cpp:845-856; all eight deformable types).  Parameter vectors (unused entries 0):
  *   LINEAR  "linear" (src/particles.cpp:297-363): [0]=mu [1]=lambda
  *   JELLY   "jelly"  (src/particles.cpp:365-438): [0]=mu [1]=lambda
  *   SNOW    "snow"   (src/particles.cpp:165-295): [0]=mu_0 [1]=lambda_0 [2]=hardening [3]=theta_c
  *                                                  [4]=theta_s [5]=min_Jp [6]=max_Jp ; scalar = Jp
  *   WATER   "water"  (src/particles.cpp:440-499): [0]=k [1]=gamma ; scalar = j
  *   SAND    "sand"   (src/particles.cpp:563-676): [0]=mu_0 [1]=lambda_0 [2]=alpha [3]=cohesion
- *                                                  [4]=beta ; scalar = logJp                      */
+ *                                                  [4]=beta ; scalar = logJp
+ *   ELASTIC "elastic" (src/particles.cpp:764-841): [0]=mu_0 [1]=lambda_0   (Hencky, no return map)
+ *   VON_MISES "von_mises" (src/particles.cpp:679-761): [0]=mu_0 [1]=lambda_0 [2]=yield_stress
+ *   VISCO   "visco"  (src/particles.cpp:40-163): [0]=mu_0 [1]=lambda_0 [2]=visco_nu [3]=visco_kappa
+ *                                                  [4]=dt (the particle's own `base_delta_t` key, default 1e-4,
+ *                                                  src/particles.cpp:66) ; scalar = visco_tau              */
 typedef enum MpmbMaterial {
   MPMB_MAT_LINEAR = 0,
   MPMB_MAT_JELLY = 1,
   MPMB_MAT_SNOW = 2,
   MPMB_MAT_WATER = 3,
-  MPMB_MAT_SAND = 4
+  MPMB_MAT_SAND = 4,
+  MPMB_MAT_ELASTIC = 5,
+  MPMB_MAT_VON_MISES = 6,
+  MPMB_MAT_VISCO = 7
 } MpmbMaterial;
 
 /* Mirrors the keys MPM<dim>::initialize reads from its Config (src/mpm.cpp:27-75). */

@@ -47,13 +47,17 @@
 
 namespace {
 
-enum MaterialKind { MAT_LINEAR = 0, MAT_JELLY = 1, MAT_SNOW = 2, MAT_WATER = 3, MAT_SAND = 4 };
+enum MaterialKind { MAT_LINEAR = 0, MAT_JELLY = 1, MAT_SNOW = 2, MAT_WATER = 3, MAT_SAND = 4, MAT_ELASTIC = 5, MAT_VON_MISES = 6, MAT_VISCO = 7 };
 constexpr int kMatParams = 8;
 // params layout (all kinds, unused = 0):
 //  LINEAR/JELLY: [0]=mu [1]=lambda
 //  SNOW        : [0]=mu_0 [1]=lambda_0 [2]=hardening [3]=theta_c [4]=theta_s [5]=min_Jp [6]=max_Jp
 //  WATER       : [0]=k [1]=gamma
 //  SAND        : [0]=mu_0 [1]=lambda_0 [2]=alpha [3]=cohesion [4]=beta
+//  ELASTIC     : [0]=mu_0 [1]=lambda_0                                  (src/particles.cpp:764-841)
+//  VON_MISES   : [0]=mu_0 [1]=lambda_0 [2]=yield_stress                 (src/particles.cpp:679-761)
+//  VISCO       : [0]=mu_0 [1]=lambda_0 [2]=visco_nu [3]=visco_kappa [4]=dt (the particle's own copy of base_delta_t,
+//                src/particles.cpp:66) ; scalar = visco_tau             (src/particles.cpp:40-163)
 
 // ---------------------------------------------------------------- small 3x3 algebra
 template <class R> inline R &at(R *m, int r, int c) { return m[c * 3 + r]; }
@@ -335,7 +339,16 @@ template <class R> void calculate_force(int kind, const R *prm, const R *F, R ps
       for (int d = 0; d < 3; d++) at(out, d, d) = -vol * j * (-p);
       return;
     }
-    case MAT_SAND: {  // src/particles.cpp:628-637
+    case MAT_VISCO: {  // src/particles.cpp:69-82: fixed corotated with the constant mu_0, lambda_0
+      first_piola_fixed_corotated(F, prm[0], prm[1], P);
+      mat_transpose(F, Ft);
+      mat_mul(P, Ft, PFt);
+      for (int i = 0; i < 9; i++) out[i] = -vol * PFt[i];
+      return;
+    }
+    case MAT_ELASTIC:    // src/particles.cpp:800-809  (the same Hencky stress, word for word)
+    case MAT_VON_MISES:  // src/particles.cpp:703-712
+    case MAT_SAND: {     // src/particles.cpp:628-637
       R mu0 = prm[0], lambda0 = prm[1];
       R U[9], s[3], V[9];
       svd3(F, U, s, V);
@@ -384,15 +397,72 @@ template <class R> void sand_project(const R *prm, const R *sigma, R &logJp, R *
   }
 }
 
+// ViscoParticle::approximate_exponent (src/particles.cpp:89-102): r = (s/2 + I) s + I with s = m dt; if det r <= 0
+// the step is halved and the result squared.
+template <class R> void visco_approximate_exponent(R dt, const R *m, R *out, int depth = 0) {
+  R s[9], h[9], r[9];
+  for (int i = 0; i < 9; i++) { s[i] = m[i] * dt; h[i] = s[i] * R(0.5); }
+  for (int d = 0; d < 3; d++) at(h, d, d) += R(1);
+  mat_mul(h, s, r);
+  for (int d = 0; d < 3; d++) at(r, d, d) += R(1);
+  if (mat_det(r) > R(0) || depth >= 16) {
+    std::memcpy(out, r, sizeof(r));
+    return;
+  }
+  R tmp[9];
+  visco_approximate_exponent(dt / R(2), m, tmp, depth + 1);
+  mat_mul(tmp, tmp, out);
+}
+
+// ViscoParticle::plasticity (src/particles.cpp:104-137).  ps = visco_tau.
+template <class R> void visco_plasticity(const R *prm, const R *cdg, R *F, R &ps) {
+  const R mu0 = prm[0], lambda0 = prm[1], nu = prm[2], kappa = prm[3], dt = prm[4];
+  R m[9], ex[9], Fh[9];
+  for (int i = 0; i < 9; i++) m[i] = cdg[i];
+  for (int d = 0; d < 3; d++) at(m, d, d) -= R(1);
+  for (int i = 0; i < 9; i++) m[i] *= (R(1) / dt);
+  visco_approximate_exponent(dt, m, ex);
+  mat_mul(ex, F, Fh);
+  R U[9], sg[3], V[9], Vt[9];
+  svd3(Fh, U, sg, V);
+  mat_transpose(V, Vt);
+  R P[9], pn2 = 0;
+  first_piola_fixed_corotated(F, mu0, lambda0, P);  // of the OLD dg_e (111: this->dg_e is not yet updated)
+  for (int i = 0; i < 9; i++) pn2 += P[i] * P[i];
+  const R pnorm = std::sqrt(pn2);
+  R gamma = 0;
+  if (pnorm > R(1e-5)) gamma = std::min(std::max(dt * nu * (pnorm - ps) / pnorm, R(0)), R(1));
+  const R det = sg[0] * sg[1] * sg[2];
+  R scale = 1;
+  if (std::abs(det) > R(1e-5)) scale = R(1) / std::pow(det, R(1) / R(3));
+  R snew[3];
+  for (int d = 0; d < 3; d++) {
+    const R mid = std::pow(sg[d] * scale, gamma);
+    const R mid_inv = std::abs(mid) > R(1e-5) ? R(1) / mid : R(1);
+    snew[d] = sg[d] * mid_inv;
+  }
+  // the second svd (127-130) of U diag(snew) V^T returns the same factors: clamp the singular values in place
+  for (int d = 0; d < 3; d++) snew[d] = std::min(std::max(snew[d], R(0.1)), R(10));
+  R US[9];
+  for (int c = 0; c < 3; c++)
+    for (int r = 0; r < 3; r++) at(US, r, c) = at(U, r, c) * snew[c];
+  mat_mul(US, Vt, F);
+  ps += kappa * gamma * pnorm;
+}
+
 template <class R> void plasticity(int kind, const R *prm, const R *cdg, R *F, R &ps) {
   if (kind == MAT_WATER) {  // src/particles.cpp:469-478: j *= tr(cdg) - (dim-1); floor 0.1
     ps *= (at(cdg, 0, 0) + at(cdg, 1, 1) + at(cdg, 2, 2)) - R(2);
     if (ps < R(0.1)) ps = R(0.1);
     return;
   }
+  if (kind == MAT_VISCO) {
+    visco_plasticity(prm, cdg, F, ps);
+    return;
+  }
   R Fn[9];
-  mat_mul(cdg, F, Fn);  // dg_e = cdg * dg_e (src/particles.cpp:223,342,414,640)
-  if (kind == MAT_LINEAR || kind == MAT_JELLY) {
+  mat_mul(cdg, F, Fn);  // dg_e = cdg * dg_e (src/particles.cpp:223,342,414,640,715,812)
+  if (kind == MAT_LINEAR || kind == MAT_JELLY || kind == MAT_ELASTIC) {
     std::memcpy(F, Fn, sizeof(Fn));
     return;
   }
@@ -400,7 +470,20 @@ template <class R> void plasticity(int kind, const R *prm, const R *cdg, R *F, R
   svd3(Fn, U, s, V);
   mat_transpose(V, Vt);
   R snew[3];
-  if (kind == MAT_SNOW) {  // src/particles.cpp:222-242
+  if (kind == MAT_VON_MISES) {  // src/particles.cpp:714-734
+    R mu0 = prm[0], yield_stress = prm[2];
+    R eps[3], tr = 0;
+    for (int i = 0; i < 3; i++) { eps[i] = std::log(s[i]); tr += eps[i]; }
+    R hat[3], n2 = 0;
+    for (int i = 0; i < 3; i++) { hat[i] = eps[i] - tr / R(3); n2 += hat[i] * hat[i]; }
+    // NB `epsilon_hat.frobenius_norm2()` (724): the SQUARED Frobenius norm enters both the yield test and the scaling
+    R dgamma = n2 - yield_stress / (R(2) * mu0);
+    if (dgamma <= 0) {  // case I: dg_e = cdg * dg_e is kept as it is (no rebuild from the factors)
+      std::memcpy(F, Fn, sizeof(Fn));
+      return;
+    }
+    for (int i = 0; i < 3; i++) snew[i] = std::exp(eps[i] - (dgamma / n2) * hat[i]);
+  } else if (kind == MAT_SNOW) {  // src/particles.cpp:222-242
     R theta_c = prm[3], theta_s = prm[4], minJp = prm[5], maxJp = prm[6];
     R det_orig = 1, det_new = 1;
     for (int i = 0; i < 3; i++) {

@@ -79,6 +79,31 @@ int ref_particle(int kind, const float *params, const float *cdg, float *F, floa
       *ps = p.logJp;
       return 0;
     }
+    case 5: {  // elastic (src/particles.cpp:764-841): E, nu enter through mu_0, lambda_0 (775-781)
+      ElasticParticle<3> p;
+      p.initialize(cfg);
+      p.mu_0 = params[0]; p.lambda_0 = params[1];
+      run(p, cdg, F, vol, force, do_plasticity);
+      return 0;
+    }
+    case 6: {  // von_mises (src/particles.cpp:679-761)
+      VonMisesParticle<3> p;
+      cfg.set("yield_stress", params[2]);
+      p.initialize(cfg);
+      p.mu_0 = params[0]; p.lambda_0 = params[1];
+      run(p, cdg, F, vol, force, do_plasticity);
+      return 0;
+    }
+    case 7: {  // visco (src/particles.cpp:40-163); scalar = visco_tau
+      ViscoParticle<3> p;
+      cfg.set("nu", params[2]).set("kappa", params[3]).set("base_delta_t", params[4]);
+      p.initialize(cfg);
+      p.mu_0 = params[0]; p.lambda_0 = params[1];
+      p.visco_tau = *ps;
+      run(p, cdg, F, vol, force, do_plasticity);
+      *ps = p.visco_tau;
+      return 0;
+    }
   }
   return -1;
 }
@@ -102,6 +127,9 @@ int ref_default_params(int kind, float *out) {
     case 2: { SnowParticle<3> p; p.initialize(cfg); out[0] = p.mu_0; out[1] = p.lambda_0; out[2] = p.hardening; out[3] = p.theta_c; out[4] = p.theta_s; out[5] = p.min_Jp; out[6] = p.max_Jp; return 0; }
     case 3: { WaterParticle<3> p; p.initialize(cfg); out[0] = p.k; out[1] = p.gamma; return 0; }
     case 4: { SandParticle<3> p; p.initialize(cfg); out[0] = p.mu_0; out[1] = p.lambda_0; out[2] = p.alpha; out[3] = p.cohesion; out[4] = p.beta; return 0; }
+    case 5: { ElasticParticle<3> p; p.initialize(cfg); out[0] = p.mu_0; out[1] = p.lambda_0; return 0; }
+    case 6: { VonMisesParticle<3> p; p.initialize(cfg); out[0] = p.mu_0; out[1] = p.lambda_0; out[2] = p.yield_stress; return 0; }
+    case 7: { ViscoParticle<3> p; p.initialize(cfg); out[0] = p.mu_0; out[1] = p.lambda_0; out[2] = p.visco_nu; out[3] = p.visco_kappa; out[4] = p.dt; return 0; }
   }
   return -1;
 }

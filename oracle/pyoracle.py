@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND = range(5)
+MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND, MAT_ELASTIC, MAT_VON_MISES, MAT_VISCO = range(8)
 N_MAT_PARAMS = 8
 
 

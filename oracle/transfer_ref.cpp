@@ -178,8 +178,8 @@ int64_t reft_add_particles(void *hp, int kind, const float *params, int64_t n, c
 int reft_add_particle(void *hp, int kind, const float *params, const float *x, const float *v, float mass, float vol, const float *F,
                       const float *b, float ps) {
   Harness *h = static_cast<Harness *>(hp);
-  static const char *names[5] = {"linear", "jelly", "snow", "water", "sand"};
-  if (kind < 0 || kind > 4) return -1;
+  static const char *names[8] = {"linear", "jelly", "snow", "water", "sand", "elastic", "von_mises", "visco"};
+  if (kind < 0 || kind > 7) return -1;
   auto alloc = h->m.allocator.allocate_particle(names[kind]);
   MPMParticle<3> *p = alloc.second;
   Config cfg;
@@ -197,6 +197,19 @@ int reft_add_particle(void *hp, int kind, const float *params, const float *x, c
       p->initialize(cfg);
       static_cast<SandParticle<3> *>(p)->alpha = params[2];
       static_cast<SandParticle<3> *>(p)->logJp = ps;
+      break;
+    case 5: p->initialize(cfg); static_cast<ElasticParticle<3> *>(p)->mu_0 = params[0]; static_cast<ElasticParticle<3> *>(p)->lambda_0 = params[1]; break;
+    case 6:
+      cfg.set("yield_stress", params[2]);
+      p->initialize(cfg);
+      static_cast<VonMisesParticle<3> *>(p)->mu_0 = params[0];
+      static_cast<VonMisesParticle<3> *>(p)->lambda_0 = params[1];
+      break;
+    case 7:
+      cfg.set("nu", params[2]).set("kappa", params[3]).set("base_delta_t", params[4]).set("tau", ps);
+      p->initialize(cfg);
+      static_cast<ViscoParticle<3> *>(p)->mu_0 = params[0];
+      static_cast<ViscoParticle<3> *>(p)->lambda_0 = params[1];
       break;
   }
   p->pos = VectorND<3, real>(x[0], x[1], x[2]);
@@ -366,6 +379,10 @@ int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, 
     case 3: { auto *q = static_cast<WaterParticle<3> *>(p0); prm[0] = q->k; prm[1] = q->gamma; L.off_scalar = (int32_t)offsetof(WaterParticle<3>, j); break; }
     case 4: { auto *q = static_cast<SandParticle<3> *>(p0); prm[0] = q->mu_0; prm[1] = q->lambda_0; prm[2] = q->alpha; prm[3] = q->cohesion; prm[4] = q->beta;
               L.off_scalar = (int32_t)offsetof(SandParticle<3>, logJp); break; }
+    case 5: prm[0] = static_cast<ElasticParticle<3> *>(p0)->mu_0; prm[1] = static_cast<ElasticParticle<3> *>(p0)->lambda_0; break;
+    case 6: { auto *q = static_cast<VonMisesParticle<3> *>(p0); prm[0] = q->mu_0; prm[1] = q->lambda_0; prm[2] = q->yield_stress; break; }
+    case 7: { auto *q = static_cast<ViscoParticle<3> *>(p0); prm[0] = q->mu_0; prm[1] = q->lambda_0; prm[2] = q->visco_nu; prm[3] = q->visco_kappa; prm[4] = q->dt;
+              L.off_scalar = (int32_t)offsetof(ViscoParticle<3>, visco_tau); break; }
     default: mpmb_destroy_(e); return fail("unknown particle type", -103);
   }
   int rc = mpmb_set_material_(e, 0, kind, prm, 8);
@@ -398,7 +415,7 @@ void reft_aos_layout(int kind, int32_t *out) {
   out[5] = (int32_t)sizeof(VectorND<3, real>);
   out[6] = (int32_t)offsetof(P3, vol);
   out[7] = kind == 2 ? (int32_t)offsetof(SnowParticle<3>, Jp) : kind == 3 ? (int32_t)offsetof(WaterParticle<3>, j)
-           : kind == 4 ? (int32_t)offsetof(SandParticle<3>, logJp) : -1;
+           : kind == 4 ? (int32_t)offsetof(SandParticle<3>, logJp) : kind == 7 ? (int32_t)offsetof(ViscoParticle<3>, visco_tau) : -1;
 }
 
 // MPM<3>::step(dt) itself (src/mpm.cpp:428-450): `real` = float clocks decide how many substeps a frame runs
@@ -428,6 +445,7 @@ void reft_get_particles(void *hp, float *x, float *v, float *F, float *b, float 
       case 2: ps[id] = static_cast<SnowParticle<3> *>(p)->Jp; break;
       case 3: ps[id] = static_cast<WaterParticle<3> *>(p)->j; break;
       case 4: ps[id] = static_cast<SandParticle<3> *>(p)->logJp; break;
+      case 7: ps[id] = static_cast<ViscoParticle<3> *>(p)->visco_tau; break;
       default: ps[id] = 0;
     }
   }

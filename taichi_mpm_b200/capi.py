@@ -14,8 +14,9 @@ from . import build as _build
 MPMB_MAX_GROUPS = 16
 MPMB_MAT_PARAMS = 8
 MPMB_N_STAGES = 5
-MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND = range(5)
-MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, "water": MAT_WATER, "sand": MAT_SAND}
+MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND, MAT_ELASTIC, MAT_VON_MISES, MAT_VISCO = range(8)
+MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, "water": MAT_WATER, "sand": MAT_SAND,
+                    "elastic": MAT_ELASTIC, "von_mises": MAT_VON_MISES, "visco": MAT_VISCO}
 
 # every symbol include/mpmb.h declares
 EXPORTS = [

@@ -869,6 +869,10 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
       // developed flow (cells hold 0..30 particles: mean/max per warp 0.56, profiles/r02_flow_stats.jsonl) that is the
       // kernel's cost.  Measured and rejected (round 2): capping the loop and adding the excess particles with one lane
       // per stencil node — 0.403 instead of 0.329 ms, the serialised excess pass costs more than the idle tail.
+      // Also measured and rejected (round 2, profiles/r02_ab_p2g_balance.log): re-assigning cells to threads per tile
+      // so that warp 0 owns the fuller cells — by bank pairs (flush stays conflict-free) +0.002 ms in both states, by
+      // population rank +0.015 / +0.020 ms: the kernel is latency-bound at 8 warps per SM, an early warp's issue slots
+      // are not what it lacks.
       const int i0 = s_start[tid], i1 = s_start[tid + 1];
       for (int it = i0; it < i1; it++) {
         const int r = s_order[it];
@@ -1990,7 +1994,7 @@ int mpmb_synchronize(MpmbHandle h) {
 int mpmb_set_material(MpmbHandle h, int32_t group, int32_t kind, const float *params, int32_t n_params) {
   CHECK_HANDLE(h);
   if (group < 0 || group >= MPMB_MAX_GROUPS) return fail(h, MPMB_ERR_INVALID, "group %d out of range", group);
-  if (kind < MPMB_MAT_LINEAR || kind > MPMB_MAT_SAND) return fail(h, MPMB_ERR_INVALID, "unknown material kind %d", kind);
+  if (kind < MPMB_MAT_LINEAR || kind > MPMB_MAT_VISCO) return fail(h, MPMB_ERR_INVALID, "unknown material kind %d", kind);
   if (n_params < 0 || n_params > MPMB_MAT_PARAMS || (n_params > 0 && !params)) return fail(h, MPMB_ERR_INVALID, "bad parameter vector");
   h->P.mats[group].kind = kind;
   for (int k = 0; k < 8; k++) h->P.mats[group].p[k] = k < n_params ? params[k] : 0.f;

@@ -15,9 +15,20 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+// out-of-line device function (host builds of this header — tests/host_math, tests/simt — take the GNU spelling:
+// libstdc++ uses the bare word __noinline__ inside attributes, so it cannot be a macro there)
+#ifdef __CUDACC__
+#define MPMB_NOINLINE_DEVICE __device__ __noinline__
+#else
+#define MPMB_NOINLINE_DEVICE __attribute__((noinline)) inline
+#endif
+
 namespace mpmb {
 
-enum { MAT_LINEAR = 0, MAT_JELLY = 1, MAT_SNOW = 2, MAT_WATER = 3, MAT_SAND = 4 };
+enum { MAT_LINEAR = 0, MAT_JELLY = 1, MAT_SNOW = 2, MAT_WATER = 3, MAT_SAND = 4, MAT_ELASTIC = 5, MAT_VON_MISES = 6, MAT_VISCO = 7 };
+// Hencky stress tau_i = 2 mu ln s_i + lambda sum ln s: sand, elastic and von Mises share calculate_force word for word
+// (src/particles.cpp:628-637, 800-809, 703-712)
+__device__ __forceinline__ bool is_hencky(int kind) { return kind == MAT_SAND || kind == MAT_ELASTIC || kind == MAT_VON_MISES; }
 
 struct Mat3 {  // column-major: m[c*3+r]
   float m[9];
@@ -219,7 +230,7 @@ __device__ __forceinline__ void calculate_force(const Material &mat, const Mat3 
   float e[3];
   eig_sym3<MPMB_EIG_SWEEPS>(left_strain(F), U, e);
   float tau[3];
-  if (mat.kind == MAT_SAND) {
+  if (is_hencky(mat.kind)) {
     // tau_i = 2 mu ln s_i + lambda sum ln s   (628-637: U (2mu S^-1 lnS + lambda tr(lnS) S^-1) V^T F^T)
     float mu = mat.p[0], la = mat.p[1];
     float l0 = 0.5f * log1p_strain(e[0]), l1 = 0.5f * log1p_strain(e[1]), l2 = 0.5f * log1p_strain(e[2]);
@@ -228,7 +239,7 @@ __device__ __forceinline__ void calculate_force(const Material &mat, const Mat3 
     tau[1] = fmaf(2.f * mu, l1, tr);
     tau[2] = fmaf(2.f * mu, l2, tr);
   } else {
-    // fixed corotated (jelly 391-398, snow 207-214): P F^T = 2mu (F-R)F^T + lambda (J-1) J I
+    // fixed corotated (jelly 391-398, snow 207-214, visco 69-82): P F^T = 2mu (F-R)F^T + lambda (J-1) J I
     //   (F-R)F^T = U diag(s(s-1)) U^T ;  s-1 = e/(s+1) ;  J^2-1 = sum e + sum e e + e e e
     float mu = mat.p[0], la = mat.p[1];
     if (mat.kind == MAT_SNOW) {
@@ -252,6 +263,126 @@ __device__ __forceinline__ void calculate_force(const Material &mat, const Mat3 
   out.m[6] = T.xz; out.m[7] = T.yz; out.m[8] = T.zz;
 }
 
+// VonMisesParticle::plasticity (src/particles.cpp:714-734) in principal log strains: eps = ln s, hat = dev(eps),
+// n2 = |hat|^2 — `frobenius_norm2()` at 724 is the SQUARED norm, and that is what enters both the yield test
+// dgamma = n2 - yield/(2 mu) and the scaling dgamma/n2 — returns sigma'/sigma per axis and (optionally) ln sigma'.
+__device__ __forceinline__ bool von_mises_return(const Material &mat, const float e[3], float ratio[3], float *lsn) {
+  float ls[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) ls[i] = 0.5f * log1p_strain(e[i]);
+  const float tr3 = (ls[0] + ls[1] + ls[2]) * (1.f / 3.f);
+  const float hat[3] = {ls[0] - tr3, ls[1] - tr3, ls[2] - tr3};
+  const float n2 = fmaf(hat[0], hat[0], fmaf(hat[1], hat[1], hat[2] * hat[2]));
+  const float dg = n2 - mat.p[2] / (2.f * mat.p[0]);
+  const bool yield = dg > 0.f;
+  const float k = yield ? dg / n2 : 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    ratio[i] = yield ? __expf(-k * hat[i]) : 1.f;
+    if (lsn) lsn[i] = fmaf(-k, hat[i], ls[i]);
+  }
+  return yield;
+}
+
+// Fixed-corotated Kirchhoff stress in principal space from en_i = s_i^2 - 1: tau_i = 2 mu s_i (s_i - 1) + lambda (J-1) J
+__device__ __forceinline__ void fixed_corotated_tau(float mu, float la, const float en[3], float tau[3]) {
+  const float s0 = sqrtf(1.f + en[0]), s1 = sqrtf(1.f + en[1]), s2 = sqrtf(1.f + en[2]);
+  const float J = s0 * s1 * s2;
+  const float J2m1 = (en[0] + en[1] + en[2]) + fmaf(en[0], en[1], fmaf(en[0], en[2], en[1] * en[2])) + en[0] * en[1] * en[2];
+  const float vol_term = la * (J2m1 / (J + 1.f)) * J;
+  tau[0] = fmaf(2.f * mu * s0, en[0] / (s0 + 1.f), vol_term);
+  tau[1] = fmaf(2.f * mu * s1, en[1] / (s1 + 1.f), vol_term);
+  tau[2] = fmaf(2.f * mu * s2, en[2] / (s2 + 1.f), vol_term);
+}
+
+__device__ __forceinline__ float det3(const Mat3 &A) {
+  return A.m[0] * (A.m[4] * A.m[8] - A.m[7] * A.m[5]) - A.m[3] * (A.m[1] * A.m[8] - A.m[7] * A.m[2]) + A.m[6] * (A.m[1] * A.m[5] - A.m[4] * A.m[2]);
+}
+
+// ViscoParticle::plasticity (src/particles.cpp:104-137) + the fixed-corotated stress of the new state (69-82).
+// ps = visco_tau.  Kept out of line: a rarely used material must not shape the register allocation of k_g2p.
+//   F^ = approximate_exponent(dt_p, (cdg - I)/dt_p) F   (89-102: (s/2 + I) s + I, halving while det <= 0)
+//   pnorm = |P(F_old)|_F = sqrt(sum_i (2 mu (s_i - 1) + lambda (J-1) J / s_i)^2)   (111: dg_e is not yet updated)
+//   gamma = clamp(dt_p nu (pnorm - tau)/pnorm, 0, 1);  sigma' = clamp(sigma / (sigma / det^(1/3))^gamma, 0.1, 10)
+// Both SVDs of the reference share the factors of F^, so one symmetric eigen-decomposition serves.
+// Everything crosses the call BY VALUE: a reference parameter of an out-of-line function would force the caller's
+// matrices (and the kernel's material table) into local memory on every path, not only on this one.
+struct ViscoOut {
+  Mat3 F, force;
+  float ps;
+};
+MPMB_NOINLINE_DEVICE ViscoOut visco_step_impl(float mu, float la, float nu, float kappa, float dtp, Mat3 cdg, Mat3 F, float ps, float vol) {
+  Mat3 force;
+  // pnorm of the old state (eigenvalues only)
+  float pnorm;
+  {
+    Mat3 U0;
+    float e0[3];
+    eig_sym3<MPMB_EIG_SWEEPS>(left_strain(F), U0, e0);
+    const float s0 = sqrtf(1.f + e0[0]), s1 = sqrtf(1.f + e0[1]), s2 = sqrtf(1.f + e0[2]);
+    const float J = s0 * s1 * s2;
+    const float vt = la * (J - 1.f) * J;
+    const float p0 = fmaf(2.f * mu, s0 - 1.f, vt / s0), p1 = fmaf(2.f * mu, s1 - 1.f, vt / s1), p2 = fmaf(2.f * mu, s2 - 1.f, vt / s2);
+    pnorm = sqrtf(fmaf(p0, p0, fmaf(p1, p1, p2 * p2)));
+  }
+  // approximate exponent of (cdg - I)
+  Mat3 m;
+#pragma unroll
+  for (int i = 0; i < 9; i++) m.m[i] = (cdg.m[i] - ((i & 3) == 0 ? 1.f : 0.f)) * (1.0f / dtp);
+  Mat3 ex;
+  int halvings = 0;
+  float dth = dtp;
+  for (;;) {
+    Mat3 sm, h;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { sm.m[i] = m.m[i] * dth; h.m[i] = sm.m[i] * 0.5f + ((i & 3) == 0 ? 1.f : 0.f); }
+    ex = mat_mul(h, sm);
+    ex.m[0] += 1.f; ex.m[4] += 1.f; ex.m[8] += 1.f;
+    if (det3(ex) > 0.f || halvings >= 16) break;
+    dth *= 0.5f;
+    halvings++;
+  }
+  for (int k = 0; k < halvings; k++) ex = mat_mul(ex, ex);
+  const Mat3 Fh = mat_mul(ex, F);
+  Mat3 U;
+  float e[3];
+  eig_sym3<MPMB_EIG_SWEEPS>(left_strain(Fh), U, e);
+  float gamma = 0.f;
+  if (pnorm > 1e-5f) gamma = fminf(fmaxf(dtp * nu * (pnorm - ps) / pnorm, 0.f), 1.f);
+  float sg[3] = {sqrtf(fmaxf(1.f + e[0], 0.f)), sqrtf(fmaxf(1.f + e[1], 0.f)), sqrtf(fmaxf(1.f + e[2], 0.f))};
+  const float det = sg[0] * sg[1] * sg[2];
+  const float scale = fabsf(det) > 1e-5f ? 1.0f / cbrtf(det) : 1.0f;
+  float ratio[3], en[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float mid = powf(sg[i] * scale, gamma);
+    const float mid_inv = fabsf(mid) > 1e-5f ? 1.0f / mid : 1.0f;
+    const float sn = fminf(fmaxf(sg[i] * mid_inv, 0.1f), 10.0f);
+    ratio[i] = sn / sg[i];
+    en[i] = fmaf(sn, sn, -1.f);
+  }
+  ps = fmaf(kappa * gamma, pnorm, ps);
+  F = sym_mul(sym_from_eig(U, ratio), Fh);
+  float tau[3];
+  fixed_corotated_tau(mu, la, en, tau);
+  tau[0] *= -vol; tau[1] *= -vol; tau[2] *= -vol;
+  const Sym3 T = sym_from_eig(U, tau);
+  force.m[0] = T.xx; force.m[1] = T.xy; force.m[2] = T.xz;
+  force.m[3] = T.xy; force.m[4] = T.yy; force.m[5] = T.yz;
+  force.m[6] = T.xz; force.m[7] = T.yz; force.m[8] = T.zz;
+  ViscoOut o;
+  o.F = F;
+  o.force = force;
+  o.ps = ps;
+  return o;
+}
+__device__ __forceinline__ void visco_step(const Material &mat, const Mat3 &cdg, Mat3 &F, float &ps, float vol, Mat3 &force) {
+  const ViscoOut o = visco_step_impl(mat.p[0], mat.p[1], mat.p[2], mat.p[3], mat.p[4], cdg, F, ps, vol);
+  F = o.F;
+  force = o.force;
+  ps = o.ps;
+}
+
 // Particle::plasticity(cdg) (src/particles.cpp:222-242,340-344,413-416,469-478,639-647):
 // F <- cdg F, then the return map of the material; ps is Jp / j / logJp.
 __device__ __forceinline__ void plasticity(const Material &mat, const Mat3 &cdg, Mat3 &F, float &ps) {
@@ -260,8 +391,13 @@ __device__ __forceinline__ void plasticity(const Material &mat, const Mat3 &cdg,
     if (ps < 0.1f) ps = 0.1f;
     return;
   }
+  if (mat.kind == MAT_VISCO) {
+    Mat3 force;
+    visco_step(mat, cdg, F, ps, 0.f, force);
+    return;
+  }
   Mat3 Ft = mat_mul(cdg, F);
-  if (mat.kind == MAT_LINEAR || mat.kind == MAT_JELLY) {
+  if (mat.kind == MAT_LINEAR || mat.kind == MAT_JELLY || mat.kind == MAT_ELASTIC) {
     F = Ft;
     return;
   }
@@ -270,7 +406,9 @@ __device__ __forceinline__ void plasticity(const Material &mat, const Mat3 &cdg,
   eig_sym3<MPMB_EIG_SWEEPS>(left_strain(Ft), U, e);
   float ratio[3];
   bool changed;
-  if (mat.kind == MAT_SNOW) {
+  if (mat.kind == MAT_VON_MISES) {
+    changed = von_mises_return(mat, e, ratio, nullptr);
+  } else if (mat.kind == MAT_SNOW) {
     // sigma clamped to [1-theta_c, 1+theta_s]; Jp <- clamp(Jp * prod(s)/prod(s'))   (222-242)
     float lo = 1.f - mat.p[3], hi = 1.f + mat.p[4];
     float prod = 1.f;
@@ -509,6 +647,10 @@ __device__ __forceinline__ void material_step(const Material &mat, const Mat3 &c
     calculate_force(mat, F, ps, vol, force);
     return;
   }
+  if (mat.kind == MAT_VISCO) {
+    visco_step(mat, cdg, F, ps, vol, force);
+    return;
+  }
   const Mat3 Ft = mat_mul(cdg, F);
   if (mat.kind == MAT_LINEAR) {
     F = Ft;
@@ -524,7 +666,20 @@ __device__ __forceinline__ void material_step(const Material &mat, const Mat3 &c
   eig_sym3<MPMB_EIG_SWEEPS>(left_strain(Ft), U, e);
   float ratio[3], tau[3];
   bool changed = false;
-  if (mat.kind == MAT_SAND) {
+  if (mat.kind == MAT_ELASTIC || mat.kind == MAT_VON_MISES) {
+    // Hencky elasticity (src/particles.cpp:800-814) with the von Mises return map (714-734) where asked for
+    const float mu = mat.p[0], la = mat.p[1];
+    float lsn[3];
+    if (mat.kind == MAT_VON_MISES) {
+      changed = von_mises_return(mat, e, ratio, lsn);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++) lsn[i] = 0.5f * log1p_strain(e[i]);
+    }
+    const float trl = la * (lsn[0] + lsn[1] + lsn[2]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) tau[i] = -vol * fmaf(2.f * mu, lsn[i], trl);
+  } else if (mat.kind == MAT_SAND) {
     const float mu = mat.p[0], la = mat.p[1], alpha = mat.p[2], coh = mat.p[3], beta = mat.p[4];
     float ls[3], eps[3];
     float sum = 0.f;

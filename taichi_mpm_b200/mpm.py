@@ -23,8 +23,10 @@ import numpy as np
 from . import bgeo, capi, scenes
 
 # MPMParticle::get_debug_info().y per registered type (src/particles.cpp:288-290,347-349,422-424,
-# 496-498,669-671); water also reports (j, 5, sticky)
-_DEBUG_CODE = {scenes.MAT_SNOW: 2.0, scenes.MAT_LINEAR: 3.0, scenes.MAT_JELLY: 4.0, scenes.MAT_WATER: 5.0, scenes.MAT_SAND: 6.0}
+# 496-498,669-671,156-158,754-756,838-840); water also reports (j, 5, sticky); elastic reports its Young's modulus in .x,
+# which this mirror does not carry per particle (0 is written)
+_DEBUG_CODE = {scenes.MAT_SNOW: 2.0, scenes.MAT_LINEAR: 3.0, scenes.MAT_JELLY: 4.0, scenes.MAT_WATER: 5.0, scenes.MAT_SAND: 6.0,
+               scenes.MAT_VISCO: 1.0, scenes.MAT_VON_MISES: 7.0, scenes.MAT_ELASTIC: 8.0}
 
 
 def frame_attributes(p, group_kinds, verbose=False):
@@ -179,6 +181,8 @@ class MPM:
         keep = (X.min(1) >= 7.0) & ((X - np.asarray(self.res, np.float32)).max(1) <= -7.0)
         x, mass, vol = x[keep], mass[keep], vol[keep]
         st = scenes.make_state(x, mass, vol, kind, group, kwargs.get("initial_velocity", (0.0, 0.0, 0.0)))
+        if kind == scenes.MAT_VISCO and "tau" in kwargs:                         # visco_tau, src/particles.cpp:62
+            st["ps"][:] = np.float32(kwargs["tau"])
         cur = self._pull_host()
         if cur is None:
             self._host = st

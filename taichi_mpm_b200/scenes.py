@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND = range(5)
+MAT_LINEAR, MAT_JELLY, MAT_SNOW, MAT_WATER, MAT_SAND, MAT_ELASTIC, MAT_VON_MISES, MAT_VISCO = range(8)
 N_MAT_PARAMS = 8
 
 
@@ -41,12 +41,22 @@ def material_params(kind, **kw):
         s = math.sin(np.float32(phi) / np.float32(180.0) * np.float32(3.141592653))
         p[2] = math.sqrt(2.0 / 3.0) * 2.0 * s / (3.0 - s)
         p[3], p[4] = kw.get("cohesion", 0.0), kw.get("beta", 1.0)
+    elif kind == MAT_ELASTIC:  # src/particles.cpp:775-781 (keys "E", "nu")
+        p[0], p[1] = lame(kw.get("E", 5e3), kw.get("nu", 0.4))
+    elif kind == MAT_VON_MISES:  # src/particles.cpp:691-700
+        p[0], p[1] = lame(kw.get("youngs_modulus", 5e3), kw.get("poisson_ratio", 0.4))
+        p[2] = kw.get("yield_stress", 1.0)
+    elif kind == MAT_VISCO:  # src/particles.cpp:55-67; [4] is the particle's own copy of base_delta_t (default 1e-4)
+        p[0], p[1] = lame(kw.get("youngs_modulus", 4e4), kw.get("poisson_ratio", 0.4))
+        p[2], p[3], p[4] = kw.get("nu", 10000.0), kw.get("kappa", 0.0), kw.get("base_delta_t", 1e-4)
     else:
         raise ValueError("unknown material kind %r" % (kind,))
     return p
 
 
 def default_scalar(kind):
+    if kind == MAT_VISCO:
+        return 1000.0  # visco_tau (src/particles.cpp:62)
     return 1.0 if kind in (MAT_SNOW, MAT_WATER) else 0.0  # Jp=1, j=1, logJp=0
 
 

@@ -11,6 +11,17 @@ TOL_X_ABS = 1e-6        # times the domain size (=1)
 TOL_PS_ABS = 1e-5
 
 
+# per-kind arguments of perturbed_scene for the single-substep comparisons: von Mises at a strain level that puts particles
+# on both sides of its yield surface (|dev eps|^2 vs yield_stress / 2 mu = 2.8e-4), visco with hardening (visco_tau moves)
+KIND_KW = {scenes.MAT_VON_MISES: dict(strain=0.006), scenes.MAT_VISCO: dict(kappa=0.3)}
+
+
+def ps_err(a, b):
+    """Error of the plastic scalar: absolute up to 1, relative above (visco_tau is O(1e3), the others O(1))."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float((np.abs(a - b) / np.maximum(1.0, np.abs(b))).max()) if a.size else 0.0
+
+
 def perturb_state(st, kind, dx, seed=0, strain=0.02, vel=0.5):
     """Random affine velocity field, random apic_b, random F perturbation and plastic scalars on top of a
     lattice state (in place): every term of P2G, the grid update and G2P + return map is exercised."""
@@ -30,6 +41,8 @@ def perturb_state(st, kind, dx, seed=0, strain=0.02, vel=0.5):
         st["ps"] = (1.0 + rng.normal(size=n) * 0.01).astype(np.float32)
     if kind == scenes.MAT_SAND:
         st["ps"] = (np.abs(rng.normal(size=n)) * 1e-3 * (rng.random(n) < 0.3)).astype(np.float32)
+    if kind == scenes.MAT_VISCO:   # visco_tau around the first Piola norms of this strain level: some particles flow, some do not
+        st["ps"] = (1000.0 * (0.2 + 1.6 * rng.random(n))).astype(np.float32)
     return st
 
 
@@ -95,6 +108,6 @@ def compare_substep(e, scene, state, check_grid=True):
     out["v"] = np.abs(got["v"] - ref["v"][sel]).max() / vmax
     out["b"] = np.abs(got["b"] - ref["b"][sel]).max() / bmax
     out["F"] = np.abs(got["F"] - ref["F"][sel]).max()
-    out["ps"] = np.abs(got["ps"] - ref["ps"][sel]).max()
+    out["ps"] = (np.abs(got["ps"] - ref["ps"][sel]) / np.maximum(1.0, np.abs(ref["ps"][sel]))).max()   # relative above 1 (visco_tau ~ 1e3)
     out["mass"] = np.abs(got["mass"] - ref["mass"][sel]).max()
     return out, got, ref

@@ -15,7 +15,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import pyoracle as O  # noqa: E402
 
 # (kind, |F - I| scale, |cdg - I| scale): the regimes the parity tests of the kernels use
-CASES = [(0, 0.05, 0.01), (1, 0.1, 0.01), (2, 0.03, 0.01), (3, 0.0, 0.01), (4, 2e-3, 1e-3), (4, 0.05, 0.02)]
+CASES = [(0, 0.05, 0.01), (1, 0.1, 0.01), (2, 0.03, 0.01), (3, 0.0, 0.01), (4, 2e-3, 1e-3), (4, 0.05, 0.02),
+         (5, 0.05, 0.01), (6, 0.02, 0.01), (6, 1e-3, 1e-3), (7, 0.05, 0.01)]
 VOL = 1e-6
 
 
@@ -28,7 +29,8 @@ def golden_states(kind, strain, rate, count=40, seed=0):
         cdg = (np.eye(3) + rng.normal(size=(3, 3)) * rate).astype(np.float32)
         if np.linalg.det(F.astype(np.float64)) <= 0.2 or np.linalg.det(cdg.astype(np.float64)) <= 0.2:
             continue
-        ps = {2: 1 + rng.normal() * 0.05, 3: 1 + rng.normal() * 0.02, 4: abs(rng.normal()) * 2e-3 * (rng.random() < 0.5)}.get(kind, 0.0)
+        ps = {2: 1 + rng.normal() * 0.05, 3: 1 + rng.normal() * 0.02, 4: abs(rng.normal()) * 2e-3 * (rng.random() < 0.5),
+              7: 1000.0 * (0.5 + rng.random())}.get(kind, 0.0)   # 7: visco_tau around its default
         out.append((F, cdg, np.float32(ps)))
     return out
 

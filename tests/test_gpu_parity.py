@@ -9,7 +9,8 @@ from tests import common as T
 pytestmark = pytest.mark.gpu
 
 KINDS = [("linear", scenes.MAT_LINEAR), ("jelly", scenes.MAT_JELLY), ("snow", scenes.MAT_SNOW), ("water", scenes.MAT_WATER),
-         ("sand", scenes.MAT_SAND)]
+         ("sand", scenes.MAT_SAND), ("elastic", scenes.MAT_ELASTIC), ("von_mises", scenes.MAT_VON_MISES), ("visco", scenes.MAT_VISCO)]
+KIND_KW = T.KIND_KW
 
 
 def _assert_parity(err):
@@ -27,9 +28,17 @@ def _assert_parity(err):
 
 @pytest.mark.parametrize("name,kind", KINDS)
 def test_single_substep_vs_fp64_oracle(name, kind):
-    scene, st = T.perturbed_scene(kind, res=32, cells=8, seed=3)
+    scene, st = T.perturbed_scene(kind, res=32, cells=8, seed=3, **KIND_KW.get(kind, {}))
     e = T.make_engine(scene, st)
     err, got, ref = T.compare_substep(e, scene, st)
+    if kind == scenes.MAT_VON_MISES:   # both branches of the return map ran (src/particles.cpp:726-733)
+        eps = np.log(np.linalg.svd(st["F"].reshape(-1, 3, 3).astype(np.float64), compute_uv=False))
+        n2 = ((eps - eps.mean(1, keepdims=True)) ** 2).sum(1)
+        yielding = n2 > scene["mat_params"][0][2] / (2 * scene["mat_params"][0][0])
+        assert 0.1 < yielding.mean() < 0.9, yielding.mean()
+    if kind == scenes.MAT_VISCO:
+        moved = np.abs(ref["ps"] - st["ps"]) > 1e-3
+        assert 0.05 < moved.mean() < 0.95, moved.mean()
     print(name, {k: (float(v) if not isinstance(v, bool) else v) for k, v in err.items()})
     _assert_parity(err)
     e.close()
@@ -39,7 +48,7 @@ def test_single_substep_vs_fp64_oracle(name, kind):
 def test_single_substep_vs_fp32_oracle(name, kind):
     # same bounds against the fp32 restatement (reference operation order)
     from oracle import pyoracle as O
-    scene, st = T.perturbed_scene(kind, res=32, cells=6, seed=4)
+    scene, st = T.perturbed_scene(kind, res=32, cells=6, seed=4, **KIND_KW.get(kind, {}))
     e = T.make_engine(scene, st)
     ref, _, _ = O.substep(scene, st, np.float32)
     e.substep(1)
@@ -337,7 +346,8 @@ def test_reupload_replaces_the_resident_set():
     e.close(); f.close(); g.close()
 
 
-@pytest.mark.parametrize("name,kind", [("jelly", scenes.MAT_JELLY), ("snow", scenes.MAT_SNOW), ("water", scenes.MAT_WATER)])
+@pytest.mark.parametrize("name,kind", [("jelly", scenes.MAT_JELLY), ("snow", scenes.MAT_SNOW), ("water", scenes.MAT_WATER),
+                                       ("elastic", scenes.MAT_ELASTIC), ("von_mises", scenes.MAT_VON_MISES), ("visco", scenes.MAT_VISCO)])
 def test_multi_step_other_materials(name, kind):
     from oracle import pyoracle as O
     scene, st = T.perturbed_scene(kind, res=32, cells=6, seed=41, strain=0.0, vel=0.5)

@@ -8,6 +8,8 @@ import os
 import numpy as np
 import pytest
 
+from tests import common as T
+
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -36,7 +38,7 @@ def test_engine_matches_reference_substeps(kind):
     assert np.abs(got["b"] - ref["b"]).max() <= 2e-3 * np.abs(ref["b"]).max()
     if kind != scenes.MAT_WATER:
         assert np.abs(got["F"] - ref["F"]).max() <= 2e-4
-    assert np.abs(got["ps"] - ref["ps"]).max() <= 1e-4
+    assert T.ps_err(got["ps"], ref["ps"]) <= (1e-3 if kind == scenes.MAT_VISCO else 1e-4)   # visco_tau hardening: see test_oracle_ref_transfer.py
 
 
 @pytest.mark.parametrize("kind", G.KINDS)
@@ -68,7 +70,7 @@ def test_engine_single_substep_matches_reference_transfers(kind):
     assert np.abs(got["b"] - ref["b"]).max() <= 2 * T.TOL_V_REL * np.abs(ref["b"]).max()
     if kind != scenes.MAT_WATER:
         assert np.abs(got["F"] - ref["F"]).max() <= 2 * T.TOL_F_ABS
-    assert np.abs(got["ps"] - ref["ps"]).max() <= 2 * T.TOL_PS_ABS
+    assert T.ps_err(got["ps"], ref["ps"]) <= 2 * T.TOL_PS_ABS
 
 
 def test_same_script_on_the_mirror_and_on_the_reference_solver():

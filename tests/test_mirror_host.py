@@ -240,8 +240,16 @@ def test_add_particles_follows_the_reference_rules(fake_engine):
     m.add_particles(type="water", positions=pts + 0.1, density=1000.0)
     m.add_particles(type="water", positions=pts + 0.2, density=1000.0, k=5e3)
     assert [k for k, _ in m._groups] == [mpm_mod.scenes.MAT_SNOW, mpm_mod.scenes.MAT_WATER, mpm_mod.scenes.MAT_WATER]
+    # all eight deformable types registered by the reference (src/particles.cpp:845-856) are accepted
+    m.add_particles(type="von_mises", positions=pts + 0.05, yield_stress=2.0)
+    m.add_particles(type="elastic", positions=pts + 0.06, E=1e4)
+    m.add_particles(type="visco", positions=pts + 0.07, tau=500.0, kappa=0.1)
+    p = m.get_particles()
+    kinds = [k for k, _ in m._groups]
+    assert kinds[3:] == [mpm_mod.scenes.MAT_VON_MISES, mpm_mod.scenes.MAT_ELASTIC, mpm_mod.scenes.MAT_VISCO]
+    assert m._groups[3][1][2] == 2.0 and np.allclose(p["ps"][p["group"] == 5], 500.0)   # yield_stress; visco_tau is the scalar
     with pytest.raises(ValueError):
-        m.add_particles(type="von_mises", positions=pts)                            # registered in the reference, not accelerated
+        m.add_particles(type="no_such_particle", positions=pts)
     with pytest.raises(ValueError):
         m.add_particles(type="rigid")
 

@@ -29,7 +29,7 @@ def _oracle_step(kind, prm, cdg, F, ps, dtype):
 
 
 # the reference evaluates log(sigma) in fp32: at strains of 2e-3 that alone is 6e-5 of the stress
-FORCE_TOL = {0: 4e-6, 1: 4e-6, 2: 2e-5, 3: 2e-5, 4: 2e-4}
+FORCE_TOL = {0: 4e-6, 1: 4e-6, 2: 2e-5, 3: 2e-5, 4: 2e-4, 5: 2e-5, 6: 2e-4, 7: 2e-5}
 
 
 @pytest.mark.parametrize("ci", range(len(G.CASES)))
@@ -44,7 +44,7 @@ def test_oracle_constitutive_matches_golden_run_of_reference_particles(ci):
         F1, ps1, force = _oracle_step(kind, prm, cdg, F, ps, np.float64)
         if kind != scenes.MAT_WATER:
             assert np.abs(F1 - Fr[i]).max() <= 1e-6, (kind, i)
-        assert abs(ps1 - psr[i]) <= 2e-6, (kind, i)
+        assert abs(ps1 - psr[i]) <= 2e-6 * max(1.0, abs(psr[i])), (kind, i)
         assert np.abs(force - fr[i]).max() <= FORCE_TOL[kind] * scale, (kind, i)
     if kind in (scenes.MAT_SNOW, scenes.MAT_SAND):                                   # the return maps were active
         assert np.abs(psr - np.array([s[2] for s in G.golden_states(kind, strain, rate)])).max() > 1e-4
@@ -70,7 +70,7 @@ def test_oracle_constitutive_matches_reference_particles_live(kind):
         F1, ps1, force = _oracle_step(kind, prm, cdg, F, ps, np.float64)
         if kind != scenes.MAT_WATER:
             assert np.abs(F1 - Fr).max() <= 2e-6
-        assert abs(ps1 - psr) <= 3e-6
+        assert abs(ps1 - psr) <= 3e-6 * max(1.0, abs(psr))
         assert np.abs(force - fr).max() <= FORCE_TOL[kind] * scale
         # and calculate_force alone (the upload-time call), without a plasticity step before it
         _, _, f0 = O.ref_particle_step(kind, prm, cdg, F, ps, G.VOL, do_plasticity=False)
