@@ -710,6 +710,404 @@ void substep(const Scene<R> &sc, Particles<R> &P, uint8_t *alive, R *grid_out /*
 }
 
 // ================================================================================
+// CPIC rigid-coupled path: rasterize_rigid_boundary + gather_cdf (src/rigid_transfer.cpp:18-113,
+// 120-274), update_rigid_page_map (src/mpm.cpp:1026-1076), block_op_rigid of rasterize_optimized / resample_optimized
+// (src/transfer.cpp:367-463, 706-835).  PARITY STATUS: the MPM side follows those lines; what they call in the
+// un-vendored core is ASSUMED and stated here once:
+//   RigidBody::get_velocity_at(p)        = velocity + angular_velocity x (p - position)
+//   RigidBody::apply_tmp_impulse(j, p)   : tmp_velocity += inv_mass j ; tmp_angular_velocity += Iw^-1 ((p - position) x j)
+//   reset_tmp_velocity / apply_tmp_velocity : zero the two accumulators / add them to velocity, angular_velocity
+//   get_mesh_to_world() = get_centroid_to_world() = x -> position + Rot x   (the mesh is re-centred on the centre of
+//                                                    mass at creation, src/mpm_rigid_body.cpp:190-207)
+//   Element::get_transformed(M)          : the three vertices mapped by M
+//   world_to_element(e)                  = [v1 - v0, v2 - v0, n]^-1, n = unit normal (v1-v0) x (v2-v0)
+//   VectorI(ind) for a Region index      = the index's integer coordinates — with which update_rigid_page_map's range test
+//                                          (src/mpm.cpp:1062) admits only the offsets {0,1}^3 of the 27 it loops over
+// Rigid ids index MPM::rigids; 0 is the background body (src/mpm.cpp:72-74), so real bodies are 1..11.
+// ================================================================================
+constexpr uint32_t kStateMask = 0xAAAAAAAAu;       // src/mpm.h:36 (the particle / node words are 32-bit)
+constexpr int kTagBits = 24;                       // GridState::tag_bits = 12 bodies x 2 (src/mpm_fwd.h:79-85)
+constexpr uint32_t kTagMask = (1u << kTagBits) - 1u;
+
+template <class R> struct Rigid {
+  int n_rigid;                      // length of the per-body arrays (body 0 = background, never referenced)
+  const R *position, *rot;          // [n_rigid][3], [n_rigid][9] column-major
+  R *velocity, *angular_velocity;   // [n_rigid][3]; updated by apply_tmp_velocity after each transfer
+  const R *inv_mass, *inv_inertia;  // [n_rigid], [n_rigid][9] world-space, column-major
+  const R *frictions;               // [n_rigid][2]
+  int64_t n_samples;                // RigidBoundaryParticles (src/boundary_particle.h)
+  const R *offset, *tri;            // [ns][3] anchor in the centroid frame, [ns][9] untransformed_element (v0,v1,v2)
+  const int32_t *sample_rigid;      // [ns]
+  R penalty, pushing_force;         // src/mpm.cpp:35,40
+  uint32_t *states;                 // [n] MPMParticle::states (persists)
+  R *bnormal, *bdist;               // [n][3], [n]   boundary_normal, boundary_distance (rewritten every substep)
+  uint8_t *near;                    // [n]           near_boundary_
+  // scratch
+  std::vector<uint32_t> node_state; // tags | (rigid id + 1) << 24   (GridState::states)
+  std::vector<R> node_dist;         // GridState::distance
+  std::vector<uint8_t> page;        // rigid_page_map over 4x4x8 blocks
+  std::vector<R> tmp_v, tmp_w;
+  int nb[3];
+};
+
+template <class R> inline void cross3(const R *a, const R *b, R *o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+template <class R> inline void rigid_to_world(const Rigid<R> &rg, int id, const R *local, R *out) {
+  const R *c = rg.position + 3 * id, *M = rg.rot + 9 * id;
+  for (int r = 0; r < 3; r++) out[r] = c[r] + (at(M, r, 0) * local[0] + at(M, r, 1) * local[1] + at(M, r, 2) * local[2]);
+}
+template <class R> inline void rigid_velocity_at(const Rigid<R> &rg, int id, const R *p, R *out) {
+  R d[3] = {p[0] - rg.position[3 * id], p[1] - rg.position[3 * id + 1], p[2] - rg.position[3 * id + 2]}, w[3];
+  cross3(rg.angular_velocity + 3 * id, d, w);
+  for (int k = 0; k < 3; k++) out[k] = rg.velocity[3 * id + k] + w[k];
+}
+template <class R> inline void rigid_apply_tmp_impulse(Rigid<R> &rg, int id, const R *j, const R *p) {
+  R d[3] = {p[0] - rg.position[3 * id], p[1] - rg.position[3 * id + 1], p[2] - rg.position[3 * id + 2]}, t[3];
+  cross3(d, j, t);
+  const R *I = rg.inv_inertia + 9 * id;
+  for (int k = 0; k < 3; k++) {
+    rg.tmp_v[3 * id + k] += rg.inv_mass[id] * j[k];
+    rg.tmp_w[3 * id + k] += at(I, k, 0) * t[0] + at(I, k, 1) * t[1] + at(I, k, 2) * t[2];
+  }
+}
+template <class R> inline void rigid_reset_tmp(Rigid<R> &rg) {
+  rg.tmp_v.assign(size_t(rg.n_rigid) * 3, R(0));
+  rg.tmp_w.assign(size_t(rg.n_rigid) * 3, R(0));
+}
+template <class R> inline void rigid_apply_tmp(Rigid<R> &rg) {
+  for (int k = 0; k < rg.n_rigid * 3; k++) { rg.velocity[k] += rg.tmp_v[k]; rg.angular_velocity[k] += rg.tmp_w[k]; }
+}
+template <class R> inline bool rigid_page_of_block(const Rigid<R> &rg, int bx, int by, int bz) {
+  if (bx < 0 || by < 0 || bz < 0 || bx >= rg.nb[0] || by >= rg.nb[1] || bz >= rg.nb[2]) return false;
+  return rg.page[(size_t(bx) * rg.nb[1] + by) * rg.nb[2] + bz] != 0;
+}
+
+// sample s: world position of its anchor (align_with_rigid_body, src/boundary_particle.h:48-53)
+template <class R> inline void sample_world(const Rigid<R> &rg, int64_t s, R *pos) { rigid_to_world(rg, rg.sample_rigid[s], rg.offset + 3 * s, pos); }
+
+// update_rigid_page_map (src/mpm.cpp:1026-1076): blocks that hold a rigid particle (by its base node) and — because of the
+// range test on the OFFSET at 1062 — their {0,1}^3 upper neighbours.
+template <class R> void rigid_pages(const Scene<R> &sc, Rigid<R> &rg) {
+  rg.nb[0] = (sc.nx() + 3) / 4 + 1; rg.nb[1] = (sc.ny() + 3) / 4 + 1; rg.nb[2] = (sc.nz() + 7) / 8 + 1;
+  rg.page.assign(size_t(rg.nb[0]) * rg.nb[1] * rg.nb[2], 0);
+  for (int64_t s = 0; s < rg.n_samples; s++) {
+    R pos[3]; int base[3]; R rel[3];
+    sample_world(rg, s, pos);
+    base_and_rel(sc, pos, base, rel);
+    const int bx = base[0] >> 2, by = base[1] >> 2, bz = base[2] >> 3;
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+      const int x = bx + i, y = by + j, z = bz + k;
+      if (x < rg.nb[0] && y < rg.nb[1] && z < rg.nb[2]) rg.page[(size_t(x) * rg.nb[1] + y) * rg.nb[2] + z] = 1;
+    }
+  }
+}
+
+// rasterize_rigid_boundary (src/rigid_transfer.cpp:18-77), 3-D branch.
+template <class R> void cdf_rasterize(const Scene<R> &sc, Rigid<R> &rg) {
+  rg.node_state.assign(sc.n_nodes(), 0u);
+  rg.node_dist.assign(sc.n_nodes(), R(0));
+  for (int64_t s = 0; s < rg.n_samples; s++) {
+    const int id = rg.sample_rigid[s];
+    R pos[3]; int base[3]; R rel[3];
+    sample_world(rg, s, pos);
+    base_and_rel(sc, pos, base, rel);                 // get_grid_base_pos_with<3> (29-30)
+    R v0[3], v1[3], v2[3];                            // get_world_space_element (32)
+    rigid_to_world(rg, id, rg.tri + 9 * s, v0);
+    rigid_to_world(rg, id, rg.tri + 9 * s + 3, v1);
+    rigid_to_world(rg, id, rg.tri + 9 * s + 6, v2);
+    R M[9], Minv[9], e1[3], e2[3], n[3];              // world_to_element (33)
+    for (int k = 0; k < 3; k++) { e1[k] = v1[k] - v0[k]; e2[k] = v2[k] - v0[k]; }
+    cross3(e1, e2, n);
+    const R nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int k = 0; k < 3; k++) { n[k] /= nl; at(M, k, 0) = e1[k]; at(M, k, 1) = e2[k]; at(M, k, 2) = n[k]; }
+    mat_inverse(M, Minv);
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int c = 0; c < 3; c++) {
+      const int i[3] = {base[0] + a, base[1] + b, base[2] + c};
+      if (i[0] < 0 || i[1] < 0 || i[2] < 0 || i[0] >= sc.nx() || i[1] >= sc.ny() || i[2] >= sc.nz()) continue;
+      R d[3] = {R(i[0]) * sc.dx - v0[0], R(i[1]) * sc.dx - v0[1], R(i[2]) * sc.dx - v0[2]};
+      R coord[3];
+      for (int r = 0; r < 3; r++) coord[r] = at(Minv, r, 0) * d[0] + at(Minv, r, 1) * d[1] + at(Minv, r, 2) * d[2];
+      const bool negative = coord[2] < 0;
+      R dist = std::abs(coord[2]);
+      if (!(R(0) <= coord[0] && R(0) <= coord[1] && coord[0] + coord[1] <= R(1))) continue;   // 50-53
+      dist *= sc.inv_dx;                                                                           // 60
+      const size_t node = sc.node(i[0], i[1], i[2]);
+      uint32_t &st = rg.node_state[node];
+      if ((st >> kTagBits) == 0u || dist < rg.node_dist[node]) {                                  // 65-69
+        rg.node_dist[node] = dist;
+        st = (st & kTagMask) | (uint32_t(id + 1) << kTagBits);
+      }
+      st |= uint32_t(2 + int(negative)) << (id * 2);                                              // 73-74
+    }
+  }
+  for (auto &d : rg.node_dist) d *= sc.dx;                                                        // 77-78
+}
+
+template <class R> R det4(const R *m) {  // m[c*4+r]
+  auto a = [&](int r, int c) { return m[c * 4 + r]; };
+  R det = 0;
+  for (int c = 0; c < 4; c++) {
+    int cc[3], k = 0;
+    for (int j = 0; j < 4; j++) if (j != c) cc[k++] = j;
+    R minor = a(1, cc[0]) * (a(2, cc[1]) * a(3, cc[2]) - a(2, cc[2]) * a(3, cc[1])) - a(1, cc[1]) * (a(2, cc[0]) * a(3, cc[2]) - a(2, cc[2]) * a(3, cc[0])) +
+              a(1, cc[2]) * (a(2, cc[0]) * a(3, cc[1]) - a(2, cc[1]) * a(3, cc[0]));
+    det += ((c & 1) ? R(-1) : R(1)) * a(0, c) * minor;
+  }
+  return det;
+}
+// solves m x = y for symmetric-positive 4x4 m by Gaussian elimination with partial pivoting (inversed(XtX) * XtY, 252)
+template <class R> void solve4(const R *m, const R *y, R *x) {
+  R a[4][5];
+  for (int r = 0; r < 4; r++) { for (int c = 0; c < 4; c++) a[r][c] = m[c * 4 + r]; a[r][4] = y[r]; }
+  for (int c = 0; c < 4; c++) {
+    int p = c;
+    for (int r = c + 1; r < 4; r++) if (std::abs(a[r][c]) > std::abs(a[p][c])) p = r;
+    for (int k = 0; k < 5; k++) std::swap(a[c][k], a[p][k]);
+    for (int r = c + 1; r < 4; r++) { const R f = a[r][c] / a[c][c]; for (int k = c; k < 5; k++) a[r][k] -= f * a[c][k]; }
+  }
+  for (int r = 3; r >= 0; r--) { R sum = a[r][4]; for (int c = r + 1; c < 4; c++) sum -= a[r][c] * x[c]; x[r] = sum / a[r][r]; }
+}
+
+// gather_cdf (src/rigid_transfer.cpp:120-274), 3-D, mpm_use_weighted_reconstruction = cdf_use_negative = true.
+template <class R> void gather_cdf(const Scene<R> &sc, Rigid<R> &rg, const Particles<R> &P, const uint8_t *alive) {
+  for (int64_t p = 0; p < P.n; p++) {
+    if (alive && !alive[p]) continue;
+    rg.bdist[p] = 0; rg.bnormal[3 * p] = rg.bnormal[3 * p + 1] = rg.bnormal[3 * p + 2] = 0; rg.near[p] = 0;   // 138-140
+    R pos[3] = {P.x[3 * p] * sc.inv_dx, P.x[3 * p + 1] * sc.inv_dx, P.x[3 * p + 2] * sc.inv_dx};
+    if (!rigid_page_of_block(rg, int(pos[0]) >> 2, int(pos[1]) >> 2, int(pos[2]) >> 3)) continue;           // 142-146: the CELL's page
+    uint32_t &pst = rg.states[p];
+    int base[3]; R rel[3];
+    base_and_rel(sc, P.x + 3 * p, base, rel);
+    R w[3][3], dw[3][3];
+    for (int d = 0; d < 3; d++) quadratic_kernel_axis(pos[d], w[d], dw[d]);
+    uint32_t all_boundaries = 0;
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int c = 0; c < 3; c++)
+      all_boundaries |= rg.node_state[sc.node(base[0] + a, base[1] + b, base[2] + c)] & kTagMask & kStateMask;   // 155-159
+    pst &= (all_boundaries + (all_boundaries >> 1));                                                           // 162
+    uint32_t to_add = all_boundaries & ~pst;                                                                   // 164
+    while (to_add) {
+      const uint32_t bit = to_add & (0u - to_add);
+      to_add ^= bit;
+      R wd[2] = {0, 0};
+      for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int c = 0; c < 3; c++) {
+        const size_t node = sc.node(base[0] + a, base[1] + b, base[2] + c);
+        const uint32_t gs = rg.node_state[node];
+        if ((gs >> kTagBits) == 0u) continue;                                                                  // 182-184
+        const R d = rg.node_dist[node] * sc.inv_dx;
+        const R weight = (w[0][a] * w[1][b]) * w[2][c];
+        if ((gs & kTagMask) & bit) wd[((gs & kTagMask) & (bit >> 1)) != 0 ? 1 : 0] += d * weight;              // 195-198
+      }
+      if (wd[0] + wd[1] > R(1e-7)) pst |= bit | ((bit >> 1) * uint32_t(wd[0] < wd[1]));                        // 200-205
+    }
+    if (pst == 0) continue;
+    R XtX[16] = {0}, XtY[4] = {0};
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int c = 0; c < 3; c++) {
+      const size_t node = sc.node(base[0] + a, base[1] + b, base[2] + c);
+      const uint32_t word = rg.node_state[node];
+      if ((word >> kTagBits) == 0u) continue;                                                                  // 217-219
+      const uint32_t gs = word & kTagMask;
+      const R dpos[3] = {pos[0] - R(base[0] + a), pos[1] - R(base[1] + b), pos[2] - R(base[2] + c)};
+      const uint32_t mask = (gs & pst & kStateMask) >> 1;
+      const R d = rg.node_dist[node] * sc.inv_dx;
+      const R xp[4] = {-dpos[0], -dpos[1], -dpos[2], R(1)};
+      const R weight = (w[0][a] * w[1][b]) * w[2][c];
+      if (gs == 0) continue;
+      R sgn;
+      if ((gs & mask) == (pst & mask)) sgn = R(1);                                                             // 232-236: same colour
+      else {
+        const uint32_t diff = (gs & mask) ^ (pst & mask);                                                      // 239-243: exactly one colour differs
+        if (diff > 0 && (diff & (diff - 1)) == 0) sgn = R(-1); else continue;
+      }
+      for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) XtX[j * 4 + i] += xp[i] * xp[j] * weight;
+      const R y[4] = {-d * dpos[0], -d * dpos[1], -d * dpos[2], d};
+      for (int i = 0; i < 4; i++) XtY[i] += sgn * y[i] * weight;
+    }
+    if (std::abs(det4(XtX)) > R(1e-4)) {                                                                       // 251: mpm_reconstruction_guard<3>
+      R r[4];
+      solve4(XtX, XtY, r);
+      rg.near[p] = 1;
+      rg.bdist[p] = r[3] * sc.dx;
+      const R l2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+      if (l2 > R(1e-4)) { const R il = R(1) / std::sqrt(l2); for (int k = 0; k < 3; k++) rg.bnormal[3 * p + k] = r[k] * il; }
+    }
+  }
+}
+
+template <class R> inline bool particle_in_rigid_page(const Scene<R> &sc, const Rigid<R> &rg, const R *x) {
+  int base[3]; R rel[3];
+  base_and_rel(sc, x, base, rel);   // block_op_switch tests the page of the block the particle is SORTED into: its base node's
+  return rigid_page_of_block(rg, base[0] >> 2, base[1] >> 2, base[2] >> 3);
+}
+
+// colour test of block_op_rigid (src/transfer.cpp:416-420, 757-761): true = compatible
+inline bool cdf_compatible(uint32_t node_word, uint32_t pst) {
+  const uint32_t gs = node_word & kTagMask;
+  const uint32_t mask = (gs & pst & kStateMask) >> 1;
+  return (gs & mask) == (pst & mask);
+}
+
+// the 27 dw_w of MPMFastKernel32 (src/kernel.h:168-189): lanes (dw_x w_y w_z, w_x dw_y w_z, w_x w_y dw_z, w_x w_y w_z),
+// dw in world units (shuffle() multiplies by inv_delta_x)
+template <class R> inline void dw_w27(const Scene<R> &sc, const R *pos_grid, R (*out)[4]) {
+  R w[3][3], dw[3][3];
+  for (int d = 0; d < 3; d++) { quadratic_kernel_axis(pos_grid[d], w[d], dw[d]); for (int k = 0; k < 3; k++) dw[d][k] *= sc.inv_dx; }
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int c = 0; c < 3; c++) {
+    R *o = out[a * 9 + b * 3 + c];
+    o[0] = (dw[0][a] * w[1][b]) * w[2][c];
+    o[1] = (w[0][a] * dw[1][b]) * w[2][c];
+    o[2] = (w[0][a] * w[1][b]) * dw[2][c];
+    o[3] = (w[0][a] * w[1][b]) * w[2][c];
+  }
+}
+
+// rasterize_optimized with block_op_switch (src/transfer.cpp:361-581): block_op_rigid for particles of rigid pages
+// (367-463), block_op_normal (p2g above) for the others.
+template <class R> void p2g_coupled(const Scene<R> &sc, Rigid<R> &rg, Particles<R> &P, const std::vector<int64_t> &order, R *grid) {
+  rigid_reset_tmp(rg);
+  std::vector<int64_t> normal, rigid;
+  for (int64_t i : order) (particle_in_rigid_page(sc, rg, P.x + 3 * i) ? rigid : normal).push_back(i);
+  p2g(sc, P, normal, grid);
+  for (int64_t i : rigid) {
+    R *v = P.v + 3 * i;
+    if (sc.particle_gravity) for (int d = 0; d < 3; d++) v[d] = v[d] + sc.gravity[d] * sc.dt;   // 383-385
+    int base[3]; R rel[3];
+    base_and_rel(sc, P.x + 3 * i, base, rel);
+    const R pos[3] = {P.x[3 * i] * sc.inv_dx, P.x[3 * i + 1] * sc.inv_dx, P.x[3 * i + 2] * sc.inv_dx};
+    R k27[27][4];
+    dw_w27(sc, pos, k27);
+    const R mass = P.mass[i];
+    const int g = P.group[i];
+    R binv[9], mv[3], tf[9];
+    for (int k = 0; k < 9; k++) binv[k] = P.b[9 * i + k] * (R(4) * mass);                       // 401
+    for (int d = 0; d < 3; d++) mv[d] = mass * v[d];
+    calculate_force(sc.mat_kind[g], sc.mat_params + g * kMatParams, P.F + 9 * i, P.ps[i], P.vol[i], tf);
+    for (int k = 0; k < 9; k++) tf[k] *= sc.dt;                                                 // 404
+    const uint32_t pst = rg.states[i];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int c = 0; c < 3; c++) {
+      const int ni[3] = {base[0] + a, base[1] + b, base[2] + c};
+      const R dpos[3] = {pos[0] - R(ni[0]), pos[1] - R(ni[1]), pos[2] - R(ni[2])};
+      const size_t node = sc.node(ni[0], ni[1], ni[2]);
+      const R *dw_w = k27[a * 9 + b * 3 + c];
+      const uint32_t word = rg.node_state[node];
+      if (!cdf_compatible(word, pst)) {                                                         // 420-446
+        const int rid = int(word >> kTagBits) - 1;
+        if (rid < 0) continue;
+        const R gp[3] = {sc.dx * R(ni[0]), sc.dx * R(ni[1]), sc.dx * R(ni[2])};
+        R rv[3], proj[3], imp[3];
+        rigid_velocity_at(rg, rid, gp, rv);
+        friction_project(v, rv, rg.bnormal + 3 * i, rg.frictions[2 * rid + ((pst >> (2 * rid)) & 1u)], proj);
+        for (int r = 0; r < 3; r++)
+          imp[r] = mass * dw_w[3] * (v[r] - proj[r]) + (at(tf, r, 0) * dw_w[0] + at(tf, r, 1) * dw_w[1] + at(tf, r, 2) * dw_w[2]);
+        rigid_apply_tmp_impulse(rg, rid, imp, gp);
+        continue;
+      }
+      R *gn = grid + 4 * node;                                                                  // 451-459 (MLSMPM)
+      for (int r = 0; r < 3; r++) {
+        const R ap = mv[r] + (at(binv, r, 0) * dpos[0] + at(binv, r, 1) * dpos[1] + at(binv, r, 2) * dpos[2]);
+        const R st = -(at(tf, r, 0) * dpos[0] + at(tf, r, 1) * dpos[1] + at(tf, r, 2) * dpos[2]) * R(4) * sc.inv_dx;
+        gn[r] += dw_w[3] * (ap + st);
+      }
+      gn[3] += dw_w[3] * mass;
+    }
+  }
+  rigid_apply_tmp(rg);                                                                          // 578-580
+}
+
+// resample_optimized with block_op_switch (src/transfer.cpp:702-970): block_op_rigid (706-835) / block_op_normal (g2p above).
+template <class R> void g2p_coupled(const Scene<R> &sc, Rigid<R> &rg, Particles<R> &P, const std::vector<int64_t> &order, const R *grid) {
+  rigid_reset_tmp(rg);                                                                          // 956-958
+  std::vector<int64_t> normal, rigid;
+  for (int64_t i : order) (particle_in_rigid_page(sc, rg, P.x + 3 * i) ? rigid : normal).push_back(i);
+  g2p(sc, P, normal, grid);
+  for (int64_t i : rigid) {
+    int base[3]; R rel[3];
+    base_and_rel(sc, P.x + 3 * i, base, rel);
+    const R pos[3] = {P.x[3 * i] * sc.inv_dx, P.x[3 * i + 1] * sc.inv_dx, P.x[3 * i + 2] * sc.inv_dx};
+    R k27[27][4];
+    dw_w27(sc, pos, k27);
+    const uint32_t pst = rg.states[i];
+    const R *pv = P.v + 3 * i, *bn = rg.bnormal + 3 * i;
+    R v[3] = {0, 0, 0}, b[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int rigid_id = -1;
+    for (int a = 0; a < 3; a++) for (int bb = 0; bb < 3; bb++) for (int c = 0; c < 3; c++) {
+      const int ni[3] = {base[0] + a, base[1] + bb, base[2] + c};
+      const R dpos[3] = {pos[0] - R(ni[0]), pos[1] - R(ni[1]), pos[2] - R(ni[2])};
+      const size_t node = sc.node(ni[0], ni[1], ni[2]);
+      const R w = k27[a * 9 + bb * 3 + c][3];
+      R gv[3] = {grid[4 * node], grid[4 * node + 1], grid[4 * node + 2]};
+      const uint32_t word = rg.node_state[node];
+      if (!cdf_compatible(word, pst)) {                                                         // 761-785
+        R fake[3] = {pv[0], pv[1], pv[2]}, vg[3] = {0, 0, 0};
+        R friction = 0;
+        const int rid = int(word >> kTagBits) - 1;
+        if (rid >= 0) {
+          const R gp[3] = {R(ni[0]) * sc.dx, R(ni[1]) * sc.dx, R(ni[2]) * sc.dx};
+          rigid_velocity_at(rg, rid, gp, vg);
+          rigid_id = rid;
+          friction = rg.frictions[2 * rid + ((pst >> (2 * rid)) & 1u)];
+        }
+        if (rg.near[i]) {
+          friction_project(pv, vg, bn, friction, fake);
+          const R push = sc.dt * sc.dx * rg.pushing_force;
+          for (int r = 0; r < 3; r++) fake[r] += bn[r] * push;
+        }
+        for (int r = 0; r < 3; r++) gv[r] = fake[r];
+      }
+      for (int r = 0; r < 3; r++) {
+        v[r] = std::fma(gv[r], w, v[r]);                                                        // 788
+        const R wg = w * gv[r];
+        for (int cc = 0; cc < 3; cc++) at(b, r, cc) = std::fma(wg, dpos[cc], at(b, r, cc));     // 793-795
+      }
+    }
+    if (rg.near[i]) {                                                                           // 800-804
+      for (int k = 0; k < 9; k++) P.b[9 * i + k] = 0;
+    } else {                                                                                    // damp_affine_momemtum with zero damping (src/mpm.h:465-469)
+      for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) {
+        const R sym = R(0.5) * (at(b, r, c) + at(b, c, r));
+        at(P.b + 9 * i, r, c) = sym + (at(b, r, c) - sym);
+      }
+    }
+    for (int d = 0; d < 3; d++) P.v[3 * i + d] = v[d];
+    R cdg[9];
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) at(cdg, r, c) = std::fma(sc.dt, at(b, r, c) * (R(-4) * sc.inv_dx), r == c ? R(1) : R(0));   // 810-815
+    const int g = P.group[i];
+    plasticity(sc.mat_kind[g], sc.mat_params + g * kMatParams, cdg, P.F + 9 * i, P.ps[i]);
+    for (int d = 0; d < 3; d++) P.x[3 * i + d] = std::fma(v[d], sc.dt, P.x[3 * i + d]);        // 819
+    if (rg.near[i] && rg.bdist[i] < R(-0.05) * sc.dx && rg.bdist[i] > -sc.dx * R(0.3)) {         // 823-832: position correction
+      R dv[3], imp[3];
+      for (int d = 0; d < 3; d++) { dv[d] = rg.bdist[i] * bn[d] * rg.penalty; P.v[3 * i + d] -= dv[d]; imp[d] = dv[d] * P.mass[i]; }
+      if (rigid_id != -1) rigid_apply_tmp_impulse(rg, rigid_id, imp, P.x + 3 * i);
+    }
+  }
+  rigid_apply_tmp(rg);                                                                          // 967-969
+}
+
+// MPM<3>::substep with rigid bodies (src/mpm.cpp:452-575), without the host-side rigid dynamics (rigidify, articulate,
+// advect_rigid_bodies): one substep at a fixed pose; velocity / angular_velocity return with the impulses of both transfers.
+template <class R>
+void substep_coupled(const Scene<R> &sc, Rigid<R> &rg, Particles<R> &P, uint8_t *alive, R *grid_out, R *grid_rast_out, uint32_t *node_state_out,
+                     R *node_dist_out) {
+  std::vector<R> grid_local;
+  R *grid = grid_out;
+  if (!grid) { grid_local.assign(sc.n_nodes() * 4, R(0)); grid = grid_local.data(); }
+  else std::fill(grid, grid + sc.n_nodes() * 4, R(0));
+  auto order = visit_order(sc, P, alive);
+  rigid_pages(sc, rg);
+  cdf_rasterize(sc, rg);
+  if (node_state_out) std::memcpy(node_state_out, rg.node_state.data(), sizeof(uint32_t) * sc.n_nodes());
+  if (node_dist_out) std::memcpy(node_dist_out, rg.node_dist.data(), sizeof(R) * sc.n_nodes());
+  gather_cdf(sc, rg, P, alive);
+  p2g_coupled(sc, rg, P, order, grid);
+  if (grid_rast_out) std::memcpy(grid_rast_out, grid, sizeof(R) * sc.n_nodes() * 4);
+  grid_update(sc, grid);
+  g2p_coupled(sc, rg, P, order, grid);
+  clear_boundary(sc, P, alive);
+}
+
+// ================================================================================
 // FAST fp32 path: the timed CPU baseline.  Mirrors the *structure* of the reference's
 // optimized path: sort by (block,node) (src/mpm.cpp:770-918), per-block tile cache
 // [6][6][10] (GridCache, src/transfer.cpp:52-156), 8-colour block passes for P2G
@@ -1193,6 +1591,26 @@ template <class R> Scene<R> make_scene(const int *res, R dx, R dt, const R *grav
     Scene<R> sc = make_scene<R>(res, dx, dt, gravity, particle_gravity, mat_kind, mat_params, sdf, friction);                  \
     Particles<R> P{n, x, v, F, b, mass, vol, ps, group};                                                                       \
     substep<R>(sc, P, alive, grid_vel, grid_rast);                                                                             \
+  }                                                                                                                            \
+  /* The same with rigid bodies (CPIC).  Per-body arrays have n_rigid rows (row 0 = background).  */                           \
+  ORACLE_API void oracle_substep_coupled_##SUF(const int *res, R dx, R dt, const R *gravity, int particle_gravity, int n_groups, \
+                                       const int32_t *mat_kind, const R *mat_params, const R *sdf, R friction, int64_t n,      \
+                                       R *x, R *v, R *F, R *b, const R *mass, const R *vol, R *ps, const int32_t *group,       \
+                                       uint8_t *alive, R *grid_rast, R *grid_vel, int n_rigid, const R *r_position,            \
+                                       const R *r_rot, R *r_velocity, R *r_angular_velocity, const R *r_inv_mass,              \
+                                       const R *r_inv_inertia, const R *r_frictions, int64_t n_samples, const R *s_offset,     \
+                                       const R *s_tri, const int32_t *s_rigid, R penalty, R pushing_force, uint32_t *states,   \
+                                       R *bnormal, R *bdist, uint8_t *near, uint32_t *node_state, R *node_dist) {              \
+    (void)n_groups;                                                                                                            \
+    Scene<R> sc = make_scene<R>(res, dx, dt, gravity, particle_gravity, mat_kind, mat_params, sdf, friction);                  \
+    Particles<R> P{n, x, v, F, b, mass, vol, ps, group};                                                                       \
+    Rigid<R> rg;                                                                                                               \
+    rg.n_rigid = n_rigid; rg.position = r_position; rg.rot = r_rot; rg.velocity = r_velocity;                                  \
+    rg.angular_velocity = r_angular_velocity; rg.inv_mass = r_inv_mass; rg.inv_inertia = r_inv_inertia;                        \
+    rg.frictions = r_frictions; rg.n_samples = n_samples; rg.offset = s_offset; rg.tri = s_tri; rg.sample_rigid = s_rigid;     \
+    rg.penalty = penalty; rg.pushing_force = pushing_force; rg.states = states; rg.bnormal = bnormal; rg.bdist = bdist;        \
+    rg.near = near;                                                                                                            \
+    substep_coupled<R>(sc, rg, P, alive, grid_vel, grid_rast, node_state, node_dist);                                          \
   }                                                                                                                            \
   ORACLE_API void oracle_mpm88_advance_##SUF(int n, R dt, R E, R nu, R hardening, R gravity_y, int plastic, int64_t np, R *x,  \
                                              R *v, R *F, R *C, R *Jp, R *grid) {                                               \

@@ -1061,7 +1061,8 @@ constexpr int G2P_CH = 256;  // rows per pipeline stage
 // STORE_B = false skips the apic_b streams (48 B/particle): no kernel reads apic_b — rasterize uses the
 // affine matrix A — so inside mpmb_substep(h, n) only the LAST substep has to leave it behind for the
 // host (downloads, visualize, save).
-template <int BLOCK, bool STORE_B>
+// EXT_MATS = false leaves the elastic / von Mises / visco branches of material_step out (see mpmb_math.cuh).
+template <int BLOCK, bool STORE_B, bool EXT_MATS>
 __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4 *vel, int part, int commit) {
   __shared__ __align__(16) float4 s_vel[2][ARENA];
   __shared__ __align__(16) float4 s_in[2][4][G2P_CH];
@@ -1230,7 +1231,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
         F.m[0] = q4.x; F.m[1] = q4.y; F.m[2] = q4.z; F.m[3] = q4.w; F.m[4] = q5.x; F.m[5] = q5.y; F.m[6] = q5.z; F.m[7] = q5.w; F.m[8] = q6.x;
         float ps = q6.y;
         Mat3 force, A;
-        material_step(mat, cdg, F, ps, vol, force);
+        material_step<EXT_MATS>(mat, cdg, F, ps, vol, force);
         make_affine(force, B, mass, scale, A);
         float3 x = make_float3(fmaf(v.x, P.dt, q0.x), fmaf(v.y, P.dt, q0.y), fmaf(v.z, P.dt, q0.z));  // 951
         uint32_t key = make_key(P, x.x, x.y, x.z);
@@ -1902,7 +1903,7 @@ int mpmb_create(const MpmbConfig *cfg, MpmbHandle *out) {
     int occ = 0;
     cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_DYN_BYTES);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g, P2G_T, P2G_DYN_BYTES) == cudaSuccess && occ > 0) h->grid_p2g = h->num_sms * occ;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<128, true>, 128, 0) == cudaSuccess && occ > 0) h->grid_g2p = h->num_sms * occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p<128, true, true>, 128, 0) == cudaSuccess && occ > 0) h->grid_g2p = h->num_sms * occ;
   }
   // tiles: every tile of the (slab of the) domain can be active
   int64_t cap_tiles = (int64_t)ntot;
@@ -2526,6 +2527,19 @@ int mpmb_rasterize(MpmbHandle h) {
   return MPMB_OK;
 }
 
+// the k_g2p instantiation for this scene: apic_b stored or not, the three later material kinds compiled in or not
+static void launch_g2p(MpmbEngine *h, const View &V, int part, int commit, bool store_b) {
+  bool ext = false;
+  for (int g = 0; g < MPMB_MAX_GROUPS; g++) ext |= h->P.mats[g].kind > MAT_SAND;
+  if (ext) {
+    if (store_b) k_g2p<128, true, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part, commit);
+    else k_g2p<128, false, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part, commit);
+  } else {
+    if (store_b) k_g2p<128, true, false><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part, commit);
+    else k_g2p<128, false, false><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part, commit);
+  }
+}
+
 int mpmb_resample(MpmbHandle h) {
   CHECK_HANDLE(h);
   if (h->stage != 2) return fail(h, MPMB_ERR_STATE, "resample must follow rasterize");
@@ -2535,8 +2549,7 @@ int mpmb_resample(MpmbHandle h) {
   prof_end(h, 1);
   prof_begin(h, 2);
   if (h->cap > 0) {
-    if (h->skip_b) k_g2p<128, false><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0, 1);
-    else k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, 0, 1);
+    launch_g2p(h, V, 0, 1, !h->skip_b);
   }
   h->launches += 2;
   prof_end(h, 1);
@@ -2582,7 +2595,7 @@ int mpmb_resample_part(MpmbHandle h, int32_t part) {
   int nl = 2;
   if (h->cap > 0) {
     k_grid<<<h->num_sms * 8, 256, 0, h->stream>>>(V, h->P, h->vel, part);
-    k_g2p<128, true><<<h->grid_g2p, 128, 0, h->stream>>>(V, h->P, h->vel, part, part == 1 ? 1 : 0);
+    launch_g2p(h, V, part, part == 1 ? 1 : 0, true);
   }
   h->launches += nl;
   prof_end(h, nl);

@@ -640,6 +640,10 @@ __device__ __forceinline__ bool sand_step_series(const Material &mat, const Mat3
 // rasterize for the updated state (src/particles.cpp:216-218,335-337,409-411,463-467,628-637).
 // Both come out of ONE eigen-decomposition: F_new = U S' V^T shares U with the trial state, so
 // -vol P F^T = U diag(-vol tau(S')) U^T needs no second factorisation.
+// EXT = false compiles the elastic / von Mises / visco branches out: k_g2p is instantiated both ways and the host
+// launches the lean one while no material group uses those kinds (measured on a B200, profiles/r02_ab_materials_g2p.log:
+// the three extra branches cost the sand headline 0.004 ms per substep through code layout alone).
+template <bool EXT = true>
 __device__ __forceinline__ void material_step(const Material &mat, const Mat3 &cdg, Mat3 &F, float &ps, float vol, Mat3 &force) {
   if (mat.kind == MAT_WATER) {
     ps *= (cdg.m[0] + cdg.m[4] + cdg.m[8]) - 2.0f;  // j *= tr(cdg) - (dim-1)
@@ -647,7 +651,7 @@ __device__ __forceinline__ void material_step(const Material &mat, const Mat3 &c
     calculate_force(mat, F, ps, vol, force);
     return;
   }
-  if (mat.kind == MAT_VISCO) {
+  if (EXT && mat.kind == MAT_VISCO) {
     visco_step(mat, cdg, F, ps, vol, force);
     return;
   }
@@ -666,7 +670,7 @@ __device__ __forceinline__ void material_step(const Material &mat, const Mat3 &c
   eig_sym3<MPMB_EIG_SWEEPS>(left_strain(Ft), U, e);
   float ratio[3], tau[3];
   bool changed = false;
-  if (mat.kind == MAT_ELASTIC || mat.kind == MAT_VON_MISES) {
+  if (EXT && (mat.kind == MAT_ELASTIC || mat.kind == MAT_VON_MISES)) {
     // Hencky elasticity (src/particles.cpp:800-814) with the von Mises return map (714-734) where asked for
     const float mu = mat.p[0], la = mat.p[1];
     float lsn[3];
