@@ -228,6 +228,53 @@ int mpmb_resample_part(MpmbHandle h, int32_t part);
  * Valid between mpmb_rasterize and the next mpmb_sort_particles_and_populate_grid.                 */
 int mpmb_download_grid(MpmbHandle h, int32_t which, float *dense4);
 
+/* ------------------------------------------------------------------------------ rigid bodies (CPIC) */
+/* Two-way coupling with rigid bodies as the reference's optimized path does it.  On the device:
+ * update_rigid_page_map (src/mpm.cpp:1026-1076), rasterize_rigid_boundary and gather_cdf (src/rigid_transfer.cpp:18-113,
+ * 120-274) and the block_op_rigid branches of rasterize_optimized / resample_optimized (src/transfer.cpp:367-463, 706-835),
+ * selected per 4x4x8-node page exactly as block_op_switch does.  On the host, as in the reference: the bodies themselves
+ * (RigidBody: integration, scripted motion, rigid-rigid collisions, articulation — src/mpm_rigid_body.cpp:252-330 call into
+ * the reference's un-vendored core for these).  Per substep the host hands over poses and velocities and reads the
+ * velocities back:
+ *     mpmb_set_rigid_state -> mpmb_substep(h, 1) -> mpmb_get_rigid_state -> host: advect_rigid_bodies
+ * (mpmb_substep(h, n > 1) keeps the pose fixed over the n substeps.)  CUDA-graph replay is off while bodies are present.
+ * Single-GPU engines only (world == 1).
+ * What the device assumes of the core's RigidBody (it cannot be read here):
+ *   get_velocity_at(p) = velocity + angular_velocity x (p - position);
+ *   apply_tmp_impulse(j, p): tmp_velocity += inv_mass j, tmp_angular_velocity += inv_inertia ((p - position) x j);
+ *   apply_tmp_velocity(): velocity += tmp_velocity, angular_velocity += tmp_angular_velocity (after each transfer);
+ *   get_mesh_to_world() = get_centroid_to_world() = x -> position + rot x;
+ *   world_to_element(e) = [v1 - v0, v2 - v0, n]^-1 with n the unit normal (v1 - v0) x (v2 - v0).                      */
+typedef struct MpmbRigidBody {
+  float position[3];          /* centre of mass, world units                                  */
+  float rot[9];               /* mesh -> world linear part, column-major                      */
+  float velocity[3];
+  float angular_velocity[3];
+  float inv_mass;             /* 0: scripted / infinite mass (set_infinity_mass)               */
+  float inv_inertia[9];       /* world-space inverse inertia, column-major; 0: scripted rotation */
+  float frictions[2];         /* RigidBody::frictions: [side of the particle's colour bit]     */
+} MpmbRigidBody;
+/* Replaces the RigidBoundaryParticles of MPM<3>::add_rigid_particle (src/mpm_rigid_body.cpp:137-250,
+ * src/boundary_particle.h): sample s belongs to body rigid_id[s] (the index into MPM::rigids: 1..n_bodies-1; 0 is the
+ * background body, src/mpm.cpp:72-74), sits at `offset` in the body's centroid frame and carries its triangle
+ * `untransformed_element` (v0, v1, v2; 9 floats).  n_samples = 0 switches the coupling off.  n_bodies <= 12
+ * (GridState::max_num_rigid_bodies, src/mpm_fwd.h:79).                                                                 */
+int mpmb_set_rigid_samples(MpmbHandle h, int32_t n_bodies, int64_t n_samples, const float *offset3, const float *tri9,
+                           const int32_t *rigid_id);
+/* `penalty` (src/mpm.cpp:35, default 0) and `pushing_force` (src/mpm.cpp:40, default 20000).                          */
+int mpmb_set_rigid_coupling(MpmbHandle h, float penalty, float pushing_force);
+/* Poses and velocities of all n_bodies bodies (entry 0 ignored) for the next substep(s).                              */
+int mpmb_set_rigid_state(MpmbHandle h, int32_t n_bodies, const MpmbRigidBody *bodies);
+/* The same records with velocity / angular_velocity as the two transfers left them (synchronises).                    */
+int mpmb_get_rigid_state(MpmbHandle h, int32_t n_bodies, MpmbRigidBody *bodies);
+/* MPMParticle::states (src/particles.h) by particle id - id_base: set (default 0 for uploaded particles) / read together
+ * with boundary_normal, boundary_distance and near_boundary_ of the last substep.  Any pointer may be NULL.            */
+int mpmb_set_particle_states(MpmbHandle h, int64_t n, const uint32_t *states);
+int mpmb_get_particle_cdf(MpmbHandle h, int64_t n, uint32_t *states, float *normal3, float *distance, uint8_t *near_boundary);
+/* Parity/debug: the node colour field of the last substep, dense [res0+1][res1+1][res2+1]: GridState::states
+ * (tags | (rigid id + 1) << 24) and GridState::distance (world units).                                                 */
+int mpmb_download_cdf(MpmbHandle h, uint32_t *node_states, float *node_distance);
+
 /* ------------------------------------------------------------------------------ profiling */
 #define MPMB_N_STAGES 5 /* 0 sort+tiles, 1 P2G, 2 G2P, 3 exchange pack/unpack, 4 grid update */
 /* When enabled, CUDA events bracket every stage on the engine's stream.                          */

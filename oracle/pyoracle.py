@@ -147,6 +147,47 @@ def substep(scene, state, dtype=np.float64, want_grids=True):
     return st, grid_rast, grid_vel
 
 
+def substep_coupled(scene, state, rigid, dtype=np.float64):
+    """One reference substep WITH rigid bodies (CPIC): rigid pages, CDF rasterisation, gather_cdf, block_op_rigid transfers
+    (oracle/mpm_oracle.cpp, section "CPIC rigid-coupled path"), at a fixed rigid pose — the host-side rigid dynamics
+    (rigidify / articulate / advect_rigid_bodies) are not part of it.
+
+    rigid: dict(position[nr,3], rot[nr,9] col-major, velocity[nr,3], angular_velocity[nr,3], inv_mass[nr],
+                inv_inertia[nr,9] world-space col-major, frictions[nr,2]  (row 0 = the background body, unused),
+                sample_offset[ns,3], sample_tri[ns,9], sample_rigid[ns] int32, penalty, pushing_force)
+    state additionally carries "states"[N] uint32 (MPMParticle::states; zeros if absent).
+    Returns (new_state, grid_rast, grid_vel, rigid_out, cdf) with new_state["states"/"bnormal"/"bdist"/"near"],
+    rigid_out = dict(velocity, angular_velocity) after both transfers, cdf = dict(node_state, node_dist)."""
+    res = np.asarray(scene["res"], np.int32)
+    st = {k: np.ascontiguousarray(np.asarray(state[k], dtype)).copy() for k in ("x", "v", "F", "b", "mass", "vol", "ps")}
+    st["group"] = np.ascontiguousarray(state["group"], np.int32)
+    n = len(st["mass"])
+    st["alive"] = np.ascontiguousarray(state.get("alive", np.ones(n, np.uint8)), np.uint8).copy()
+    st["states"] = np.ascontiguousarray(state.get("states", np.zeros(n, np.uint32)), np.uint32).copy()
+    st["bnormal"], st["bdist"], st["near"] = np.zeros((n, 3), dtype), np.zeros(n, dtype), np.zeros(n, np.uint8)
+    mk = np.ascontiguousarray(scene["mat_kind"], np.int32)
+    mp = np.ascontiguousarray(scene["mat_params"], dtype)
+    sdf = scene.get("sdf")
+    sdf = None if sdf is None else np.ascontiguousarray(sdf, dtype)
+    g = np.ascontiguousarray(scene["gravity"], dtype)
+    nn = tuple(int(r) + 1 for r in res)
+    grid_rast, grid_vel = np.zeros(nn + (4,), dtype), np.zeros(nn + (4,), dtype)
+    node_state, node_dist = np.zeros(nn, np.uint32), np.zeros(nn, dtype)
+    r = {k: np.ascontiguousarray(np.asarray(rigid[k], dtype)).copy() for k in ("position", "rot", "velocity", "angular_velocity", "inv_mass",
+                                                                             "inv_inertia", "frictions", "sample_offset", "sample_tri")}
+    sr = np.ascontiguousarray(rigid["sample_rigid"], np.int32)
+    sc = _scalar(dtype)
+    getattr(lib(), "oracle_substep_coupled_" + _suf(dtype))(
+        _p(res), sc(scene["dx"]), sc(scene["dt"]), _p(g), C.c_int(int(scene.get("particle_gravity", 1))), C.c_int(len(mk)),
+        _p(mk), _p(mp), _p(sdf), sc(scene.get("friction", 0.0)), C.c_int64(n),
+        _p(st["x"]), _p(st["v"]), _p(st["F"]), _p(st["b"]), _p(st["mass"]), _p(st["vol"]), _p(st["ps"]), _p(st["group"]),
+        _p(st["alive"]), _p(grid_rast), _p(grid_vel), C.c_int(len(r["inv_mass"])), _p(r["position"]), _p(r["rot"]), _p(r["velocity"]),
+        _p(r["angular_velocity"]), _p(r["inv_mass"]), _p(r["inv_inertia"]), _p(r["frictions"]), C.c_int64(len(sr)), _p(r["sample_offset"]),
+        _p(r["sample_tri"]), _p(sr), sc(rigid.get("penalty", 0.0)), sc(rigid.get("pushing_force", 20000.0)), _p(st["states"]),
+        _p(st["bnormal"]), _p(st["bdist"]), _p(st["near"]), _p(node_state), _p(node_dist))
+    return st, grid_rast, grid_vel, dict(velocity=r["velocity"], angular_velocity=r["angular_velocity"]), dict(node_state=node_state, node_dist=node_dist)
+
+
 class FastOracle:
     """fp32 OpenMP restatement of the reference's optimized CPU path (the timed CPU baseline)."""
 

@@ -27,6 +27,8 @@ EXPORTS = [
     "mpmb_resample_part", "mpmb_download_grid",
     "mpmb_set_profiling", "mpmb_get_profile", "mpmb_get_counters", "mpmb_get_ordering_stats",
     "mpmb_halo_bytes", "mpmb_halo_pack", "mpmb_halo_unpack", "mpmb_migrate_bytes", "mpmb_migrate_pack", "mpmb_migrate_unpack",
+    "mpmb_set_rigid_samples", "mpmb_set_rigid_coupling", "mpmb_set_rigid_state", "mpmb_get_rigid_state", "mpmb_set_particle_states",
+    "mpmb_get_particle_cdf", "mpmb_download_cdf",
     "mpmb_xchg_buffer", "mpmb_xchg_ipc_handle", "mpmb_xchg_connect", "mpmb_halo_send", "mpmb_halo_recv", "mpmb_migrate_send", "mpmb_migrate_recv",
 ]
 
@@ -62,6 +64,11 @@ class MpmbAosLayout(C.Structure):
 
 class MpmbShape(C.Structure):
     _fields_ = [("kind", C.c_int32), ("inside_out", C.c_int32), ("p", C.c_float * 6)]
+
+
+class MpmbRigidBody(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("rot", C.c_float * 9), ("velocity", C.c_float * 3), ("angular_velocity", C.c_float * 3),
+                ("inv_mass", C.c_float), ("inv_inertia", C.c_float * 9), ("frictions", C.c_float * 2)]
 
 
 SHAPE_PLANE, SHAPE_SPHERE, SHAPE_CUBOID = range(3)
@@ -279,6 +286,54 @@ class Engine:
     # --- hot path
     def substep(self, nsub=1):
         self._check(self.L.mpmb_substep(self.h, C.c_int32(nsub)))
+
+    # ---- rigid bodies (CPIC): `rigid` is the dict scenes.make_rigid builds (row 0 = the background body)
+    def _rigid_records(self, rigid):
+        nb = len(rigid["inv_mass"])
+        arr = (MpmbRigidBody * nb)()
+        for b in range(nb):
+            arr[b].position[:] = [float(v) for v in rigid["position"][b]]
+            arr[b].rot[:] = [float(v) for v in np.asarray(rigid["rot"][b]).reshape(9)]
+            arr[b].velocity[:] = [float(v) for v in rigid["velocity"][b]]
+            arr[b].angular_velocity[:] = [float(v) for v in rigid["angular_velocity"][b]]
+            arr[b].inv_mass = float(rigid["inv_mass"][b])
+            arr[b].inv_inertia[:] = [float(v) for v in np.asarray(rigid["inv_inertia"][b]).reshape(9)]
+            arr[b].frictions[:] = [float(v) for v in rigid["frictions"][b]]
+        return nb, arr
+
+    def set_rigid(self, rigid):
+        """Boundary samples + coupling constants + the current state of every body."""
+        off, tri = _f32(rigid["sample_offset"], (-1, 3)), _f32(rigid["sample_tri"], (-1, 9))
+        rid = np.ascontiguousarray(rigid["sample_rigid"], np.int32)
+        self._check(self.L.mpmb_set_rigid_samples(self.h, C.c_int32(len(rigid["inv_mass"])), C.c_int64(len(rid)), _ptr(off), _ptr(tri), _ptr(rid)))
+        if len(rid):
+            self._check(self.L.mpmb_set_rigid_coupling(self.h, C.c_float(rigid.get("penalty", 0.0)), C.c_float(rigid.get("pushing_force", 20000.0))))
+            self.set_rigid_state(rigid)
+
+    def set_rigid_state(self, rigid):
+        nb, arr = self._rigid_records(rigid)
+        self._check(self.L.mpmb_set_rigid_state(self.h, C.c_int32(nb), arr))
+
+    def get_rigid_state(self, n_bodies):
+        arr = (MpmbRigidBody * n_bodies)()
+        self._check(self.L.mpmb_get_rigid_state(self.h, C.c_int32(n_bodies), arr))
+        return dict(velocity=np.array([list(a.velocity) for a in arr], np.float32), angular_velocity=np.array([list(a.angular_velocity) for a in arr], np.float32),
+                    position=np.array([list(a.position) for a in arr], np.float32))
+
+    def set_particle_states(self, states):
+        st = np.ascontiguousarray(states, np.uint32)
+        self._check(self.L.mpmb_set_particle_states(self.h, C.c_int64(len(st)), _ptr(st)))
+
+    def get_particle_cdf(self, n):
+        out = dict(states=np.zeros(n, np.uint32), bnormal=np.zeros((n, 3), np.float32), bdist=np.zeros(n, np.float32), near=np.zeros(n, np.uint8))
+        self._check(self.L.mpmb_get_particle_cdf(self.h, C.c_int64(n), _ptr(out["states"]), _ptr(out["bnormal"]), _ptr(out["bdist"]), _ptr(out["near"])))
+        return out
+
+    def download_cdf(self):
+        nn = tuple(r + 1 for r in self.res)
+        st, d = np.zeros(nn, np.uint32), np.zeros(nn, np.float32)
+        self._check(self.L.mpmb_download_cdf(self.h, _ptr(st), _ptr(d)))
+        return dict(node_state=st, node_dist=d)
 
     def sort_particles_and_populate_grid(self):
         self._check(self.L.mpmb_sort_particles_and_populate_grid(self.h))

@@ -122,6 +122,7 @@ struct View {  // raw pointers handed to kernels
   Counters *cnt;
   int cap_tiles;
   int cap_particles;
+  const unsigned char *rigid_flag;  // [slot] 1 = the tile lies in a rigid page: k_g2p leaves it to k_g2p_rigid (null: no rigid bodies)
 };
 
 // ------------------------------------------------------------------------------ helpers
@@ -1085,6 +1086,8 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
     it.rb = 0; it.first = 1;
     if (part != 0)  // next tile of this CTA's round-robin share that belongs to the part
       while (slot < n_tiles && !tile_in_part(P, V.meta[slot].tile, part)) slot += (int)gridDim.x;
+    if (V.rigid_flag)  // CPIC scenes: tiles of rigid pages belong to k_g2p_rigid
+      while (slot < n_tiles && V.rigid_flag[slot]) slot += (int)gridDim.x;
     it.slot = slot;
     if (slot < n_tiles) it.tm = V.meta[slot];
     else {
@@ -1278,6 +1281,480 @@ __global__ void __launch_bounds__(BLOCK, 5) k_g2p(View V, Params P, const float4
         c->g2p_done = 0;
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------ CPIC rigid coupling
+// Replaces, for scenes with rigid bodies: update_rigid_page_map (src/mpm.cpp:1026-1076), rasterize_rigid_boundary and
+// gather_cdf (src/rigid_transfer.cpp:18-113, 120-274) and the block_op_rigid branches of rasterize_optimized /
+// resample_optimized (src/transfer.cpp:367-463, 706-835).  The rigid bodies themselves (RigidBody, its integrator, the
+// rigid-rigid solver, articulation) belong to the reference's un-vendored core and stay on the host: the engine takes poses and
+// velocities (mpmb_set_rigid_state), applies the impulses of both transfers as apply_tmp_impulse / apply_tmp_velocity would
+// (assumptions stated in include/mpmb.h) and hands the velocities back (mpmb_get_rigid_state).
+// Layout: RigidBoundaryParticles are NOT MPM particles here but a sample list (anchor offset + untransformed triangle + body);
+// node colour data is two dense node arrays (a 64-bit key (distance bits, body) taken with atomicMin, the tags with atomicOr),
+// cleared sample by sample; particle colour state is kept by particle id.  Tiles whose 4x4x8 page is a rigid page are
+// skipped by k_g2p and processed by k_g2p_rigid; their arenas are rewritten by k_p2g_rigid after k_p2g (which still provides
+// the output rows).  This is the reference's slow path too: simple kernels, shared-memory float atomics, no pipelining.
+constexpr int RIGID_MAX = 12;                     // GridState::max_num_rigid_bodies (src/mpm_fwd.h:79)
+constexpr uint32_t CDF_STATE_MASK = 0xAAAAAAAAu;  // state_mask (src/mpm.h:36)
+constexpr uint32_t CDF_TAG_MASK = 0x00FFFFFFu;    // GridState::tag_mask
+constexpr unsigned long long CDF_NO_KEY = ~0ull;
+
+struct RigidDev {  // one body on the device
+  float pos[3], rot[9], vel[3], ang[3], inv_mass, inv_inertia[9], fric[2];
+  float acc[6];    // impulses of the running transfer: sum j, sum (p - pos) x j
+};
+struct RigidView {
+  RigidDev *bodies;
+  int n_bodies;
+  int n_samples;
+  const float *s_offset, *s_tri;
+  const int *s_rigid;
+  int *s_base;                     // packed base node of each sample's last rasterisation (-1: none), for the clear
+  unsigned long long *node_key;    // (distance bits << 32) | (body + 1); CDF_NO_KEY = no rigid boundary near this node
+  uint32_t *node_tags;             // GridState tag bits
+  unsigned char *page;             // rigid_page_map over 4x4x8 blocks
+  int nb[3];
+  unsigned char *tile_flag;        // [slot]
+  uint32_t *p_states;              // MPMParticle::states by particle id - id_base (persists)
+  float4 *p_cdf;                   // (boundary_normal, boundary_distance) of this substep
+  unsigned char *p_near;           // near_boundary_ of this substep
+  uint32_t id_base;
+  int id_cap;
+  float penalty, pushing_force;
+};
+
+__device__ __forceinline__ uint32_t cdf_word(const RigidView &R, size_t node) {  // GridState::states: tags | (body + 1) << 24
+  const unsigned long long k = R.node_key[node];
+  return (R.node_tags[node] & CDF_TAG_MASK) | (k == CDF_NO_KEY ? 0u : ((uint32_t)k & 0xffu) << 24);
+}
+__device__ __forceinline__ float cdf_dist_world(const RigidView &R, size_t node, float dx) {  // GridState::distance after line 77-78
+  const unsigned long long k = R.node_key[node];
+  return k == CDF_NO_KEY ? 0.f : __uint_as_float((uint32_t)(k >> 32)) * dx;
+}
+__device__ __forceinline__ bool cdf_compatible(uint32_t word, uint32_t pst) {  // src/transfer.cpp:416-420
+  const uint32_t gs = word & CDF_TAG_MASK;
+  const uint32_t mask = (gs & pst & CDF_STATE_MASK) >> 1;
+  return (gs & mask) == (pst & mask);
+}
+__device__ __forceinline__ float3 rigid_to_world(const RigidDev &b, const float *l) {
+  return make_float3(b.pos[0] + (b.rot[0] * l[0] + b.rot[3] * l[1] + b.rot[6] * l[2]), b.pos[1] + (b.rot[1] * l[0] + b.rot[4] * l[1] + b.rot[7] * l[2]),
+                     b.pos[2] + (b.rot[2] * l[0] + b.rot[5] * l[1] + b.rot[8] * l[2]));
+}
+__device__ __forceinline__ float3 rigid_velocity_at(const RigidDev &b, float3 p) {  // velocity + angular_velocity x (p - position)
+  const float dx = p.x - b.pos[0], dy = p.y - b.pos[1], dz = p.z - b.pos[2];
+  return make_float3(b.vel[0] + (b.ang[1] * dz - b.ang[2] * dy), b.vel[1] + (b.ang[2] * dx - b.ang[0] * dz), b.vel[2] + (b.ang[0] * dy - b.ang[1] * dx));
+}
+// apply_tmp_impulse: into six accumulators (shared or global); the division by mass / inertia happens in k_rigid_apply
+__device__ __forceinline__ void rigid_add_impulse(float *acc, const RigidDev &b, float3 j, float3 p) {
+  const float dx = p.x - b.pos[0], dy = p.y - b.pos[1], dz = p.z - b.pos[2];
+  atomicAdd(acc + 0, j.x); atomicAdd(acc + 1, j.y); atomicAdd(acc + 2, j.z);
+  atomicAdd(acc + 3, dy * j.z - dz * j.y); atomicAdd(acc + 4, dz * j.x - dx * j.z); atomicAdd(acc + 5, dx * j.y - dy * j.x);
+}
+// friction_project (src/mpm_fwd.h:25-57) against a moving base
+__device__ __forceinline__ float3 friction_project_rel(float3 v, float3 base, float3 n, float friction) {
+  const float3 r = friction_project0(make_float3(v.x - base.x, v.y - base.y, v.z - base.z), n, friction);
+  return make_float3(r.x + base.x, r.y + base.y, r.z + base.z);
+}
+__device__ __forceinline__ int pack_base(int bx, int by, int bz) { return (bx << 20) | (by << 10) | bz; }   // node coordinates < 1024
+
+// nodes of the previous rasterisation back to "no boundary"
+__global__ void k_cdf_clear(RigidView R, Params P) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= R.n_samples) return;
+  const int pb = R.s_base[s];
+  if (pb < 0) return;
+  const int bx = pb >> 20, by = (pb >> 10) & 1023, bz = pb & 1023;
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int c = 0; c < 3; c++) {
+    const int i = bx + a, j = by + b, k = bz + c;
+    if (i >= P.nnode[0] || j >= P.nnode[1] || k >= P.nnode[2]) continue;
+    const size_t node = ((size_t)i * P.nnode[1] + j) * P.nnode[2] + k;
+    R.node_key[node] = CDF_NO_KEY;
+    R.node_tags[node] = 0u;
+  }
+}
+
+// update_rigid_page_map + rasterize_rigid_boundary, one thread per RigidBoundaryParticle
+__global__ void k_cdf_raster(RigidView R, Params P) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= R.n_samples) return;
+  const int id = R.s_rigid[s];
+  const RigidDev &B = R.bodies[id];
+  const float3 pos = rigid_to_world(B, R.s_offset + 3 * s);   // align_with_rigid_body (src/boundary_particle.h:48-53)
+  int bx, by, bz;
+  float rr;
+  base_rel(pos.x, P.inv_dx, bx, rr);
+  base_rel(pos.y, P.inv_dx, by, rr);
+  base_rel(pos.z, P.inv_dx, bz, rr);
+  if (bx < 0 || by < 0 || bz < 0 || bx + 2 >= P.nnode[0] || by + 2 >= P.nnode[1] || bz + 2 >= P.nnode[2]) { R.s_base[s] = -1; return; }
+  R.s_base[s] = pack_base(bx, by, bz);
+  // page of the block the particle is sorted into, and (src/mpm.cpp:1062: the range test is on the OFFSET) its {0,1}^3 upper neighbours
+  for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+    const int x = (bx >> 2) + i, y = (by >> 2) + j, z = (bz >> 3) + k;
+    if (x < R.nb[0] && y < R.nb[1] && z < R.nb[2]) R.page[((size_t)x * R.nb[1] + y) * R.nb[2] + z] = 1;
+  }
+  const float3 v0 = rigid_to_world(B, R.s_tri + 9 * s), v1 = rigid_to_world(B, R.s_tri + 9 * s + 3), v2 = rigid_to_world(B, R.s_tri + 9 * s + 6);
+  // world_to_element: [v1 - v0, v2 - v0, n]^-1
+  Mat3 M, Mi;
+  const float e1[3] = {v1.x - v0.x, v1.y - v0.y, v1.z - v0.z}, e2[3] = {v2.x - v0.x, v2.y - v0.y, v2.z - v0.z};
+  float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+  const float nl = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  for (int k = 0; k < 3; k++) { n[k] /= nl; M(k, 0) = e1[k]; M(k, 1) = e2[k]; M(k, 2) = n[k]; }
+  {
+    const float d = det3(M), idet = 1.0f / d;
+    Mi(0, 0) = (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) * idet; Mi(0, 1) = (M(0, 2) * M(2, 1) - M(0, 1) * M(2, 2)) * idet; Mi(0, 2) = (M(0, 1) * M(1, 2) - M(0, 2) * M(1, 1)) * idet;
+    Mi(1, 0) = (M(1, 2) * M(2, 0) - M(1, 0) * M(2, 2)) * idet; Mi(1, 1) = (M(0, 0) * M(2, 2) - M(0, 2) * M(2, 0)) * idet; Mi(1, 2) = (M(0, 2) * M(1, 0) - M(0, 0) * M(1, 2)) * idet;
+    Mi(2, 0) = (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0)) * idet; Mi(2, 1) = (M(0, 1) * M(2, 0) - M(0, 0) * M(2, 1)) * idet; Mi(2, 2) = (M(0, 0) * M(1, 1) - M(0, 1) * M(1, 0)) * idet;
+  }
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int c = 0; c < 3; c++) {
+    const int i = bx + a, j = by + b, k = bz + c;
+    const float d0 = (float)i * P.dx - v0.x, d1 = (float)j * P.dx - v0.y, d2 = (float)k * P.dx - v0.z;
+    const float c0 = Mi(0, 0) * d0 + Mi(0, 1) * d1 + Mi(0, 2) * d2, c1 = Mi(1, 0) * d0 + Mi(1, 1) * d1 + Mi(1, 2) * d2, c2 = Mi(2, 0) * d0 + Mi(2, 1) * d1 + Mi(2, 2) * d2;
+    if (!(0.f <= c0 && 0.f <= c1 && c0 + c1 <= 1.f)) continue;                          // src/rigid_transfer.cpp:50-53
+    const float dist = fabsf(c2) * P.inv_dx;                                              // 43, 60
+    const size_t node = ((size_t)i * P.nnode[1] + j) * P.nnode[2] + k;
+    // 65-69 under the node's lock: the nearest body wins (a tie goes to the smaller id here, to whoever came first there)
+    atomicMin(&R.node_key[node], ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(id + 1));
+    atomicOr(&R.node_tags[node], (uint32_t)(2 + (c2 < 0.f ? 1 : 0)) << (id * 2));     // 73-74
+  }
+}
+
+__global__ void k_rigid_tile_flags(View V, Params P, RigidView R) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= V.cnt->n_tiles) return;
+  const TileMeta tm = V.meta[slot];
+  MPMB_TILE_XYZ(P, tm, tx, ty, tz);
+  R.tile_flag[slot] = R.page[((size_t)tx * R.nb[1] + ty) * R.nb[2] + (tz >> 1)];   // tile (4x4x4 nodes) -> page (4x4x8 nodes)
+}
+
+__device__ __forceinline__ float det4(const float *m) {  // m[c*4+r]
+  float det = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    int cc[3], k = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (j != c) cc[k++] = j;
+#define A4(r, c_) m[(c_) * 4 + (r)]
+    const float minor = A4(1, cc[0]) * (A4(2, cc[1]) * A4(3, cc[2]) - A4(2, cc[2]) * A4(3, cc[1])) - A4(1, cc[1]) * (A4(2, cc[0]) * A4(3, cc[2]) - A4(2, cc[2]) * A4(3, cc[0])) +
+                        A4(1, cc[2]) * (A4(2, cc[0]) * A4(3, cc[1]) - A4(2, cc[1]) * A4(3, cc[0]));
+    det += ((c & 1) ? -1.f : 1.f) * A4(0, c) * minor;
+#undef A4
+  }
+  return det;
+}
+
+// gather_cdf (src/rigid_transfer.cpp:120-274): one thread per storage row that holds a live particle
+__global__ void __launch_bounds__(128) k_gather_cdf(View V, Params P, RigidView R) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= V.cnt->n_store) return;
+  if (V.keys[row] >= (uint32_t)P.ntiles_total) return;   // dead or migrating
+  const float4 q0 = V.q[0][row];
+  const uint32_t id = (__float_as_uint(V.q[6][row].w) & TAG_ID_MASK) - R.id_base;
+  if (id >= (uint32_t)R.id_cap) { atomicOr(&V.cnt->error, DEVERR_BAD_INPUT); return; }
+  R.p_cdf[id] = make_float4(0.f, 0.f, 0.f, 0.f);   // 138-140
+  R.p_near[id] = 0;
+  const float X = __fmul_rn(q0.x, P.inv_dx), Y = __fmul_rn(q0.y, P.inv_dx), Z = __fmul_rn(q0.z, P.inv_dx);
+  {  // 142-146: the page of the particle's CELL
+    const int cx = (int)X >> 2, cy = (int)Y >> 2, cz = (int)Z >> 3;
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= R.nb[0] || cy >= R.nb[1] || cz >= R.nb[2] || !R.page[((size_t)cx * R.nb[1] + cy) * R.nb[2] + cz]) return;
+  }
+  int bx, by, bz;
+  float rx, ry, rz;
+  base_rel(q0.x, P.inv_dx, bx, rx);
+  base_rel(q0.y, P.inv_dx, by, ry);
+  base_rel(q0.z, P.inv_dx, bz, rz);
+  float wx[3], wy[3], wz[3];
+  bspline_weights(rx, wx);
+  bspline_weights(ry, wy);
+  bspline_weights(rz, wz);
+  uint32_t pst = R.p_states[id];
+  uint32_t words[27];
+  uint32_t all_b = 0;
+  for (int n = 0; n < 27; n++) {
+    const size_t node = ((size_t)(bx + n / 9) * P.nnode[1] + (by + (n / 3) % 3)) * P.nnode[2] + (bz + n % 3);
+    words[n] = cdf_word(R, node);
+    all_b |= words[n] & CDF_TAG_MASK & CDF_STATE_MASK;                                   // 155-159
+  }
+  pst &= (all_b + (all_b >> 1));                                                         // 162
+  uint32_t to_add = all_b & ~pst;                                                        // 164
+  while (to_add) {
+    const uint32_t bit = to_add & (0u - to_add);
+    to_add ^= bit;
+    float wd0 = 0.f, wd1 = 0.f;
+    for (int n = 0; n < 27; n++) {
+      if ((words[n] >> 24) == 0u) continue;                                              // 182-184
+      const size_t node = ((size_t)(bx + n / 9) * P.nnode[1] + (by + (n / 3) % 3)) * P.nnode[2] + (bz + n % 3);
+      const float d = cdf_dist_world(R, node, P.dx) * P.inv_dx;
+      const float w = (wx[n / 9] * wy[(n / 3) % 3]) * wz[n % 3];
+      if (words[n] & CDF_TAG_MASK & bit) { if (words[n] & (bit >> 1)) wd1 += d * w; else wd0 += d * w; }   // 195-198
+    }
+    if (wd0 + wd1 > 1e-7f) pst |= bit | ((bit >> 1) * (uint32_t)(wd0 < wd1));           // 200-205
+  }
+  R.p_states[id] = pst;
+  if (pst == 0u) return;
+  float XtX[16], XtY[4];
+  for (int k = 0; k < 16; k++) XtX[k] = 0.f;
+  for (int k = 0; k < 4; k++) XtY[k] = 0.f;
+  for (int n = 0; n < 27; n++) {
+    if ((words[n] >> 24) == 0u) continue;                                                // 217-219
+    const uint32_t gs = words[n] & CDF_TAG_MASK;
+    if (gs == 0u) continue;
+    const uint32_t mask = (gs & pst & CDF_STATE_MASK) >> 1;
+    float sgn;
+    if ((gs & mask) == (pst & mask)) sgn = 1.f;                                          // 232-236: same colour
+    else {
+      const uint32_t diff = (gs & mask) ^ (pst & mask);                                  // 239-243: exactly one colour differs
+      if (diff > 0u && (diff & (diff - 1u)) == 0u) sgn = -1.f; else continue;
+    }
+    const int a = n / 9, b = (n / 3) % 3, c = n % 3;
+    const size_t node = ((size_t)(bx + a) * P.nnode[1] + (by + b)) * P.nnode[2] + (bz + c);
+    const float d = cdf_dist_world(R, node, P.dx) * P.inv_dx;
+    const float w = (wx[a] * wy[b]) * wz[c];
+    const float xp[4] = {-(rx - (float)a), -(ry - (float)b), -(rz - (float)c), 1.f};   // (-dpos, 1)
+    for (int i = 0; i < 4; i++) {
+      for (int j = 0; j < 4; j++) XtX[j * 4 + i] += xp[i] * xp[j] * w;
+      XtY[i] += sgn * (d * xp[i]) * w;                                                   // (-d dpos, d) resp. its negative
+    }
+  }
+  if (fabsf(det4(XtX)) > 1e-4f) {                                                        // 251: mpm_reconstruction_guard<3>
+    // inversed(XtX) * XtY by Gaussian elimination with partial pivoting
+    float A[4][5];
+    for (int r = 0; r < 4; r++) { for (int c = 0; c < 4; c++) A[r][c] = XtX[c * 4 + r]; A[r][4] = XtY[r]; }
+    for (int c = 0; c < 4; c++) {
+      int pv = c;
+      for (int r = c + 1; r < 4; r++) if (fabsf(A[r][c]) > fabsf(A[pv][c])) pv = r;
+      for (int k = 0; k < 5; k++) { const float t = A[c][k]; A[c][k] = A[pv][k]; A[pv][k] = t; }
+      for (int r = c + 1; r < 4; r++) { const float f = A[r][c] / A[c][c]; for (int k = c; k < 5; k++) A[r][k] -= f * A[c][k]; }
+    }
+    float sol[4];
+    for (int r = 3; r >= 0; r--) { float sum = A[r][4]; for (int c = r + 1; c < 4; c++) sum -= A[r][c] * sol[c]; sol[r] = sum / A[r][r]; }
+    R.p_near[id] = 1;
+    const float l2 = sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2];
+    float4 o = make_float4(0.f, 0.f, 0.f, sol[3] * P.dx);
+    if (l2 > 1e-4f) { const float il = 1.0f / sqrtf(l2); o.x = sol[0] * il; o.y = sol[1] * il; o.z = sol[2] * il; }
+    R.p_cdf[id] = o;
+  }
+}
+
+// Node colour words of a tile's 6x6x6 stencil block into shared memory
+__device__ __forceinline__ void load_tile_words(const RigidView &R, const Params &P, int tx, int ty, int tz, uint32_t *s_word) {
+  for (int n = threadIdx.x; n < ARENA; n += blockDim.x) {
+    const int i = tx * 4 + n / 36, j = ty * 4 + (n / 6) % 6, k = tz * 4 + n % 6;
+    s_word[n] = (i < P.nnode[0] && j < P.nnode[1] && k < P.nnode[2]) ? cdf_word(R, ((size_t)i * P.nnode[1] + j) * P.nnode[2] + k) : 0u;
+  }
+}
+
+// block_op_rigid of rasterize_optimized (src/transfer.cpp:367-463) for the tiles of rigid pages: rewrites the tile's arena
+// (k_p2g ran on it first and provided the output rows).  One CTA per tile, one thread per row, shared float atomics.
+__global__ void __launch_bounds__(128) k_p2g_rigid(View V, Params P, RigidView R) {
+  __shared__ float s_arena[4][ARENA];
+  __shared__ uint32_t s_word[ARENA];
+  __shared__ float s_acc[RIGID_MAX][6];
+  const int tid = threadIdx.x;
+  const int n_tiles = V.cnt->n_tiles;
+    for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
+    if (!R.tile_flag[slot]) continue;
+    const TileMeta tm = V.meta[slot];
+    MPMB_TILE_XYZ(P, tm, tx, ty, tz);
+    for (int n = tid; n < ARENA; n += blockDim.x) { s_arena[0][n] = 0.f; s_arena[1][n] = 0.f; s_arena[2][n] = 0.f; s_arena[3][n] = 0.f; }
+    for (int n = tid; n < RIGID_MAX * 6; n += blockDim.x) (&s_acc[0][0])[n] = 0.f;
+    load_tile_words(R, P, tx, ty, tz, s_word);
+    __syncthreads();
+    const int nrow = tm.run_len + tm.arr_len;
+    for (int g = tid; g < nrow; g += blockDim.x) {
+      const uint32_t row = g < tm.run_len ? (uint32_t)(tm.run_begin + g) : V.arrivals_sorted[tm.arr_off + (g - tm.run_len)];
+      const float4 a0 = V.q[0][row];
+      if (g < tm.run_len && !(a0.w > 0.f)) continue;   // hole
+      const float4 a1 = V.q[1][row], a2 = V.q[2][row], a3 = V.q[3][row];
+      const float4 b0 = V.q[7][row], b1 = V.q[8][row], b2 = V.q[9][row];
+      const float mass = fabsf(a0.w);
+      const uint32_t id = (__float_as_uint(V.q[6][row].w) & TAG_ID_MASK) - R.id_base;
+      const uint32_t pst = id < (uint32_t)R.id_cap ? R.p_states[id] : 0u;
+      const float4 pc = id < (uint32_t)R.id_cap ? R.p_cdf[id] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float3 v = make_float3(a1.x, a1.y, a1.z);
+      if (P.particle_gravity) { v.x += P.gdt[0]; v.y += P.gdt[1]; v.z += P.gdt[2]; }
+      int bx, by, bz;
+      float rx, ry, rz;
+      base_rel(a0.x, P.inv_dx, bx, rx);
+      base_rel(a0.y, P.inv_dx, by, ry);
+      base_rel(a0.z, P.inv_dx, bz, rz);
+      const int lx = bx - tx * 4, ly = by - ty * 4, lz = bz - tz * 4;
+      if ((unsigned)lx >= 4u || (unsigned)ly >= 4u || (unsigned)lz >= 4u) continue;
+      float wx[3], wy[3], wz[3], gx[3], gy[3], gz[3];
+      bspline_weights(rx, wx); bspline_weights(ry, wy); bspline_weights(rz, wz);
+      // dw of MPMKernel<3,2> (src/kernel.h:133-134), in world units (shuffle(): * inv_delta_x)
+      { const float f = rx - 0.5f; gx[0] = (f - 1.0f) * P.inv_dx; gx[1] = (-2.0f * f + 1.0f) * P.inv_dx; gx[2] = f * P.inv_dx; }
+      { const float f = ry - 0.5f; gy[0] = (f - 1.0f) * P.inv_dx; gy[1] = (-2.0f * f + 1.0f) * P.inv_dx; gy[2] = f * P.inv_dx; }
+      { const float f = rz - 0.5f; gz[0] = (f - 1.0f) * P.inv_dx; gz[1] = (-2.0f * f + 1.0f) * P.inv_dx; gz[2] = f * P.inv_dx; }
+      const float A[9] = {a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+      const float bb[9] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x};
+      // dt * calculate_force() back out of the cached affine matrix: A = force * S + apic_b * 4 m, S = -4 dt / dx
+      float tf[9];
+      for (int k = 0; k < 9; k++) tf[k] = (A[k] - bb[k] * (4.0f * mass)) * (-0.25f * P.dx);
+      for (int n = 0; n < 27; n++) {
+        const int a = n / 9, b = (n / 3) % 3, c = n % 3;
+        const int ln = ((lx + a) * 6 + (ly + b)) * 6 + (lz + c);
+        const float w = (wx[a] * wy[b]) * wz[c];
+        const float dpx = rx - (float)a, dpy = ry - (float)b, dpz = rz - (float)c;
+        const uint32_t word = s_word[ln];
+        if (!cdf_compatible(word, pst)) {   // different colour: project against the body instead of writing to the grid (420-446)
+          const int rid = (int)(word >> 24) - 1;
+          if (rid < 0 || rid >= R.n_bodies) continue;
+          const RigidDev &B = R.bodies[rid];
+          const float3 gp = make_float3(P.dx * (float)(bx + a), P.dx * (float)(by + b), P.dx * (float)(bz + c));
+          const float3 rv = rigid_velocity_at(B, gp);
+          const float3 pr = friction_project_rel(v, rv, make_float3(pc.x, pc.y, pc.z), B.fric[(pst >> (2 * rid)) & 1u]);
+          const float dwx = (gx[a] * wy[b]) * wz[c], dwy = (wx[a] * gy[b]) * wz[c], dwz = (wx[a] * wy[b]) * gz[c];
+          const float3 j = make_float3(mass * w * (v.x - pr.x) + (tf[0] * dwx + tf[3] * dwy + tf[6] * dwz), mass * w * (v.y - pr.y) + (tf[1] * dwx + tf[4] * dwy + tf[7] * dwz),
+                                       mass * w * (v.z - pr.z) + (tf[2] * dwx + tf[5] * dwy + tf[8] * dwz));
+          rigid_add_impulse(s_acc[rid], B, j, gp);
+          continue;
+        }
+        atomicAdd(&s_arena[0][ln], w * (mass * v.x + (A[0] * dpx + A[3] * dpy + A[6] * dpz)));   // 451-459
+        atomicAdd(&s_arena[1][ln], w * (mass * v.y + (A[1] * dpx + A[4] * dpy + A[7] * dpz)));
+        atomicAdd(&s_arena[2][ln], w * (mass * v.z + (A[2] * dpx + A[5] * dpy + A[8] * dpz)));
+        atomicAdd(&s_arena[3][ln], w * mass);
+      }
+    }
+    __syncthreads();
+    float4 *out = V.arena + (size_t)slot * ARENA;
+    for (int n = tid; n < ARENA; n += blockDim.x) out[n] = make_float4(s_arena[0][n], s_arena[1][n], s_arena[2][n], s_arena[3][n]);
+    for (int n = tid; n < RIGID_MAX * 6; n += blockDim.x) {
+      const float a = (&s_acc[0][0])[n];
+      if (a != 0.f) atomicAdd(&R.bodies[n / 6].acc[n % 6], a);
+    }
+    __syncthreads();
+  }
+}
+
+// apply_tmp_velocity (src/transfer.cpp:578-580, 967-969): velocity += inv_mass * sum j, angular_velocity += Iw^-1 * sum (p - c) x j
+__global__ void k_rigid_apply(RigidView R) {
+  const int b = threadIdx.x;
+  if (b >= R.n_bodies) return;
+  RigidDev &B = R.bodies[b];
+  for (int k = 0; k < 3; k++) {
+    B.vel[k] += B.inv_mass * B.acc[k];
+    B.ang[k] += B.inv_inertia[k] * B.acc[3] + B.inv_inertia[3 + k] * B.acc[4] + B.inv_inertia[6 + k] * B.acc[5];
+  }
+  for (int k = 0; k < 6; k++) B.acc[k] = 0.f;
+}
+
+// block_op_rigid of resample_optimized (src/transfer.cpp:706-835) + what k_g2p does for the ordering (output rows, keys,
+// movers, stay counts), for the tiles of rigid pages.  Launched BEFORE k_g2p, which commits the substep.
+__global__ void __launch_bounds__(128) k_g2p_rigid(View V, Params P, RigidView R, const float4 *vel) {
+  __shared__ float4 s_vel[ARENA];
+  __shared__ uint32_t s_word[ARENA];
+  __shared__ int s_stay;
+  const int tid = threadIdx.x;
+  const int n_tiles = V.cnt->n_tiles;
+  const float scale = -4.0f * P.inv_dx * P.dt;
+  for (int slot = blockIdx.x; slot < n_tiles; slot += gridDim.x) {
+    if (!R.tile_flag[slot]) continue;
+    const TileMeta tm = V.meta[slot];
+    const int tile = tm.tile;
+    MPMB_TILE_XYZ(P, tm, tx, ty, tz);
+    for (int n = tid; n < ARENA; n += blockDim.x) s_vel[n] = vel[(size_t)slot * ARENA + n];
+    load_tile_words(R, P, tx, ty, tz, s_word);
+    if (tid == 0) s_stay = 0;
+    __syncthreads();
+    const int nrow = tm.run_len + tm.arr_len;
+    int my_stay = 0;
+    for (int g = tid; g < nrow; g += blockDim.x) {
+      const uint32_t row = g < tm.run_len ? (uint32_t)(tm.run_begin + g) : V.arrivals_sorted[tm.arr_off + (g - tm.run_len)];
+      const float4 q0 = V.q[0][row];
+      if (g < tm.run_len && !(q0.w > 0.f)) continue;   // hole
+      const float mass = fabsf(q0.w);
+      const float4 q1 = V.q[1][row], q4 = V.q[4][row], q5 = V.q[5][row], q6 = V.q[6][row];
+      const size_t o = V.outpos[row];
+      if (o >= (size_t)V.cap_particles) { atomicOr(&V.cnt->error, DEVERR_PARTICLE_CAPACITY); continue; }
+      const uint32_t tag = __float_as_uint(q6.w);
+      const uint32_t id = (tag & TAG_ID_MASK) - R.id_base;
+      const bool known = id < (uint32_t)R.id_cap;
+      const uint32_t pst = known ? R.p_states[id] : 0u;
+      const float4 pc = known ? R.p_cdf[id] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool near = known && R.p_near[id];
+      const float3 bn = make_float3(pc.x, pc.y, pc.z);
+      // p.get_velocity() as rasterize left it: the gravity kick is stored back there (src/transfer.cpp:383-385)
+      float3 pv = make_float3(q1.x, q1.y, q1.z);
+      if (P.particle_gravity) { pv.x += P.gdt[0]; pv.y += P.gdt[1]; pv.z += P.gdt[2]; }
+      int bx, by, bz;
+      float rx, ry, rz;
+      base_rel(q0.x, P.inv_dx, bx, rx);
+      base_rel(q0.y, P.inv_dx, by, ry);
+      base_rel(q0.z, P.inv_dx, bz, rz);
+      const int lx = bx - tx * 4, ly = by - ty * 4, lz = bz - tz * 4;
+      if ((unsigned)lx >= 4u || (unsigned)ly >= 4u || (unsigned)lz >= 4u) continue;
+      float wx[3], wy[3], wz[3];
+      bspline_weights(rx, wx); bspline_weights(ry, wy); bspline_weights(rz, wz);
+      float3 v = make_float3(0.f, 0.f, 0.f);
+      Mat3 B;
+      for (int k = 0; k < 9; k++) B.m[k] = 0.f;
+      int rigid_id = -1;
+      for (int n = 0; n < 27; n++) {
+        const int a = n / 9, b = (n / 3) % 3, c = n % 3;
+        const int ln = ((lx + a) * 6 + (ly + b)) * 6 + (lz + c);
+        const float w = (wx[a] * wy[b]) * wz[c];
+        const float dp[3] = {rx - (float)a, ry - (float)b, rz - (float)c};
+        float3 gv = make_float3(s_vel[ln].x, s_vel[ln].y, s_vel[ln].z);
+        const uint32_t word = s_word[ln];
+        if (!cdf_compatible(word, pst)) {   // different colour (761-785)
+          float3 fake = pv, vg = make_float3(0.f, 0.f, 0.f);
+          float friction = 0.f;
+          const int rid = (int)(word >> 24) - 1;
+          if (rid >= 0 && rid < R.n_bodies) {
+            const RigidDev &Bd = R.bodies[rid];
+            vg = rigid_velocity_at(Bd, make_float3((float)(bx + a) * P.dx, (float)(by + b) * P.dx, (float)(bz + c) * P.dx));
+            rigid_id = rid;
+            friction = Bd.fric[(pst >> (2 * rid)) & 1u];
+          }
+          if (near) {
+            fake = friction_project_rel(pv, vg, bn, friction);
+            const float push = P.dt * P.dx * R.pushing_force;
+            fake.x += bn.x * push; fake.y += bn.y * push; fake.z += bn.z * push;
+          }
+          gv = fake;
+        }
+        v.x = fmaf(gv.x, w, v.x); v.y = fmaf(gv.y, w, v.y); v.z = fmaf(gv.z, w, v.z);                  // 788
+        const float wgx = w * gv.x, wgy = w * gv.y, wgz = w * gv.z;
+        for (int cc = 0; cc < 3; cc++) { B(0, cc) = fmaf(wgx, dp[cc], B(0, cc)); B(1, cc) = fmaf(wgy, dp[cc], B(1, cc)); B(2, cc) = fmaf(wgz, dp[cc], B(2, cc)); }   // 793-795
+      }
+      Mat3 cdg;  // 810-815
+      for (int k = 0; k < 9; k++) cdg.m[k] = fmaf(scale, B.m[k], (k % 4 == 0) ? 1.f : 0.f);
+      Mat3 Bst = B;  // p.apic_b: zero next to a boundary (800-804)
+      if (near) for (int k = 0; k < 9; k++) Bst.m[k] = 0.f;
+      Mat3 F;
+      F.m[0] = q4.x; F.m[1] = q4.y; F.m[2] = q4.z; F.m[3] = q4.w; F.m[4] = q5.x; F.m[5] = q5.y; F.m[6] = q5.z; F.m[7] = q5.w; F.m[8] = q6.x;
+      float ps = q6.y;
+      const float vol = q6.z;
+      Mat3 force, A;
+      material_step<true>(P.mats[tag >> TAG_ID_BITS], cdg, F, ps, vol, force);
+      make_affine(force, Bst, mass, scale, A);
+      float3 x = make_float3(fmaf(v.x, P.dt, q0.x), fmaf(v.y, P.dt, q0.y), fmaf(v.z, P.dt, q0.z));   // 819
+      if (near && pc.w < -0.05f * P.dx && pc.w > -P.dx * 0.3f) {   // 823-832: position correction
+        const float3 dv = make_float3(pc.w * bn.x * R.penalty, pc.w * bn.y * R.penalty, pc.w * bn.z * R.penalty);
+        v.x -= dv.x; v.y -= dv.y; v.z -= dv.z;
+        if (rigid_id != -1) rigid_add_impulse(R.bodies[rigid_id].acc, R.bodies[rigid_id], make_float3(dv.x * mass, dv.y * mass, dv.z * mass), x);
+      }
+      uint32_t key = make_key(P, x.x, x.y, x.z);
+      if (P.clean_boundary && reference_deletes(P, x, v)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
+      if (!isfinite(x.x + x.y + x.z)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
+      store_particle<true>(V.qn, o, x, key == (uint32_t)tile ? mass : -mass, v, A, F, ps, vol, tag, Bst);
+      V.keys_next[o] = key;
+      if (key == (uint32_t)tile) {
+        my_stay++;
+      } else if (key != (uint32_t)(P.ntiles_total + SPECIAL_DEAD)) {
+        const int m = atomicAdd(&V.cnt->n_movers_next, 1);
+        if (m >= V.cap_particles) { atomicOr(&V.cnt->error, DEVERR_PARTICLE_CAPACITY); continue; }
+        V.mover_dst_n[m] = key;
+        V.mover_idx_n[m] = (uint32_t)o;
+        MPMB_COUNT_ARRIVAL(V, P, key);
+      }
+    }
+    if (my_stay) atomicAdd(&s_stay, my_stay);
+    __syncthreads();
+    if (tid == 0) V.stay_next[tile] = s_stay;
+    __syncthreads();
   }
 }
 
@@ -1686,6 +2163,13 @@ struct MpmbEngine {
   cudaStream_t cap_stream = nullptr;
   bool use_graph = true;
 
+  // CPIC rigid coupling (enabled by mpmb_set_rigid_samples with at least one sample)
+  RigidView R{};
+  bool rigid_on = false;
+  float *rs_offset = nullptr, *rs_tri = nullptr;
+  int *rs_rigid = nullptr;
+  size_t rigid_nodes = 0;
+
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int stage; };
   std::vector<Ev> events;
@@ -1762,6 +2246,7 @@ static View make_view(MpmbEngine *h) {
   V.cnt = h->cnt;
   V.cap_tiles = h->cap_tiles;
   V.cap_particles = (int)h->cap;
+  V.rigid_flag = h->rigid_on ? h->R.tile_flag : nullptr;
   return V;
 }
 
@@ -1968,6 +2453,8 @@ int mpmb_destroy(MpmbHandle h) {
   for (auto &e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   graph_reset(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  cudaFree(h->R.bodies); cudaFree(h->rs_offset); cudaFree(h->rs_tri); cudaFree(h->rs_rigid); cudaFree(h->R.s_base); cudaFree(h->R.node_key);
+  cudaFree(h->R.node_tags); cudaFree(h->R.page); cudaFree(h->R.tile_flag); cudaFree(h->R.p_states); cudaFree(h->R.p_cdf); cudaFree(h->R.p_near);
 
   delete h;
   return MPMB_OK;
@@ -2089,10 +2576,16 @@ static int ensure_capacity(MpmbEngine *h, int64_t n) {
   return MPMB_OK;
 }
 
+static int rigid_reserve_ids(MpmbEngine *h, int64_t n_ids);
 static int finish_upload(MpmbEngine *h, int64_t n) {
   // Fresh storage in upload order: no runs yet, every particle is an "arrival" of its tile.  The
   // one radix sort of the engine's life (per upload) groups the rows by tile; the ordinary
   // ordering scan then lays out the first runs.
+  if (h->rigid_on) {  // new particles start with MPMParticle::states = 0 (mpmb_set_particle_states overrides)
+    int rc = rigid_reserve_ids(h, std::max<int64_t>(n, h->cap));
+    if (rc != MPMB_OK) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(h->R.p_states, 0, sizeof(uint32_t) * h->R.id_cap, h->stream));
+  }
   View V = make_view(h);
   const size_t dense = sizeof(int) * (size_t)h->ntot;
   CUDA_TRY(h, cudaMemsetAsync(h->run_begin[h->ord], 0, dense, h->stream));
@@ -2486,6 +2979,183 @@ int mpmb_download_bgeo_points(MpmbHandle h, int64_t id_range, void *records, int
   return MPMB_OK;
 }
 
+// ------------------------------------------------------------------------------ CPIC host side
+static int rigid_reserve_ids(MpmbEngine *h, int64_t n_ids) {
+  if (n_ids <= h->R.id_cap && h->R.p_states) return MPMB_OK;
+  const int64_t cap = std::max<int64_t>(n_ids, 1024);
+  uint32_t *st = nullptr;
+  float4 *cdf = nullptr;
+  unsigned char *nr = nullptr;
+  CUDA_TRY(h, cudaMalloc(&st, sizeof(uint32_t) * cap));
+  CUDA_TRY(h, cudaMalloc(&cdf, sizeof(float4) * cap));
+  CUDA_TRY(h, cudaMalloc(&nr, cap));
+  CUDA_TRY(h, cudaMemsetAsync(st, 0, sizeof(uint32_t) * cap, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(cdf, 0, sizeof(float4) * cap, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(nr, 0, cap, h->stream));
+  if (h->R.p_states && h->R.id_cap > 0) CUDA_TRY(h, cudaMemcpyAsync(st, h->R.p_states, sizeof(uint32_t) * h->R.id_cap, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(h->R.p_states); cudaFree(h->R.p_cdf); cudaFree(h->R.p_near);
+  h->R.p_states = st; h->R.p_cdf = cdf; h->R.p_near = nr;
+  h->R.id_cap = (int)cap;
+  return MPMB_OK;
+}
+
+// per substep, after the ordering: pages + colour field of this pose, tile flags, particle colours
+static int rigid_prepare(MpmbEngine *h, const View &V, int *nl) {
+  RigidView &R = h->R;
+  R.id_base = h->id_base;
+  if (!R.p_states) { int rc = rigid_reserve_ids(h, h->cap); if (rc != MPMB_OK) return rc; }
+  const int ns = R.n_samples, sb = (ns + 127) / 128;
+  k_cdf_clear<<<sb, 128, 0, h->stream>>>(R, h->P);
+  CUDA_TRY(h, cudaMemsetAsync(R.page, 0, (size_t)R.nb[0] * R.nb[1] * R.nb[2], h->stream));
+  k_cdf_raster<<<sb, 128, 0, h->stream>>>(R, h->P);
+  k_rigid_tile_flags<<<(h->cap_tiles + 127) / 128, 128, 0, h->stream>>>(V, h->P, R);
+  k_gather_cdf<<<(int)((h->cap + 127) / 128), 128, 0, h->stream>>>(V, h->P, R);
+  *nl += 4;
+  return MPMB_OK;
+}
+
+int mpmb_set_rigid_samples(MpmbHandle h, int32_t n_bodies, int64_t n_samples, const float *offset3, const float *tri9, const int32_t *rigid_id) {
+  CHECK_HANDLE(h);
+  if (h->cfg.world > 1) return fail(h, MPMB_ERR_STATE, "rigid coupling is implemented for single-GPU engines (world == 1)");
+  if (n_samples == 0) { h->rigid_on = false; graph_reset(h); return MPMB_OK; }
+  if (n_bodies < 2 || n_bodies > RIGID_MAX || n_samples < 0 || n_samples > (1 << 24) || !offset3 || !tri9 || !rigid_id)
+    return fail(h, MPMB_ERR_INVALID, "need 2..%d bodies (entry 0 is the background body) and their boundary samples", RIGID_MAX);
+  if (h->P.nnode[0] > 1023 || h->P.nnode[1] > 1023 || h->P.nnode[2] > 1023) return fail(h, MPMB_ERR_INVALID, "rigid coupling supports grids up to 1022 cells per axis");
+  for (int64_t s = 0; s < n_samples; s++)
+    if (rigid_id[s] < 1 || rigid_id[s] >= n_bodies) return fail(h, MPMB_ERR_INVALID, "sample %lld names body %d (valid: 1..%d)", (long long)s, rigid_id[s], n_bodies - 1);
+  RigidView &R = h->R;
+  cudaFree(h->rs_offset); cudaFree(h->rs_tri); cudaFree(h->rs_rigid); cudaFree(R.s_base);
+  h->rs_offset = h->rs_tri = nullptr; h->rs_rigid = nullptr; R.s_base = nullptr;
+  CUDA_TRY(h, cudaMalloc(&h->rs_offset, sizeof(float) * 3 * n_samples));
+  CUDA_TRY(h, cudaMalloc(&h->rs_tri, sizeof(float) * 9 * n_samples));
+  CUDA_TRY(h, cudaMalloc(&h->rs_rigid, sizeof(int) * n_samples));
+  CUDA_TRY(h, cudaMalloc(&R.s_base, sizeof(int) * n_samples));
+  CUDA_TRY(h, cudaMemcpyAsync(h->rs_offset, offset3, sizeof(float) * 3 * n_samples, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->rs_tri, tri9, sizeof(float) * 9 * n_samples, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->rs_rigid, rigid_id, sizeof(int) * n_samples, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(R.s_base, 0xff, sizeof(int) * n_samples, h->stream));
+  R.s_offset = h->rs_offset; R.s_tri = h->rs_tri; R.s_rigid = h->rs_rigid;
+  R.n_samples = (int)n_samples;
+  R.n_bodies = n_bodies;
+  if (!R.bodies) {
+    CUDA_TRY(h, cudaMalloc(&R.bodies, sizeof(RigidDev) * RIGID_MAX));
+    CUDA_TRY(h, cudaMemsetAsync(R.bodies, 0, sizeof(RigidDev) * RIGID_MAX, h->stream));
+  }
+  const size_t nn = (size_t)h->P.nnode[0] * h->P.nnode[1] * h->P.nnode[2];
+  if (!R.node_key) {
+    CUDA_TRY(h, cudaMalloc(&R.node_key, sizeof(unsigned long long) * nn));
+    CUDA_TRY(h, cudaMalloc(&R.node_tags, sizeof(uint32_t) * nn));
+    R.nb[0] = (h->P.nnode[0] + 3) / 4 + 1; R.nb[1] = (h->P.nnode[1] + 3) / 4 + 1; R.nb[2] = (h->P.nnode[2] + 7) / 8 + 1;
+    CUDA_TRY(h, cudaMalloc(&R.page, (size_t)R.nb[0] * R.nb[1] * R.nb[2]));
+    CUDA_TRY(h, cudaMalloc(&R.tile_flag, (size_t)std::max(h->cap_tiles, 1)));
+    CUDA_TRY(h, cudaMemsetAsync(R.tile_flag, 0, (size_t)std::max(h->cap_tiles, 1), h->stream));
+    h->rigid_nodes = nn;
+  }
+  CUDA_TRY(h, cudaMemsetAsync(R.node_key, 0xff, sizeof(unsigned long long) * nn, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(R.node_tags, 0, sizeof(uint32_t) * nn, h->stream));
+  if (R.pushing_force == 0.f && R.penalty == 0.f) R.pushing_force = 20000.0f;   // src/mpm.cpp:35,40 defaults
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->rigid_on = true;
+  h->use_graph = false;   // poses change between substeps: the host drives every substep
+  graph_reset(h);
+  return MPMB_OK;
+}
+
+int mpmb_set_rigid_coupling(MpmbHandle h, float penalty, float pushing_force) {
+  CHECK_HANDLE(h);
+  h->R.penalty = penalty;
+  h->R.pushing_force = pushing_force;
+  return MPMB_OK;
+}
+
+int mpmb_set_rigid_state(MpmbHandle h, int32_t n_bodies, const MpmbRigidBody *bodies) {
+  CHECK_HANDLE(h);
+  if (!h->rigid_on) return fail(h, MPMB_ERR_STATE, "no rigid bodies: call mpmb_set_rigid_samples first");
+  if (n_bodies != h->R.n_bodies || !bodies) return fail(h, MPMB_ERR_INVALID, "expected %d bodies", h->R.n_bodies);
+  RigidDev dev[RIGID_MAX];
+  memset(dev, 0, sizeof(dev));
+  for (int b = 0; b < n_bodies; b++) {
+    const MpmbRigidBody &s = bodies[b];
+    RigidDev &d = dev[b];
+    for (int k = 0; k < 3; k++) { d.pos[k] = s.position[k]; d.vel[k] = s.velocity[k]; d.ang[k] = s.angular_velocity[k]; }
+    for (int k = 0; k < 9; k++) { d.rot[k] = s.rot[k]; d.inv_inertia[k] = s.inv_inertia[k]; }
+    d.inv_mass = s.inv_mass;
+    d.fric[0] = s.frictions[0]; d.fric[1] = s.frictions[1];
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->R.bodies, dev, sizeof(RigidDev) * RIGID_MAX, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // `dev` lives on this stack frame
+  return MPMB_OK;
+}
+
+int mpmb_get_rigid_state(MpmbHandle h, int32_t n_bodies, MpmbRigidBody *bodies) {
+  CHECK_HANDLE(h);
+  if (!h->rigid_on) return fail(h, MPMB_ERR_STATE, "no rigid bodies");
+  if (n_bodies != h->R.n_bodies || !bodies) return fail(h, MPMB_ERR_INVALID, "expected %d bodies", h->R.n_bodies);
+  RigidDev dev[RIGID_MAX];
+  CUDA_TRY(h, cudaMemcpyAsync(dev, h->R.bodies, sizeof(RigidDev) * RIGID_MAX, cudaMemcpyDeviceToHost, h->stream));
+  int rc = mpmb_synchronize(h);
+  if (rc != MPMB_OK) return rc;
+  for (int b = 0; b < n_bodies; b++) {
+    MpmbRigidBody &s = bodies[b];
+    const RigidDev &d = dev[b];
+    for (int k = 0; k < 3; k++) { s.position[k] = d.pos[k]; s.velocity[k] = d.vel[k]; s.angular_velocity[k] = d.ang[k]; }
+    for (int k = 0; k < 9; k++) { s.rot[k] = d.rot[k]; s.inv_inertia[k] = d.inv_inertia[k]; }
+    s.inv_mass = d.inv_mass;
+    s.frictions[0] = d.fric[0]; s.frictions[1] = d.fric[1];
+  }
+  return MPMB_OK;
+}
+
+int mpmb_set_particle_states(MpmbHandle h, int64_t n, const uint32_t *states) {
+  CHECK_HANDLE(h);
+  if (!h->rigid_on) return fail(h, MPMB_ERR_STATE, "no rigid bodies");
+  if (n < 0 || (n > 0 && !states)) return fail(h, MPMB_ERR_INVALID, "bad argument");
+  int rc = rigid_reserve_ids(h, std::max<int64_t>(n, h->cap));
+  if (rc != MPMB_OK) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->R.p_states, states, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MPMB_OK;
+}
+
+int mpmb_get_particle_cdf(MpmbHandle h, int64_t n, uint32_t *states, float *normal3, float *distance, uint8_t *near_boundary) {
+  CHECK_HANDLE(h);
+  if (!h->rigid_on || !h->R.p_states) return fail(h, MPMB_ERR_STATE, "no rigid bodies / no substep yet");
+  if (n < 0 || n > h->R.id_cap) return fail(h, MPMB_ERR_INVALID, "n exceeds the %d particle ids tracked", h->R.id_cap);
+  std::vector<float4> cdf((size_t)n);
+  if (states) CUDA_TRY(h, cudaMemcpyAsync(states, h->R.p_states, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (near_boundary) CUDA_TRY(h, cudaMemcpyAsync(near_boundary, h->R.p_near, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(cdf.data(), h->R.p_cdf, sizeof(float4) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; i++) {
+    if (normal3) { normal3[3 * i] = cdf[i].x; normal3[3 * i + 1] = cdf[i].y; normal3[3 * i + 2] = cdf[i].z; }
+    if (distance) distance[i] = cdf[i].w;
+  }
+  return MPMB_OK;
+}
+
+int mpmb_download_cdf(MpmbHandle h, uint32_t *node_states, float *node_distance) {
+  CHECK_HANDLE(h);
+  if (!h->rigid_on) return fail(h, MPMB_ERR_STATE, "no rigid bodies");
+  const size_t nn = h->rigid_nodes;
+  std::vector<unsigned long long> key(nn);
+  std::vector<uint32_t> tags(nn);
+  CUDA_TRY(h, cudaMemcpyAsync(key.data(), h->R.node_key, sizeof(unsigned long long) * nn, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(tags.data(), h->R.node_tags, sizeof(uint32_t) * nn, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < nn; i++) {
+    const bool has = key[i] != CDF_NO_KEY;
+    if (node_states) node_states[i] = (tags[i] & CDF_TAG_MASK) | (has ? ((uint32_t)key[i] & 0xffu) << 24 : 0u);
+    if (node_distance) {
+      uint32_t bits = (uint32_t)(key[i] >> 32);
+      float d;
+      memcpy(&d, &bits, 4);
+      node_distance[i] = has ? d * h->P.dx : 0.f;
+    }
+  }
+  return MPMB_OK;
+}
+
 // ------------------------------------------------------------------------------ stages
 int mpmb_sort_particles_and_populate_grid(MpmbHandle h) {
   CHECK_HANDLE(h);
@@ -2506,6 +3176,10 @@ int mpmb_sort_particles_and_populate_grid(MpmbHandle h) {
     if (!h->fresh) k_validate_order<<<h->num_sms * 2, 256, 0, h->stream>>>(V, h->ntot);
 #endif
     h->fresh = false;
+    if (h->rigid_on) {
+      int rc = rigid_prepare(h, V, &nl);
+      if (rc != MPMB_OK) return rc;
+    }
   }
   h->launches += nl;
   prof_end(h, nl);
@@ -2521,6 +3195,11 @@ int mpmb_rasterize(MpmbHandle h) {
   View V = make_view(h);
   if (h->cap > 0) k_p2g<<<h->grid_p2g, P2G_T, P2G_DYN_BYTES, h->stream>>>(V, h->P, 0);
   h->launches += 1;
+  if (h->cap > 0 && h->rigid_on) {  // block_op_rigid for the tiles of rigid pages, then apply_tmp_velocity (src/transfer.cpp:578-580)
+    k_p2g_rigid<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, h->R);
+    k_rigid_apply<<<1, 32, 0, h->stream>>>(h->R);
+    h->launches += 2;
+  }
   prof_end(h, 1);
   CUDA_TRY(h, cudaGetLastError());
   h->stage = 2;
@@ -2549,7 +3228,15 @@ int mpmb_resample(MpmbHandle h) {
   prof_end(h, 1);
   prof_begin(h, 2);
   if (h->cap > 0) {
-    launch_g2p(h, V, 0, 1, !h->skip_b);
+    if (h->rigid_on) {
+      k_g2p_rigid<<<h->num_sms * 4, 128, 0, h->stream>>>(V, h->P, h->R, h->vel);
+      h->launches += 1;
+    }
+    launch_g2p(h, V, 0, 1, !h->skip_b || h->rigid_on);   // rigid tiles read apic_b back (the impulse needs dt * force)
+    if (h->rigid_on) {
+      k_rigid_apply<<<1, 32, 0, h->stream>>>(h->R);       // src/transfer.cpp:967-969
+      h->launches += 1;
+    }
   }
   h->launches += 2;
   prof_end(h, 1);

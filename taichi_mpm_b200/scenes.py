@@ -265,3 +265,88 @@ def config(name, scale=1.0, state=True):
     meta = dict(name=name, res=res, n=n_block, kind=kind, lo=tuple(int(v) for v in lo), hi=tuple(int(v) for v in hi), density=400.0,
                 vol=float(vol1), mass=float(np.float32(vol1 * np.float32(400.0))), jitter=0.05, seed=20260922)
     return dict(scene=scene, state=st, meta=meta)
+
+
+# --------------------------------------------------------------------------- rigid bodies (CPIC)
+def rigid_boundary_samples(tris, dx, eps=1e-6):
+    """The RigidBoundaryParticles MPM<3>::add_rigid_particle seeds on a triangle mesh (src/mpm_rigid_body.cpp:227-250):
+    per element a lattice of spacing dx along its two edges from v0, starting at min(len/3, dx/2), points past an edge pulled
+    back by dx/2, kept while x/|e1| + y/|e2| <= 1 - eps.  tris: [m,3,3] in the centroid frame.  Returns (offset[ns,3],
+    tri[ns,9], element index[ns])."""
+    tris = np.asarray(tris, np.float64).reshape(-1, 3, 3)
+    off, tri, idx = [], [], []
+    for e, (v0, v1, v2) in enumerate(tris):
+        lx, ly = np.linalg.norm(v1 - v0), np.linalg.norm(v2 - v0)
+        xn, yn = (v1 - v0) / lx, (v2 - v0) / ly
+        _x = min(lx / 3.0, dx / 2.0)
+        while _x < lx + dx:
+            _y = min(ly / 3.0, dx / 2.0)
+            while _y < ly + dx:
+                x = _x if _x < lx else _x - dx / 2.0
+                y = _y if _y < ly else _y - dx / 2.0
+                if not (x / lx + y / ly > 1.0 - eps):
+                    off.append(v0 + xn * x + yn * y)
+                    tri.append(np.concatenate([v0, v1, v2]))
+                    idx.append(e)
+                _y += dx
+            _x += dx
+    return np.asarray(off, np.float32).reshape(-1, 3), np.asarray(tri, np.float32).reshape(-1, 9), np.asarray(idx, np.int32)
+
+
+def box_mesh(half):
+    """Triangles [12,3,3] of an axis-aligned box centred at the origin, outward normals."""
+    hx, hy, hz = half
+    c = np.array([[sx * hx, sy * hy, sz * hz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float64)   # index = 4 sx + 2 sy + sz
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]   # -x +x -y +y -z +z, counter-clockwise from outside
+    tris = []
+    for a, b, cc, d in quads:
+        tris += [[c[a], c[b], c[cc]], [c[a], c[cc], c[d]]]
+    return np.asarray(tris)
+
+
+def plate_mesh(half_u, half_v, axis=1):
+    """Two triangles [2,3,3] of a thin (codimensional) rectangular plate through the origin, normal along +axis."""
+    u, v = [a for a in range(3) if a != axis]
+    p = np.zeros((4, 3))
+    p[0, [u, v]] = [-half_u, -half_v]; p[1, [u, v]] = [half_u, -half_v]; p[2, [u, v]] = [half_u, half_v]; p[3, [u, v]] = [-half_u, half_v]
+    t = np.array([[p[0], p[1], p[2]], [p[0], p[2], p[3]]])
+    n = np.cross(t[0, 1] - t[0, 0], t[0, 2] - t[0, 0])
+    return t if n[axis] > 0 else t[:, ::-1]
+
+
+def euler_rotation(euler_deg):
+    """Rotation matrix of create_rigid_body's `initial_rotation` (degrees; Rx(a) Ry(b) Rz(c), src/mpm_rigid_body.cpp:118-128)."""
+    a, b, c = np.radians(np.asarray(euler_deg, np.float64))
+    rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    return rx @ ry @ rz
+
+
+def make_rigid(bodies, dx, penalty=0.0, pushing_force=20000.0):
+    """Assembles the rigid-body description the engine and the oracle take.  bodies: list of dicts(tris[m,3,3] in the centroid
+    frame, position[3], rotation (3x3 matrix, default I), velocity, angular_velocity, inv_mass (0 = scripted / infinite mass),
+    inv_inertia (3x3 world-space, default 0), friction or frictions (2,)).  Body k of the list gets the reference's rigid id k+1
+    (id 0 is MPM::rigids[0], the background body, src/mpm.cpp:72-74); at most 11 bodies (GridState::max_num_rigid_bodies = 12)."""
+    nr = len(bodies) + 1
+    if nr > 12:
+        raise ValueError("at most 11 rigid bodies (GridState::max_num_rigid_bodies, src/mpm_fwd.h:79)")
+    r = dict(position=np.zeros((nr, 3), np.float32), rot=np.tile(np.eye(3, dtype=np.float32).reshape(9), (nr, 1)), velocity=np.zeros((nr, 3), np.float32),
+             angular_velocity=np.zeros((nr, 3), np.float32), inv_mass=np.zeros(nr, np.float32), inv_inertia=np.zeros((nr, 9), np.float32),
+             frictions=np.zeros((nr, 2), np.float32), penalty=float(penalty), pushing_force=float(pushing_force))
+    offs, tris, rid = [], [], []
+    for k, b in enumerate(bodies):
+        i = k + 1
+        r["position"][i] = b["position"]
+        r["rot"][i] = np.asarray(b.get("rotation", np.eye(3)), np.float32).T.reshape(9)      # column-major
+        r["velocity"][i] = b.get("velocity", (0, 0, 0))
+        r["angular_velocity"][i] = b.get("angular_velocity", (0, 0, 0))
+        r["inv_mass"][i] = b.get("inv_mass", 0.0)
+        r["inv_inertia"][i] = np.asarray(b.get("inv_inertia", np.zeros((3, 3))), np.float32).T.reshape(9)
+        r["frictions"][i] = b["frictions"] if "frictions" in b else (b.get("friction", 0.0),) * 2
+        o, t, _ = rigid_boundary_samples(b["tris"], dx)
+        offs.append(o); tris.append(t); rid.append(np.full(len(o), i, np.int32))
+    r["sample_offset"] = np.concatenate(offs) if offs else np.zeros((0, 3), np.float32)
+    r["sample_tri"] = np.concatenate(tris) if tris else np.zeros((0, 9), np.float32)
+    r["sample_rigid"] = np.concatenate(rid) if rid else np.zeros(0, np.int32)
+    return r

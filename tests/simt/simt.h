@@ -164,6 +164,7 @@ static inline int atomicOr(int *p, int v) { int o = *p; *p = o | v; return o; }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 static inline int atomicMax(int *p, int v) { int o = *p; *p = std::max(o, v); return o; }
 static inline int atomicMin(int *p, int v) { int o = *p; *p = std::min(o, v); return o; }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = std::min(o, v); return o; }
 static inline int atomicExch(int *p, int v) { int o = *p; *p = v; return o; }
 static inline int atomicCAS(int *p, int c, int v) { int o = *p; if (o == c) *p = v; return o; }
 

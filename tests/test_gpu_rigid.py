@@ -1,0 +1,155 @@
+"""GPU parity of the CPIC rigid-coupled path: the colour field, the particle colours, both transfers with
+their impulses, against the oracle's restatement of src/rigid_transfer.cpp and the block_op_rigid branches of
+src/transfer.cpp on identical inputs.  Runs on the SIMT emulator too (tests/test_simt_emulated.py)."""
+import numpy as np
+import pytest
+
+from taichi_mpm_b200 import scenes
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(kind=scenes.MAT_JELLY, seed=3, dynamic=False, two_bodies=False, penalty=1e3, vel=0.3):
+    res = 32
+    dx = 1.0 / res
+    scene, st = T.perturbed_scene(kind, res=res, cells=8, seed=seed, strain=0.005, vel=vel)
+    c = st["x"].mean(0)
+    rot = scenes.euler_rotation((7.0, 13.0, -5.0))     # generic orientation: no grid node sits on a triangle edge
+    plate = dict(tris=scenes.plate_mesh(0.21, 0.19, axis=1), position=c + np.array([0.004, 0.011, -0.003]), rotation=rot,
+                 velocity=(0.1, -0.8, 0.05), angular_velocity=(0.3, 0.0, -0.4), frictions=(0.3, 0.5))
+    if dynamic:
+        plate.update(inv_mass=1 / 3.0, inv_inertia=np.diag([40.0, 25.0, 40.0]))
+    bodies = [plate]
+    if two_bodies:
+        bodies.append(dict(tris=scenes.box_mesh((0.05, 0.04, 0.06)), position=c + np.array([0.09, 0.07, 0.02]),
+                           rotation=scenes.euler_rotation((20.0, 5.0, 33.0)), velocity=(-0.5, 0.0, 0.2), friction=-1.0,
+                           inv_mass=2.0, inv_inertia=np.diag([300.0, 300.0, 300.0])))
+    rigid = scenes.make_rigid(bodies, dx, penalty=penalty)
+    return scene, st, rigid
+
+
+def _engine(scene, st, rigid, states=None):
+    e = T.make_engine(scene, st)
+    e.set_rigid(rigid)
+    if states is not None:
+        e.set_particle_states(states)
+    return e
+
+
+@pytest.mark.parametrize("variant", ["kinematic", "dynamic", "two_bodies"])
+def test_coupled_substep_vs_fp64_oracle(variant):
+    from oracle import pyoracle as O
+    scene, st, rigid = _scene(dynamic=variant != "kinematic", two_bodies=variant == "two_bodies")
+    n = len(st["x"])
+    ref, grid_rast, grid_vel, rref, cdf = O.substep_coupled(scene, st, rigid, np.float64)
+    e = _engine(scene, st, rigid)
+    e.sort_particles_and_populate_grid()
+    # the colour field: same nodes, same tags, same nearest body, same distances
+    dcdf = e.download_cdf()
+    assert (cdf["node_state"] >> 24 != 0).sum() > 300
+    assert np.array_equal(dcdf["node_state"], cdf["node_state"])
+    assert np.abs(dcdf["node_dist"] - cdf["node_dist"]).max() <= 2e-6 * scene["dx"] * 3
+    # the particle colours and the reconstructed boundary
+    pc = e.get_particle_cdf(n)
+    assert np.array_equal(pc["states"], ref["states"]) and len(np.unique(ref["states"])) >= 3
+    assert np.array_equal(pc["near"], ref["near"]) and 0 < ref["near"].sum() < n
+    assert np.abs(pc["bdist"] - ref["bdist"]).max() <= 2e-4 * scene["dx"]
+    assert np.abs(pc["bnormal"] - ref["bnormal"]).max() <= 2e-4
+    e.rasterize()
+    g0 = e.download_grid(0).astype(np.float64)
+    pmax = max(np.abs(grid_rast[..., :3]).max(), grid_rast[..., 3].max())
+    assert np.abs(g0 - grid_rast).max() <= T.TOL_GRID_REL * pmax
+    uncoupled, ug, _ = O.substep(scene, st, np.float64)
+    assert np.abs(ug - grid_rast).max() > 1e-2 * pmax            # the colour mask really removed contributions
+    e.resample()
+    got = e.download()
+    ids = got["id"].astype(np.int64)
+    assert np.array_equal(np.sort(ids), np.nonzero(ref["alive"])[0])
+    vmax = np.abs(ref["v"]).max()
+    assert np.abs(got["x"] - ref["x"][ids]).max() <= T.TOL_X_ABS
+    assert np.abs(got["v"] - ref["v"][ids]).max() <= T.TOL_V_REL * vmax
+    assert np.abs(got["b"] - ref["b"][ids]).max() <= T.TOL_V_REL * max(np.abs(ref["b"]).max(), 1e-30)
+    assert np.abs(got["F"] - ref["F"][ids]).max() <= T.TOL_F_ABS
+    assert np.abs(ref["v"] - uncoupled["v"]).max() > 0.05 * vmax  # ... and the coupling moved particles
+    # the bodies: both transfers' impulses applied (scripted bodies keep their velocity)
+    rs = e.get_rigid_state(len(rigid["inv_mass"]))
+    for b in range(1, len(rigid["inv_mass"])):
+        dv_ref = rref["velocity"][b] - rigid["velocity"][b]
+        dw_ref = rref["angular_velocity"][b] - rigid["angular_velocity"][b]
+        if rigid["inv_mass"][b] == 0:
+            assert np.array_equal(rs["velocity"][b], rigid["velocity"][b]) and np.array_equal(rs["angular_velocity"][b], rigid["angular_velocity"][b])
+        else:
+            assert np.abs(dv_ref).max() > 1e-4
+            assert np.abs((rs["velocity"][b] - rigid["velocity"][b]) - dv_ref).max() <= 2e-3 * np.abs(dv_ref).max() + 1e-6
+            assert np.abs((rs["angular_velocity"][b] - rigid["angular_velocity"][b]) - dw_ref).max() <= 2e-3 * np.abs(dw_ref).max() + 1e-5
+    e.close()
+
+
+def test_particle_colours_persist_and_are_cleared_as_in_the_reference():
+    # a particle keeps its colour from substep to substep; colours of bodies it no longer touches are dropped
+    # (src/rigid_transfer.cpp:162), and a preset colour decides which side of the plate the particle counts on
+    from oracle import pyoracle as O
+    scene, st, rigid = _scene()
+    n = len(st["x"])
+    preset = np.zeros(n, np.uint32)
+    preset[: n // 2] = 0b1000            # body 1, positive side — also for particles that sit on the negative side
+    preset[n // 2:] = 0b110000           # a body that does not exist near them: dropped at the first gather
+    st2 = dict(st, states=preset)
+    ref, _, _, _, _ = O.substep_coupled(scene, st2, rigid, np.float64)
+    e = _engine(scene, st, rigid, states=preset)
+    e.substep(1)
+    pc = e.get_particle_cdf(n)
+    assert np.array_equal(pc["states"], ref["states"])
+    stale = (pc["states"][n // 2:] & 0b110000) != 0
+    # dropped for the particles of rigid pages; particles whose cell lies outside keep what they had — gather_cdf returns
+    # before it looks at them (src/rigid_transfer.cpp:142-146)
+    assert (~stale).any() and stale.any()
+    fresh, _, _, _, _ = O.substep_coupled(scene, st, rigid, np.float64)
+    assert (ref["states"] != fresh["states"]).any()          # the preset overrode what the distances would have said
+    e.close()
+
+
+def test_several_coupled_substeps_follow_the_oracle_with_host_side_advection():
+    # the loop a host runs: set the pose, one substep, read the velocities back, advance the pose
+    from oracle import pyoracle as O
+    scene, st, rigid = _scene(dynamic=True, penalty=0.0, vel=0.2)
+    n = len(st["x"])
+    e = _engine(scene, st, rigid)
+    cur = dict(st, states=np.zeros(n, np.uint32))
+    r_o = {k: (np.array(v, np.float64) if isinstance(v, np.ndarray) else v) for k, v in rigid.items()}
+    r_d = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in rigid.items()}
+    for step in range(6):
+        new, _, _, rv, _ = O.substep_coupled(scene, cur, r_o, np.float64)
+        cur = dict(new)
+        e.set_rigid_state(r_d)
+        e.substep(1)
+        rs = e.get_rigid_state(2)
+        for r, vel, ang in ((r_o, rv["velocity"], rv["angular_velocity"]), (r_d, rs["velocity"], rs["angular_velocity"])):
+            r["velocity"], r["angular_velocity"] = np.array(vel), np.array(ang)
+            r["position"] = r["position"] + r["velocity"] * scene["dt"]          # translation only: enough for the loop's plumbing
+    got = e.download()
+    ids = got["id"].astype(np.int64)
+    assert np.array_equal(np.sort(ids), np.nonzero(cur["alive"])[0])
+    assert np.abs(got["x"] - cur["x"][ids]).max() <= 5e-6
+    assert np.abs(got["v"] - cur["v"][ids]).max() <= 2e-3 * np.abs(cur["v"]).max()
+    assert np.abs(r_d["velocity"][1] - r_o["velocity"][1]).max() <= 1e-3 * np.abs(r_o["velocity"][1]).max()
+    pc = e.get_particle_cdf(n)
+    assert (pc["states"] != cur["states"]).mean() < 0.002     # a colour decided by two nearly equal weighted distances may flip in fp32
+    e.close()
+
+
+def test_rigid_coupling_is_refused_where_it_is_not_implemented():
+    from taichi_mpm_b200 import capi
+    scene, st, rigid = _scene()
+    e = T.make_engine(scene, st)
+    bad = dict(rigid, sample_rigid=np.full(len(rigid["sample_rigid"]), 5, np.int32))
+    with pytest.raises(capi.MpmbError):
+        e.set_rigid(bad)                                       # samples naming a body that was not declared
+    with pytest.raises(capi.MpmbError):
+        e.get_rigid_state(2)                                   # no bodies yet
+    e.set_rigid(rigid)
+    e.set_rigid(dict(rigid, sample_offset=np.zeros((0, 3)), sample_tri=np.zeros((0, 9)), sample_rigid=np.zeros(0, np.int32)))   # off again
+    e.substep(2)
+    ref, _, _ = __import__("oracle.pyoracle", fromlist=["x"]).substep(scene, st, np.float64)
+    e.close()
