@@ -541,6 +541,54 @@ class RefSolver:
         out["alive_ids"] = np.sort(ids)
         return out
 
+    # ---- rigid bodies (CPIC): src/rigid_transfer.cpp and the block_op_rigid branches of src/transfer.cpp, run by the
+    # reference's own solver object against the stand-in RigidBody (oracle/taichi_stub/taichi/dynamics/rigid_body.h)
+    def set_rigid(self, rigid):
+        f32 = np.float32
+        r = {k: np.ascontiguousarray(rigid[k], f32) for k in ("position", "rot", "velocity", "angular_velocity", "inv_mass", "inv_inertia", "frictions",
+                                                               "sample_offset", "sample_tri")}
+        sr = np.ascontiguousarray(rigid["sample_rigid"], np.int32)
+        rc = self.L.reft_set_rigid(self.h, C.c_int(len(r["inv_mass"])), _p(r["position"]), _p(r["rot"]), _p(r["velocity"]), _p(r["angular_velocity"]),
+                                   _p(r["inv_mass"]), _p(r["inv_inertia"]), _p(r["frictions"]), C.c_int64(len(sr)), _p(r["sample_offset"]),
+                                   _p(r["sample_tri"]), _p(sr), C.c_float(rigid.get("penalty", 0.0)), C.c_float(rigid.get("pushing_force", 20000.0)))
+        assert rc == 0
+        self.n_bodies = len(r["inv_mass"])
+
+    def set_rigid_state(self, rigid):
+        f32 = np.float32
+        r = {k: np.ascontiguousarray(rigid[k], f32) for k in ("position", "rot", "velocity", "angular_velocity")}
+        self.L.reft_set_rigid_state(self.h, _p(r["position"]), _p(r["rot"]), _p(r["velocity"]), _p(r["angular_velocity"]))
+
+    def rigid_state(self):
+        v, w = np.zeros((self.n_bodies, 3), np.float32), np.zeros((self.n_bodies, 3), np.float32)
+        self.L.reft_get_rigid_state(self.h, _p(v), _p(w))
+        return dict(velocity=v, angular_velocity=w)
+
+    def set_states(self, states):
+        st = np.ascontiguousarray(states, np.uint32)
+        assert len(st) == self.n
+        self.L.reft_set_states(self.h, _p(st))
+
+    def coupled_stage(self, stage):
+        """0: ordering + rigid pages + rasterize_rigid_boundary + gather_cdf; 1: rasterize_optimized; 2: grid update;
+        3: resample_optimized + clear_boundary_particles (the calls of MPM<3>::substep, src/mpm.cpp:464-565)."""
+        self.L.reft_coupled_stage(self.h, C.c_int(int(stage)))
+
+    def cdf_particles(self):
+        n = self.n
+        out = dict(states=np.zeros(n, np.uint32), bnormal=np.zeros((n, 3), np.float32), bdist=np.zeros(n, np.float32), near=np.zeros(n, np.uint8))
+        self.L.reft_get_cdf_particles(self.h, _p(out["states"]), _p(out["bnormal"]), _p(out["bdist"]), _p(out["near"]))
+        return out
+
+    def cdf_grid(self):
+        nn = tuple(int(r) + 1 for r in self.res)
+        st, d = np.zeros(nn, np.uint32), np.zeros(nn, np.float32)
+        self.L.reft_get_cdf_grid(self.h, _p(st), _p(d))
+        return dict(node_state=st, node_dist=d)
+
+    def is_rigid_page(self, node):
+        return bool(self.L.reft_is_rigid_page(self.h, C.c_int(int(node[0])), C.c_int(int(node[1])), C.c_int(int(node[2]))))
+
     def write_partio(self, path):
         """MPM<3>::write_partio (src/visualize.cpp:16-100) on the solver's current particles."""
         self.L.reft_write_partio(self.h, str(path).encode())
@@ -571,6 +619,30 @@ def ref_transfer_substep(scene, state, grid_vel, optimized=True):
         p = s.particles()
         p.pop("alive_ids")
         return grid, p
+    finally:
+        s.close()
+
+
+def ref_substep_coupled(scene, state, rigid):
+    """One coupled substep by the REFERENCE's own code (src/mpm.cpp ordering and rigid pages, src/rigid_transfer.cpp,
+    src/transfer.cpp block_op_switch) at a fixed rigid pose, fp32.  Same return shape as substep_coupled()."""
+    s = RefSolver(scene, state)
+    try:
+        s.set_rigid(rigid)
+        if state.get("states") is not None:
+            s.set_states(state["states"])
+        s.coupled_stage(0)
+        cdf, pc = s.cdf_grid(), s.cdf_particles()
+        s.coupled_stage(1)
+        grid_rast = s.get_grid()
+        s.coupled_stage(2)
+        grid_vel = s.get_grid()
+        s.coupled_stage(3)
+        p = s.particles()
+        alive = np.zeros(s.n, np.uint8)
+        alive[p.pop("alive_ids")] = 1
+        new = dict(p, alive=alive, states=pc["states"], bnormal=pc["bnormal"], bdist=pc["bdist"], near=pc["near"])
+        return new, grid_rast, grid_vel, s.rigid_state(), cdf
     finally:
         s.close()
 

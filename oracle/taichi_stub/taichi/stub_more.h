@@ -45,6 +45,7 @@ struct ArrayND {
   bool inside(const VectorND<dim, int> &i) const { for (int k = 0; k < dim; k++) if (i[k] < 0 || i[k] >= res[k]) return false; return true; }
   RegionND<dim> get_region() const { return RegionND<dim>(VectorND<dim, int>(0), res); }
   void write_as_image(const std::string &) const {}
+  void reset_zero() { std::fill(data.begin(), data.end(), T()); }
 };
 template <class T> using Array2D = ArrayND<2, T>;
 template <class T> using Array3D = ArrayND<3, T>;

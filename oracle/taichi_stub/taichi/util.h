@@ -371,6 +371,32 @@ template <class T> inline MatrixND<3, T> inversed(const MatrixND<3, T> &a) {
     }
   return r;
 }
+// 4x4 (gather_cdf's weighted least squares, src/rigid_transfer.cpp:251-252): cofactor expansion, evaluated in double and rounded
+// like the 3x3 inverse above — differences seen by the tests come from the reference's formulas, not from this header
+template <class T> inline double det3_rows(const double m[4][4], const int r[3], const int c[3]) {
+  return m[r[0]][c[0]] * (m[r[1]][c[1]] * m[r[2]][c[2]] - m[r[1]][c[2]] * m[r[2]][c[1]]) - m[r[0]][c[1]] * (m[r[1]][c[0]] * m[r[2]][c[2]] - m[r[1]][c[2]] * m[r[2]][c[0]]) +
+         m[r[0]][c[2]] * (m[r[1]][c[0]] * m[r[2]][c[1]] - m[r[1]][c[1]] * m[r[2]][c[0]]);
+}
+template <class T> inline double cofactor4(const MatrixND<4, T> &a, int row, int col) {
+  double m[4][4];
+  for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) m[r][c] = a[c][r];
+  int rr[3], cc[3], k = 0, l = 0;
+  for (int i = 0; i < 4; i++) { if (i != row) rr[k++] = i; if (i != col) cc[l++] = i; }
+  return (((row + col) & 1) ? -1.0 : 1.0) * det3_rows<T>(m, rr, cc);
+}
+template <class T> inline T determinant(const MatrixND<4, T> &a) {
+  double d = 0;
+  for (int c = 0; c < 4; c++) d += (double)a[c][0] * cofactor4(a, 0, c);
+  return (T)d;
+}
+template <class T> inline MatrixND<4, T> inversed(const MatrixND<4, T> &a) {
+  double d = 0;
+  for (int c = 0; c < 4; c++) d += (double)a[c][0] * cofactor4(a, 0, c);
+  MatrixND<4, T> r;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) r[j][i] = (T)(cofactor4(a, j, i) / d);   // inverse(i,j) = cofactor(j,i) / det
+  return r;
+}
+template <int n, class T> inline VectorND<n, T> cross(const VectorND<n, T> &a, const VectorND<n, T> &b) { return a.cross(b); }
 template <int n, class T> inline MatrixND<n, T> inverse(const MatrixND<n, T> &a) { return inversed(a); }
 
 

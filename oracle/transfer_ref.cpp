@@ -44,6 +44,8 @@
 #include REF_MPM_SOURCE
 #include REF_VISUALIZE_SOURCE
 #include REF_PARTICLES_SOURCE
+#include REF_RIGID_TRANSFER_SOURCE       // rasterize_rigid_boundary, gather_cdf (src/rigid_transfer.cpp)
+#include REF_BOUNDARY_PARTICLE_SOURCE    // registers "rigid_boundary" (src/boundary_particle.cpp)
 #undef private
 #include <cstddef>
 #include <cstdint>
@@ -52,19 +54,16 @@
 #include "../include/mpmb.h"
 
 namespace taichi {
-// members of the solver that live in translation units which are not part of this build (src/rigid_transfer.cpp,
-// ...): empty, and unreachable on the pinned path (no rigid bodies)
+// members of the solver that live in translation units which are not part of this build (src/mpm_rigid_body.cpp):
+// empty — rigid bodies keep their pose over a substep here (the harness sets it), so rigidify / advect_rigid_bodies have
+// nothing to do; src/rigid_transfer.cpp IS part of the build
 template <> void MPM<3>::add_rigid_particle(Config) {}
 template <> void MPM<3>::rigidify(real) {}
 template <> void MPM<3>::advect_rigid_bodies(real) {}
-template <> void MPM<3>::rasterize_rigid_boundary() {}
-template <> void MPM<3>::gather_cdf() {}
 template <> void MPM<3>::rigid_body_levelset_collision(real, real) {}
 // src/mpm.cpp instantiates parts of the 2-D solver explicitly (general_action); the same members, never called
 template <> void MPM<2>::rigidify(real) {}
 template <> void MPM<2>::advect_rigid_bodies(real) {}
-template <> void MPM<2>::rasterize_rigid_boundary() {}
-template <> void MPM<2>::gather_cdf() {}
 template <> void MPM<2>::rigid_body_levelset_collision(real, real) {}
 }  // namespace taichi
 
@@ -308,10 +307,127 @@ int64_t reft_substep(void *hp, int n) {
   for (int i = 0; i < n; i++) m.substep();
   return (int64_t)m.particles.size();
 }
+// ---- rigid bodies (CPIC).  Bodies 1..n_bodies-1 become MPM::rigids[1..] (row 0 is the background body MPM::initialize
+// creates, src/mpm.cpp:72-74); every sample becomes a RigidBoundaryParticle in the reference's own pool
+// (add_boundry_particle, src/mpm_rigid_body.cpp:153-169), aligned with its body.  Call after the MPM particles are loaded.
+int reft_set_rigid(void *hp, int n_bodies, const float *position, const float *rot, const float *velocity, const float *angular_velocity,
+                   const float *inv_mass, const float *inv_inertia, const float *frictions, int64_t n_samples, const float *offset,
+                   const float *tri, const int32_t *sample_rigid, float penalty, float pushing_force) {
+  Harness *h = static_cast<Harness *>(hp);
+  Solver &m = h->m;
+  if (!m.rigids.empty()) return -1;
+  using V3 = VectorND<3, real>;
+  for (int b = 0; b < n_bodies; b++) {
+    auto r = std::make_unique<RigidBody<3>>();
+    r->id = b;
+    r->position = V3(position[3 * b], position[3 * b + 1], position[3 * b + 2]);
+    r->velocity = V3(velocity[3 * b], velocity[3 * b + 1], velocity[3 * b + 2]);
+    r->angular_velocity.value = V3(angular_velocity[3 * b], angular_velocity[3 * b + 1], angular_velocity[3 * b + 2]);
+    r->rotation.value = load(rot + 9 * b);
+    r->inv_mass = inv_mass[b];
+    r->inv_inertia = load(inv_inertia + 9 * b);
+    r->frictions[0] = frictions[2 * b];
+    r->frictions[1] = frictions[2 * b + 1];
+    m.rigids.push_back(std::move(r));
+  }
+  m.penalty = penalty;
+  m.pushing_force = pushing_force;
+  m.config_backup.set("rigid_body_collision", false);   // rigidify() is outside this build anyway
+  for (int64_t s = 0; s < n_samples; s++) {
+    auto alloc = m.allocator.allocate_particle("rigid_boundary");
+    auto *p = static_cast<RigidBoundaryParticle<3> *>(alloc.second);
+    p->rigid = m.rigids[sample_rigid[s]].get();
+    p->offset = V3(offset[3 * s], offset[3 * s + 1], offset[3 * s + 2]);
+    for (int k = 0; k < 3; k++) p->untransformed_element.v[k] = V3(tri[9 * s + 3 * k], tri[9 * s + 3 * k + 1], tri[9 * s + 3 * k + 2]);
+    p->original_normal = p->untransformed_element.get_normal();
+    p->set_mass(0.0f);
+    p->align_with_rigid_body();
+    m.particles.push_back(alloc.first);
+    h->kind.push_back(-1);
+  }
+  return 0;
+}
+// pose and velocities of every body for the next substep; the boundary particles follow (align_with_rigid_body,
+// what advect_rigid_bodies does at the end of a substep, src/mpm_rigid_body.cpp:278-283)
+void reft_set_rigid_state(void *hp, const float *position, const float *rot, const float *velocity, const float *angular_velocity) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  using V3 = VectorND<3, real>;
+  for (size_t b = 0; b < m.rigids.size(); b++) {
+    auto &r = *m.rigids[b];
+    r.position = V3(position[3 * b], position[3 * b + 1], position[3 * b + 2]);
+    r.velocity = V3(velocity[3 * b], velocity[3 * b + 1], velocity[3 * b + 2]);
+    r.angular_velocity.value = V3(angular_velocity[3 * b], angular_velocity[3 * b + 1], angular_velocity[3 * b + 2]);
+    r.rotation.value = load(rot + 9 * b);
+  }
+  for (auto ptr : m.particles) {
+    MPMParticle<3> *p = m.allocator[ptr];
+    if (p->is_rigid()) static_cast<RigidBoundaryParticle<3> *>(p)->align_with_rigid_body();
+  }
+}
+void reft_get_rigid_state(void *hp, float *velocity, float *angular_velocity) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  for (size_t b = 0; b < m.rigids.size(); b++)
+    for (int d = 0; d < 3; d++) { velocity[3 * b + d] = m.rigids[b]->velocity[d]; angular_velocity[3 * b + d] = m.rigids[b]->angular_velocity.value[d]; }
+}
+// MPMParticle::states in (by id), states / boundary_normal / boundary_distance / near_boundary_ out (by id)
+void reft_set_states(void *hp, const uint32_t *states) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  for (auto ptr : m.particles) { MPMParticle<3> *p = m.allocator[ptr]; if (!p->is_rigid()) p->states = states[p->id]; }
+}
+void reft_get_cdf_particles(void *hp, uint32_t *states, float *normal, float *dist, uint8_t *near) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  for (auto ptr : m.particles) {
+    MPMParticle<3> *p = m.allocator[ptr];
+    if (p->is_rigid()) continue;
+    const int id = p->id;
+    states[id] = p->states;
+    for (int d = 0; d < 3; d++) normal[3 * id + d] = p->boundary_normal[d];
+    dist[id] = p->boundary_distance;
+    near[id] = p->near_boundary_ ? 1 : 0;
+  }
+}
+// GridState::states (tags | (rigid id + 1) << 24) and GridState::distance of every node of the fat blocks, dense
+void reft_get_cdf_grid(void *hp, uint32_t *states, float *dist) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  const int nx = m.res[0] + 1, ny = m.res[1] + 1, nz = m.res[2] + 1;
+  auto fat = m.fat_page_map->Get_Blocks();
+  auto grid_array = m.grid->Get_Array();
+  for (int b = 0; b < (int)fat.second; b++) {
+    auto c = Mask::LinearToCoord(fat.first[b]);
+    for (int i = 0; i < (1 << Mask::block_xbits); i++)
+      for (int j = 0; j < (1 << Mask::block_ybits); j++)
+        for (int k = 0; k < (1 << Mask::block_zbits); k++) {
+          int X = c[0] + i, Y = c[1] + j, Z = c[2] + k;
+          if (X >= nx || Y >= ny || Z >= nz) continue;
+          const GridState<3> &g = grid_array(std::array<int, 3>{X, Y, Z});
+          states[(size_t(X) * ny + Y) * nz + Z] = g.states;
+          dist[(size_t(X) * ny + Y) * nz + Z] = g.distance;
+        }
+  }
+}
+// 1 if the block holding node (X,Y,Z) is a rigid page (update_rigid_page_map, src/mpm.cpp:1026-1076)
+int reft_is_rigid_page(void *hp, int X, int Y, int Z) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  return m.rigid_page_map->Test_Page(Mask::Linear_Offset(std::array<int, 3>{X, Y, Z})) ? 1 : 0;
+}
+// one coupled substep in stages, exactly the calls MPM<3>::substep makes between rigidify and advect_rigid_bodies
+// (src/mpm.cpp:464-565), so that the grid can be read after each transfer:
+//   stage 0: sort_particles_and_populate_grid (with update_rigid_page_map), rasterize_rigid_boundary, gather_cdf
+//   stage 1: rasterize_optimized            stage 2: grid update            stage 3: resample_optimized + clear_boundary_particles
+void reft_coupled_stage(void *hp, int stage) {
+  Solver &m = static_cast<Harness *>(hp)->m;
+  if (!m.levelset.levelset0) m.levelset.levelset0 = std::make_shared<LevelSet<3>>();
+  if (stage == 0) { m.sort_particles_and_populate_grid(); m.rasterize_rigid_boundary(); m.gather_cdf(); }
+  if (stage == 1) m.rasterize_optimized(m.base_delta_t);
+  if (stage == 2) reft_grid_update(hp);
+  if (stage == 3) { m.resample_optimized(); m.clear_boundary_particles(); m.current_t += m.base_delta_t; m.substep_counter += 1; }
+}
 // ids of the live particles, in the solver's current order
 void reft_alive_ids(void *hp, int32_t *ids) {
   Solver &m = static_cast<Harness *>(hp)->m;
-  for (size_t k = 0; k < m.particles.size(); k++) ids[k] = m.allocator[m.particles[k]]->id;
+  size_t o = 0;
+  for (size_t k = 0; k < m.particles.size(); k++)
+    if (!m.allocator[m.particles[k]]->is_rigid()) ids[o++] = m.allocator[m.particles[k]]->id;
 }
 // the reference's own benchmark seeding (add_particles with benchmark = 125 | 8000, src/mpm.cpp:155-186): a cube of
 // res*0.2 (resp. res*0.8) cells per axis, 8 particles per cell.  type = registered particle name.  Returns the count.
@@ -430,13 +546,19 @@ int64_t reft_step(void *hp, float dt, float *current_t, float *request_t) {
 
 // frame dump by MPM<3>::write_partio itself (src/visualize.cpp:16-100) through the vendored Partio
 void reft_write_partio(void *hp, const char *file_name) { static_cast<Harness *>(hp)->m.write_partio(file_name); }
-int64_t reft_num_particles(void *hp) { return (int64_t) static_cast<Harness *>(hp)->m.particles.size(); }
+int64_t reft_num_particles(void *hp) {   // MPM particles (RigidBoundaryParticles not counted)
+  Solver &m = static_cast<Harness *>(hp)->m;
+  int64_t n = 0;
+  for (auto ptr : m.particles) n += m.allocator[ptr]->is_rigid() ? 0 : 1;
+  return n;
+}
 // particle state by id (= order of reft_add_particle)
 void reft_get_particles(void *hp, float *x, float *v, float *F, float *b, float *ps) {
   Harness *h = static_cast<Harness *>(hp);
   Solver &m = h->m;
   for (auto ptr : m.particles) {
     MPMParticle<3> *p = m.allocator[ptr];
+    if (p->is_rigid()) continue;   // RigidBoundaryParticles (ids after the MPM particles') are not part of the read-back
     const int id = p->id;
     for (int d = 0; d < 3; d++) { x[3 * id + d] = p->pos[d]; v[3 * id + d] = p->get_velocity()[d]; }
     store(p->dg_e, F + 9 * id);
