@@ -734,7 +734,10 @@ constexpr int P2G_DYN_BYTES = 4 * P2G_ROWS * (int)sizeof(float4);
 constexpr int AR_SX = 68, AR_SY = 8;           // arena strides in shared memory
 constexpr int AR_SIZE = 6 * AR_SX;
 
-__global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
+#ifndef MPMB_P2G_MINB
+#define MPMB_P2G_MINB 1
+#endif
+__global__ void __launch_bounds__(P2G_T, MPMB_P2G_MINB) k_p2g(View V, Params P, int part) {
   // the row staging area is dynamic shared memory (static + dynamic = 51.7 KB, above the 48 KB static limit)
 #ifndef MPMB_SIMT_HOST
   extern __shared__ __align__(16) unsigned char p2g_dyn[];
@@ -745,7 +748,9 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
   __shared__ unsigned short s_order[P2G_CH];
   __shared__ unsigned short s_hist[P2G_K * 2][64];
   __shared__ int s_start[65];
+#ifndef MPMB_EXP_P2G_OVERLAY
   __shared__ float s_arena[4][AR_SIZE];
+#endif
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = V.cnt->n_tiles;
   const int cx = tid >> 4, cy = (tid >> 2) & 3, cz = tid & 3;
@@ -761,7 +766,9 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
     F4 acc[27];  // (p_x, p_y | p_z, m) of the 27 nodes of my cell's stencil
 #pragma unroll
     for (int n = 0; n < 27; n++) acc[n] = f4_zero();
+#ifndef MPMB_EXP_P2G_OVERLAY
     for (int n = tid; n < AR_SIZE; n += P2G_T) { s_arena[0][n] = 0.f; s_arena[1][n] = 0.f; s_arena[2][n] = 0.f; s_arena[3][n] = 0.f; }
+#endif
     int vbase = 0;  // valid rows in the chunks already processed
     // storage row of tile-row g: run rows first, then arrivals
     auto row_of = [&](int g) -> uint32_t {
@@ -925,6 +932,16 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
     // ---- 4: both warps flush at once, warp 0 into s_arena, warp 1 into a second arena laid over the
     // row staging area (free after the last chunk's barrier; zeroed by warp 1 itself, so a __syncwarp
     // is all it needs).  The store below sums the two in a fixed order: still bit-reproducible.
+#ifdef MPMB_EXP_P2G_OVERLAY
+    // BOTH arenas laid over the row staging area: 6.5 KB less static shared memory per CTA
+    float (*s_arena)[AR_SIZE] = reinterpret_cast<float (*)[AR_SIZE]>(&s_rows[0][0]);
+    float (*ar1)[AR_SIZE] = s_arena + 4;
+    {
+      float (*arz)[AR_SIZE] = warp == 0 ? s_arena : ar1;
+      for (int n = lane; n < 4 * AR_SIZE; n += 32) (&arz[0][0])[n] = 0.f;
+      __syncwarp();
+      float (*ar)[AR_SIZE] = arz;
+#else
     float (*ar1)[AR_SIZE] = reinterpret_cast<float (*)[AR_SIZE]>(&s_rows[0][0]);
     {
       if (warp == 1) {
@@ -932,6 +949,7 @@ __global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
         __syncwarp();
       }
       float (*ar)[AR_SIZE] = warp == 0 ? s_arena : ar1;
+#endif
       const int nb = cx * AR_SX + cy * AR_SY + cz;
 #pragma unroll
       for (int i = 0; i < 3; i++)

@@ -20,7 +20,7 @@ import os
 
 import numpy as np
 
-from . import bgeo, capi, scenes
+from . import bgeo, capi, rigid as rigid_mod, scenes
 
 # MPMParticle::get_debug_info().y per registered type (src/particles.cpp:288-290,347-349,422-424,
 # 496-498,669-671,156-158,754-756,838-840); water also reports (j, 5, sticky); elastic reports its Young's modulus in .x,
@@ -109,9 +109,13 @@ class MPM:
         self.clean_boundary = bool(kwargs.get("clean_boundary", True))          # mpm.cpp:563
         if not kwargs.get("optimized", True):
             raise ValueError("optimized=False (the scalar transfers) is not accelerated")
-        for key in ("apic_damping", "rpic_damping", "affine_damping", "penalty"):
+        for key in ("apic_damping", "rpic_damping", "affine_damping"):
             if float(kwargs.get(key, 0.0)) != 0.0:
                 raise ValueError("%s != 0 is outside the accelerated fast path" % key)
+        self.penalty = float(kwargs.get("penalty", 0.0))                        # mpm.cpp:35: rigid-coupled scenes only
+        self.pushing_force = float(kwargs.get("pushing_force", 20000.0))        # mpm.cpp:40
+        self.rigids = []          # HostRigidBody per add_particles(type='rigid'); engine body id = index + 1 (rigids[0] of the
+        self._rigid_dirty = False  # reference is the background body, mpm.cpp:72-74)
         self.engine = capi.Engine(self.res, self.delta_x, self.base_delta_t, self.gravity, self.particle_gravity,
                                   self.clean_boundary, device=int(kwargs.get("device", 0)), capacity=int(kwargs.get("capacity", 0)))
         self.current_t = np.float32(0.0)
@@ -161,7 +165,7 @@ class MPM:
         reference type (E, nu, youngs_modulus, friction_angle, ...) are honoured."""
         name = kwargs["type"]
         if name == "rigid":
-            raise ValueError("rigid bodies are outside the accelerated fast path")
+            return self.add_rigid_particle(**kwargs)
         if name not in self.PARTICLE_TYPES:
             raise ValueError("unknown particle type %r" % name)
         kind = self.PARTICLE_TYPES[name]
@@ -191,6 +195,62 @@ class MPM:
         self._dirty = True
         return ""
 
+    def add_rigid_particle(self, **kwargs):
+        """MPM<3>::add_rigid_particle (src/mpm_rigid_body.cpp:57-250): the keys of create_rigid_body — initial_position |
+        scripted_position, initial_rotation (Euler degrees) | scripted_rotation, initial_velocity, initial_angular_velocity,
+        friction | friction0 + friction1, density (40 codimensional / 400), codimensional (required, as in the reference), scale,
+        recenter, rotation_axis, linear_damping, angular_damping — with the mesh given as `mesh_fn` (.obj) or `tris` [m,3,3].
+        Scripted functions are Python callables t -> 3 numbers (the reference wraps them with tc.function13).  Returns the
+        body's id as the reference does (a string)."""
+        if "scripted" in kwargs or "position" in kwargs or "rotation" in kwargs:                # check_scripting_parameters, :16-22
+            raise ValueError("use initial_position / scripted_position and initial_rotation / scripted_rotation")
+        if ("scripted_position" in kwargs) == ("initial_position" in kwargs):
+            raise ValueError("specify one (and only one) of 'scripted_position' and 'initial_position'")
+        if "friction" in kwargs and ("friction0" in kwargs or "friction1" in kwargs):
+            raise ValueError("friction and friction0/friction1 cannot coexist")
+        if ("friction0" in kwargs) != ("friction1" in kwargs):
+            raise ValueError("friction0 and friction1 must be specified simultaneously")
+        if len(self.rigids) >= 11:
+            raise ValueError("at most 11 rigid bodies (GridState::max_num_rigid_bodies)")
+        codim = bool(kwargs["codimensional"])
+        tris = rigid_mod.load_obj(kwargs["mesh_fn"]) if "mesh_fn" in kwargs else np.asarray(kwargs["tris"], np.float64).reshape(-1, 3, 3)
+        tris = tris * np.asarray(kwargs.get("scale", (1.0, 1.0, 1.0)), np.float64)              # :183-189
+        fr = (kwargs["friction0"], kwargs["friction1"]) if "friction0" in kwargs else (kwargs.get("friction", 0.0),) * 2
+        body = rigid_mod.HostRigidBody(
+            tris, density=float(kwargs.get("density", 40.0 if codim else 400.0)), codimensional=codim,
+            position=kwargs.get("initial_position", (0, 0, 0)), euler_deg=kwargs.get("initial_rotation", (0, 0, 0)),
+            velocity=kwargs.get("initial_velocity", (0, 0, 0)), angular_velocity=kwargs.get("initial_angular_velocity", (0, 0, 0)), frictions=fr,
+            scripted_position=kwargs.get("scripted_position"), scripted_rotation=kwargs.get("scripted_rotation"),
+            recenter=bool(kwargs.get("recenter", True)), rotation_axis=kwargs.get("rotation_axis", (0, 0, 0)),
+            linear_damping=float(kwargs.get("linear_damping", 0.0)), angular_damping=float(kwargs.get("angular_damping", 0.0)), t0=float(self.current_t))
+        self.rigids.append(body)
+        self._rigid_dirty = True
+        return str(len(self.rigids))
+
+    def _rigid_records(self):
+        return rigid_mod.engine_records(self.rigids, self.delta_x, self.penalty, self.pushing_force)
+
+    def _substeps_with_rigid(self, n):
+        """The reference's substep() with bodies (src/mpm.cpp:452-575): transfers at the current pose, then
+        advect_rigid_bodies — one engine substep per pose."""
+        h = np.float32(self.base_delta_t)
+        t = np.float32(self.current_t)
+        for _ in range(n):
+            rec = self._rigid_records()
+            if self._rigid_dirty:
+                self.engine.set_rigid(rec)            # boundary samples of every body + coupling constants + state
+                self._rigid_dirty = False
+            else:
+                self.engine.set_rigid_state(rec)
+            self.engine.substep(1)
+            rs = self.engine.get_rigid_state(len(self.rigids) + 1)
+            for k, b in enumerate(self.rigids):
+                b.velocity = rs["velocity"][k + 1].astype(np.float64)
+                b.angular_velocity = rs["angular_velocity"][k + 1].astype(np.float64)
+                b.advect(float(t), float(h), self.gravity)
+            t = np.float32(t + h)
+        return t
+
     def _pull_host(self):
         """Host copy of the resident particles (download -> mutate -> upload contract)."""
         if self._host is not None:
@@ -212,8 +272,11 @@ class MPM:
     # ---- time stepping
     def substep(self):
         self._push()
-        self.engine.substep(1)
-        self.current_t = np.float32(self.current_t + np.float32(self.base_delta_t))   # src/mpm.cpp:573, float
+        if self.rigids:
+            self.current_t = self._substeps_with_rigid(1)
+        else:
+            self.engine.substep(1)
+            self.current_t = np.float32(self.current_t + np.float32(self.base_delta_t))   # src/mpm.cpp:573, float
         self.substep_counter += 1
 
     def step(self, dt):
@@ -235,7 +298,10 @@ class MPM:
         if n:
             # "Times of particle updating" (src/mpm.cpp:436,449) = particles.size() per substep: the engine sums the
             # particles every ordering bins (exact when particles are deleted inside the frame); see update_counter
-            self.engine.substep(n)
+            if self.rigids:
+                self._substeps_with_rigid(n)
+            else:
+                self.engine.substep(n)
             self.current_t = t
             self.substep_counter += n
         self._host = None

@@ -255,7 +255,7 @@ def test_add_particles_follows_the_reference_rules(fake_engine):
 
 
 def test_unsupported_solver_options_are_rejected_not_ignored(fake_engine):
-    for kw in (dict(optimized=False), dict(apic_damping=0.1), dict(rpic_damping=0.1), dict(penalty=1.0), dict(res=(64, 64))):
+    for kw in (dict(optimized=False), dict(apic_damping=0.1), dict(rpic_damping=0.1), dict(res=(64, 64))):
         with pytest.raises(ValueError):
             mpm_mod.MPM(**{"res": (32, 32, 32), **kw})
     m = mpm_mod.MPM(res=(32, 32, 32))
