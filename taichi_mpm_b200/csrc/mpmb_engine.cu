@@ -734,10 +734,13 @@ constexpr int P2G_DYN_BYTES = 4 * P2G_ROWS * (int)sizeof(float4);
 constexpr int AR_SX = 68, AR_SY = 8;           // arena strides in shared memory
 constexpr int AR_SIZE = 6 * AR_SX;
 
-#ifndef MPMB_P2G_MINB
-#define MPMB_P2G_MINB 1
-#endif
-__global__ void __launch_bounds__(P2G_T, MPMB_P2G_MINB) k_p2g(View V, Params P, int part) {
+// Occupancy, measured and rejected (round 2, profiles/r02_ab_p2g_occupancy.log): this kernel holds 243 registers and 51.7 KB
+// of shared memory, i.e. 4 CTAs = 8 warps per SM by both limits.  Laying BOTH flush arenas over the row staging area (-6.5 KB)
+// and bounding the launch to 5 CTAs per SM gives a spill-free 168-register build that fits 5 CTAs with 512-row chunks — and
+// is slower everywhere: 0.2628 / 0.3773 ms (at rest / flowing) against 0.2463 / 0.3275; the 168-register code alone, still at
+// 4 CTAs with 576-row chunks, 0.2638 / 0.3559.  The time is in-warp latency of the per-particle dependency chain, which the
+// wider register allocation schedules around; two more warps do not buy it back.
+__global__ void __launch_bounds__(P2G_T) k_p2g(View V, Params P, int part) {
   // the row staging area is dynamic shared memory (static + dynamic = 51.7 KB, above the 48 KB static limit)
 #ifndef MPMB_SIMT_HOST
   extern __shared__ __align__(16) unsigned char p2g_dyn[];
@@ -748,9 +751,7 @@ __global__ void __launch_bounds__(P2G_T, MPMB_P2G_MINB) k_p2g(View V, Params P, 
   __shared__ unsigned short s_order[P2G_CH];
   __shared__ unsigned short s_hist[P2G_K * 2][64];
   __shared__ int s_start[65];
-#ifndef MPMB_EXP_P2G_OVERLAY
   __shared__ float s_arena[4][AR_SIZE];
-#endif
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = V.cnt->n_tiles;
   const int cx = tid >> 4, cy = (tid >> 2) & 3, cz = tid & 3;
@@ -766,9 +767,7 @@ __global__ void __launch_bounds__(P2G_T, MPMB_P2G_MINB) k_p2g(View V, Params P, 
     F4 acc[27];  // (p_x, p_y | p_z, m) of the 27 nodes of my cell's stencil
 #pragma unroll
     for (int n = 0; n < 27; n++) acc[n] = f4_zero();
-#ifndef MPMB_EXP_P2G_OVERLAY
     for (int n = tid; n < AR_SIZE; n += P2G_T) { s_arena[0][n] = 0.f; s_arena[1][n] = 0.f; s_arena[2][n] = 0.f; s_arena[3][n] = 0.f; }
-#endif
     int vbase = 0;  // valid rows in the chunks already processed
     // storage row of tile-row g: run rows first, then arrivals
     auto row_of = [&](int g) -> uint32_t {
@@ -882,6 +881,8 @@ __global__ void __launch_bounds__(P2G_T, MPMB_P2G_MINB) k_p2g(View V, Params P, 
       // population rank +0.015 / +0.020 ms: the kernel is latency-bound at 8 warps per SM, an early warp's issue slots
       // are not what it lacks.
       const int i0 = s_start[tid], i1 = s_start[tid + 1];
+      // (software-pipelining this loop — the next particle's row fetched one iteration ahead, 252 registers, no spills — was
+      // measured slower as well: 0.2665 / 0.3644 ms against 0.2465 / 0.3275, profiles/r02_ab_p2g_prefetch.log)
       for (int it = i0; it < i1; it++) {
         const int r = s_order[it];
         const int ri = r + (r >> 3);
@@ -932,16 +933,6 @@ __global__ void __launch_bounds__(P2G_T, MPMB_P2G_MINB) k_p2g(View V, Params P, 
     // ---- 4: both warps flush at once, warp 0 into s_arena, warp 1 into a second arena laid over the
     // row staging area (free after the last chunk's barrier; zeroed by warp 1 itself, so a __syncwarp
     // is all it needs).  The store below sums the two in a fixed order: still bit-reproducible.
-#ifdef MPMB_EXP_P2G_OVERLAY
-    // BOTH arenas laid over the row staging area: 6.5 KB less static shared memory per CTA
-    float (*s_arena)[AR_SIZE] = reinterpret_cast<float (*)[AR_SIZE]>(&s_rows[0][0]);
-    float (*ar1)[AR_SIZE] = s_arena + 4;
-    {
-      float (*arz)[AR_SIZE] = warp == 0 ? s_arena : ar1;
-      for (int n = lane; n < 4 * AR_SIZE; n += 32) (&arz[0][0])[n] = 0.f;
-      __syncwarp();
-      float (*ar)[AR_SIZE] = arz;
-#else
     float (*ar1)[AR_SIZE] = reinterpret_cast<float (*)[AR_SIZE]>(&s_rows[0][0]);
     {
       if (warp == 1) {
@@ -949,7 +940,6 @@ __global__ void __launch_bounds__(P2G_T, MPMB_P2G_MINB) k_p2g(View V, Params P, 
         __syncwarp();
       }
       float (*ar)[AR_SIZE] = warp == 0 ? s_arena : ar1;
-#endif
       const int nb = cx * AR_SX + cy * AR_SY + cz;
 #pragma unroll
       for (int i = 0; i < 3; i++)
