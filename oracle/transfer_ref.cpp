@@ -463,8 +463,16 @@ int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, 
   if (!lib) return fail(dlerror(), -100);
 #define SYM(name) auto name##_ = reinterpret_cast<decltype(&name)>(dlsym(lib, #name)); if (!name##_) return fail("missing symbol " #name, -101)
   SYM(mpmb_create); SYM(mpmb_destroy); SYM(mpmb_last_error); SYM(mpmb_set_material); SYM(mpmb_set_planes); SYM(mpmb_upload_aos);
-  SYM(mpmb_substep); SYM(mpmb_download_aos);
+  SYM(mpmb_substep); SYM(mpmb_download_aos); SYM(mpmb_set_rigid_samples); SYM(mpmb_set_rigid_coupling); SYM(mpmb_set_rigid_state);
+  SYM(mpmb_get_rigid_state); SYM(mpmb_set_particle_states); SYM(mpmb_get_particle_cdf);
 #undef SYM
+  // with rigid bodies: the RigidBoundaryParticles leave the index vector for the duration — the engine
+  // takes them as a sample list — and come back behind the survivors
+  const bool coupled = m.rigids.size() > 1;
+  std::vector<Solver::ParticlePtr> rigid_ptrs, mpm_ptrs;
+  for (auto ptr : m.particles) (m.allocator[ptr]->is_rigid() ? rigid_ptrs : mpm_ptrs).push_back(ptr);
+  m.particles = mpm_ptrs;
+  if (m.particles.empty()) { m.particles.insert(m.particles.end(), rigid_ptrs.begin(), rigid_ptrs.end()); return 0; }
   MpmbConfig c{};
   for (int d = 0; d < 3; d++) { c.res[d] = m.res[d]; c.gravity[d] = m.gravity[d]; }
   c.dx = m.delta_x; c.dt = m.base_delta_t;
@@ -507,12 +515,63 @@ int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, 
     for (auto &q : m.levelset.levelset0->planes) for (int k = 0; k < 4; k++) pl.push_back(q[k]);
     rc = mpmb_set_planes_(e, (int32_t)m.levelset.levelset0->planes.size(), pl.data(), m.levelset.levelset0->friction);
   }
-  if (rc == MPMB_OK) rc = mpmb_upload_aos_(e, (int64_t)m.particles.size(), m.allocator.pool.data(), (int64_t)m.allocator.pool.size(), m.particles.data(), &L, nullptr);
-  if (rc == MPMB_OK) rc = mpmb_substep_(e, n);
+  const int64_t n_up = (int64_t)m.particles.size();
+  if (rc == MPMB_OK && coupled) {
+    std::vector<float> off, tri;
+    std::vector<int32_t> rid;
+    for (auto ptr : rigid_ptrs) {
+      auto *p = static_cast<RigidBoundaryParticle<3> *>(m.allocator[ptr]);
+      for (int d = 0; d < 3; d++) off.push_back(p->offset[d]);
+      for (int k = 0; k < 3; k++) for (int d = 0; d < 3; d++) tri.push_back(p->untransformed_element.v[k][d]);
+      rid.push_back(p->rigid->id);
+    }
+    rc = mpmb_set_rigid_samples_(e, (int32_t)m.rigids.size(), (int64_t)rid.size(), off.data(), tri.data(), rid.data());
+    if (rc == MPMB_OK) rc = mpmb_set_rigid_coupling_(e, m.penalty, m.pushing_force);
+  }
+  if (rc == MPMB_OK) rc = mpmb_upload_aos_(e, n_up, m.allocator.pool.data(), (int64_t)m.allocator.pool.size(), m.particles.data(), &L, nullptr);
+  if (rc == MPMB_OK && coupled) {  // MPMParticle::states travel by id (= position in the upload)
+    std::vector<uint32_t> st((size_t)n_up);
+    for (int64_t k = 0; k < n_up; k++) st[k] = m.allocator[mpm_ptrs[k]]->states;
+    rc = mpmb_set_particle_states_(e, n_up, st.data());
+  }
+  if (rc == MPMB_OK && !coupled) rc = mpmb_substep_(e, n);
+  for (int s = 0; rc == MPMB_OK && coupled && s < n; s++) {   // the substep loop of INTEGRATION.md §2c: pose in, one substep, velocities out
+    std::vector<MpmbRigidBody> rb(m.rigids.size());
+    for (size_t b = 0; b < m.rigids.size(); b++) {
+      const RigidBody<3> &r = *m.rigids[b];
+      for (int d = 0; d < 3; d++) { rb[b].position[d] = r.position[d]; rb[b].velocity[d] = r.velocity[d]; rb[b].angular_velocity[d] = r.angular_velocity.value[d]; }
+      store(r.rotation.value, rb[b].rot);
+      store(r.inv_inertia, rb[b].inv_inertia);
+      rb[b].inv_mass = r.inv_mass;
+      rb[b].frictions[0] = r.frictions[0]; rb[b].frictions[1] = r.frictions[1];
+    }
+    rc = mpmb_set_rigid_state_(e, (int32_t)rb.size(), rb.data());
+    if (rc == MPMB_OK) rc = mpmb_substep_(e, 1);
+    if (rc == MPMB_OK) rc = mpmb_get_rigid_state_(e, (int32_t)rb.size(), rb.data());
+    for (size_t b = 1; rc == MPMB_OK && b < m.rigids.size(); b++) {
+      m.rigids[b]->velocity = VectorND<3, real>(rb[b].velocity[0], rb[b].velocity[1], rb[b].velocity[2]);
+      m.rigids[b]->angular_velocity.value = VectorND<3, real>(rb[b].angular_velocity[0], rb[b].angular_velocity[1], rb[b].angular_velocity[2]);
+    }
+    m.advect_rigid_bodies(m.base_delta_t);   // host side, as in substep() (src/mpm.cpp:567-569); empty in this harness
+  }
   int64_t alive = 0;
   if (rc == MPMB_OK) rc = mpmb_download_aos_(e, m.allocator.pool.data(), (int64_t)m.allocator.pool.size(), m.particles.data(), (int64_t)m.particles.size(), &L, &alive);
-  if (rc != MPMB_OK) { fail(mpmb_last_error_(e), rc); mpmb_destroy_(e); return rc; }
+  if (rc == MPMB_OK && coupled) {
+    std::vector<uint32_t> st((size_t)n_up);
+    std::vector<float> nrm((size_t)n_up * 3), dist((size_t)n_up);
+    std::vector<uint8_t> nearb((size_t)n_up);
+    rc = mpmb_get_particle_cdf_(e, n_up, st.data(), nrm.data(), dist.data(), nearb.data());
+    for (int64_t k = 0; rc == MPMB_OK && k < n_up; k++) {
+      MPMParticle<3> *p = m.allocator[mpm_ptrs[k]];
+      p->states = st[k];
+      p->boundary_normal = VectorND<3, real>(nrm[3 * k], nrm[3 * k + 1], nrm[3 * k + 2]);
+      p->boundary_distance = dist[k];
+      p->near_boundary_ = nearb[k] != 0;
+    }
+  }
+  if (rc != MPMB_OK) { fail(mpmb_last_error_(e), rc); mpmb_destroy_(e); m.particles.insert(m.particles.end(), rigid_ptrs.begin(), rigid_ptrs.end()); return rc; }
   m.particles.resize((size_t)alive);                      // == what clear_boundary_particles leaves (src/mpm.cpp:583-633)
+  m.particles.insert(m.particles.end(), rigid_ptrs.begin(), rigid_ptrs.end());
   m.current_t += n * m.base_delta_t;
   m.substep_counter += n;
   mpmb_destroy_(e);

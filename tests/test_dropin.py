@@ -50,3 +50,48 @@ def run_dropin(lib_path, kind, tmp_path, nsub=12):
 def test_reference_solver_steps_through_the_c_abi_on_the_emulator(kind, tmp_path):
     from tests.simt import build_simt
     run_dropin(build_simt.build(), kind, tmp_path)
+
+
+def run_dropin_rigid(lib_path, variant, nsub=4):
+    """The same with rigid bodies: body A steps with the reference's own coupled substep
+    (rasterize_rigid_boundary, gather_cdf, block_op_rigid), body B hands pool, boundary samples, particle colours and rigid state
+    to libmpmb through the C-ABI every substep and takes velocities, colours and the reconstructed boundary back."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_rigid_golden", os.path.join(here, "golden", "make_rigid_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    scene, st, rigid = G.golden_scene(variant)
+    a, b = O.RefSolver(scene, st), O.RefSolver(scene, st)
+    for s in (a, b):
+        s.set_rigid(rigid)
+        if st.get("states") is not None:
+            s.set_states(st["states"])
+    a.substep(nsub)                                         # MPM<3>::substep() itself, has_rigid_body() true
+    b.substep_via_mpmb(lib_path, nsub)
+    pa, pb, ca, cb = a.particles(), b.particles(), a.cdf_particles(), b.cdf_particles()
+    ids = pa["alive_ids"]
+    assert len(ids) == len(st["x"]) and np.array_equal(ids, pb["alive_ids"])
+    assert np.abs(pa["x"] - pb["x"]).max() <= 2e-6
+    assert np.abs(pa["v"] - pb["v"]).max() <= 5e-4 * np.abs(pa["v"]).max()
+    assert np.abs(pa["F"] - pb["F"]).max() <= 5e-5
+    same = ca["states"] == cb["states"]
+    assert same.mean() > 0.998                              # a colour decided by two nearly equal weighted distances may differ in fp32
+    assert np.array_equal(ca["near"][same], cb["near"][same]) and np.abs(ca["bdist"] - cb["bdist"])[same].max() <= 1e-4 * scene["dx"] * 32
+    ra, rb = a.rigid_state(), b.rigid_state()
+    for k in range(1, len(rigid["inv_mass"])):
+        dv = ra["velocity"][k] - rigid["velocity"][k]
+        assert np.abs(ra["velocity"][k] - rb["velocity"][k]).max() <= 5e-3 * np.abs(dv).max() + 1e-6
+        assert (np.abs(dv).max() > 1e-3) == (rigid["inv_mass"][k] > 0)
+    # the pool is a valid reference state again (RigidBoundaryParticles back in the index vector): both carry on by themselves
+    a.substep(2); b.substep(2)
+    qa, qb = a.particles(), b.particles()
+    assert np.abs(qa["x"] - qb["x"]).max() <= 4e-6
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("variant", ["dynamic", "two_bodies", "sand_preset"])
+def test_reference_solver_with_rigid_bodies_steps_through_the_c_abi_on_the_emulator(variant):
+    from tests.simt import build_simt
+    run_dropin_rigid(build_simt.build(), variant)

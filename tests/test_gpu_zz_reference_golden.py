@@ -112,3 +112,16 @@ def test_reference_solver_object_steps_through_libmpmb(tmp_path):
     from tests.test_dropin import run_dropin
     capi.lib()
     run_dropin(capi.lib_path(), scenes.MAT_SAND, tmp_path)
+
+
+def test_reference_solver_object_with_rigid_bodies_steps_through_libmpmb():
+    """INTEGRATION.md §2c executed on the device: the reference's MPM<3> object with RigidBoundaryParticles in its pool and two
+    bodies in MPM::rigids steps through libmpmb.so (samples, colours, rigid state in; velocities, colours, boundary out) — against
+    the same object running its own rasterize_rigid_boundary / gather_cdf / block_op_rigid."""
+    from oracle import pyoracle as O
+    if not O.ref_transfer_available():
+        pytest.skip("reference build (oracle/_ref) not available")
+    from taichi_mpm_b200 import capi
+    from tests.test_dropin import run_dropin_rigid
+    capi.lib()
+    run_dropin_rigid(capi.lib_path(), "two_bodies")
