@@ -1327,7 +1327,9 @@ struct RigidView {
   unsigned char *tile_flag;        // [slot]
   uint32_t *p_states;              // MPMParticle::states by particle id - id_base (persists)
   float4 *p_cdf;                   // (boundary_normal, boundary_distance) of this substep
-  unsigned char *p_near;           // near_boundary_ of this substep
+  uint32_t *p_mark;                // (epoch << 1) | near_boundary_: p_cdf / near of a particle count only if its mark carries THIS substep's
+                                   // epoch — gather_cdf then touches only the particles of rigid pages (no 8 M scattered zero-writes)
+  uint32_t epoch;
   uint32_t id_base;
   int id_cap;
   float penalty, pushing_force;
@@ -1354,12 +1356,27 @@ __device__ __forceinline__ float3 rigid_velocity_at(const RigidDev &b, float3 p)
   const float dx = p.x - b.pos[0], dy = p.y - b.pos[1], dz = p.z - b.pos[2];
   return make_float3(b.vel[0] + (b.ang[1] * dz - b.ang[2] * dy), b.vel[1] + (b.ang[2] * dx - b.ang[0] * dz), b.vel[2] + (b.ang[0] * dy - b.ang[1] * dx));
 }
-// apply_tmp_impulse: into six accumulators (shared or global); the division by mass / inertia happens in k_rigid_apply
-__device__ __forceinline__ void rigid_add_impulse(float *acc, const RigidDev &b, float3 j, float3 p) {
-  const float dx = p.x - b.pos[0], dy = p.y - b.pos[1], dz = p.z - b.pos[2];
-  atomicAdd(acc + 0, j.x); atomicAdd(acc + 1, j.y); atomicAdd(acc + 2, j.z);
-  atomicAdd(acc + 3, dy * j.z - dz * j.y); atomicAdd(acc + 4, dz * j.x - dx * j.z); atomicAdd(acc + 5, dx * j.y - dy * j.x);
-}
+// Per-thread impulse accumulator for ONE body at a time: every incompatible (particle, node) pair of a tile otherwise hits the
+// same six shared floats (a 128-way contended CAS loop: 0.97 ms of k_p2g_rigid at config 3's size, profiles/r02g_rigid_cost.json);
+// a thread flushes only when the body changes and at the end of its rows.
+struct ImpulseAcc {
+  float a[6];
+  int id;
+  __device__ __forceinline__ void init() { id = -1; a[0] = a[1] = a[2] = a[3] = a[4] = a[5] = 0.f; }
+  __device__ __forceinline__ void flush(float (*s_acc)[6]) {
+    if (id >= 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) if (a[k] != 0.f) atomicAdd(&s_acc[id][k], a[k]);
+    }
+    a[0] = a[1] = a[2] = a[3] = a[4] = a[5] = 0.f;
+  }
+  __device__ __forceinline__ void add(float (*s_acc)[6], int rid, const RigidDev &b, float3 j, float3 p) {
+    if (rid != id) { flush(s_acc); id = rid; }
+    const float dx = p.x - b.pos[0], dy = p.y - b.pos[1], dz = p.z - b.pos[2];
+    a[0] += j.x; a[1] += j.y; a[2] += j.z;
+    a[3] += dy * j.z - dz * j.y; a[4] += dz * j.x - dx * j.z; a[5] += dx * j.y - dy * j.x;
+  }
+};
 // friction_project (src/mpm_fwd.h:25-57) against a moving base
 __device__ __forceinline__ float3 friction_project_rel(float3 v, float3 base, float3 n, float friction) {
   const float3 r = friction_project0(make_float3(v.x - base.x, v.y - base.y, v.z - base.z), n, friction);
@@ -1458,15 +1475,16 @@ __global__ void __launch_bounds__(128) k_gather_cdf(View V, Params P, RigidView 
   if (row >= V.cnt->n_store) return;
   if (V.keys[row] >= (uint32_t)P.ntiles_total) return;   // dead or migrating
   const float4 q0 = V.q[0][row];
-  const uint32_t id = (__float_as_uint(V.q[6][row].w) & TAG_ID_MASK) - R.id_base;
-  if (id >= (uint32_t)R.id_cap) { atomicOr(&V.cnt->error, DEVERR_BAD_INPUT); return; }
-  R.p_cdf[id] = make_float4(0.f, 0.f, 0.f, 0.f);   // 138-140
-  R.p_near[id] = 0;
   const float X = __fmul_rn(q0.x, P.inv_dx), Y = __fmul_rn(q0.y, P.inv_dx), Z = __fmul_rn(q0.z, P.inv_dx);
-  {  // 142-146: the page of the particle's CELL
+  {  // 142-146: the page of the particle's CELL.  Outside: boundary_distance = 0, normal = 0, near_boundary_ = false (138-140)
+     // and the colours untouched — expressed by NOT renewing the particle's mark
     const int cx = (int)X >> 2, cy = (int)Y >> 2, cz = (int)Z >> 3;
     if (cx < 0 || cy < 0 || cz < 0 || cx >= R.nb[0] || cy >= R.nb[1] || cz >= R.nb[2] || !R.page[((size_t)cx * R.nb[1] + cy) * R.nb[2] + cz]) return;
   }
+  const uint32_t id = (__float_as_uint(V.q[6][row].w) & TAG_ID_MASK) - R.id_base;
+  if (id >= (uint32_t)R.id_cap) { atomicOr(&V.cnt->error, DEVERR_BAD_INPUT); return; }
+  R.p_cdf[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+  R.p_mark[id] = R.epoch << 1;
   int bx, by, bz;
   float rx, ry, rz;
   base_rel(q0.x, P.inv_dx, bx, rx);
@@ -1537,7 +1555,7 @@ __global__ void __launch_bounds__(128) k_gather_cdf(View V, Params P, RigidView 
     }
     float sol[4];
     for (int r = 3; r >= 0; r--) { float sum = A[r][4]; for (int c = r + 1; c < 4; c++) sum -= A[r][c] * sol[c]; sol[r] = sum / A[r][r]; }
-    R.p_near[id] = 1;
+    R.p_mark[id] = (R.epoch << 1) | 1u;
     const float l2 = sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2];
     float4 o = make_float4(0.f, 0.f, 0.f, sol[3] * P.dx);
     if (l2 > 1e-4f) { const float il = 1.0f / sqrtf(l2); o.x = sol[0] * il; o.y = sol[1] * il; o.z = sol[2] * il; }
@@ -1570,7 +1588,14 @@ __global__ void __launch_bounds__(128) k_p2g_rigid(View V, Params P, RigidView R
     load_tile_words(R, P, tx, ty, tz, s_word);
     __syncthreads();
     const int nrow = tm.run_len + tm.arr_len;
-    for (int g = tid; g < nrow; g += blockDim.x) {
+    // A tile's run is cell-sorted, so neighbouring rows scatter to the same nodes: lanes take rows a large odd stride apart
+    // (a bijection of [0, nrow)), which cuts the retries of the shared float atomics (CAS loops) — measured at config 3's size
+    // with a 13 740-sample paddle: k_p2g_rigid 1.73 ms with rows in order (profiles/r02f_rigid_cost.json)
+    const int stride = (nrow % 61) ? 61 : ((nrow % 67) ? 67 : 1);
+    ImpulseAcc imp;
+    imp.init();
+    for (int idx = tid; idx < nrow; idx += blockDim.x) {
+      const int g = (int)(((long long)idx * stride) % nrow);
       const uint32_t row = g < tm.run_len ? (uint32_t)(tm.run_begin + g) : V.arrivals_sorted[tm.arr_off + (g - tm.run_len)];
       const float4 a0 = V.q[0][row];
       if (g < tm.run_len && !(a0.w > 0.f)) continue;   // hole
@@ -1579,7 +1604,8 @@ __global__ void __launch_bounds__(128) k_p2g_rigid(View V, Params P, RigidView R
       const float mass = fabsf(a0.w);
       const uint32_t id = (__float_as_uint(V.q[6][row].w) & TAG_ID_MASK) - R.id_base;
       const uint32_t pst = id < (uint32_t)R.id_cap ? R.p_states[id] : 0u;
-      const float4 pc = id < (uint32_t)R.id_cap ? R.p_cdf[id] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool fresh = id < (uint32_t)R.id_cap && (R.p_mark[id] >> 1) == R.epoch;   // gather_cdf saw this particle in this substep
+      const float4 pc = fresh ? R.p_cdf[id] : make_float4(0.f, 0.f, 0.f, 0.f);
       float3 v = make_float3(a1.x, a1.y, a1.z);
       if (P.particle_gravity) { v.x += P.gdt[0]; v.y += P.gdt[1]; v.z += P.gdt[2]; }
       int bx, by, bz;
@@ -1616,7 +1642,7 @@ __global__ void __launch_bounds__(128) k_p2g_rigid(View V, Params P, RigidView R
           const float dwx = (gx[a] * wy[b]) * wz[c], dwy = (wx[a] * gy[b]) * wz[c], dwz = (wx[a] * wy[b]) * gz[c];
           const float3 j = make_float3(mass * w * (v.x - pr.x) + (tf[0] * dwx + tf[3] * dwy + tf[6] * dwz), mass * w * (v.y - pr.y) + (tf[1] * dwx + tf[4] * dwy + tf[7] * dwz),
                                        mass * w * (v.z - pr.z) + (tf[2] * dwx + tf[5] * dwy + tf[8] * dwz));
-          rigid_add_impulse(s_acc[rid], B, j, gp);
+          imp.add(s_acc, rid, B, j, gp);
           continue;
         }
         atomicAdd(&s_arena[0][ln], w * (mass * v.x + (A[0] * dpx + A[3] * dpy + A[6] * dpz)));   // 451-459
@@ -1625,6 +1651,7 @@ __global__ void __launch_bounds__(128) k_p2g_rigid(View V, Params P, RigidView R
         atomicAdd(&s_arena[3][ln], w * mass);
       }
     }
+    imp.flush(s_acc);
     __syncthreads();
     float4 *out = V.arena + (size_t)slot * ARENA;
     for (int n = tid; n < ARENA; n += blockDim.x) out[n] = make_float4(s_arena[0][n], s_arena[1][n], s_arena[2][n], s_arena[3][n]);
@@ -1653,6 +1680,7 @@ __global__ void k_rigid_apply(RigidView R) {
 __global__ void __launch_bounds__(128) k_g2p_rigid(View V, Params P, RigidView R, const float4 *vel) {
   __shared__ float4 s_vel[ARENA];
   __shared__ uint32_t s_word[ARENA];
+  __shared__ float s_acc[RIGID_MAX][6];
   __shared__ int s_stay;
   const int tid = threadIdx.x;
   const int n_tiles = V.cnt->n_tiles;
@@ -1663,11 +1691,14 @@ __global__ void __launch_bounds__(128) k_g2p_rigid(View V, Params P, RigidView R
     const int tile = tm.tile;
     MPMB_TILE_XYZ(P, tm, tx, ty, tz);
     for (int n = tid; n < ARENA; n += blockDim.x) s_vel[n] = vel[(size_t)slot * ARENA + n];
+    for (int n = tid; n < RIGID_MAX * 6; n += blockDim.x) (&s_acc[0][0])[n] = 0.f;
     load_tile_words(R, P, tx, ty, tz, s_word);
     if (tid == 0) s_stay = 0;
     __syncthreads();
     const int nrow = tm.run_len + tm.arr_len;
     int my_stay = 0;
+    ImpulseAcc imp;
+    imp.init();
     for (int g = tid; g < nrow; g += blockDim.x) {
       const uint32_t row = g < tm.run_len ? (uint32_t)(tm.run_begin + g) : V.arrivals_sorted[tm.arr_off + (g - tm.run_len)];
       const float4 q0 = V.q[0][row];
@@ -1680,8 +1711,10 @@ __global__ void __launch_bounds__(128) k_g2p_rigid(View V, Params P, RigidView R
       const uint32_t id = (tag & TAG_ID_MASK) - R.id_base;
       const bool known = id < (uint32_t)R.id_cap;
       const uint32_t pst = known ? R.p_states[id] : 0u;
-      const float4 pc = known ? R.p_cdf[id] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const bool near = known && R.p_near[id];
+      const uint32_t mark = known ? R.p_mark[id] : 0u;
+      const bool fresh = known && (mark >> 1) == R.epoch;   // gather_cdf saw this particle in this substep
+      const float4 pc = fresh ? R.p_cdf[id] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool near = fresh && (mark & 1u);
       const float3 bn = make_float3(pc.x, pc.y, pc.z);
       // p.get_velocity() as rasterize left it: the gravity kick is stored back there (src/transfer.cpp:383-385)
       float3 pv = make_float3(q1.x, q1.y, q1.z);
@@ -1742,7 +1775,7 @@ __global__ void __launch_bounds__(128) k_g2p_rigid(View V, Params P, RigidView R
       if (near && pc.w < -0.05f * P.dx && pc.w > -P.dx * 0.3f) {   // 823-832: position correction
         const float3 dv = make_float3(pc.w * bn.x * R.penalty, pc.w * bn.y * R.penalty, pc.w * bn.z * R.penalty);
         v.x -= dv.x; v.y -= dv.y; v.z -= dv.z;
-        if (rigid_id != -1) rigid_add_impulse(R.bodies[rigid_id].acc, R.bodies[rigid_id], make_float3(dv.x * mass, dv.y * mass, dv.z * mass), x);
+        if (rigid_id != -1) imp.add(s_acc, rigid_id, R.bodies[rigid_id], make_float3(dv.x * mass, dv.y * mass, dv.z * mass), x);
       }
       uint32_t key = make_key(P, x.x, x.y, x.z);
       if (P.clean_boundary && reference_deletes(P, x, v)) key = (uint32_t)(P.ntiles_total + SPECIAL_DEAD);
@@ -1760,8 +1793,13 @@ __global__ void __launch_bounds__(128) k_g2p_rigid(View V, Params P, RigidView R
       }
     }
     if (my_stay) atomicAdd(&s_stay, my_stay);
+    imp.flush(s_acc);
     __syncthreads();
     if (tid == 0) V.stay_next[tile] = s_stay;
+    for (int n = tid; n < RIGID_MAX * 6; n += blockDim.x) {
+      const float a = (&s_acc[0][0])[n];
+      if (a != 0.f) atomicAdd(&R.bodies[n / 6].acc[n % 6], a);
+    }
     __syncthreads();
   }
 }
@@ -2462,7 +2500,7 @@ int mpmb_destroy(MpmbHandle h) {
   graph_reset(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   cudaFree(h->R.bodies); cudaFree(h->rs_offset); cudaFree(h->rs_tri); cudaFree(h->rs_rigid); cudaFree(h->R.s_base); cudaFree(h->R.node_key);
-  cudaFree(h->R.node_tags); cudaFree(h->R.page); cudaFree(h->R.tile_flag); cudaFree(h->R.p_states); cudaFree(h->R.p_cdf); cudaFree(h->R.p_near);
+  cudaFree(h->R.node_tags); cudaFree(h->R.page); cudaFree(h->R.tile_flag); cudaFree(h->R.p_states); cudaFree(h->R.p_cdf); cudaFree(h->R.p_mark);
 
   delete h;
   return MPMB_OK;
@@ -2993,17 +3031,17 @@ static int rigid_reserve_ids(MpmbEngine *h, int64_t n_ids) {
   const int64_t cap = std::max<int64_t>(n_ids, 1024);
   uint32_t *st = nullptr;
   float4 *cdf = nullptr;
-  unsigned char *nr = nullptr;
+  uint32_t *nr = nullptr;
   CUDA_TRY(h, cudaMalloc(&st, sizeof(uint32_t) * cap));
   CUDA_TRY(h, cudaMalloc(&cdf, sizeof(float4) * cap));
-  CUDA_TRY(h, cudaMalloc(&nr, cap));
+  CUDA_TRY(h, cudaMalloc(&nr, sizeof(uint32_t) * cap));
   CUDA_TRY(h, cudaMemsetAsync(st, 0, sizeof(uint32_t) * cap, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(cdf, 0, sizeof(float4) * cap, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(nr, 0, cap, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(nr, 0, sizeof(uint32_t) * cap, h->stream));   // epoch 0 is never current
   if (h->R.p_states && h->R.id_cap > 0) CUDA_TRY(h, cudaMemcpyAsync(st, h->R.p_states, sizeof(uint32_t) * h->R.id_cap, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  cudaFree(h->R.p_states); cudaFree(h->R.p_cdf); cudaFree(h->R.p_near);
-  h->R.p_states = st; h->R.p_cdf = cdf; h->R.p_near = nr;
+  cudaFree(h->R.p_states); cudaFree(h->R.p_cdf); cudaFree(h->R.p_mark);
+  h->R.p_states = st; h->R.p_cdf = cdf; h->R.p_mark = nr;
   h->R.id_cap = (int)cap;
   return MPMB_OK;
 }
@@ -3013,6 +3051,8 @@ static int rigid_prepare(MpmbEngine *h, const View &V, int *nl) {
   RigidView &R = h->R;
   R.id_base = h->id_base;
   if (!R.p_states) { int rc = rigid_reserve_ids(h, h->cap); if (rc != MPMB_OK) return rc; }
+  R.epoch = (R.epoch + 1u) & 0x7fffffffu;
+  if (R.epoch == 0u) R.epoch = 1u;
   const int ns = R.n_samples, sb = (ns + 127) / 128;
   k_cdf_clear<<<sb, 128, 0, h->stream>>>(R, h->P);
   CUDA_TRY(h, cudaMemsetAsync(R.page, 0, (size_t)R.nb[0] * R.nb[1] * R.nb[2], h->stream));
@@ -3131,13 +3171,16 @@ int mpmb_get_particle_cdf(MpmbHandle h, int64_t n, uint32_t *states, float *norm
   if (!h->rigid_on || !h->R.p_states) return fail(h, MPMB_ERR_STATE, "no rigid bodies / no substep yet");
   if (n < 0 || n > h->R.id_cap) return fail(h, MPMB_ERR_INVALID, "n exceeds the %d particle ids tracked", h->R.id_cap);
   std::vector<float4> cdf((size_t)n);
+  std::vector<uint32_t> mark((size_t)n);
   if (states) CUDA_TRY(h, cudaMemcpyAsync(states, h->R.p_states, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
-  if (near_boundary) CUDA_TRY(h, cudaMemcpyAsync(near_boundary, h->R.p_near, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(mark.data(), h->R.p_mark, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(cdf.data(), h->R.p_cdf, sizeof(float4) * n, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  for (int64_t i = 0; i < n; i++) {
-    if (normal3) { normal3[3 * i] = cdf[i].x; normal3[3 * i + 1] = cdf[i].y; normal3[3 * i + 2] = cdf[i].z; }
-    if (distance) distance[i] = cdf[i].w;
+  for (int64_t i = 0; i < n; i++) {   // particles gather_cdf did not see in the last substep: distance 0, normal 0, not near (138-146)
+    const bool fresh = (mark[i] >> 1) == h->R.epoch;
+    if (normal3) { normal3[3 * i] = fresh ? cdf[i].x : 0.f; normal3[3 * i + 1] = fresh ? cdf[i].y : 0.f; normal3[3 * i + 2] = fresh ? cdf[i].z : 0.f; }
+    if (distance) distance[i] = fresh ? cdf[i].w : 0.f;
+    if (near_boundary) near_boundary[i] = (fresh && (mark[i] & 1u)) ? 1 : 0;
   }
   return MPMB_OK;
 }

@@ -241,3 +241,60 @@ def test_mirror_scripted_body_follows_its_functions_and_keeps_infinite_mass():
     with pytest.raises(ValueError):
         m.add_particles(type="rigid", tris=scenes.plate_mesh(0.1, 0.1), codimensional=True, initial_position=(0.5, 0.5, 0.5),
                         scripted_position=lambda t: (0.5, 0.5, 0.5))
+
+
+def test_rigid_state_survives_reupload_resampling_and_bodies_near_the_domain_edge():
+    from oracle import pyoracle as O
+    scene, st, rigid = _scene(dynamic=True)
+    n = len(st["x"])
+    e = _engine(scene, st, rigid)
+    e.substep(2)
+    # (1) new boundary samples with a different count (a second body appears), then a re-upload: colours restart at 0
+    scene2, st2, rigid2 = _scene(two_bodies=True)
+    e.set_rigid(rigid2)
+    e.upload(st2["x"], st2["v"], st2["mass"], st2["vol"], st2["F"], st2["b"], st2["ps"], st2["group"])
+    ref, _, _, rref, cdf = O.substep_coupled(scene2, st2, rigid2, np.float64)
+    e.sort_particles_and_populate_grid()
+    assert np.array_equal(e.download_cdf()["node_state"], cdf["node_state"])      # nothing of the first body's old field is left
+    assert np.array_equal(e.get_particle_cdf(n)["states"], ref["states"])
+    e.rasterize(); e.resample()
+    got = e.download()
+    assert np.abs(got["x"] - ref["x"][got["id"].astype(np.int64)]).max() <= T.TOL_X_ABS
+    # (2) a body whose samples reach outside the node grid: those samples are skipped (no stencil), the rest still colour nodes
+    far = dict(rigid2)
+    far["position"] = rigid2["position"].copy()
+    far["position"][2] = (0.5, 0.995, 0.5)
+    e.set_rigid_state(far)
+    e.substep(1)
+    assert np.isfinite(e.download()["x"]).all()
+    # (3) coupling off again: the plain substep, bit for bit what an engine that never saw a body computes
+    e.set_rigid(dict(rigid, sample_offset=np.zeros((0, 3)), sample_tri=np.zeros((0, 9)), sample_rigid=np.zeros(0, np.int32)))
+    e.upload(st["x"], st["v"], st["mass"], st["vol"], st["F"], st["b"], st["ps"], st["group"])
+    f = T.make_engine(scene, st)
+    e.substep(3); f.substep(3)
+    a, b = e.download(), f.download()
+    for k in ("x", "v", "F"):
+        assert np.array_equal(a[k], b[k]), k
+    e.close(); f.close()
+
+
+def test_two_bodies_claiming_one_node_the_nearer_one_wins_and_both_leave_their_tags():
+    # two parallel plates less than a cell apart: nodes between them carry both bodies' tag bits and the id of the nearer
+    # (src/rigid_transfer.cpp:65-74)
+    from oracle import pyoracle as O
+    scene, st, _ = _scene()
+    dx = scene["dx"]
+    c = st["x"].mean(0)
+    rot = scenes.euler_rotation((3.0, 8.0, 2.0))
+    mk = lambda off: dict(tris=scenes.plate_mesh(0.1, 0.1, axis=1), position=c + np.array([0.0, off, 0.0]), rotation=rot, friction=0.1)
+    rigid = scenes.make_rigid([mk(0.0), mk(0.6 * dx)], dx)
+    ref, _, _, _, cdf = O.substep_coupled(scene, st, rigid, np.float64)
+    tags = cdf["node_state"] & 0xFFFFFF
+    both = ((tags & 0b1000) != 0) & ((tags & 0b100000) != 0)
+    assert both.sum() > 50 and len(np.unique(cdf["node_state"][both] >> 24)) == 2     # both ids occur as the nearer body
+    e = _engine(scene, st, rigid)
+    e.sort_particles_and_populate_grid()
+    d = e.download_cdf()
+    assert np.array_equal(d["node_state"], cdf["node_state"])
+    assert np.array_equal(e.get_particle_cdf(len(st["x"]))["states"], ref["states"])
+    e.close()
