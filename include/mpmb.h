@@ -121,6 +121,11 @@ int mpmb_set_material(MpmbHandle h, int32_t group, int32_t kind, const float *pa
 /* (Called with particles of `group` already resident — between substeps — it also rebuilds their cached
  * affine matrices, so the next rasterize uses the new material's stress; apic_b must be current, i.e. the
  * call follows an upload or a completed mpmb_substep / mpmb_resample.)                              */
+/* `base_delta_t` of the following substeps.  MPM<3> keeps it fixed, but AsyncMPM sets it before every MPM<dim>::substep() it
+ * schedules (src/async/async_mpm.cpp:407-409: base_delta_t = unit_delta_t * delta_t_int), and a host that adapts its step does
+ * the same.  With particles resident their cached affine matrices are rebuilt for the new step (apic_b must be current, as for
+ * mpmb_set_material); an upload after the call needs nothing.  Between substeps only.                                      */
+int mpmb_set_delta_t(MpmbHandle h, float dt);
 /* Replaces Simulation::set_levelset + DynamicLevelSet::sample/get_spatial_gradient as used by
  * apply_grid_boundary_conditions (src/mpm.cpp:296-372) for a static level set.  `sdf4` is a host
  * array [res0+1][res1+1][res2+1][4] = (n_x,n_y,n_z,phi), phi in grid units at the node, n the

@@ -21,7 +21,7 @@ MATERIAL_BY_NAME = {"linear": MAT_LINEAR, "jelly": MAT_JELLY, "snow": MAT_SNOW, 
 # every symbol include/mpmb.h declares
 EXPORTS = [
     "mpmb_create", "mpmb_destroy", "mpmb_last_error", "mpmb_version", "mpmb_set_stream", "mpmb_synchronize",
-    "mpmb_set_material", "mpmb_set_sdf", "mpmb_set_planes", "mpmb_set_levelset_shapes", "mpmb_set_id_base",
+    "mpmb_set_material", "mpmb_set_delta_t", "mpmb_set_sdf", "mpmb_set_planes", "mpmb_set_levelset_shapes", "mpmb_set_id_base",
     "mpmb_upload_particles", "mpmb_upload_aos", "mpmb_seed_lattice", "mpmb_num_particles", "mpmb_get_update_count", "mpmb_download_bgeo_points", "mpmb_download_particles", "mpmb_download_aos",
     "mpmb_substep", "mpmb_sort_particles_and_populate_grid", "mpmb_rasterize", "mpmb_resample", "mpmb_rasterize_part",
     "mpmb_resample_part", "mpmb_download_grid",
@@ -176,6 +176,9 @@ class Engine:
         p = np.zeros(MPMB_MAT_PARAMS, np.float32)
         p[: len(params)] = params
         self._check(self.L.mpmb_set_material(self.h, C.c_int32(group), C.c_int32(kind), _ptr(p), C.c_int32(len(params))))
+
+    def set_delta_t(self, dt):
+        self._check(self.L.mpmb_set_delta_t(self.h, C.c_float(float(dt))))
 
     def set_sdf(self, sdf4, friction):
         if sdf4 is not None:

@@ -2548,6 +2548,32 @@ int mpmb_set_material(MpmbHandle h, int32_t group, int32_t kind, const float *pa
   return MPMB_OK;
 }
 
+int mpmb_set_delta_t(MpmbHandle h, float dt) {
+  CHECK_HANDLE(h);
+  if (!(dt > 0.f) || !std::isfinite(dt)) return fail(h, MPMB_ERR_INVALID, "delta_t must be positive and finite");
+  if (h->stage != 0) return fail(h, MPMB_ERR_STATE, "delta_t changes between substeps, not inside one");
+  if (dt == h->P.dt) return MPMB_OK;
+  h->cfg.dt = dt;
+  h->P.dt = dt;
+  for (int d = 0; d < 3; d++) h->P.gdt[d] = h->cfg.gravity[d] * dt;
+  graph_reset(h);
+  // resident particles: the affine matrix cached for the next rasterize carries the old dt (stress * (-4 dt / dx))
+  if (h->cap > 0) {
+    int ns = 0;
+    int rc = read_n_store(h, &ns);
+    if (rc != MPMB_OK) return rc;
+    if (ns > 0) {
+      View V = make_view(h);
+      for (int g = 0; g < MPMB_MAX_GROUPS; g++) {
+        k_refresh_affine<<<(ns + 127) / 128, 128, 0, h->stream>>>(V, h->P, h->keys[h->cur], ns, h->special_min, g);
+        h->launches++;
+      }
+      CUDA_TRY(h, cudaGetLastError());
+    }
+  }
+  return MPMB_OK;
+}
+
 int mpmb_set_id_base(MpmbHandle h, int64_t base) {
   CHECK_HANDLE(h);
   if (base < 0 || base >= (1ll << TAG_ID_BITS)) return fail(h, MPMB_ERR_INVALID, "id base %lld outside [0, 2^%d)", (long long)base, TAG_ID_BITS);

@@ -386,3 +386,40 @@ def test_graph_replay_is_bit_identical_to_host_launches_and_follows_state_change
     for k in ("id", "x", "v", "F", "ps", "b"):
         assert np.array_equal(out[0][0][k], out[1][0][k]), k
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
+
+
+@pytest.mark.parametrize("name,kind", [("sand", scenes.MAT_SAND), ("jelly", scenes.MAT_JELLY)])
+def test_delta_t_changes_between_substeps_as_asyncmpm_sets_it(name, kind):
+    # AsyncMPM sets base_delta_t before every MPM::substep() it schedules (src/async/async_mpm.cpp:407-409): resident particles
+    # keep going with the new step (their cached affine matrices are rebuilt), and an upload after the change needs nothing
+    from oracle import pyoracle as O
+    scene, st = T.perturbed_scene(kind, res=32, cells=6, seed=51, vel=0.4)
+    dts = [scene["dt"], scene["dt"] * 0.5, scene["dt"] * 0.25, scene["dt"]]
+    cur = st
+    for dt in dts:
+        cur, _, _ = O.substep(dict(scene, dt=dt), cur, np.float64)
+    e = T.make_engine(scene, st)
+    for dt in dts:
+        e.set_delta_t(dt)
+        e.substep(1)
+    got = e.download()
+    ids = got["id"].astype(np.int64)
+    assert np.array_equal(np.sort(ids), np.nonzero(cur["alive"])[0])
+    vmax = np.abs(cur["v"]).max()
+    assert np.abs(got["x"] - cur["x"][ids]).max() <= 4 * T.TOL_X_ABS
+    assert np.abs(got["v"] - cur["v"][ids]).max() <= 4 * T.TOL_V_REL * vmax
+    assert np.abs(got["F"] - cur["F"][ids]).max() <= 4 * T.TOL_F_ABS
+    # the same through a re-upload under the new step, and it is not what the old step would have given
+    f = T.make_engine(scene, st)
+    f.set_delta_t(dts[1])
+    f.upload(st["x"], st["v"], st["mass"], st["vol"], st["F"], st["b"], st["ps"], st["group"])
+    f.substep(1)
+    one, _, _ = O.substep(dict(scene, dt=dts[1]), st, np.float64)
+    same_dt, _, _ = O.substep(scene, st, np.float64)
+    g = f.download()
+    assert np.abs(g["x"] - one["x"][g["id"].astype(np.int64)]).max() <= T.TOL_X_ABS
+    assert np.abs(one["x"] - same_dt["x"]).max() > 3 * T.TOL_X_ABS
+    from taichi_mpm_b200 import capi
+    with pytest.raises(capi.MpmbError):
+        f.set_delta_t(0.0)
+    e.close(); f.close()

@@ -113,3 +113,56 @@ def test_sand_large_strain_takes_the_eigen_path_on_the_device(strain):
     assert err["grid_rast"] <= T.TOL_GRID_REL
     assert err["v"] <= T.TOL_V_REL and err["b"] <= T.TOL_V_REL and err["x"] <= T.TOL_X_ABS
     assert err["F"] <= T.TOL_F_ABS * max(1.0, 10 * strain) and err["ps"] <= T.TOL_PS_ABS * max(1.0, 10 * strain)
+
+
+def test_full_size_config2_with_rigid_bodies_one_coupled_substep_vs_fp64_oracle():
+    # BASELINE config 2 (128^3 grid, 1.0 M jelly particles, every particle perturbed) cut by a tilted free plate and holding a small
+    # free box: one coupled substep — colour field, gather_cdf, both transfers with their impulses — per particle against the oracle's
+    # restatement of the reference's CPIC path (itself pinned to src/rigid_transfer.cpp / block_op_rigid run in place)
+    from oracle import pyoracle as O
+    scene, st = _perturbed_config("jelly128", 1.0, seed=81, strain=0.01, vel=0.3)
+    n = len(st["x"])
+    assert n == 1000000
+    c = st["x"].mean(0)
+    dx = scene["dx"]
+    plate = dict(tris=scenes.plate_mesh(0.27, 0.23, axis=1), position=c + np.array([0.004, 0.031, -0.003]), rotation=scenes.euler_rotation((7.0, 13.0, -5.0)),
+                 velocity=(0.1, -0.8, 0.05), angular_velocity=(0.3, 0.0, -0.4), frictions=(0.3, 0.5), inv_mass=1 / 30.0, inv_inertia=np.diag([4.0, 2.5, 4.0]))
+    box = dict(tris=scenes.box_mesh((0.05, 0.04, 0.06)), position=c + np.array([0.09, -0.08, 0.02]), rotation=scenes.euler_rotation((20.0, 5.0, 33.0)),
+               velocity=(-0.5, 0.0, 0.2), friction=-1.0, inv_mass=0.2, inv_inertia=np.diag([30.0, 30.0, 30.0]))
+    rigid = scenes.make_rigid([plate, box], dx, penalty=1e3)
+    ref, grid_rast, _, rref, cdf = O.substep_coupled(scene, st, rigid, np.float64)
+    e = T.make_engine(dict(scene, sdf=None), st)
+    e.set_rigid(rigid)
+    e.sort_particles_and_populate_grid()
+    assert np.array_equal(e.download_cdf()["node_state"], cdf["node_state"])
+    pc = e.get_particle_cdf(n)
+    same = pc["states"] == ref["states"]
+    assert (ref["states"] != 0).sum() > 50000 and same.mean() > 1 - 2e-5       # a colour decided by two nearly equal weighted distances may flip in fp32
+    assert np.array_equal(pc["near"][same], ref["near"][same]) and ref["near"].sum() > 20000
+    e.rasterize()
+    g0 = e.download_grid(0).astype(np.float64)
+    pmax = max(np.abs(grid_rast[..., :3]).max(), grid_rast[..., 3].max())
+    flipped_cells = (~same).sum()
+    assert np.abs(g0 - grid_rast).max() <= (T.TOL_GRID_REL if flipped_cells == 0 else 1e-3) * pmax
+    e.resample()
+    got = e.download()
+    rs = e.get_rigid_state(3)
+    e.close()
+    alive = ref["alive"].astype(bool)
+    ids = got["id"].astype(np.int64)
+    assert np.array_equal(ids, np.nonzero(alive)[0])
+    ok = same[ids]
+    if flipped_cells:   # a flipped colour changes the node values its particle scatters to: compare away from those particles' stencils
+        bad = np.zeros(n, bool)
+        bx = np.floor(st["x"] / dx).astype(int)
+        for p in np.nonzero(~same)[0]:
+            bad |= (np.abs(bx - bx[p]).max(1) <= 3)
+        ok &= ~bad[ids]
+    vmax = np.abs(ref["v"]).max()
+    err = dict(x=np.abs(got["x"] - ref["x"][ids])[ok].max(), v=np.abs(got["v"] - ref["v"][ids])[ok].max() / vmax,
+               b=np.abs(got["b"] - ref["b"][ids])[ok].max() / np.abs(ref["b"]).max(), F=np.abs(got["F"] - ref["F"][ids])[ok].max(), ps=0.0)
+    _check(err, "config 2 + rigid bodies vs fp64 oracle (%d colour flips of %d coloured particles)" % (flipped_cells, int((ref["states"] != 0).sum())))
+    for b in (1, 2):
+        dv = rref["velocity"][b] - rigid["velocity"][b]
+        assert np.abs(dv).max() > 1e-4
+        assert np.abs((rs["velocity"][b] - rigid["velocity"][b]) - dv).max() <= 5e-3 * np.abs(dv).max() + 1e-6
