@@ -605,6 +605,69 @@ class RefSolver:
             pass
 
 
+class RefAsyncSolver:
+    """The reference's AsyncMPM<3> object (src/async/async_mpm.{h,cpp} compiled in place, oracle/transfer_ref.cpp): its own
+    scheduler — per-block power-of-two time levels, backup pools, update_dt_limits / advance / step — around MPM<3>::substep(),
+    which runs either as the reference's own code or, after route_through(lib), on libmpmb through the C-ABI (the drop-in patch
+    point; base_delta_t changes from call to call).  One material; fp32."""
+
+    def __init__(self, scene, state, unit_delta_t, max_units=8192, cfl_dt_mul=1.0, strength_dt_mul=1.0):
+        L = ref_transfer()
+        f32 = np.float32
+        self.L = L
+        self.res = np.ascontiguousarray(scene["res"], np.int32)
+        g = np.ascontiguousarray(scene["gravity"], f32)
+        L.reft_create_async.restype = C.c_void_p
+        self.h = C.c_void_p(L.reft_create_async(_p(self.res), C.c_float(scene["dx"]), _p(g), C.c_int(int(scene.get("particle_gravity", 1))),
+                                                C.c_float(unit_delta_t), C.c_int64(int(max_units)), C.c_float(cfl_dt_mul), C.c_float(strength_dt_mul)))
+        kinds = np.asarray(scene["mat_kind"], np.int32)
+        prm = np.zeros(N_MAT_PARAMS, f32)
+        prm[: len(scene["mat_params"][0])] = scene["mat_params"][0]
+        st = {k: np.ascontiguousarray(state[k], f32) for k in ("x", "v", "F", "b", "mass", "vol", "ps")}
+        self.n = len(st["x"])
+        L.reft_add_particles.restype = C.c_int64
+        assert L.reft_add_particles(self.h, C.c_int(int(kinds[0])), _p(prm), C.c_int64(self.n), _p(st["x"]), _p(st["v"]), _p(st["mass"]), _p(st["vol"]),
+                                    _p(st["F"]), _p(st["b"]), _p(st["ps"])) == self.n
+        if scene.get("planes") is not None:
+            pl = np.ascontiguousarray(scene["planes"], f32).reshape(-1, 4)
+            L.reft_set_planes(self.h, C.c_int(len(pl)), _p(pl), C.c_float(scene.get("friction", 0.0)))
+        L.reft_async_distribute(self.h)
+
+    def route_through(self, lib_path):
+        self.L.reft_route_through(self.h, str(lib_path or "").encode())
+
+    def step(self, dt):
+        """AsyncMPM<3>::step(dt).  Returns dict(alive, update_counter, current_t_int, min_level, max_level, routed_substeps)."""
+        self.L.reft_async_step.restype = C.c_int64
+        self.L.reft_routed_substeps.restype = C.c_int64
+        out = np.zeros(4, np.int64)
+        n = int(self.L.reft_async_step(self.h, C.c_float(float(dt)), _p(out)))
+        if n < 0:
+            self.L.reft_route_error.restype = C.c_char_p
+            raise RuntimeError("routed substep failed: " + self.L.reft_route_error(self.h).decode(errors="replace"))
+        return dict(alive=n, update_counter=int(out[0]), current_t_int=int(out[1]), min_level=int(out[2]), max_level=int(out[3]),
+                    routed_substeps=int(self.L.reft_routed_substeps(self.h)))
+
+    def particles(self):
+        n, f32 = self.n, np.float32
+        out = dict(x=np.zeros((n, 3), f32), v=np.zeros((n, 3), f32), F=np.zeros((n, 9), f32), b=np.zeros((n, 9), f32), ps=np.zeros(n, f32),
+                   alive=np.zeros(n, np.uint8))
+        self.L.reft_async_get_particles.restype = C.c_int64
+        self.L.reft_async_get_particles(self.h, _p(out["x"]), _p(out["v"]), _p(out["F"]), _p(out["b"]), _p(out["ps"]), _p(out["alive"]))
+        return out
+
+    def close(self):
+        if self.h is not None:
+            self.L.reft_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def ref_transfer_substep(scene, state, grid_vel, optimized=True):
     """One substep's two transfers by the reference's own code (src/transfer.cpp), fp32:
     P2G = rasterize_optimized / rasterize on the given particles -> dense node (momentum, mass);

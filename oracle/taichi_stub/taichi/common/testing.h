@@ -2,6 +2,6 @@
 // the core's unit-test macros: the bodies still have to compile, they are never run here
 #include <taichi/util.h>
 // never instantiated: the bodies are parsed, nothing in them is generated
-#define TC_TEST(name) template <class TcStubNeverInstantiated> static void TC_STUB_CAT(tc_stub_test_, __LINE__)()
+#define TC_TEST(name) template <typename TcStubNeverInstantiated> static void TC_STUB_CAT(tc_stub_test_, __LINE__)()
 #define TC_CHECK_EQUAL(a, b, tol) ((void)(a), (void)(b), (void)(tol))
 #define TC_CHECK(x) ((void)(x))

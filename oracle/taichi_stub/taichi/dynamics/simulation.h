@@ -55,7 +55,7 @@ class Simulation : public Unit {
   real current_t = 0;
   int num_threads = 1;
   DynamicLevelSet<dim> levelset;
-  template <class S> void io(S &) {}
+  template <class S> void io(S &) const {}
   virtual std::string add_particles(const Config &) { return ""; }
   virtual void step(real) {}
   virtual std::vector<RenderParticle> get_render_particles() const { return {}; }
@@ -63,6 +63,8 @@ class Simulation : public Unit {
   virtual std::string general_action(const Config &) { return ""; }
   virtual std::string get_debug_information() { return ""; }
   virtual bool test() const { return true; }
+  virtual void binary_io(BinaryOutputSerializer &) const {}   // AsyncMPM overrides both (src/async/async_mpm.h:119-124)
+  virtual void binary_io(BinaryInputSerializer &) const {}
 };
 using Simulation2D = Simulation<2>;
 using Simulation3D = Simulation<3>;

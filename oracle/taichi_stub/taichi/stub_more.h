@@ -70,5 +70,25 @@ template <class It> inline void parallel_sort(It b, It e) {
 #endif
   std::sort(b, e);
 }
+// What src/async/async_mpm.{h,cpp} names of TBB (serial stand-ins: one "thread", vectors are std::vector)
+template <class T> struct blocked_range {
+  T b, e;
+  blocked_range(T b_, T e_) : b(b_), e(e_) {}
+  T begin() const { return b; }
+  T end() const { return e; }
+};
+template <class T, class F> inline void parallel_for(const blocked_range<T> &r, const F &f) { f(r); }
+template <class T> struct concurrent_vector : std::vector<T> {
+  using std::vector<T>::vector;
+};
+template <class T> struct enumerable_thread_specific {
+  T one[1];
+  T &local() { return one[0]; }
+  T *begin() { return one; }
+  T *end() { return one + 1; }
+};
 }  // namespace tbb
+#ifndef TC_ERROR_IF
+#define TC_ERROR_IF(cond, ...) do { if (cond) throw std::runtime_error("TC_ERROR_IF"); } while (0)
+#endif
 #define TC_LOAD_CONFIG(name, default_val) this->name = config.get(#name, default_val)

@@ -45,6 +45,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -58,7 +59,7 @@
 #define TC_ERROR(...) throw std::runtime_error("TC_ERROR")
 #define TC_WARN(...) ((void)0)
 #define TC_INFO(...) ((void)0)
-#define TC_STOP std::abort()
+#define TC_STOP do { std::fprintf(stderr, "TC_STOP at %s:%d\n", __FILE__, __LINE__); std::abort(); } while (0)
 #define TC_ALIGNED(x) alignas(x)
 #define TC_IO_DEF_VIRT(...)
 #define TC_IO_DEF_WITH_BASE(...)
@@ -66,7 +67,7 @@
 #define TC_IO(...)
 #define TC_IO_DECL template <class S> void io(S &serializer) const
 #define TC_IO_DECL_VIRT template <class S> void io(S &serializer) const
-#define TC_SERIALIZER_IS(T) false
+#define TC_SERIALIZER_IS(T) (false)
 #define TC_P(x) ((void)0)
 #define TC_TRACE(...) ((void)0)
 #define TC_DEBUG(...) ((void)0)
@@ -295,6 +296,7 @@ struct VectorND<3, int> {
   bool operator<=(const VectorND &o) const { return d[0] <= o.d[0] && d[1] <= o.d[1] && d[2] <= o.d[2]; }
   int min() const { return std::min(d[0], std::min(d[1], d[2])); }
   int max() const { return std::max(d[0], std::max(d[1], d[2])); }
+  int prod() const { return d[0] * d[1] * d[2]; }
 };
 template <int n, class T> inline std::array<T, n> to_std_array(const VectorND<n, T> &v) { std::array<T, n> a; for (int i = 0; i < n; i++) a[i] = v[i]; return a; }
 template <int n, class T> inline VectorND<n, T> fract(const VectorND<n, T> &a) { VectorND<n, T> r; for (int i = 0; i < n; i++) r[i] = a[i] - std::floor(a[i]); return r; }

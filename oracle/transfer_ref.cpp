@@ -46,6 +46,20 @@
 #include REF_PARTICLES_SOURCE
 #include REF_RIGID_TRANSFER_SOURCE       // rasterize_rigid_boundary, gather_cdf (src/rigid_transfer.cpp)
 #include REF_BOUNDARY_PARTICLE_SOURCE    // registers "rigid_boundary" (src/boundary_particle.cpp)
+// AsyncMPM (src/async/async_mpm.{h,cpp}): the scheduler calls MPM<dim>::substep() for every time level (advance(), :329;
+// step(), :377).  Those calls are the patch point of the drop-in, and the reference's sources are not
+// edited, so within this one include `substep()` expands to a harness hook that either runs the reference's own
+// MPM<3>::substep() or hands the pool to libmpmb; `class` -> `struct` only opens AsyncMPM's leading private section to the
+// harness (it sets the fields AsyncMPM::initialize would, since MPM::initialize needs the real core's Config).
+namespace taichi {
+void harness_substep(MPM<3> *m);
+inline void harness_substep(MPM<2> *) {}
+}  // namespace taichi
+#define substep() res; ::taichi::harness_substep(this)
+#define class struct
+#include REF_ASYNC_SOURCE
+#undef class
+#undef substep
 #undef private
 #include <cstddef>
 #include <cstdint>
@@ -61,6 +75,7 @@ template <> void MPM<3>::add_rigid_particle(Config) {}
 template <> void MPM<3>::rigidify(real) {}
 template <> void MPM<3>::advect_rigid_bodies(real) {}
 template <> void MPM<3>::rigid_body_levelset_collision(real, real) {}
+template <> void AsyncMPM<3>::visualize() const {}   // src/async/async_visualize.cpp (debug images of the time levels) is not part of the build
 // src/mpm.cpp instantiates parts of the 2-D solver explicitly (general_action); the same members, never called
 template <> void MPM<2>::rigidify(real) {}
 template <> void MPM<2>::advect_rigid_bodies(real) {}
@@ -73,9 +88,18 @@ using Solver = MPM<3>;
 using Mask = Solver::SparseMask;
 
 struct Harness {
-  Solver m;
-  std::vector<int> kind;  // per allocator slot
+  std::unique_ptr<Solver> owner;   // MPM<3>, or AsyncMPM<3> (its scheduler calls MPM<3>::substep through harness_substep)
+  Solver &m;
+  std::vector<int> kind;           // per allocator slot
+  // route of harness_substep: empty = the reference's own MPM<3>::substep(); else libmpmb through the C-ABI
+  std::string route_lib;
+  std::string route_error;
+  int64_t routed_substeps = 0;
+  MpmbHandle route_engine = nullptr;          // kept from one routed substep to the next: the step changes through mpmb_set_delta_t
+  int (*route_destroy)(MpmbHandle) = nullptr;
+  explicit Harness(bool async = false) : owner(async ? static_cast<Solver *>(new AsyncMPM<3>()) : new Solver()), m(*owner) {}
 };
+std::unordered_map<Solver *, Harness *> &harness_registry() { static std::unordered_map<Solver *, Harness *> r; return r; }
 
 // src/mpm.cpp:770-918 with std::sort instead of tbb::parallel_sort, no periodic pool re-pack
 void populate(Solver &m) {
@@ -160,7 +184,12 @@ void *reft_create(const int *res, float dx, float dt, const float *gravity, int 
   m.fat_page_map = std::make_unique<Solver::PageMap>(*m.grid);
   return h;
 }
-void reft_destroy(void *hp) { delete static_cast<Harness *>(hp); }
+void reft_destroy(void *hp) {
+  Harness *h = static_cast<Harness *>(hp);
+  harness_registry().erase(&h->m);
+  if (h->route_engine && h->route_destroy) h->route_destroy(h->route_engine);
+  delete h;
+}
 // threads for the stand-in's parallel loops (ThreadedTaskManager / tbb): 1 = serial (the pins); more only to time
 void reft_set_threads(void *hp, int n) {
   static_cast<Harness *>(hp)->m.num_threads = n < 1 ? 1 : n;
@@ -307,6 +336,110 @@ int64_t reft_substep(void *hp, int n) {
   for (int i = 0; i < n; i++) m.substep();
   return (int64_t)m.particles.size();
 }
+// ---- AsyncMPM (src/async/async_mpm.{h,cpp}), SURVEY §8f row 3: the reference's own scheduler object.  reft_create_async sets
+// what AsyncMPM<3>::initialize sets (src/async/async_mpm.cpp:13-58) after the solver fields of reft_create; particles are loaded
+// with reft_add_particle(s) and then handed to the block pools (the tail of AsyncMPM::add_particles, :62-76).
+void *reft_create_async(const int *res, float dx, const float *gravity, int particle_gravity, float unit_delta_t, int64_t max_units,
+                        float cfl_dt_mul, float strength_dt_mul) {
+  Harness *h = new Harness(true);
+  auto &m = *static_cast<AsyncMPM<3> *>(h->owner.get());
+  m.res = VectorND<3, int>(res[0], res[1], res[2]);
+  m.delta_x = dx;
+  m.inv_delta_x = 1.0f / dx;
+  m.base_delta_t = unit_delta_t;
+  m.gravity = VectorND<3, real>(gravity[0], gravity[1], gravity[2]);
+  m.particle_gravity = particle_gravity != 0;
+  m.apic = true;
+  m.apic_damping = m.rpic_damping = m.affine_damping = m.penalty = 0;
+  m.pushing_force = 20000.0f;
+  m.cutting_counter = m.plasticity_counter = 0;
+  m.reorder_interval = 0;                                 // AsyncMPM keeps id == pool slot (gather_from_pool asserts it)
+  m.spgrid_size = 4096;
+  while (m.spgrid_size / 2 > (m.res.max() + 1)) m.spgrid_size /= 2;
+  m.grid = std::make_unique<Solver::SparseGrid>(m.spgrid_size, m.spgrid_size, m.spgrid_size);
+  m.page_map = std::make_unique<Solver::PageMap>(*m.grid);
+  m.rigid_page_map = std::make_unique<Solver::PageMap>(*m.grid);
+  m.fat_page_map = std::make_unique<Solver::PageMap>(*m.grid);
+  m.levelset.levelset0 = std::make_shared<LevelSet<3>>();
+  // AsyncMPM<3>::initialize, src/async/async_mpm.cpp:16-58
+  {
+    auto bs = m.grid_block_size();
+    m.scheduler_size = (uint64)m.spgrid_size * m.spgrid_size * m.spgrid_size / (uint64)(bs[0] * bs[1] * bs[2]);
+  }
+  m.scheduler_mask = m.scheduler_size - 1;
+  m.unit_delta_t = unit_delta_t;
+  m.max_units = max_units;
+  m.cfl_dt_mul = cfl_dt_mul;
+  m.strength_dt_mul = strength_dt_mul;
+  m.blocks.resize(m.scheduler_size);
+  std::memset(&m.blocks[0], 0, sizeof(m.blocks[0]) * m.blocks.size());
+  for (uint64 o = 0; o < m.scheduler_size; ++o) {
+    m.blocks[o].strength_dt_limit = 1LL << 31;
+    m.blocks[o].cfl_dt_limit = 1LL << 31;
+    m.blocks[o].continuous_dt_limit = 1;
+    m.blocks[o].local_min_dt_limit = 1;
+  }
+  m.precompute_neighbor_pairs();
+  harness_registry()[&h->m] = h;
+  return h;
+}
+// the tail of AsyncMPM::add_particles (src/async/async_mpm.cpp:64-75): every loaded particle into the pool of its block
+void reft_async_distribute(void *hp) {
+  Harness *h = static_cast<Harness *>(hp);
+  auto &m = *static_cast<AsyncMPM<3> *>(h->owner.get());
+  for (auto p : m.particles) {
+    uint64 grid_offset = Mask::Linear_Offset(to_std_array(m.get_grid_base_pos(m.allocator[p]->pos * m.inv_delta_x)));
+    uint64 offset = (grid_offset >> Mask::data_bits >> Mask::block_bits) & m.scheduler_mask;
+    m.particle_pool[offset].push_back(m.allocator.pool[p]);
+  }
+  m.particles.clear();
+}
+// AsyncMPM<3>::step(dt) itself (src/async/async_mpm.cpp:375-421).  out[4] = {update_counter, current_t_int, min and max
+// continuous_dt_limit over the non-empty blocks (the spread of time levels the scheduler chose)}
+int64_t reft_async_step(void *hp, float dt, int64_t *out) {
+  Harness *h = static_cast<Harness *>(hp);
+  auto &m = *static_cast<AsyncMPM<3> *>(h->owner.get());
+  h->route_error.clear();
+  m.step(dt);
+  int64_t lo = 1LL << 40, hi = 0, n = 0;
+  for (uint64 o = 0; o < m.scheduler_size; ++o)
+    if (!m.particle_pool[o].empty()) {
+      lo = std::min<int64_t>(lo, m.blocks[o].continuous_dt_limit);
+      hi = std::max<int64_t>(hi, m.blocks[o].continuous_dt_limit);
+      n += (int64_t)m.particle_pool[o].size();
+    }
+  if (out) { out[0] = (int64_t)m.update_counter; out[1] = m.current_t_int; out[2] = lo; out[3] = hi; }
+  return h->route_error.empty() ? n : -1;
+}
+const char *reft_route_error(void *hp) { return static_cast<Harness *>(hp)->route_error.c_str(); }
+// particle state by id out of the block pools (every live particle sits in exactly one particle_pool)
+int64_t reft_async_get_particles(void *hp, float *x, float *v, float *F, float *b, float *ps, uint8_t *alive) {
+  Harness *h = static_cast<Harness *>(hp);
+  auto &m = *static_cast<AsyncMPM<3> *>(h->owner.get());
+  int64_t n = 0;
+  for (uint64 o = 0; o < m.scheduler_size; ++o)
+    for (const auto &c : m.particle_pool[o]) {
+      const MPMParticle<3> *p = reinterpret_cast<const MPMParticle<3> *>(&c);
+      const int id = p->id;
+      for (int d = 0; d < 3; d++) { x[3 * id + d] = p->pos[d]; v[3 * id + d] = p->get_velocity()[d]; }
+      store(p->dg_e, F + 9 * id);
+      store(p->apic_b, b + 9 * id);
+      switch (h->kind[id]) {
+        case 2: ps[id] = static_cast<const SnowParticle<3> *>(p)->Jp; break;
+        case 3: ps[id] = static_cast<const WaterParticle<3> *>(p)->j; break;
+        case 4: ps[id] = static_cast<const SandParticle<3> *>(p)->logJp; break;
+        case 7: ps[id] = static_cast<const ViscoParticle<3> *>(p)->visco_tau; break;
+        default: ps[id] = 0;
+      }
+      alive[id] = 1;
+      n++;
+    }
+  return n;
+}
+// from now on every MPM<3>::substep() the scheduler asks for goes to libmpmb (lib_path; empty string: back to the reference)
+void reft_route_through(void *hp, const char *lib_path) { static_cast<Harness *>(hp)->route_lib = lib_path ? lib_path : ""; }
+int64_t reft_routed_substeps(void *hp) { return static_cast<Harness *>(hp)->routed_substeps; }
+
 // ---- rigid bodies (CPIC).  Bodies 1..n_bodies-1 become MPM::rigids[1..] (row 0 is the background body MPM::initialize
 // creates, src/mpm.cpp:72-74); every sample becomes a RigidBoundaryParticle in the reference's own pool
 // (add_boundry_particle, src/mpm_rigid_body.cpp:153-169), aligned with its body.  Call after the MPM particles are loaded.
@@ -464,7 +597,7 @@ int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, 
 #define SYM(name) auto name##_ = reinterpret_cast<decltype(&name)>(dlsym(lib, #name)); if (!name##_) return fail("missing symbol " #name, -101)
   SYM(mpmb_create); SYM(mpmb_destroy); SYM(mpmb_last_error); SYM(mpmb_set_material); SYM(mpmb_set_planes); SYM(mpmb_upload_aos);
   SYM(mpmb_substep); SYM(mpmb_download_aos); SYM(mpmb_set_rigid_samples); SYM(mpmb_set_rigid_coupling); SYM(mpmb_set_rigid_state);
-  SYM(mpmb_get_rigid_state); SYM(mpmb_set_particle_states); SYM(mpmb_get_particle_cdf);
+  SYM(mpmb_get_rigid_state); SYM(mpmb_set_particle_states); SYM(mpmb_get_particle_cdf); SYM(mpmb_set_delta_t);
 #undef SYM
   // with rigid bodies: the RigidBoundaryParticles leave the index vector for the duration — the engine
   // takes them as a sample list — and come back behind the survivors
@@ -479,8 +612,17 @@ int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, 
   c.particle_gravity = m.particle_gravity;
   c.clean_boundary = m.config_backup.get("clean_boundary", true);
   c.device = 0; c.world = 1;
-  MpmbHandle e = nullptr;
-  if (mpmb_create_(&c, &e) != MPMB_OK) return fail(mpmb_last_error_(nullptr), -102);
+  // a routed solver (AsyncMPM's scheduler) keeps ONE engine and changes its step before every substep, as the reference changes
+  // base_delta_t (src/async/async_mpm.cpp:407-409); the one-shot drop-in test creates and destroys its own
+  const bool keep = !h->route_lib.empty();
+  MpmbHandle e = keep ? h->route_engine : nullptr;
+  if (!e) {
+    if (mpmb_create_(&c, &e) != MPMB_OK) return fail(mpmb_last_error_(nullptr), -102);
+  } else if (mpmb_set_delta_t_(e, m.base_delta_t) != MPMB_OK) {
+    return fail(mpmb_last_error_(e), -104);
+  }
+  if (keep) { h->route_engine = e; h->route_destroy = mpmb_destroy_; }
+  auto mpmb_release = [&](MpmbHandle x) { if (!keep) mpmb_destroy_(x); };
   // one material group: kind and parameters read back from the first particle (all are of one registered type here)
   const int kind = h->kind[m.allocator[m.particles[0]]->id];
   float prm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -507,7 +649,7 @@ int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, 
     case 6: { auto *q = static_cast<VonMisesParticle<3> *>(p0); prm[0] = q->mu_0; prm[1] = q->lambda_0; prm[2] = q->yield_stress; break; }
     case 7: { auto *q = static_cast<ViscoParticle<3> *>(p0); prm[0] = q->mu_0; prm[1] = q->lambda_0; prm[2] = q->visco_nu; prm[3] = q->visco_kappa; prm[4] = q->dt;
               L.off_scalar = (int32_t)offsetof(ViscoParticle<3>, visco_tau); break; }
-    default: mpmb_destroy_(e); return fail("unknown particle type", -103);
+    default: mpmb_release(e); return fail("unknown particle type", -103);
   }
   int rc = mpmb_set_material_(e, 0, kind, prm, 8);
   if (rc == MPMB_OK && m.levelset.levelset0 && !m.levelset.levelset0->planes.empty()) {
@@ -569,12 +711,12 @@ int64_t reft_substep_via_mpmb(void *hp, const char *lib_path, int n, char *err, 
       p->near_boundary_ = nearb[k] != 0;
     }
   }
-  if (rc != MPMB_OK) { fail(mpmb_last_error_(e), rc); mpmb_destroy_(e); m.particles.insert(m.particles.end(), rigid_ptrs.begin(), rigid_ptrs.end()); return rc; }
+  if (rc != MPMB_OK) { fail(mpmb_last_error_(e), rc); mpmb_release(e); m.particles.insert(m.particles.end(), rigid_ptrs.begin(), rigid_ptrs.end()); return rc; }
   m.particles.resize((size_t)alive);                      // == what clear_boundary_particles leaves (src/mpm.cpp:583-633)
   m.particles.insert(m.particles.end(), rigid_ptrs.begin(), rigid_ptrs.end());
   m.current_t += n * m.base_delta_t;
   m.substep_counter += n;
-  mpmb_destroy_(e);
+  mpmb_release(e);
   return alive;
 }
 
@@ -632,3 +774,17 @@ void reft_get_particles(void *hp, float *x, float *v, float *F, float *b, float 
   }
 }
 }
+
+namespace taichi {
+// the patch point of INTEGRATION.md §2, for a solver object whose substep() calls cannot be edited (AsyncMPM's scheduler):
+// the reference's own MPM<3>::substep(), or one substep on libmpmb with the step the caller has just set in base_delta_t
+void harness_substep(MPM<3> *m) {
+  auto it = harness_registry().find(m);
+  Harness *h = it == harness_registry().end() ? nullptr : it->second;
+  if (!h || h->route_lib.empty()) { m->substep(); return; }
+  char err[512] = {0};
+  const int64_t rc = reft_substep_via_mpmb(h, h->route_lib.c_str(), 1, err, (int)sizeof(err));
+  if (rc < 0) h->route_error = err;
+  h->routed_substeps++;
+}
+}  // namespace taichi

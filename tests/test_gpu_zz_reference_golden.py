@@ -125,3 +125,15 @@ def test_reference_solver_object_with_rigid_bodies_steps_through_libmpmb():
     from tests.test_dropin import run_dropin_rigid
     capi.lib()
     run_dropin_rigid(capi.lib_path(), "two_bodies")
+
+
+def test_reference_asyncmpm_scheduler_steps_through_libmpmb():
+    """SURVEY §8f row 3 on the device: the reference's own AsyncMPM<3> scheduler (time levels, backup pools) with every
+    MPM<3>::substep() it schedules run by libmpmb.so at the level's step — against the same scheduler on the reference's substep."""
+    from oracle import pyoracle as O
+    if not O.ref_transfer_available():
+        pytest.skip("reference build (oracle/_ref) not available")
+    from taichi_mpm_b200 import capi
+    from tests.test_dropin import run_async
+    capi.lib()
+    run_async(capi.lib_path())
