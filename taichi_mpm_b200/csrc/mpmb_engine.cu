@@ -2215,6 +2215,9 @@ struct MpmbEngine {
   float *rs_offset = nullptr, *rs_tri = nullptr;
   int *rs_rigid = nullptr;
   size_t rigid_nodes = 0;
+  int64_t id_span_pending = 0;
+  int64_t id_span = 0;   // ids of the resident particles lie in [id_base, id_base + id_span): uploads number 0..n-1, the seeded
+                         // lattice numbers by lattice index (gaps where the boundary band is skipped)
 
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int stage; };
@@ -2653,8 +2656,10 @@ static int finish_upload(MpmbEngine *h, int64_t n) {
   // Fresh storage in upload order: no runs yet, every particle is an "arrival" of its tile.  The
   // one radix sort of the engine's life (per upload) groups the rows by tile; the ordinary
   // ordering scan then lays out the first runs.
+  h->id_span = std::max<int64_t>(h->id_span_pending, n);
+  h->id_span_pending = 0;
   if (h->rigid_on) {  // new particles start with MPMParticle::states = 0 (mpmb_set_particle_states overrides)
-    int rc = rigid_reserve_ids(h, std::max<int64_t>(n, h->cap));
+    int rc = rigid_reserve_ids(h, std::max<int64_t>(h->id_span, h->cap));
     if (rc != MPMB_OK) return rc;
     CUDA_TRY(h, cudaMemsetAsync(h->R.p_states, 0, sizeof(uint32_t) * h->R.id_cap, h->stream));
   }
@@ -2869,6 +2874,7 @@ int mpmb_seed_lattice(MpmbHandle h, const int32_t lo_cell[3], const int32_t hi_c
     CUDA_TRY(h, cudaGetLastError());
   }
   if (n_seeded) *n_seeded = total;
+  h->id_span_pending = (int64_t)n_cand;   // ids = lattice index
   return finish_upload(h, total);
 }
 
@@ -3076,7 +3082,7 @@ static int rigid_reserve_ids(MpmbEngine *h, int64_t n_ids) {
 static int rigid_prepare(MpmbEngine *h, const View &V, int *nl) {
   RigidView &R = h->R;
   R.id_base = h->id_base;
-  if (!R.p_states) { int rc = rigid_reserve_ids(h, h->cap); if (rc != MPMB_OK) return rc; }
+  if (!R.p_states || R.id_cap < h->id_span) { int rc = rigid_reserve_ids(h, std::max<int64_t>(h->id_span, h->cap)); if (rc != MPMB_OK) return rc; }
   R.epoch = (R.epoch + 1u) & 0x7fffffffu;
   if (R.epoch == 0u) R.epoch = 1u;
   const int ns = R.n_samples, sb = (ns + 127) / 128;
@@ -3131,7 +3137,8 @@ int mpmb_set_rigid_samples(MpmbHandle h, int32_t n_bodies, int64_t n_samples, co
   if (R.pushing_force == 0.f && R.penalty == 0.f) R.pushing_force = 20000.0f;   // src/mpm.cpp:35,40 defaults
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->rigid_on = true;
-  h->use_graph = false;   // poses change between substeps: the host drives every substep
+  // poses change between substeps: the host drives every substep, so mpmb_substep does not replay graphs while bodies are present
+  // (use_graph itself keeps what the configuration asked for: switching the coupling off brings graph replay back)
   graph_reset(h);
   return MPMB_OK;
 }
@@ -3434,7 +3441,7 @@ int mpmb_substep(MpmbHandle h, int32_t nsub) {
     s = 1;
   }
   // pairs of intermediate substeps through the captured graph; the last substep (it stores apic_b) always runs directly
-  while (h->use_graph && !h->profiling && h->cap > 0 && h->stage == 0 && nsub - s >= 3) {
+  while (h->use_graph && !h->rigid_on && !h->profiling && h->cap > 0 && h->stage == 0 && nsub - s >= 3) {
     const int par = h->cur;
     if (!h->graph_exec[par]) {
       if ((rc = graph_capture_pair(h, peers)) != MPMB_OK) return rc;

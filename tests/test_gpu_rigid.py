@@ -298,3 +298,32 @@ def test_two_bodies_claiming_one_node_the_nearer_one_wins_and_both_leave_their_t
     assert np.array_equal(d["node_state"], cdf["node_state"])
     assert np.array_equal(e.get_particle_cdf(len(st["x"]))["states"], ref["states"])
     e.close()
+
+
+def test_device_seeded_lattice_with_id_gaps_and_a_rigid_body():
+    # mpmb_seed_lattice numbers particles by lattice index and skips the 7-cell boundary band: ids have gaps and exceed the particle
+    # count; the by-id colour arrays must cover them
+    from oracle import pyoracle as O
+    from taichi_mpm_b200 import capi
+    res, dx = 32, 1.0 / 32
+    scene, _, _ = _scene()
+    e = capi.Engine(scene["res"], scene["dx"], scene["dt"], scene["gravity"], 1, True)
+    e.set_material(0, int(scene["mat_kind"][0]), scene["mat_params"][0])
+    vol = dx ** 3 / 8
+    n = e.seed_lattice((4, 12, 12), (14, 18, 18), vol, vol * 400.0, jitter=0.1, seed=5)     # cells 4..6 along x lie in the deletion band
+    p = e.download()
+    ids = p["id"].astype(np.int64)
+    assert n == len(ids) and ids.max() + 1 > n                       # gaps
+    plate = dict(tris=scenes.plate_mesh(0.12, 0.12, axis=1), position=p["x"].mean(0) + np.array([0.0, 0.004, 0.0]),
+                 rotation=scenes.euler_rotation((5.0, 9.0, -4.0)), velocity=(0.0, -0.5, 0.0), friction=0.2)
+    rigid = scenes.make_rigid([plate], dx, penalty=1e3)
+    st = dict(x=p["x"], v=p["v"], F=p["F"], b=p["b"], mass=p["mass"], vol=p["vol"], ps=p["ps"], group=p["group"])
+    ref, _, _, _, _ = O.substep_coupled(scene, st, rigid, np.float64)
+    e.set_rigid(rigid)
+    e.substep(1)
+    pc = e.get_particle_cdf(int(ids.max()) + 1)
+    assert np.array_equal(pc["states"][ids], ref["states"]) and (ref["states"] != 0).sum() > 100
+    got = e.download()
+    assert np.array_equal(got["id"].astype(np.int64), ids[ref["alive"].astype(bool)])
+    assert np.abs(got["x"] - ref["x"][ref["alive"].astype(bool)]).max() <= T.TOL_X_ABS
+    e.close()
