@@ -1,0 +1,99 @@
+"""the AsyncMPM scheduler of the mirror (taichi_mpm_b200/async_mpm.py) against the REFERENCE's own AsyncMPM<3>
+object (src/async/async_mpm.{h,cpp} compiled in place, oracle/transfer_ref.cpp) — scheduler decisions identical (pool sizes,
+update counter, integer clock, time levels, survivors), particle states to fp32 rounding.  The substeps of the mirror run on a
+stand-in engine here that executes the oracle's fp32 substep on the CPU (no GPU in this suite); tests/test_gpu_async.py runs the
+same comparison on the device engine."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from taichi_mpm_b200 import async_mpm, capi, scenes
+from tests import common as T
+
+pytestmark = pytest.mark.skipif(not O.ref_transfer_available(), reason="reference build (oracle/_ref) not available")
+
+
+class OracleEngine:
+    """The Engine calls AsyncMPM makes, executed by the oracle (test infrastructure: the product has no CPU path)."""
+
+    def __init__(self, res, dx, dt, gravity=(0.0, -10.0, 0.0), particle_gravity=True, clean_boundary=True, **kw):
+        self.scene = dict(res=tuple(res), dx=dx, dt=dt, gravity=gravity, particle_gravity=int(particle_gravity), mat_kind=[], mat_params=[], sdf=None, friction=0.0)
+        self.p = None
+
+    def set_material(self, group, kind, params):
+        while len(self.scene["mat_kind"]) <= group:
+            self.scene["mat_kind"].append(0); self.scene["mat_params"].append(np.zeros(8, np.float32))
+        self.scene["mat_kind"][group] = int(kind)
+        q = np.zeros(8, np.float32); q[: len(params)] = params
+        self.scene["mat_params"][group] = q
+
+    def set_delta_t(self, dt):
+        self.scene["dt"] = float(dt)
+
+    def upload(self, x, v, mass, vol, F=None, b=None, scalar=None, group=None):
+        n = len(x)
+        self.p = dict(x=x, v=v, mass=mass, vol=vol, F=F, b=b, ps=scalar, group=np.zeros(n, np.int32) if group is None else group, alive=np.ones(n, np.uint8))
+
+    def substep(self, n=1):
+        sc = dict(self.scene, mat_kind=np.asarray(self.scene["mat_kind"], np.int32), mat_params=np.stack(self.scene["mat_params"]))
+        for _ in range(n):
+            self.p, _, _ = O.substep(sc, self.p, np.float32, want_grids=False)
+
+    def download(self):
+        a = self.p["alive"].astype(bool)
+        out = {k: np.asarray(self.p[k])[a] for k in ("x", "v", "F", "b", "mass", "vol", "ps", "group")}
+        out["id"] = np.nonzero(a)[0].astype(np.uint32)
+        return out
+
+    def close(self):
+        pass
+
+
+def async_pair(kind, monkeypatch=None, engine_cls=None):
+    scene, st = T.perturbed_scene(kind, res=32, cells=8, seed=7, strain=0.0, vel=0.0, with_floor=False)
+    st["v"][:] = 0
+    st["v"][st["x"][:, 0] > 0.55, 0] = 10.0                    # a fast half: its blocks take a finer time level (cfl_dt_mul = 0.1)
+    unit = 2.5e-5 if kind == scenes.MAT_SNOW else 5e-6
+    kw = dict(unit_delta_t=unit, max_units=64, cfl_dt_mul=0.1)
+    ref = O.RefAsyncSolver(scene, st, **kw)
+    if engine_cls is not None:
+        monkeypatch.setattr(capi, "Engine", engine_cls)
+    m = async_mpm.AsyncMPM(res=(32, 32, 32), base_delta_t=unit, gravity=scene["gravity"], **kw)
+    m.add_particles(type={scenes.MAT_SNOW: "snow", scenes.MAT_SAND: "sand"}[kind], positions=st["x"], density=400.0)
+    for k in ("v", "mass", "vol", "F", "b", "ps"):
+        m.pool[k][:] = st[k]                                   # the state the reference run starts from
+    return scene, st, unit, ref, m
+
+
+def compare_async(ref, m, unit, steps, tol):
+    for _ in range(steps):
+        r = ref.step(80 * unit)
+        m.step(80 * unit)
+        s = m.scheduler_stats()
+        assert (r["alive"], r["update_counter"], r["current_t_int"], r["min_level"], r["max_level"]) == \
+               (s["pool_entries"], s["update_counter"], s["current_t_int"], s["min_level"], s["max_level"])
+    assert s["min_level"] < s["max_level"]                    # really asynchronous
+    pa, pm = ref.particles(), m.get_particles()
+    assert np.array_equal(np.nonzero(pa["alive"])[0], pm["id"])
+    ids = pm["id"]
+    assert np.abs(pa["x"][ids] - pm["x"]).max() <= tol["x"]
+    assert np.abs(pa["v"][ids] - pm["v"]).max() <= tol["v"] * np.abs(pa["v"]).max()
+    assert np.abs(pa["F"][ids] - pm["F"]).max() <= tol["F"]
+    assert m.update_counter == r["update_counter"] and m.num_particles() == len(ids)
+
+
+@pytest.mark.parametrize("kind", [scenes.MAT_SNOW, scenes.MAT_SAND])
+def test_mirror_scheduler_makes_the_reference_s_decisions(kind, monkeypatch):
+    scene, st, unit, ref, m = async_pair(kind, monkeypatch, OracleEngine)
+    compare_async(ref, m, unit, steps=2, tol=dict(x=2e-6, v=2e-5, F=5e-5))
+    ref.close()
+
+
+def test_block_order_is_spgrid_s_and_types_without_a_limit_are_refused(monkeypatch):
+    # the scheduler's block order (which copy of a particle wins a gather) is SPGrid's page order: y, x, z bits interleaved
+    assert [int(async_mpm._morton(*c)) for c in ((0, 0, 0), (0, 1, 0), (1, 0, 0), (0, 0, 1), (1, 1, 1), (2, 0, 0), (0, 2, 0))] == [0, 1, 2, 4, 7, 16, 8]
+    monkeypatch.setattr(capi, "Engine", OracleEngine)
+    m = async_mpm.AsyncMPM(res=(32, 32, 32), base_delta_t=1e-5, unit_delta_t=1e-5)
+    m.add_particles(type="jelly", benchmark_block=((12, 12, 12), (14, 14, 14)))
+    with pytest.raises(ValueError):
+        m.step(1e-4)                                          # JellyParticle::get_allowed_dt returns 0: the reference stops (TC_STOP, :124)

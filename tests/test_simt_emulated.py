@@ -28,7 +28,7 @@ def _run(extra_env, args):
 def test_gpu_parity_suite_passes_on_the_simt_emulator():
     # everything that does not need a real device, minus the two longest multi-step runs (they pass too: ~1 min more)
     tail = _run({}, ["tests/test_gpu_parity.py", "tests/test_gpu_zz_reference_golden.py", "tests/test_gpu_mpm_mirror.py",
-                     "tests/test_gpu_zz_frame_io.py", "tests/test_gpu_rigid.py", "-k", "not many_movers and not multi_step_invariants"])
+                     "tests/test_gpu_zz_frame_io.py", "tests/test_gpu_rigid.py", "tests/test_gpu_async.py", "-k", "not many_movers and not multi_step_invariants"])
     assert " passed" in tail and "failed" not in tail
 
 
