@@ -85,6 +85,32 @@ class LevelSet:
         # phi_grid(X) = phi(x)/dx with X = x/dx  ->  n.X + d/dx
         return np.array([[p[0], p[1], p[2], p[3] / self.delta_x] for p in self.planes], np.float32)
 
+    def node_phi(self):
+        """phi at the nodes, grid units (what the engine's level set holds)."""
+        if self.dense is not None:
+            return np.asarray(self.dense[..., 3], np.float32)
+        sh = self.shapes_grid_units()
+        if not sh:
+            return np.full(tuple(r + 1 for r in self.res), 1e30, np.float32)
+        return scenes.shapes_sdf(self.res, sh)[..., 3]
+
+    def sample(self, X):
+        """phi at positions X (grid units), trilinear in the node values — LevelSet::sample as
+        delete_particles_inside_level_set uses it (src/mpm.cpp:960-961; the interpolation itself is core code: assumed)."""
+        phi = self.node_phi()
+        X = np.asarray(X, np.float64)
+        hi = np.asarray(phi.shape) - 1
+        Xc = np.clip(X, 0, hi - 1e-9)
+        i0 = np.floor(Xc).astype(np.int64)
+        f = Xc - i0
+        out = np.zeros(len(X))
+        for a in (0, 1):
+            for b in (0, 1):
+                for c in (0, 1):
+                    w = (f[:, 0] if a else 1 - f[:, 0]) * (f[:, 1] if b else 1 - f[:, 1]) * (f[:, 2] if c else 1 - f[:, 2])
+                    out += w * np.minimum(phi[i0[:, 0] + a, i0[:, 1] + b, i0[:, 2] + c], np.float32(1e20))
+        return out
+
 
 class MPM:
     """Mirror of `tc.dynamics.MPM(**kwargs)` for 3D scenes on the accelerated path."""
@@ -138,6 +164,7 @@ class MPM:
     def set_levelset(self, levelset, is_dynamic_levelset=False):
         if is_dynamic_levelset:
             raise ValueError("dynamic level sets are outside the accelerated fast path")
+        self._levelset = levelset
         if levelset.dense is not None:
             self.engine.set_sdf(levelset.dense, levelset.friction)
         elif levelset.shapes:
@@ -401,7 +428,50 @@ class MPM:
             self._dirty = True
             self._push_with_ids(ids)
             return ""
+        if action == "delete_particles_inside_level_set":                      # mpm.cpp:958-972
+            ls = getattr(self, "_levelset", None)
+            p = self.get_particles()
+            if ls is None or len(p["x"]) == 0:
+                return ""
+            keep = ~(ls.sample(p["x"].astype(np.float64) / self.delta_x) < 0)
+            if keep.all():
+                return ""
+            self._host = {k: np.ascontiguousarray(p[k][keep]) for k in ("x", "v", "F", "b", "mass", "vol", "ps", "group")}
+            self._dirty = True
+            self._push_with_ids(p["id"][keep].astype(np.int64))
+            return ""
         raise ValueError("Unknown action: %s" % action)  # TC_ERROR("Unknown action") mpm.cpp:974
+
+    # ---- the verbs of the reference's Python driver around general_action and the frame loop (scripts/async/async_mpm.py:217-299)
+    def action(self, **kwargs):
+        return self.general_action(**kwargs)
+
+    def save(self, fn):
+        return self.general_action(action="save", file_name=fn)
+
+    def load(self, fn):
+        return self.general_action(action="load", file_name=fn)
+
+    def delete_particles_inside_level_set(self):
+        return self.general_action(action="delete_particles_inside_level_set")
+
+    def simulate(self, num_frames=None, frame_update=None, update_frequency=1, snapshot_interval=0, snapshot_directory=None):
+        """The driver's main cycle (scripts/async/async_mpm.py:236-248): per frame `update_frequency` calls of
+        frame_update(t, dt) + step(dt), then visualize(); a snapshot every `snapshot_interval` frames."""
+        n = int(num_frames if num_frames is not None else getattr(self, "num_frames", 1000))
+        frame = 0
+        while frame < n:
+            for _ in range(update_frequency):
+                if frame_update:
+                    frame_update(float(self.get_current_time()), self.frame_dt / update_frequency)
+                self.step(self.frame_dt / update_frequency)
+            if self.frame_directory:
+                self.visualize()
+            frame += 1
+            if snapshot_interval and snapshot_directory and frame % snapshot_interval == 0:
+                os.makedirs(snapshot_directory, exist_ok=True)
+                self.save(os.path.join(snapshot_directory, "%04d.npz" % frame))
+        return frame
 
     def _push_with_ids(self, ids):
         """Upload after 'load': the engine numbers particles id_base + position, so a snapshot whose

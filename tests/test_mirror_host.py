@@ -264,3 +264,30 @@ def test_unsupported_solver_options_are_rejected_not_ignored(fake_engine):
     assert m.base_delta_t == float(np.float32(1e-4)) and m.gravity == (0.0, -10.0, 0.0)                # defaults of src/mpm.cpp:38,42
     assert m.get_debug_information() == "" and m.test() is True and m.get_name() == "mpm"   # the remaining verbs of the plugin surface
     assert mpm_mod.MPM(res=(32, 32, 32), gravity=-5, base_delta_t=1e-3, dt_multiplier=0.5).gravity == (0.0, -5.0, 0.0)
+
+
+def test_driver_verbs_simulate_save_load_and_delete_inside_level_set(tmp_path, fake_engine):
+    # scripts/async/async_mpm.py:217-299: the frame loop, save / load wrappers, delete_particles_inside_level_set (src/mpm.cpp:958-972)
+    m = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=1e-4, frame_dt=1e-3, frame_directory=str(tmp_path / "frames"))
+    ls = m.create_levelset()
+    ls.add_plane((0, 1, 0), -0.36)                      # obstacle below y = 0.36
+    ls.set_friction(0.4)
+    m.set_levelset(ls, False)
+    m.add_particles(type="sand", benchmark_block=((10, 10, 10), (13, 14, 13)), initial_velocity=(0.0, 0.1, 0.0))
+    n0 = m.num_particles()
+    y = m.get_particles()["x"][:, 1]
+    assert (y < 0.36).any() and (y > 0.36).any()
+    m.delete_particles_inside_level_set()
+    p = m.get_particles()
+    assert 0 < len(p["x"]) < n0 and (p["x"][:, 1] >= 0.36 - 1e-6).all()
+    assert np.abs(ls.sample(np.array([[16.0, 12.8, 16.0]])) - (12.8 - 0.36 * 32)) < 1e-4      # phi in grid units, trilinear = exact for a plane
+    calls = []
+    frames = m.simulate(num_frames=3, frame_update=lambda t, dt: calls.append((round(t, 6), dt)), update_frequency=2,
+                        snapshot_interval=2, snapshot_directory=str(tmp_path / "snap"))
+    assert frames == 3 and len(calls) == 6 and calls[0][0] == 0.0 and abs(calls[1][1] - 5e-4) < 1e-12
+    assert sorted(f for f in (tmp_path / "frames").iterdir())[-1].name == "0003.bgeo" and (tmp_path / "snap" / "0002.npz").exists()
+    m2 = mpm_mod.MPM(res=(32, 32, 32), base_delta_t=1e-4)
+    m2.load(str(tmp_path / "snap" / "0002.npz"))
+    assert m2.num_particles() == len(p["x"]) and m2.frame_count == 2
+    with pytest.raises(ValueError):
+        m.action(action="no_such_action")
