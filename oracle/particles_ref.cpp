@@ -108,6 +108,35 @@ int ref_particle(int kind, const float *params, const float *cdg, float *F, floa
   return -1;
 }
 
+// MPMParticle::get_allowed_dt(dx) of the registered type (the strength limit AsyncMPM's scheduler reads,
+// src/async/async_mpm.cpp:105-110).  Returns the reference's value; -1 for an unknown kind.
+float ref_allowed_dt(int kind, const float *params, const float *F, float ps, float mass, float vol, const float *v, float dx) {
+  Config cfg;
+  auto fill = [&](auto &p) {
+    p.dg_e = load(F);
+    p.vol = vol;
+    p.set_mass(mass);
+    p.set_velocity(VectorND<3, real>(v[0], v[1], v[2]));
+    return p.get_allowed_dt(dx);
+  };
+  switch (kind) {
+    case 0: { LinearParticle<3> p; p.initialize(cfg); return fill(p); }
+    case 1: { JellyParticle<3> p; p.initialize(cfg); return fill(p); }
+    case 2: {
+      SnowParticle<3> p;
+      cfg.set("mu_0", params[0]).set("lambda_0", params[1]).set("hardening", params[2]).set("Jp", ps);
+      p.initialize(cfg);
+      return fill(p);
+    }
+    case 3: { WaterParticle<3> p; cfg.set("k", params[0]).set("gamma", params[1]); p.initialize(cfg); p.j = ps; return fill(p); }
+    case 4: { SandParticle<3> p; cfg.set("mu_0", params[0]).set("lambda_0", params[1]); p.initialize(cfg); return fill(p); }
+    case 5: { ElasticParticle<3> p; p.initialize(cfg); p.mu_0 = params[0]; p.lambda_0 = params[1]; return fill(p); }
+    case 6: { VonMisesParticle<3> p; p.initialize(cfg); p.mu_0 = params[0]; p.lambda_0 = params[1]; return fill(p); }
+    case 7: { ViscoParticle<3> p; p.initialize(cfg); p.mu_0 = params[0]; p.lambda_0 = params[1]; return fill(p); }
+  }
+  return -1.0f;
+}
+
 // alpha as SandParticle::initialize computes it from the friction angle in degrees (src/particles.cpp:591-593)
 float ref_sand_alpha(float friction_angle) {
   Config cfg;

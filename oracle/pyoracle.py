@@ -358,6 +358,17 @@ def ref_particle_step(kind, params, cdg, F, ps, vol, do_plasticity=True):
     return f.reshape(3, 3).T.copy(), float(s[0]), force.reshape(3, 3).T.copy()
 
 
+def ref_allowed_dt(kind, params, F, ps, mass, vol, v, dx):
+    """MPMParticle::get_allowed_dt of the reference's own particle classes (oracle/particles_ref.cpp)."""
+    L = ref_particles()
+    L.ref_allowed_dt.restype = C.c_float
+    prm = np.zeros(N_MAT_PARAMS, np.float32)
+    prm[: len(params)] = params
+    f = np.ascontiguousarray(F, np.float32).reshape(9)
+    vv = np.ascontiguousarray(v, np.float32)
+    return float(L.ref_allowed_dt(C.c_int(kind), _p(prm), _p(f), C.c_float(ps), C.c_float(mass), C.c_float(vol), _p(vv), C.c_float(dx)))
+
+
 def ref_default_params(kind):
     out = np.zeros(N_MAT_PARAMS, np.float32)
     assert ref_particles().ref_default_params(C.c_int(kind), _p(out)) == 0

@@ -97,3 +97,32 @@ def test_block_order_is_spgrid_s_and_types_without_a_limit_are_refused(monkeypat
     m.add_particles(type="jelly", benchmark_block=((12, 12, 12), (14, 14, 14)))
     with pytest.raises(ValueError):
         m.step(1e-4)                                          # JellyParticle::get_allowed_dt returns 0: the reference stops (TC_STOP, :124)
+
+
+@pytest.mark.parametrize("kind", [scenes.MAT_SNOW, scenes.MAT_WATER, scenes.MAT_SAND, scenes.MAT_ELASTIC, scenes.MAT_VON_MISES, scenes.MAT_VISCO])
+def test_strength_limit_is_the_reference_particle_s_get_allowed_dt(kind):
+    # the per-particle limit the scheduler reads (src/async/async_mpm.cpp:105-110) against the reference's own classes run in place
+    if not O.ref_particles_available():
+        pytest.skip("reference build (oracle/_ref) not available")
+    rng = np.random.default_rng(kind)
+    prm = scenes.material_params(kind)
+    n, dx = 40, 1.0 / 64
+    F = (np.eye(3)[None] + rng.normal(size=(n, 3, 3)) * 0.05).astype(np.float32)
+    ps = {scenes.MAT_SNOW: 1 + rng.normal(size=n) * 0.05, scenes.MAT_WATER: 1 + rng.normal(size=n) * 0.03}.get(kind, np.zeros(n)).astype(np.float32)
+    v = rng.normal(size=(n, 3)).astype(np.float32) * 2
+    vol = np.full(n, dx ** 3 / 8, np.float32)
+    mass = vol * np.float32(400.0)
+    Fcm = np.ascontiguousarray(np.transpose(F, (0, 2, 1)).reshape(n, 9))       # column-major, as the engine and the oracle carry it
+    got = async_mpm.allowed_dt(kind, prm, F.reshape(n, 9), ps, mass, vol, v, dx)   # the determinant does not care about the layout
+    ref = np.array([O.ref_allowed_dt(kind, prm, Fcm[i], float(ps[i]), float(mass[i]), float(vol[i]), v[i], dx) for i in range(n)])
+    assert np.abs(got - ref).max() <= 2e-6 * ref.max()
+
+
+def test_types_without_a_strength_limit_return_zero_in_the_reference_too():
+    if not O.ref_particles_available():
+        pytest.skip("reference build (oracle/_ref) not available")
+    for kind in (scenes.MAT_LINEAR, scenes.MAT_JELLY):
+        assert O.ref_allowed_dt(kind, scenes.material_params(kind), np.eye(3).reshape(9), 0.0, 1e-3, 1e-6, np.zeros(3), 1 / 64) == 0.0
+        with pytest.raises(ValueError):
+            async_mpm.allowed_dt(kind, scenes.material_params(kind), np.eye(3, dtype=np.float32).reshape(1, 9), np.zeros(1, np.float32),
+                                 np.ones(1, np.float32), np.ones(1, np.float32), np.zeros((1, 3), np.float32), 1 / 64)
