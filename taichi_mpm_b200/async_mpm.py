@@ -323,6 +323,26 @@ class AsyncMPM(MPM):
     def num_particles(self):
         return 0 if self.pool is None else len(np.unique(self.pool["id"]))
 
+    def visualize(self):
+        """The frame dump of MPM.visualize from the pools (the engine only ever holds the particle set of the last advance)."""
+        import os
+        from . import bgeo
+        from .mpm import frame_attributes
+        if not self.frame_directory:
+            raise ValueError("frame_directory was not given to AsyncMPM(...)")
+        self.frame_count += 1
+        os.makedirs(self.frame_directory, exist_ok=True)
+        fn = os.path.join(self.frame_directory, "%04d.bgeo" % self.frame_count)
+        p = self.get_particles()
+        p = dict(p, id=p["id"].astype(np.uint32))
+        bgeo.write_bgeo(fn, p["x"], frame_attributes(p, [k for k, _ in self._groups], self.verbose_bgeo))
+        return fn
+
+    def general_action(self, **kwargs):
+        if kwargs.get("action") in ("save", "load", "delete_particles_inside_level_set"):
+            raise ValueError("AsyncMPM: %s is not supported (the reference's AsyncMPM::io is a stub too, src/async/async_mpm.h:126-129)" % kwargs["action"])
+        return super().general_action(**kwargs)
+
     def scheduler_stats(self):
         p = self.pool
         ne = np.zeros(self.nb, bool)

@@ -126,3 +126,20 @@ def test_types_without_a_strength_limit_return_zero_in_the_reference_too():
         with pytest.raises(ValueError):
             async_mpm.allowed_dt(kind, scenes.material_params(kind), np.eye(3, dtype=np.float32).reshape(1, 9), np.zeros(1, np.float32),
                                  np.ones(1, np.float32), np.ones(1, np.float32), np.zeros((1, 3), np.float32), 1 / 64)
+
+
+def test_async_mirror_frame_dump_comes_from_the_pools(monkeypatch, tmp_path):
+    from taichi_mpm_b200 import bgeo
+    monkeypatch.setattr(capi, "Engine", OracleEngine)
+    m = async_mpm.AsyncMPM(res=(32, 32, 32), base_delta_t=2.5e-5, unit_delta_t=2.5e-5, max_units=64, cfl_dt_mul=0.1, frame_directory=str(tmp_path))
+    m.add_particles(type="snow", benchmark_block=((12, 12, 12), (16, 16, 16)), initial_velocity=(4.0, 0.0, 0.0))
+    m.add_particles(type="snow", benchmark_block=((17, 12, 12), (20, 16, 16)))
+    n = m.num_particles()
+    m.step(40 * 2.5e-5)
+    fn = m.visualize()
+    pos, attrs = bgeo.read_bgeo(fn)
+    p = m.get_particles()
+    assert fn.endswith("0001.bgeo") and len(pos) == n == len(p["x"]) and np.array_equal(pos, p["x"])
+    assert np.array_equal(dict((a[0], a[2]) for a in attrs)["index"].ravel(), np.arange(n))
+    with pytest.raises(ValueError):
+        m.general_action(action="save", file_name=str(tmp_path / "s.npz"))
