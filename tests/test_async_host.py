@@ -143,3 +143,12 @@ def test_async_mirror_frame_dump_comes_from_the_pools(monkeypatch, tmp_path):
     assert np.array_equal(dict((a[0], a[2]) for a in attrs)["index"].ravel(), np.arange(n))
     with pytest.raises(ValueError):
         m.general_action(action="save", file_name=str(tmp_path / "s.npz"))
+
+
+def test_mirror_scheduler_follows_the_reference_through_deletions_and_level_changes(monkeypatch):
+    # eight steps: the fast half of the block runs into the deletion band (4096 -> 3874 pool entries), levels regroup every step;
+    # the two schedulers stay in lockstep (≈ 400 000 particle updates)
+    scene, st, unit, ref, m = async_pair(scenes.MAT_SNOW, monkeypatch, OracleEngine)
+    compare_async(ref, m, unit, steps=8, tol=dict(x=5e-6, v=1e-4, F=2e-4))
+    assert m.scheduler_stats()["pool_entries"] < 3900
+    ref.close()
