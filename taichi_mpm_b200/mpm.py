@@ -140,6 +140,7 @@ class MPM:
                 raise ValueError("%s != 0 is outside the accelerated fast path" % key)
         self.penalty = float(kwargs.get("penalty", 0.0))                        # mpm.cpp:35: rigid-coupled scenes only
         self.pushing_force = float(kwargs.get("pushing_force", 20000.0))        # mpm.cpp:40
+        self.rigid_body_levelset_collision = bool(kwargs.get("rigid_body_levelset_collision", False))   # mpm.cpp:535-538
         self.rigids = []          # HostRigidBody per add_particles(type='rigid'); engine body id = index + 1 (rigids[0] of the
         self._rigid_dirty = False  # reference is the background body, mpm.cpp:72-74)
         self.engine = capi.Engine(self.res, self.delta_x, self.base_delta_t, self.gravity, self.particle_gravity,
@@ -249,7 +250,8 @@ class MPM:
             velocity=kwargs.get("initial_velocity", (0, 0, 0)), angular_velocity=kwargs.get("initial_angular_velocity", (0, 0, 0)), frictions=fr,
             scripted_position=kwargs.get("scripted_position"), scripted_rotation=kwargs.get("scripted_rotation"),
             recenter=bool(kwargs.get("recenter", True)), rotation_axis=kwargs.get("rotation_axis", (0, 0, 0)),
-            linear_damping=float(kwargs.get("linear_damping", 0.0)), angular_damping=float(kwargs.get("angular_damping", 0.0)), t0=float(self.current_t))
+            linear_damping=float(kwargs.get("linear_damping", 0.0)), angular_damping=float(kwargs.get("angular_damping", 0.0)), t0=float(self.current_t),
+            restitution=float(kwargs.get("restitution", 0.0)))
         self.rigids.append(body)
         self._rigid_dirty = True
         return str(len(self.rigids))
@@ -274,9 +276,28 @@ class MPM:
             for k, b in enumerate(self.rigids):
                 b.velocity = rs["velocity"][k + 1].astype(np.float64)
                 b.angular_velocity = rs["angular_velocity"][k + 1].astype(np.float64)
+            if self.rigid_body_levelset_collision and getattr(self, "_levelset", None) is not None:
+                # in the reference this sits between the grid normalisation and the boundary condition of the same substep
+                # (src/mpm.cpp:535-538); here the transfers of a substep are one engine call, so it follows them
+                self._rigid_levelset_collision(rec)
+            for b in self.rigids:
                 b.advect(float(t), float(h), self.gravity)
             t = np.float32(t + h)
         return t
+
+    def _rigid_levelset_collision(self, rec):
+        ls = self._levelset
+        for k, b in enumerate(self.rigids):
+            sel = rec["sample_rigid"] == k + 1
+            if not sel.any():
+                continue
+            world = b.position + rec["sample_offset"][sel].astype(np.float64) @ b.rotation.T
+            X = world / self.delta_x
+            phi = ls.sample(X)
+            eps = 0.25
+            grad = np.stack([(ls.sample(X + e) - ls.sample(X - e)) / (2 * eps) for e in np.eye(3) * eps], 1)   # get_spatial_gradient
+            nrm = np.linalg.norm(grad, axis=1, keepdims=True)
+            b.levelset_collision(world, phi, grad / np.maximum(nrm, 1e-12))
 
     def _pull_host(self):
         """Host copy of the resident particles (download -> mutate -> upload contract)."""

@@ -75,7 +75,7 @@ class HostRigidBody:
 
     def __init__(self, tris, density=400.0, codimensional=False, position=(0, 0, 0), euler_deg=(0, 0, 0), velocity=(0, 0, 0),
                  angular_velocity=(0, 0, 0), frictions=(0.0, 0.0), scripted_position=None, scripted_rotation=None, recenter=True,
-                 rotation_axis=(0, 0, 0), linear_damping=0.0, angular_damping=0.0, t0=0.0):
+                 rotation_axis=(0, 0, 0), linear_damping=0.0, angular_damping=0.0, t0=0.0, restitution=0.0):
         tris = np.asarray(tris, np.float64).reshape(-1, 3, 3)
         self.mass, com, self.inertia_body = mass_properties(tris, density, codimensional)     # src/mpm_rigid_body.cpp:190
         if not recenter:                                                                       # :191-195 (needs both scripts)
@@ -93,6 +93,7 @@ class HostRigidBody:
         self.inv_inertia_body = np.zeros((3, 3)) if scripted_rotation else np.linalg.inv(self.inertia_body)   # :201-203
         self.rotation_axis = np.asarray(rotation_axis, np.float64)
         self.linear_damping, self.angular_damping = float(linear_damping), float(angular_damping)
+        self.restitution = float(restitution)                                                  # src/mpm_rigid_body.cpp:74
 
     def inv_inertia_world(self):
         return self.rotation @ self.inv_inertia_body @ self.rotation.T
@@ -101,6 +102,44 @@ class HostRigidBody:
         if np.abs(self.rotation_axis).max() > 0.1:                                             # src/mpm_rigid_body.cpp:256-258
             a = self.rotation_axis / np.linalg.norm(self.rotation_axis)
             self.angular_velocity = a * float(a @ self.angular_velocity)
+
+    # ---- what the solver calls of the core's RigidBody for collisions with the level set (standard rigid-body impulse algebra)
+    def velocity_at(self, p):
+        return self.velocity + np.cross(self.angular_velocity, np.asarray(p, np.float64) - self.position)
+
+    def impulse_contribution(self, r0, n):
+        """Velocity change along n at the contact point per unit impulse along n: 1/m + n . ((I^-1 (r0 x n)) x r0)."""
+        return self.inv_mass + float(np.dot(n, np.cross(self.inv_inertia_world() @ np.cross(r0, n), r0)))
+
+    def apply_impulse(self, j, p):
+        self.velocity = self.velocity + self.inv_mass * np.asarray(j, np.float64)
+        self.angular_velocity = self.angular_velocity + self.inv_inertia_world() @ np.cross(np.asarray(p, np.float64) - self.position, j)
+
+    def levelset_collision(self, sample_world, phi, gradient):
+        """MPM<dim>::rigid_body_levelset_collision for this body (src/mpm_rigid_body.cpp:346-381): every boundary sample inside
+        the level set (phi < 0) takes a normal impulse that removes the approach velocity (restitution e) and a Coulomb friction
+        impulse bounded by frictions[0] times it; the impulses are applied one sample after the other, as the reference loops."""
+        if self.inv_mass == 0.0 and not self.inv_inertia_body.any():
+            return 0
+        hits = 0
+        for p, ph, g in zip(sample_world, phi, gradient):
+            if not ph < 0:
+                continue
+            r0 = p - self.position
+            v0 = float(np.dot(g, self.velocity_at(p)))
+            J = -((1.0 + self.restitution) * v0) / self.impulse_contribution(r0, g)
+            if J < 0:
+                continue
+            self.apply_impulse(J * g, p)
+            v10 = self.velocity_at(p)
+            tao = v10 - g * float(np.dot(g, v10))
+            if np.abs(tao).max() > 1e-7:
+                tao = tao / np.linalg.norm(tao)
+                j = -float(np.dot(v10, tao)) / self.impulse_contribution(r0, tao)
+                j = min(max(j, -self.frictions[0] * J), self.frictions[0] * J)
+                self.apply_impulse(j * tao, p)
+            hits += 1
+        return hits
 
     def advect(self, t, dt, gravity):
         """advect_rigid_bodies for this body (src/mpm_rigid_body.cpp:254-267): axis constraint, advance, gravity impulse."""
