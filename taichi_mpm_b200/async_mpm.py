@@ -15,8 +15,6 @@ import numpy as np
 from . import scenes
 from .mpm import MPM
 
-_FIELDS = ("x", "v", "F", "b", "mass", "vol", "ps", "group", "id")
-
 
 def _morton(bx, by, bz):
     """The scheduler's block order: the page index of SPGrid's linear offset for 32-byte elements in 4 KB pages — bits of the
@@ -100,9 +98,6 @@ class AsyncMPM(MPM):
         X = x.astype(np.float32) * np.float32(1.0 / self.delta_x)
         base = (X - np.float32(0.5)).astype(np.int32)                      # get_grid_base_pos (src/mpm.h:244-247)
         return np.stack([base[:, 0] >> 2, base[:, 1] >> 2, base[:, 2] >> 3], 1)
-
-    def _lvl(self, arr, blk):
-        return arr[blk[:, 0], blk[:, 1], blk[:, 2]]
 
     def add_particles(self, **kwargs):
         """AsyncMPM::add_particles (:60-76): the new particles go to the pool of their block."""
