@@ -78,3 +78,15 @@ def test_host_mirror_kwargs_without_gpu():
     ls.set_friction(0.4)
     pl = ls.planes_grid_units()
     assert pl.shape == (1, 4) and pl[0, 1] == pytest.approx(1.0) and pl[0, 3] == pytest.approx(-6.4)
+
+
+def test_header_is_plain_c(tmp_path):
+    # the drop-in boundary is a C ABI: include/mpmb.h must compile as C99 (and as C++11) on its own, warnings as errors
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "include/mpmb.h"\nint main(void) { MpmbConfig c; MpmbRigidBody r; (void)c; (void)r; return MPMB_VERSION ? 0 : 1; }\n')
+    for cmd in (["gcc", "-std=c99"], ["g++", "-std=c++11", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-Wall", "-Wextra", "-pedantic", "-Werror", "-I", root, "-fsyntax-only", str(src)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
