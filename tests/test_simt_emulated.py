@@ -69,3 +69,25 @@ def test_results_do_not_depend_on_cta_or_thread_scheduling_order(tmp_path, defin
         outs.append(np.load(out))
     for k in outs[0].files:
         assert np.array_equal(outs[0][k], outs[1][k]) and np.array_equal(outs[0][k], outs[2][k]), k
+
+
+_EXAMPLES_SCRIPT = r"""
+import os, sys, importlib.util
+sys.path.insert(0, %r)
+from tests.simt import build_simt
+os.environ["MPMB_LIB"] = build_simt.build()
+for name, args in (("rigid_paddle", (1, 32)), ("async_snow", (1,))):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(%r, "examples", name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    m.main(*args)
+"""
+
+
+def test_example_scripts_run_on_the_emulator():
+    # examples/rigid_paddle.py (a scripted paddle through sand: CPIC) and examples/async_snow.py (the AsyncMPM scheduler)
+    env = dict(os.environ, MPMB_SIMT="1")
+    env.pop("MPMB_LIB", None)
+    r = subprocess.run([sys.executable, "-c", _EXAMPLES_SCRIPT % (ROOT, ROOT)], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "coloured" in r.stdout and "time levels 8..32 units" in r.stdout, r.stdout[-500:]
